@@ -1,0 +1,191 @@
+/* ORACLE (test infrastructure only -- see suews_oracle.h).
+ * Name-keyed C API so tests can fill SoParams/SoState from the reference's own
+ * argument names (as they appear in suews_ctrl_driver.f95:45-91 and in the
+ * *_state_init.txt dumps written by suews_ctrl_translate.f95:1280-1500). */
+#include "suews_oracle.h"
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+
+typedef struct {
+   const char *name;
+   int is_int;
+   size_t off;
+   int n;
+} SoField;
+
+#define PD(f) {#f, 0, offsetof(SoParams, f), (int)(sizeof(((SoParams *)0)->f) / sizeof(double))}
+#define PI(f) {#f, 1, offsetof(SoParams, f), (int)(sizeof(((SoParams *)0)->f) / sizeof(int))}
+static const SoField PARAM_FIELDS[] = {
+   PI(AerodynamicResistanceMethod), PI(BaseTMethod), PI(Diagnose), PI(DiagQN), PI(DiagQS), PI(startDLS), PI(endDLS),
+   PI(EmissionsMethod), PI(Gridiv), PI(gsModel), PI(Ie_end), PI(Ie_start), PI(EvapMethod), PI(LAICalcYes),
+   PI(NetRadiationMethod), PI(OHMIncQF), PI(RoughLenHeatMethod), PI(RoughLenMomMethod), PI(SMDMethod), PI(snowUse),
+   PI(StabilityMethod), PI(StorageHeatMethod), PI(tstep), PI(veg_type), PI(WaterUseMethod), PI(LAIType),
+   PD(AlbMax_DecTr), PD(AlbMax_EveTr), PD(AlbMax_Grass), PD(AlbMin_DecTr), PD(AlbMin_EveTr), PD(AlbMin_Grass),
+   PD(alt), PD(BaseT_HC), PD(bldgH), PD(CapMax_dec), PD(CapMin_dec), PD(CO2PointSource), PD(CRWmax), PD(CRWmin),
+   PD(DecTreeH), PD(DRAINRT), PD(EF_umolCO2perJ), PD(EnEF_v_Jkm), PD(EveTreeH), PD(FAIBldg), PD(FAIDecTree),
+   PD(FAIEveTree), PD(Faut), PD(FlowChange), PD(FrFossilFuel_Heat), PD(FrFossilFuel_NonHeat), PD(G1), PD(G2), PD(G3),
+   PD(G4), PD(G5), PD(G6), PD(H_maintain), PD(InternalWaterUse_h), PD(IrrFracPaved), PD(IrrFracBldgs),
+   PD(IrrFracEveTr), PD(IrrFracDecTr), PD(IrrFracGrass), PD(IrrFracBSoil), PD(IrrFracWater), PD(Kmax), PD(lat),
+   PD(lng), PD(MaxFCMetab), PD(MaxQFMetab), PD(MinFCMetab), PD(MinQFMetab), PD(NARP_EMIS_SNOW), PD(NARP_TRANS_SITE),
+   PD(PipeCapacity), PD(PopDensNighttime), PD(PorMax_dec), PD(PorMin_dec), PD(PrecipLimit), PD(PrecipLimitAlb),
+   PD(RadMeltFact), PD(RAINCOVER), PD(RainMaxRes), PD(RunoffToWater), PD(S1), PD(S2), PD(SnowAlbMax), PD(SnowAlbMin),
+   PD(SnowDensMax), PD(SnowDensMin), PD(SnowLimBldg), PD(SnowLimPaved), PD(SurfaceArea), PD(tau_a), PD(tau_f),
+   PD(tau_r), PD(TempMeltFact), PD(TH), PD(timezone), PD(TL), PD(TrafficUnits), PD(Z), PD(z0m_in), PD(zdm_in),
+   PD(AH_MIN), PD(AH_SLOPE_Cooling), PD(AH_SLOPE_Heating), PD(FcEF_v_kgkm), PD(QF0_BEU), PD(Qf_A), PD(Qf_B), PD(Qf_C),
+   PD(PopDensDaytime), PD(BaseT_Cooling), PD(BaseT_Heating), PD(TrafficRate), PD(Ie_a), PD(Ie_m), PD(MaxConductance),
+   PD(DayWat), PD(DayWatPer), PD(OHM_threshSW), PD(OHM_threshWD), PD(chAnOHM), PD(cpAnOHM), PD(emis), PD(kkAnOHM),
+   PD(SatHydraulicConduct), PD(sfr), PD(SnowPackLimit), PD(SoilDepth), PD(SoilStoreCap), PD(StateLimit),
+   PD(WetThresh), PD(alpha_bioCO2), PD(alpha_enh_bioCO2), PD(BaseT), PD(BaseTe), PD(beta_bioCO2),
+   PD(beta_enh_bioCO2), PD(GDDFull), PD(LAIMax), PD(LAIMin), PD(min_res_bioCO2), PD(resp_a), PD(resp_b), PD(SDDFull),
+   PD(theta_bioCO2), PD(SnowProf_24hr), PD(LAIPower), PD(OHM_coef), PD(WaterDist), PD(AHProf_24hr),
+   PD(HumActivity_24hr), PD(PopProf_24hr), PD(TraffProf_24hr), PD(WUProfA_24hr), PD(WUProfM_24hr),
+};
+#undef PD
+#undef PI
+
+#define SD(f) {#f, 0, offsetof(SoState, f), (int)(sizeof(((SoState *)0)->f) / sizeof(double))}
+#define SI(f) {#f, 1, offsetof(SoState, f), (int)(sizeof(((SoState *)0)->f) / sizeof(int))}
+static const SoField STATE_FIELDS[] = {
+   SD(qn1_av), SD(dqndt), SD(qn1_s_av), SD(dqnsdt), SD(SnowfallCum), SD(SnowAlb), SD(IceFrac), SD(SnowWater),
+   SD(SnowDens), SD(SnowFrac), SD(SnowPack), SD(soilstore_id), SD(state_id), SD(StoreDrainPrm), SD(alb), SD(GDD_id),
+   SD(SDD_id), SD(LAI_id), SD(Tmin_id), SD(Tmax_id), SD(lenDay_id), SD(DecidCap_id), SD(albDecTr_id),
+   SD(albEveTr_id), SD(albGrass_id), SD(porosity_id), SD(HDD_id), SD(WUDay_id), SD(Tair_av), SI(dt_since_start),
+   SI(tstep_prev), SI(lv_switch1), SI(lv_switch2), SD(alb1_hidden),
+};
+#undef SD
+#undef SI
+
+static const SoField *find(const SoField *tab, int ntab, const char *name)
+{
+   int i;
+   for (i = 0; i < ntab; i++)
+      if (strcasecmp(tab[i].name, name) == 0) return &tab[i];
+   return NULL;
+}
+
+static int set_field(void *base, const SoField *fd, const double *vals, int n)
+{
+   int i;
+   if (!fd) return -1;
+   if (n != fd->n) return -2;
+   if (fd->is_int) {
+      int *d = (int *)((char *)base + fd->off);
+      for (i = 0; i < n; i++) d[i] = (int)vals[i];
+   } else {
+      double *d = (double *)((char *)base + fd->off);
+      for (i = 0; i < n; i++) d[i] = vals[i];
+   }
+   return 0;
+}
+
+static int get_field(const void *base, const SoField *fd, double *vals, int n)
+{
+   int i;
+   if (!fd) return -1;
+   if (n != fd->n) return -2;
+   if (fd->is_int) {
+      const int *d = (const int *)((const char *)base + fd->off);
+      for (i = 0; i < n; i++) vals[i] = d[i];
+   } else {
+      const double *d = (const double *)((const char *)base + fd->off);
+      for (i = 0; i < n; i++) vals[i] = d[i];
+   }
+   return 0;
+}
+
+#define NPF ((int)(sizeof(PARAM_FIELDS) / sizeof(PARAM_FIELDS[0])))
+#define NSF ((int)(sizeof(STATE_FIELDS) / sizeof(STATE_FIELDS[0])))
+
+SoParams *so_params_new(void) { return (SoParams *)calloc(1, sizeof(SoParams)); }
+SoState *so_state_new(void) { return (SoState *)calloc(1, sizeof(SoState)); }
+void so_free(void *p) { free(p); }
+void so_state_copy(SoState *dst, const SoState *src) { *dst = *src; }
+
+int so_params_nfields(void) { return NPF; }
+int so_state_nfields(void) { return NSF; }
+const char *so_params_field(int i, int *is_int, int *n)
+{
+   if (i < 0 || i >= NPF) return NULL;
+   *is_int = PARAM_FIELDS[i].is_int;
+   *n = PARAM_FIELDS[i].n;
+   return PARAM_FIELDS[i].name;
+}
+const char *so_state_field(int i, int *is_int, int *n)
+{
+   if (i < 0 || i >= NSF) return NULL;
+   *is_int = STATE_FIELDS[i].is_int;
+   *n = STATE_FIELDS[i].n;
+   return STATE_FIELDS[i].name;
+}
+int so_params_set(SoParams *p, const char *name, const double *vals, int n)
+{
+   return set_field(p, find(PARAM_FIELDS, NPF, name), vals, n);
+}
+int so_params_get(const SoParams *p, const char *name, double *vals, int n)
+{
+   return get_field(p, find(PARAM_FIELDS, NPF, name), vals, n);
+}
+int so_state_set(SoState *s, const char *name, const double *vals, int n)
+{
+   return set_field(s, find(STATE_FIELDS, NSF, name), vals, n);
+}
+int so_state_get(const SoState *s, const char *name, double *vals, int n)
+{
+   return get_field(s, find(STATE_FIELDS, NSF, name), vals, n);
+}
+
+/* Run len_sim steps for one cell.  Returns the first fatal ErrorHint code (0 = ok). */
+int so_run(const SoParams *p, SoState *st, const double *met, int len_sim, double *blkSUEWS, double *blkSnow,
+           double *blkESTM, double *blkRSL, double *blkSOL, double *blkDaily, char *msg, int msglen,
+           long *warn_count128, int *n_iter_last)
+{
+   SoCtx cx;
+   int i;
+   so_ctx_init(&cx);
+   so_cal_multitsteps(&cx, p, st, met, len_sim, blkSUEWS, blkSnow, blkESTM, blkRSL, blkSOL, blkDaily);
+   if (msg && msglen > 0) {
+      strncpy(msg, cx.fatal_msg, (size_t)msglen - 1);
+      msg[msglen - 1] = 0;
+   }
+   if (warn_count128)
+      for (i = 0; i < 128; i++) warn_count128[i] = cx.warn_count[i];
+   if (n_iter_last) *n_iter_last = cx.n_iter_last;
+   return cx.fatal_code;
+}
+
+/* Many independent cells, each with its own params/state; shared or per-cell forcing.
+ * P0-style reduction for the CPU baseline: per-cell sums of the SUEWS line over the run.
+ * met_stride = 0 -> all cells share one forcing block. */
+int so_run_cells(int ncell, const SoParams *params, SoState *states, const double *met, long met_stride, int len_sim,
+                 double *sum_suews /* [ncell x NCOL_SUEWS] or NULL */)
+{
+   int c, ir, k, rc = 0;
+   for (c = 0; c < ncell; c++) {
+      SoCtx cx;
+      SoForcing f;
+      SoOutLines out;
+      const double *m = met + (size_t)c * (size_t)met_stride;
+      so_ctx_init(&cx);
+      if (sum_suews)
+         for (k = 0; k < NCOL_SUEWS; k++) sum_suews[(size_t)c * NCOL_SUEWS + k] = 0;
+      for (ir = 0; ir < len_sim; ir++) {
+#define MET(col) m[(size_t)ir + (size_t)len_sim * (col)]
+         f.iy = (int)MET(0); f.id = (int)MET(1); f.it = (int)MET(2); f.imin = (int)MET(3); f.isec = 0;
+         f.qn1_obs = MET(4); f.qs_obs = MET(7); f.qf_obs = MET(8); f.avU1 = MET(9); f.avRh = MET(10);
+         f.Temp_C = MET(11); f.Press_hPa = MET(12); f.Precip = MET(13); f.avkdn = MET(14); f.snowFrac_obs = MET(15);
+         f.ldown_obs = MET(16); f.fcld_obs = MET(17); f.wu_m3 = MET(18); f.xsmd = MET(19); f.LAI_obs = MET(20);
+#undef MET
+         so_cal_main(&cx, &params[c], &f, &states[c], &out);
+         states[c].dt_since_start += params[c].tstep;
+         if (sum_suews)
+            for (k = 0; k < NCOL_SUEWS; k++) sum_suews[(size_t)c * NCOL_SUEWS + k] += out.SUEWS[k];
+         if (cx.fatal_code) { rc = cx.fatal_code; break; }
+      }
+   }
+   return rc;
+}
+
+size_t so_sizeof_params(void) { return sizeof(SoParams); }
+size_t so_sizeof_state(void) { return sizeof(SoState); }

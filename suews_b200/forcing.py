@@ -1,0 +1,163 @@
+"""Met-forcing preparation: the step immediately before the hot path.
+
+Host-side (numpy, float64) restatement of the reference's forcing reader and
+hourly -> model-timestep disaggregation:
+
+* ``read_met``           MetRead, SUEWS-SourceCode/suews_ctrl_input.f95:13-135
+                         (kPa -> hPa :109, xsmd = -999 when SMDMethod == 0 :96-102)
+* ``disaggregate_met``   DisaggregateMet :1380-1640 with
+  ``_disagg_datetime``   DisaggregateDateTime :1849-1900
+  ``_disagg_lin``        Disagg_Lin :1908-2011 (type 10 period averages, type 20 instantaneous)
+  ``_disagg_p_among_n``  DisaggP_amongN :2016-2068 (RainDisaggMethod = 100: even spread)
+
+Output is the [len_sim, 24] ``MetForcingBlock`` consumed by ``suews_cal_multitsteps``
+(column order suews_ctrl_driver.f95:3177-3201).  Arithmetic order follows the
+reference expression by expression so that the result is bit-identical to the
+in-memory array the Fortran binary uses (its text dump only keeps 4-6 decimals).
+"""
+import numpy as np
+
+NCOL_MET = 24
+
+
+def read_met(path, smd_method=0):
+    """Read an original-resolution SUEWS met file (InputMetFormat = 10)."""
+    rows = []
+    with open(path) as fh:
+        fh.readline()
+        for ln in fh:
+            t = ln.split()
+            if len(t) < NCOL_MET or t[0].startswith("-9"):
+                continue
+            rows.append([float(x) for x in t[:NCOL_MET]])
+    a = np.array(rows, dtype=np.float64)
+    a[:, 12] = a[:, 12] * 10.0  # Pres_hPa = Pres_kPa*10.
+    if smd_method == 0:
+        a[:, 19] = -999.0
+    return a
+
+
+def _days_in_year(y):
+    y = np.asarray(y)
+    return np.where(((y % 4 == 0) & (y % 100 != 0)) | (y % 400 == 0), 366, 365)
+
+
+def _nint(x):
+    return np.where(x >= 0, np.floor(x + 0.5), -np.floor(-x + 0.5)).astype(np.int64)
+
+
+def _disagg_datetime(dt4, tstep, nper):
+    n = dt4.shape[0]
+    out = np.zeros((n * nper, 4))
+    # 24.0 and 60.0*24.0 are REAL(4) constants (exact); tstep/60.0 is a REAL(4) quotient
+    dectime_orig = (dt4[:, 1] - 1) + dt4[:, 2] / 24.0 + dt4[:, 3] / (60.0 * 24.0)
+    step = np.float64(np.float32(np.float32(tstep) / np.float32(60.0)) / np.float32(60.0 * 24.0))
+    seq = np.arange(nper - 1, -1, -1)
+    for i in range(n):
+        # (tstep/60.0)/(60.0*24.0)*ii is evaluated in REAL(4) (integer ii promoted), then widened
+        off = (np.float32(step) * seq.astype(np.float32)).astype(np.float64)
+        td = dectime_orig[i] - off
+        # NINT(x*60*60*24)/(60*60*24*1.): integer / REAL(4) -> REAL(4) quotient
+        td = (_nint(td * 60 * 60 * 24).astype(np.float32) / np.float32(86400.0)).astype(np.float64)
+        iy = np.where(td < 0, int(dt4[i, 0]) - 1, int(dt4[i, 0]))
+        nd = _days_in_year(iy)
+        td = np.where(td < 0, td + nd, td)
+        idd = np.floor(td).astype(np.int64) + 1
+        ihm = _nint((td + 1 - idd / 1.0) * 60.0 * 24.0)
+        ih = (ihm - ihm % 60) // 60
+        ih = np.where(ih < 24, ih, 0)
+        im = ihm % 60
+        sl = slice(nper * i, nper * (i + 1))
+        out[sl, 0], out[sl, 1], out[sl, 2], out[sl, 3] = iy, idd, ih, im
+    return out
+
+
+def _disagg_lin(slow, slow_prev, slow_next, dtype, nper, first_block=True, last_block=True):
+    n = slow.shape[0]
+    fast = np.full(n * nper, -999.0)
+    xn = 2 if nper % 2 == 0 else 1
+    seq = np.arange(1, nper + 1)
+    half = int(np.floor(nper / 2.0))
+    if dtype == 10:
+        rows = half + seq  # 1-based
+        for i in range(n - 1):
+            d = slow[i + 1] - slow[i]
+            fast[nper * i + rows - 1] = slow[i] - d / (xn * nper) + d / nper * seq
+        nfirst = rows[0] - 1
+        if first_block:
+            fast[:nfirst] = fast[rows[0] - 1]
+        else:
+            d = slow[0] - slow_prev
+            ii = np.arange(nper - nfirst + 1, nper + 1)
+            fast[:nfirst] = slow_prev - d / (xn * nper) + d / nper * ii
+        last_start = nper * (n - 2) + rows[-1]  # 0-based index of first unfilled row
+        nlast = n * nper - last_start
+        if last_block:
+            fast[last_start:] = fast[last_start - 1]
+        else:
+            d = slow_next - slow[n - 1]
+            fast[last_start:] = slow[n - 1] - d / (xn * nper) + d / nper * np.arange(1, nlast + 1)
+    elif dtype == 20:
+        rows = nper + seq
+        for i in range(n - 1):
+            d = slow[i + 1] - slow[i]
+            fast[nper * i + rows - 1] = (slow[i] + d / nper * 2 * (seq - 1) + slow[i]) / 2
+        nfirst = rows[0] - 1
+        if first_block:
+            fast[:nfirst] = fast[rows[0] - 1]
+        else:
+            d = slow[0] - slow_prev
+            ii = np.arange(nper - nfirst + 1, nper + 1)
+            fast[:nfirst] = (slow_prev + d / nper * 2 * (ii - 1) + slow_prev) / 2
+    else:
+        raise ValueError("DisaggType must be 10 or 20")
+    if np.any(fast == -999.0):
+        raise RuntimeError("Problem in SUEWS_MetDisagg: -999 values in disaggregated data.")  # ErrorHint 13
+    return fast
+
+
+def _disagg_p_among_n(slow, among_n, nper):
+    if among_n != nper:
+        raise NotImplementedError("RainDisaggMethod 101/102 draw unseeded random sub-intervals in the reference")
+    fast = np.zeros(slow.shape[0] * nper)
+    for i in range(slow.shape[0]):
+        if slow[i] > 0:
+            fast[nper * i:nper * (i + 1)] = slow[i] / among_n
+    return fast
+
+
+def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, rain_disagg_method=100,
+                     first_block=True, last_block=True, prev_row=None, next_row=None):
+    """Disaggregate an original-resolution met block (already passed through ``read_met``)."""
+    met_orig = np.asarray(met_orig, dtype=np.float64)
+    nper = resolution_in // tstep
+    n = met_orig.shape[0]
+    method = np.full(NCOL_MET, 10)
+    if disagg_method == 2:
+        method[:] = 20
+    elif disagg_method == 3:
+        method[9:13] = 20
+    elif disagg_method != 1:
+        raise ValueError("DisaggMethod value should be 1, 2, or 3")  # ErrorHint 2
+    if rain_disagg_method != 100:
+        raise NotImplementedError("only RainDisaggMethod=100 is deterministic in the reference")
+    out = np.full((n * nper, NCOL_MET), -999.0)
+    out[:, 0:4] = _disagg_datetime(met_orig[:, 0:4], tstep, nper)
+    for c in range(4, NCOL_MET):
+        if c == 13:
+            out[:, 13] = _disagg_p_among_n(met_orig[:, 13], nper, nper)
+            if np.all(met_orig[:, 15] == -999):
+                out[:, 15] = -999.0
+            else:
+                out[:, 15] = _disagg_p_among_n(met_orig[:, 15], nper, nper)
+        elif c == 23:
+            continue  # wind direction: not disaggregated by the reference
+        elif np.all(met_orig[:, c] == -999):
+            out[:, c] = -999.0
+        else:
+            sp = prev_row[c] if prev_row is not None else -999.0
+            sn = next_row[c] if next_row is not None else -999.0
+            out[:, c] = _disagg_lin(met_orig[:, c], sp, sn, method[c], nper, first_block, last_block)
+    if np.all(out[:, 15] == -999):
+        out[:, 15] = 0.0
+    return out

@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Build tests/golden/ from the reference's own BaseRun fixtures.
+
+Run in the authoring container only (needs /root/reference); outputs are small
+and committed.  Nothing here is reference *code*: only its test data.
+
+  state_init_{2004,2005}.json   the complete SUEWS_cal_Main argument dump at the first
+                                step (Test/BaseRun/2020b/Output/test1_*_state_init.txt,
+                                written by suews_ctrl_translate.f95:1280-1500)
+  forcing_2005_5min.txt         Test/BaseRun/2019a/Input/test_2005_data_5.txt (1440 rows)
+  forcing_2005_60min.txt        Test/BaseRun/2020b/Input/test_2005_data_60.txt (119 rows)
+  forcing_2004_60min.txt        Test/BaseRun/2020b/Input/test_2004_data_60.txt.long (8784 rows)
+  ref_2005_{SUEWS,snow,RSL}_60.txt, ref_2005_DailyState.txt, ref_2004_DailyState.txt
+                                the reference's golden outputs (hourly, 4-6 decimals)
+"""
+import json, os, re, shutil
+
+REF = "/root/reference/Test/BaseRun"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def parse_state_init(path):
+    d = {}
+    for ln in open(path):
+        ln = ln.strip()
+        if not ln or ln.startswith("&") or ln == "/":
+            continue
+        m = re.match(r"^(\w+)\s*=\s*(.*)$", ln)
+        if not m:
+            continue
+        key = m.group(1).lower()
+        vals = []
+        for tok in m.group(2).replace(",", " ").split():
+            mm = re.match(r"^(\d+)\*(.*)$", tok)  # Fortran repeat count r*c
+            if mm:
+                vals += [mm.group(2)] * int(mm.group(1))
+            else:
+                vals.append(tok)
+        out = []
+        for v in vals:
+            if re.fullmatch(r"[-+]?\d+", v):
+                out.append(int(v))
+            else:
+                out.append(float(v.replace("D", "E").replace("d", "e")))
+        d[key] = out
+    return d
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for yr in (2004, 2005):
+        d = parse_state_init(f"{REF}/2020b/Output/test1_{yr}_state_init.txt")
+        with open(os.path.join(OUT, f"state_init_{yr}.json"), "w") as fh:
+            json.dump(d, fh, indent=0, sort_keys=True)
+        print(yr, len(d), "entries")
+    cp = [
+        ("2019a/Input/test_2005_data_5.txt", "forcing_2005_5min.txt"),
+        ("2020b/Input/test_2005_data_60.txt", "forcing_2005_60min.txt"),
+        ("2020b/Input/test_2004_data_60.txt.long", "forcing_2004_60min.txt"),
+        ("2020b/Output/test1_2005_SUEWS_60.txt", "ref_2005_SUEWS_60.txt"),
+        ("2020b/Output/test1_2005_snow_60.txt", "ref_2005_snow_60.txt"),
+        ("2020b/Output/test1_2005_RSL_60.txt", "ref_2005_RSL_60.txt"),
+        ("2020b/Output/test1_2005_DailyState.txt", "ref_2005_DailyState.txt"),
+        ("2020b/Output/test1_2004_DailyState.txt", "ref_2004_DailyState.txt"),
+    ]
+    for src, dst in cp:
+        shutil.copyfile(f"{REF}/{src}", os.path.join(OUT, dst))
+        os.chmod(os.path.join(OUT, dst), 0o644)
+    print("golden files in", OUT)
+
+
+if __name__ == "__main__":
+    main()
