@@ -1,0 +1,121 @@
+/*
+ * suews_b200.h -- C ABI of libsuews_b200.so: the B200-native SUEWS per-grid-cell timestep physics.
+ *
+ * Drop-in boundary for the reference's hot path:
+ *
+ *   suews_cal_multitsteps_c   replaces SUEWS_Driver::SUEWS_cal_multitsteps
+ *                             (SUEWS-SourceCode/suews_ctrl_driver.f95:2814-3505), what
+ *                             supy_driver.suews_driver.suews_cal_multitsteps binds through f2py
+ *                             (supy-driver/setup.py:29-50);
+ *   suews_cal_main_c          replaces SUEWS_Driver::SUEWS_cal_Main (driver.f95:45-1045), called by
+ *                             SUEWS_Calculations (suews_ctrl_calculations.f95:127) and SuMin
+ *                             (suews_ctrl_sumin.f95:543);
+ *   suews_cal_sunposition_c   replaces SUEWS_cal_sunposition (driver.f95:3508);
+ *   suews_output_name_n / suews_output_size   replace output_name_n / output_size (driver.f95:2778-2812);
+ *   suews_last_error          replaces the ErrorHint -> problems.txt -> STOP convention
+ *                             (suews_ctrl_error.f95:392-415; supy-driver/nonstopf2py.py:54-60).
+ *
+ * plus the batched device API the reference has no counterpart for (its hosts loop cells serially,
+ * suews_program.f95:606-623): many cells resident in HBM, advanced many timesteps per launch.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; all reals are double, all integers
+ * 32-bit int; arrays are Fortran (column-major) ordered exactly as the reference declares them
+ * (driver.f95:226-343); every function returns 0 on success or a SUEWS error code (the ErrorHint
+ * number of the first fatal condition, or a SUEWS_E_* value).  Nothing here aborts the process.
+ * The library needs a CUDA device: there is no CPU fallback (SUEWS_E_NO_DEVICE).
+ */
+#ifndef SUEWS_B200_H
+#define SUEWS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct suews_b200_handle_s *suews_b200_handle;
+
+enum {
+   SUEWS_OK = 0,
+   SUEWS_E_NO_DEVICE = 2001,   /* no CUDA device / CUDA runtime failure (message in suews_last_error) */
+   SUEWS_E_BAD_NAME = 2002,    /* unknown parameter/state name */
+   SUEWS_E_BAD_SIZE = 2003,    /* value count does not match the field */
+   SUEWS_E_BAD_ARG = 2004,
+   SUEWS_E_NOT_IMPL = 1003     /* scheme outside this library (AnOHM, ESTM): see suews_last_error */
+};
+
+/* output policy bits for suews_b200_advance */
+enum {
+   SUEWS_OUT_SUM82 = 1,   /* accumulate per-cell sums of the 82 SUEWS columns over the advanced steps */
+   SUEWS_OUT_FULL = 2     /* keep every output block of every step (reference SUEWS_cal_multitsteps semantics) */
+};
+
+/* ---- batched device API -------------------------------------------------------------------- */
+int suews_b200_device_count(void);
+int suews_b200_create(int ncell, int nclass, int device, suews_b200_handle *out);
+int suews_b200_destroy(suews_b200_handle h);
+
+/* Parameters by reference argument name (case-insensitive; driver.f95:45-91).  Integer-typed
+ * arguments are passed as doubles holding integral values.  Class fields: one class at a time.
+ * Cell fields and state: vals is [ncell][n] (cell-major).  suews_b200_field_info reports where a
+ * name lives: kind 0 = class int, 1 = class double, 2 = per-cell double, 3 = state; returns n or -1. */
+int suews_b200_field_info(const char *name, int *kind);
+int suews_b200_set_class_param(suews_b200_handle h, int cls, const char *name, const double *vals, int n);
+int suews_b200_set_cell_param(suews_b200_handle h, const char *name, const double *vals, int n);
+int suews_b200_set_cell_class(suews_b200_handle h, const int *class_of_cell);
+int suews_b200_set_state(suews_b200_handle h, const char *name, const double *vals, int n);
+int suews_b200_get_state(suews_b200_handle h, const char *name, double *vals, int n);
+int suews_b200_set_clock(suews_b200_handle h, int dt_since_start, int tstep_prev);
+int suews_b200_get_clock(suews_b200_handle h, int *dt_since_start, int *tstep_prev);
+
+/* Push parameters + state to HBM (SoA).  Call after the setters, before advancing. */
+int suews_b200_upload(suews_b200_handle h);
+
+/* Forcing shared by all cells: MetForcingBlock [nsteps x 24], column-major, columns as in
+ * driver.f95:3177-3201 (pressure already in hPa).  Copies host -> device and builds the per-step
+ * clock/ephemeris records on the device. */
+int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps);
+
+/* Advance all cells over forcing rows [step0, step0 + nsteps).  One kernel launch.  Asynchronous
+ * with respect to the host; suews_b200_sync waits and returns the first fatal cell error (0 if none). */
+int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags);
+int suews_b200_sync(suews_b200_handle h);
+
+/* Results.  sums: [ncell][82] (cell-major).  Full blocks (after SUEWS_OUT_FULL): per cell a
+ * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50 columns). */
+int suews_b200_get_sums(suews_b200_handle h, double *sums);
+int suews_b200_reset_sums(suews_b200_handle h);
+int suews_b200_get_block(suews_b200_handle h, const char *group /* "SUEWS","snow","RSL","DailyState" */, int cell,
+                         double *block, int nsteps, int ncol);
+int suews_b200_get_diag(suews_b200_handle h, int *fatal_code_per_cell, unsigned long long *warn_mask2_per_cell,
+                        long long *tsurf_iterations_per_cell);
+/* device time (ms) of the last advance, measured with CUDA events on the library's stream */
+int suews_b200_last_advance_ms(suews_b200_handle h, float *ms);
+/* raw device pointers for callers that keep forcing / results on the GPU (bench, multi-GPU hosts) */
+int suews_b200_device_ptrs(suews_b200_handle h, void **d_state, void **d_sums, long long *cell_stride);
+
+/* ---- reference-shaped entry points --------------------------------------------------------- */
+/* Same positional argument list as the Fortran (all by pointer, arrays column-major).  The argument
+ * tables live in suews_b200/csrc/suews_refargs.inc; see INTEGRATION.md for the f2py/ctypes/ISO_C_BINDING
+ * stubs.  Both run one cell on the device through the batched path. */
+int suews_cal_multitsteps_c(const double *MetForcingBlock, int len_sim, const void *const *args_in_order,
+                            double *dataOutBlockSUEWS, double *dataOutBlockSnow, double *dataOutBlockESTM,
+                            double *dataOutBlockRSL, double *dataOutBlockSOL, double *DailyStateBlock);
+int suews_cal_main_c(const void *const *args_in_order, double *datetimeLine, double *dataOutLineSUEWS,
+                     double *dataOutLineSnow, double *dataOutLineESTM, double *dataoutLineRSL,
+                     double *dataOutLineSOLWEIG, double *DailyStateLine);
+/* names of the arguments expected in args_in_order, in order; returns the count */
+int suews_cal_multitsteps_argnames(const char *const **names);
+int suews_cal_main_argnames(const char *const **names);
+
+int suews_cal_sunposition_c(double year, double idectime, double UTC, double locationlatitude,
+                            double locationlongitude, double locationaltitude, double *sunazimuth,
+                            double *sunzenith);
+int suews_output_size(int *nVar);
+int suews_output_name_n(int i, char name[16], char group[16], char aggreg[16], int *outlevel);
+
+/* last error of the calling thread: code and human-readable message */
+int suews_last_error(int *code, char *buf, int len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,70 @@
+"""ctypes binding of libsuews_b200.so (include/suews_b200.h).  No PyTorch, no CPU fallback:
+if the CUDA library is missing or no device is present this fails loudly."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsuews_b200.so")
+
+_lib = None
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class SuewsError(RuntimeError):
+    """Raised where the reference would STOP 'Fatal error in SUEWS!' (suews_ctrl_error.f95:392-415;
+    supy_driver turns that STOP into a RuntimeError, supy-driver/nonstopf2py.py:54-60)."""
+
+    def __init__(self, code, msg):
+        super().__init__("SUEWS error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "suews_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C suews_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        H = C.c_void_p
+        L.suews_b200_device_count.restype = C.c_int
+        L.suews_b200_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+        L.suews_b200_destroy.argtypes = [H]
+        L.suews_b200_field_info.argtypes = [C.c_char_p, ip]
+        L.suews_b200_set_class_param.argtypes = [H, C.c_int, C.c_char_p, dp, C.c_int]
+        L.suews_b200_set_cell_param.argtypes = [H, C.c_char_p, dp, C.c_int]
+        L.suews_b200_set_cell_class.argtypes = [H, ip]
+        L.suews_b200_set_state.argtypes = [H, C.c_char_p, dp, C.c_int]
+        L.suews_b200_get_state.argtypes = [H, C.c_char_p, dp, C.c_int]
+        L.suews_b200_set_clock.argtypes = [H, C.c_int, C.c_int]
+        L.suews_b200_get_clock.argtypes = [H, ip, ip]
+        L.suews_b200_upload.argtypes = [H]
+        L.suews_b200_set_forcing.argtypes = [H, dp, C.c_int]
+        L.suews_b200_advance.argtypes = [H, C.c_int, C.c_int, C.c_int]
+        L.suews_b200_sync.argtypes = [H]
+        L.suews_b200_get_sums.argtypes = [H, dp]
+        L.suews_b200_reset_sums.argtypes = [H]
+        L.suews_b200_get_block.argtypes = [H, C.c_char_p, C.c_int, dp, C.c_int, C.c_int]
+        L.suews_b200_get_diag.argtypes = [H, ip, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
+        L.suews_b200_last_advance_ms.argtypes = [H, C.POINTER(C.c_float)]
+        L.suews_b200_device_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+        L.suews_cal_sunposition_c.argtypes = [C.c_double] * 6 + [dp, dp]
+        L.suews_last_error.argtypes = [ip, C.c_char_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def last_error():
+    code = C.c_int()
+    buf = C.create_string_buffer(256)
+    lib().suews_last_error(C.byref(code), buf, 256)
+    return code.value, buf.value.decode(errors="replace")
+
+
+def check(rc):
+    if rc != 0:
+        code, msg = last_error()
+        raise SuewsError(rc if rc else code, msg)

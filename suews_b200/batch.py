@@ -1,0 +1,179 @@
+"""SuewsBatch: many grid cells resident on one B200, advanced many timesteps per launch.
+
+Host-side mirror of the batched C ABI (include/suews_b200.h).  Parameters are given with the
+reference's own argument names (SUEWS_cal_Main, suews_ctrl_driver.f95:45-91): class-level values
+per class, site values and state per cell.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, dp, ip
+
+NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50}
+OUT_SUM82 = 1
+OUT_FULL = 2
+
+KIND_CLASS_INT, KIND_CLASS_DBL, KIND_CELL, KIND_STATE = 0, 1, 2, 3
+
+
+def field_info(name):
+    kind = C.c_int()
+    n = _lib.lib().suews_b200_field_info(name.encode(), C.byref(kind))
+    if n < 0:
+        return None
+    return kind.value, n
+
+
+def _arr(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+class SuewsBatch:
+    def __init__(self, ncell, nclass=1, device=0):
+        self.L = _lib.lib()
+        self.ncell, self.nclass, self.device = int(ncell), int(nclass), int(device)
+        self.h = C.c_void_p()
+        check(self.L.suews_b200_create(self.ncell, self.nclass, self.device, C.byref(self.h)))
+        self.nsteps = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.suews_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters
+    def set_class_param(self, cls, name, vals):
+        a = _arr(np.atleast_1d(vals)).ravel()
+        check(self.L.suews_b200_set_class_param(self.h, int(cls), name.encode(), a.ctypes.data_as(dp), a.size))
+
+    def set_cell_param(self, name, vals):
+        """vals: scalar / [n] (broadcast to all cells) or [ncell, n]."""
+        kind, n = field_info(name)
+        a = _arr(vals)
+        if a.ndim <= 1 and a.size == n:
+            a = np.broadcast_to(a.reshape(1, n), (self.ncell, n))
+        a = _arr(a).reshape(self.ncell, n)
+        check(self.L.suews_b200_set_cell_param(self.h, name.encode(), a.ctypes.data_as(dp), n))
+
+    def set_state(self, name, vals):
+        kind, n = field_info(name)
+        a = _arr(vals)
+        if a.ndim <= 1 and a.size == n:
+            a = np.broadcast_to(a.reshape(1, n), (self.ncell, n))
+        a = _arr(a).reshape(self.ncell, n)
+        check(self.L.suews_b200_set_state(self.h, name.encode(), a.ctypes.data_as(dp), n))
+
+    def get_state(self, name):
+        kind, n = field_info(name)
+        a = np.zeros((self.ncell, n))
+        check(self.L.suews_b200_get_state(self.h, name.encode(), a.ctypes.data_as(dp), n))
+        return a
+
+    def set_cell_class(self, ids):
+        a = np.ascontiguousarray(np.asarray(ids, dtype=np.int32))
+        assert a.size == self.ncell
+        check(self.L.suews_b200_set_cell_class(self.h, a.ctypes.data_as(ip)))
+
+    def set_clock(self, dt_since_start, tstep_prev):
+        check(self.L.suews_b200_set_clock(self.h, int(dt_since_start), int(tstep_prev)))
+
+    def get_clock(self):
+        a, b = C.c_int(), C.c_int()
+        check(self.L.suews_b200_get_clock(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def load_reference_args(self, values, cls=0, cells=True):
+        """Fill class `cls` (and, if cells, every cell's site values + state) from a dict keyed by the
+        reference's argument names (e.g. a parsed *_state_init.txt dump).  Returns names not found."""
+        low = {k.lower(): v for k, v in values.items()}
+        missing = []
+        for name, kind, n in all_fields():
+            key = name.lower()
+            if key not in low:
+                if name not in ("dTemp_C", "dRH", "alb1_hidden", "lv_switch"):
+                    missing.append(name)
+                continue
+            v = np.atleast_1d(np.asarray(low[key], dtype=np.float64)).ravel()
+            assert v.size == n, (name, v.size, n)
+            if kind in (KIND_CLASS_INT, KIND_CLASS_DBL):
+                self.set_class_param(cls, name, v)
+            elif cells and kind == KIND_CELL:
+                self.set_cell_param(name, v)
+            elif cells and kind == KIND_STATE:
+                self.set_state(name, v)
+        if "dt_since_start" in low:
+            self.set_clock(int(low["dt_since_start"][0]), int(low.get("tstep_prev", low.get("tstep"))[0]))
+        return missing
+
+    # ---- run
+    def upload(self):
+        check(self.L.suews_b200_upload(self.h))
+
+    def set_forcing(self, met):
+        """met: [nsteps, 24] MetForcingBlock (driver.f95:3177-3201), pressure in hPa."""
+        m = np.asfortranarray(np.asarray(met, dtype=np.float64))
+        assert m.shape[1] == 24
+        check(self.L.suews_b200_set_forcing(self.h, m.ctypes.data_as(dp), m.shape[0]))
+        self.nsteps = m.shape[0]
+
+    def advance(self, step0, nsteps, out_flags=OUT_SUM82, sync=True):
+        check(self.L.suews_b200_advance(self.h, int(step0), int(nsteps), int(out_flags)))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        check(self.L.suews_b200_sync(self.h))
+
+    def last_ms(self):
+        ms = C.c_float()
+        check(self.L.suews_b200_last_advance_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def sums(self):
+        a = np.zeros((self.ncell, 82))
+        check(self.L.suews_b200_get_sums(self.h, a.ctypes.data_as(dp)))
+        return a
+
+    def reset_sums(self):
+        check(self.L.suews_b200_reset_sums(self.h))
+
+    def block(self, group, cell, nsteps):
+        b = np.zeros((nsteps, NCOL[group]), order="F")
+        check(self.L.suews_b200_get_block(self.h, group.encode(), int(cell), b.ctypes.data_as(dp), nsteps, NCOL[group]))
+        return b
+
+    def diag(self):
+        fatal = np.zeros(self.ncell, dtype=np.int32)
+        warn = np.zeros((self.ncell, 2), dtype=np.uint64)
+        iters = np.zeros(self.ncell, dtype=np.int64)
+        check(self.L.suews_b200_get_diag(self.h, fatal.ctypes.data_as(ip), warn.ctypes.data_as(C.POINTER(C.c_ulonglong)),
+                                         iters.ctypes.data_as(C.POINTER(C.c_longlong))))
+        return fatal, warn, iters
+
+
+_FIELDS = None
+
+
+def all_fields():
+    """[(name, kind, n)] for every parameter/state field the library knows (from suews_fields.h)."""
+    global _FIELDS
+    if _FIELDS is None:
+        import os
+        import re
+        hdr = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "suews_fields.h")).read()
+        out = []
+        for macro, kind in (("SUEWS_CLASS_INT_FIELDS", 0), ("SUEWS_CLASS_DBL_FIELDS", 1), ("SUEWS_CELL_DBL_FIELDS", 2),
+                            ("SUEWS_STATE_DBL_FIELDS", 3)):
+            m = re.search(r"#define %s\(X\)(.*?)\n\n" % macro, hdr, re.S)
+            for nm, n in re.findall(r"X\((\w+),\s*(\d+)\)", m.group(1)):
+                out.append((nm, kind, int(n)))
+        _FIELDS = out
+    return _FIELDS

@@ -1,0 +1,778 @@
+// suews_b200.cu -- kernels and C ABI of libsuews_b200.so (sm_100a).
+//
+// Data layout in HBM:
+//   classes   SuewsClassParams[nclass]            AoS, broadcast reads (cells are grouped by class)
+//   cellp     double[SUEWS_N_CELL_DBL][stride]    SoA, coalesced
+//   state     double[SUEWS_N_STATE_DBL][stride]   SoA, coalesced; loaded once per launch into the thread
+//   steps     SuewsStepRec[nsteps]                clock + forcing, shared by all cells; staged into shared
+//                                                 memory in chunks by cp.async.bulk (TMA) + mbarrier
+//   ephem     SuewsEphem[ntz][nsteps]             time-only half of the solar position, one thread / step
+//   sums      double[82][stride]                  per-cell running sums of the SUEWS output line
+// One thread owns one cell and advances it through all requested timesteps of a launch.
+#include "suews_fields.h"
+#include "dev_step.cuh"
+#include "../../include/suews_b200.h"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <strings.h>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+#define SU_BLOCK 128
+#define SU_CHUNK 32   // timesteps staged per bulk copy (32 x 160 B = 5 KB)
+
+struct SuRunArgs {
+   const SuewsClassParams *classes;
+   const int *class_of_cell;
+   const int *tz_of_cell;
+   const double *cellp;
+   double *state;
+   const SuewsStepRec *steps;   // already offset to step0
+   const SuewsEphem *ephem;     // [ntz][nsteps_total], offset to step0 inside
+   long long ephem_tz_stride;
+   double *sums;                // [82][stride] or NULL
+   int *fatal;                  // [ncell]
+   unsigned long long *warn;    // [2][stride]
+   long long *iters;            // [ncell]
+   // full output (SUEWS_OUT_FULL): per cell column-major [nsteps x ncol]
+   double *blkSUEWS, *blkSnow, *blkRSL, *blkDaily;
+   int ncell;
+   long long stride;
+   int nsteps;
+   int dt_since_start, tstep_prev, tstep;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+// Time-only half of the solar position + nothing else: one thread per (time zone, step).
+__global__ void suews_ephem_kernel(const SuewsStepRec *steps, int nsteps, const double *tz_list, int ntz, int tstep,
+                                   SuewsEphem *ephem)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nsteps * ntz) return;
+   int s = i % nsteps, z = i / nsteps;
+   // dectime [days] minus the INTEGER tstep/2 [seconds], exactly as the reference call (driver.f95:689)
+   spa_time_part((double)steps[s].iy, steps[s].dectime - (double)(tstep / 2), tz_list[z], ephem[(size_t)z * nsteps + s]);
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(SU_BLOCK) suews_run_kernel(SuRunArgs a)
+{
+   __shared__ alignas(128) SuewsStepRec sm_steps[2][SU_CHUNK];
+   __shared__ alignas(8) uint64_t sm_bar[2];
+
+   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool active = cell < a.ncell;
+   const int nchunk = (a.nsteps + SU_CHUNK - 1) / SU_CHUNK;
+
+   if (threadIdx.x == 0) {
+      mbar_init(&sm_bar[0], 1);
+      mbar_init(&sm_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   if (threadIdx.x == 0 && nchunk > 0) {
+      uint32_t n0 = (uint32_t)min(SU_CHUNK, a.nsteps) * (uint32_t)sizeof(SuewsStepRec);
+      mbar_expect_tx(&sm_bar[0], n0);
+      bulk_g2s(&sm_steps[0][0], a.steps, n0, &sm_bar[0]);
+   }
+
+   // ---- per-thread residents: cell parameters, state, accumulators
+   SuewsCellParams C;
+   SuewsCellState S;
+   SuDiag dg;
+   dg.fatal = 0; dg.warn[0] = 0; dg.warn[1] = 0;
+   double acc[SUEWS_NCOL_SUEWS];
+   long long iters = 0;
+   int cls = 0, tz = 0;
+   if (active) {
+      cls = a.class_of_cell[cell];
+      tz = a.tz_of_cell[cell];
+      double *cp = reinterpret_cast<double *>(&C);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_CELL_DBL; j++) cp[j] = a.cellp[(size_t)j * a.stride + cell];
+      double *sp = reinterpret_cast<double *>(&S);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) sp[j] = a.state[(size_t)j * a.stride + cell];
+      dg.fatal = a.fatal[cell];
+      dg.warn[0] = a.warn[cell];
+      dg.warn[1] = a.warn[a.stride + cell];
+      if (a.sums) {
+#pragma unroll 1
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = a.sums[(size_t)c * a.stride + cell];
+      }
+   }
+   const SuewsClassParams &P = a.classes[cls];
+   const SuewsEphem *eph = a.ephem + (size_t)tz * a.ephem_tz_stride;
+   int dt_since_start = a.dt_since_start;
+   int tstep_prev = a.tstep_prev;
+
+   for (int ch = 0; ch < nchunk; ch++) {
+      const int buf = ch & 1;
+      // prefetch the next chunk into the other buffer (its readers finished at the previous barrier)
+      if (threadIdx.x == 0 && ch + 1 < nchunk) {
+         int s1 = (ch + 1) * SU_CHUNK;
+         uint32_t n1 = (uint32_t)min(SU_CHUNK, a.nsteps - s1) * (uint32_t)sizeof(SuewsStepRec);
+         mbar_expect_tx(&sm_bar[buf ^ 1], n1);
+         bulk_g2s(&sm_steps[buf ^ 1][0], a.steps + s1, n1, &sm_bar[buf ^ 1]);
+      }
+      mbar_wait(&sm_bar[buf], (uint32_t)((ch >> 1) & 1));
+      const int s0 = ch * SU_CHUNK;
+      const int ns = min(SU_CHUNK, a.nsteps - s0);
+      if (active) {
+         for (int t = 0; t < ns; t++) {
+            if (dg.fatal == 0) {
+               const int gs = s0 + t;
+               SuLines L;
+               L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr;
+               double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY];
+               if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; }
+               iters += suews_step(dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
+                                   a.sums ? acc : nullptr, L);
+               if (FULL) {
+                  const size_t n = (size_t)a.nsteps;
+                  double *b;
+                  b = a.blkSUEWS + (size_t)cell * n * (SUEWS_NCOL_SUEWS + 5);
+                  for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+                  for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) b[gs + n * (5 + c)] = l_su[c];
+                  b = a.blkRSL + (size_t)cell * n * (SUEWS_NCOL_RSL + 5);
+                  for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+                  for (int c = 0; c < SUEWS_NCOL_RSL; c++) b[gs + n * (5 + c)] = l_rs[c];
+                  b = a.blkDaily + (size_t)cell * n * (SUEWS_NCOL_DAILY + 5);
+                  for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+                  for (int c = 0; c < SUEWS_NCOL_DAILY; c++) b[gs + n * (5 + c)] = l_da[c];
+                  if (P.snowUse == 1) {   // SUEWS_update_output, driver.f95:2499-2501 (with set_nan :2737)
+                     b = a.blkSnow + (size_t)cell * n * (SUEWS_NCOL_SNOW + 5);
+                     for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+                     for (int c = 0; c < SUEWS_NCOL_SNOW; c++) b[gs + n * (5 + c)] = (fabs(l_sn[c]) > 30000) ? -999.0 : l_sn[c];
+                  }
+               }
+            }
+            dt_since_start += a.tstep;   // caller-side clock, driver.f95:3483
+            tstep_prev = a.tstep;
+         }
+      }
+      __syncthreads();   // everyone is done with buffer `buf` before it is refilled two chunks later
+   }
+
+   if (active) {
+      double *sp = reinterpret_cast<double *>(&S);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + cell] = sp[j];
+      a.fatal[cell] = dg.fatal;
+      a.warn[cell] = dg.warn[0];
+      a.warn[a.stride + cell] = dg.warn[1];
+      a.iters[cell] += iters;
+      if (a.sums) {
+#pragma unroll 1
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) a.sums[(size_t)c * a.stride + cell] = acc[c];
+      }
+   }
+}
+
+__global__ void suews_sunpos_kernel(double year, double idectime, double UTC, double lat, double lng, double alt, double *out)
+{
+   SuewsEphem e;
+   spa_time_part(year, idectime, UTC, e);
+   double az, zen;
+   spa_location_part(e, lat, lng, alt, az, zen);
+   out[0] = az;
+   out[1] = zen;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct FieldDesc {
+   const char *name;
+   int kind;     // 0 class int, 1 class double, 2 cell double, 3 state double
+   size_t off;   // element offset inside its group
+   int n;
+};
+
+static std::vector<FieldDesc> build_fields()
+{
+   std::vector<FieldDesc> v;
+   size_t o;
+#define ADD(kind_) [&](const char *nm, int n) { v.push_back({nm, kind_, o, n}); o += (size_t)n; }
+   {
+      o = 0;
+      auto add = ADD(0);
+#define X(name, n) add(#name, n);
+      SUEWS_CLASS_INT_FIELDS(X)
+#undef X
+   }
+   {
+      o = 0;
+      auto add = ADD(1);
+#define X(name, n) add(#name, n);
+      SUEWS_CLASS_DBL_FIELDS(X)
+#undef X
+   }
+   {
+      o = 0;
+      auto add = ADD(2);
+#define X(name, n) add(#name, n);
+      SUEWS_CELL_DBL_FIELDS(X)
+#undef X
+   }
+   {
+      o = 0;
+      auto add = ADD(3);
+#define X(name, n) add(#name, n);
+      SUEWS_STATE_DBL_FIELDS(X)
+#undef X
+   }
+#undef ADD
+   return v;
+}
+static const std::vector<FieldDesc> &fields()
+{
+   static std::vector<FieldDesc> f = build_fields();
+   return f;
+}
+static const FieldDesc *find_field(const char *name)
+{
+   for (const auto &f : fields())
+      if (strcasecmp(f.name, name) == 0) return &f;
+   return nullptr;
+}
+
+static thread_local int tl_err_code = 0;
+static thread_local char tl_err_msg[256] = "";
+static int set_err(int code, const char *fmt, ...)
+{
+   tl_err_code = code;
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(tl_err_msg, sizeof(tl_err_msg), fmt, ap);
+   va_end(ap);
+   return code;
+}
+#define CUDA_OK(call)                                                                                       \
+   do {                                                                                                     \
+      cudaError_t e_ = (call);                                                                              \
+      if (e_ != cudaSuccess) return set_err(SUEWS_E_NO_DEVICE, "CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+   } while (0)
+
+static const char *fatal_text(int code)
+{
+   switch (code) {
+   case 14: return "In SUEWS_cal_RoughnessParameters, z0 / zd / (z-zd) < 0 m.";
+   case 17: return "In stability subroutine, (z-zd) < z0.";
+   case 21: return "In SUEWS_OHM.f95: bad value for qn1 found during qs calculation.";
+   case 32: return "Windspeed Ht too low relative to zdm [Stability calc]";
+   case 62: return "SUEWS_store / SUEWS_Calculations: soil store out of range";
+   case 71: return "Value of gsModel not recognised.";
+   case 73: return "RunControl.nml:EmissionsMethod unusable";
+   case 75: return "RunControl.nml: BaseTMethod / TrafficUnits not usable";
+   case 1001: return "NetRadiationMethod: Value not usable";
+   case 1003: return "StorageHeatMethod 3 (AnOHM) / 4 (ESTM) are not part of this library";
+   case 1004: return "EmissionsMethod >= 11 (biogenic CO2) is not part of this library yet";
+   default: return "Fatal error in SUEWS!";
+   }
+}
+
+struct suews_b200_handle_s {
+   int device = 0, ncell = 0, nclass = 0;
+   long long stride = 0;
+   std::vector<SuewsClassParams> classes;
+   std::vector<double> cellp, state;   // SoA [field][stride]
+   std::vector<int> cls_of_cell, tz_of_cell;
+   std::vector<double> tz_list;
+   int dt_since_start = 0, tstep_prev = 0, tstep = 0;
+   int nsteps = 0;
+   bool uploaded = false;
+   // device
+   SuewsClassParams *d_classes = nullptr;
+   int *d_cls = nullptr, *d_tz = nullptr, *d_fatal = nullptr;
+   double *d_cellp = nullptr, *d_state = nullptr, *d_sums = nullptr, *d_tzlist = nullptr;
+   unsigned long long *d_warn = nullptr;
+   long long *d_iters = nullptr;
+   SuewsStepRec *d_steps = nullptr;
+   SuewsEphem *d_ephem = nullptr;
+   double *d_blk[4] = {nullptr, nullptr, nullptr, nullptr};
+   int blk_nsteps = 0;
+   cudaStream_t stream = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   int first_fatal_code = 0, first_fatal_cell = -1;
+};
+
+template <typename T> static cudaError_t dev_alloc(T **p, size_t n)
+{
+   if (*p) { cudaFree(*p); *p = nullptr; }
+   return cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
+}
+
+extern "C" {
+
+int suews_last_error(int *code, char *buf, int len)
+{
+   if (code) *code = tl_err_code;
+   if (buf && len > 0) {
+      strncpy(buf, tl_err_msg, (size_t)len - 1);
+      buf[len - 1] = 0;
+   }
+   return tl_err_code;
+}
+
+int suews_b200_device_count(void)
+{
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+   return n;
+}
+
+int suews_b200_field_info(const char *name, int *kind)
+{
+   const FieldDesc *f = find_field(name);
+   if (!f) return -1;
+   if (kind) *kind = f->kind;
+   return f->n;
+}
+
+int suews_b200_create(int ncell, int nclass, int device, suews_b200_handle *out)
+{
+   if (!out || ncell <= 0 || nclass <= 0) return set_err(SUEWS_E_BAD_ARG, "create: bad ncell/nclass");
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0)
+      return set_err(SUEWS_E_NO_DEVICE, "libsuews_b200 needs a CUDA device (no CPU fallback): %s",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "no device found");
+   if (device < 0 || device >= ndev) return set_err(SUEWS_E_BAD_ARG, "create: device %d of %d", device, ndev);
+   CUDA_OK(cudaSetDevice(device));
+   auto *h = new suews_b200_handle_s();
+   h->device = device;
+   h->ncell = ncell;
+   h->nclass = nclass;
+   h->stride = ((long long)ncell + 31) / 32 * 32;
+   h->classes.assign((size_t)nclass, SuewsClassParams());
+   memset(h->classes.data(), 0, sizeof(SuewsClassParams) * (size_t)nclass);
+   h->cellp.assign((size_t)SUEWS_N_CELL_DBL * h->stride, 0.0);
+   h->state.assign((size_t)SUEWS_N_STATE_DBL * h->stride, 0.0);
+   h->cls_of_cell.assign((size_t)ncell, 0);
+   h->tz_of_cell.assign((size_t)ncell, 0);
+   if (cudaStreamCreate(&h->stream) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
+       cudaEventCreate(&h->ev1) != cudaSuccess) {
+      delete h;
+      return set_err(SUEWS_E_NO_DEVICE, "CUDA stream/event creation failed");
+   }
+   *out = h;
+   return SUEWS_OK;
+}
+
+static void free_dev(suews_b200_handle h)
+{
+   cudaSetDevice(h->device);
+   cudaFree(h->d_classes); cudaFree(h->d_cls); cudaFree(h->d_tz); cudaFree(h->d_fatal); cudaFree(h->d_cellp);
+   cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
+   cudaFree(h->d_steps); cudaFree(h->d_ephem);
+   for (int i = 0; i < 4; i++) cudaFree(h->d_blk[i]);
+}
+
+int suews_b200_destroy(suews_b200_handle h)
+{
+   if (!h) return SUEWS_OK;
+   free_dev(h);
+   if (h->stream) cudaStreamDestroy(h->stream);
+   if (h->ev0) cudaEventDestroy(h->ev0);
+   if (h->ev1) cudaEventDestroy(h->ev1);
+   delete h;
+   return SUEWS_OK;
+}
+
+int suews_b200_set_class_param(suews_b200_handle h, int cls, const char *name, const double *vals, int n)
+{
+   if (!h || cls < 0 || cls >= h->nclass) return set_err(SUEWS_E_BAD_ARG, "set_class_param: bad class %d", cls);
+   const FieldDesc *f = find_field(name);
+   if (!f || f->kind > 1) return set_err(SUEWS_E_BAD_NAME, "set_class_param: '%s' is not a class field", name);
+   if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "set_class_param: '%s' has %d values, got %d", name, f->n, n);
+   SuewsClassParams &P = h->classes[(size_t)cls];
+   if (f->kind == 0) {
+      int *base = reinterpret_cast<int *>(&P);
+      for (int i = 0; i < n; i++) base[f->off + i] = (int)vals[i];
+   } else {
+      double *base = reinterpret_cast<double *>(&P.AlbMax_DecTr);
+      for (int i = 0; i < n; i++) base[f->off + i] = vals[i];
+   }
+   h->uploaded = false;
+   return SUEWS_OK;
+}
+
+static int set_soa(std::vector<double> &soa, long long stride, int ncell, const FieldDesc *f, const double *vals)
+{
+   for (int k = 0; k < f->n; k++) {
+      double *dst = &soa[(f->off + (size_t)k) * (size_t)stride];
+      for (int c = 0; c < ncell; c++) dst[c] = vals[(size_t)c * f->n + k];
+   }
+   return SUEWS_OK;
+}
+
+int suews_b200_set_cell_param(suews_b200_handle h, const char *name, const double *vals, int n)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   const FieldDesc *f = find_field(name);
+   if (!f || f->kind != 2) return set_err(SUEWS_E_BAD_NAME, "set_cell_param: '%s' is not a per-cell field", name);
+   if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "set_cell_param: '%s' has %d values per cell, got %d", name, f->n, n);
+   h->uploaded = false;
+   return set_soa(h->cellp, h->stride, h->ncell, f, vals);
+}
+
+int suews_b200_set_cell_class(suews_b200_handle h, const int *class_of_cell)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   for (int c = 0; c < h->ncell; c++) {
+      if (class_of_cell[c] < 0 || class_of_cell[c] >= h->nclass)
+         return set_err(SUEWS_E_BAD_ARG, "set_cell_class: cell %d has class %d of %d", c, class_of_cell[c], h->nclass);
+      h->cls_of_cell[(size_t)c] = class_of_cell[c];
+   }
+   h->uploaded = false;
+   return SUEWS_OK;
+}
+
+int suews_b200_set_state(suews_b200_handle h, const char *name, const double *vals, int n)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   const FieldDesc *f = find_field(name);
+   if (!f || f->kind != 3) return set_err(SUEWS_E_BAD_NAME, "set_state: '%s' is not a state field", name);
+   if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "set_state: '%s' has %d values per cell, got %d", name, f->n, n);
+   h->uploaded = false;
+   return set_soa(h->state, h->stride, h->ncell, f, vals);
+}
+
+int suews_b200_get_state(suews_b200_handle h, const char *name, double *vals, int n)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   const FieldDesc *f = find_field(name);
+   if (!f || f->kind != 3) return set_err(SUEWS_E_BAD_NAME, "get_state: '%s' is not a state field", name);
+   if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "get_state: '%s' has %d values per cell, got %d", name, f->n, n);
+   if (h->uploaded) {
+      CUDA_OK(cudaSetDevice(h->device));
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      CUDA_OK(cudaMemcpy(&h->state[f->off * (size_t)h->stride], h->d_state + f->off * (size_t)h->stride,
+                         sizeof(double) * (size_t)f->n * (size_t)h->stride, cudaMemcpyDeviceToHost));
+   }
+   for (int k = 0; k < f->n; k++) {
+      const double *src = &h->state[(f->off + (size_t)k) * (size_t)h->stride];
+      for (int c = 0; c < h->ncell; c++) vals[(size_t)c * f->n + k] = src[c];
+   }
+   return SUEWS_OK;
+}
+
+int suews_b200_set_clock(suews_b200_handle h, int dt_since_start, int tstep_prev)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   h->dt_since_start = dt_since_start;
+   h->tstep_prev = tstep_prev;
+   return SUEWS_OK;
+}
+int suews_b200_get_clock(suews_b200_handle h, int *dt_since_start, int *tstep_prev)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   if (dt_since_start) *dt_since_start = h->dt_since_start;
+   if (tstep_prev) *tstep_prev = h->tstep_prev;
+   return SUEWS_OK;
+}
+
+int suews_b200_upload(suews_b200_handle h)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   CUDA_OK(cudaSetDevice(h->device));
+   // derived class constants: sequential 24-term sums of the diurnal profiles (ctrl_input.f95:784,816)
+   h->tstep = h->classes[0].tstep;
+   for (auto &P : h->classes) {
+      const double *prof[6] = {P.AHProf_24hr.v, P.HumActivity_24hr.v, P.PopProf_24hr.v,
+                               P.TraffProf_24hr.v, P.WUProfA_24hr.v, P.WUProfM_24hr.v};
+      for (int k = 0; k < 6; k++)
+         for (int u = 0; u < 2; u++) {
+            double s = 0;
+            for (int i = 0; i < 24; i++) s += prof[k][24 * u + i];
+            P.prof_sum[k][u] = s;
+         }
+      if (P.tstep != h->tstep || P.tstep <= 0)
+         return set_err(SUEWS_E_BAD_ARG, "upload: all classes must share one positive tstep (got %d and %d)", h->tstep, (int)P.tstep);
+   }
+   // distinct time zones -> ephemeris index per cell
+   h->tz_list.clear();
+   const FieldDesc *ftz = find_field("timezone");
+   for (int c = 0; c < h->ncell; c++) {
+      double tz = h->cellp[ftz->off * (size_t)h->stride + c];
+      int idx = -1;
+      for (size_t k = 0; k < h->tz_list.size(); k++)
+         if (h->tz_list[k] == tz) { idx = (int)k; break; }
+      if (idx < 0) { idx = (int)h->tz_list.size(); h->tz_list.push_back(tz); }
+      h->tz_of_cell[(size_t)c] = idx;
+   }
+   const size_t st = (size_t)h->stride;
+   CUDA_OK(dev_alloc(&h->d_classes, (size_t)h->nclass));
+   CUDA_OK(dev_alloc(&h->d_cls, st));
+   CUDA_OK(dev_alloc(&h->d_tz, st));
+   CUDA_OK(dev_alloc(&h->d_fatal, st));
+   CUDA_OK(dev_alloc(&h->d_cellp, (size_t)SUEWS_N_CELL_DBL * st));
+   CUDA_OK(dev_alloc(&h->d_state, (size_t)SUEWS_N_STATE_DBL * st));
+   CUDA_OK(dev_alloc(&h->d_sums, (size_t)SUEWS_NCOL_SUEWS * st));
+   CUDA_OK(dev_alloc(&h->d_warn, 2 * st));
+   CUDA_OK(dev_alloc(&h->d_iters, st));
+   CUDA_OK(dev_alloc(&h->d_tzlist, h->tz_list.size()));
+   CUDA_OK(cudaMemcpy(h->d_classes, h->classes.data(), sizeof(SuewsClassParams) * (size_t)h->nclass, cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemcpy(h->d_cls, h->cls_of_cell.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemcpy(h->d_tz, h->tz_of_cell.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemcpy(h->d_cellp, h->cellp.data(), sizeof(double) * h->cellp.size(), cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemcpy(h->d_state, h->state.data(), sizeof(double) * h->state.size(), cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemcpy(h->d_tzlist, h->tz_list.data(), sizeof(double) * h->tz_list.size(), cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemset(h->d_sums, 0, sizeof(double) * (size_t)SUEWS_NCOL_SUEWS * st));
+   CUDA_OK(cudaMemset(h->d_fatal, 0, sizeof(int) * st));
+   CUDA_OK(cudaMemset(h->d_warn, 0, sizeof(unsigned long long) * 2 * st));
+   CUDA_OK(cudaMemset(h->d_iters, 0, sizeof(long long) * st));
+   h->uploaded = true;
+   h->first_fatal_code = 0;
+   h->first_fatal_cell = -1;
+   return SUEWS_OK;
+}
+
+// host-side clock decode of one forcing row (SUEWS_cal_dectime util_time.f95:270, SUEWS_cal_weekday :301)
+static void decode_clock(SuewsStepRec &r)
+{
+   r.dectime = (double)(r.id - 1) + (double)r.it / 24 + (double)r.imin / (60 * 24) + (double)0 / (60 * 60 * 24);
+   int year = r.iy, b = r.id, k, mb, md;
+   auto fmod_ = [](int a, int p) { int m = a % p; if (m != 0 && ((m < 0) != (p < 0))) m += p; return m; };
+   k = ((fmod_(year, 4) == 0 && fmod_(year, 100) != 0) || fmod_(year, 400) == 0) ? 1 : 0;
+   if (b <= 31) { mb = 1; md = b; }
+   else if (b <= 59 + k) { mb = 2; md = b - 31; }
+   else if (b <= 90 + k) { mb = 3; md = b - (59 + k); }
+   else if (b <= 120 + k) { mb = 4; md = b - (90 + k); }
+   else if (b <= 151 + k) { mb = 5; md = b - (120 + k); }
+   else if (b <= 181 + k) { mb = 6; md = b - (151 + k); }
+   else if (b <= 212 + k) { mb = 7; md = b - (181 + k); }
+   else if (b <= 243 + k) { mb = 8; md = b - (212 + k); }
+   else if (b <= 273 + k) { mb = 9; md = b - (243 + k); }
+   else if (b <= 304 + k) { mb = 10; md = b - (273 + k); }
+   else if (b <= 334 + k) { mb = 11; md = b - (304 + k); }
+   else { mb = 12; md = b - (334 + k); }
+   int yr = year, mn = mb;
+   if (!(mn > 2)) { mn += 12; yr -= 1; }
+   int n1 = (26 * (mn + 1)) / 10, n2 = (125 * yr) / 100;
+   int day = (md + n1 + n2 - (yr / 100) + (yr / 400) - 1);
+   r.dow = day % 7 + 1;
+   r.month = mb;
+   r.pad0_ = 0;
+   r.pad1_ = 0;
+}
+
+int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
+{
+   if (!h || !met || nsteps <= 0) return set_err(SUEWS_E_BAD_ARG, "set_forcing: bad arguments");
+   if (!h->uploaded) {
+      int rc = suews_b200_upload(h);
+      if (rc) return rc;
+   }
+   CUDA_OK(cudaSetDevice(h->device));
+   std::vector<SuewsStepRec> recs((size_t)nsteps);
+   const size_t n = (size_t)nsteps;
+#define MET(col) met[(size_t)i + n * (col)]
+   for (int i = 0; i < nsteps; i++) {   // driver.f95:3177-3201
+      SuewsStepRec &r = recs[(size_t)i];
+      r.iy = (int)MET(0); r.id = (int)MET(1); r.it = (int)MET(2); r.imin = (int)MET(3);
+      r.qn1_obs = MET(4); r.qs_obs = MET(7); r.qf_obs = MET(8); r.avU1 = MET(9); r.avRh = MET(10); r.Temp_C = MET(11);
+      r.Press_hPa = MET(12); r.Precip = MET(13); r.avkdn = MET(14); r.snowFrac_obs = MET(15); r.ldown_obs = MET(16);
+      r.fcld_obs = MET(17); r.wu_m3 = MET(18); r.xsmd = MET(19); r.LAI_obs = MET(20);
+      decode_clock(r);
+   }
+#undef MET
+   CUDA_OK(dev_alloc(&h->d_steps, n));
+   CUDA_OK(dev_alloc(&h->d_ephem, n * h->tz_list.size()));
+   CUDA_OK(cudaMemcpyAsync(h->d_steps, recs.data(), sizeof(SuewsStepRec) * n, cudaMemcpyHostToDevice, h->stream));
+   int total = nsteps * (int)h->tz_list.size();
+   suews_ephem_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_steps, nsteps, h->d_tzlist, (int)h->tz_list.size(),
+                                                                 h->tstep, h->d_ephem);
+   CUDA_OK(cudaGetLastError());
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   h->nsteps = nsteps;
+   return SUEWS_OK;
+}
+
+int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags)
+{
+   if (!h || !h->uploaded || !h->d_steps) return set_err(SUEWS_E_BAD_ARG, "advance: upload parameters and forcing first");
+   if (step0 < 0 || nsteps <= 0 || step0 + nsteps > h->nsteps)
+      return set_err(SUEWS_E_BAD_ARG, "advance: rows [%d,%d) outside the %d forcing rows", step0, step0 + nsteps, h->nsteps);
+   CUDA_OK(cudaSetDevice(h->device));
+   const bool full = (out_flags & SUEWS_OUT_FULL) != 0;
+   if (full) {
+      const int ncol[4] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5};
+      for (int i = 0; i < 4; i++) {
+         size_t cnt = (size_t)h->ncell * (size_t)nsteps * (size_t)ncol[i];
+         CUDA_OK(dev_alloc(&h->d_blk[i], cnt));
+         // unwritten rows (snow block when snowUse = 0) are left unassigned by the reference; -999 here
+         std::vector<double> fill(cnt, -999.0);
+         CUDA_OK(cudaMemcpy(h->d_blk[i], fill.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice));
+      }
+      h->blk_nsteps = nsteps;
+   }
+   SuRunArgs a;
+   a.classes = h->d_classes; a.class_of_cell = h->d_cls; a.tz_of_cell = h->d_tz; a.cellp = h->d_cellp; a.state = h->d_state;
+   a.steps = h->d_steps + step0;
+   a.ephem = h->d_ephem + step0;
+   a.ephem_tz_stride = h->nsteps;
+   a.sums = (out_flags & SUEWS_OUT_SUM82) ? h->d_sums : nullptr;
+   a.fatal = h->d_fatal; a.warn = h->d_warn; a.iters = h->d_iters;
+   a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3];
+   a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
+   a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;
+   const int grid = (h->ncell + SU_BLOCK - 1) / SU_BLOCK;
+   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+   if (full) suews_run_kernel<true><<<grid, SU_BLOCK, 0, h->stream>>>(a);
+   else suews_run_kernel<false><<<grid, SU_BLOCK, 0, h->stream>>>(a);
+   CUDA_OK(cudaGetLastError());
+   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+   h->dt_since_start += nsteps * h->tstep;
+   h->tstep_prev = h->tstep;
+   return SUEWS_OK;
+}
+
+int suews_b200_sync(suews_b200_handle h)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   std::vector<int> fatal((size_t)h->ncell);
+   CUDA_OK(cudaMemcpy(fatal.data(), h->d_fatal, sizeof(int) * (size_t)h->ncell, cudaMemcpyDeviceToHost));
+   for (int c = 0; c < h->ncell; c++)
+      if (fatal[(size_t)c] != 0) {
+         h->first_fatal_code = fatal[(size_t)c];
+         h->first_fatal_cell = c;
+         return set_err(fatal[(size_t)c], "Fatal error in SUEWS! code %d in cell %d: %s", fatal[(size_t)c], c, fatal_text(fatal[(size_t)c]));
+      }
+   return SUEWS_OK;
+}
+
+int suews_b200_last_advance_ms(suews_b200_handle h, float *ms)
+{
+   if (!h || !ms) return set_err(SUEWS_E_BAD_ARG, "null argument");
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaEventSynchronize(h->ev1));
+   CUDA_OK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+   return SUEWS_OK;
+}
+
+int suews_b200_get_sums(suews_b200_handle h, double *sums)
+{
+   if (!h || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "get_sums: nothing uploaded");
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   std::vector<double> tmp((size_t)SUEWS_NCOL_SUEWS * (size_t)h->stride);
+   CUDA_OK(cudaMemcpy(tmp.data(), h->d_sums, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+   for (int c = 0; c < h->ncell; c++)
+      for (int k = 0; k < SUEWS_NCOL_SUEWS; k++) sums[(size_t)c * SUEWS_NCOL_SUEWS + k] = tmp[(size_t)k * h->stride + c];
+   return SUEWS_OK;
+}
+
+int suews_b200_reset_sums(suews_b200_handle h)
+{
+   if (!h || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "reset_sums: nothing uploaded");
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaMemsetAsync(h->d_sums, 0, sizeof(double) * (size_t)SUEWS_NCOL_SUEWS * (size_t)h->stride, h->stream));
+   return SUEWS_OK;
+}
+
+int suews_b200_get_block(suews_b200_handle h, const char *group, int cell, double *block, int nsteps, int ncol)
+{
+   if (!h || !group || !block) return set_err(SUEWS_E_BAD_ARG, "null argument");
+   const char *names[4] = {"SUEWS", "snow", "RSL", "DailyState"};
+   const int ncols[4] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5};
+   int g = -1;
+   for (int i = 0; i < 4; i++)
+      if (strcasecmp(group, names[i]) == 0) g = i;
+   if (g < 0) return set_err(SUEWS_E_BAD_NAME, "get_block: unknown group '%s'", group);
+   if (!h->d_blk[g] || nsteps != h->blk_nsteps || ncol != ncols[g] || cell < 0 || cell >= h->ncell)
+      return set_err(SUEWS_E_BAD_SIZE, "get_block: %s block is [%d x %d] per cell", names[g], h->blk_nsteps, ncols[g]);
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   size_t cnt = (size_t)nsteps * (size_t)ncol;
+   CUDA_OK(cudaMemcpy(block, h->d_blk[g] + (size_t)cell * cnt, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+   return SUEWS_OK;
+}
+
+int suews_b200_get_diag(suews_b200_handle h, int *fatal, unsigned long long *warn2, long long *iters)
+{
+   if (!h || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "get_diag: nothing uploaded");
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   if (fatal) CUDA_OK(cudaMemcpy(fatal, h->d_fatal, sizeof(int) * (size_t)h->ncell, cudaMemcpyDeviceToHost));
+   if (iters) CUDA_OK(cudaMemcpy(iters, h->d_iters, sizeof(long long) * (size_t)h->ncell, cudaMemcpyDeviceToHost));
+   if (warn2) {
+      std::vector<unsigned long long> tmp(2 * (size_t)h->stride);
+      CUDA_OK(cudaMemcpy(tmp.data(), h->d_warn, sizeof(unsigned long long) * tmp.size(), cudaMemcpyDeviceToHost));
+      for (int c = 0; c < h->ncell; c++) {
+         warn2[2 * (size_t)c] = tmp[(size_t)c];
+         warn2[2 * (size_t)c + 1] = tmp[(size_t)h->stride + c];
+      }
+   }
+   return SUEWS_OK;
+}
+
+int suews_b200_device_ptrs(suews_b200_handle h, void **d_state, void **d_sums, long long *cell_stride)
+{
+   if (!h || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "device_ptrs: nothing uploaded");
+   if (d_state) *d_state = h->d_state;
+   if (d_sums) *d_sums = h->d_sums;
+   if (cell_stride) *cell_stride = h->stride;
+   return SUEWS_OK;
+}
+
+int suews_cal_sunposition_c(double year, double idectime, double UTC, double lat, double lng, double alt, double *az,
+                            double *zen)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return set_err(SUEWS_E_NO_DEVICE, "libsuews_b200 needs a CUDA device (no CPU fallback)");
+   double *d = nullptr, hbuf[2];
+   CUDA_OK(cudaMalloc((void **)&d, 2 * sizeof(double)));
+   suews_sunpos_kernel<<<1, 1>>>(year, idectime, UTC, lat, lng, alt, d);
+   cudaError_t e = cudaMemcpy(hbuf, d, sizeof(hbuf), cudaMemcpyDeviceToHost);
+   cudaFree(d);
+   CUDA_OK(e);
+   if (az) *az = hbuf[0];
+   if (zen) *zen = hbuf[1];
+   return SUEWS_OK;
+}
+
+}   // extern "C"
