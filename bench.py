@@ -1,0 +1,294 @@
+#!/usr/bin/env python3
+"""bench.py -- cell-timesteps/s of the SUEWS per-grid-cell timestep physics on B200.
+
+Workload (BASELINE.json configs[2]): synthetic 1 048 576 cells per GPU, BaseRun cell with per-cell
+surface fractions / location / morphology / forcing offsets, default scheme set
+(NetRadiationMethod 3, OHM, LUMPS first guess, StabilityMethod 3, snow off), forcing = the reference's
+2004 hourly series disaggregated to 5 min.  One bench "step" advances every cell by one day
+(288 timesteps) in ONE kernel launch; consecutive steps are consecutive days.
+
+  value  whole-job cell-timesteps/s with forcing + state resident in HBM (CUDA-event time of the
+         kernel launches, max over ranks)
+  e2e    the same through the public host API with host buffers: per step the day's forcing goes
+         host -> device and the per-cell running sums of the 7 parity fluxes come back device -> host
+  --impl reference   the CPU oracle (a C port of the Fortran: no Fortran compiler exists in this
+         image) on all host cores, one process per core, bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "cell_timesteps_per_s"
+UNIT = "cell-timesteps/s"
+PARITY_COLS = [5, 6, 7, 8, 9, 16, 71]  # QN QF QS QH QE RO SWE (0-based in the 82-column line)
+N_STATE, N_CELL, N_SUM = 208, 46, 82
+
+
+def load_inputs(ndays, day0=0):
+    import fixtures as fx
+    base = fx.state_init(2005)
+    from suews_b200.forcing import disaggregate_met, read_met
+    hourly = read_met(os.path.join(fx.GOLDEN, "forcing_2004_60min.txt"))
+    nh = min(hourly.shape[0], (day0 + ndays) * 24 + 48)
+    met = disaggregate_met(hourly[:nh], last_block=(nh == hourly.shape[0]), next_row=hourly[min(nh, hourly.shape[0] - 1)])
+    # the 5-min series starts at 00:05; a day = 288 rows
+    return base, met[day0 * 288:(day0 + ndays) * 288]
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx = gpu_index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle)
+def _cpu_worker(args):
+    worker, budget_s, max_cells, scheme = args
+    import fixtures as fx
+    import oracle_lib as ol
+    from suews_b200 import synth
+    base, met = load_inputs(1)
+    d = synth.base_with_scheme(base, scheme)
+    site = synth.cell_site_arrays(worker * max_cells, max_cells, d)
+    t0 = time.perf_counter()
+    done = 0
+    for c in range(max_cells):
+        dd = dict(d)
+        for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
+            dd[k.lower()] = np.atleast_1d(site[k][c])
+        cell = ol.Cell(dd)
+        m = met.copy()
+        m[:, 11] += site["dTemp_C"][c]
+        m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + site["dRH"][c]))
+        cell.run(m, want=())
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0
+
+
+def cpu_arm(budget_s, scheme, cores=None):
+    import multiprocessing as mp
+    import oracle_lib as ol
+    ol.build()
+    cores = cores or os.cpu_count() or 1
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(w, budget_s, 4096, scheme) for w in range(cores)])
+        wall = time.perf_counter() - t0
+    cells = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return cells * 288 / slowest, cores, cells, slowest, wall
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells-per-gpu", type=int, default=1048576)
+    ap.add_argument("--scheme", default="default")
+    ap.add_argument("--cpu-budget", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    K, W = a.steps, max(a.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = "synthetic %d cells/GPU x 288 five-minute steps per bench step, %s schemes, shared 2004 forcing + per-cell dT/dRH" % (
+        a.cells_per_gpu, a.scheme)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        rates, info = [], None
+        for i in range(W + K):
+            r, cores, cells, slowest, wall = cpu_arm(max(2.0, a.cpu_budget / 2), a.scheme)
+            if i >= W:
+                rates.append((cells * 288, slowest))
+            info = (cores, cells)
+        tot_cs = sum(x[0] for x in rates)
+        tot_t = sum(x[1] for x in rates)
+        val = tot_cs / tot_t
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * tot_t / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "sample": "%d cells x 288 steps per step over %d host processes" % (info[1], info[0])},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": info[0], "kind": "port",
+                             "sample": "%d cells x 288 steps per step; CPU oracle (C port of the Fortran; no Fortran compiler in the image)" % info[1]},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from suews_b200 import OUT_SUM82, SuewsBatch, synth
+    from suews_b200 import _lib
+    from suews_b200.batch import all_fields
+    global N_STATE, N_CELL
+    N_STATE = sum(n for _nm, kind, n in all_fields() if kind == 3)
+    N_CELL = sum(n for _nm, kind, n in all_fields() if kind == 2)
+
+    ndays = 2 * (W + K)
+    base, met = load_inputs(ndays)
+    ncell = a.cells_per_gpu
+    b = SuewsBatch(ncell, 1, device=local_rank)
+    synth.build_batch(b, base, cell0=rank * ncell, scheme=a.scheme)
+    b.upload()
+
+    def barrier():
+        b.device_sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    b.set_forcing(met[: (W + K) * 288])
+    for i in range(W):
+        b.advance(i * 288, 288, OUT_SUM82, sync=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    ms = []
+    for i in range(W, W + K):
+        b.advance(i * 288, 288, OUT_SUM82, sync=False)
+        ms.append(b.last_ms())   # CUDA events recorded on the library's launch stream
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    b.sync()   # raises if any cell hit a fatal SUEWS error
+    dev_s = sum(ms) * 1e-3
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_s, wall], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, wall = float(t[0]), float(t[1])
+    total_cs = float(world) * ncell * 288 * K
+    value = total_cs / dev_s
+
+    # ---------------- end-to-end through the host API (host buffers in, host results out)
+    e2e_t0 = None
+    cols = PARITY_COLS
+    for i in range(W + K):
+        if i == W:
+            barrier()
+            e2e_t0 = time.perf_counter()
+        day = met[(W + K + i) * 288:(W + K + i + 1) * 288]
+        b.set_forcing(day)                      # host -> device (pinned staging) + ephemeris kernel
+        b.advance(0, 288, OUT_SUM82, sync=False)
+        res = b.sums_cols(cols)                 # device -> host (pinned staging), waits for the kernel
+    barrier()
+    e2e_s = time.perf_counter() - e2e_t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_val = total_cs / e2e_s
+    checksum = float(np.sum(res[:, 0]))
+    fatal, warn, iters = b.diag()
+
+    if rank != 0:
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    # algorithmic bytes per launch: state read+write, cell params read, sums read+write, per cell; forcing shared
+    bytes_per_launch = ncell * 8.0 * (2 * N_STATE + N_CELL + 2 * N_SUM) + 288 * 160.0
+    launch_s = dev_s / K
+    ach_gbs = bytes_per_launch / launch_s / 1e9
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
+    except Exception:
+        pass
+    import ctypes as C
+    tf = C.c_double()
+    fp64_peak = None
+    if _lib.lib().suews_b200_fp64_peak(local_rank, C.byref(tf)) == 0:
+        fp64_peak = tf.value
+    fp64 = {"peak_tflops_measured_dfma": fp64_peak, "flops_per_cell_step_executed": prof.get("fp64_flops_per_cell_step"),
+            "source": prof.get("source")}
+    if fp64_peak and prof.get("fp64_flops_per_cell_step"):
+        fp64["achieved_tflops"] = prof["fp64_flops_per_cell_step"] * ncell * 288 / launch_s / 1e12
+        fp64["frac"] = fp64["achieved_tflops"] / fp64_peak
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "cells_per_gpu": ncell, "timesteps_per_step": 288, "output_policy": "per-cell sums of all 82 SUEWS columns (P0+)",
+                   "l2": "inputs (state+params %.0f MB/GPU) larger than L2" % (ncell * 8.0 * (N_STATE + N_CELL + N_SUM) / 1e6),
+                   "tsurf_iterations_per_step": float(iters.sum()) / (ncell * 288.0 * (2 * (W + K))), "wall_s_timed": wall,
+                   "checksum_QN": checksum, "fatal_cells": int((fatal != 0).sum())},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 288 * 160, "d2h_bytes_per_step": ncell * len(cols) * 8},
+        "gpu_launches": K,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                     "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "note": "kernel is FP64-pipe / latency bound, not HBM bound (SURVEY 8d); see fp64"},
+        "fp64": fp64,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        r, cores, cells, slowest, _ = cpu_arm(a.cpu_budget, a.scheme)
+        line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d cells x 288 steps of the same synthetic workload, one process per core (%.1f s)" % (cells, slowest)}
+    print(json.dumps(line))
+    b.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,11 @@ int suews_b200_sync(suews_b200_handle h);
 /* Results.  sums: [ncell][82] (cell-major).  Full blocks (after SUEWS_OUT_FULL): per cell a
  * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50 columns). */
 int suews_b200_get_sums(suews_b200_handle h, double *sums);
+/* selected columns only (0-based indices into the 82-column SUEWS line), [ncell][ncols]; device -> pinned host */
+int suews_b200_get_sums_cols(suews_b200_handle h, const int *cols, int ncols, double *out);
+int suews_b200_device_sync(suews_b200_handle h);
+/* measured FP64 FMA throughput of the device in TFLOP/s (compute-roofline denominator) */
+int suews_b200_fp64_peak(int device, double *tflops);
 int suews_b200_reset_sums(suews_b200_handle h);
 int suews_b200_get_block(suews_b200_handle h, const char *group /* "SUEWS","snow","RSL","DailyState" */, int cell,
                          double *block, int nsteps, int ncol);

@@ -47,6 +47,9 @@ def lib():
         L.suews_b200_sync.argtypes = [H]
         L.suews_b200_get_sums.argtypes = [H, dp]
         L.suews_b200_reset_sums.argtypes = [H]
+        L.suews_b200_get_sums_cols.argtypes = [H, ip, C.c_int, dp]
+        L.suews_b200_device_sync.argtypes = [H]
+        L.suews_b200_fp64_peak.argtypes = [C.c_int, dp]
         L.suews_b200_get_block.argtypes = [H, C.c_char_p, C.c_int, dp, C.c_int, C.c_int]
         L.suews_b200_get_diag.argtypes = [H, ip, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
         L.suews_b200_last_advance_ms.argtypes = [H, C.POINTER(C.c_float)]

@@ -142,6 +142,15 @@ class SuewsBatch:
         check(self.L.suews_b200_get_sums(self.h, a.ctypes.data_as(dp)))
         return a
 
+    def sums_cols(self, cols):
+        c = np.ascontiguousarray(np.asarray(cols, dtype=np.int32))
+        a = np.zeros((self.ncell, c.size))
+        check(self.L.suews_b200_get_sums_cols(self.h, c.ctypes.data_as(ip), c.size, a.ctypes.data_as(dp)))
+        return a
+
+    def device_sync(self):
+        check(self.L.suews_b200_device_sync(self.h))
+
     def reset_sums(self):
         check(self.L.suews_b200_reset_sums(self.h))
 

@@ -59,7 +59,7 @@ SU_DEV double sat_vap_pressIce(SuDiag &dg, double &T, double Press_hPa, int from
 }
 
 // suews_util_meteo.f95:409-427
-SU_DEV double psyc_const(SuDiag &dg, double cp, double Press_hPa, double lv_J_kg)
+SU_INL double psyc_const(SuDiag &dg, double cp, double Press_hPa, double lv_J_kg)
 {
    const double epsil = F(0.62197);
    if (cp * Press_hPa < 900 || lv_J_kg < 10000) su_warn(dg, 19);
@@ -67,13 +67,13 @@ SU_DEV double psyc_const(SuDiag &dg, double cp, double Press_hPa, double lv_J_kg
 }
 
 // suews_util_meteo.f95:444-492 (genuine double-precision literals)
-SU_DEV double slope_svp(double t)
+SU_INL double slope_svp(double t)
 {
    return 4.438099984e-1 +
           t * (2.857002636e-2 +
                t * (7.938054040e-4 + t * (1.215215065e-5 + t * (1.036561403e-7 + t * (3.532421810e-10 + -7.090244804e-13 * t)))));
 }
-SU_DEV double slopeIce_svp(double t)
+SU_INL double slopeIce_svp(double t)
 {
    return 5.030305237e-1 +
           t * (3.773255020e-2 +
@@ -202,7 +202,7 @@ SU_DEV double stab_psi_mom(int sm, double &zl)
    }
    return psim;
 }
-SU_DEV double stab_psi_mom_v(int sm, double zl) { return stab_psi_mom(sm, zl); }
+SU_INL double stab_psi_mom_v(int sm, double zl) { return stab_psi_mom(sm, zl); }
 
 // atmmoiststab.f95:334-394
 SU_DEV double stab_phi_mom(int sm, double zl)

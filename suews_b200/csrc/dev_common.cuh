@@ -9,8 +9,44 @@
 #define SU_MAX(a, b) ((a) > (b) ? (a) : (b))
 #define SU_MIN(a, b) ((a) < (b) ? (a) : (b))
 
-#define SU_DEV __device__ __forceinline__
+// Code size is a first-order performance parameter here: one cell-step is ~45 k SASS instructions when
+// everything is inlined (726 KB of text), far beyond the SM instruction caches, and the first profile
+// showed 69 % of warp stalls on instruction fetch (profiles/r1_ncu_notes.md).  So physics routines are
+// real functions (SU_DEV = noinline), the double-precision libm entry points are shared out-of-line
+// wrappers, and only leaf helpers are inlined (SU_INL).
+#define SU_INL __device__ __forceinline__
 #define SU_DEVNI __device__ __noinline__
+#ifdef SU_INLINE_ALL
+#define SU_DEV __device__ __forceinline__
+#else
+#define SU_DEV __device__ __noinline__
+#endif
+
+#ifndef SU_INLINE_ALL
+SU_DEVNI double su_exp(double x) { return exp(x); }
+SU_DEVNI double su_log(double x) { return log(x); }
+SU_DEVNI double su_pow(double x, double y) { return pow(x, y); }
+SU_DEVNI double su_sin(double x) { return sin(x); }
+SU_DEVNI double su_cos(double x) { return cos(x); }
+SU_DEVNI double su_tan(double x) { return tan(x); }
+SU_DEVNI double su_atan(double x) { return atan(x); }
+SU_DEVNI double su_atan2(double y, double x) { return atan2(y, x); }
+SU_DEVNI double su_asin(double x) { return asin(x); }
+SU_DEVNI double su_acos(double x) { return acos(x); }
+SU_DEVNI double su_tanh(double x) { return tanh(x); }
+// from here on the physics headers call the shared wrappers (undone at the end of dev_step.cuh)
+#define exp su_exp
+#define log su_log
+#define pow su_pow
+#define sin su_sin
+#define cos su_cos
+#define tan su_tan
+#define atan su_atan
+#define atan2 su_atan2
+#define asin su_asin
+#define acos su_acos
+#define tanh su_tanh
+#endif
 
 enum { PAV = 0, BLDG = 1, CONIF = 2, DECID = 3, GRASS = 4, BSOIL = 5, WATER = 6 };
 enum { NSURF = SUEWS_NSURF, NVEG = SUEWS_NVEG };
@@ -21,8 +57,8 @@ struct SuDiag {
    int fatal;                 // 0 = ok
    unsigned long long warn[2];   // bit c set <=> warning code c (< 128) was raised
 };
-SU_DEV void su_warn(SuDiag &d, int code) { d.warn[(code >> 6) & 1] |= (1ull << (code & 63)); }
-SU_DEV void su_fatal(SuDiag &d, int code)
+SU_INL void su_warn(SuDiag &d, int code) { d.warn[(code >> 6) & 1] |= (1ull << (code & 63)); }
+SU_INL void su_fatal(SuDiag &d, int code)
 {
    if (d.fatal == 0) d.fatal = code;
 }
@@ -35,11 +71,11 @@ SU_DEV void su_fatal(SuDiag &d, int code)
 #define SU_SDP(p, i, is) ((p)[(i) + 6 * (is)])
 
 // x**n for constant integer n as gfortran -O3 expands it (optimal powi chains)
-SU_DEV double su_p2(double x) { return x * x; }
-SU_DEV double su_p3(double x) { return x * (x * x); }
-SU_DEV double su_p4(double x) { double a = x * x; return a * a; }
-SU_DEV double su_p5(double x) { double a = x * x; return a * (x * a); }
-SU_DEV double su_p8(double x) { double a = x * x; a = a * a; return a * a; }
+SU_INL double su_p2(double x) { return x * x; }
+SU_INL double su_p3(double x) { return x * (x * x); }
+SU_INL double su_p4(double x) { double a = x * x; return a * a; }
+SU_INL double su_p5(double x) { double a = x * x; return a * (x * a); }
+SU_INL double su_p8(double x) { double a = x * x; a = a * a; return a * a; }
 
 // Per-step quantities that do not depend on the Tsurf iteration (hoisted out of the DO WHILE at
 // driver.f95:642, which recomputes all of them on every trip).

@@ -12,7 +12,7 @@
 #define SU_PI 3.141592653589793
 
 // narp.f95:1219-1236
-SU_DEV double set_to_range(double var)
+SU_INL double set_to_range(double var)
 {
    double vari = var - F(360.0) * (int)floor(var / F(360.0));
    if (vari < F(0.0)) vari = vari + F(360.0);
@@ -45,7 +45,7 @@ SU_DEV void day2month(int b, int year, int &mb, int &md)
 }
 
 // util_time.f95:173-199
-SU_DEV int day_of_week(int date, int month, int year)
+SU_INL int day_of_week(int date, int month, int year)
 {
    int yr = year, mn = month;
    if (!(mn > 2)) { mn = mn + 12; yr = yr - 1; }
@@ -211,7 +211,7 @@ SU_DEVNI void spa_location_part(const SuewsEphem &e, double lat, double lng, dou
 
 // ------------------------------------------------------------------ NARP
 // narp.f95:44-102
-SU_DEV void RadMethod(SuDiag &dg, int NetRadiationMethod, int snowUse, int &nrm_use, int &AlbedoChoice, int &ldown_option)
+SU_INL void RadMethod(SuDiag &dg, int NetRadiationMethod, int snowUse, int &nrm_use, int &AlbedoChoice, int &ldown_option)
 {
    AlbedoChoice = 0;
    ldown_option = 0;

@@ -7,7 +7,7 @@
 
 // ------------------------------------------------------------------ OHM (ohm.f95)
 // ohm.f95:271-305
-SU_DEV void OHM_dqndt_cal_X(int dt, int dt_since_start, double qn1_av_prev, double qn1, double dqndt_prev,
+SU_INL void OHM_dqndt_cal_X(int dt, int dt_since_start, double qn1_av_prev, double qn1, double dqndt_prev,
                             double &qn1_av_next, double &dqndt_next)
 {
    const double dt0_thresh = 3600, window_hr = 2;
@@ -167,7 +167,7 @@ struct SuFlood {
 };
 
 // waterdist.f95:405-451
-SU_DEV void updateFlood(int is, double runoff_is, const double *sfr, double PipeCapacity, double RunoffToWater,
+SU_INL void updateFlood(int is, double runoff_is, const double *sfr, double PipeCapacity, double RunoffToWater,
                         SuFlood &fl)
 {
    fl.runoffPipes = fl.runoffPipes + (runoff_is * sfr[is]);
@@ -403,13 +403,13 @@ SU_DEVNI void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *s
 // ------------------------------------------------------------------ diurnal profiles (ctrl_input.f95:743-826)
 // The 24-term SUM the reference redoes on every call is a class constant (prof_sum), computed at
 // upload with the same sequential order.
-SU_DEV double prof_inst(int Hour, int Min, const double *p24)
+SU_INL double prof_inst(int Hour, int Min, const double *p24)
 {
    int j = (Hour + 1 == 24) ? 0 : Hour + 1;
    double deltaProf = (p24[j] - p24[Hour]) / 3600;
    return p24[Hour] + deltaProf * (Min * 60);
 }
-SU_DEV double prof_mean(int Hour, int Min, const double *p24, double sum24)
+SU_INL double prof_mean(int Hour, int Min, const double *p24, double sum24)
 {
    int j = (Hour + 1 == 24) ? 0 : Hour + 1;
    double pi_ = 0.0, pj_ = 0.0;
@@ -421,7 +421,7 @@ SU_DEV double prof_mean(int Hour, int Min, const double *p24, double sum24)
    double deltaProf = (pj_ - pi_) / 3600;
    return pi_ + deltaProf * (Min * 60);
 }
-SU_DEV double prof_sum(int Hour, int Min, const double *p24, double sum24, int dt)
+SU_INL double prof_sum(int Hour, int Min, const double *p24, double sum24, int dt)
 {
    int j = (Hour + 1 == 24) ? 0 : Hour + 1;
    double pi_ = 0.0, pj_ = 0.0;
@@ -478,12 +478,12 @@ SU_DEV void cal_WaterUse(const SuewsClassParams &P, const SuewsCellParams &C, do
 }
 
 // ------------------------------------------------------------------ anthropogenic heat (anemsn.f95:29-338)
-SU_DEV bool em_is(int m, int a, int b)
+SU_INL bool em_is(int m, int a, int b)
 {
    int r = m % 10, dcd = m / 10;
    return dcd <= 4 && (r == a || r == b);
 }
-SU_DEV bool em_in(int m, int lo, int hi)
+SU_INL bool em_in(int m, int lo, int hi)
 {
    int r = m % 10, dcd = m / 10;
    return dcd <= 4 && r >= lo && r <= hi;

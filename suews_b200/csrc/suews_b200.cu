@@ -9,10 +9,6 @@
 //   ephem     SuewsEphem[ntz][nsteps]             time-only half of the solar position, one thread / step
 //   sums      double[82][stride]                  per-cell running sums of the SUEWS output line
 // One thread owns one cell and advances it through all requested timesteps of a launch.
-#include "suews_fields.h"
-#include "dev_step.cuh"
-#include "../../include/suews_b200.h"
-
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdint>
@@ -22,6 +18,10 @@
 #include <strings.h>
 #include <string>
 #include <vector>
+
+#include "suews_fields.h"
+#include "dev_step.cuh"
+#include "../../include/suews_b200.h"
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -157,38 +157,36 @@ __global__ void __launch_bounds__(SU_BLOCK) suews_run_kernel(SuRunArgs a)
       mbar_wait(&sm_bar[buf], (uint32_t)((ch >> 1) & 1));
       const int s0 = ch * SU_CHUNK;
       const int ns = min(SU_CHUNK, a.nsteps - s0);
-      if (active) {
-         for (int t = 0; t < ns; t++) {
-            if (dg.fatal == 0) {
-               const int gs = s0 + t;
-               SuLines L;
-               L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr;
-               double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY];
-               if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; }
-               iters += suews_step(dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
-                                   a.sums ? acc : nullptr, L);
-               if (FULL) {
-                  const size_t n = (size_t)a.nsteps;
-                  double *b;
-                  b = a.blkSUEWS + (size_t)cell * n * (SUEWS_NCOL_SUEWS + 5);
-                  for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
-                  for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) b[gs + n * (5 + c)] = l_su[c];
-                  b = a.blkRSL + (size_t)cell * n * (SUEWS_NCOL_RSL + 5);
-                  for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
-                  for (int c = 0; c < SUEWS_NCOL_RSL; c++) b[gs + n * (5 + c)] = l_rs[c];
-                  b = a.blkDaily + (size_t)cell * n * (SUEWS_NCOL_DAILY + 5);
-                  for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
-                  for (int c = 0; c < SUEWS_NCOL_DAILY; c++) b[gs + n * (5 + c)] = l_da[c];
-                  if (P.snowUse == 1) {   // SUEWS_update_output, driver.f95:2499-2501 (with set_nan :2737)
-                     b = a.blkSnow + (size_t)cell * n * (SUEWS_NCOL_SNOW + 5);
-                     for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
-                     for (int c = 0; c < SUEWS_NCOL_SNOW; c++) b[gs + n * (5 + c)] = (fabs(l_sn[c]) > 30000) ? -999.0 : l_sn[c];
-                  }
-               }
+      for (int t = 0; t < ns; t++) {
+         const int gs = s0 + t;
+         const bool live = active && dg.fatal == 0;
+         SuLines L;
+         L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr;
+         double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY];
+         if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; }
+         // every thread of the block enters the step (phase barriers inside); only live cells compute
+         iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
+                             a.sums ? acc : nullptr, L);
+         if (FULL && live && dg.fatal == 0) {
+            const size_t n = (size_t)a.nsteps;
+            double *b;
+            b = a.blkSUEWS + (size_t)cell * n * (SUEWS_NCOL_SUEWS + 5);
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) b[gs + n * (5 + c)] = l_su[c];
+            b = a.blkRSL + (size_t)cell * n * (SUEWS_NCOL_RSL + 5);
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_RSL; c++) b[gs + n * (5 + c)] = l_rs[c];
+            b = a.blkDaily + (size_t)cell * n * (SUEWS_NCOL_DAILY + 5);
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_DAILY; c++) b[gs + n * (5 + c)] = l_da[c];
+            if (P.snowUse == 1) {   // SUEWS_update_output, driver.f95:2499-2501 (with set_nan :2737)
+               b = a.blkSnow + (size_t)cell * n * (SUEWS_NCOL_SNOW + 5);
+               for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+               for (int c = 0; c < SUEWS_NCOL_SNOW; c++) b[gs + n * (5 + c)] = (fabs(l_sn[c]) > 30000) ? -999.0 : l_sn[c];
             }
-            dt_since_start += a.tstep;   // caller-side clock, driver.f95:3483
-            tstep_prev = a.tstep;
          }
+         dt_since_start += a.tstep;   // caller-side clock, driver.f95:3483
+         tstep_prev = a.tstep;
       }
       __syncthreads();   // everyone is done with buffer `buf` before it is refilled two chunks later
    }
@@ -206,6 +204,17 @@ __global__ void __launch_bounds__(SU_BLOCK) suews_run_kernel(SuRunArgs a)
          for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) a.sums[(size_t)c * a.stride + cell] = acc[c];
       }
    }
+}
+
+__global__ void suews_dfma_kernel(double *out, int iters, double m)
+{
+   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+   const double b = 1e-9;
+   for (int i = 0; i < iters; i++) {
+      a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+      a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+   }
+   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 __global__ void suews_sunpos_kernel(double year, double idectime, double UTC, double lat, double lng, double alt, double *out)
@@ -334,6 +343,11 @@ struct suews_b200_handle_s {
    cudaStream_t stream = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    int first_fatal_code = 0, first_fatal_cell = -1;
+   void *pinned = nullptr;   // pinned host staging (forcing records in, selected sums out)
+   size_t pinned_bytes = 0;
+   void *pinned_in = nullptr;
+   size_t pinned_in_bytes = 0;
+   size_t steps_cap = 0;
 };
 
 template <typename T> static cudaError_t dev_alloc(T **p, size_t n)
@@ -412,6 +426,8 @@ int suews_b200_destroy(suews_b200_handle h)
 {
    if (!h) return SUEWS_OK;
    free_dev(h);
+   if (h->pinned) cudaFreeHost(h->pinned);
+   if (h->pinned_in) cudaFreeHost(h->pinned_in);
    if (h->stream) cudaStreamDestroy(h->stream);
    if (h->ev0) cudaEventDestroy(h->ev0);
    if (h->ev1) cudaEventDestroy(h->ev1);
@@ -563,6 +579,7 @@ int suews_b200_upload(suews_b200_handle h)
    CUDA_OK(cudaMemset(h->d_warn, 0, sizeof(unsigned long long) * 2 * st));
    CUDA_OK(cudaMemset(h->d_iters, 0, sizeof(long long) * st));
    h->uploaded = true;
+   h->steps_cap = 0;   // the ephemeris table is sized by the number of distinct time zones
    h->first_fatal_code = 0;
    h->first_fatal_cell = -1;
    return SUEWS_OK;
@@ -605,8 +622,14 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
       if (rc) return rc;
    }
    CUDA_OK(cudaSetDevice(h->device));
-   std::vector<SuewsStepRec> recs((size_t)nsteps);
    const size_t n = (size_t)nsteps;
+   if (h->pinned_in_bytes < sizeof(SuewsStepRec) * n) {
+      if (h->pinned_in) cudaFreeHost(h->pinned_in);
+      h->pinned_in = nullptr;
+      CUDA_OK(cudaHostAlloc(&h->pinned_in, sizeof(SuewsStepRec) * n, cudaHostAllocDefault));
+      h->pinned_in_bytes = sizeof(SuewsStepRec) * n;
+   }
+   SuewsStepRec *recs = (SuewsStepRec *)h->pinned_in;
 #define MET(col) met[(size_t)i + n * (col)]
    for (int i = 0; i < nsteps; i++) {   // driver.f95:3177-3201
       SuewsStepRec &r = recs[(size_t)i];
@@ -617,9 +640,12 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
       decode_clock(r);
    }
 #undef MET
-   CUDA_OK(dev_alloc(&h->d_steps, n));
-   CUDA_OK(dev_alloc(&h->d_ephem, n * h->tz_list.size()));
-   CUDA_OK(cudaMemcpyAsync(h->d_steps, recs.data(), sizeof(SuewsStepRec) * n, cudaMemcpyHostToDevice, h->stream));
+   if (h->steps_cap < n) {
+      CUDA_OK(dev_alloc(&h->d_steps, n));
+      CUDA_OK(dev_alloc(&h->d_ephem, n * h->tz_list.size()));
+      h->steps_cap = n;
+   }
+   CUDA_OK(cudaMemcpyAsync(h->d_steps, recs, sizeof(SuewsStepRec) * n, cudaMemcpyHostToDevice, h->stream));
    int total = nsteps * (int)h->tz_list.size();
    suews_ephem_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_steps, nsteps, h->d_tzlist, (int)h->tz_list.size(),
                                                                  h->tstep, h->d_ephem);
@@ -702,6 +728,70 @@ int suews_b200_get_sums(suews_b200_handle h, double *sums)
    CUDA_OK(cudaMemcpy(tmp.data(), h->d_sums, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
    for (int c = 0; c < h->ncell; c++)
       for (int k = 0; k < SUEWS_NCOL_SUEWS; k++) sums[(size_t)c * SUEWS_NCOL_SUEWS + k] = tmp[(size_t)k * h->stride + c];
+   return SUEWS_OK;
+}
+
+// Selected columns of the running sums, [ncell][ncols] cell-major, through a pinned staging buffer.
+int suews_b200_get_sums_cols(suews_b200_handle h, const int *cols, int ncols, double *out)
+{
+   if (!h || !h->uploaded || !cols || !out || ncols <= 0) return set_err(SUEWS_E_BAD_ARG, "get_sums_cols: bad arguments");
+   CUDA_OK(cudaSetDevice(h->device));
+   size_t need = sizeof(double) * (size_t)ncols * (size_t)h->stride;
+   if (h->pinned_bytes < need) {
+      if (h->pinned) cudaFreeHost(h->pinned);
+      h->pinned = nullptr;
+      CUDA_OK(cudaHostAlloc(&h->pinned, need, cudaHostAllocDefault));
+      h->pinned_bytes = need;
+   }
+   double *pin = (double *)h->pinned;
+   for (int k = 0; k < ncols; k++) {
+      if (cols[k] < 0 || cols[k] >= SUEWS_NCOL_SUEWS) return set_err(SUEWS_E_BAD_ARG, "get_sums_cols: column %d", cols[k]);
+      CUDA_OK(cudaMemcpyAsync(pin + (size_t)k * h->stride, h->d_sums + (size_t)cols[k] * h->stride,
+                              sizeof(double) * (size_t)h->ncell, cudaMemcpyDeviceToHost, h->stream));
+   }
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   for (int c = 0; c < h->ncell; c++)
+      for (int k = 0; k < ncols; k++) out[(size_t)c * ncols + k] = pin[(size_t)k * h->stride + c];
+   return SUEWS_OK;
+}
+
+int suews_b200_device_sync(suews_b200_handle h)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaDeviceSynchronize());
+   return SUEWS_OK;
+}
+
+// Measured FP64 FMA throughput of this device [TFLOP/s]: the compute-roofline denominator
+// (MEASURED_PEAKS.json has no FP64 figure).  8 independent DFMA chains per thread.
+int suews_b200_fp64_peak(int device, double *tflops)
+{
+   CUDA_OK(cudaSetDevice(device));
+   cudaDeviceProp prop;
+   CUDA_OK(cudaGetDeviceProperties(&prop, device));
+   const int iters = 1 << 14, threads = 256, blocks = prop.multiProcessorCount * 8;
+   double *d = nullptr;
+   CUDA_OK(cudaMalloc((void **)&d, sizeof(double) * (size_t)threads * blocks));
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0);
+   cudaEventCreate(&e1);
+   float best = 1e30f;
+   for (int rep = 0; rep < 5; rep++) {
+      cudaEventRecord(e0);
+      suews_dfma_kernel<<<blocks, threads>>>(d, iters, 1.0000001);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+   }
+   cudaEventDestroy(e0);
+   cudaEventDestroy(e1);
+   cudaFree(d);
+   CUDA_OK(cudaGetLastError());
+   double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+   *tflops = flops / (best * 1e-3) / 1e12;
    return SUEWS_OK;
 }
 

