@@ -205,7 +205,7 @@ SU_DEV double stab_psi_mom(int sm, double &zl)
 SU_INL double stab_psi_mom_v(int sm, double zl) { return stab_psi_mom(sm, zl); }
 
 // atmmoiststab.f95:334-394
-SU_DEV double stab_phi_mom(int sm, double zl)
+SU_INL double stab_phi_mom(int sm, double zl)
 {
    double phim = 0;
    if (fabs(zl) < SU_NEUT_LIMIT) {
@@ -251,7 +251,7 @@ SU_DEV double stab_psi_heat(int sm, double zl)
 }
 
 // atmmoiststab.f95:455-497
-SU_DEV double stab_phi_heat(int sm, double zl)
+SU_INL double stab_phi_heat(int sm, double zl)
 {
    double phih = 0;
    if (fabs(zl) < SU_NEUT_LIMIT) {

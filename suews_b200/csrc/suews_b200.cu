@@ -26,7 +26,14 @@
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-#define SU_BLOCK 128
+// One 512-thread block per SM (<= 128 registers): all 16 warps of an SM walk the same phase of the
+// step together, which is what keeps instruction fetch off the critical path (profiles/r1_ncu_notes.md).
+#ifndef SU_BLOCK
+#define SU_BLOCK 512
+#endif
+#ifndef SU_MINBLOCKS
+#define SU_MINBLOCKS 1
+#endif
 #define SU_CHUNK 32   // timesteps staged per bulk copy (32 x 160 B = 5 KB)
 
 struct SuRunArgs {
@@ -94,7 +101,7 @@ __global__ void suews_ephem_kernel(const SuewsStepRec *steps, int nsteps, const 
 }
 
 template <bool FULL>
-__global__ void __launch_bounds__(SU_BLOCK) suews_run_kernel(SuRunArgs a)
+__global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRunArgs a)
 {
    __shared__ alignas(128) SuewsStepRec sm_steps[2][SU_CHUNK];
    __shared__ alignas(8) uint64_t sm_bar[2];
