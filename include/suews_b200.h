@@ -42,6 +42,9 @@ enum {
    SUEWS_E_NOT_IMPL = 1003     /* scheme outside this library (AnOHM, ESTM): see suews_last_error */
 };
 
+/* where a named field lives (suews_b200_field_info) */
+enum { SUEWS_KIND_CLASS_INT = 0, SUEWS_KIND_CLASS_DBL = 1, SUEWS_KIND_CELL_DBL = 2, SUEWS_KIND_STATE_DBL = 3 };
+
 /* output policy bits for suews_b200_advance */
 enum {
    SUEWS_OUT_SUM82 = 1,   /* accumulate per-cell sums of the 82 SUEWS columns over the advanced steps */
@@ -98,18 +101,29 @@ int suews_b200_last_advance_ms(suews_b200_handle h, float *ms);
 int suews_b200_device_ptrs(suews_b200_handle h, void **d_state, void **d_sums, long long *cell_stride);
 
 /* ---- reference-shaped entry points --------------------------------------------------------- */
-/* Same positional argument list as the Fortran (all by pointer, arrays column-major).  The argument
- * tables live in suews_b200/csrc/suews_refargs.inc; see INTEGRATION.md for the f2py/ctypes/ISO_C_BINDING
- * stubs.  Both run one cell on the device through the batched path. */
-int suews_cal_multitsteps_c(const double *MetForcingBlock, int len_sim, const void *const *args_in_order,
-                            double *dataOutBlockSUEWS, double *dataOutBlockSnow, double *dataOutBlockESTM,
-                            double *dataOutBlockRSL, double *dataOutBlockSOL, double *DailyStateBlock);
-int suews_cal_main_c(const void *const *args_in_order, double *datetimeLine, double *dataOutLineSUEWS,
-                     double *dataOutLineSnow, double *dataOutLineESTM, double *dataoutLineRSL,
-                     double *dataOutLineSOLWEIG, double *DailyStateLine);
-/* names of the arguments expected in args_in_order, in order; returns the count */
+/* The Fortran positional argument lists, every argument by reference (INTEGER -> int*, REAL(KIND(1d0))
+ * -> double*), arrays column-major: args[k] is the k-th dummy argument of the reference subroutine,
+ * inputs, INTENT(INOUT) state and INTENT(OUT) lines/blocks alike (200 for SUEWS_cal_multitsteps,
+ * driver.f95:2814-2862; 220 for SUEWS_cal_Main, driver.f95:45-91).  nargs must equal that count.
+ * INOUT arguments are updated in place and the output lines/blocks are filled exactly as the reference
+ * fills them; the two assumed-shape AnOHM/ESTM inputs (MetForcingData_grid, Ts5mindata_ir) and any
+ * unwanted output block may be NULL.  The tables (name, type, intent, extent) are generated from the
+ * reference's SUBROUTINE statements into suews_b200/csrc/suews_refargs.inc; *_argnames returns the names
+ * in order.  Both calls run the one cell on the device through the batched path.  Return: 0, the
+ * ErrorHint number of a fatal condition (outputs up to the failing step are still returned), or SUEWS_E_*. */
+int suews_cal_multitsteps_c(void *const *args, int nargs);
+int suews_cal_main_c(void *const *args, int nargs);
 int suews_cal_multitsteps_argnames(const char *const **names);
 int suews_cal_main_argnames(const char *const **names);
+/* argument i (0-based) of SUEWS_cal_Main (which = 0) or SUEWS_cal_multitsteps (which = 1): INTEGER or REAL,
+ * intent (0 in, 1 inout, 2 out), element count, and whether that count is per forcing row (x len_sim) */
+int suews_refapi_arginfo(int which, int i, const char **name, int *is_int, int *intent, int *elements, int *per_row);
+/* The same two calls under the symbol names and calling convention gfortran gives an external procedure
+ * (suews_cal_main_, suews_cal_multitsteps_: 220 / 200 pointer parameters) are exported too; their
+ * prototypes are SUEWS_CAL_MAIN_PARAMS / SUEWS_CAL_MULTITSTEPS_PARAMS in suews_refargs.inc.  They return
+ * nothing, like the SUBROUTINEs they replace: check suews_last_error afterwards. */
+/* forget the process-wide hidden SAVE state (Lat_vap switches, NARP alb1) -- a fresh reference process */
+void suews_refapi_reset_hidden(void);
 
 int suews_cal_sunposition_c(double year, double idectime, double UTC, double locationlatitude,
                             double locationlongitude, double locationaltitude, double *sunazimuth,

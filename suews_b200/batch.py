@@ -98,7 +98,7 @@ class SuewsBatch:
         for name, kind, n in all_fields():
             key = name.lower()
             if key not in low:
-                if name not in ("dTemp_C", "dRH", "alb1_hidden", "lv_switch"):
+                if name not in ("dTemp_C", "dRH", "alb1_hidden", "lv_switch", "rsl_cache"):
                     missing.append(name)
                 continue
             v = np.atleast_1d(np.asarray(low[key], dtype=np.float64)).ravel()

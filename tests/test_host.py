@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "suews_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(suews_\w+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(?:int|void)\s+(suews_\w+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -26,6 +26,52 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 25
     missing = [s for s in syms if not hasattr(L, s)]
     assert not missing, missing
+
+
+def test_gfortran_named_entry_points_are_exported():
+    from suews_b200 import _lib
+    L = C.CDLL(_lib.LIB_PATH)
+    assert hasattr(L, "suews_cal_main_") and hasattr(L, "suews_cal_multitsteps_")
+
+
+def test_output_name_table_like_supy_driver():
+    """supy-driver/supy_driver/test/test-supy_driver.py: output_name_n(3)[0] is bytes; plus the table itself"""
+    import json
+    from suews_b200.supy_driver import suews_driver as sd
+    s = sd.output_name_n(3)[0]
+    assert isinstance(s, bytes) and s == b"Hour".ljust(15)
+    assert sd.output_size() == 500                      # SIZE(varListAll), suews_ctrl_output.f95:68
+    rows = json.load(open(os.path.join(ROOT, "suews_b200", "varlist.json")))
+    for i, r in enumerate(rows, start=1):
+        nm, grp, agg, lvl = sd.output_name_n(i)
+        assert nm.strip().decode() == r["name"] and grp.strip().decode() == r["group"], i
+        assert agg.strip().decode() == r["aggreg"] and lvl == r["level"], i
+    for i in (0, -1, len(rows) + 1, 499, 500, 501):     # unfilled tail and out-of-range: blanks, level 0
+        assert sd.output_name_n(i) == (b" " * 15, b" " * 15, b" " * 15, 0)
+
+
+def test_reference_argument_tables():
+    """the positional tables the reference-shaped calls are built on (generated from the SUBROUTINE statements)"""
+    from suews_b200.supy_driver import arg_table
+    main, multi = arg_table(0), arg_table(1)
+    assert len(main) == 220 and len(multi) == 200
+    assert [r[0] for r in multi[:3]] == ["MetForcingBlock", "len_sim", "AerodynamicResistanceMethod"]
+    assert [r[0] for r in multi[-6:]] == ["dataOutBlockSUEWS", "dataOutBlockSnow", "dataOutBlockESTM", "dataOutBlockRSL",
+                                          "dataOutBlockSOL", "DailyStateBlock"]
+    assert [(r[3], r[4]) for r in multi[-6:]] == [(87, True), (103, True), (32, True), (138, True), (31, True), (50, True)]
+    assert [r[3] for r in main[-7:]] == [5, 82, 98, 27, 133, 26, 45] and all(r[2] == 2 for r in main[-7:])
+    byname = {r[0].lower(): r for r in main}
+    assert byname["ohm_coef"][3] == 8 * 4 * 3 and byname["storedrainprm"][3] == 42 and byname["hdd_id"][3] == 12
+    assert byname["snowuse"][1] and byname["tstep"][1] and not byname["alb"][1]
+    assert byname["alb"][2] == 1 and byname["state_id"][2] == 1 and byname["sfr"][2] == 0
+    # without a device the calls fail loudly
+    from suews_b200 import _lib
+    if _lib.lib().suews_b200_device_count() == 0:
+        f = _lib.lib().suews_cal_main_c
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        arr = (C.c_void_p * 220)()
+        assert f(arr, 220) == 2001
+        assert f(arr, 219) == 2004
 
 
 def test_no_device_is_a_loud_error_not_a_fallback():
@@ -101,8 +147,9 @@ def test_forcing_disaggregation_types():
     assert f20[4] == slow[0] and abs(f20[7] - (slow[0] + (slow[1] - slow[0]) * 3 / 4)) < 1e-15
     p = _disagg_p_among_n(np.array([1.2, 0.0, 0.6]), 4, 4)
     assert np.allclose(p, [0.3] * 4 + [0.0] * 4 + [0.15] * 4)
+    # a constant -999 series stays -999 -> the reference's ErrorHint 13
     with pytest.raises(RuntimeError):
-        _disagg_lin(np.array([1.0]), -999.0, -999.0, 20, 4)
+        _disagg_lin(np.array([-999.0, -999.0, -999.0]), -999.0, -999.0, 10, 4)
 
 
 _GLOO_WORKER = r"""
