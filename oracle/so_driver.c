@@ -9,6 +9,7 @@
  * list.  SOLWEIG_cal_main (diagnostic only) is not restated: its output line
  * is -999-filled. */
 #include "suews_oracle.h"
+extern double *so_debug_trace;
 #include <math.h>
 #include <string.h>
 
@@ -541,6 +542,11 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
 
       TSfc_C = so_cal_tsfc(qh, avdens, avcp, RA, Temp_C);
 
+      if (so_debug_trace && i_iter < 100) { /* test hook: the fixed-point sequence of the Tsurf loop */
+         so_debug_trace[3 * (i_iter - 1)] = qh;
+         so_debug_trace[3 * (i_iter - 1) + 1] = L_mod;
+         so_debug_trace[3 * (i_iter - 1) + 2] = TSfc_C;
+      }
       if (fabs(Ts_iter - TSfc_C) > F(0.1)) flag_converge = 0; else flag_converge = 1;
       Ts_iter = TSfc_C;
       i_iter = i_iter + 1;
@@ -623,6 +629,9 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
    (void)TStar; (void)gsc; (void)zL; (void)SoilState; (void)TempVeg; (void)VPD_Pa; (void)dens_dry; (void)es_hPa;
    (void)kclear; (void)qh_residual; (void)ImpervFraction;
 }
+
+/* test hook (tests only): when non-NULL, [99][3] = (qh, L_mod, TSfc_C) of every trip of the last step */
+double *so_debug_trace = 0;
 
 /* ===== SUEWS_cal_multitsteps driver.f95:2814-3505 ===== */
 static const int NCOLS_BLK[6] = {NCOL_SUEWS + 5, NCOL_SNOW + 5, NCOL_ESTM + 5, NCOL_RSL + 5, NCOL_SOLWEIG + 5,

@@ -35,6 +35,29 @@
 #define SU_SYNC_OR(p) (p)
 #endif
 
+// Profiling build only (-DSU_PHASE_CLOCKS): SM cycles per phase, as seen by thread 0 of each block after the
+// phase's barrier (so a phase's time is that of its slowest warp).  tools/prof_run.py prints them.
+#ifdef SU_PHASE_CLOCKS
+__device__ unsigned long long su_phase_clk[16];
+#define SU_CLK_DECL long long clk_ = clock64()
+#define SU_CLK(i)                                                              \
+   do {                                                                        \
+      if (threadIdx.x == 0) {                                                  \
+         long long t_ = clock64();                                             \
+         atomicAdd(&su_phase_clk[i], (unsigned long long)(t_ - clk_));         \
+         clk_ = t_;                                                            \
+      }                                                                        \
+   } while (0)
+#define SU_CNT(i, n)                                                           \
+   do {                                                                        \
+      if (threadIdx.x == 0) atomicAdd(&su_phase_clk[i], (unsigned long long)(n)); \
+   } while (0)
+#else
+#define SU_CLK_DECL
+#define SU_CLK(i)
+#define SU_CNT(i, n)
+#endif
+
 // Optional per-step output lines (reference layouts).  NULL = not wanted.
 struct SuLines {
    double *datetime5, *suews82, *snow98, *rsl133, *daily45;
@@ -253,6 +276,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    bool rad_invariant = false, rad_done = false, qe_full_done = false;
    double lv_at_melt = 0;
 
+   SU_CLK_DECL;
    // ================= phase P0: geometry, sun, daily state =================
    if (live) {
       for (int is = 0; is < NSURF; is++) { deltaQi[is] = 0; smd_nsurf[is] = 0; SnowWater_in[is] = S.SnowWater[is]; }
@@ -267,6 +291,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H);
    }
    SU_SYNC();
+   SU_CLK(0);
    // ================= phase P1: moist air + Tsurf-independent stages =================
    if (live) {
       int sw_in = lv_sw;
@@ -279,10 +304,15 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
 
    bool done = !live || dg.fatal != 0;
    double Ts_iter = Temp_C;
+   // state after the previous two trips, for the exact cycle detection in phase L3
+   double cyc_qh[2] = {0, 0}, cyc_ts[2] = {0, 0}, cyc_alb[2] = {0, 0};
+   int cyc_sw[2] = {-1, -1};
    int i_iter = 1;
    for (;;) {
       const bool run = !done;
       if (!SU_SYNC_OR(run)) break;
+      SU_CLK(i_iter == 1 ? 1 : 4);
+      SU_CNT(8, 1);
       // ================= phase L1: radiation, storage heat, melt heat =================
       if (run) {
          if (i_iter > 1) {
@@ -351,6 +381,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
             LUMPS_cal_QHQE(dg, P, sfr, qn1, qf, qs, Hs.Qm, Temp_C, Hs.veg_fr, A.avcp, Press_hPa, A.lv_J_kg, H.d.LAI_id, Lm);
       }
       SU_SYNC();
+      SU_CLK(2);
       // ================= phase L2: stability and resistances (driver.f95:2134-2270) =================
       if (run) {
          const double QH_Init = (i_iter == 1) ? Lm.QH_LUMPS : qh;
@@ -362,6 +393,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
          rb = BoundaryLayerResistance(ZZD, z0m, avU1, UStar);
       }
       SU_SYNC();
+      SU_CLK(3);
       // ================= phase L3: QE, QH, surface temperature, convergence =================
       if (run) {
          const double qn_e = qn1_snowfree + qf - qs;
@@ -384,9 +416,25 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
          Ts_iter = TSfc_C;
          i_iter = i_iter + 1;
          if (converged || !(i_iter < 100) || dg.fatal != 0) done = true;
+         if (!done) {
+            // A trip is a pure function of what the previous trip left behind: (qh, Ts_iter, the Lat_vap switch
+            // state, NARP's persistent alb1); everything else restarts from the *_prev state.  When the loop does
+            // not converge it falls into an exact 2-cycle within 3-4 trips (stable nights: L_mod flips between
+            // two values), and the reference then burns all 99 trips of DO WHILE (driver.f95:642).  Once the
+            // state after trip n equals, bit for bit, the state after trip n-2, trips n+1.. repeat trips n-1,n..
+            // exactly, so the state after trip 99 is the one after trip n (99-n even) or n+1 (99-n odd).
+            const int n = i_iter - 1;
+            if (n >= 4 && qh == cyc_qh[0] && Ts_iter == cyc_ts[0] && lv_sw == cyc_sw[0] && Rd.alb1 == cyc_alb[0]) {
+               if (((99 - n) & 1) == 0) { done = true; i_iter = 100; }
+               else i_iter = 99;   // one more trip, which then ends the loop as the 99th
+            }
+            cyc_qh[0] = cyc_qh[1]; cyc_ts[0] = cyc_ts[1]; cyc_sw[0] = cyc_sw[1]; cyc_alb[0] = cyc_alb[1];
+            cyc_qh[1] = qh; cyc_ts[1] = Ts_iter; cyc_sw[1] = lv_sw; cyc_alb[1] = Rd.alb1;
+         }
       }
    }
    SU_SYNC();
+   SU_CLK(4);
    // ================= phase F1: state update of the last trip + soil water =================
    if (live && dg.fatal == 0) {
       if (!qe_full_done) {
@@ -403,6 +451,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
                     W.soilstore_id, soilstoreOld, sfr, smd, smd_nsurf, tot_chang_per_tstep);
    }
    SU_SYNC();
+   SU_CLK(5);
    // ================= phase F2: roughness-sublayer diagnostics (driver.f95:943-949) =================
    SuRSL rs;
    rs.T2_C = 0; rs.q2_gkg = 0; rs.U10_ms = 0; rs.RH2 = 0;
@@ -414,6 +463,8 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       if (P.EmissionsMethod >= 11) su_fatal(dg, 1004);
    }
    SU_SYNC();
+   SU_CLK(6);
+   SU_CNT(9, 1);
    // ================= phase F3: commit (driver.f95:965-994) and output lines =================
    if (!(live && dg.fatal == 0)) return i_iter - 1;
 
@@ -513,6 +564,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
          o[k++] = a1; o[k++] = a2; o[k++] = a3;
       }
    }
+   SU_CLK(7);
    return i_iter - 1;
 }
 

@@ -870,6 +870,20 @@ int suews_b200_get_diag(suews_b200_handle h, int *fatal, unsigned long long *war
    return SUEWS_OK;
 }
 
+#ifdef SU_PHASE_CLOCKS
+// profiling builds only: read (and optionally clear) the per-phase cycle counters of dev_step.cuh
+int suews_b200_debug_phase_clocks(unsigned long long *out16, int reset)
+{
+   CUDA_OK(cudaDeviceSynchronize());
+   if (out16) CUDA_OK(cudaMemcpyFromSymbol(out16, su_phase_clk, sizeof(unsigned long long) * 16));
+   if (reset) {
+      unsigned long long z[16] = {0};
+      CUDA_OK(cudaMemcpyToSymbol(su_phase_clk, z, sizeof(z)));
+   }
+   return SUEWS_OK;
+}
+#endif
+
 int suews_b200_device_ptrs(suews_b200_handle h, void **d_state, void **d_sums, long long *cell_stride)
 {
    if (!h || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "device_ptrs: nothing uploaded");

@@ -151,6 +151,7 @@ class Cell:
         if rc != 0:
             raise RuntimeError("SUEWS fatal error %d: %s" % (rc, msg.value.decode()))
         blocks["_warn"] = np.array(warn[:])
+        self.n_iter_last = nit.value      # Tsurf-loop trips of the last step
         return blocks
 
 

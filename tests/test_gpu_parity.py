@@ -182,6 +182,49 @@ def test_many_cells_match_per_cell_oracle():
     print("worst flux-sum rel err over sampled cells: %.3e" % worst)
 
 
+def test_non_converging_tsurf_loop_is_exact():
+    """Stable winter nights put the Tsurf loop (driver.f95:642) into an exact 2-cycle and the reference runs all
+    99 trips; the kernel detects the cycle and jumps to the state trip 99 would leave.  Results must be the
+    99-trip results: compare full output blocks on steps where the oracle really used 99 trips."""
+    from suews_b200 import OUT_FULL, SuewsBatch, synth
+    base = fx.state_init(2005)
+    met = fx.forcing(2004)[:60]
+    n = 8
+    b = SuewsBatch(n, 1)
+    _missing, site = synth.build_batch(b, base, cell0=0, scheme="default")
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, 60, OUT_FULL)
+    _fatal, _warn, iters = b.diag()
+    d0 = synth.base_with_scheme(base, "default")
+    n99 = 0
+    for c in (0, 1, 5):
+        dd = dict(d0)
+        for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
+            dd[k.lower()] = np.atleast_1d(site[k][c])
+        m = met.copy()
+        m[:, 11] += site["dTemp_C"][c]
+        m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + site["dRH"][c]))
+        cell = ol.Cell(dd)
+        trips = 0
+        ref = {g: np.zeros((60, ol.NCOL[g]), order="F") for g in ("SUEWS", "RSL")}
+        for i in range(60):     # one step at a time to read the oracle's trip count of every step
+            r = cell.run(m[i:i + 1], want=("SUEWS", "RSL"))
+            nit = cell.n_iter_last
+            trips += nit
+            n99 += int(nit == 99)
+            for g in ref:
+                ref[g][i] = r[g][0]
+        assert int(iters[c]) == trips, (c, int(iters[c]), trips)      # logical trip count == the reference's
+        for g in ref:
+            out = b.block(g, c, 60)
+            assert np.array_equal(out == -999.0, ref[g] == -999.0)
+            e = rel_err(out[:, 5:], ref[g][:, 5:], g)
+            assert e.max() <= TOL_DAY1, (c, g, float(e.max()), np.unravel_index(e.argmax(), e.shape))
+    assert n99 >= 20, n99      # the case under test really occurs in this window
+    b.close()
+
+
 def test_sun_position_entry_point():
     import ctypes as C
     from suews_b200 import _lib

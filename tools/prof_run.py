@@ -17,9 +17,23 @@ b = SuewsBatch(ncell, 1)
 synth.build_batch(b, base, scheme=scheme)
 b.upload()
 b.set_forcing(met[: row0 + 3 * nsteps])
-b.advance(0, row0, OUT_SUM82)
+if row0 > 0:
+    b.advance(0, row0, OUT_SUM82)
+import ctypes as C
+from suews_b200._lib import lib
+PH = ["P0 geometry/daily", "P1 moist air+hoisted", "L1 rad/OHM/melt", "L2 stab/resist", "L3 QE/QH/Tsfc", "F1 water balance",
+      "F2 RSL profile", "F3 commit/output"]
+clk = (C.c_ulonglong * 16)()
+has_clk = hasattr(lib(), "suews_b200_debug_phase_clocks")
 for i in range(3):
+    if has_clk:
+        lib().suews_b200_debug_phase_clocks(clk, 1)
     b.advance(row0 + i * nsteps, nsteps, OUT_SUM82)
     print("launch %d: %.2f ms -> %.3e cell-steps/s" % (i, b.last_ms(), ncell * nsteps / (b.last_ms() * 1e-3)))
+    if has_clk:
+        lib().suews_b200_debug_phase_clocks(clk, 0)
+        tot = float(sum(clk[:8])) or 1.0
+        print("   block-steps %d, Tsurf trips/step %.2f; share of block cycles: " % (clk[9], clk[8] / max(clk[9], 1)) +
+              ", ".join("%s %.1f%%" % (PH[k], 100.0 * clk[k] / tot) for k in range(8)))
 fatal, warn, iters = b.diag()
 print("fatal cells", int((fatal != 0).sum()), "iters/step", iters.sum() / (ncell * (row0 + 3.0 * nsteps)))
