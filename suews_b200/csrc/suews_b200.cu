@@ -27,10 +27,12 @@
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-// One 512-thread block per SM (<= 128 registers): all 16 warps of an SM walk the same phase of the
-// step together, which is what keeps instruction fetch off the critical path (profiles/r1_ncu_notes.md).
+// One 1024-thread block per SM (64 registers): all 32 warps of an SM walk the same phase of the step
+// together, which keeps instruction fetch off the critical path, and 32 warps hide the FP64 dependency
+// and local-memory latencies better than 16 warps with 128 registers did (profiles/r1_ncu_notes.md:
+// 512x1 1.01e8, 512x2 1.10e8, 768x2 1.23e8, 1024x1 1.29e8, 1024x2 1.14e8 cell-steps/s).
 #ifndef SU_BLOCK
-#define SU_BLOCK 512
+#define SU_BLOCK 1024
 #endif
 #ifndef SU_MINBLOCKS
 #define SU_MINBLOCKS 1
