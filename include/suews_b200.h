@@ -131,6 +131,10 @@ int suews_cal_sunposition_c(double year, double idectime, double UTC, double loc
 int suews_output_size(int *nVar);
 int suews_output_name_n(int i, char name[16], char group[16], char aggreg[16], int *outlevel);
 
+/* Diagnostic: compares the library's own exp/log (suews_b200/csrc/dev_math.cuh) with the CUDA math library
+ * bit for bit on n pseudo-random arguments; returns the mismatch counts (expected 0 and 0). */
+int suews_b200_selftest_math(long long n, unsigned long long seed, long long *bad_exp, long long *bad_log);
+
 /* last error of the calling thread: code and human-readable message */
 int suews_last_error(int *code, char *buf, int len);
 

@@ -14,14 +14,14 @@ SU_DEV double sat_vap_press(double TK, double P)
    return e * f;
 }
 
-// suews_util_meteo.f95:148-192.  Rewrites T when |T| < 0.001 (reference side effect, kept).
-SU_DEV double sat_vap_press_x(SuDiag &dg, double &T, double Press_hPa, int from)
+// suews_util_meteo.f95:148-192.  The reference rewrites its argument T to 0.001 when |T| < 0.001 (a side
+// effect the callers see); by-reference scalars of out-of-line device functions live in local memory, so the
+// rewrite is a separate inline step (su_fix_T) and the evaluation takes T by value.  Warnings 28/29 are
+// raised by the callers through sat_vap_press_warn.
+SU_INL double su_fix_T(double T) { return (fabs(T) < F(0.001000)) ? (double)F(0.001000) : T; }
+SU_DEV double sat_vap_press_v(double T, double Press_hPa)   // T already through su_fix_T
 {
    double es_hPa = 1000;
-   if (fabs(T) < F(0.001000)) {
-      if (from == 1) su_warn(dg, 29);
-      T = F(0.001000);
-   }
    double Press_kPa = Press_hPa / 10;
    if (T < 50 && T > -40) {
       if (T >= F(0.001000)) {
@@ -33,10 +33,17 @@ SU_DEV double sat_vap_press_x(SuDiag &dg, double &T, double Press_hPa, int from)
          double f = F(1.00022) + Press_kPa * (F(3.83E-6) + F(6.4E-10) * (T * T));
          es_hPa = e_mb * f;
       }
-   } else {
-      su_warn(dg, 28);
    }
    return es_hPa;
+}
+SU_INL double sat_vap_press_x(SuDiag &dg, double &T, double Press_hPa, int from)
+{
+   if (fabs(T) < F(0.001000)) {
+      if (from == 1) su_warn(dg, 29);
+      T = F(0.001000);
+   }
+   if (!(T < 50 && T > -40)) su_warn(dg, 28);
+   return sat_vap_press_v(T, Press_hPa);
 }
 
 // suews_util_meteo.f95:195-228
@@ -97,7 +104,7 @@ SU_DEV double qa2RH(double qa_gkg, double pres_hPa, double Ta_degC)
 
 // suews_util_meteo.f95:277-346.  The reference keeps switch1/switch2 in implicit-SAVE locals, so
 // their exit values seed the next call; here they are per-cell state (sw = switch1 | switch2 << 1).
-SU_DEVNI double Lat_vap(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
+SU_INL double Lat_vap(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
 {
    bool switch1 = (sw & 1) != 0, switch2 = (sw & 2) != 0;
    const double ea_fix = Ea_hPa;
@@ -169,7 +176,7 @@ SU_DEV void cal_AtmMoist(SuDiag &dg, double &Temp_C, double Press_hPa, double av
 #define SU_PIOVER2 ((double)(3.14159274f / 2.f))   // ACOS(-1.)/2. in REAL(4)
 
 // atmmoiststab.f95:252-331.  SM is a template parameter where the caller knows the scheme.
-SU_DEV double stab_psi_mom(int sm, double &zl)
+SU_DEV double stab_psi_mom(int sm, double zl)   // by value: the reference's in-place clip of zL (sm = 2) never outlives its callers' own clips
 {
    double psim = 0, x, x2;
    if (fabs(zl) < SU_NEUT_LIMIT) {

@@ -23,8 +23,14 @@
 #endif
 
 #ifndef SU_INLINE_ALL
+#include "dev_math.cuh"
+#ifdef SU_LIBM_EXPLOG
 SU_DEVNI double su_exp(double x) { return exp(x); }
 SU_DEVNI double su_log(double x) { return log(x); }
+#else
+SU_DEVNI double su_exp(double x) { return su_exp_fast(x); }
+SU_DEVNI double su_log(double x) { return su_log_fast(x); }
+#endif
 SU_DEVNI double su_pow_general(double x, double y) { return pow(x, y); }
 // x**0.5, x**0.25, x**(-0.25), x**(-0.5), x**1.5 -- the exponents of the stability functions, NARP's
 // Tsurf and van Genuchten -- go through DSQRT / rsqrt (<= 1.25 ulp) instead of the ~400-instruction general

@@ -1,8 +1,8 @@
 // dev_rsl.cuh -- roughness-sublayer profile diagnostics (T2, q2, U10, RH2 and the 30-level profile).
 // Device restatement of suews_phys_rslprof.f95.  Differences in organisation, not in arithmetic:
-//  * cal_psim_hat (rslprof.f95:366) is a recursion z -> 1.01 z up to 100 m; here it is a two-pass loop
-//    (levels up, accumulation down) with the same add order, the level-invariant cal_cm / zd / elm
-//    evaluated once instead of twice per level, and phim(zp) reused as the next level's phim(z);
+//  * cal_psim_hat (rslprof.f95:366) is a recursion z -> 1.01 z up to 100 m; here it is one upward loop
+//    with the level-invariant cal_cm / zd / elm evaluated once instead of twice per level and phim(zp)
+//    reused as the next level's phim(z) (the additions run bottom-up: a few ulp, see cal_psim_hat_zh);
 //  * the whole z0_RSL search is skipped when the RSL correction is off (flag_RSL false): the
 //    reference computes it and then overwrites z0_RSL with z0m (rslprof.f95:220-223).
 #pragma once
@@ -45,41 +45,31 @@ SU_DEVNI double cal_psim_hat_zh(int sm, double zh, double L_MOD, double beta, do
    // the two per-level divisions by loop constants become multiplications (<= 1 ulp on the arguments)
    const double invL = 1.0 / L_MOD;
    const double nae = (F(-1.) * c2 * beta) / elm;
-   // number of levels: z_0 = zh, z_{k+1} = 1.01 z_k, stop at the first z_n > 100
-   int n = 0;
-   double z = zh;
-   while (!(z > 100)) { z = F(1.01) * z; n++; }
-   // walk back down: psi(z_k) = psi(z_{k+1}) + term(z_{k+1}) + term(z_k); the levels are regenerated by
-   // the same forward products, kept in a small window, so values are bit-identical to the recursion.
-   // term(z) = dz/2 * phim(z) * (1 - phim_hat(z)) / (z - zd),  phim_hat(z) = 1 - cm*exp(-c2*beta*(z - zd)/elm)
+   // Levels z_0 = zh, z_{k+1} = 1.01 z_k up to the first z_n > 100, where the recursion returns 0;
+   // psi(z_k) = psi(z_{k+1}) + term(z_{k+1}) + term(z_k) with
+   //    term(z) = dz/2 * phim(z) * (1 - phim_hat(z)) / (z - zd),  phim_hat(z) = 1 - cm*exp(-c2*beta*(z - zd)/elm).
+   // The recursion adds the terms from the top level down.  Walking down needs the whole ladder of z_k in
+   // (local) memory -- 2 x ~200 DRAM-backed accesses per call, 6 % of the kernel's local traffic -- so the terms
+   // are accumulated upwards instead, each level formed from the previous one in registers.  Same terms, other
+   // order of the additions: the sum differs from the recursion's by a few ulp (<= n * 2^-53 relative), far
+   // inside the 1e-10 parity tolerance (numerics).
    double psi = F(0.);
-   // Regenerating z_k from z_0 for every k would be O(n^2); instead store the ladder in chunks.
-   const int CH = 64;
-   double zl[CH];
-   int top = n;   // psi currently holds psi(z_top)
-   while (top > 0) {
-      int lo = (top > CH - 1) ? top - (CH - 1) : 0;   // rebuild z_lo .. z_top
-      double zz = zh;
-      for (int k = 0; k < lo; k++) zz = F(1.01) * zz;
-      zl[0] = zz;
-      for (int k = 1; k <= top - lo; k++) { zz = F(1.01) * zz; zl[k] = zz; }
-      double term_p;   // term(z_{k+1})
-      {
-         double zp = zl[top - lo];
-         double phim_zp = stab_phi_mom(sm, (zp - zd) * invL);
-         double phim_hat_zp = 1 - cm * exp(nae * (zp - zd));
-         term_p = dzh * phim_zp * (1 - phim_hat_zp) / (zp - zd);
-      }
-      for (int k = top - 1; k >= lo; k--) {
-         double zk = zl[k - lo];
-         double phim_z = stab_phi_mom(sm, (zk - zd) * invL);
-         double phim_hat_z = 1 - cm * exp(nae * (zk - zd));
-         double term_z = dzh * phim_z * (1 - phim_hat_z) / (zk - zd);
-         psi = psi + term_p;
-         psi = psi + term_z;
-         term_p = term_z;
-      }
-      top = lo;
+   double z = zh;
+   double term_z;
+   {
+      double phim_z = stab_phi_mom(sm, (z - zd) * invL);
+      double phim_hat_z = 1 - cm * su_exp_fast(nae * (z - zd));
+      term_z = dzh * phim_z * (1 - phim_hat_z) / (z - zd);
+   }
+   while (!(z > 100)) {
+      const double zp = F(1.01) * z;
+      double phim_zp = stab_phi_mom(sm, (zp - zd) * invL);
+      double phim_hat_zp = 1 - cm * su_exp_fast(nae * (zp - zd));
+      const double term_p = dzh * phim_zp * (1 - phim_hat_zp) / (zp - zd);
+      psi = psi + term_p;
+      psi = psi + term_z;
+      term_z = term_p;
+      z = zp;
    }
    return psi;
 }
@@ -105,7 +95,7 @@ struct SuRSL {
 
 // interp_z, rslprof.f95:315-353 (the reference's `if (idx > 0)` tests an uninitialised variable that is
 // 0 in practice: the interpolation branch is always taken)
-SU_DEV void bracket_z(double z_x, const double *z, int &idx_low, int &idx_high)
+SU_INL void bracket_z(double z_x, const double *z, int &idx_low, int &idx_high)
 {
    idx_low = -1;
    idx_high = -1;
@@ -231,13 +221,13 @@ SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD
       // level are the z terms of the level above.  c2 == c2h == 0.5 (rslprof.f95:497,549), so the momentum and
       // heat terms share one EXP per level.
       double zzp = zarray[SU_NZ - 1];
-      double ex = exp(F(-1.) * c2 * beta * (zzp - zd_RSL) / elm);
+      double ex = su_exp_fast(F(-1.) * c2 * beta * (zzp - zd_RSL) / elm);
       double tmp = dz / F(2.) * stab_phi_mom(sm, (zzp - zd_RSL) / L_MOD_RSL) * (cm * ex) / (zzp - zd_RSL);
       double thp = dz / F(2.) * stab_phi_heat(sm, (zzp - zd_RSL) / L_MOD_RSL) * (ch * ex) / (zzp - zd_RSL);
       double pm_run = 0, ph_run = 0;   // psihat at the level above
       for (int z = SU_NZ - 1; z >= idx_can; z--) {
          double zz = zarray[z - 1];
-         ex = exp(F(-1.) * c2 * beta * (zz - zd_RSL) / elm);
+         ex = su_exp_fast(F(-1.) * c2 * beta * (zz - zd_RSL) / elm);
          double tm = dz / F(2.) * stab_phi_mom(sm, (zz - zd_RSL) / L_MOD_RSL) * (cm * ex) / (zz - zd_RSL);
          double th = dz / F(2.) * stab_phi_heat(sm, (zz - zd_RSL) / L_MOD_RSL) * (ch * ex) / (zz - zd_RSL);
          pm_run = pm_run + tmp;

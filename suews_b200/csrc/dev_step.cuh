@@ -168,6 +168,8 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPa
    const double tlv = A.lv_J_kg / tstep_r;
    const double pin = SU_MAX(F(0.), R.Precip);
    double qe_per_tstep = 0, ev = 0, qe_surf = 0;
+   SuEvapTrip et;
+   evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
    T.ev_per_tstep = 0; T.surf_chang_per_tstep = 0; T.runoff_per_tstep = 0; T.state_per_tstep = 0; T.NWstate_per_tstep = 0;
    T.chSnow_per_interval = 0;
 #pragma unroll 1
@@ -191,8 +193,7 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPa
             W.SnowPack[is] = 0;
          }
       } else {
-         cal_evap(P.EvapMethod, W.state_id[is], P.WetThresh[is], cap, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa,
-                  H.ResistSurf, RA, rb, tlv, ev, qe_surf);
+         evap_surface<true>(et, W.state_id[is], P.WetThresh[is], cap, ev, qe_surf);
          double runoff_is, state_is = W.state_id[is];
          cal_water_storage(dg, is, P, C, pin, H.wu_nsurf[is], H.drain[is], H.AddWater[is], nsh_r, S.state_id[is],
                            H.AddWaterRunoff[is], PervFraction, W.fl, ev, W.soilstore_id, W.SurplusEvap, runoff_is, state_is);
@@ -214,12 +215,13 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
                            const SuLumps &Lm, const SuHoist &H, double RA, double rb, double qn_e)
 {
    const double tlv = A.lv_J_kg / (P.tstep * 1.0);
-   double qe = 0, ev, qe_surf = 0;
+   double qe = 0, ev = 0, qe_surf = 0;
+   SuEvapTrip et;
+   evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
 #pragma unroll 1
    for (int is = 0; is < NSURF; is++) {
       const double cap = (is == DECID) ? H.d.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
-      cal_evap(P.EvapMethod, S.state_id[is], P.WetThresh[is], cap, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa,
-               H.ResistSurf, RA, rb, tlv, ev, qe_surf);
+      evap_surface<false>(et, S.state_id[is], P.WetThresh[is], cap, ev, qe_surf);
       qe = qe + qe_surf * C.sfr[is];
    }
    return qe;

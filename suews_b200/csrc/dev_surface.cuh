@@ -135,6 +135,68 @@ SU_DEV void cal_evap(int EvapMethod, double state_is, double WetThresh_is, doubl
    }
 }
 
+// cal_evap evaluated for the seven surfaces of one trip.  Everything but state, WetThresh and the store
+// capacity is the same for all surfaces, so the shared sub-expressions (numPM, the dry-surface QE, rbsg,
+// rsrbsg, r, the fully-wet QE) are formed once per trip -- by the same expressions, hence the same bits --
+// instead of once per surface: 21 out-of-line calls and ~230 divisions per cell-step become ~20 divisions.
+struct SuEvapTrip {
+   double numPM, s_hPa, psyc_hPa, ResistSurf, RA, tlv;
+   double qe_dry, qe_wet1, rbsg, rsrbsg, r, qe_m1;
+   int EvapMethod;
+   bool have_dry, have_m2, have_wet1;
+};
+SU_INL void evap_trip_init(SuEvapTrip &e, int EvapMethod, double vpd_hPa, double avdens, double avcp, double qn_e,
+                           double s_hPa, double psyc_hPa, double ResistSurf, double RA, double rb, double tlv)
+{
+   e.numPM = s_hPa * qn_e + vpd_hPa * avdens * avcp / RA;
+   e.s_hPa = s_hPa; e.psyc_hPa = psyc_hPa; e.ResistSurf = ResistSurf; e.RA = RA; e.tlv = tlv;
+   e.EvapMethod = EvapMethod;
+   e.have_dry = false; e.have_m2 = false; e.have_wet1 = false;
+   e.qe_dry = 0; e.qe_wet1 = 0; e.rbsg = rb; e.rsrbsg = 0; e.r = 0;   // rbsg holds rb until the method-2 terms are formed
+   e.qe_m1 = (EvapMethod == 1) ? e.numPM / (s_hPa + psyc_hPa) : 0.0;
+}
+// qe of one surface (and ev when WANT_EV); like evap.f95, qe/ev are left untouched for an unknown EvapMethod
+template <bool WANT_EV>
+SU_INL void evap_surface(SuEvapTrip &e, double state_is, double WetThresh_is, double capStore_is, double &ev, double &qe)
+{
+   if (state_is <= F(0.001)) {
+      if (!e.have_dry) {
+         e.qe_dry = e.numPM / (e.s_hPa + e.psyc_hPa * (1 + e.ResistSurf / e.RA));
+         e.have_dry = true;
+      }
+      qe = e.qe_dry;
+      if (WANT_EV) ev = qe / e.tlv;
+   } else if (e.EvapMethod == 2) {
+      if (!e.have_m2) {
+         const double rb = e.rbsg;
+         e.rbsg = rb * (e.s_hPa / e.psyc_hPa + 1);
+         e.rsrbsg = e.ResistSurf + e.rbsg;
+         e.r = (e.ResistSurf / e.RA) * (e.RA - rb) / e.rsrbsg;
+         e.have_m2 = true;
+      }
+      if (state_is >= WetThresh_is || e.ResistSurf < 25) {
+         if (!e.have_wet1) {
+            const double W = 1;
+            double rss = (1 / ((W / e.rbsg) + ((1 - W) / e.rsrbsg))) - e.rbsg;
+            e.qe_wet1 = e.numPM / (e.s_hPa + e.psyc_hPa * (1 + rss / e.RA));
+            e.have_wet1 = true;
+         }
+         qe = e.qe_wet1;
+      } else {
+         double W = (e.r - 1) / (e.r - (WetThresh_is / state_is));
+         double rss = (1 / ((W / e.rbsg) + ((1 - W) / e.rsrbsg))) - e.rbsg;
+         qe = e.numPM / (e.s_hPa + e.psyc_hPa * (1 + rss / e.RA));
+      }
+      if (WANT_EV) ev = qe / e.tlv;
+   } else if (e.EvapMethod == 1) {
+      double ev1 = e.qe_m1 / e.tlv;
+      double x = (state_is > capStore_is) ? 1.0 : state_is / capStore_is;
+      ev1 = ev1 * x;
+      qe = ev1 * e.tlv;
+      ev = ev1;
+   }
+}
+
 // ------------------------------------------------------------------ water balance (waterdist.f95)
 // waterdist.f95:20-89
 SU_DEV double drainage(SuDiag &dg, double state_is, double StorCap, double DrainEq, double DrainCoef1, double DrainCoef2,
@@ -275,14 +337,17 @@ SU_DEV void ReDistributeWater(int snowUse, const double *WaterDist, const double
 {
    for (int ii = 0; ii < NSURF - 1; ii++) AddWaterRunoff[ii] = SU_WDIST(WaterDist, 7, ii);
    AddWaterRunoff[WATER] = 0;
-   for (int ii = 0; ii < NSURF; ii++) AddWater[ii] = 0;
+   // same accumulation order as the reference's ii/jj loops; a surface that does not drain adds an exact zero
+   // and is skipped, and the running sum of a receiving surface stays in a register
    for (int ii = 0; ii < NSURF; ii++) {
-      for (int jj = 0; jj < NSURF - 1; jj++) {
-         if (sfr[ii] != 0 && snowUse == 0) {
-            AddWater[ii] = AddWater[ii] + (Drain[jj] * sfr[jj] / sfr[ii]) * SU_WDIST(WaterDist, ii, jj);
-         } else {
-            AddWaterRunoff[jj] = AddWaterRunoff[jj] + SU_WDIST(WaterDist, ii, jj);
-         }
+      if (sfr[ii] != 0 && snowUse == 0) {
+         double a = 0;
+         for (int jj = 0; jj < NSURF - 1; jj++)
+            if (Drain[jj] != 0) a = a + (Drain[jj] * sfr[jj] / sfr[ii]) * SU_WDIST(WaterDist, ii, jj);
+         AddWater[ii] = a;
+      } else {
+         AddWater[ii] = 0;
+         for (int jj = 0; jj < NSURF - 1; jj++) AddWaterRunoff[jj] = AddWaterRunoff[jj] + SU_WDIST(WaterDist, ii, jj);
       }
    }
 }

@@ -229,6 +229,38 @@ __global__ void suews_dfma_kernel(double *out, int iters, double m)
    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// Bit-for-bit check of dev_math.cuh against the CUDA math library on pseudo-random arguments.
+__global__ void suews_math_selftest_kernel(long long n, unsigned long long seed, unsigned long long *bad)
+{
+   unsigned long long st = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(blockIdx.x * (long long)blockDim.x + threadIdx.x + 1);
+   auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+   unsigned long long be = 0, bl = 0;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const unsigned long long u = next(), v = next();
+      const double f = (double)(u >> 11) * 0x1p-53;
+      double xe, xl;
+      switch ((int)(v & 7)) {
+      case 0: xe = -760.0 + 1480.0 * f; break;                    // whole range, both tails
+      case 1: xe = -40.0 + 80.0 * f; break;                       // where the physics lives
+      case 2: xe = (f - 0.5) * 1e-3; break;
+      case 3: xe = __longlong_as_double((long long)u); break;     // any bit pattern (NaN, inf, subnormal)
+      default: xe = -20.0 * f; break;
+      }
+      switch ((int)((v >> 3) & 7)) {
+      case 0: xl = __longlong_as_double((long long)(u & 0x7fffffffffffffffull)); break;   // any non-negative pattern
+      case 1: xl = 0.5 + f; break;                                // around 1
+      case 2: xl = __longlong_as_double((long long)u); break;     // negatives, NaN
+      case 3: xl = f * 0x1p-1040; break;                          // subnormal
+      default: xl = 1e-6 + 1e6 * f * f * f; break;
+      }
+      const double a = su_exp_fast(xe), b = exp(xe), c = su_log_fast(xl), d = log(xl);
+      if (__double_as_longlong(a) != __double_as_longlong(b) && !(a != a && b != b)) be++;
+      if (__double_as_longlong(c) != __double_as_longlong(d) && !(c != c && d != d)) bl++;
+   }
+   if (be) atomicAdd(&bad[0], be);
+   if (bl) atomicAdd(&bad[1], bl);
+}
+
 __global__ void suews_sunpos_kernel(double year, double idectime, double UTC, double lat, double lng, double alt, double *out)
 {
    SuewsEphem e;
@@ -892,6 +924,22 @@ int suews_b200_device_ptrs(suews_b200_handle h, void **d_state, void **d_sums, l
    if (d_state) *d_state = h->d_state;
    if (d_sums) *d_sums = h->d_sums;
    if (cell_stride) *cell_stride = h->stride;
+   return SUEWS_OK;
+}
+
+int suews_b200_selftest_math(long long n, unsigned long long seed, long long *bad_exp, long long *bad_log)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(SUEWS_E_NO_DEVICE, "no CUDA device");
+   unsigned long long *d = nullptr, h[2] = {0, 0};
+   CUDA_OK(cudaMalloc(&d, sizeof(h)));
+   CUDA_OK(cudaMemset(d, 0, sizeof(h)));
+   suews_math_selftest_kernel<<<148 * 4, 256>>>(n, seed, d);
+   CUDA_OK(cudaGetLastError());
+   CUDA_OK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+   cudaFree(d);
+   if (bad_exp) *bad_exp = (long long)h[0];
+   if (bad_log) *bad_log = (long long)h[1];
    return SUEWS_OK;
 }
 

@@ -225,6 +225,17 @@ def test_non_converging_tsurf_loop_is_exact():
     b.close()
 
 
+def test_library_exp_log_equal_cuda_libm_bit_for_bit():
+    """dev_math.cuh restates exp/log with constant-bank coefficients; same operations, so the same bits"""
+    import ctypes as C
+    from suews_b200._lib import lib
+    L = lib()
+    L.suews_b200_selftest_math.argtypes = [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    be, bl = C.c_longlong(-1), C.c_longlong(-1)
+    assert L.suews_b200_selftest_math(200_000_000, 20261019, C.byref(be), C.byref(bl)) == 0
+    assert (be.value, bl.value) == (0, 0)
+
+
 def test_sun_position_entry_point():
     import ctypes as C
     from suews_b200 import _lib

@@ -27,12 +27,15 @@ rd = csv.DictReader(io.StringIO("\n".join(lines[start:])))
 rows = list(rd)
 base = int(rows[0]["Address"], 16)
 agg = {}
+first = {}
 for r in rows:
     off = int(r["Address"], 16) - base
     name = "kernel_body"
     for v, s, n in funcs:
         if v <= off < v + s and s < 400000:
             name = n
+    if name not in first:
+        first[name] = int(r["Instructions Executed"] or 0)   # executions of the entry instruction = warp-level calls
     a = agg.setdefault(name, [0, 0, 0, 0, 0])
     a[0] += int(r["# Samples"] or 0)
     a[1] += int(r["Instructions Executed"] or 0)
@@ -40,7 +43,9 @@ for r in rows:
     a[3] += int(r.get("stall_wait") or 0)
     a[4] += int(r.get("stall_long_sb") or 0)
 ts = sum(a[0] for a in agg.values()); ti = sum(a[1] for a in agg.values())
-print("%-46s %7s %7s %6s %6s %6s" % ("function", "samp%", "inst%", "simt", "wait%", "lsb%"))
+wsteps = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0   # warp-steps of the launch (cells/32 * timesteps)
+print("%-46s %7s %7s %6s %6s %6s %9s %9s" % ("function", "samp%", "inst%", "simt", "wait%", "lsb%", "calls/stp", "inst/call"))
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
-    print("%-46s %6.2f%% %6.2f%% %6.1f %5.1f%% %5.1f%%" % (n[:46], 100.0 * a[0] / ts, 100.0 * a[1] / ti, a[2] / max(a[1], 1),
-                                                   100.0 * a[3] / max(a[0], 1), 100.0 * a[4] / max(a[0], 1)))
+    print("%-46s %6.2f%% %6.2f%% %6.1f %5.1f%% %5.1f%% %9.2f %9.1f" % (n[:46], 100.0 * a[0] / ts, 100.0 * a[1] / ti, a[2] / max(a[1], 1),
+                                                   100.0 * a[3] / max(a[0], 1), 100.0 * a[4] / max(a[0], 1),
+                                                   first[n] / wsteps if wsteps else 0.0, a[1] / max(first[n], 1)))
