@@ -128,6 +128,8 @@ def main():
     ap.add_argument("--scheme", default="default")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sums", default="parity7", choices=["parity7", "all82"],
+                    help="on-device output reduction: P0 = running sums of the 7 parity fluxes (SURVEY 8d), or of all 82 columns")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -166,13 +168,15 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from suews_b200 import OUT_SUM82, SuewsBatch, synth
+    from suews_b200 import OUT_SUM7, OUT_SUM82, SuewsBatch, synth
     from suews_b200 import _lib
     from suews_b200.batch import all_fields
     global N_STATE, N_CELL
     N_STATE = sum(n for _nm, kind, n in all_fields() if kind == 3)
     N_CELL = sum(n for _nm, kind, n in all_fields() if kind == 2)
 
+    OUT = OUT_SUM7 if a.sums == "parity7" else OUT_SUM82
+    n_sum = 7 if a.sums == "parity7" else N_SUM
     ndays = 2 * (W + K)
     base, met = load_inputs(ndays)
     ncell = a.cells_per_gpu
@@ -190,14 +194,14 @@ def main():
     # ---------------- device-resident timing
     b.set_forcing(met[: (W + K) * 288])
     for i in range(W):
-        b.advance(i * 288, 288, OUT_SUM82, sync=False)
+        b.advance(i * 288, 288, OUT, sync=False)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0 = time.perf_counter()
     ms = []
     for i in range(W, W + K):
-        b.advance(i * 288, 288, OUT_SUM82, sync=False)
+        b.advance(i * 288, 288, OUT, sync=False)
         ms.append(b.last_ms())   # CUDA events recorded on the library's launch stream
     barrier()
     wall = time.perf_counter() - t0
@@ -221,7 +225,7 @@ def main():
             e2e_t0 = time.perf_counter()
         day = met[(W + K + i) * 288:(W + K + i + 1) * 288]
         b.set_forcing(day)                      # host -> device (pinned staging) + ephemeris kernel
-        b.advance(0, 288, OUT_SUM82, sync=False)
+        b.advance(0, 288, OUT, sync=False)
         res = b.sums_cols(cols)                 # device -> host (pinned staging), waits for the kernel
     barrier()
     e2e_s = time.perf_counter() - e2e_t0
@@ -245,7 +249,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     # algorithmic bytes per launch: state read+write, cell params read, sums read+write, per cell; forcing shared
-    bytes_per_launch = ncell * 8.0 * (2 * N_STATE + N_CELL + 2 * N_SUM) + 288 * 160.0
+    bytes_per_launch = ncell * 8.0 * (2 * N_STATE + N_CELL + 2 * n_sum) + 288 * 160.0
     launch_s = dev_s / K
     ach_gbs = bytes_per_launch / launch_s / 1e9
     prof = {}
@@ -268,7 +272,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "cells_per_gpu": ncell, "timesteps_per_step": 288, "output_policy": "per-cell sums of all 82 SUEWS columns (P0+)",
+        "config": {"workload": workload, "cells_per_gpu": ncell, "timesteps_per_step": 288, "output_policy": ("P0: per-cell running sums of the 7 parity fluxes QN,QF,QS,QH,QE,RO,SWE" if a.sums == "parity7"
+                                     else "P0+: per-cell running sums of all 82 SUEWS columns"),
                    "l2": "inputs (state+params %.0f MB/GPU) larger than L2" % (ncell * 8.0 * (N_STATE + N_CELL + N_SUM) / 1e6),
                    "tsurf_iterations_per_step": float(iters.sum()) / (ncell * 288.0 * (2 * (W + K))), "wall_s_timed": wall,
                    "checksum_QN": checksum, "fatal_cells": int((fatal != 0).sum())},
@@ -276,7 +281,7 @@ def main():
         "gpu_launches": K,
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "traffic": (prof["dram_bytes_per_cell_step"] * ncell * 288.0 if "dram_bytes_per_cell_step" in prof else None), "peak_source": peak_src,
                      "note": "kernel is FP64-pipe / latency bound, not HBM bound (SURVEY 8d); see fp64"},
         "fp64": fp64,
     }

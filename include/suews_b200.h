@@ -48,7 +48,9 @@ enum { SUEWS_KIND_CLASS_INT = 0, SUEWS_KIND_CLASS_DBL = 1, SUEWS_KIND_CELL_DBL =
 /* output policy bits for suews_b200_advance */
 enum {
    SUEWS_OUT_SUM82 = 1,   /* accumulate per-cell sums of the 82 SUEWS columns over the advanced steps */
-   SUEWS_OUT_FULL = 2     /* keep every output block of every step (reference SUEWS_cal_multitsteps semantics) */
+   SUEWS_OUT_FULL = 2,    /* keep every output block of every step (reference SUEWS_cal_multitsteps semantics) */
+   SUEWS_OUT_SUM7 = 4     /* accumulate only the seven parity fluxes QN, QF, QS, QH, QE, RO, SWE (columns 5-9, 16, 71
+                             of the same [ncell][82] sums array; the other columns are left untouched) */
 };
 
 /* ---- batched device API -------------------------------------------------------------------- */

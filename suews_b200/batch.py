@@ -14,6 +14,7 @@ from ._lib import check, dp, ip
 NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50}
 OUT_SUM82 = 1
 OUT_FULL = 2
+OUT_SUM7 = 4   # only the seven parity fluxes (output policy P0)
 
 KIND_CLASS_INT, KIND_CLASS_DBL, KIND_CELL, KIND_STATE = 0, 1, 2, 3
 

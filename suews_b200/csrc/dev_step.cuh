@@ -232,7 +232,7 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
 // Returns the number of Tsurf iterations used.
 __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
-                          SuewsCellState &S, double *acc82, const SuLines &L)
+                          SuewsCellState &S, double *acc82, double *acc7, const SuLines &L)
 {
    const double *sfr = C.sfr.v;
    const int sm = P.StabilityMethod;
@@ -487,6 +487,12 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    S.lv_switch = (double)lv_sw;
    S.alb1_hidden = Rd.alb1;
 
+   // output policy P0: running sums of the seven parity fluxes only -- QN, QF, QS, QH, QE, RO, SWE,
+   // the same values the 82-column line carries in columns 6-10, 17 and 72
+   if (acc7) {
+      acc7[0] += qn1; acc7[1] += qf; acc7[2] += qs; acc7[3] += qh; acc7[4] += qe;
+      acc7[5] += QT.runoff_per_tstep; acc7[6] += W.swe;
+   }
    // SUEWS_update_outputLine driver.f95:2273-2457
    if (acc82 || L.suews82) {
       int k = 0;

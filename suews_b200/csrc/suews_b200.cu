@@ -50,6 +50,7 @@ struct SuRunArgs {
    const SuewsEphem *ephem;     // [ntz][nsteps_total], offset to step0 inside
    long long ephem_tz_stride;
    double *sums;                // [82][stride] or NULL
+   int sum7;                    // 1: accumulate only the seven parity columns (SUEWS_OUT_SUM7)
    int *fatal;                  // [ncell]
    unsigned long long *warn;    // [2][stride]
    long long *iters;            // [ncell]
@@ -60,6 +61,12 @@ struct SuRunArgs {
    int nsteps;
    int dt_since_start, tstep_prev, tstep;
 };
+
+// QN, QF, QS, QH, QE, RO, SWE in the 82-column SUEWS line (0-based)
+__host__ __device__ __forceinline__ int su_parity_col(int i)
+{
+   return i < 5 ? 5 + i : (i == 5 ? 16 : 71);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
    SuDiag dg;
    dg.fatal = 0; dg.warn[0] = 0; dg.warn[1] = 0;
    double acc[SUEWS_NCOL_SUEWS];
+   double acc7[7] = {0, 0, 0, 0, 0, 0, 0};
    long long iters = 0;
    int cls = 0, tz = 0;
    if (active) {
@@ -147,9 +155,11 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
       dg.fatal = a.fatal[cell];
       dg.warn[0] = a.warn[cell];
       dg.warn[1] = a.warn[a.stride + cell];
-      if (a.sums) {
+      if (a.sums && !a.sum7) {
 #pragma unroll 1
          for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = a.sums[(size_t)c * a.stride + cell];
+      } else if (a.sums) {
+         for (int c = 0; c < 7; c++) acc7[c] = a.sums[(size_t)su_parity_col(c) * a.stride + cell];
       }
    }
    const SuewsClassParams &P = a.classes[cls];
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
          if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; }
          // every thread of the block enters the step (phase barriers inside); only live cells compute
          iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
-                             a.sums ? acc : nullptr, L);
+                             (a.sums && !a.sum7) ? acc : nullptr, (a.sums && a.sum7) ? acc7 : nullptr, L);
          if (FULL && live && dg.fatal == 0) {
             const size_t n = (size_t)a.nsteps;
             double *b;
@@ -211,9 +221,11 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
       a.warn[cell] = dg.warn[0];
       a.warn[a.stride + cell] = dg.warn[1];
       a.iters[cell] += iters;
-      if (a.sums) {
+      if (a.sums && !a.sum7) {
 #pragma unroll 1
          for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) a.sums[(size_t)c * a.stride + cell] = acc[c];
+      } else if (a.sums) {
+         for (int c = 0; c < 7; c++) a.sums[(size_t)su_parity_col(c) * a.stride + cell] = acc7[c];
       }
    }
 }
@@ -743,7 +755,8 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.steps = h->d_steps + step0;
    a.ephem = h->d_ephem + step0;
    a.ephem_tz_stride = h->nsteps;
-   a.sums = (out_flags & SUEWS_OUT_SUM82) ? h->d_sums : nullptr;
+   a.sums = (out_flags & (SUEWS_OUT_SUM82 | SUEWS_OUT_SUM7)) ? h->d_sums : nullptr;
+   a.sum7 = ((out_flags & SUEWS_OUT_SUM7) && !(out_flags & SUEWS_OUT_SUM82)) ? 1 : 0;
    a.fatal = h->d_fatal; a.warn = h->d_warn; a.iters = h->d_iters;
    a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3];
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;

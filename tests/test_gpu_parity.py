@@ -92,6 +92,22 @@ def test_flux_sums_and_state(gpu_and_ref_2005):
     assert sw == int(sd["lv_switch1"][0]) + 2 * int(sd["lv_switch2"][0])
 
 
+def test_parity_sums_policy_equals_full_sums(gpu_and_ref_2005):
+    """output policy P0 (seven parity fluxes) accumulates exactly what the 82-column policy holds in those columns"""
+    from suews_b200 import OUT_SUM7, SuewsBatch
+    b1, _ref, _cell, met = gpu_and_ref_2005
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(fx.state_init(2005))
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, met.shape[0], OUT_SUM7)
+    cols = list(PARITY_COLS.values())
+    assert np.array_equal(b.sums()[:, cols], b1.sums()[:, cols])
+    other = [c for c in range(82) if c not in cols]
+    assert np.all(b.sums()[:, other] == 0.0)
+    b.close()
+
+
 def test_chunked_advance_equals_single_launch(gpu_and_ref_2005):
     """state carried across launches == one long launch (the persistent-state contract)"""
     from suews_b200 import OUT_SUM82, SuewsBatch

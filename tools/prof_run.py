@@ -6,7 +6,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
-from suews_b200 import OUT_SUM82, SuewsBatch, synth
+from suews_b200 import OUT_SUM7, OUT_SUM82, SuewsBatch, synth
+OUT = OUT_SUM82 if os.environ.get('SU_SUMS', '7') == '82' else OUT_SUM7   # output policy of the profiled launches
 
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 37888
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 48
@@ -18,7 +19,7 @@ synth.build_batch(b, base, scheme=scheme)
 b.upload()
 b.set_forcing(met[: row0 + 3 * nsteps])
 if row0 > 0:
-    b.advance(0, row0, OUT_SUM82)
+    b.advance(0, row0, OUT)
 import ctypes as C
 from suews_b200._lib import lib
 PH = ["P0 geometry/daily", "P1 moist air+hoisted", "L1 rad/OHM/melt", "L2 stab/resist", "L3 QE/QH/Tsfc", "F1 water balance",
@@ -28,7 +29,7 @@ has_clk = hasattr(lib(), "suews_b200_debug_phase_clocks")
 for i in range(3):
     if has_clk:
         lib().suews_b200_debug_phase_clocks(clk, 1)
-    b.advance(row0 + i * nsteps, nsteps, OUT_SUM82)
+    b.advance(row0 + i * nsteps, nsteps, OUT)
     print("launch %d: %.2f ms -> %.3e cell-steps/s" % (i, b.last_ms(), ncell * nsteps / (b.last_ms() * 1e-3)))
     if has_clk:
         lib().suews_b200_debug_phase_clocks(clk, 0)
