@@ -148,7 +148,7 @@ SU_DEV void cal_AtmMoist(SuDiag &dg, double &Temp_C, double Press_hPa, double av
    a.es_hPa = sat_vap_press_x(dg, Temp_C, Press_hPa, 1);
    a.Ea_hPa = avRh / 100 * a.es_hPa;
    a.VPd_hpa = a.es_hPa - a.Ea_hPa;
-   a.dq = F(621.97) * a.VPd_hpa / Press_hPa;   // spec_hum_def, meteo.f95:235
+   a.dq = su_div0(F(621.97) * a.VPd_hpa, Press_hPa);   // spec_hum_def, meteo.f95:235
    double vap_dens = (a.Ea_hPa * 100 / ((Temp_C + F(273.16)) * gas_ct_wv));
    double dens_dry = ((Press_hPa - a.Ea_hPa) * 100) / (gas_ct_dry * (F(273.16) + Temp_C));
    a.avdens = (Press_hPa * 100) / (gas_ct_dry * (Temp_C + F(273.16)));
@@ -277,18 +277,20 @@ SU_INL double stab_phi_heat(int sm, double zl)
 // atmmoiststab.f95:104-248: fixed-point iteration for the Obukhov length (<= 329 trips).
 // log(zzd/z0m) is loop-invariant and evaluated once.
 SU_DEVNI void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double avU1, double Temp_C, double QH_init,
-                       double avdens, double avcp, double &L_MOD, double &TStar, double &UStar, double &zL)
+                       double avdens, double avcp, double &L_MOD_out, double &TStar_out, double &UStar_out, double &zL_out)
 {
+   // the iteration runs on register copies; the by-reference results (stack slots of the caller) are written once
    const double k = F(0.4), grav = F(9.80665);
    double H_init = QH_init / (avdens * avcp);
    double G_T_K = (grav / (Temp_C + F(273.16))) * k;
    double KUZ = k * avU1;
    if (zzd < 0) su_fatal(dg, 32);
    const double lg = log(zzd / z0m);
-   UStar = KUZ / lg;
+   double UStar = KUZ / lg;
    double h = (fabs(H_init) < F(0.001)) ? F(0.001) : H_init;
-   TStar = (-h / UStar);
-   L_MOD = (UStar * UStar) / (G_T_K * TStar);
+   double TStar = (-h / UStar);
+   double L_MOD = (UStar * UStar) / (G_T_K * TStar);
+   double zL = zL_out;
    if (lg < F(0.001000)) su_fatal(dg, 17);
    int i = 1;
    double LOLD = F(-999.), z0L, psim, psimz0;
@@ -312,6 +314,7 @@ SU_DEVNI void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double avU1, 
    UStar = KUZ / (lg - psim + psimz0);
    UStar = SU_MAX(F(0.15), UStar);
    TStar = (-h / UStar);
+   L_MOD_out = L_MOD; TStar_out = TStar; UStar_out = UStar; zL_out = zL;
 }
 
 // ------------------------------------------------------------------ resistances
@@ -383,7 +386,7 @@ SU_DEV void SurfaceResistance(SuDiag &dg, const SuewsClassParams &P, const doubl
          gq = (avkdn / (G2 + avkdn)) / QNM;
          gdq = (dq < G4) ? 1 - G3 * dq : 1 - G3 * G4;
       } else {
-         gq = (avkdn / (avkdn + G2)) / QNM;
+         gq = su_div0(su_div0(avkdn, avkdn + G2), QNM);
          if (avkdn >= Kmax) gq = 1;
          gdq = G3 + (1 - G3) * pow(G4, dq);
       }

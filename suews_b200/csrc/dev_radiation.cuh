@@ -310,7 +310,7 @@ SU_DEVNI void NARP(const double *sfr, const double *SnowFrac, const double *alb,
 
       if (SF_all != 0) qsf = qsf + QSTAR * sfr[is] * (1 - SnowFrac[is]) / SF_all;
       else qsf = qsf + QSTAR * sfr[is] * (1 - SnowFrac[is]);
-      if ((1 - SF_all) != 0) qs = qs + QSTAR_SNOW * sfr[is] * SnowFrac[is] / (1 - SF_all);
+      if ((1 - SF_all) != 0) qs = qs + su_div0(QSTAR_SNOW * sfr[is] * SnowFrac[is], 1 - SF_all);
       else qs = qs + QSTAR_SNOW * sfr[is] * SnowFrac[is];
 
       double qn1_is = QSTAR * (1 - SnowFrac[is]) + QSTAR_SNOW * SnowFrac[is];

@@ -148,7 +148,7 @@ struct SuEvapTrip {
 SU_INL void evap_trip_init(SuEvapTrip &e, int EvapMethod, double vpd_hPa, double avdens, double avcp, double qn_e,
                            double s_hPa, double psyc_hPa, double ResistSurf, double RA, double rb, double tlv)
 {
-   e.numPM = s_hPa * qn_e + vpd_hPa * avdens * avcp / RA;
+   e.numPM = s_hPa * qn_e + su_div0(vpd_hPa * avdens * avcp, RA);
    e.s_hPa = s_hPa; e.psyc_hPa = psyc_hPa; e.ResistSurf = ResistSurf; e.RA = RA; e.tlv = tlv;
    e.EvapMethod = EvapMethod;
    e.have_dry = false; e.have_m2 = false; e.have_wet1 = false;
@@ -177,8 +177,8 @@ SU_INL void evap_surface(SuEvapTrip &e, double state_is, double WetThresh_is, do
       if (state_is >= WetThresh_is || e.ResistSurf < 25) {
          if (!e.have_wet1) {
             const double W = 1;
-            double rss = (1 / ((W / e.rbsg) + ((1 - W) / e.rsrbsg))) - e.rbsg;
-            e.qe_wet1 = e.numPM / (e.s_hPa + e.psyc_hPa * (1 + rss / e.RA));
+            double rss = (1 / ((W / e.rbsg) + su_div0(1 - W, e.rsrbsg))) - e.rbsg;
+            e.qe_wet1 = e.numPM / (e.s_hPa + e.psyc_hPa * (1 + su_div0(rss, e.RA)));
             e.have_wet1 = true;
          }
          qe = e.qe_wet1;
@@ -309,7 +309,7 @@ SU_DEV void cal_water_storage(SuDiag &dg, int is, const SuewsClassParams &P, con
       }
    } else if (is == WATER) {
       if (sfr[WATER] != 0) {
-         chang = p_mm + C.FlowChange / nsh_real - ev;
+         chang = p_mm + su_div0(C.FlowChange, nsh_real) - ev;
          state_is = stateOld_is + chang;
          if (state_is < F(0.0)) {
             ev = ev - fabs(state_is);
@@ -369,7 +369,7 @@ SU_DEV void update_SoilMoist(double NonWaterFraction, const double *SoilStoreCap
    vsmd = 0;
    double vf = sfr[CONIF] + sfr[DECID] + sfr[GRASS];
    if (vf != 0)
-      for (int is = CONIF; is <= GRASS; is++) vsmd = vsmd + (SoilStoreCap[is] - soilstore_id[is]) * sfr[is] / vf;
+      for (int is = CONIF; is <= GRASS; is++) vsmd = vsmd + su_div0((SoilStoreCap[is] - soilstore_id[is]) * sfr[is], vf);
 }
 
 // waterdist.f95:553-619
@@ -438,11 +438,12 @@ SU_DEVNI void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *s
                vg_store(soilstore_id[jj], P.SoilStoreCap[jj], P.SoilDepth[jj], P.SatHydraulicConduct[jj], MatPot2, Km2);
                double Distance = (rt[is] + rt[jj]) / 2;
                double KmWeight = (sfr[is] * Km1 + sfr[jj] * Km2) / (sfr[is] + sfr[jj]);
-               double dI_dt = -(KmWeight) * (-MatPot1 + MatPot2) / (Distance * 1000);
+               double dI_dt = su_div0(-(KmWeight) * (-MatPot1 + MatPot2), Distance * 1000);
                double dI = dI_dt * tstep_real;
-               if ((soilstore_id[jj] >= dI * sfr[is] / sfr[jj]) && ((soilstore_id[is] + dI) >= 0)) {
+               const double dI_jj = su_div0(dI * sfr[is], sfr[jj]);
+               if ((soilstore_id[jj] >= dI_jj) && ((soilstore_id[is] + dI) >= 0)) {
                   soilstore_id[is] = soilstore_id[is] + dI;
-                  soilstore_id[jj] = soilstore_id[jj] - dI * sfr[is] / sfr[jj];
+                  soilstore_id[jj] = soilstore_id[jj] - dI_jj;
                } else if ((soilstore_id[is] + dI) < 0) {
                   soilstore_id[jj] = soilstore_id[jj] + soilstore_id[is] * sfr[is] / sfr[jj];
                   soilstore_id[is] = 0;
@@ -460,7 +461,7 @@ SU_DEVNI void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *s
                }
             }
          }
-         runoffSoil_per_tstep = runoffSoil_per_tstep + (runoffSoil[is] * sfr[is] / NonWaterFraction);
+         runoffSoil_per_tstep = runoffSoil_per_tstep + su_div0(runoffSoil[is] * sfr[is], NonWaterFraction);
       }
    }
 }
@@ -471,7 +472,7 @@ SU_DEVNI void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *s
 SU_INL double prof_inst(int Hour, int Min, const double *p24)
 {
    int j = (Hour + 1 == 24) ? 0 : Hour + 1;
-   double deltaProf = (p24[j] - p24[Hour]) / 3600;
+   double deltaProf = su_div0(p24[j] - p24[Hour], 3600.0);
    return p24[Hour] + deltaProf * (Min * 60);
 }
 SU_INL double prof_mean(int Hour, int Min, const double *p24, double sum24)
@@ -483,7 +484,7 @@ SU_INL double prof_mean(int Hour, int Min, const double *p24, double sum24)
       pi_ = p24[Hour] / m;
       pj_ = p24[j] / m;
    }
-   double deltaProf = (pj_ - pi_) / 3600;
+   double deltaProf = su_div0(pj_ - pi_, 3600.0);
    return pi_ + deltaProf * (Min * 60);
 }
 SU_INL double prof_sum(int Hour, int Min, const double *p24, double sum24, int dt)
@@ -534,7 +535,7 @@ SU_DEV void cal_WaterUse(const SuewsClassParams &P, const SuewsCellParams &C, do
       for (int is = 0; is < NSURF; is++) wu_nsurf[is] = wu_nsurf[is] * IrrFrac[is];
       for (int is = 0; is < NSURF; is++) wu += wu_nsurf[is] * sfr[is];
    }
-   double InternalWaterUse = P.InternalWaterUse_h / nsh_real;
+   double InternalWaterUse = su_div0(P.InternalWaterUse_h, nsh_real);
    wu_ext = wu - (InternalWaterUse + OverUse);
    if (wu_ext < 0) wu_ext = 0;
    wu_int = wu - wu_ext;
@@ -606,7 +607,7 @@ SU_DEV void cal_AnthropogenicEmission(SuDiag &dg, const SuewsClassParams &P, con
       Fc_build = heat * P.FrFossilFuel_Heat * P.EF_umolCO2perJ;
       if ((base - QF_metab) > 0) Fc_build = Fc_build + base * C.QF0_BEU[u] * P.FrFossilFuel_NonHeat * P.EF_umolCO2perJ;
       QF_traff = base * (F(1.0) - C.QF0_BEU[u]) - QF_metab;
-      Fc_traff = QF_traff / P.EnEF_v_Jkm * P.FcEF_v_kgkm[u] * F(1e3) * F(1e6) / 44;
+      Fc_traff = su_div0(su_div0(QF_traff, P.EnEF_v_Jkm) * P.FcEF_v_kgkm[u] * F(1e3) * F(1e6), 44.0);
       Fc_point = (P.CO2PointSource > 0) ? P.CO2PointSource * F(1e3) * F(1e6) / (12 * 60 * 60 * 24 * C.SurfaceArea) : 0.0;
    } else if (em_in(EM, 4, 6)) {
       if (P.TrafficUnits == 1) {
