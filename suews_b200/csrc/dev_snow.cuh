@@ -321,9 +321,15 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
             SnowWater[is] = SnowWater[is] + rainOnSnow;
          }
          SnowPack[is] = SnowPack[is] + changSnow;
-         if (Precip > 0 && FreezState == state_id[is]) snowFracFresh1 = 1;
-         else if (Precip == 0 && FreezState > 0 && FreezState == state_id[is]) snowFracFresh1 = 1;
-         else if (FreezState > 0 && FreezState < state_id[is]) snowFracFresh1 = F(0.95);
+         {   // snow.f95:810-820.  Written with named conditions: as an if / else-if / else-if chain on the array
+             // element, nvcc 12.9 (sm_100a, -O3) dropped the third assignment (found by the 2004 annual parity run).
+            const double st_now = state_id[is];
+            const bool c1 = (Precip > 0 && FreezState == st_now);
+            const bool c2 = (Precip == 0 && FreezState > 0 && FreezState == st_now);
+            const bool c3 = (FreezState > 0 && FreezState < st_now);
+            if (c1 || c2) snowFracFresh1 = 1;
+            else if (c3) snowFracFresh1 = F(0.95);
+         }
       } else if (SnowPack[is] == 0 && Tsurf_ind[is] < 0) {
          if ((Precip > 0 && state_id[is] == 0) || (Precip == 0 && FreezState == state_id[is]) ||
              (Precip > 0 && FreezState == state_id[is])) {

@@ -426,10 +426,12 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
             // state after trip n equals, bit for bit, the state after trip n-2, trips n+1.. repeat trips n-1,n..
             // exactly, so the state after trip 99 is the one after trip n (99-n even) or n+1 (99-n odd).
             const int n = i_iter - 1;
+#ifndef SU_NO_CYCLE
             if (n >= 4 && qh == cyc_qh[0] && Ts_iter == cyc_ts[0] && lv_sw == cyc_sw[0] && Rd.alb1 == cyc_alb[0]) {
                if (((99 - n) & 1) == 0) { done = true; i_iter = 100; }
                else i_iter = 99;   // one more trip, which then ends the loop as the 99th
             }
+#endif
             cyc_qh[0] = cyc_qh[1]; cyc_ts[0] = cyc_ts[1]; cyc_sw[0] = cyc_sw[1]; cyc_alb[0] = cyc_alb[1];
             cyc_qh[1] = qh; cyc_ts[1] = Ts_iter; cyc_sw[1] = lv_sw; cyc_alb[1] = Rd.alb1;
          }

@@ -164,6 +164,48 @@ def test_scheme_options_match_oracle(scheme_over):
     assert e.max() <= TOL_DAY1, (scheme_over, float(e.max()), np.unravel_index(e.argmax(), e.shape))
 
 
+@pytest.mark.parametrize("scheme_over", [
+    dict(), dict(snowuse=0), dict(netradiationmethod=3), dict(netradiationmethod=1), dict(netradiationmethod=11),
+    dict(netradiationmethod=100), dict(netradiationmethod=0), dict(stabilitymethod=2), dict(stabilitymethod=4),
+    dict(roughlenheatmethod=1), dict(roughlenmommethod=1), dict(emissionsmethod=2), dict(evapmethod=1),
+    dict(storageheatmethod=0), dict(smdmethod=1), dict(waterusemethod=1), dict(aerodynamicresistancemethod=1),
+])
+def test_scheme_options_winter_start(scheme_over):
+    """The same option sweep from the 2004 dump: sub-zero air, snow on the ground, freezing surface water and
+    rain in the first days -- the snow/freeze branches the mild 2005 start never enters.  Three days."""
+    from suews_b200 import OUT_FULL, SuewsBatch
+    d = fx.state_init(2004)
+    for k, v in scheme_over.items():
+        d[k] = [v]
+    if scheme_over.get("snowuse", 1) == 0:
+        for k in ("snowpack", "snowfrac", "snowwater"):
+            d[k] = [0.0] * 7
+    n = 3 * 288
+    met = fx.forcing(2004)[:n].copy()
+    if scheme_over.get("smdmethod", 0) > 0:
+        met[:, 19] = 30.0
+    ref = ol.Cell(d).run(met, want=("SUEWS", "snow"))
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, n, OUT_FULL)
+    groups = ("SUEWS", "snow") if d["snowuse"][0] == 1 else ("SUEWS",)
+    for g in groups:
+        out = b.block(g, 0, n)
+        assert np.array_equal(out[:, :5], ref[g][:, :5])
+        e = rel_err(out[:, 5:], ref[g][:, 5:], g)
+        assert e[:288].max() <= TOL_DAY1, (scheme_over, g, float(e[:288].max()), np.unravel_index(e[:288].argmax(), e[:288].shape))
+        # beyond day 1 a last-ulp libm difference can flip the Tsurf loop's |dT| > 0.1 test for one step
+        # (one trip more or less); the north_star bounds those days through the flux sums
+        assert e.max() <= 1e-6, (scheme_over, g, float(e.max()), np.unravel_index(e.argmax(), e.shape))
+        if g == "SUEWS":
+            so, sr = out[:, 5:].sum(axis=0), ref[g][:, 5:].sum(axis=0)
+            for nm, c in PARITY_COLS.items():
+                assert abs(so[c] - sr[c]) <= TOL_SUM * max(abs(sr[c]), 1e-30), (scheme_over, nm)
+    b.close()
+
+
 def test_many_cells_match_per_cell_oracle():
     """Synthetic multi-cell batch (perturbed fractions, location, morphology, forcing offsets): every
     cell equals its own single-cell oracle run -- the reference's multi-grid == single-grid property
@@ -239,6 +281,60 @@ def test_non_converging_tsurf_loop_is_exact():
             assert e.max() <= TOL_DAY1, (c, g, float(e.max()), np.unravel_index(e.argmax(), e.shape))
     assert n99 >= 20, n99      # the case under test really occurs in this window
     b.close()
+
+
+def test_annual_flux_sums_match_oracle():
+    """north_star: 1e-6 relative on annual flux sums (QN, QF, QS, QH, QE, runoff, SWE).  Full leap year 2004
+    (105 408 five-minute steps) from the 2004 state_init dump, snow on; plus the end-of-year state."""
+    from suews_b200 import OUT_SUM7, SuewsBatch
+    d = fx.state_init(2004)
+    met = fx.forcing(2004)
+    assert met.shape[0] == 366 * 288
+    cell = ol.Cell(d)
+    ref = cell.run(met, want=("SUEWS",))["SUEWS"][:, 5:]
+    b = SuewsBatch(1, 1)
+    assert b.load_reference_args(d) == []
+    b.upload()
+    b.set_forcing(met)
+    for day0 in range(0, 366, 61):                      # six launches of 61 days: state carried on the device
+        b.advance(day0 * 288, 61 * 288, OUT_SUM7)
+    sums = b.sums()[0]
+    rs = ref.sum(axis=0)
+    for nm, c in PARITY_COLS.items():
+        assert abs(sums[c] - rs[c]) <= TOL_SUM * max(abs(rs[c]), 1e-30), (nm, sums[c], rs[c])
+    fatal, _w, iters = b.diag()
+    assert fatal[0] == 0
+    for nm, v in cell.state_dict().items():
+        if nm in ("dt_since_start", "tstep_prev", "lv_switch1", "lv_switch2"):
+            continue
+        assert np.allclose(b.get_state(nm)[0], v, rtol=1e-7, atol=1e-9), nm
+    b.close()
+
+
+def test_replicated_cells_equal_single_cell():
+    """BASELINE configs[1]: the BaseRun cell replicated to 10 000 grids -- the reference's multi-grid == single-grid
+    property (Test/code/Test_SUEWS.py:384), here bit for bit"""
+    from suews_b200 import OUT_SUM82, SuewsBatch
+    d = fx.state_init(2005)
+    met = fx.forcing(2005)[:288]
+    n = 10000
+    b = SuewsBatch(n, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, 288, OUT_SUM82)
+    sums = b.sums()
+    assert np.array_equal(sums, np.broadcast_to(sums[0], sums.shape))
+    st = b.get_state("state_id")
+    assert np.array_equal(st, np.broadcast_to(st[0], st.shape))
+    b1 = SuewsBatch(1, 1)
+    b1.load_reference_args(d)
+    b1.upload()
+    b1.set_forcing(met)
+    b1.advance(0, 288, OUT_SUM82)
+    assert np.array_equal(b1.sums()[0], sums[0])
+    b.close()
+    b1.close()
 
 
 def test_library_exp_log_equal_cuda_libm_bit_for_bit():
