@@ -36,11 +36,37 @@ SU_DEVNI double su_pow_general(double x, double y) { return pow(x, y); }
 // Tsurf and van Genuchten -- go through DSQRT / rsqrt (<= 1.25 ulp) instead of the ~400-instruction general
 // pow: the second profile had pow at 45 % of all executed instructions.  Literal exponents fold at compile
 // time; run-time exponents (LAIPower, drainage coefficients, ...) take the same route when they match.
+// x^(-1/4), the unstable-side phi of every stability scheme: single-precision seed (two MUFU ops) and two
+// Newton steps y <- y (5 - x y^4) / 4 in double (quadratic: 2^-22 -> 1e-13 -> rounding), <= 2 ulp, a third of the
+// instructions of rsqrt(sqrt(x)).  Outside the single-precision range the exact pair is used.
+SU_INL double su_rqrt4(double x)
+{
+   if (!(x > 1e-30 && x < 1e30)) return rsqrt(sqrt(x));
+   double y = (double)rsqrtf(sqrtf((float)x));
+   const double qx = 0.25 * x;
+   double y2 = y * y;
+   y = y * __fma_rn(-qx, y2 * y2, 1.25);
+   y2 = y * y;
+   y = y * __fma_rn(-qx, y2 * y2, 1.25);
+   return y;
+}
+// 1 / d for a normal d of ordinary magnitude: hardware seed + two Newton steps, <= 1 ulp (not correctly rounded;
+// used only inside the psi-hat integrations of dev_rsl.cuh, see DESIGN.md "numerics")
+SU_INL double su_rcp_fast(double d)
+{
+   double r;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+   double e = __fma_rn(-d, r, 1.0);
+   r = __fma_rn(r, e, r);
+   e = __fma_rn(-d, r, 1.0);
+   r = __fma_rn(r, e, r);
+   return r;
+}
 SU_INL double su_pow(double x, double y)
 {
    if (y == 0.5) return sqrt(x);
    if (y == 0.25) return sqrt(sqrt(x));
-   if (y == -0.25) return rsqrt(sqrt(x));
+   if (y == -0.25) return su_rqrt4(x);
    if (y == -0.5) return rsqrt(x);
    if (y == 1.5) return x * sqrt(x);
    return su_pow_general(x, y);

@@ -55,22 +55,24 @@ SU_DEVNI double cal_psim_hat_zh(int sm, double zh, double L_MOD, double beta, do
    // inside the 1e-10 parity tolerance (numerics).
    double psi = F(0.);
    double z = zh;
-   double term_z;
-   {
-      double phim_z = stab_phi_mom(sm, (z - zd) * invL);
-      double phim_hat_z = 1 - cm * su_exp_fast(nae * (z - zd));
-      term_z = dzh * phim_z * (1 - phim_hat_z) / (z - zd);
-   }
+   // term(z) with the division by (z - zd) as a multiplication by a Newton reciprocal (<= 1 ulp)
+#define SU_PSIHAT_TERM(zz_) (dzh * stab_phi_mom(sm, ((zz_) - zd) * invL) * (1 - (1 - cm * su_exp_fast(nae * ((zz_) - zd)))) * su_rcp_fast((zz_) - zd))
+   double term_z = SU_PSIHAT_TERM(z);
+   // two levels per pass: their evaluations are independent, which gives the FP64 pipe two chains to overlap
    while (!(z > 100)) {
-      const double zp = F(1.01) * z;
-      double phim_zp = stab_phi_mom(sm, (zp - zd) * invL);
-      double phim_hat_zp = 1 - cm * su_exp_fast(nae * (zp - zd));
-      const double term_p = dzh * phim_zp * (1 - phim_hat_zp) / (zp - zd);
-      psi = psi + term_p;
+      const double z1 = F(1.01) * z;
+      const double z2 = F(1.01) * z1;
+      const double t1 = SU_PSIHAT_TERM(z1);
+      const double t2 = SU_PSIHAT_TERM(z2);
+      psi = psi + t1;
       psi = psi + term_z;
-      term_z = term_p;
-      z = zp;
+      if (z1 > 100) { z = z1; break; }
+      psi = psi + t2;
+      psi = psi + t1;
+      term_z = t2;
+      z = z2;
    }
+#undef SU_PSIHAT_TERM
    return psi;
 }
 
