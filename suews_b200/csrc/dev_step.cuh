@@ -144,18 +144,20 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPa
                         const SuewsCellState &S, const SuAtm &A, const SuLumps &Lm, const SuHoist &H, const SuSnowHeat &Hs,
                         const double *Tsurf_ind, const double *SnowPack_m, const double *SnowFrac_q,
                         const double *SnowDens_m, double Temp_C, double avRh, double RA, double RAsnow, double rb,
-                        double qn_e, double PervFraction, double VegFraction, double NonWaterFraction, SuQEWork &W,
-                        SuQETot &T)
+                        double qn_e, double PervFraction, double VegFraction, double NonWaterFraction, bool snow_arrays,
+                        SuQEWork &W, SuQETot &T)
 {
    const double *sfr = C.sfr.v;
    for (int is = 0; is < NSURF; is++) {
       W.state_id[is] = S.state_id[is];
       W.soilstore_id[is] = S.soilstore_id[is];
-      W.SnowPack[is] = SnowPack_m[is];
-      W.SnowFrac[is] = SnowFrac_q[is];
-      W.SnowWater[is] = S.SnowWater[is];
-      W.iceFrac[is] = S.IceFrac[is];
-      W.SnowDens[is] = SnowDens_m[is];
+      if (snow_arrays) {
+         W.SnowPack[is] = SnowPack_m[is];
+         W.SnowFrac[is] = SnowFrac_q[is];
+         W.SnowWater[is] = S.SnowWater[is];
+         W.iceFrac[is] = S.IceFrac[is];
+         W.SnowDens[is] = SnowDens_m[is];
+      }
       W.SurplusEvap[is] = 0;
       W.runoffSoil[is] = 0;
    }
@@ -276,6 +278,9 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    double lv_memo[4];
    int lv_exit[4] = {-1, -1, -1, -1};
    bool rad_invariant = false, rad_done = false, qe_full_done = false;
+   // with snow off (and no snow output line wanted) the snow work arrays are neither formed nor committed
+   const bool want_snow_line = (L.snow98 != nullptr);
+   const bool snow_arrays = (snowUse == 1) || want_snow_line;
    double lv_at_melt = 0;
 
    SU_CLK_DECL;
@@ -372,10 +377,20 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
                for (int is = 0; is < NSURF; is++)
                   SnowFrac_q[is] = (nrm_use > 0) ? ((snowUse == 0) ? 0.0 : (double)S.SnowFrac[is]) : R.snowFrac_obs;
             SnowAlb_next = H.SnowAlb_q;
-            Snow_cal_MeltHeat(P, sfr, A.lvS_J_kg, A.lv_J_kg, tstep_real, Temp_C, Precip, nsh_real, Rd.Tsurf_ind,
-                              S.state_id.v, Rd.qn1_ind_snow, S.SnowWater.v, deltaQi, S.SnowPack.v, SnowFrac_q, SnowAlb_next,
-                              S.SnowDens.v, S.SnowfallCum, SnowPack_m, SnowFrac_q, SnowAlb_next, SnowDens_m,
-                              SnowfallCum_next, Hs);
+            if (snowUse == 1 || want_snow_line) {
+               Snow_cal_MeltHeat(P, sfr, A.lvS_J_kg, A.lv_J_kg, tstep_real, Temp_C, Precip, nsh_real, Rd.Tsurf_ind,
+                                 S.state_id.v, Rd.qn1_ind_snow, S.SnowWater.v, deltaQi, S.SnowPack.v, SnowFrac_q, SnowAlb_next,
+                                 S.SnowDens.v, S.SnowfallCum, SnowPack_m, SnowFrac_q, SnowAlb_next, SnowDens_m,
+                                 SnowfallCum_next, Hs);
+            } else {
+               // snowUse = 0: what Snow_cal_MeltHeat reduces to (snow.f95:160-176, :1299-1315) -- no melt terms, snow
+               // fraction 0, pack and density carried; none of the per-surface arrays is formed or read on this path
+               Hs.mwh = 0; Hs.Qm = 0; Hs.QmFreez = 0; Hs.QmRain = 0;
+               SnowfallCum_next = 0;
+               double vf = 0;
+               for (int is = 2; is < 7; is++) vf += sfr[is] * (1 - 0.0);
+               Hs.veg_fr = vf;
+            }
             lv_at_melt = A.lv_J_kg;
          }
          rad_done = true;
@@ -404,7 +419,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
             for (int is = 0; is < NSURF; is++) snow_branch = snow_branch || (Hs.snowCalcSwitch[is] == 1);
          if (snow_branch) {
             cal_QE_full(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow,
-                        rb, qn_e, PervFraction, VegFraction, NonWaterFraction, W, QT);
+                        rb, qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT);
             qe = QT.qe;
             qe_full_done = true;
          } else {
@@ -444,7 +459,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       if (!qe_full_done) {
          const double qn_e = qn1_snowfree + qf - qs;
          cal_QE_full(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow, rb,
-                     qn_e, PervFraction, VegFraction, NonWaterFraction, W, QT);
+                     qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT);
       }
       qh_resist = (RA != 0) ? A.avdens * A.avcp * (Rd.tsurf - Temp_C) / RA : -999.0;
       double soilstoreOld[NSURF];
@@ -475,8 +490,13 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    S.qn1_av = qn1_av_next; S.dqndt = dqndt_next; S.qn1_s_av = qn1_s_av_next; S.dqnsdt = dqnsdt_next;
    S.SnowfallCum = SnowfallCum_next; S.SnowAlb = SnowAlb_next;
    for (int is = 0; is < NSURF; is++) {
-      S.IceFrac[is] = W.iceFrac[is]; S.SnowWater[is] = W.SnowWater[is]; S.SnowDens[is] = W.SnowDens[is];
-      S.SnowFrac[is] = W.SnowFrac[is]; S.SnowPack[is] = W.SnowPack[is]; S.soilstore_id[is] = W.soilstore_id[is];
+      if (snow_arrays) {
+         S.IceFrac[is] = W.iceFrac[is]; S.SnowWater[is] = W.SnowWater[is]; S.SnowDens[is] = W.SnowDens[is];
+         S.SnowFrac[is] = W.SnowFrac[is]; S.SnowPack[is] = W.SnowPack[is];
+      } else {
+         S.SnowFrac[is] = 0;   // snowUse = 0: ice fraction, snow water, density and pack are carried unchanged
+      }
+      S.soilstore_id[is] = W.soilstore_id[is];
       S.state_id[is] = W.state_id[is]; S.alb[is] = alb_next[is];
    }
    for (int i = 0; i < 3; i++) { S.GDD_id[i] = H.d.GDD_id[i]; S.SDD_id[i] = H.d.SDD_id[i]; S.LAI_id[i] = H.d.LAI_id[i]; }
