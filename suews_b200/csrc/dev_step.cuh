@@ -34,6 +34,11 @@
 #define SU_SYNC() ((void)0)
 #define SU_SYNC_OR(p) (p)
 #endif
+// phase barrier k (0 P0|P1, 1 L1|L2, 2 L2|L3, 3 loop|F1, 4 F1|F2, 5 F2|F3); SU_NOSYNC_MASK drops some (tuning)
+#ifndef SU_NOSYNC_MASK
+#define SU_NOSYNC_MASK 0
+#endif
+#define SU_SYNCN(k) do { if (!((SU_NOSYNC_MASK >> (k)) & 1)) SU_SYNC(); } while (0)
 
 // Profiling build only (-DSU_PHASE_CLOCKS): SM cycles per phase, as seen by thread 0 of each block after the
 // phase's barrier (so a phase's time is that of its slowest warp).  tools/prof_run.py prints them.
@@ -297,7 +302,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
          SnowFrac_res[is] = (snowUse == 1) ? ((nrm_use > 0) ? S.SnowFrac[is] : R.snowFrac_obs) : 0.0;
       stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H);
    }
-   SU_SYNC();
+   SU_SYNCN(0);
    SU_CLK(0);
    // ================= phase P1: moist air + Tsurf-independent stages =================
    if (live) {
@@ -397,7 +402,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
          if (i_iter == 1)   // LUMPS first guess (driver.f95:809-824)
             LUMPS_cal_QHQE(dg, P, sfr, qn1, qf, qs, Hs.Qm, Temp_C, Hs.veg_fr, A.avcp, Press_hPa, A.lv_J_kg, H.d.LAI_id, Lm);
       }
-      SU_SYNC();
+      SU_SYNCN(1);
       SU_CLK(2);
       // ================= phase L2: stability and resistances (driver.f95:2134-2270) =================
       if (run) {
@@ -409,7 +414,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
             RAsnow = AerodynamicResistance(dg, ZZD, z0m, avU1, L_mod, UStar, VegFraction, P.AerodynamicResistanceMethod, sm, 3);
          rb = BoundaryLayerResistance(ZZD, z0m, avU1, UStar);
       }
-      SU_SYNC();
+      SU_SYNCN(2);
       SU_CLK(3);
       // ================= phase L3: QE, QH, surface temperature, convergence =================
       if (run) {
@@ -452,7 +457,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
          }
       }
    }
-   SU_SYNC();
+   SU_SYNCN(3);
    SU_CLK(4);
    // ================= phase F1: state update of the last trip + soil water =================
    if (live && dg.fatal == 0) {
@@ -469,7 +474,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       cal_SoilState(dg, P.SMDMethod, R.xsmd, NonWaterFraction, H.SoilMoistCap, P.SoilStoreCap.v, QT.surf_chang_per_tstep,
                     W.soilstore_id, soilstoreOld, sfr, smd, smd_nsurf, tot_chang_per_tstep);
    }
-   SU_SYNC();
+   SU_SYNCN(4);
    SU_CLK(5);
    // ================= phase F2: roughness-sublayer diagnostics (driver.f95:943-949) =================
    SuRSL rs;
@@ -481,7 +486,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       // (EmissionsMethod >= 11) is not part of this kernel yet.
       if (P.EmissionsMethod >= 11) su_fatal(dg, 1004);
    }
-   SU_SYNC();
+   SU_SYNCN(5);
    SU_CLK(6);
    SU_CNT(9, 1);
    // ================= phase F3: commit (driver.f95:965-994) and output lines =================
@@ -499,13 +504,19 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       S.soilstore_id[is] = W.soilstore_id[is];
       S.state_id[is] = W.state_id[is]; S.alb[is] = alb_next[is];
    }
-   for (int i = 0; i < 3; i++) { S.GDD_id[i] = H.d.GDD_id[i]; S.SDD_id[i] = H.d.SDD_id[i]; S.LAI_id[i] = H.d.LAI_id[i]; }
-   S.DecidCap_id = H.d.DecidCap_id; S.albDecTr_id = H.d.albDecTr_id; S.albEveTr_id = H.d.albEveTr_id;
-   S.albGrass_id = H.d.albGrass_id; S.porosity_id = H.d.porosity_id;
-   SU_SDP(S.StoreDrainPrm.v, 5, DECID) = H.d.DecidStoreCap;
+   // Daily state: within a day only the running degree-day sums HDD_id(1:6), Tmin, Tmax and the day length move
+   // (update_DailyState_Day, dailystate.f95:496-575); everything else is rewritten by update_DailyState_End
+   // on the last step of the day only (dailystate.f95:355-493)
    S.Tair_av = H.Tair_av_next; S.Tmin_id = H.d.Tmin_id; S.Tmax_id = H.d.Tmax_id; S.lenDay_id = H.d.lenDay_id;
-   for (int i = 0; i < 12; i++) S.HDD_id[i] = H.d.HDD_id[i];
-   for (int i = 0; i < 9; i++) S.WUDay_id[i] = H.d.WUDay_id[i];
+   for (int i = 0; i < 6; i++) S.HDD_id[i] = H.d.HDD_id[i];
+   if ((R.it * 3600 + R.imin * 60 + P.tstep) >= 86400) {
+      for (int i = 6; i < 12; i++) S.HDD_id[i] = H.d.HDD_id[i];
+      for (int i = 0; i < 3; i++) { S.GDD_id[i] = H.d.GDD_id[i]; S.SDD_id[i] = H.d.SDD_id[i]; S.LAI_id[i] = H.d.LAI_id[i]; }
+      S.DecidCap_id = H.d.DecidCap_id; S.albDecTr_id = H.d.albDecTr_id; S.albEveTr_id = H.d.albEveTr_id;
+      S.albGrass_id = H.d.albGrass_id; S.porosity_id = H.d.porosity_id;
+      SU_SDP(S.StoreDrainPrm.v, 5, DECID) = H.d.DecidStoreCap;
+      for (int i = 0; i < 9; i++) S.WUDay_id[i] = H.d.WUDay_id[i];
+   }
    S.lv_switch = (double)lv_sw;
    S.alb1_hidden = Rd.alb1;
 

@@ -337,6 +337,43 @@ def test_replicated_cells_equal_single_cell():
     b1.close()
 
 
+def test_full_size_batch_properties():
+    """BASELINE configs[2] size (1 048 576 cells on one GPU) through size-independent properties: no fatal cell,
+    energy balance closed by construction (QH is the residual), water balance closed to the model's own
+    accuracy, and any block of cells equal, bit for bit, to the same cells run as a small batch."""
+    import bench
+    from suews_b200 import OUT_SUM82, SuewsBatch, synth
+    base, met = bench.load_inputs(1)
+    n = 1 << 20
+    b = SuewsBatch(n, 1)
+    synth.build_batch(b, base, cell0=0, scheme="default")
+    b.upload()
+    b.set_forcing(met[:144])
+    b.advance(0, 96, OUT_SUM82)          # night, including the non-converging stable hours
+    b.reset_sums()
+    b.advance(96, 48, OUT_SUM82)         # 08:00-12:00
+    fatal, _w, _it = b.diag()
+    assert (fatal == 0).all()
+    s = b.sums()
+    assert np.isfinite(s).all()
+    energy = s[:, 5] + s[:, 6] - (s[:, 7] + s[:, 8] + s[:, 9])            # QN + QF - QS - QH - QE (snow off: QM = 0)
+    assert np.abs(energy).max() <= 1e-9 * np.abs(s[:, 5]).max()
+    water = s[:, 13] + s[:, 14] - (s[:, 15] + s[:, 16] + s[:, 17])         # Rain + Irr - Evap - RO - TotCh  [mm]
+    assert np.abs(water).max() <= 1e-3
+    c0 = 777000
+    small = SuewsBatch(64, 1)
+    synth.build_batch(small, base, cell0=c0, scheme="default")
+    small.upload()
+    small.set_forcing(met[:144])
+    small.advance(0, 96, OUT_SUM82)
+    small.reset_sums()
+    small.advance(96, 48, OUT_SUM82)
+    assert np.array_equal(small.sums(), s[c0:c0 + 64])
+    assert np.array_equal(small.get_state("soilstore_id"), b.get_state("soilstore_id")[c0:c0 + 64])
+    small.close()
+    b.close()
+
+
 def test_library_exp_log_equal_cuda_libm_bit_for_bit():
     """dev_math.cuh restates exp/log with constant-bank coefficients; same operations, so the same bits"""
     import ctypes as C
