@@ -123,6 +123,42 @@ SU_DEV double interp_z(double z_x, const double *z, const double *v)
    return interp_2(z_x, z[idx_low], z[idx_high], v[idx_low], v[idx_high]);
 }
 
+// the vertical grid of RSLProfile (rslprof.f95:153-191), element by element
+struct SuRslGrid {
+   double zH, zMeas, dzc, dza;
+   int nz_can, idx_can;
+   // zarray(i0 + 1) before the idx_can / zMeas overrides
+   SU_INL double pre(int i0) const
+   {
+      const int i = i0 + 1;
+      if (i <= nz_can) {
+         if (i == nz_can) return zH;
+         if (i == 1 && dzc > 2) return F(1.999);
+         return dzc * i;
+      }
+      return zH + (i - nz_can) * dza;
+   }
+   SU_INL double at(int i0) const
+   {
+      if (i0 == SU_NZ - 1) return zMeas;
+      if (i0 == idx_can - 1) return zH;
+      return pre(i0);
+   }
+};
+SU_INL void bracket_grid(double z_x, const SuRslGrid &g, int &idx_low, int &idx_high)
+{
+   idx_low = -1;
+   idx_high = -1;
+   double bl = 0, bh = 0;
+   for (int i = 0; i < SU_NZ; i++) {
+      double dif = g.at(i) - z_x;
+      if (dif < F(0.) && (idx_low < 0 || dif > bl)) { idx_low = i; bl = dif; }
+      if (dif > F(0.) && (idx_high < 0 || dif < bh)) { idx_high = i; bh = dif; }
+   }
+   if (idx_low < 0) idx_low = 0;
+   if (idx_high < 0) idx_high = 0;
+}
+
 // RSLProfile, rslprof.f95:13-313.  line133 may be NULL when the 133-column profile is not wanted.
 SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD, const double *sfr, double FAI,
                          double avcp, double lv_J_kg, double avdens, double avU1, double Temp_C, double avRH,
@@ -157,25 +193,23 @@ SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD
    const bool flag_RSL = ((F(1.) - PAI) / FAI <= 18) && ((F(1.) - PAI) / FAI > F(.021)) && (zH_RSL > 6);
    double z0_RSL;
 
-   // ---- vertical grid rslprof.f95:153-191
-   double zarray[SU_NZ];
-   const int nz_can = (zH_RSL <= 2) ? 3 : ((zH_RSL <= 10) ? 10 : 15);
-   double dz = zH_RSL / nz_can;
-   for (int i = 1; i <= nz_can; i++) zarray[i - 1] = dz * i;
-   if (dz > 2) zarray[0] = F(1.999);
-   zarray[nz_can - 1] = zH_RSL;
-   dz = (zMeas - zH_RSL) / (SU_NZ - nz_can);
-   for (int i = nz_can + 1; i <= SU_NZ; i++) zarray[i - 1] = zH_RSL + (i - nz_can) * dz;
-   int idx_can = 1;
+   // ---- vertical grid rslprof.f95:153-191.  The 30 heights follow from (zH_RSL, zMeas); they are generated on
+   // demand (SuRslGrid::at returns exactly what the reference's zarray holds) and only stored for the profile line.
+   SuRslGrid grid;
+   grid.zH = zH_RSL; grid.zMeas = zMeas;
+   grid.nz_can = (zH_RSL <= 2) ? 3 : ((zH_RSL <= 10) ? 10 : 15);
+   grid.dzc = zH_RSL / grid.nz_can;
+   grid.dza = (zMeas - zH_RSL) / (SU_NZ - grid.nz_can);
+   grid.idx_can = 1;
    {
-      double mn = fabs(zarray[0] - zH_RSL);
+      double mn = fabs(grid.pre(0) - zH_RSL);
       for (int z = 1; z < SU_NZ; z++) {
-         double dif = fabs(zarray[z] - zH_RSL);
-         if (dif < mn) { mn = dif; idx_can = z + 1; }
+         double dif = fabs(grid.pre(z) - zH_RSL);
+         if (dif < mn) { mn = dif; grid.idx_can = z + 1; }
       }
    }
-   zarray[idx_can - 1] = zH_RSL;
-   zarray[SU_NZ - 1] = zMeas;
+   const int nz_can = grid.nz_can, idx_can = grid.idx_can;
+   const double dz = grid.dza;
 
    // The 30-level profile is only an output (dataoutLineRSL); the step itself consumes T2, q2 and U10, which
    // interp_z takes from the two levels bracketing 2 m and 10 m.  Without the profile line only those levels
@@ -183,12 +217,12 @@ SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD
    const bool full = (line133 != nullptr);
    int need[5];
    double need_pm[5] = {0, 0, 0, 0, 0}, need_ph[5] = {0, 0, 0, 0, 0};
-   bracket_z(2.0, zarray, need[0], need[1]);
-   bracket_z(10.0, zarray, need[2], need[3]);
+   bracket_grid(2.0, grid, need[0], need[1]);
+   bracket_grid(10.0, grid, need[2], need[3]);
    need[4] = idx_can - 1;
-   double psihatm_z[SU_NZ], psihath_z[SU_NZ];
+   double psihatm_z[SU_NZ], psihath_z[SU_NZ], zarray[SU_NZ];
    if (full)
-      for (int z = 0; z < SU_NZ; z++) { psihatm_z[z] = 0; psihath_z[z] = 0; }
+      for (int z = 0; z < SU_NZ; z++) { psihatm_z[z] = 0; psihath_z[z] = 0; zarray[z] = grid.at(z); }
 
    if (flag_RSL) {
       // cal_z0_RSL rslprof.f95:730-771.  z0_RSL is a pure function of (zH, L_MOD_RSL, beta, Lc); when
@@ -222,13 +256,13 @@ SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD
       // Taylor integration downward from the forcing height (rslprof.f95:198-214); the z+1 terms of one
       // level are the z terms of the level above.  c2 == c2h == 0.5 (rslprof.f95:497,549), so the momentum and
       // heat terms share one EXP per level.
-      double zzp = zarray[SU_NZ - 1];
+      double zzp = grid.at(SU_NZ - 1);
       double ex = su_exp_fast(F(-1.) * c2 * beta * (zzp - zd_RSL) / elm);
       double tmp = dz / F(2.) * stab_phi_mom(sm, (zzp - zd_RSL) / L_MOD_RSL) * (cm * ex) / (zzp - zd_RSL);
       double thp = dz / F(2.) * stab_phi_heat(sm, (zzp - zd_RSL) / L_MOD_RSL) * (ch * ex) / (zzp - zd_RSL);
       double pm_run = 0, ph_run = 0;   // psihat at the level above
       for (int z = SU_NZ - 1; z >= idx_can; z--) {
-         double zz = zarray[z - 1];
+         double zz = grid.at(z - 1);
          ex = su_exp_fast(F(-1.) * c2 * beta * (zz - zd_RSL) / elm);
          double tm = dz / F(2.) * stab_phi_mom(sm, (zz - zd_RSL) / L_MOD_RSL) * (cm * ex) / (zz - zd_RSL);
          double th = dz / F(2.) * stab_phi_heat(sm, (zz - zd_RSL) / L_MOD_RSL) * (ch * ex) / (zz - zd_RSL);
@@ -266,7 +300,7 @@ SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD
       double Ud[5], Td[5], qd[5];
       for (int j = 4; j >= 0; j--) {
          const int zi = need[j];
-         const double zz = zarray[zi];
+         const double zz = grid.at(zi);
          if (zi >= idx_can - 1) {
             double psimz = stab_psi_mom_v(sm, (zz - zd_RSL) / L_MOD_RSL);
             double psihz = stab_psi_heat(sm, (zz - zd_RSL) / L_MOD_RSL);
@@ -287,9 +321,9 @@ SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD
          Td[j] = Td[j] * TStar_RSL + Temp_C;
          qd[j] = (qd[j] * qStar_RSL + qa_gkg / F(1000.)) * F(1000.);
       }
-      o.T2_C = interp_2(2.0, zarray[need[0]], zarray[need[1]], Td[0], Td[1]);
-      o.q2_gkg = interp_2(2.0, zarray[need[0]], zarray[need[1]], qd[0], qd[1]);
-      o.U10_ms = interp_2(10.0, zarray[need[2]], zarray[need[3]], Ud[2], Ud[3]);
+      o.T2_C = interp_2(2.0, grid.at(need[0]), grid.at(need[1]), Td[0], Td[1]);
+      o.q2_gkg = interp_2(2.0, grid.at(need[0]), grid.at(need[1]), qd[0], qd[1]);
+      o.U10_ms = interp_2(10.0, grid.at(need[2]), grid.at(need[3]), Ud[2], Ud[3]);
       o.RH2 = qa2RH(o.q2_gkg, Press_hPa, o.T2_C);
       return;
    }
