@@ -21,20 +21,17 @@ SU_DEV double sat_vap_press(double TK, double P)
 SU_INL double su_fix_T(double T) { return (fabs(T) < F(0.001000)) ? (double)F(0.001000) : T; }
 SU_DEV double sat_vap_press_v(double T, double Press_hPa)   // T already through su_fix_T
 {
-   double es_hPa = 1000;
-   double Press_kPa = Press_hPa / 10;
-   if (T < 50 && T > -40) {
-      if (T >= F(0.001000)) {
-         double e_mb = F(6.1121) * exp(((F(18.678) - T / F(234.5)) * T) / (T + F(257.14)));
-         double f = F(1.00072) + Press_kPa * (F(3.2E-6) + F(5.9E-10) * (T * T));
-         es_hPa = e_mb * f;
-      } else if (T <= -F(0.001000)) {
-         double e_mb = F(6.1115) * exp(((F(23.036) - T / F(333.7)) * T) / (T + F(279.82)));
-         double f = F(1.00022) + Press_kPa * (F(3.83E-6) + F(6.4E-10) * (T * T));
-         es_hPa = e_mb * f;
-      }
-   }
-   return es_hPa;
+   // water (T >= 0.001) and ice (T <= -0.001) branches of meteo.f95:171-186 differ only in seven constants;
+   // selecting the constants keeps a warp whose cells straddle 0 degC on one instruction stream
+   const bool w = (T >= F(0.001000));
+   const double c0 = w ? F(6.1121) : F(6.1115), c1 = w ? F(18.678) : F(23.036), c2 = w ? F(234.5) : F(333.7),
+                c3 = w ? F(257.14) : F(279.82), f0 = w ? F(1.00072) : F(1.00022), f1 = w ? F(3.2E-6) : F(3.83E-6),
+                f2 = w ? F(5.9E-10) : F(6.4E-10);
+   const double Press_kPa = Press_hPa / 10;
+   const double e_mb = c0 * exp(((c1 - T / c2) * T) / (T + c3));
+   const double f = f0 + Press_kPa * (f1 + f2 * (T * T));
+   const bool in_range = (T < 50 && T > -40) && (w || T <= -F(0.001000));
+   return in_range ? e_mb * f : 1000.0;
 }
 SU_INL double sat_vap_press_x(SuDiag &dg, double &T, double Press_hPa, int from)
 {
