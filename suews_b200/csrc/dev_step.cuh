@@ -479,12 +479,27 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    // ================= phase F2: roughness-sublayer diagnostics (driver.f95:943-949) =================
    SuRSL rs;
    rs.T2_C = 0; rs.q2_gkg = 0; rs.U10_ms = 0; rs.RH2 = 0;
+   double Fc_biogen = 0, Fc_photo = 0, Fc_respi = 0;
    if (live && dg.fatal == 0) {
       RSLProfile(sm, zH, z0m, zdm, L_mod, sfr, FAI, A.avcp, A.lv_J_kg, A.avdens, avU1, Temp_C, avRh, Press_hPa, C.Z, qh, qe,
                  S.rsl_cache.v, rs, L.rsl133);
-      // SUEWS_cal_BiogenCO2: Fc terms are zeroed for EmissionsMethod 0-6 (driver.f95:1276-1280); CO2_biogen
-      // (EmissionsMethod >= 11) is not part of this kernel yet.
-      if (P.EmissionsMethod >= 11) su_fatal(dg, 1004);
+      // SUEWS_cal_BiogenCO2 driver.f95:1156-1286: zero for EmissionsMethod 0-6, CO2_biogen for >= 11.  It sees the
+      // still un-committed SnowFrac (driver.f95:957) and, for gsModel 3/4, a second cal_AtmMoist / SurfaceResistance
+      // at the modelled 2 m temperature (which also steps the Lat_vap switches, as in the reference).
+      if (P.EmissionsMethod >= 11) {
+         double gfunc2 = 0, t2 = 0;
+         if (P.gsModel == 3 || P.gsModel == 4) {
+            t2 = (fabs(Temp_C - rs.T2_C) > 5) ? Temp_C : rs.T2_C;
+            SuAtm A2;
+            cal_AtmMoist(dg, t2, Press_hPa, avRh, lv_sw, A2);
+            double gsc2, rs2;
+            SurfaceResistance(dg, P, sfr, S.SnowFrac.v, avkdn, t2, A2.dq, R.xsmd, H.vsmd, H.d.LAI_id, gfunc2, gsc2, rs2);
+         }
+         // SUEWS_cal_Main's own `gfunc` (driver.f95:374) is never assigned -- SUEWS_cal_Resistance keeps its gfunc
+         // to itself (driver.f95:2199) -- so the conductance-based family with gsModel 1/2 multiplies by an
+         // uninitialised local there; like the oracle, this takes it as 0
+         Fc_biogen = CO2_biogen(P, sfr, S.SnowFrac.v, H.d.LAI_id, avkdn, 0.0, gfunc2, t2, Temp_C, Fc_photo, Fc_respi);
+      }
    }
    SU_SYNCN(5);
    SU_CLK(6);
@@ -557,7 +572,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       SU_OUT(rad ? ((ldown_option == 1) ? -999.0 : Rd.fcld) : -999.0);
       SU_OUT(LAI_wt); SU_OUT(z0m); SU_OUT(zdm);
       SU_OUT(UStar); SU_OUT(L_mod); SU_OUT(RA); SU_OUT(H.ResistSurf);
-      SU_OUT(H.an.Fc_anthro); SU_OUT(0.0); SU_OUT(0.0); SU_OUT(H.an.Fc_metab); SU_OUT(H.an.Fc_traff);
+      SU_OUT(H.an.Fc_anthro + Fc_biogen); SU_OUT(Fc_photo); SU_OUT(Fc_respi); SU_OUT(H.an.Fc_metab); SU_OUT(H.an.Fc_traff);
       SU_OUT(H.an.Fc_build); SU_OUT(H.an.Fc_point);
       SU_OUT(qn1_snowfree); SU_OUT(qn1_S); SU_OUT((double)S.SnowAlb);
       SU_OUT(Hs.Qm); SU_OUT(Hs.QmFreez); SU_OUT(Hs.QmRain); SU_OUT(W.swe); SU_OUT(Hs.mwh); SU_OUT(W.mwstore);

@@ -197,6 +197,80 @@ SU_INL void evap_surface(SuEvapTrip &e, double state_is, double WetThresh_is, do
    }
 }
 
+// ------------------------------------------------------------------ biogenic CO2 (biogenco2.f95:33-231)
+// Photosynthesis by the four model families selected by the decade of EmissionsMethod (11-16 rectangular
+// hyperbola, 21-26 non-rectangular hyperbola, 31-36 bulk non-rectangular, 41-46 conductance based) and
+// temperature-driven respiration.  Returns Fc_biogen; Fc_photo / Fc_respi through the references.
+SU_DEV double CO2_biogen(const SuewsClassParams &P, const double *sfr, const double *SnowFrac, const double *LAI_id,
+                         double avkdn, double gfunc, double gfunc2, double t2, double Temp_C, double &Fc_photo,
+                         double &Fc_respi)
+{
+   const int EM = P.EmissionsMethod, gsmodel = P.gsModel;
+   const double *al = P.alpha_bioCO2.v, *be = P.beta_bioCO2.v, *th = P.theta_bioCO2.v;
+   const double PAR = F(4.6) * F(0.46) * avkdn;
+   const double VegFracSum = sfr[CONIF] + sfr[DECID] + sfr[GRASS];
+   double avf[3], avf0[3];
+   for (int iv = 0; iv < 3; iv++) {
+      avf[iv] = (sfr[iv + 2] * (1 - SnowFrac[iv + 2])) * (LAI_id[iv] / P.LAIMax[iv]);
+      avf0[iv] = (sfr[iv + 2] * (1 - SnowFrac[iv + 2])) * LAI_id[iv];
+   }
+   double photo = Fc_photo;   // left as it was for an unknown family, as the reference does
+   if (EM >= 11 && EM <= 16) {
+      photo = 0;
+      for (int iv = 0; iv < 3; iv++) {
+         double q = -be[iv] * al[iv] * PAR / (al[iv] * PAR + be[iv]);
+         photo = photo + q * avf[iv];
+      }
+   } else if (EM >= 21 && EM <= 26) {
+      double Pho = 0;
+      for (int iv = 0; iv < 3; iv++) {
+         double q = al[iv] * PAR + be[iv];
+         q = -(1 / (2 * th[iv]) * (al[iv] * PAR + be[iv] - sqrt(q * q - 4 * al[iv] * be[iv] * th[iv] * PAR)));
+         Pho = Pho + q * avf[iv];
+      }
+      photo = Pho;
+   } else if (EM >= 31 && EM <= 36) {
+      const double s4 = (sfr[CONIF] + sfr[DECID] + sfr[GRASS] + sfr[BSOIL]);
+      double a2, b2, Pho, q;
+      if (al[0] == al[1] && al[0] == al[2] && be[0] == be[1] && be[0] == be[2] && th[0] == th[1] && th[0] == th[2]) {
+         a2 = al[0] + P.alpha_enh_bioCO2[0] * s4;
+         b2 = -be[0] + P.beta_enh_bioCO2[0] * s4;
+         q = a2 * PAR + b2;
+         Pho = -(1 / (2 * th[0]) * (a2 * PAR + b2 - sqrt(q * q - 4 * a2 * b2 * th[0] * PAR)));
+      } else {
+         a2 = (al[0] * sfr[CONIF] / VegFracSum + al[1] * sfr[DECID] / VegFracSum + al[2] * sfr[GRASS] / VegFracSum) /
+              (al[0] + al[1] + al[2]);
+         b2 = (be[0] * sfr[CONIF] / VegFracSum + be[1] * sfr[DECID] / VegFracSum + be[2] * sfr[GRASS] / VegFracSum) /
+              (be[0] + be[1] + be[2]);
+         double t2v = (th[0] * sfr[CONIF] / VegFracSum + th[1] * sfr[DECID] / VegFracSum + th[2] * sfr[GRASS] / VegFracSum) /
+                      (th[0] + th[1] + th[2]);
+         a2 = a2 + P.alpha_enh_bioCO2[0] * s4;
+         b2 = -b2 + P.beta_enh_bioCO2[0] * s4;
+         q = a2 * PAR + b2;
+         Pho = -(1 / (2 * t2v) * (a2 * PAR + b2 - sqrt(q * q - 4 * a2 * b2 * t2v * PAR)));
+      }
+      photo = Pho * avf[0] + Pho * avf[1] + Pho * avf[2];
+   } else if (EM >= 41 && EM <= 46) {
+      photo = 0;
+      for (int iv = 0; iv < 3; iv++) photo = photo + avf0[iv] * be[iv];
+      if (gsmodel == 1 || gsmodel == 2) photo = -photo * gfunc;
+      else if (gsmodel == 3 || gsmodel == 4) photo = -photo * gfunc2;
+   }
+   double Res = F(0.0), Res_surf = F(0.0);
+   if (VegFracSum > F(0.01)) {
+      for (int iv = 0; iv < 3; iv++) {
+         if (sfr[2 + iv] > F(0.005)) {
+            if (gsmodel == 1 || gsmodel == 2) Res_surf = SU_MAX(P.min_res_bioCO2[iv], P.resp_a[iv] * exp(P.resp_b[iv] * Temp_C));
+            else if (gsmodel == 3 || gsmodel == 4) Res_surf = SU_MAX(P.min_res_bioCO2[iv], P.resp_a[iv] * exp(P.resp_b[iv] * t2));
+            Res = Res + Res_surf * sfr[2 + iv] / VegFracSum;
+         }
+      }
+   }
+   Fc_photo = photo;
+   Fc_respi = Res * (sfr[CONIF] + sfr[DECID] + sfr[GRASS] + sfr[BSOIL]);
+   return Fc_photo + Fc_respi;
+}
+
 // ------------------------------------------------------------------ water balance (waterdist.f95)
 // waterdist.f95:20-89
 SU_DEV double drainage(SuDiag &dg, double state_is, double StorCap, double DrainEq, double DrainCoef1, double DrainCoef2,

@@ -371,7 +371,7 @@ static const char *fatal_text(int code)
    case 75: return "RunControl.nml: BaseTMethod / TrafficUnits not usable";
    case 1001: return "NetRadiationMethod: Value not usable";
    case 1003: return "StorageHeatMethod 3 (AnOHM) / 4 (ESTM) are not part of this library";
-   case 1004: return "EmissionsMethod >= 11 (biogenic CO2) is not part of this library yet";
+   case 1004: return "EmissionsMethod outside 0-6 / 11-46";
    default: return "Fatal error in SUEWS!";
    }
 }

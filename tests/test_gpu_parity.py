@@ -125,6 +125,9 @@ def test_chunked_advance_equals_single_launch(gpu_and_ref_2005):
     b.close()
 
 
+BIOCO2 = dict(theta_bioco2=[0.96] * 3, alpha_enh_bioco2=[0.016] * 3, beta_enh_bioco2=[33.454] * 3)
+
+
 @pytest.mark.parametrize("scheme_over", [
     dict(snowuse=0, netradiationmethod=3, emissionsmethod=2),                 # user-facing default set
     dict(netradiationmethod=1), dict(netradiationmethod=2), dict(netradiationmethod=3), dict(netradiationmethod=11),
@@ -137,6 +140,10 @@ def test_chunked_advance_equals_single_launch(gpu_and_ref_2005):
     dict(storageheatmethod=0), dict(ohmincqf=1), dict(evapmethod=1), dict(aerodynamicresistancemethod=1),
     dict(aerodynamicresistancemethod=3), dict(gsmodel=1), dict(smdmethod=1), dict(waterusemethod=1),
     dict(basetmethod=2), dict(laicalcyes=0),
+    # biogenic CO2 families (biogenco2.f95): rectangular / non-rectangular / bulk hyperbola, conductance based
+    dict(emissionsmethod=11), dict(emissionsmethod=14), dict(emissionsmethod=22, **BIOCO2), dict(emissionsmethod=33, **BIOCO2),
+    dict(emissionsmethod=36, theta_bioco2=[0.9, 0.96, 0.8], alpha_enh_bioco2=[0.016] * 3, beta_enh_bioco2=[33.454] * 3),
+    dict(emissionsmethod=41), dict(emissionsmethod=45, gsmodel=4), dict(emissionsmethod=12, gsmodel=3),
 ])
 def test_scheme_options_match_oracle(scheme_over):
     """Every option of the reference's physics sweep (Test/code/BTS_config.nml &physics_test) that is
@@ -144,7 +151,7 @@ def test_scheme_options_match_oracle(scheme_over):
     from suews_b200 import OUT_FULL, SuewsBatch
     d = fx.state_init(2005)
     for k, v in scheme_over.items():
-        d[k] = [v]
+        d[k] = list(v) if isinstance(v, (list, tuple)) else [v]
     if scheme_over.get("snowuse", 1) == 0:
         for k in ("snowpack", "snowfrac", "snowwater"):
             d[k] = [0.0] * 7
