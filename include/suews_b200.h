@@ -85,7 +85,7 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
 int suews_b200_sync(suews_b200_handle h);
 
 /* Results.  sums: [ncell][82] (cell-major).  Full blocks (after SUEWS_OUT_FULL): per cell a
- * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50 columns). */
+ * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50/31 columns). */
 int suews_b200_get_sums(suews_b200_handle h, double *sums);
 /* selected columns only (0-based indices into the 82-column SUEWS line), [ncell][ncols]; device -> pinned host */
 int suews_b200_get_sums_cols(suews_b200_handle h, const int *cols, int ncols, double *out);
@@ -93,7 +93,7 @@ int suews_b200_device_sync(suews_b200_handle h);
 /* measured FP64 FMA throughput of the device in TFLOP/s (compute-roofline denominator) */
 int suews_b200_fp64_peak(int device, double *tflops);
 int suews_b200_reset_sums(suews_b200_handle h);
-int suews_b200_get_block(suews_b200_handle h, const char *group /* "SUEWS","snow","RSL","DailyState" */, int cell,
+int suews_b200_get_block(suews_b200_handle h, const char *group /* "SUEWS","snow","RSL","DailyState","SOLWEIG" */, int cell,
                          double *block, int nsteps, int ncol);
 int suews_b200_get_diag(suews_b200_handle h, int *fatal_code_per_cell, unsigned long long *warn_mask2_per_cell,
                         long long *tsurf_iterations_per_cell);

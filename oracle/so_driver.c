@@ -570,8 +570,13 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
       st->lv_switch2 = s2;
    }
    st->alb1_hidden = alb1;
-   /* SOLWEIG (driver.f95:997-1002): not restated */
-   for (i = 0; i < NCOL_SOLWEIG; i++) out->SOLWEIG[i] = NAN_;
+   /* SOLWEIG point diagnostics (driver.f95:997-1002): the state has been committed, so alb is alb_next */
+   if (p->sfr[BLDG] > 0) {
+      so_SOLWEIG_cal_main(f->id, f->it, dectime, 0.8, FAI, f->avkdn, ldown, Temp_C, f->avRh, f->Press_hPa, TSfc_C, p->lat,
+                          ZENITH_deg, azimuth, 1.0, st->alb[0], st->alb[1], p->emis[0], p->emis[1], p->bldgH, out->SOLWEIG);
+   } else {
+      for (i = 0; i < NCOL_SOLWEIG; i++) out->SOLWEIG[i] = NAN_;
+   }
 
    /* SUEWS_update_outputLine driver.f95:2273-2457 */
    {

@@ -362,6 +362,11 @@ void so_RSLProfile(SoCtx *cx, double Zh, double z0m, double zdm, double L_MOD, c
 double so_cal_tair_av(double tair_av_prev, int dt_since_start, int tstep, double temp_c);
 double so_cal_tsfc(double qh, double avdens, double avcp, double RA, double temp_c);
 double so_set_nan(double x);
+/* suews_phys_solweig.f95 (point version) */
+void so_SOLWEIG_cal_main(int id, int it, double dectime, double lamdaP, double lamdaF, double avkdn, double ldown,
+                         double Temp_C, double avrh, double Press_hPa, double Tg, double lat, double zenith_deg,
+                         double azimuth, double scale, double alb_ground, double alb_bldg, double emis_ground,
+                         double emis_wall, double heightgravity, double out[NCOL_SOLWEIG]);
 
 /* One cell, one timestep == SUEWS_cal_Main.  Mutates *st (including
  * nothing of dt_since_start: the caller advances it, as in the reference). */

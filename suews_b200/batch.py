@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, dp, ip
 
-NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50}
+NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50, "SOLWEIG": 31}
 OUT_SUM82 = 1
 OUT_FULL = 2
 OUT_SUM7 = 4   # only the seven parity fluxes (output policy P0)

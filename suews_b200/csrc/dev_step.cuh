@@ -26,6 +26,7 @@
 #include "dev_snow.cuh"
 #include "dev_daily.cuh"
 #include "dev_rsl.cuh"
+#include "dev_solweig.cuh"
 
 #ifdef SU_PHASE_SYNC
 #define SU_SYNC() __syncthreads()
@@ -65,7 +66,7 @@ __device__ unsigned long long su_phase_clk[16];
 
 // Optional per-step output lines (reference layouts).  NULL = not wanted.
 struct SuLines {
-   double *datetime5, *suews82, *snow98, *rsl133, *daily45;
+   double *datetime5, *suews82, *snow98, *rsl133, *daily45, *sol26;
 };
 
 // Tsurf-independent quantities of a step
@@ -602,6 +603,14 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       for (int is = 0; is < NSURF; is++) o[k++] = Hs.SnowDepth[is];
       for (int is = 0; is < NSURF; is++) o[k++] = Rd.Tsurf_ind_snow[is];
       o[k++] = Rd.alb1;
+   }
+   if (L.sol26) {   // SOLWEIG point diagnostics, driver.f95:997-1002 (after the commit: alb is alb_next)
+      if (sfr[BLDG] > 0) {
+         SOLWEIG_cal_main(R.id, R.it, R.dectime, 0.8, FAI, avkdn, Rd.ldown, Temp_C, avRh, Press_hPa, TSfc_C, C.lat, zenith_deg,
+                          azimuth, 1.0, S.alb[0], S.alb[1], P.emis[0], P.emis[1], C.bldgH, L.sol26);
+      } else {
+         for (int i = 0; i < SUEWS_NCOL_SOLWEIG; i++) L.sol26[i] = -999;
+      }
    }
    if (L.daily45) {   // update_DailyStateLine, dailystate.f95:1044-1113 (HDD_id is DIMENSION(6) in the packer)
       double *o = L.daily45;

@@ -55,7 +55,7 @@ struct SuRunArgs {
    unsigned long long *warn;    // [2][stride]
    long long *iters;            // [ncell]
    // full output (SUEWS_OUT_FULL): per cell column-major [nsteps x ncol]
-   double *blkSUEWS, *blkSnow, *blkRSL, *blkDaily;
+   double *blkSUEWS, *blkSnow, *blkRSL, *blkDaily, *blkSOL;
    int ncell;
    long long stride;
    int nsteps;
@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
          const int gs = s0 + t;
          const bool live = active && dg.fatal == 0;
          SuLines L;
-         L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr;
-         double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY];
-         if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; }
+         L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr; L.sol26 = nullptr;
+         double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY], l_so[SUEWS_NCOL_SOLWEIG];
+         if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; }
          // every thread of the block enters the step (phase barriers inside); only live cells compute
          iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
                              (a.sums && !a.sum7) ? acc : nullptr, (a.sums && a.sum7) ? acc7 : nullptr, L);
@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
             b = a.blkDaily + (size_t)cell * n * (SUEWS_NCOL_DAILY + 5);
             for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
             for (int c = 0; c < SUEWS_NCOL_DAILY; c++) b[gs + n * (5 + c)] = l_da[c];
+            b = a.blkSOL + (size_t)cell * n * (SUEWS_NCOL_SOLWEIG + 5);   // SUEWS_update_output with set_nan, driver.f95:2497
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_SOLWEIG; c++) b[gs + n * (5 + c)] = (fabs(l_so[c]) > 30000) ? -999.0 : l_so[c];
             if (P.snowUse == 1) {   // SUEWS_update_output, driver.f95:2499-2501 (with set_nan :2737)
                b = a.blkSnow + (size_t)cell * n * (SUEWS_NCOL_SNOW + 5);
                for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
@@ -394,7 +397,7 @@ struct suews_b200_handle_s {
    long long *d_iters = nullptr;
    SuewsStepRec *d_steps = nullptr;
    SuewsEphem *d_ephem = nullptr;
-   double *d_blk[4] = {nullptr, nullptr, nullptr, nullptr};
+   double *d_blk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
    int blk_nsteps = 0;
    cudaStream_t stream = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -475,7 +478,7 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_classes); cudaFree(h->d_cls); cudaFree(h->d_tz); cudaFree(h->d_fatal); cudaFree(h->d_cellp);
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
-   for (int i = 0; i < 4; i++) cudaFree(h->d_blk[i]);
+   for (int i = 0; i < 5; i++) cudaFree(h->d_blk[i]);
 }
 
 int suews_b200_destroy(suews_b200_handle h)
@@ -740,8 +743,8 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    CUDA_OK(cudaSetDevice(h->device));
    const bool full = (out_flags & SUEWS_OUT_FULL) != 0;
    if (full) {
-      const int ncol[4] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5};
-      for (int i = 0; i < 4; i++) {
+      const int ncol[5] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5};
+      for (int i = 0; i < 5; i++) {
          size_t cnt = (size_t)h->ncell * (size_t)nsteps * (size_t)ncol[i];
          CUDA_OK(dev_alloc(&h->d_blk[i], cnt));
          // unwritten rows (snow block when snowUse = 0) are left unassigned by the reference; -999 here
@@ -758,7 +761,7 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.sums = (out_flags & (SUEWS_OUT_SUM82 | SUEWS_OUT_SUM7)) ? h->d_sums : nullptr;
    a.sum7 = ((out_flags & SUEWS_OUT_SUM7) && !(out_flags & SUEWS_OUT_SUM82)) ? 1 : 0;
    a.fatal = h->d_fatal; a.warn = h->d_warn; a.iters = h->d_iters;
-   a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3];
+   a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3]; a.blkSOL = h->d_blk[4];
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
    a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;
    const int grid = (h->ncell + SU_BLOCK - 1) / SU_BLOCK;
@@ -884,10 +887,10 @@ int suews_b200_reset_sums(suews_b200_handle h)
 int suews_b200_get_block(suews_b200_handle h, const char *group, int cell, double *block, int nsteps, int ncol)
 {
    if (!h || !group || !block) return set_err(SUEWS_E_BAD_ARG, "null argument");
-   const char *names[4] = {"SUEWS", "snow", "RSL", "DailyState"};
-   const int ncols[4] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5};
+   const char *names[5] = {"SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"};
+   const int ncols[5] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5};
    int g = -1;
-   for (int i = 0; i < 4; i++)
+   for (int i = 0; i < 5; i++)
       if (strcasecmp(group, names[i]) == 0) g = i;
    if (g < 0) return set_err(SUEWS_E_BAD_NAME, "get_block: unknown group '%s'", group);
    if (!h->d_blk[g] || nsteps != h->blk_nsteps || ncol != ncols[g] || cell < 0 || cell >= h->ncell)

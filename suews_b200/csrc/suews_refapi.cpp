@@ -145,15 +145,15 @@ int run_rows(const double *met, int len_sim, int dt_since_start, int tstep_prev,
    // failing step are still returned, then the code; library errors return at once
    const int fatal_rc = suews_b200_sync(g_h);
    if (fatal_rc >= SUEWS_E_NO_DEVICE) return fatal_rc;
-   static const char *const grp[6] = {"SUEWS", "snow", nullptr, "RSL", nullptr, "DailyState"};
+   static const char *const grp[6] = {"SUEWS", "snow", nullptr, "RSL", "SOLWEIG", "DailyState"};
    for (int g = 0; g < 6; g++) {
       if (!blk[g]) continue;
       if (grp[g]) {
          rc = suews_b200_get_block(g_h, grp[g], 0, blk[g], len_sim, kBlkCols[g]);
          if (rc) return rc;
       } else {
-         // SOLWEIG is not run on this path: its line is NAN = -999 (driver.f95:1040-1043); the ESTM block is
-         // only written when StorageHeatMethod = 4 (driver.f95:2503), which this library rejects -- -999 too.
+         // the ESTM block is only written when StorageHeatMethod = 4 (driver.f95:2503), which this library
+         // rejects: date columns + -999
          const size_t n = (size_t)len_sim;
          for (size_t c = 0; c < (size_t)kBlkCols[g]; c++)
             for (size_t r = 0; r < n; r++)
@@ -242,8 +242,8 @@ int suews_cal_main_c(void *const *args, int nargs)
    if (*(const int *)args[i_sec] != 0) return SUEWS_E_NOT_IMPL;   // forcing rows carry whole minutes (driver.f95:3181)
    rc = push_fields(kMainArgs, kNMain, args);
    if (rc) return rc;
-   double b0[87], b1[103], b3[138], b5[50];
-   double *blk[6] = {b0, b1, nullptr, b3, nullptr, b5};
+   double b0[87], b1[103], b3[138], b4[31], b5[50];
+   double *blk[6] = {b0, b1, nullptr, b3, b4, b5};
    const int run_rc = run_rows(met, 1, *(const int *)args[i_dt], *(const int *)args[i_tp], blk);
    if (run_rc >= SUEWS_E_NO_DEVICE) return run_rc;
    rc = pull_state(kMainArgs, kNMain, args);
@@ -254,7 +254,7 @@ int suews_cal_main_c(void *const *args, int nargs)
    if (out[2]) memcpy(out[2], b1 + 5, sizeof(double) * 98);
    if (out[3]) for (int k = 0; k < 27; k++) out[3][k] = -999.0;
    if (out[4]) memcpy(out[4], b3 + 5, sizeof(double) * 133);
-   if (out[5]) for (int k = 0; k < 26; k++) out[5][k] = -999.0;
+   if (out[5]) memcpy(out[5], b4 + 5, sizeof(double) * 26);
    if (out[6]) memcpy(out[6], b5 + 5, sizeof(double) * 45);
    return run_rc;
 }

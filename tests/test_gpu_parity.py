@@ -23,7 +23,8 @@ TOL_SUM = 1e-6
 PARITY_COLS = {"QN": 5, "QF": 6, "QS": 7, "QH": 8, "QE": 9, "RO": 16, "SWE": 71}
 
 
-TEMP_COLS = {"SUEWS": [4, 77, 78], "RSL": list(range(60, 90)), "snow": list(range(90, 97)), "DailyState": [12, 13]}
+TEMP_COLS = {"SUEWS": [4, 77, 78], "RSL": list(range(60, 90)), "snow": list(range(90, 97)), "DailyState": [12, 13],
+             "SOLWEIG": [17, 24, 25]}
 BIG_COLS = {"SUEWS": {12: 1.0e4}}
 
 
@@ -49,7 +50,7 @@ def gpu_and_ref_2005():
     d = fx.state_init(2005)
     met = fx.forcing(2005)
     cell = ol.Cell(d)
-    ref = cell.run(met, want=("SUEWS", "snow", "RSL", "DailyState"))
+    ref = cell.run(met, want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
     b = SuewsBatch(1, 1)
     assert b.load_reference_args(d) == []
     b.upload()
@@ -59,7 +60,7 @@ def gpu_and_ref_2005():
     b.close()
 
 
-@pytest.mark.parametrize("group", ["SUEWS", "snow", "RSL", "DailyState"])
+@pytest.mark.parametrize("group", ["SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"])
 def test_blocks_match_oracle(gpu_and_ref_2005, group):
     b, ref, _cell, met = gpu_and_ref_2005
     out = b.block(group, 0, met.shape[0])

@@ -12,7 +12,7 @@ from test_gpu_parity import TOL_DAY1, rel_err
 
 pytestmark = pytest.mark.gpu
 
-GROUP_OF_BLOCK = {0: "SUEWS", 1: "snow", 3: "RSL", 5: "DailyState"}
+GROUP_OF_BLOCK = {0: "SUEWS", 1: "snow", 3: "RSL", 4: "SOLWEIG", 5: "DailyState"}
 
 
 def _kwargs(d, which):
@@ -44,15 +44,15 @@ def test_cal_multitsteps_matches_oracle():
     d = fx.state_init(2005)
     met = fx.forcing(2005)[:288]
     cell = ol.Cell(d)
-    ref = cell.run(met)
+    ref = cell.run(met, want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
     kw = _kwargs(d, 1)
     dt0 = int(kw["dt_since_start"][0])
     outs = sd.suews_cal_multitsteps(metforcingblock=met, len_sim=288, **kw)
     assert len(outs) == 6
     assert [o.shape[1] for o in outs] == [87, 103, 32, 138, 31, 50]
     _check_blocks(outs, ref, 288)
-    # SOLWEIG block: date columns + NAN (driver.f95:1040); ESTM untouched on this path
-    assert np.array_equal(outs[4][:, :5], ref["SUEWS"][:, :5]) and np.all(outs[4][:, 5:] == -999.0)
+    # ESTM block: never written on this path (StorageHeatMethod = 4 is rejected): date columns + -999
+    assert np.array_equal(outs[2][:, :5], ref["SUEWS"][:, :5]) and np.all(outs[2][:, 5:] == -999.0)
     # INTENT(INOUT) arguments were advanced in place
     assert int(kw["dt_since_start"][0]) == dt0 + 288 * 300
     st = cell.state_dict()
@@ -62,7 +62,7 @@ def test_cal_multitsteps_matches_oracle():
 
     # a second call continues from the updated arguments (supy's chunked runs)
     met2 = fx.forcing(2005)[288:288 + 36]
-    ref2 = cell.run(met2)
+    ref2 = cell.run(met2, want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
     outs2 = sd.suews_cal_multitsteps(metforcingblock=met2, **kw)
     _check_blocks(outs2, ref2, 36, tol=1e-9)
 
@@ -73,7 +73,7 @@ def test_cal_main_step_by_step():
     d = fx.state_init(2005)
     nstep = 14
     met = fx.forcing(2005)[:nstep]
-    ref = ol.Cell(d).run(met)
+    ref = ol.Cell(d).run(met, want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
     kw = _kwargs(d, 0)
     cols = {"iy": 0, "id": 1, "it": 2, "imin": 3, "qn1_obs": 4, "qs_obs": 7, "qf_obs": 8, "avu1": 9, "avrh": 10, "temp_c": 11,
             "press_hpa": 12, "precip": 13, "avkdn": 14, "snowfrac_obs": 15, "ldown_obs": 16, "fcld_obs": 17, "wu_m3": 18,
@@ -86,7 +86,7 @@ def test_cal_main_step_by_step():
         line = sd.suews_cal_main(**kw)
         assert [x.size for x in line] == [5, 82, 98, 27, 133, 26, 45]
         assert np.array_equal(line[0], ref["SUEWS"][i, :5])
-        for k, group in ((1, "SUEWS"), (4, "RSL"), (6, "DailyState")):
+        for k, group in ((1, "SUEWS"), (4, "RSL"), (5, "SOLWEIG"), (6, "DailyState")):
             r = ref[group][i:i + 1, 5:]
             e = rel_err(line[k][None, :], r, group)
             # single rows have no column history for the scale: use the day-1 tolerance on max(|ref|, 1)
@@ -94,7 +94,6 @@ def test_cal_main_step_by_step():
             assert np.nanmax(e) <= TOL_DAY1, (i, group, float(np.nanmax(e)))
         # the caller advances the clock between SUEWS_cal_Main calls (driver.f95:3482, SuMin :590)
         kw["dt_since_start"] = kw["dt_since_start"] + tstep
-    assert np.all(line[5] == -999.0)
 
 
 def test_gfortran_positional_symbol_equals_pointer_table_call():

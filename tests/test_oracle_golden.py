@@ -3,8 +3,9 @@
 Test/BaseRun/2020b: the complete SUEWS_cal_Main argument dump at the first step of 2005
 (test1_2005_state_init.txt) is replayed for 1440 five-minute steps; the hourly aggregates must
 reproduce the reference's text outputs to the printed precision: SUEWS (82 cols), snow (98),
-RSL (133), DailyState (45).  The 2004 leg (105 408 steps) is pinned by the year-long DailyState
-golden (366 x 45), the only full-year golden that survives in the reference checkout.
+RSL (133), DailyState (45), SOLWEIG (26).  The 2004 leg (105 408 steps) is pinned by the year-long
+DailyState (366 x 45) and SOLWEIG (8784 x 26) goldens, the full-year outputs that survive in the reference
+checkout.
 """
 import numpy as np
 import pytest
@@ -16,7 +17,7 @@ import oracle_lib as ol
 @pytest.fixture(scope="module")
 def run2005():
     cell = ol.Cell(fx.state_init(2005))
-    return cell.run(fx.forcing(2005), want=("SUEWS", "snow", "RSL", "DailyState"))
+    return cell.run(fx.forcing(2005), want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
 
 
 def test_forcing_disaggregation_matches_dump():
@@ -66,11 +67,40 @@ def test_oracle_dailystate_2005(run2005):
     _check_daily(run2005["DailyState"], "ref_2005_DailyState.txt")
 
 
-@pytest.mark.slow
-def test_oracle_dailystate_full_year_2004():
+@pytest.fixture(scope="module")
+def run2004():
     cell = ol.Cell(fx.state_init(2004))
-    out = cell.run(fx.forcing(2004), want=("DailyState",))
-    _check_daily(out["DailyState"], "ref_2004_DailyState.txt")
+    return cell.run(fx.forcing(2004), want=("DailyState", "SOLWEIG"))
+
+
+@pytest.mark.slow
+def test_oracle_dailystate_full_year_2004(run2004):
+    _check_daily(run2004["DailyState"], "ref_2004_DailyState.txt")
+
+
+def _check_solweig(block, fname, nhours):
+    """SOLWEIG point diagnostics (26 columns, all hourly means).  I0 is only assigned in daylight by the
+    reference (solweig.f95:270); at night its output is stack residue, so hours with any night step are masked."""
+    hdr, ref = fx.load_ref_table(fname)
+    ours = fx.aggregate_hourly(block, "SOLWEIG")
+    assert ours.shape == (nhours, 26) and ref.shape == (nhours, 31)
+    assert np.array_equal(block[11::12, :4], ref[:, :4])
+    night = (block[:, 5 + 1].reshape(nhours, 12) <= 0).any(axis=1)          # altitude <= 0 at some step of the hour
+    for c in range(26):
+        r = ref[:, 5 + c]
+        ok = np.isnan(r) | (np.abs(ours[:, c] - r) <= 0.6e-6 + 1e-9 * np.abs(np.nan_to_num(r)))
+        if hdr[5 + c] == "I0":
+            ok = ok | night
+        assert ok.all(), (hdr[5 + c], int(np.argmin(ok)), ours[~ok, c][:3], r[~ok][:3])
+
+
+def test_oracle_solweig_2005(run2005):
+    _check_solweig(run2005["SOLWEIG"], "ref_2005_SOLWEIG_60.txt", 120)
+
+
+@pytest.mark.slow
+def test_oracle_solweig_full_year_2004(run2004):
+    _check_solweig(run2004["SOLWEIG"], "ref_2004_SOLWEIG_60.txt", 8784)
 
 
 def test_sun_position_golden_quirk():

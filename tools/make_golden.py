@@ -10,7 +10,7 @@ and committed.  Nothing here is reference *code*: only its test data.
   forcing_2005_5min.txt         Test/BaseRun/2019a/Input/test_2005_data_5.txt (1440 rows)
   forcing_2005_60min.txt        Test/BaseRun/2020b/Input/test_2005_data_60.txt (119 rows)
   forcing_2004_60min.txt        Test/BaseRun/2020b/Input/test_2004_data_60.txt.long (8784 rows)
-  ref_2005_{SUEWS,snow,RSL}_60.txt, ref_2005_DailyState.txt, ref_2004_DailyState.txt
+  ref_2005_{SUEWS,snow,RSL,SOLWEIG}_60.txt, ref_2005_DailyState.txt, ref_2004_DailyState.txt, ref_2004_SOLWEIG_60.txt
                                 the reference's golden outputs (hourly, 4-6 decimals)
 """
 import json, os, re, shutil
@@ -62,6 +62,8 @@ def main():
         ("2020b/Output/test1_2005_RSL_60.txt", "ref_2005_RSL_60.txt"),
         ("2020b/Output/test1_2005_DailyState.txt", "ref_2005_DailyState.txt"),
         ("2020b/Output/test1_2004_DailyState.txt", "ref_2004_DailyState.txt"),
+        ("2020b/Output/test1_2005_SOLWEIG_60.txt", "ref_2005_SOLWEIG_60.txt"),
+        ("2020b/Output/test1_2004_SOLWEIG_60.txt", "ref_2004_SOLWEIG_60.txt"),
     ]
     for src, dst in cp:
         shutil.copyfile(f"{REF}/{src}", os.path.join(OUT, dst))
