@@ -62,6 +62,24 @@ SU_INL double su_rcp_fast(double d)
    r = __fma_rn(r, e, r);
    return r;
 }
+// Correctly rounded x^(1/4) for a normal positive x: sqrt(sqrt(x)) (two roundings, ~0.75 ulp) corrected by one
+// Newton step whose residual y^4 - x is formed in double-double.  Used where a caller raises the root back to the
+// fourth power and subtracts the original (NARP's snow surface temperature): that difference is pure rounding
+// residue, the reference branches on its sign, and glibc's pow -- which the oracle and the reference use -- is
+// correctly rounded in all but ~4 % of arguments.
+SU_INL double su_root4_cr(double x)
+{
+   double y = sqrt(sqrt(x));
+   for (int it = 0; it < 2; it++) {
+      const double h1 = y * y, l1 = __fma_rn(y, y, -h1);
+      const double h2 = h1 * h1, l2 = __fma_rn(h1, h1, -h2) + 2.0 * h1 * l1;
+      const double e = (h2 - x) + l2;              // y^4 - x
+      const double yn = y - e / (4.0 * h1 * y);    // rounds to the double nearest the corrected root
+      if (yn == y) break;
+      y = yn;
+   }
+   return y;
+}
 SU_INL double su_pow(double x, double y)
 {
    if (y == 0.5) return sqrt(x);

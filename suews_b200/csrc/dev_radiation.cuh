@@ -277,7 +277,7 @@ SU_DEVNI void NARP(const double *sfr, const double *SnowFrac, const double *alb,
 
    double qn1_cum = 0, kup_cum = 0, lup_cum = 0, tsurf_cum = 0, qsf = 0, qs = 0;
    const double TS_SNOW_NARP =
-      (nrm_use < 10) ? pow((NARP_EMIS_SNOW * SIGMATK4) / (NARP_EMIS_SNOW * SIGMA_SB), F(0.25)) : 0.0;
+      (nrm_use < 10) ? su_root4_cr((NARP_EMIS_SNOW * SIGMATK4) / (NARP_EMIS_SNOW * SIGMA_SB)) : 0.0;   // **0.25, correctly rounded
    for (int is = 0; is < NSURF; is++) {
       double ALB0 = zen_alb ? alb[is] + dalb : alb[is];
       double EMIS0 = emis[is];

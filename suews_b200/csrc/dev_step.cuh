@@ -261,6 +261,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    if (C.dRH != 0) avRh = SU_MIN(100.0, SU_MAX(F(0.01), avRh));
    const double avkdn = R.avkdn, avU1 = R.avU1, Precip = R.Precip, Press_hPa = R.Press_hPa;
    const bool temp_will_rewrite = fabs(Temp_C) < F(0.001000);
+   const double Temp_C_in = Temp_C;
 
    int lv_sw = (int)S.lv_switch;
    double qn1_av_next = S.qn1_av, dqndt_next = S.dqndt, qn1_s_av_next = S.qn1_s_av, dqnsdt_next = S.dqnsdt;
@@ -316,7 +317,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    }
 
    bool done = !live || dg.fatal != 0;
-   double Ts_iter = Temp_C;
+   double Ts_iter = Temp_C_in;   // driver.f95:640: taken before cal_AtmMoist can rewrite Temp_C
    // state after the previous two trips, for the exact cycle detection in phase L3
    double cyc_qh[2] = {0, 0}, cyc_ts[2] = {0, 0}, cyc_alb[2] = {0, 0};
    int cyc_sw[2] = {-1, -1};

@@ -345,6 +345,41 @@ def test_replicated_cells_equal_single_cell():
     b1.close()
 
 
+@pytest.mark.parametrize("scheme", ["default", "snow", "baserun"])
+def test_differential_seasons(scheme):
+    """Synthetic cells started in winter, spring and late summer (melting snow, freezing rain, temperatures crossing
+    0 degC: the branches a January start never reaches), two days each: flux sums and end state equal the per-cell
+    oracle runs far inside the tolerance.  tools/diff_fuzz.py is the long version of this test."""
+    from suews_b200 import OUT_SUM82, SuewsBatch, synth
+    base = fx.state_init(2005)
+    allmet = fx.forcing(2004)
+    n = 16
+    for day0 in (59, 121, 288):
+        met = allmet[day0 * 288:(day0 + 2) * 288]
+        b = SuewsBatch(n, 1)
+        _m, site = synth.build_batch(b, base, cell0=17 * day0, scheme=scheme)
+        b.upload()
+        b.set_forcing(met)
+        b.advance(0, met.shape[0], OUT_SUM82)
+        sums = b.sums()
+        d0 = synth.base_with_scheme(base, scheme)
+        for c in range(0, n, 2):
+            dd = dict(d0)
+            for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
+                dd[k.lower()] = np.atleast_1d(site[k][c])
+            m = met.copy()
+            m[:, 11] += site["dTemp_C"][c]
+            m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + site["dRH"][c]))
+            cell = ol.Cell(dd)
+            rs = cell.run(m, want=("SUEWS",))["SUEWS"][:, 5:].sum(axis=0)
+            scale = np.abs(rs[list(PARITY_COLS.values())]).max()
+            for nm, col in PARITY_COLS.items():
+                assert abs(sums[c, col] - rs[col]) <= 1e-9 * max(abs(rs[col]), 1e-6 * scale), (scheme, day0, c, nm)
+            for nm in ("state_id", "soilstore_id", "SnowPack", "SnowWater", "SnowFrac", "qn1_av"):
+                assert np.allclose(b.get_state(nm)[c], cell.get_state(nm), rtol=1e-8, atol=1e-10), (scheme, day0, c, nm)
+        b.close()
+
+
 def test_full_size_batch_properties():
     """BASELINE configs[2] size (1 048 576 cells on one GPU) through size-independent properties: no fatal cell,
     energy balance closed by construction (QH is the residual), water balance closed to the model's own
