@@ -15,10 +15,20 @@ ndays = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 tol = float(sys.argv[5]) if len(sys.argv) > 5 else 1e-9
 base = fx.state_init(2005)
 met = fx.forcing(2004)[day0 * 288:(day0 + ndays) * 288]
+if os.environ.get("SU_LDOWN"):      # a physical incoming long-wave series (the test forcing's column is not one)
+    met = met.copy()
+    met[:, 16] = 0.85 * 5.67e-8 * (met[:, 11] + 273.15) ** 4
 b = SuewsBatch(1, 1)
 _m, site = synth.build_batch(b, base, cell0=17 * day0 + cellno, scheme=scheme)
+over = {}
+for kv in os.environ.get("SU_OVER", "").split(","):      # e.g. SU_OVER=netradiationmethod=11,gsmodel=1
+    if "=" in kv:
+        k, v = kv.split("=")
+        over[k] = [float(v)]
+        b.set_class_param(0, k, np.asarray([float(v)]))
 b.upload(); b.set_forcing(met); b.advance(0, met.shape[0], OUT_FULL)
 d0 = synth.base_with_scheme(base, scheme)
+d0.update(over)
 dd = dict(d0)
 for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
     dd[k.lower()] = np.atleast_1d(site[k][0])
