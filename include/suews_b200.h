@@ -39,11 +39,13 @@ enum {
    SUEWS_E_BAD_NAME = 2002,    /* unknown parameter/state name */
    SUEWS_E_BAD_SIZE = 2003,    /* value count does not match the field */
    SUEWS_E_BAD_ARG = 2004,
-   SUEWS_E_NOT_IMPL = 1003     /* scheme outside this library (AnOHM, ESTM): see suews_last_error */
+   SUEWS_E_NOT_IMPL = 1003,    /* scheme outside this library (AnOHM): see suews_last_error */
+   SUEWS_E_ESTM_INPUT = 1005   /* StorageHeatMethod 4/14 without ESTM state / surface-temperature forcing */
 };
 
 /* where a named field lives (suews_b200_field_info) */
-enum { SUEWS_KIND_CLASS_INT = 0, SUEWS_KIND_CLASS_DBL = 1, SUEWS_KIND_CELL_DBL = 2, SUEWS_KIND_STATE_DBL = 3 };
+enum { SUEWS_KIND_CLASS_INT = 0, SUEWS_KIND_CLASS_DBL = 1, SUEWS_KIND_CELL_DBL = 2, SUEWS_KIND_STATE_DBL = 3,
+       SUEWS_KIND_ESTM_STATE = 4 /* ESTM element temperatures: set/get through suews_b200_set_state / _get_state */ };
 
 /* output policy bits for suews_b200_advance */
 enum {
@@ -79,13 +81,25 @@ int suews_b200_upload(suews_b200_handle h);
  * clock/ephemeris records on the device. */
 int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps);
 
+/* ESTM (StorageHeatMethod 4/14) only.  The reference keeps ESTM's parameters and element temperatures in MODULE
+ * ESTM_data (suews_phys_estm.f95:1-176), outside the SUEWS_cal_Main argument list.  Here the parameters are class
+ * fields under the module's variable names (evolveTibld, TsurfChoice, ibldCHmod, Nibld/Nwall/Nroof/Nground,
+ * LBC_soil [degC], THEAT_ON/OFF/fix [K], ivf_*, z/k/r of ibld, wall, roof and ground (5 each), nroom, alb_ibld,
+ * em_ibld, CH_iroof/iwall/ibld, Tfloor [K]), the wall area is the per-cell field AreaWall, and the variables ESTM
+ * carries between calls are per-cell state of kind SUEWS_KIND_ESTM_STATE (Tair2, Tievolve, lup_ground/wall/roof,
+ * T0_ibld/ground/wall/roof, TN_wall/roof, Tground/Twall/Troof/Tibld (5), Tw_4 (5 x 4), HVAC, Tair2Set,
+ * NewtonConverged).  The surface-temperature forcing replaces ESTMForcingData / Ts5mindata_ir
+ * (suews_ctrl_translate.f95:1264-1265): ts5 is [nsteps x 13] column-major (iy id it imin Tiair Tsurf Troof Troad
+ * Twall Twall_n Twall_e Twall_s Twall_w), shared by all cells, the same rows as the forcing block set before it. */
+int suews_b200_set_estm_forcing(suews_b200_handle h, const double *ts5, int nsteps);
+
 /* Advance all cells over forcing rows [step0, step0 + nsteps).  One kernel launch.  Asynchronous
  * with respect to the host; suews_b200_sync waits and returns the first fatal cell error (0 if none). */
 int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags);
 int suews_b200_sync(suews_b200_handle h);
 
 /* Results.  sums: [ncell][82] (cell-major).  Full blocks (after SUEWS_OUT_FULL): per cell a
- * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50/31 columns). */
+ * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50/31/32 columns). */
 int suews_b200_get_sums(suews_b200_handle h, double *sums);
 /* selected columns only (0-based indices into the 82-column SUEWS line), [ncell][ncols]; device -> pinned host */
 int suews_b200_get_sums_cols(suews_b200_handle h, const int *cols, int ncols, double *out);
@@ -93,7 +107,7 @@ int suews_b200_device_sync(suews_b200_handle h);
 /* measured FP64 FMA throughput of the device in TFLOP/s (compute-roofline denominator) */
 int suews_b200_fp64_peak(int device, double *tflops);
 int suews_b200_reset_sums(suews_b200_handle h);
-int suews_b200_get_block(suews_b200_handle h, const char *group /* "SUEWS","snow","RSL","DailyState","SOLWEIG" */, int cell,
+int suews_b200_get_block(suews_b200_handle h, const char *group /* "SUEWS","snow","RSL","DailyState","SOLWEIG","ESTM" */, int cell,
                          double *block, int nsteps, int ncol);
 int suews_b200_get_diag(suews_b200_handle h, int *fatal_code_per_cell, unsigned long long *warn_mask2_per_cell,
                         long long *tsurf_iterations_per_cell);
@@ -124,8 +138,16 @@ int suews_refapi_arginfo(int which, int i, const char **name, int *is_int, int *
  * (suews_cal_main_, suews_cal_multitsteps_: 220 / 200 pointer parameters) are exported too; their
  * prototypes are SUEWS_CAL_MAIN_PARAMS / SUEWS_CAL_MULTITSTEPS_PARAMS in suews_refargs.inc.  They return
  * nothing, like the SUBROUTINEs they replace: check suews_last_error afterwards. */
-/* forget the process-wide hidden SAVE state (Lat_vap switches, NARP alb1) -- a fresh reference process */
+/* forget the process-wide hidden SAVE state (Lat_vap switches, NARP alb1, MODULE ESTM_data) -- a fresh reference process */
 void suews_refapi_reset_hidden(void);
+/* MODULE ESTM_data (suews_phys_estm.f95:1-176) for the reference-shaped calls.  The reference's SUEWS_cal_Main reads
+ * ESTM's parameters and element temperatures from that module, not from its arguments; the host fills the module
+ * (ESTM_initials :589, SUEWS_Translate, ESTM_translate :637) before the call.  Here the host does the same through
+ * these two functions, by the module's variable names (the ESTM class fields, AreaWall and the ESTM state fields
+ * listed at suews_b200_set_estm_forcing); state variables are updated by every SUEWS_cal_Main / _multitsteps call
+ * with StorageHeatMethod 4/14 and can be read back.  Ts5mindata_ir is the argument of those calls. */
+int suews_estm_data_set(const char *name, const double *vals, int n);
+int suews_estm_data_get(const char *name, double *vals, int n);
 
 int suews_cal_sunposition_c(double year, double idectime, double UTC, double locationlatitude,
                             double locationlongitude, double locationaltitude, double *sunazimuth,

@@ -17,6 +17,8 @@ typedef struct {
 
 #define PD(f) {#f, 0, offsetof(SoParams, f), (int)(sizeof(((SoParams *)0)->f) / sizeof(double))}
 #define PI(f) {#f, 1, offsetof(SoParams, f), (int)(sizeof(((SoParams *)0)->f) / sizeof(int))}
+#define PDE(f) {#f, 0, offsetof(SoParams, estm.f), (int)(sizeof(((SoParams *)0)->estm.f) / sizeof(double))}
+#define PIE(f) {#f, 1, offsetof(SoParams, estm.f), (int)(sizeof(((SoParams *)0)->estm.f) / sizeof(int))}
 static const SoField PARAM_FIELDS[] = {
    PI(AerodynamicResistanceMethod), PI(BaseTMethod), PI(Diagnose), PI(DiagQN), PI(DiagQS), PI(startDLS), PI(endDLS),
    PI(EmissionsMethod), PI(Gridiv), PI(gsModel), PI(Ie_end), PI(Ie_start), PI(EvapMethod), PI(LAICalcYes),
@@ -41,18 +43,29 @@ static const SoField PARAM_FIELDS[] = {
    PD(beta_enh_bioCO2), PD(GDDFull), PD(LAIMax), PD(LAIMin), PD(min_res_bioCO2), PD(resp_a), PD(resp_b), PD(SDDFull),
    PD(theta_bioCO2), PD(SnowProf_24hr), PD(LAIPower), PD(OHM_coef), PD(WaterDist), PD(AHProf_24hr),
    PD(HumActivity_24hr), PD(PopProf_24hr), PD(TraffProf_24hr), PD(WUProfA_24hr), PD(WUProfM_24hr),
+   /* MODULE ESTM_data (suews_phys_estm.f95:1-176) */
+   PIE(evolveTibld), PIE(TsurfChoice), PIE(ibldCHmod), PIE(Nibld), PIE(Nwall), PIE(Nroof), PIE(Nground),
+   PDE(LBC_soil), PDE(THEAT_ON), PDE(THEAT_OFF), PDE(THEAT_fix), PDE(ivf_iw), PDE(ivf_ir), PDE(ivf_ii), PDE(ivf_if),
+   PDE(ivf_ww), PDE(ivf_wr), PDE(ivf_wi), PDE(ivf_wf), PDE(ivf_rw), PDE(ivf_ri), PDE(ivf_rf), PDE(ivf_fw), PDE(ivf_fr),
+   PDE(ivf_fi), PDE(zibld), PDE(kibld), PDE(ribld), PDE(zwall), PDE(kwall), PDE(rwall), PDE(zroof), PDE(kroof),
+   PDE(rroof), PDE(zground), PDE(kground), PDE(rground), PDE(nroom), PDE(alb_ibld), PDE(em_ibld), PDE(CH_iroof),
+   PDE(CH_iwall), PDE(CH_ibld), PDE(AreaWall), PDE(Tfloor),
 };
 #undef PD
 #undef PI
 
 #define SD(f) {#f, 0, offsetof(SoState, f), (int)(sizeof(((SoState *)0)->f) / sizeof(double))}
 #define SI(f) {#f, 1, offsetof(SoState, f), (int)(sizeof(((SoState *)0)->f) / sizeof(int))}
+#define SDE(f) {#f, 0, offsetof(SoState, estm.f), (int)(sizeof(((SoState *)0)->estm.f) / sizeof(double))}
 static const SoField STATE_FIELDS[] = {
    SD(qn1_av), SD(dqndt), SD(qn1_s_av), SD(dqnsdt), SD(SnowfallCum), SD(SnowAlb), SD(IceFrac), SD(SnowWater),
    SD(SnowDens), SD(SnowFrac), SD(SnowPack), SD(soilstore_id), SD(state_id), SD(StoreDrainPrm), SD(alb), SD(GDD_id),
    SD(SDD_id), SD(LAI_id), SD(Tmin_id), SD(Tmax_id), SD(lenDay_id), SD(DecidCap_id), SD(albDecTr_id),
    SD(albEveTr_id), SD(albGrass_id), SD(porosity_id), SD(HDD_id), SD(WUDay_id), SD(Tair_av), SI(dt_since_start),
    SI(tstep_prev), SI(lv_switch1), SI(lv_switch2), SD(alb1_hidden),
+   SDE(Tair2), SDE(Tievolve), SDE(lup_ground), SDE(lup_wall), SDE(lup_roof), SDE(T0_ibld), SDE(T0_ground), SDE(T0_wall),
+   SDE(T0_roof), SDE(TN_wall), SDE(TN_roof), SDE(Tground), SDE(Twall), SDE(Troof), SDE(Tibld), SDE(Tw_4), SDE(HVAC),
+   SDE(Tair2Set), SDE(NewtonConverged),
 };
 #undef SD
 #undef SI
@@ -155,6 +168,16 @@ int so_run(const SoParams *p, SoState *st, const double *met, int len_sim, doubl
    return cx.fatal_code;
 }
 
+/* ESTM forcing block for the next so_run / so_run_cells: [len_sim x 13] column-major (iy id it imin Tiair Tsurf
+ * Troof Troad Twall Twall_n Twall_e Twall_s Twall_w), or NULL.  The pointer is borrowed. */
+void so_set_ts5_block(const double *ts5) { so_ts5_block = ts5; }
+
+/* First-call initialisation of the ESTM element temperatures (ESTM_translate, ESTMStart == 1) */
+void so_estm_start(const SoParams *p, SoState *st, const double *ts_row1_13)
+{
+   so_ESTM_translate_start(p, st->alb, ts_row1_13, &st->estm);
+}
+
 /* Many independent cells, each with its own params/state; shared or per-cell forcing.
  * P0-style reduction for the CPU baseline: per-cell sums of the SUEWS line over the run.
  * met_stride = 0 -> all cells share one forcing block. */
@@ -176,6 +199,7 @@ int so_run_cells(int ncell, const SoParams *params, SoState *states, const doubl
          f.qn1_obs = MET(4); f.qs_obs = MET(7); f.qf_obs = MET(8); f.avU1 = MET(9); f.avRh = MET(10);
          f.Temp_C = MET(11); f.Press_hPa = MET(12); f.Precip = MET(13); f.avkdn = MET(14); f.snowFrac_obs = MET(15);
          f.ldown_obs = MET(16); f.fcld_obs = MET(17); f.wu_m3 = MET(18); f.xsmd = MET(19); f.LAI_obs = MET(20);
+         for (k = 0; k < 13; k++) f.Ts5mindata_ir[k] = so_ts5_block ? so_ts5_block[(size_t)ir + (size_t)len_sim * k] : -999;
 #undef MET
          so_cal_main(&cx, &params[c], &f, &states[c], &out);
          states[c].dt_since_start += params[c].tstep;

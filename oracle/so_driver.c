@@ -5,7 +5,7 @@
  * cal_tair_av :3530, cal_tsfc :3558, set_nan :2737.
  *
  * Not restated (fatal code 1003 when selected): StorageHeatMethod 3 (AnOHM)
- * and 4/14 (ESTM) -- both need module state outside the cal_Main argument
+ * -- needs module state outside the cal_Main argument
  * list.  SOLWEIG_cal_main (diagnostic only) is not restated: its output line
  * is -999-filled. */
 #include "suews_oracle.h"
@@ -138,7 +138,8 @@ static void cal_Qn(SoCtx *cx, const SoParams *p, const SoForcing *f, const doubl
 }
 
 /* driver.f95:1457-1612 */
-static void cal_Qs(SoCtx *cx, const SoParams *p, const SoForcing *f, int dt_since_start,
+static void cal_Qs(SoCtx *cx, const SoParams *p, const SoForcing *f, int dt_since_start, SoEstmState *estm,
+                   double zenith_deg, double ldown, double Tair_av,
                    const double soilstore_id[NSURF], const double state_id[NSURF], const double SnowFrac[NSURF],
                    const double HDD_id[12], double qf, double qn1, double qn1_av_prev, double dqndt_prev,
                    double qn1_s_av_prev, double dqnsdt_prev, double qn1_S, double dataOutLineESTM[NCOL_ESTM],
@@ -167,7 +168,8 @@ static void cal_Qs(SoCtx *cx, const SoParams *p, const SoForcing *f, int dt_sinc
    } else if (p->StorageHeatMethod == 3) {
       so_error_hint(cx, 1003, "oracle: StorageHeatMethod=3 (AnOHM) not restated", -999, -999, 3);
    } else if (p->StorageHeatMethod == 4 || p->StorageHeatMethod == 14) {
-      so_error_hint(cx, 1003, "oracle: StorageHeatMethod=4/14 (ESTM) not restated", -999, -999, 4);
+      so_ESTM(cx, p, estm, p->tstep, f->avkdn, f->avU1, f->Temp_C, zenith_deg, f->avRh, f->Press_hPa, ldown, p->bldgH,
+              f->Ts5mindata_ir, Tair_av, dataOutLineESTM, qs);
    }
 }
 
@@ -491,7 +493,7 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
              &qn1_snowfree, &qn1_S, &kclear, &kup, &lup, &tsurf, qn1_ind_snow, kup_ind_snow, Tsurf_ind_snow, tsurf_ind,
              &alb1, nx.SnowFrac, &nx.SnowAlb);
 
-      cal_Qs(cx, p, &fl, st->dt_since_start, pv.soilstore_id, pv.state_id, nx.SnowFrac, nx.HDD_id, qf, qn1, pv.qn1_av,
+      cal_Qs(cx, p, &fl, st->dt_since_start, &st->estm, ZENITH_deg, ldown, nx.Tair_av, pv.soilstore_id, pv.state_id, nx.SnowFrac, nx.HDD_id, qf, qn1, pv.qn1_av,
              pv.dqndt, pv.qn1_s_av, pv.dqnsdt, qn1_S, out->ESTM, &qs, &nx.qn1_av, &nx.dqndt, &nx.qn1_s_av, &nx.dqnsdt,
              deltaQi, &a1, &a2, &a3);
 
@@ -563,6 +565,7 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
    /* commit (driver.f95:965-994); caller-side clock and hidden SAVEs are not part of *_next */
    {
       int dt = st->dt_since_start, tp = st->tstep_prev, s1 = st->lv_switch1, s2 = st->lv_switch2;
+      nx.estm = st->estm;   /* MODULE ESTM_data variables: advanced in place by every trip */
       *st = nx;
       st->dt_since_start = dt;
       st->tstep_prev = tp;
@@ -672,6 +675,7 @@ void so_cal_multitsteps(SoCtx *cx, const SoParams *p, SoState *st, const double 
       f.wu_m3 = MET(18);
       f.xsmd = MET(19);
       f.LAI_obs = MET(20);
+      for (c = 0; c < 13; c++) f.Ts5mindata_ir[c] = so_ts5_block ? so_ts5_block[(size_t)ir + (size_t)len_sim * c] : -999;
 
       so_cal_main(cx, p, &f, st, &out);
       st->dt_since_start = st->dt_since_start + p->tstep;

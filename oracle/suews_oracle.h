@@ -39,6 +39,34 @@ enum {
    NCOL_SOLWEIG = 26, NCOL_DAILY = 45
 };
 
+/* ESTM (StorageHeatMethod 4/14) does not receive its parameters and state through the SUEWS_cal_Main argument
+ * list: they are variables of MODULE ESTM_data (suews_phys_estm.f95:1-176), filled by ESTM_initials (:589-634,
+ * namelist ESTMinput.nml), by SUEWS_Translate (suews_ctrl_translate.f95:393-394, :470-670: facet layers) and by
+ * ESTM_translate (:637-967).  Here the facet-level values after SUEWS_Translate are parameters (SoEstmParams) */
+typedef struct {
+   int evolveTibld, TsurfChoice, ibldCHmod;   /* ESTMinput.nml */
+   int Nibld, Nwall, Nroof, Nground;          /* layers per element (suews_ctrl_translate.f95:641-670) */
+   double LBC_soil;                            /* deg C */
+   double THEAT_ON, THEAT_OFF, THEAT_fix;      /* K (converted by ESTM_initials, estm.f95:617-619) */
+   double ivf_iw, ivf_ir, ivf_ii, ivf_if, ivf_ww, ivf_wr, ivf_wi, ivf_wf, ivf_rw, ivf_ri, ivf_rf, ivf_fw, ivf_fr, ivf_fi;
+   double zibld[5], kibld[5], ribld[5], zwall[5], kwall[5], rwall[5], zroof[5], kroof[5], rroof[5];
+   double zground[5], kground[5], rground[5];
+   double nroom, alb_ibld, em_ibld, CH_iroof, CH_iwall, CH_ibld;
+   double AreaWall;                            /* fwall = AreaWall/SurfaceArea (suews_ctrl_translate.f95:393-394) */
+   double Tfloor;                              /* K (estm.f95:673-674: 20 degC) */
+} SoEstmParams;
+
+/* and the variables ESTM carries from call to call are state (the *_grids copies, estm.f95:1587-1603, and the
+ * SAVE'd HVAC / Tair2Set / NewtonPolynomial's `converged`). */
+typedef struct {
+   double Tair2, Tievolve, lup_ground, lup_wall, lup_roof, T0_ibld, T0_ground, T0_wall, T0_roof, TN_wall, TN_roof;
+   double Tground[5], Twall[5], Troof[5], Tibld[5];
+   double Tw_4[20];            /* (Nwall,4) column-major with leading dimension 5 here */
+   double HVAC;                /* LOGICAL, SAVE (estm.f95:165) */
+   double Tair2Set;            /* INTEGER :: Tair2Set = 0, SAVE (estm.f95:1162) */
+   double NewtonConverged;     /* LOGICAL :: converged = .FALSE., SAVE (estm.f95:222): once true, true for ever */
+} SoEstmState;
+
 /* Static per-cell configuration: the INTENT(IN) arguments of SUEWS_cal_Main
  * that do not change from step to step (suews_ctrl_driver.f95:97-285).
  * Arrays keep Fortran column-major storage; see the index macros below. */
@@ -76,6 +104,7 @@ typedef struct {
    double WaterDist[(NSURF + 1) * (NSURF - 1)]; /* (8,6) -> [i + 8*j] */
    double AHProf_24hr[48], HumActivity_24hr[48], PopProf_24hr[48], TraffProf_24hr[48];
    double WUProfA_24hr[48], WUProfM_24hr[48];
+   SoEstmParams estm;
 } SoParams;
 
 #define PROF24(p, hr, col) ((p)[(hr) + 24 * (col)])       /* col 0 = weekday, 1 = weekend */
@@ -89,6 +118,7 @@ typedef struct {
    int iy, id, it, imin, isec;
    double avkdn, avRh, avU1, fcld_obs, LAI_obs, ldown_obs, Precip, Press_hPa;
    double qn1_obs, qs_obs, qf_obs, snowFrac_obs, Temp_C, wu_m3, xsmd;
+   double Ts5mindata_ir[13];   /* ESTM surface-temperature forcing row (driver.f95:276); unused unless ESTM runs */
 } SoForcing;
 
 /* Evolving per-cell state: the 29 INTENT(INOUT) arguments
@@ -112,6 +142,7 @@ typedef struct {
    /* cal_Main's local alb1 is only assigned when some surface carries snow (narp.f95:366-370); its
     * stack slot keeps the previous call's value otherwise (golden snow file: 0 on step 1, 0.18 after) */
    double alb1_hidden;
+   SoEstmState estm;
 } SoState;
 
 typedef struct {
@@ -367,6 +398,19 @@ void so_SOLWEIG_cal_main(int id, int it, double dectime, double lamdaP, double l
                          double Temp_C, double avrh, double Press_hPa, double Tg, double lat, double zenith_deg,
                          double azimuth, double scale, double alb_ground, double alb_bldg, double emis_ground,
                          double emis_wall, double heightgravity, double out[NCOL_SOLWEIG]);
+
+/* ---- suews_phys_estm.f95 ---- */
+double so_heatcapacity_air(double TK, double RH, double P);
+double so_NewtonPolynomial(double x0, const double Pcoeff[5], double conv, int maxiter, double *converged_save);
+void so_heatcond1d(double *T, double *Qs, const double *dx, double dt, const double *k, const double *rhocp, int n,
+                   const double bc[2], const int bctype[2]);
+void so_ESTM_translate_start(const SoParams *p, const double alb[NSURF], const double Ts5mindata_row1[13],
+                             SoEstmState *e);
+void so_ESTM(SoCtx *cx, const SoParams *p, SoEstmState *e, int tstep, double avkdn, double avu1, double temp_c,
+             double zenith_deg, double avrh, double press_hpa, double ldown, double bldgh,
+             const double Ts5mindata_ir[13], double Tair_av, double dataOutLineESTM[NCOL_ESTM], double *QS);
+/* optional ESTM forcing block for so_cal_multitsteps / so_run_cells: [len_sim x 13] column-major, or NULL */
+extern const double *so_ts5_block;
 
 /* One cell, one timestep == SUEWS_cal_Main.  Mutates *st (including
  * nothing of dt_since_start: the caller advances it, as in the reference). */

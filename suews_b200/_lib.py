@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsuews_b200.so")
+# SUEWS_B200_LIB: another build of the same library (launch-geometry tuning builds of tools/variants.sh)
+LIB_PATH = os.environ.get("SUEWS_B200_LIB") or os.path.join(_HERE, "libsuews_b200.so")
 
 _lib = None
 
@@ -43,6 +44,7 @@ def lib():
         L.suews_b200_get_clock.argtypes = [H, ip, ip]
         L.suews_b200_upload.argtypes = [H]
         L.suews_b200_set_forcing.argtypes = [H, dp, C.c_int]
+        L.suews_b200_set_estm_forcing.argtypes = [H, dp, C.c_int]
         L.suews_b200_advance.argtypes = [H, C.c_int, C.c_int, C.c_int]
         L.suews_b200_sync.argtypes = [H]
         L.suews_b200_get_sums.argtypes = [H, dp]

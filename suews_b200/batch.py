@@ -11,12 +11,12 @@ import numpy as np
 from . import _lib
 from ._lib import check, dp, ip
 
-NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50, "SOLWEIG": 31}
+NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50, "SOLWEIG": 31, "ESTM": 32}
 OUT_SUM82 = 1
 OUT_FULL = 2
 OUT_SUM7 = 4   # only the seven parity fluxes (output policy P0)
 
-KIND_CLASS_INT, KIND_CLASS_DBL, KIND_CELL, KIND_STATE = 0, 1, 2, 3
+KIND_CLASS_INT, KIND_CLASS_DBL, KIND_CELL, KIND_STATE, KIND_ESTM_STATE = 0, 1, 2, 3, 4
 
 
 def field_info(name):
@@ -99,7 +99,8 @@ class SuewsBatch:
         for name, kind, n in all_fields():
             key = name.lower()
             if key not in low:
-                if name not in ("dTemp_C", "dRH", "alb1_hidden", "lv_switch", "rsl_cache"):
+                # optional: synthetic forcing offsets, hidden SAVE state, and MODULE ESTM_data (not SUEWS_cal_Main arguments)
+                if name not in ("dTemp_C", "dRH", "alb1_hidden", "lv_switch", "rsl_cache") and name not in estm_names():
                     missing.append(name)
                 continue
             v = np.atleast_1d(np.asarray(low[key], dtype=np.float64)).ravel()
@@ -108,7 +109,7 @@ class SuewsBatch:
                 self.set_class_param(cls, name, v)
             elif cells and kind == KIND_CELL:
                 self.set_cell_param(name, v)
-            elif cells and kind == KIND_STATE:
+            elif cells and kind in (KIND_STATE, KIND_ESTM_STATE):
                 self.set_state(name, v)
         if "dt_since_start" in low:
             self.set_clock(int(low["dt_since_start"][0]), int(low.get("tstep_prev", low.get("tstep"))[0]))
@@ -124,6 +125,14 @@ class SuewsBatch:
         assert m.shape[1] == 24
         check(self.L.suews_b200_set_forcing(self.h, m.ctypes.data_as(dp), m.shape[0]))
         self.nsteps = m.shape[0]
+
+    def set_estm_forcing(self, ts5):
+        """ts5: [nsteps, 13] ESTM surface-temperature forcing (iy id it imin Tiair Tsurf Troof Troad Twall Twall_n
+        Twall_e Twall_s Twall_w; the reference's ESTMForcingData, suews_ctrl_translate.f95:1264), same rows as the
+        forcing block set just before.  Only read when StorageHeatMethod is 4/14."""
+        t = np.asfortranarray(np.asarray(ts5, dtype=np.float64))
+        assert t.shape == (self.nsteps, 13)
+        check(self.L.suews_b200_set_estm_forcing(self.h, t.ctypes.data_as(dp), t.shape[0]))
 
     def advance(self, step0, nsteps, out_flags=OUT_SUM82, sync=True):
         check(self.L.suews_b200_advance(self.h, int(step0), int(nsteps), int(out_flags)))
@@ -181,9 +190,26 @@ def all_fields():
         hdr = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "suews_fields.h")).read()
         out = []
         for macro, kind in (("SUEWS_CLASS_INT_FIELDS", 0), ("SUEWS_CLASS_DBL_FIELDS", 1), ("SUEWS_CELL_DBL_FIELDS", 2),
-                            ("SUEWS_STATE_DBL_FIELDS", 3)):
+                            ("SUEWS_STATE_DBL_FIELDS", 3), ("SUEWS_ESTM_STATE_FIELDS", 4)):
             m = re.search(r"#define %s\(X\)(.*?)\n\n" % macro, hdr, re.S)
             for nm, n in re.findall(r"X\((\w+),\s*(\d+)\)", m.group(1)):
                 out.append((nm, kind, int(n)))
         _FIELDS = out
     return _FIELDS
+
+
+_ESTM_NAMES = None
+
+
+def estm_names():
+    """Names of the fields that mirror MODULE ESTM_data (suews_phys_estm.f95:1-176): ESTM parameters and state."""
+    global _ESTM_NAMES
+    if _ESTM_NAMES is None:
+        names = {nm for nm, kind, _n in all_fields() if kind == KIND_ESTM_STATE}
+        names |= {"evolveTibld", "TsurfChoice", "ibldCHmod", "Nibld", "Nwall", "Nroof", "Nground", "LBC_soil", "THEAT_ON",
+                  "THEAT_OFF", "THEAT_fix", "nroom", "alb_ibld", "em_ibld", "CH_iroof", "CH_iwall", "CH_ibld", "Tfloor",
+                  "AreaWall"}
+        names |= {"ivf_" + a + b for a in "iwrf" for b in "iwrf"}
+        names |= {p + e for p in "zkr" for e in ("ibld", "wall", "roof", "ground")}
+        _ESTM_NAMES = names
+    return _ESTM_NAMES

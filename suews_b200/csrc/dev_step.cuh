@@ -27,6 +27,7 @@
 #include "dev_daily.cuh"
 #include "dev_rsl.cuh"
 #include "dev_solweig.cuh"
+#include "dev_estm.cuh"
 
 #ifdef SU_PHASE_SYNC
 #define SU_SYNC() __syncthreads()
@@ -66,7 +67,7 @@ __device__ unsigned long long su_phase_clk[16];
 
 // Optional per-step output lines (reference layouts).  NULL = not wanted.
 struct SuLines {
-   double *datetime5, *suews82, *snow98, *rsl133, *daily45, *sol26;
+   double *datetime5, *suews82, *snow98, *rsl133, *daily45, *sol26, *estm27;
 };
 
 // Tsurf-independent quantities of a step
@@ -240,7 +241,8 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
 // Returns the number of Tsurf iterations used.
 __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
-                          SuewsCellState &S, double *acc82, double *acc7, const SuLines &L)
+                          SuewsCellState &S, double *acc82, double *acc7, const SuLines &L, SuewsEstmState *ES = nullptr,
+                          const double *ts9 = nullptr)
 {
    const double *sfr = C.sfr.v;
    const int sm = P.StabilityMethod;
@@ -286,6 +288,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    int lv_exit[4] = {-1, -1, -1, -1};
    bool rad_invariant = false, rad_done = false, qe_full_done = false;
    // with snow off (and no snow output line wanted) the snow work arrays are neither formed nor committed
+   const bool use_estm = (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14);
    const bool want_snow_line = (L.snow98 != nullptr);
    const bool snow_arrays = (snowUse == 1) || want_snow_line;
    double lv_at_melt = 0;
@@ -297,8 +300,9 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       cal_RoughnessParameters(dg, P.RoughLenMomMethod, C, S.porosity_id, FAI, zH, z0m, zdm, ZZD);
       spa_location_part(E, C.lat, C.lng, C.alt, azimuth, zenith_deg);
       RadMethod(dg, P.NetRadiationMethod, snowUse, nrm_use, AlbedoChoice, ldown_option);
-      // Tsurf enters NARP only through the iteration-based methods (narp.f95:337-346)
-      rad_invariant = (nrm_use < 10);
+      // Tsurf enters NARP only through the iteration-based methods (narp.f95:337-346); ESTM advances its element
+      // temperatures on every call of SUEWS_cal_Qs, i.e. on every trip (dev_estm.cuh)
+      rad_invariant = (nrm_use < 10) && !use_estm;
       // snow fraction seen by SurfaceResistance = SnowFrac_next after Snow_cal_MeltHeat (driver.f95:848)
       for (int is = 0; is < NSURF; is++)
          SnowFrac_res[is] = (snowUse == 1) ? ((nrm_use > 0) ? S.SnowFrac[is] : R.snowFrac_obs) : 0.0;
@@ -374,8 +378,13 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
                OHM(dg, P, sfr, qn1_use, S.qn1_av, S.dqndt, qn1_av_next, dqndt_next, qn1_S, S.qn1_s_av, S.dqnsdt, qn1_s_av_next,
                    dqnsdt_next, dt_since_start, H.d.HDD_id[9], S.soilstore_id.v, S.state_id.v, SnowFrac_q, a1, a2, a3, qs,
                    deltaQi);
+            } else if (use_estm) {
+               // ESTM (driver.f95:1598-1606): parameters and element temperatures live in MODULE ESTM_data in the
+               // reference, in the class record and the per-cell ESTM state here; Tair_av is Tair_av_next (:784)
+               if (ES && ts9) qs = ESTM(P, C, *ES, avU1, Temp_C, avRh, Press_hPa, ts9, H.Tair_av_next, L.estm27);
+               else su_fatal(dg, 1005);   // ESTM selected but no ESTM state / surface-temperature forcing was supplied
             } else {
-               su_fatal(dg, 1003);   // AnOHM / ESTM need state outside the cal_Main argument list
+               su_fatal(dg, 1003);   // AnOHM needs module state outside the cal_Main argument list
             }
          }
          if (redo_rad || A.lv_J_kg != lv_at_melt) {
@@ -449,7 +458,8 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
             // exactly, so the state after trip 99 is the one after trip n (99-n even) or n+1 (99-n odd).
             const int n = i_iter - 1;
 #ifndef SU_NO_CYCLE
-            if (n >= 4 && qh == cyc_qh[0] && Ts_iter == cyc_ts[0] && lv_sw == cyc_sw[0] && Rd.alb1 == cyc_alb[0]) {
+            // (with ESTM a trip also depends on the element temperatures, which never repeat: no short cut)
+            if (n >= 4 && !use_estm && qh == cyc_qh[0] && Ts_iter == cyc_ts[0] && lv_sw == cyc_sw[0] && Rd.alb1 == cyc_alb[0]) {
                if (((99 - n) & 1) == 0) { done = true; i_iter = 100; }
                else i_iter = 99;   // one more trip, which then ends the loop as the 99th
             }

@@ -55,7 +55,11 @@ struct SuRunArgs {
    unsigned long long *warn;    // [2][stride]
    long long *iters;            // [ncell]
    // full output (SUEWS_OUT_FULL): per cell column-major [nsteps x ncol]
-   double *blkSUEWS, *blkSnow, *blkRSL, *blkDaily, *blkSOL;
+   double *blkSUEWS, *blkSnow, *blkRSL, *blkDaily, *blkSOL, *blkESTM;
+   // ESTM (StorageHeatMethod 4/14): per-cell element temperatures [SUEWS_N_ESTM_DBL][stride] and the shared
+   // surface-temperature forcing [nsteps][SUEWS_N_TS5], offset to step0; NULL when no class runs ESTM
+   double *estm;
+   const double *ts5;
    int ncell;
    long long stride;
    int nsteps;
@@ -143,6 +147,12 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
    double acc7[7] = {0, 0, 0, 0, 0, 0, 0};
    long long iters = 0;
    int cls = 0, tz = 0;
+   SuewsEstmState ES;
+   if (active && a.estm) {
+      double *ep = reinterpret_cast<double *>(&ES);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) ep[j] = a.estm[(size_t)j * a.stride + cell];
+   }
    if (active) {
       cls = a.class_of_cell[cell];
       tz = a.tz_of_cell[cell];
@@ -184,11 +194,14 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
          const bool live = active && dg.fatal == 0;
          SuLines L;
          L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr; L.sol26 = nullptr;
+         L.estm27 = nullptr;
          double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY], l_so[SUEWS_NCOL_SOLWEIG];
-         if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; }
+         double l_es[SUEWS_NCOL_ESTM];
+         if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; L.estm27 = l_es; }
          // every thread of the block enters the step (phase barriers inside); only live cells compute
          iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
-                             (a.sums && !a.sum7) ? acc : nullptr, (a.sums && a.sum7) ? acc7 : nullptr, L);
+                             (a.sums && !a.sum7) ? acc : nullptr, (a.sums && a.sum7) ? acc7 : nullptr, L,
+                             a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr);
          if (FULL && live && dg.fatal == 0) {
             const size_t n = (size_t)a.nsteps;
             double *b;
@@ -204,6 +217,13 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
             b = a.blkSOL + (size_t)cell * n * (SUEWS_NCOL_SOLWEIG + 5);   // SUEWS_update_output with set_nan, driver.f95:2497
             for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
             for (int c = 0; c < SUEWS_NCOL_SOLWEIG; c++) b[gs + n * (5 + c)] = (fabs(l_so[c]) > 30000) ? -999.0 : l_so[c];
+            // the reference stores the ESTM line for StorageHeatMethod 4 only (driver.f95:2503-2505); the line itself is
+            // also formed for 14 and is kept here for both (the reference-shaped block call filters on 4)
+            if ((P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14) && a.blkESTM) {
+               b = a.blkESTM + (size_t)cell * n * (SUEWS_NCOL_ESTM + 5);
+               for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+               for (int c = 0; c < SUEWS_NCOL_ESTM; c++) b[gs + n * (5 + c)] = (fabs(l_es[c]) > 30000) ? -999.0 : l_es[c];
+            }
             if (P.snowUse == 1) {   // SUEWS_update_output, driver.f95:2499-2501 (with set_nan :2737)
                b = a.blkSnow + (size_t)cell * n * (SUEWS_NCOL_SNOW + 5);
                for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
@@ -220,6 +240,11 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
       for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + cell] = sp[j];
+      if (a.estm) {
+         double *ep = reinterpret_cast<double *>(&ES);
+#pragma unroll 1
+         for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) a.estm[(size_t)j * a.stride + cell] = ep[j];
+      }
       a.fatal[cell] = dg.fatal;
       a.warn[cell] = dg.warn[0];
       a.warn[a.stride + cell] = dg.warn[1];
@@ -291,7 +316,7 @@ __global__ void suews_sunpos_kernel(double year, double idectime, double UTC, do
 // ------------------------------------------------------------------------------------------------
 struct FieldDesc {
    const char *name;
-   int kind;     // 0 class int, 1 class double, 2 cell double, 3 state double
+   int kind;     // 0 class int, 1 class double, 2 cell double, 3 state double, 4 ESTM state double
    size_t off;   // element offset inside its group
    int n;
 };
@@ -327,6 +352,13 @@ static std::vector<FieldDesc> build_fields()
       auto add = ADD(3);
 #define X(name, n) add(#name, n);
       SUEWS_STATE_DBL_FIELDS(X)
+#undef X
+   }
+   {
+      o = 0;
+      auto add = ADD(4);
+#define X(name, n) add(#name, n);
+      SUEWS_ESTM_STATE_FIELDS(X)
 #undef X
    }
 #undef ADD
@@ -373,7 +405,8 @@ static const char *fatal_text(int code)
    case 73: return "RunControl.nml:EmissionsMethod unusable";
    case 75: return "RunControl.nml: BaseTMethod / TrafficUnits not usable";
    case 1001: return "NetRadiationMethod: Value not usable";
-   case 1003: return "StorageHeatMethod 3 (AnOHM) / 4 (ESTM) are not part of this library";
+   case 1005: return "StorageHeatMethod 4/14 (ESTM) needs the ESTM state and a surface-temperature forcing block (suews_b200_set_estm_forcing)";
+   case 1003: return "StorageHeatMethod 3 (AnOHM) is not part of this library";
    case 1004: return "EmissionsMethod outside 0-6 / 11-46";
    default: return "Fatal error in SUEWS!";
    }
@@ -384,6 +417,10 @@ struct suews_b200_handle_s {
    long long stride = 0;
    std::vector<SuewsClassParams> classes;
    std::vector<double> cellp, state;   // SoA [field][stride]
+   std::vector<double> estm;           // ESTM state SoA [SUEWS_N_ESTM_DBL][stride]; empty until ESTM is used
+   std::vector<double> ts5;            // ESTM surface-temperature forcing [nsteps][SUEWS_N_TS5]
+   double *d_estm = nullptr, *d_ts5 = nullptr;
+   int ts5_nsteps = 0;
    std::vector<int> cls_of_cell, tz_of_cell;
    std::vector<double> tz_list;
    int dt_since_start = 0, tstep_prev = 0, tstep = 0;
@@ -397,7 +434,7 @@ struct suews_b200_handle_s {
    long long *d_iters = nullptr;
    SuewsStepRec *d_steps = nullptr;
    SuewsEphem *d_ephem = nullptr;
-   double *d_blk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+   double *d_blk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SUEWS, snow, RSL, DailyState, SOLWEIG, ESTM
    int blk_nsteps = 0;
    cudaStream_t stream = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -478,7 +515,8 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_classes); cudaFree(h->d_cls); cudaFree(h->d_tz); cudaFree(h->d_fatal); cudaFree(h->d_cellp);
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
-   for (int i = 0; i < 5; i++) cudaFree(h->d_blk[i]);
+   for (int i = 0; i < 6; i++) cudaFree(h->d_blk[i]);
+   cudaFree(h->d_estm); cudaFree(h->d_ts5);
 }
 
 int suews_b200_destroy(suews_b200_handle h)
@@ -547,9 +585,13 @@ int suews_b200_set_state(suews_b200_handle h, const char *name, const double *va
 {
    if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
    const FieldDesc *f = find_field(name);
-   if (!f || f->kind != 3) return set_err(SUEWS_E_BAD_NAME, "set_state: '%s' is not a state field", name);
+   if (!f || (f->kind != 3 && f->kind != 4)) return set_err(SUEWS_E_BAD_NAME, "set_state: '%s' is not a state field", name);
    if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "set_state: '%s' has %d values per cell, got %d", name, f->n, n);
    h->uploaded = false;
+   if (f->kind == 4) {
+      if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
+      return set_soa(h->estm, h->stride, h->ncell, f, vals);
+   }
    return set_soa(h->state, h->stride, h->ncell, f, vals);
 }
 
@@ -557,8 +599,22 @@ int suews_b200_get_state(suews_b200_handle h, const char *name, double *vals, in
 {
    if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
    const FieldDesc *f = find_field(name);
-   if (!f || f->kind != 3) return set_err(SUEWS_E_BAD_NAME, "get_state: '%s' is not a state field", name);
+   if (!f || (f->kind != 3 && f->kind != 4)) return set_err(SUEWS_E_BAD_NAME, "get_state: '%s' is not a state field", name);
    if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "get_state: '%s' has %d values per cell, got %d", name, f->n, n);
+   if (f->kind == 4) {
+      if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
+      if (h->uploaded && h->d_estm) {
+         CUDA_OK(cudaSetDevice(h->device));
+         CUDA_OK(cudaStreamSynchronize(h->stream));
+         CUDA_OK(cudaMemcpy(&h->estm[f->off * (size_t)h->stride], h->d_estm + f->off * (size_t)h->stride,
+                            sizeof(double) * (size_t)f->n * (size_t)h->stride, cudaMemcpyDeviceToHost));
+      }
+      for (int k = 0; k < f->n; k++) {
+         const double *src = &h->estm[(f->off + (size_t)k) * (size_t)h->stride];
+         for (int c = 0; c < h->ncell; c++) vals[(size_t)c * f->n + k] = src[c];
+      }
+      return SUEWS_OK;
+   }
    if (h->uploaded) {
       CUDA_OK(cudaSetDevice(h->device));
       CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -654,6 +710,18 @@ int suews_b200_upload(suews_b200_handle h)
    CUDA_OK(cudaMemcpy(h->d_cellp, h->cellp.data(), sizeof(double) * h->cellp.size(), cudaMemcpyHostToDevice));
    CUDA_OK(cudaMemcpy(h->d_state, h->state.data(), sizeof(double) * h->state.size(), cudaMemcpyHostToDevice));
    CUDA_OK(cudaMemcpy(h->d_tzlist, h->tz_list.data(), sizeof(double) * h->tz_list.size(), cudaMemcpyHostToDevice));
+   {   // ESTM state travels only when some class runs ESTM
+      bool any_estm = false;
+      for (const auto &P : h->classes) any_estm = any_estm || P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14;
+      if (any_estm) {
+         if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
+         CUDA_OK(dev_alloc(&h->d_estm, (size_t)SUEWS_N_ESTM_DBL * st));
+         CUDA_OK(cudaMemcpy(h->d_estm, h->estm.data(), sizeof(double) * h->estm.size(), cudaMemcpyHostToDevice));
+      } else if (h->d_estm) {
+         cudaFree(h->d_estm);
+         h->d_estm = nullptr;
+      }
+   }
    CUDA_OK(cudaMemset(h->d_sums, 0, sizeof(double) * (size_t)SUEWS_NCOL_SUEWS * st));
    CUDA_OK(cudaMemset(h->d_fatal, 0, sizeof(int) * st));
    CUDA_OK(cudaMemset(h->d_warn, 0, sizeof(unsigned long long) * 2 * st));
@@ -732,6 +800,23 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
    CUDA_OK(cudaGetLastError());
    CUDA_OK(cudaStreamSynchronize(h->stream));
    h->nsteps = nsteps;
+   h->ts5_nsteps = 0;   // a surface-temperature block belongs to one forcing block
+   return SUEWS_OK;
+}
+
+int suews_b200_set_estm_forcing(suews_b200_handle h, const double *ts5, int nsteps)
+{
+   if (!h || !ts5 || nsteps <= 0) return set_err(SUEWS_E_BAD_ARG, "set_estm_forcing: bad arguments");
+   if (nsteps != h->nsteps)
+      return set_err(SUEWS_E_BAD_ARG, "set_estm_forcing: %d rows, but the forcing block has %d (call set_forcing first)", nsteps, h->nsteps);
+   CUDA_OK(cudaSetDevice(h->device));
+   const size_t n = (size_t)nsteps;
+   h->ts5.resize(n * SUEWS_N_TS5);
+   for (size_t i = 0; i < n; i++)
+      for (int c = 0; c < SUEWS_N_TS5; c++) h->ts5[i * SUEWS_N_TS5 + c] = ts5[i + n * (size_t)(4 + c)];   // Ts5mindata_ir(5:13)
+   CUDA_OK(dev_alloc(&h->d_ts5, n * SUEWS_N_TS5));
+   CUDA_OK(cudaMemcpy(h->d_ts5, h->ts5.data(), sizeof(double) * n * SUEWS_N_TS5, cudaMemcpyHostToDevice));
+   h->ts5_nsteps = nsteps;
    return SUEWS_OK;
 }
 
@@ -743,8 +828,10 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    CUDA_OK(cudaSetDevice(h->device));
    const bool full = (out_flags & SUEWS_OUT_FULL) != 0;
    if (full) {
-      const int ncol[5] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5};
-      for (int i = 0; i < 5; i++) {
+      const int ncol[6] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5,
+                           SUEWS_NCOL_ESTM + 5};
+      for (int i = 0; i < 6; i++) {
+         if (i == 5 && !h->d_estm) continue;   // the ESTM block exists only when ESTM runs
          size_t cnt = (size_t)h->ncell * (size_t)nsteps * (size_t)ncol[i];
          CUDA_OK(dev_alloc(&h->d_blk[i], cnt));
          // unwritten rows (snow block when snowUse = 0) are left unassigned by the reference; -999 here
@@ -762,6 +849,9 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.sum7 = ((out_flags & SUEWS_OUT_SUM7) && !(out_flags & SUEWS_OUT_SUM82)) ? 1 : 0;
    a.fatal = h->d_fatal; a.warn = h->d_warn; a.iters = h->d_iters;
    a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3]; a.blkSOL = h->d_blk[4];
+   a.blkESTM = h->d_estm ? h->d_blk[5] : nullptr;
+   a.estm = h->d_estm;
+   a.ts5 = (h->d_estm && h->ts5_nsteps == h->nsteps) ? h->d_ts5 + (size_t)step0 * SUEWS_N_TS5 : nullptr;
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
    a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;
    const int grid = (h->ncell + SU_BLOCK - 1) / SU_BLOCK;
@@ -887,10 +977,11 @@ int suews_b200_reset_sums(suews_b200_handle h)
 int suews_b200_get_block(suews_b200_handle h, const char *group, int cell, double *block, int nsteps, int ncol)
 {
    if (!h || !group || !block) return set_err(SUEWS_E_BAD_ARG, "null argument");
-   const char *names[5] = {"SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"};
-   const int ncols[5] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5};
+   const char *names[6] = {"SUEWS", "snow", "RSL", "DailyState", "SOLWEIG", "ESTM"};
+   const int ncols[6] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5,
+                         SUEWS_NCOL_ESTM + 5};
    int g = -1;
-   for (int i = 0; i < 5; i++)
+   for (int i = 0; i < 6; i++)
       if (strcasecmp(group, names[i]) == 0) g = i;
    if (g < 0) return set_err(SUEWS_E_BAD_NAME, "get_block: unknown group '%s'", group);
    if (!h->d_blk[g] || nsteps != h->blk_nsteps || ncol != ncols[g] || cell < 0 || cell >= h->ncell)

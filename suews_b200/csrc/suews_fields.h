@@ -22,7 +22,9 @@
    X(startDLS, 1) X(endDLS, 1) X(EmissionsMethod, 1) X(gsModel, 1) X(Ie_end, 1) X(Ie_start, 1) \
    X(EvapMethod, 1) X(LAICalcYes, 1) X(NetRadiationMethod, 1) X(OHMIncQF, 1) X(RoughLenHeatMethod, 1) \
    X(RoughLenMomMethod, 1) X(SMDMethod, 1) X(snowUse, 1) X(StabilityMethod, 1) X(StorageHeatMethod, 1) \
-   X(tstep, 1) X(veg_type, 1) X(WaterUseMethod, 1) X(LAIType, 3)
+   X(tstep, 1) X(veg_type, 1) X(WaterUseMethod, 1) X(LAIType, 3) \
+   /* MODULE ESTM_data (suews_phys_estm.f95:1-176): ESTMinput.nml switches and layer counts */ \
+   X(evolveTibld, 1) X(TsurfChoice, 1) X(ibldCHmod, 1) X(Nibld, 1) X(Nwall, 1) X(Nroof, 1) X(Nground, 1)
 
 // ---- class-level doubles
 #define SUEWS_CLASS_DBL_FIELDS(X) \
@@ -43,7 +45,13 @@
    X(beta_bioCO2, 3) X(beta_enh_bioCO2, 3) X(GDDFull, 3) X(LAIMax, 3) X(LAIMin, 3) X(min_res_bioCO2, 3) \
    X(resp_a, 3) X(resp_b, 3) X(SDDFull, 3) X(theta_bioCO2, 3) X(SnowProf_24hr, 48) X(LAIPower, 12) \
    X(OHM_coef, 96) X(WaterDist, 48) X(AHProf_24hr, 48) X(HumActivity_24hr, 48) X(PopProf_24hr, 48) \
-   X(TraffProf_24hr, 48) X(WUProfA_24hr, 48) X(WUProfM_24hr, 48)
+   X(TraffProf_24hr, 48) X(WUProfA_24hr, 48) X(WUProfM_24hr, 48) \
+   /* MODULE ESTM_data as SUEWS_Translate / ESTM_initials leave it (THEAT_* in K, layers of the four elements) */ \
+   X(LBC_soil, 1) X(THEAT_ON, 1) X(THEAT_OFF, 1) X(THEAT_fix, 1) X(ivf_iw, 1) X(ivf_ir, 1) X(ivf_ii, 1) \
+   X(ivf_if, 1) X(ivf_ww, 1) X(ivf_wr, 1) X(ivf_wi, 1) X(ivf_wf, 1) X(ivf_rw, 1) X(ivf_ri, 1) X(ivf_rf, 1) \
+   X(ivf_fw, 1) X(ivf_fr, 1) X(ivf_fi, 1) X(zibld, 5) X(kibld, 5) X(ribld, 5) X(zwall, 5) X(kwall, 5) X(rwall, 5) \
+   X(zroof, 5) X(kroof, 5) X(rroof, 5) X(zground, 5) X(kground, 5) X(rground, 5) X(nroom, 1) X(alb_ibld, 1) \
+   X(em_ibld, 1) X(CH_iroof, 1) X(CH_iwall, 1) X(CH_ibld, 1) X(Tfloor, 1)
 
 // ---- per-cell doubles (the SUEWS_SiteSelect.txt site columns)
 #define SUEWS_CELL_DBL_FIELDS(X) \
@@ -53,7 +61,8 @@
    X(FAIEveTree, 1) X(FAIDecTree, 1) X(PopDensDaytime, 2) X(PopDensNighttime, 1) X(TrafficRate, 2) \
    X(QF0_BEU, 2) X(DRAINRT, 1) X(RAINCOVER, 1) X(RainMaxRes, 1) X(NARP_TRANS_SITE, 1) X(FlowChange, 1) \
    X(RunoffToWater, 1) X(PipeCapacity, 1) \
-   X(dTemp_C, 1) X(dRH, 1) /* optional additive forcing offsets (synthetic configs) */
+   X(dTemp_C, 1) X(dRH, 1) /* optional additive forcing offsets (synthetic configs) */ \
+   X(AreaWall, 1)          /* ESTM: fwall = AreaWall / SurfaceArea (suews_ctrl_translate.f95:393-394) */
 
 // ---- evolving per-cell state (the 29 INTENT(INOUT) arguments, driver.f95:290-333, + hidden SAVEs)
 #define SUEWS_STATE_DBL_FIELDS(X) \
@@ -64,8 +73,17 @@
    X(HDD_id, 12) X(WUDay_id, 9) X(Tair_av, 1) X(alb1_hidden, 1) X(lv_switch, 1) \
    X(rsl_cache, 10) /* library-internal: last z0_RSL per stability sign (pure-function memo, dev_rsl.cuh) */
 
+// ---- ESTM state: what MODULE ESTM_data carries from call to call (the *_grids copies, estm.f95:1587-1603, and
+// the SAVE'd HVAC, Tair2Set and NewtonPolynomial's `converged`).  A separate SoA [field][cell], resident only when
+// a class runs StorageHeatMethod 4/14.  Tw_4 is (layer, wall) column-major with leading dimension 5.
+#define SUEWS_ESTM_STATE_FIELDS(X) \
+   X(Tair2, 1) X(Tievolve, 1) X(lup_ground, 1) X(lup_wall, 1) X(lup_roof, 1) X(T0_ibld, 1) X(T0_ground, 1) \
+   X(T0_wall, 1) X(T0_roof, 1) X(TN_wall, 1) X(TN_roof, 1) X(Tground, 5) X(Twall, 5) X(Troof, 5) X(Tibld, 5) \
+   X(Tw_4, 20) X(HVAC, 1) X(Tair2Set, 1) X(NewtonConverged, 1)
+
 #define SUEWS_COUNT_X(name, n) +(n)
 enum {
+   SUEWS_N_ESTM_DBL = 0 SUEWS_ESTM_STATE_FIELDS(SUEWS_COUNT_X),
    SUEWS_N_CLASS_INT = 0 SUEWS_CLASS_INT_FIELDS(SUEWS_COUNT_X),
    SUEWS_N_CLASS_DBL = 0 SUEWS_CLASS_DBL_FIELDS(SUEWS_COUNT_X),
    SUEWS_N_CELL_DBL = 0 SUEWS_CELL_DBL_FIELDS(SUEWS_COUNT_X),
@@ -113,6 +131,11 @@ struct SuewsCellParams {
 struct SuewsCellState {
    SUEWS_STATE_DBL_FIELDS(SUEWS_DECL_DBL)
 };
+
+struct SuewsEstmState {
+   SUEWS_ESTM_STATE_FIELDS(SUEWS_DECL_DBL)
+};
+enum { SUEWS_N_TS5 = 9 };   // Tiair Tsurf Troof Troad Twall Twall_n Twall_e Twall_s Twall_w (Ts5mindata_ir(5:13))
 
 // One record per timestep, shared by all cells: clock + forcing (driver.f95:3177-3201).
 // Staged into shared memory in chunks by bulk async copy.  160 bytes.

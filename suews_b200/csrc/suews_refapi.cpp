@@ -16,7 +16,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
 #include <strings.h>
 #include <vector>
 
@@ -69,6 +71,17 @@ struct {
    double lv_switch;
 } g_hidden = {0.0, 0.0};
 
+// MODULE ESTM_data (suews_phys_estm.f95:1-176) is process-wide in the reference; so is this copy of it, keyed by
+// lower-cased variable name.  Parameters are set by the host (suews_estm_data_set) where the reference runs
+// ESTM_initials / SUEWS_Translate; the element temperatures come back here after every call.
+std::map<std::string, std::vector<double>> g_estm;
+std::string lower(const char *s)
+{
+   std::string r(s ? s : "");
+   for (auto &c : r) c = (char)tolower((unsigned char)c);
+   return r;
+}
+
 int ensure_handle()
 {
    if (g_h) return SUEWS_OK;
@@ -96,6 +109,17 @@ int push_fields(const ArgDesc *tab, int ntab, void *const *args)
       if (kind == SUEWS_KIND_CLASS_INT || kind == SUEWS_KIND_CLASS_DBL) rc = suews_b200_set_class_param(g_h, 0, a.name, tmp.data(), n);
       else if (kind == SUEWS_KIND_CELL_DBL) rc = suews_b200_set_cell_param(g_h, a.name, tmp.data(), n);
       else rc = suews_b200_set_state(g_h, a.name, tmp.data(), n);
+      if (rc) return rc;
+   }
+   // MODULE ESTM_data: parameters and element temperatures
+   for (const auto &kv : g_estm) {
+      int kind = -1;
+      const int n = suews_b200_field_info(kv.first.c_str(), &kind);
+      if (n <= 0 || n != (int)kv.second.size()) return SUEWS_E_BAD_SIZE;
+      int rc;
+      if (kind == SUEWS_KIND_CLASS_INT || kind == SUEWS_KIND_CLASS_DBL) rc = suews_b200_set_class_param(g_h, 0, kv.first.c_str(), kv.second.data(), n);
+      else if (kind == SUEWS_KIND_CELL_DBL) rc = suews_b200_set_cell_param(g_h, kv.first.c_str(), kv.second.data(), n);
+      else rc = suews_b200_set_state(g_h, kv.first.c_str(), kv.second.data(), n);
       if (rc) return rc;
    }
    // hidden SAVE'd state and the library's own per-cell scratch
@@ -128,32 +152,44 @@ int pull_state(const ArgDesc *tab, int ntab, void *const *args)
    }
    int rc = suews_b200_get_state(g_h, "alb1_hidden", &g_hidden.alb1, 1);
    if (!rc) rc = suews_b200_get_state(g_h, "lv_switch", &g_hidden.lv_switch, 1);
+   for (auto &kv : g_estm) {   // the element temperatures ESTM left behind
+      int kind = -1;
+      const int n = suews_b200_field_info(kv.first.c_str(), &kind);
+      if (rc || kind != SUEWS_KIND_ESTM_STATE) continue;
+      rc = suews_b200_get_state(g_h, kv.first.c_str(), kv.second.data(), n);
+   }
    return rc;
 }
 
 const int kBlkCols[6] = {87, 103, 32, 138, 31, 50};   // SUEWS, snow, ESTM, RSL, SOLWEIG, DailyState (suews_ctrl_const.f95:49-55)
 
 // Run len_sim rows of a [len_sim x 24] forcing block for the single cell and fill the six output blocks.
-int run_rows(const double *met, int len_sim, int dt_since_start, int tstep_prev, double *const blk[6])
+int run_rows(const double *met, int len_sim, int dt_since_start, int tstep_prev, double *const blk[6], const double *ts5_ir,
+             bool estm_block)
 {
    int rc = suews_b200_set_clock(g_h, dt_since_start, tstep_prev);
    if (!rc) rc = suews_b200_upload(g_h);
    if (!rc) rc = suews_b200_set_forcing(g_h, met, len_sim);
+   if (!rc && ts5_ir) {   // Ts5mindata_ir is one row, used for every step of the block (driver.f95:3044, :3475)
+      std::vector<double> ts((size_t)len_sim * 13);
+      for (int c = 0; c < 13; c++)
+         for (int r = 0; r < len_sim; r++) ts[(size_t)r + (size_t)len_sim * c] = ts5_ir[c];
+      rc = suews_b200_set_estm_forcing(g_h, ts.data(), len_sim);
+   }
    if (!rc) rc = suews_b200_advance(g_h, 0, len_sim, SUEWS_OUT_FULL);
    if (rc) return rc;
    // a physics fatal code (< 2000, the reference's ErrorHint number) stops that cell only: rows up to the
    // failing step are still returned, then the code; library errors return at once
    const int fatal_rc = suews_b200_sync(g_h);
    if (fatal_rc >= SUEWS_E_NO_DEVICE) return fatal_rc;
-   static const char *const grp[6] = {"SUEWS", "snow", nullptr, "RSL", "SOLWEIG", "DailyState"};
+   static const char *const grp[6] = {"SUEWS", "snow", "ESTM", "RSL", "SOLWEIG", "DailyState"};
    for (int g = 0; g < 6; g++) {
       if (!blk[g]) continue;
-      if (grp[g]) {
+      if (g != 2 || estm_block) {
          rc = suews_b200_get_block(g_h, grp[g], 0, blk[g], len_sim, kBlkCols[g]);
          if (rc) return rc;
       } else {
-         // the ESTM block is only written when StorageHeatMethod = 4 (driver.f95:2503), which this library
-         // rejects: date columns + -999
+         // the ESTM block is only written when StorageHeatMethod = 4 (driver.f95:2503); otherwise date columns + -999
          const size_t n = (size_t)len_sim;
          for (size_t c = 0; c < (size_t)kBlkCols[g]; c++)
             for (size_t r = 0; r < n; r++)
@@ -210,7 +246,10 @@ int suews_cal_multitsteps_c(void *const *args, int nargs)
       own_main.resize((size_t)*len_sim * 87);
       blk[0] = own_main.data();
    }
-   const int run_rc = run_rows(met, *len_sim, *(const int *)args[i_dt], *(const int *)args[i_tp], blk);
+   const int i_shm = find_arg(kMultiArgs, kNMulti, "StorageHeatMethod"), i_ts5 = find_arg(kMultiArgs, kNMulti, "Ts5mindata_ir");
+   const int shm = (i_shm >= 0 && args[i_shm]) ? *(const int *)args[i_shm] : 0;
+   const double *ts5 = ((shm == 4 || shm == 14) && i_ts5 >= 0) ? (const double *)args[i_ts5] : nullptr;
+   const int run_rc = run_rows(met, *len_sim, *(const int *)args[i_dt], *(const int *)args[i_tp], blk, ts5, shm == 4);
    if (run_rc >= SUEWS_E_NO_DEVICE) return run_rc;
    rc = pull_state(kMultiArgs, kNMulti, args);
    if (rc) return rc;
@@ -242,9 +281,12 @@ int suews_cal_main_c(void *const *args, int nargs)
    if (*(const int *)args[i_sec] != 0) return SUEWS_E_NOT_IMPL;   // forcing rows carry whole minutes (driver.f95:3181)
    rc = push_fields(kMainArgs, kNMain, args);
    if (rc) return rc;
-   double b0[87], b1[103], b3[138], b4[31], b5[50];
-   double *blk[6] = {b0, b1, nullptr, b3, b4, b5};
-   const int run_rc = run_rows(met, 1, *(const int *)args[i_dt], *(const int *)args[i_tp], blk);
+   double b0[87], b1[103], b2[32], b3[138], b4[31], b5[50];
+   double *blk[6] = {b0, b1, b2, b3, b4, b5};
+   const int i_shm = find_arg(kMainArgs, kNMain, "StorageHeatMethod"), i_ts5 = find_arg(kMainArgs, kNMain, "Ts5mindata_ir");
+   const int shm = (i_shm >= 0 && args[i_shm]) ? *(const int *)args[i_shm] : 0;
+   const double *ts5 = ((shm == 4 || shm == 14) && i_ts5 >= 0) ? (const double *)args[i_ts5] : nullptr;
+   const int run_rc = run_rows(met, 1, *(const int *)args[i_dt], *(const int *)args[i_tp], blk, ts5, shm == 4 || shm == 14);
    if (run_rc >= SUEWS_E_NO_DEVICE) return run_rc;
    rc = pull_state(kMainArgs, kNMain, args);
    if (rc) return rc;
@@ -252,7 +294,7 @@ int suews_cal_main_c(void *const *args, int nargs)
    if (out[0]) memcpy(out[0], b0, sizeof(double) * 5);
    if (out[1]) memcpy(out[1], b0 + 5, sizeof(double) * 82);
    if (out[2]) memcpy(out[2], b1 + 5, sizeof(double) * 98);
-   if (out[3]) for (int k = 0; k < 27; k++) out[3][k] = -999.0;
+   if (out[3]) memcpy(out[3], b2 + 5, sizeof(double) * 27);   // dataOutLineESTM: -999 unless ESTM ran (driver.f95:1545)
    if (out[4]) memcpy(out[4], b3 + 5, sizeof(double) * 133);
    if (out[5]) memcpy(out[5], b4 + 5, sizeof(double) * 26);
    if (out[6]) memcpy(out[6], b5 + 5, sizeof(double) * 45);
@@ -303,6 +345,29 @@ void suews_refapi_reset_hidden(void)
    std::lock_guard<std::mutex> lk(g_mu);
    g_hidden.alb1 = 0.0;
    g_hidden.lv_switch = 0.0;
+   g_estm.clear();
+}
+
+// MODULE ESTM_data for the reference-shaped calls: a variable by its module name (a class / cell / ESTM-state
+// field of the library that is not a SUEWS_cal_Main argument)
+int suews_estm_data_set(const char *name, const double *vals, int n)
+{
+   int kind = -1;
+   const int nf = suews_b200_field_info(name, &kind);
+   if (nf <= 0 || !vals) return SUEWS_E_BAD_NAME;
+   if (nf != n) return SUEWS_E_BAD_SIZE;
+   std::lock_guard<std::mutex> lk(g_mu);
+   g_estm[lower(name)].assign(vals, vals + n);
+   return SUEWS_OK;
+}
+int suews_estm_data_get(const char *name, double *vals, int n)
+{
+   std::lock_guard<std::mutex> lk(g_mu);
+   auto it = g_estm.find(lower(name));
+   if (it == g_estm.end() || !vals) return SUEWS_E_BAD_NAME;
+   if ((int)it->second.size() != n) return SUEWS_E_BAD_SIZE;
+   memcpy(vals, it->second.data(), sizeof(double) * (size_t)n);
+   return SUEWS_OK;
 }
 
 }   // extern "C"

@@ -120,8 +120,30 @@ class _SuewsDriver:
         return az.value, zen.value
 
     def reset_hidden_state(self):
-        """A fresh reference process starts with the SAVE'd Lat_vap switches and NARP alb1 cleared."""
+        """A fresh reference process starts with the SAVE'd Lat_vap switches and NARP alb1 cleared (and an empty
+        MODULE ESTM_data)."""
         lib().suews_refapi_reset_hidden()
+
+    # MODULE ESTM_data (suews_phys_estm.f95:1-176).  SUEWS_cal_Main reads ESTM's parameters and element temperatures
+    # from that module, not from its arguments; the reference's hosts fill it (ESTM_initials, SUEWS_Translate,
+    # ESTM_translate) before calling.  f2py would expose the module as an attribute object; these two calls stand there.
+    def estm_data_set(self, **kw):
+        L = lib()
+        L.suews_estm_data_set.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int]
+        for name, v in kw.items():
+            a = np.ascontiguousarray(np.atleast_1d(np.asarray(v, dtype=np.float64)).ravel())
+            rc = L.suews_estm_data_set(name.encode(), a.ctypes.data_as(C.POINTER(C.c_double)), a.size)
+            if rc != 0:
+                raise SuewsError(rc, "estm_data_set: '%s' (%d values) is not an ESTM_data variable of that size" % (name, a.size))
+
+    def estm_data_get(self, name, n=1):
+        L = lib()
+        L.suews_estm_data_get.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int]
+        a = np.zeros(int(n))
+        rc = L.suews_estm_data_get(name.encode(), a.ctypes.data_as(C.POINTER(C.c_double)), a.size)
+        if rc != 0:
+            raise SuewsError(rc, "estm_data_get: '%s' (%d values) has not been set" % (name, a.size))
+        return a
 
 
 suews_driver = _SuewsDriver()

@@ -49,6 +49,8 @@ def lib():
         L.so_sizeof_params.restype = C.c_size_t
         L.so_sizeof_state.restype = C.c_size_t
         L.so_NARP_cal_SunPosition.argtypes = [C.c_double] * 6 + [dp, dp]
+        L.so_set_ts5_block.argtypes = [dp]
+        L.so_estm_start.argtypes = [C.c_void_p, C.c_void_p, dp]
         _lib = L
     return _lib
 
@@ -129,11 +131,23 @@ class Cell:
     def state_dict(self):
         return {nm: self.get_state(nm) for nm, _i, _c in state_fields()}
 
-    def run(self, met, want=("SUEWS", "snow", "RSL", "DailyState")):
-        """met: [len_sim, 24] array in the reference's MetForcingBlock column order.
+    def estm_start(self, ts_row):
+        """First-call initialisation of the ESTM element temperatures (ESTM_translate, ESTMStart == 1) from the
+        first row [13] of the surface-temperature forcing."""
+        row = np.ascontiguousarray(np.asarray(ts_row, dtype=np.float64))
+        assert row.size == 13
+        lib().so_estm_start(self.p, self.s, row.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def run(self, met, want=("SUEWS", "snow", "RSL", "DailyState"), ts5=None):
+        """met: [len_sim, 24] array in the reference's MetForcingBlock column order; ts5: [len_sim, 13] ESTM
+        surface-temperature forcing (only read when StorageHeatMethod is 4/14).
         Returns dict of output blocks [len_sim, ncol] (datetime columns included)."""
         met = np.asfortranarray(np.asarray(met, dtype=np.float64))
         n = met.shape[0]
+        if ts5 is not None:
+            ts5 = np.asfortranarray(np.asarray(ts5, dtype=np.float64))
+            assert ts5.shape == (n, 13)
+        lib().so_set_ts5_block(ts5.ctypes.data_as(C.POINTER(C.c_double)) if ts5 is not None else None)
         blocks = {}
         ptrs = []
         for key in ("SUEWS", "snow", "ESTM", "RSL", "SOLWEIG", "DailyState"):

@@ -450,3 +450,75 @@ def test_fatal_error_is_reported_not_aborted():
         b.advance(0, 12, OUT_SUM82)
     assert ei.value.code == 1003
     b.close()
+
+
+# ---- ESTM (StorageHeatMethod 4/14): parity unpinned -- no ESTM output of the reference exists; CUDA == oracle
+ESTM_VARIANTS = [
+    dict(),                                      # ESTMinput.nml of the BaseRun: forced Tsurf, measured indoor temperature
+    dict(evolveTibld=1, ibldCHmod=1),            # HVAC hysteresis, ASHRAE convection
+    dict(evolveTibld=2, ibldCHmod=2),            # diagnosed indoor temperature, Awbi convection
+    dict(TsurfChoice=1),
+    dict(TsurfChoice=2, evolveTibld=1),          # four walls
+    dict(storageheatmethod=14),                  # same physics, no ESTM output block (driver.f95:2503)
+]
+
+
+def _estm_case(over):
+    d = dict(fx.state_init(2005))
+    over = dict(over)
+    d["storageheatmethod"] = [over.pop("storageheatmethod", 4)]
+    ep = fx.estm_example(d["surfacearea"][0], **over)
+    d.update({k.lower(): v for k, v in ep.items()})
+    return d, ep
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("over", ESTM_VARIANTS, ids=lambda o: "-".join("%s%s" % kv for kv in o.items()) or "baserun")
+def test_estm_first_day_matches_oracle(over):
+    from suews_b200 import OUT_FULL, SuewsBatch, estm
+    d, ep = _estm_case(over)
+    n = 288
+    met = fx.forcing(2005)[:n]
+    ts = fx.estm_ts_forcing(met)
+    cell = ol.Cell(d)
+    cell.estm_start(ts[0])
+    ref = cell.run(met, want=("SUEWS", "ESTM"), ts5=ts)
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    st0 = estm.initial_state(ep, d["sfr"], d["emis"], ts[0])
+    for k, v in st0.items():
+        b.set_state(k, v)
+    b.upload()
+    b.set_forcing(met)
+    b.set_estm_forcing(ts)
+    b.advance(0, n, OUT_FULL)
+    out = b.block("SUEWS", 0, n)
+    assert np.array_equal(out[:, :5], ref["SUEWS"][:, :5])
+    assert float(rel_err(out[:, 5:], ref["SUEWS"][:, 5:], "SUEWS").max()) <= 1e-10
+    if d["storageheatmethod"][0] == 4:
+        oe, re_ = b.block("ESTM", 0, n), ref["ESTM"]
+        assert np.array_equal(oe[:, :5], re_[:, :5])
+        assert np.array_equal(oe == -999.0, re_ == -999.0)
+        scale = np.maximum(np.abs(re_[:, 5:]), np.where(np.abs(re_[:, 5:]).max(axis=0) > 200, 273.15, 1.0))
+        assert float((np.abs(oe[:, 5:] - re_[:, 5:]) / scale).max()) <= 1e-10
+    # the element temperatures ESTM carries between calls, and its SAVE'd switches
+    for name in ("Tievolve", "Tground", "Twall", "Troof", "Tibld", "Tw_4", "T0_ibld", "TN_wall", "TN_roof", "lup_ground",
+                 "lup_wall", "lup_roof", "Tair2"):
+        np.testing.assert_allclose(b.get_state(name)[0], cell.get_state(name), rtol=1e-11, atol=0, err_msg=name)
+    for name in ("HVAC", "Tair2Set", "NewtonConverged"):
+        assert np.array_equal(b.get_state(name)[0], cell.get_state(name)), name
+    b.close()
+
+
+@pytest.mark.gpu
+def test_estm_without_inputs_fails_loudly():
+    from suews_b200 import OUT_FULL, SuewsBatch, SuewsError
+    d, _ep = _estm_case({})
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(fx.forcing(2005)[:2])
+    with pytest.raises(SuewsError) as e:
+        b.advance(0, 2, OUT_FULL)       # no set_estm_forcing
+    assert e.value.code == 1005
+    b.close()

@@ -51,7 +51,7 @@ def test_cal_multitsteps_matches_oracle():
     assert len(outs) == 6
     assert [o.shape[1] for o in outs] == [87, 103, 32, 138, 31, 50]
     _check_blocks(outs, ref, 288)
-    # ESTM block: never written on this path (StorageHeatMethod = 4 is rejected): date columns + -999
+    # ESTM block: not written unless StorageHeatMethod = 4 (driver.f95:2503): date columns + -999
     assert np.array_equal(outs[2][:, :5], ref["SUEWS"][:, :5]) and np.all(outs[2][:, 5:] == -999.0)
     # INTENT(INOUT) arguments were advanced in place
     assert int(kw["dt_since_start"][0]) == dt0 + 288 * 300
@@ -142,3 +142,36 @@ def test_fatal_condition_raises_like_the_reference():
     with pytest.raises(SuewsError) as ei:
         sd.suews_cal_multitsteps(metforcingblock=fx.forcing(2005)[:3], **kw)
     assert ei.value.code == 1003
+
+
+def test_cal_multitsteps_with_estm():
+    """StorageHeatMethod 4 through the reference-shaped call: ESTM's parameters and element temperatures are the
+    variables of MODULE ESTM_data (set by the host, as ESTM_initials / SUEWS_Translate / ESTM_translate do in the
+    reference), Ts5mindata_ir is the argument -- one row for the whole block (driver.f95:3044)."""
+    from suews_b200 import estm
+    from suews_b200.supy_driver import suews_driver as sd
+    sd.reset_hidden_state()
+    d = dict(fx.state_init(2005))
+    d["storageheatmethod"] = [4]
+    ep = fx.estm_example(d["surfacearea"][0], evolveTibld=1, ibldCHmod=1)
+    n = 48
+    met = fx.forcing(2005)[:n]
+    row = fx.estm_ts_forcing(met)[0]
+    ts = np.tile(row, (n, 1))
+    dd = dict(d)
+    dd.update({k.lower(): v for k, v in ep.items()})
+    cell = ol.Cell(dd)
+    cell.estm_start(row)
+    ref = cell.run(met, want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG", "ESTM"), ts5=ts)
+    sd.estm_data_set(**ep)
+    sd.estm_data_set(**estm.initial_state(ep, d["sfr"], d["emis"], row))
+    kw = _kwargs(d, 1)
+    outs = sd.suews_cal_multitsteps(metforcingblock=met, len_sim=n, ts5mindata_ir=row.copy(), **kw)
+    _check_blocks(outs, ref, n)
+    oe, re_ = outs[2], ref["ESTM"]
+    assert np.array_equal(oe[:, :5], re_[:, :5]) and np.array_equal(oe == -999.0, re_ == -999.0)
+    assert np.abs(oe[:, 5:] - re_[:, 5:]).max() <= 1e-9
+    # the module's element temperatures were advanced and can be read back
+    np.testing.assert_allclose(sd.estm_data_get("Twall", 5), cell.get_state("Twall"), rtol=1e-11)
+    np.testing.assert_allclose(sd.estm_data_get("Tievolve", 1), cell.get_state("Tievolve"), rtol=1e-11)
+    sd.reset_hidden_state()
