@@ -138,10 +138,14 @@ def test_fatal_condition_raises_like_the_reference():
     from suews_b200.supy_driver import suews_driver as sd
     d = fx.state_init(2005)
     kw = _kwargs(d, 1)
-    kw["storageheatmethod"] = np.array([4], dtype=np.int32)      # ESTM: outside this library
+    kw["storageheatmethod"] = np.array([3], dtype=np.int32)      # AnOHM: outside this library
     with pytest.raises(SuewsError) as ei:
         sd.suews_cal_multitsteps(metforcingblock=fx.forcing(2005)[:3], **kw)
     assert ei.value.code == 1003
+    kw["storageheatmethod"] = np.array([4], dtype=np.int32)      # ESTM without MODULE ESTM_data / Ts5mindata_ir
+    with pytest.raises(SuewsError) as ei:
+        sd.suews_cal_multitsteps(metforcingblock=fx.forcing(2005)[:3], **kw)
+    assert ei.value.code == 1005
 
 
 def test_cal_multitsteps_with_estm():
