@@ -81,6 +81,17 @@ int suews_b200_upload(suews_b200_handle h);
  * clock/ephemeris records on the device. */
 int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps);
 
+/* The same from forcing at its ORIGINAL resolution (e.g. hourly): met_orig is the [nrows x 24] block as MetRead reads
+ * it from the file (suews_ctrl_input.f95:13-135), column-major; the device applies MetRead's conversions when
+ * raw_units = 1 (pressure kPa -> hPa :109; xsmd = -999 when smd_method = 0 :96-102) and DisaggregateMet (:1380-1640:
+ * DisaggregateDateTime, Disagg_Lin with DisaggMethod 1/2/3, DisaggP_amongN with RainDisaggMethod 100) to the model
+ * timestep of the uploaded classes, whole-file semantics (first and last half period repeated).  The block then holds
+ * nrows * resolution_in_s / tstep rows, bit-identical to the reference's in-memory MetForcingData;
+ * suews_b200_get_forcing_block reads it back ([nsteps x 24], column-major). */
+int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int nrows, int resolution_in_s, int disagg_method,
+                                int rain_disagg_method, int raw_units, int smd_method);
+int suews_b200_get_forcing_block(suews_b200_handle h, double *met_fast, int nsteps);
+
 /* ESTM (StorageHeatMethod 4/14) only.  The reference keeps ESTM's parameters and element temperatures in MODULE
  * ESTM_data (suews_phys_estm.f95:1-176), outside the SUEWS_cal_Main argument list.  Here the parameters are class
  * fields under the module's variable names (evolveTibld, TsurfChoice, ibldCHmod, Nibld/Nwall/Nroof/Nground,

@@ -38,6 +38,7 @@ class SuewsBatch:
         self.h = C.c_void_p()
         check(self.L.suews_b200_create(self.ncell, self.nclass, self.device, C.byref(self.h)))
         self.nsteps = 0
+        self._class_cache = {}
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -51,8 +52,13 @@ class SuewsBatch:
             pass
 
     # ---- parameters
+    def _class_value(self, name):
+        return self._class_cache[name.lower()]
+
     def set_class_param(self, cls, name, vals):
         a = _arr(np.atleast_1d(vals)).ravel()
+        if int(cls) == 0 and a.size == 1:
+            self._class_cache[name.lower()] = float(a[0])
         check(self.L.suews_b200_set_class_param(self.h, int(cls), name.encode(), a.ctypes.data_as(dp), a.size))
 
     def set_cell_param(self, name, vals):
@@ -125,6 +131,28 @@ class SuewsBatch:
         assert m.shape[1] == 24
         check(self.L.suews_b200_set_forcing(self.h, m.ctypes.data_as(dp), m.shape[0]))
         self.nsteps = m.shape[0]
+
+    def set_forcing_orig(self, met_orig, resolution_in=3600, disagg_method=1, rain_disagg_method=100, raw_units=False,
+                         smd_method=0):
+        """Forcing at file resolution, disaggregated to the model timestep on the device (DisaggregateMet,
+        suews_ctrl_input.f95:1380-1640).  met_orig: [nrows, 24]; raw_units: the file's own units (pressure in kPa),
+        i.e. a block that has not been through forcing.read_met.  Returns the number of model timesteps."""
+        m = np.asfortranarray(np.asarray(met_orig, dtype=np.float64))
+        assert m.shape[1] == 24
+        check(self.L.suews_b200_set_forcing_orig(self.h, m.ctypes.data_as(dp), m.shape[0], int(resolution_in), int(disagg_method),
+                                                 int(rain_disagg_method), int(bool(raw_units)), int(smd_method)))
+        self.nsteps = m.shape[0] * (int(resolution_in) // self.tstep())
+        return self.nsteps
+
+    def tstep(self):
+        # class 0 carries the timestep all classes share (checked at upload)
+        return int(self._class_value("tstep"))
+
+    def forcing_block(self):
+        """The MetForcingBlock [nsteps, 24] the device built in set_forcing_orig."""
+        b = np.zeros((self.nsteps, 24), order="F")
+        check(self.L.suews_b200_get_forcing_block(self.h, b.ctypes.data_as(dp), self.nsteps))
+        return b
 
     def set_estm_forcing(self, ts5):
         """ts5: [nsteps, 13] ESTM surface-temperature forcing (iy id it imin Tiair Tsurf Troof Troad Twall Twall_n

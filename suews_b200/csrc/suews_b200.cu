@@ -22,6 +22,7 @@
 
 #include "suews_fields.h"
 #include "dev_step.cuh"
+#include "forcing_kernels.cuh"
 #include "../../include/suews_b200.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -102,6 +103,55 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
       "}\n" ::"r"(smem_u32(bar)),
       "r"(phase)
       : "memory");
+}
+
+// clock decode of one forcing row (SUEWS_cal_dectime util_time.f95:270, SUEWS_cal_weekday :301)
+__host__ __device__ static void decode_clock(SuewsStepRec &r)
+{
+   r.dectime = (double)(r.id - 1) + (double)r.it / 24 + (double)r.imin / (60 * 24) + (double)0 / (60 * 60 * 24);
+   int year = r.iy, b = r.id, k, mb, md;
+   k = ((year % 4 == 0 && year % 100 != 0) || year % 400 == 0) ? 1 : 0;   // MODULO(year, p) == 0 <=> year % p == 0
+   if (b <= 31) { mb = 1; md = b; }
+   else if (b <= 59 + k) { mb = 2; md = b - 31; }
+   else if (b <= 90 + k) { mb = 3; md = b - (59 + k); }
+   else if (b <= 120 + k) { mb = 4; md = b - (90 + k); }
+   else if (b <= 151 + k) { mb = 5; md = b - (120 + k); }
+   else if (b <= 181 + k) { mb = 6; md = b - (151 + k); }
+   else if (b <= 212 + k) { mb = 7; md = b - (181 + k); }
+   else if (b <= 243 + k) { mb = 8; md = b - (212 + k); }
+   else if (b <= 273 + k) { mb = 9; md = b - (243 + k); }
+   else if (b <= 304 + k) { mb = 10; md = b - (273 + k); }
+   else if (b <= 334 + k) { mb = 11; md = b - (304 + k); }
+   else { mb = 12; md = b - (334 + k); }
+   int yr = year, mn = mb;
+   if (!(mn > 2)) { mn += 12; yr -= 1; }
+   int n1 = (26 * (mn + 1)) / 10, n2 = (125 * yr) / 100;
+   int day = (md + n1 + n2 - (yr / 100) + (yr / 400) - 1);
+   r.dow = day % 7 + 1;
+   r.month = mb;
+   r.pad0_ = 0;
+   r.pad1_ = 0;
+}
+
+
+// MetForcingBlock row -> step record (driver.f95:3177-3201), one thread per row
+__host__ __device__ static void pack_step(SuewsStepRec &r, const double *met, size_t n, size_t i)
+{
+#define MET(col) met[i + n * (col)]
+   r.iy = (int)MET(0); r.id = (int)MET(1); r.it = (int)MET(2); r.imin = (int)MET(3);
+   r.qn1_obs = MET(4); r.qs_obs = MET(7); r.qf_obs = MET(8); r.avU1 = MET(9); r.avRh = MET(10); r.Temp_C = MET(11);
+   r.Press_hPa = MET(12); r.Precip = MET(13); r.avkdn = MET(14); r.snowFrac_obs = MET(15); r.ldown_obs = MET(16);
+   r.fcld_obs = MET(17); r.wu_m3 = MET(18); r.xsmd = MET(19); r.LAI_obs = MET(20);
+#undef MET
+   decode_clock(r);
+}
+__global__ void suews_pack_steps_kernel(const double *met, int nsteps, SuewsStepRec *recs)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nsteps) return;
+   SuewsStepRec r;
+   pack_step(r, met, (size_t)nsteps, (size_t)i);
+   recs[i] = r;
 }
 
 // Time-only half of the solar position + nothing else: one thread per (time zone, step).
@@ -420,6 +470,7 @@ struct suews_b200_handle_s {
    std::vector<double> estm;           // ESTM state SoA [SUEWS_N_ESTM_DBL][stride]; empty until ESTM is used
    std::vector<double> ts5;            // ESTM surface-temperature forcing [nsteps][SUEWS_N_TS5]
    double *d_estm = nullptr, *d_ts5 = nullptr;
+   double *d_met_orig = nullptr, *d_met_fast = nullptr;   // forcing at file resolution / disaggregated on the device
    int ts5_nsteps = 0;
    std::vector<int> cls_of_cell, tz_of_cell;
    std::vector<double> tz_list;
@@ -516,7 +567,7 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
    for (int i = 0; i < 6; i++) cudaFree(h->d_blk[i]);
-   cudaFree(h->d_estm); cudaFree(h->d_ts5);
+   cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast);
 }
 
 int suews_b200_destroy(suews_b200_handle h)
@@ -733,35 +784,6 @@ int suews_b200_upload(suews_b200_handle h)
    return SUEWS_OK;
 }
 
-// host-side clock decode of one forcing row (SUEWS_cal_dectime util_time.f95:270, SUEWS_cal_weekday :301)
-static void decode_clock(SuewsStepRec &r)
-{
-   r.dectime = (double)(r.id - 1) + (double)r.it / 24 + (double)r.imin / (60 * 24) + (double)0 / (60 * 60 * 24);
-   int year = r.iy, b = r.id, k, mb, md;
-   auto fmod_ = [](int a, int p) { int m = a % p; if (m != 0 && ((m < 0) != (p < 0))) m += p; return m; };
-   k = ((fmod_(year, 4) == 0 && fmod_(year, 100) != 0) || fmod_(year, 400) == 0) ? 1 : 0;
-   if (b <= 31) { mb = 1; md = b; }
-   else if (b <= 59 + k) { mb = 2; md = b - 31; }
-   else if (b <= 90 + k) { mb = 3; md = b - (59 + k); }
-   else if (b <= 120 + k) { mb = 4; md = b - (90 + k); }
-   else if (b <= 151 + k) { mb = 5; md = b - (120 + k); }
-   else if (b <= 181 + k) { mb = 6; md = b - (151 + k); }
-   else if (b <= 212 + k) { mb = 7; md = b - (181 + k); }
-   else if (b <= 243 + k) { mb = 8; md = b - (212 + k); }
-   else if (b <= 273 + k) { mb = 9; md = b - (243 + k); }
-   else if (b <= 304 + k) { mb = 10; md = b - (273 + k); }
-   else if (b <= 334 + k) { mb = 11; md = b - (304 + k); }
-   else { mb = 12; md = b - (334 + k); }
-   int yr = year, mn = mb;
-   if (!(mn > 2)) { mn += 12; yr -= 1; }
-   int n1 = (26 * (mn + 1)) / 10, n2 = (125 * yr) / 100;
-   int day = (md + n1 + n2 - (yr / 100) + (yr / 400) - 1);
-   r.dow = day % 7 + 1;
-   r.month = mb;
-   r.pad0_ = 0;
-   r.pad1_ = 0;
-}
-
 int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
 {
    if (!h || !met || nsteps <= 0) return set_err(SUEWS_E_BAD_ARG, "set_forcing: bad arguments");
@@ -778,16 +800,7 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
       h->pinned_in_bytes = sizeof(SuewsStepRec) * n;
    }
    SuewsStepRec *recs = (SuewsStepRec *)h->pinned_in;
-#define MET(col) met[(size_t)i + n * (col)]
-   for (int i = 0; i < nsteps; i++) {   // driver.f95:3177-3201
-      SuewsStepRec &r = recs[(size_t)i];
-      r.iy = (int)MET(0); r.id = (int)MET(1); r.it = (int)MET(2); r.imin = (int)MET(3);
-      r.qn1_obs = MET(4); r.qs_obs = MET(7); r.qf_obs = MET(8); r.avU1 = MET(9); r.avRh = MET(10); r.Temp_C = MET(11);
-      r.Press_hPa = MET(12); r.Precip = MET(13); r.avkdn = MET(14); r.snowFrac_obs = MET(15); r.ldown_obs = MET(16);
-      r.fcld_obs = MET(17); r.wu_m3 = MET(18); r.xsmd = MET(19); r.LAI_obs = MET(20);
-      decode_clock(r);
-   }
-#undef MET
+   for (int i = 0; i < nsteps; i++) pack_step(recs[(size_t)i], met, n, (size_t)i);   // driver.f95:3177-3201
    if (h->steps_cap < n) {
       CUDA_OK(dev_alloc(&h->d_steps, n));
       CUDA_OK(dev_alloc(&h->d_ephem, n * h->tz_list.size()));
@@ -801,6 +814,70 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
    CUDA_OK(cudaStreamSynchronize(h->stream));
    h->nsteps = nsteps;
    h->ts5_nsteps = 0;   // a surface-temperature block belongs to one forcing block
+   if (h->d_met_fast) { cudaFree(h->d_met_fast); h->d_met_fast = nullptr; }
+   return SUEWS_OK;
+}
+
+// Forcing at its original resolution: disaggregated to the model timestep on the device.
+int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int nrows, int resolution_in_s, int disagg_method,
+                                int rain_disagg_method, int raw_units, int smd_method)
+{
+   if (!h || !met_orig || nrows < 2) return set_err(SUEWS_E_BAD_ARG, "set_forcing_orig: need at least two rows");
+   if (!h->uploaded) {
+      int rc = suews_b200_upload(h);
+      if (rc) return rc;
+   }
+   const int tstep = h->tstep;
+   if (resolution_in_s <= 0 || tstep <= 0 || resolution_in_s % tstep != 0)
+      return set_err(SUEWS_E_BAD_ARG, "set_forcing_orig: ResolutionFilesIn %d is not a multiple of tstep %d", resolution_in_s, tstep);
+   if (disagg_method < 1 || disagg_method > 3)
+      return set_err(2, "DisaggMethod value should be 1, 2, or 3 (got %d)", disagg_method);   // ErrorHint 2, ctrl_input.f95:1438
+   if (rain_disagg_method != 100)   // 101 / 102 draw unseeded random sub-intervals in the reference (RandomSamples, :2070)
+      return set_err(SUEWS_E_NOT_IMPL, "set_forcing_orig: only RainDisaggMethod 100 is deterministic (got %d)", rain_disagg_method);
+   CUDA_OK(cudaSetDevice(h->device));
+   const int nper = resolution_in_s / tstep;
+   const size_t n = (size_t)nrows, nfast = n * (size_t)nper;
+   if (nfast > (size_t)0x7fffffff) return set_err(SUEWS_E_BAD_ARG, "set_forcing_orig: too many timesteps");
+   SuDisaggArgs a;
+   a.n = nrows; a.nper = nper; a.tstep = tstep; a.raw_units = raw_units; a.smd_method = smd_method;
+   a.all_missing = 0; a.type20 = 0;
+   for (int c = 4; c < SUEWS_NCOL_MET; c++) {
+      bool all = true;
+      for (size_t i = 0; i < n && all; i++) all = (met_orig[i + n * c] == -999.0);
+      if (c == 19 && smd_method == 0) all = true;
+      if (all) a.all_missing |= (1u << c);
+      if (disagg_method == 2 || (disagg_method == 3 && c >= 9 && c <= 12)) a.type20 |= (1u << c);
+   }
+   CUDA_OK(dev_alloc(&h->d_met_orig, n * SUEWS_NCOL_MET));
+   CUDA_OK(dev_alloc(&h->d_met_fast, nfast * SUEWS_NCOL_MET));
+   a.slow = h->d_met_orig; a.fast = h->d_met_fast;
+   if (h->steps_cap < nfast) {
+      CUDA_OK(dev_alloc(&h->d_steps, nfast));
+      CUDA_OK(dev_alloc(&h->d_ephem, nfast * h->tz_list.size()));
+      h->steps_cap = nfast;
+   }
+   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+   CUDA_OK(cudaMemcpyAsync(h->d_met_orig, met_orig, sizeof(double) * n * SUEWS_NCOL_MET, cudaMemcpyHostToDevice, h->stream));
+   suews_disagg_kernel<<<(unsigned)((nfast + 255) / 256), 256, 0, h->stream>>>(a);
+   suews_pack_steps_kernel<<<(unsigned)((nfast + 255) / 256), 256, 0, h->stream>>>(h->d_met_fast, (int)nfast, h->d_steps);
+   const int total = (int)nfast * (int)h->tz_list.size();
+   suews_ephem_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_steps, (int)nfast, h->d_tzlist, (int)h->tz_list.size(),
+                                                                 h->tstep, h->d_ephem);
+   CUDA_OK(cudaGetLastError());
+   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   h->nsteps = (int)nfast;
+   h->ts5_nsteps = 0;
+   return SUEWS_OK;
+}
+
+// The disaggregated MetForcingBlock [nsteps x 24], column-major, as the device holds it
+int suews_b200_get_forcing_block(suews_b200_handle h, double *met_fast, int nsteps)
+{
+   if (!h || !met_fast || !h->d_met_fast || nsteps != h->nsteps)
+      return set_err(SUEWS_E_BAD_ARG, "get_forcing_block: no device-disaggregated block of %d rows", nsteps);
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaMemcpy(met_fast, h->d_met_fast, sizeof(double) * (size_t)nsteps * SUEWS_NCOL_MET, cudaMemcpyDeviceToHost));
    return SUEWS_OK;
 }
 

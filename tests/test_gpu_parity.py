@@ -522,3 +522,51 @@ def test_estm_without_inputs_fails_loudly():
         b.advance(0, 2, OUT_FULL)       # no set_estm_forcing
     assert e.value.code == 1005
     b.close()
+
+
+# ---- forcing preparation on the device: DisaggregateMet as a kernel, bit-identical to the numpy
+# restatement whose output reproduces the reference goldens (tests/test_oracle_golden.py)
+@pytest.mark.gpu
+@pytest.mark.parametrize("year,method", [(2005, 1), (2004, 1), (2005, 2), (2005, 3)])
+def test_device_disaggregation_is_bit_identical(year, method):
+    import os
+    from suews_b200 import SuewsBatch
+    from suews_b200.forcing import disaggregate_met, read_met
+    path = os.path.join(fx.GOLDEN, "forcing_%d_60min.txt" % year)
+    host = disaggregate_met(read_met(path), disagg_method=method)
+    raw = read_met(path)
+    raw[:, 12] = raw[:, 12] / 10.0          # back to the file's kPa: the device applies MetRead's conversion
+    rows = [ln.split()[:24] for ln in open(path).readlines()[1:] if len(ln.split()) >= 24 and not ln.startswith("-9")]
+    raw = np.array(rows, dtype=np.float64)  # exactly what the file holds
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(fx.state_init(2005))
+    b.upload()
+    n = b.set_forcing_orig(raw, resolution_in=3600, disagg_method=method, raw_units=True, smd_method=0)
+    assert n == host.shape[0]
+    dev = b.forcing_block()
+    cols = [c for c in range(24) if c not in (23,)]       # wind direction: left unset by the reference (-999 both sides)
+    assert np.array_equal(dev[:, cols], host[:, cols])
+    assert np.all(dev[:, 23] == -999.0)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_run_from_device_disaggregated_forcing_equals_host_path():
+    import os
+    from suews_b200 import OUT_SUM82, SuewsBatch
+    from suews_b200.forcing import read_met
+    d = fx.state_init(2005)
+    met = fx.forcing(2005)
+    sums = []
+    for dev_path in (False, True):
+        b = SuewsBatch(1, 1)
+        b.load_reference_args(d)
+        b.upload()
+        if dev_path:
+            b.set_forcing_orig(read_met(os.path.join(fx.GOLDEN, "forcing_2005_60min.txt")), raw_units=False)
+        else:
+            b.set_forcing(met)
+        b.advance(0, 576, OUT_SUM82)
+        sums.append(b.sums().copy())
+        b.close()
+    assert np.array_equal(sums[0], sums[1])
