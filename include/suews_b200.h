@@ -51,8 +51,11 @@ enum { SUEWS_KIND_CLASS_INT = 0, SUEWS_KIND_CLASS_DBL = 1, SUEWS_KIND_CELL_DBL =
 enum {
    SUEWS_OUT_SUM82 = 1,   /* accumulate per-cell sums of the 82 SUEWS columns over the advanced steps */
    SUEWS_OUT_FULL = 2,    /* keep every output block of every step (reference SUEWS_cal_multitsteps semantics) */
-   SUEWS_OUT_SUM7 = 4     /* accumulate only the seven parity fluxes QN, QF, QS, QH, QE, RO, SWE (columns 5-9, 16, 71
+   SUEWS_OUT_SUM7 = 4,    /* accumulate only the seven parity fluxes QN, QF, QS, QH, QE, RO, SWE (columns 5-9, 16, 71
                              of the same [ncell][82] sums array; the other columns are left untouched) */
+   SUEWS_OUT_AGG = 8      /* output policy P1: the SUEWS block aggregated to the output frequency (default hourly) inside
+                             the kernel, as SUEWS_Output_Agg does after the run (suews_ctrl_output.f95:912-957: mean /
+                             sum / last value per column as varListAll says); exclusive with the running sums */
 };
 
 /* ---- batched device API -------------------------------------------------------------------- */
@@ -108,6 +111,13 @@ int suews_b200_set_estm_forcing(suews_b200_handle h, const double *ts5, int nste
  * with respect to the host; suews_b200_sync waits and returns the first fatal cell error (0 if none). */
 int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags);
 int suews_b200_sync(suews_b200_handle h);
+/* Output policy P1.  set_output_freq: ResolutionFilesOut in seconds (default 3600); every advance with SUEWS_OUT_AGG
+ * aggregates its own rows [step0, step0 + nsteps) into INT(nsteps / nlinesOut) rows (a trailing partial period is
+ * dropped, as in the reference).  get_agg_block: one cell's [nrows x 87] block, column-major, datetime columns =
+ * the last step of each period; get_agg_column: one column (0-based, 0-4 datetime) of one row for all cells. */
+int suews_b200_set_output_freq(suews_b200_handle h, int out_freq_s);
+int suews_b200_get_agg_block(suews_b200_handle h, int cell, double *block, int nrows);
+int suews_b200_get_agg_column(suews_b200_handle h, int row, int col, double *vals);
 
 /* Results.  sums: [ncell][82] (cell-major).  Full blocks (after SUEWS_OUT_FULL): per cell a
  * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50/31/32 columns). */

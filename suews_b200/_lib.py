@@ -49,6 +49,9 @@ def lib():
         L.suews_b200_get_forcing_block.argtypes = [H, dp, C.c_int]
         L.suews_b200_advance.argtypes = [H, C.c_int, C.c_int, C.c_int]
         L.suews_b200_sync.argtypes = [H]
+        L.suews_b200_set_output_freq.argtypes = [H, C.c_int]
+        L.suews_b200_get_agg_block.argtypes = [H, C.c_int, dp, C.c_int]
+        L.suews_b200_get_agg_column.argtypes = [H, C.c_int, C.c_int, dp]
         L.suews_b200_get_sums.argtypes = [H, dp]
         L.suews_b200_reset_sums.argtypes = [H]
         L.suews_b200_get_sums_cols.argtypes = [H, ip, C.c_int, dp]

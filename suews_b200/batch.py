@@ -15,6 +15,7 @@ NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50, "SOLWEIG": 31, "
 OUT_SUM82 = 1
 OUT_FULL = 2
 OUT_SUM7 = 4   # only the seven parity fluxes (output policy P0)
+OUT_AGG = 8    # SUEWS block aggregated to the output frequency inside the kernel (output policy P1)
 
 KIND_CLASS_INT, KIND_CLASS_DBL, KIND_CELL, KIND_STATE, KIND_ESTM_STATE = 0, 1, 2, 3, 4
 
@@ -169,6 +170,20 @@ class SuewsBatch:
 
     def sync(self):
         check(self.L.suews_b200_sync(self.h))
+
+    def set_output_freq(self, seconds):
+        check(self.L.suews_b200_set_output_freq(self.h, int(seconds)))
+
+    def agg_block(self, cell, nrows):
+        """One cell's SUEWS block aggregated as SUEWS_Output_Agg does (suews_ctrl_output.f95:912-957), [nrows, 87]."""
+        b = np.zeros((nrows, 87), order="F")
+        check(self.L.suews_b200_get_agg_block(self.h, int(cell), b.ctypes.data_as(dp), int(nrows)))
+        return b
+
+    def agg_column(self, row, col):
+        a = np.zeros(self.ncell)
+        check(self.L.suews_b200_get_agg_column(self.h, int(row), int(col), a.ctypes.data_as(dp)))
+        return a
 
     def last_ms(self):
         ms = C.c_float()

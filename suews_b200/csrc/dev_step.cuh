@@ -242,7 +242,7 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
 __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
                           SuewsCellState &S, double *acc82, double *acc7, const SuLines &L, SuewsEstmState *ES = nullptr,
-                          const double *ts9 = nullptr)
+                          const double *ts9 = nullptr, unsigned long long last_lo = 0, unsigned long long last_hi = 0)
 {
    const double *sfr = C.sfr.v;
    const int sm = P.StabilityMethod;
@@ -559,7 +559,8 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
 #define SU_OUT(v)                                  \
    do {                                            \
       const double v_ = (v);                       \
-      if (acc82) acc82[k] += v_;                   \
+      /* columns aggregated as "last value" (bit set) are overwritten, the others summed */ \
+      if (acc82) acc82[k] = (((k < 64 ? last_lo >> k : last_hi >> (k - 64)) & 1ull) ? 0.0 : acc82[k]) + v_; \
       if (L.suews82) L.suews82[k] = v_;            \
       k++;                                         \
    } while (0)

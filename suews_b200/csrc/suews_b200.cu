@@ -61,6 +61,10 @@ struct SuRunArgs {
    // surface-temperature forcing [nsteps][SUEWS_N_TS5], offset to step0; NULL when no class runs ESTM
    double *estm;
    const double *ts5;
+   // output policy P1 (SUEWS_OUT_AGG): the SUEWS block aggregated over every agg_nlines steps as SUEWS_Output_Agg
+   // does (suews_ctrl_output.f95:912-957), [row][87][stride] indexed by thread slot so that a warp writes 256 B lines
+   double *agg;
+   int agg_nlines;
    int ncell;
    long long stride;
    int nsteps;
@@ -68,6 +72,14 @@ struct SuRunArgs {
 };
 
 // QN, QF, QS, QH, QE, RO, SWE in the 82-column SUEWS line (0-based)
+// aggregation method of the 82 SUEWS columns (varListAll, suews_ctrl_output.f95:80-166): 0 mean, 1 sum, 2 last
+__constant__ unsigned char su_agg82[SUEWS_NCOL_SUEWS] = {
+#include "suews_agg82.inc"
+};
+static const unsigned char su_agg82_host[SUEWS_NCOL_SUEWS] = {
+#include "suews_agg82.inc"
+};
+
 __host__ __device__ __forceinline__ int su_parity_col(int i)
 {
    return i < 5 ? 5 + i : (i == 5 ? 16 : 71);
@@ -215,13 +227,20 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
       dg.fatal = a.fatal[cell];
       dg.warn[0] = a.warn[cell];
       dg.warn[1] = a.warn[a.stride + cell];
-      if (a.sums && !a.sum7) {
+      if (a.agg) {
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = 0.0;
+      } else if (a.sums && !a.sum7) {
 #pragma unroll 1
          for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = a.sums[(size_t)c * a.stride + cell];
       } else if (a.sums) {
          for (int c = 0; c < 7; c++) acc7[c] = a.sums[(size_t)su_parity_col(c) * a.stride + cell];
       }
    }
+   // "last value" columns as a bit mask; only the aggregating policy overwrites instead of summing
+   unsigned long long last_lo = 0, last_hi = 0;
+   if (a.agg)
+      for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
+         if (su_agg82[c] == 2) { if (c < 64) last_lo |= 1ull << c; else last_hi |= 1ull << (c - 64); }
    const SuewsClassParams &P = a.classes[cls];
    const SuewsEphem *eph = a.ephem + (size_t)tz * a.ephem_tz_stride;
    int dt_since_start = a.dt_since_start;
@@ -250,8 +269,20 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
          if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; L.estm27 = l_es; }
          // every thread of the block enters the step (phase barriers inside); only live cells compute
          iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
-                             (a.sums && !a.sum7) ? acc : nullptr, (a.sums && a.sum7) ? acc7 : nullptr, L,
-                             a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr);
+                             (a.agg || (a.sums && !a.sum7)) ? acc : nullptr, (!a.agg && a.sums && a.sum7) ? acc7 : nullptr, L,
+                             a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi);
+         if (a.agg && (gs + 1) % a.agg_nlines == 0) {   // SUEWS_Output_Agg: rows i-nlinesOut+1 .. i -> row i/nlinesOut
+            if (live && dg.fatal == 0) {
+               const SuewsStepRec &R = sm_steps[buf][t];
+               double *o = a.agg + (size_t)((gs + 1) / a.agg_nlines - 1) * (SUEWS_NCOL_SUEWS + 5) * (size_t)a.stride + slot;
+               o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
+               o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
+#pragma unroll 1
+               for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
+                  o[(size_t)(5 + c) * a.stride] = (su_agg82[c] == 0) ? acc[c] / a.agg_nlines : acc[c];
+            }
+            for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = 0.0;
+         }
          if (FULL && live && dg.fatal == 0) {
             const size_t n = (size_t)a.nsteps;
             double *b;
@@ -299,7 +330,9 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
       a.warn[cell] = dg.warn[0];
       a.warn[a.stride + cell] = dg.warn[1];
       a.iters[cell] += iters;
-      if (a.sums && !a.sum7) {
+      if (a.agg) {
+         // partial periods at the end of a block are dropped, as INT(irMax/nlinesOut) drops them
+      } else if (a.sums && !a.sum7) {
 #pragma unroll 1
          for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) a.sums[(size_t)c * a.stride + cell] = acc[c];
       } else if (a.sums) {
@@ -471,6 +504,10 @@ struct suews_b200_handle_s {
    std::vector<double> ts5;            // ESTM surface-temperature forcing [nsteps][SUEWS_N_TS5]
    double *d_estm = nullptr, *d_ts5 = nullptr;
    double *d_met_orig = nullptr, *d_met_fast = nullptr;   // forcing at file resolution / disaggregated on the device
+   double *d_agg = nullptr;                               // aggregated SUEWS block [rows][87][stride] (thread-slot order)
+   size_t agg_cap = 0;
+   int agg_rows = 0, out_freq_s = 3600;
+   std::vector<int> slot_of_cell;
    int ts5_nsteps = 0;
    std::vector<int> cls_of_cell, tz_of_cell;
    std::vector<double> tz_list;
@@ -567,7 +604,7 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
    for (int i = 0; i < 6; i++) cudaFree(h->d_blk[i]);
-   cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast);
+   cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg);
 }
 
 int suews_b200_destroy(suews_b200_handle h)
@@ -742,6 +779,8 @@ int suews_b200_upload(suews_b200_handle h)
       }
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[(size_t)x] < key[(size_t)y]; });
    }
+   h->slot_of_cell.assign((size_t)h->ncell, 0);
+   for (int sl = 0; sl < h->ncell; sl++) h->slot_of_cell[(size_t)order[(size_t)sl]] = sl;
    const size_t st = (size_t)h->stride;
    CUDA_OK(dev_alloc(&h->d_order, st));
    CUDA_OK(cudaMemcpy(h->d_order, order.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
@@ -918,6 +957,30 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
       h->blk_nsteps = nsteps;
    }
    SuRunArgs a;
+   a.agg = nullptr; a.agg_nlines = 1;
+   if (out_flags & SUEWS_OUT_AGG) {
+      if (out_flags & (SUEWS_OUT_SUM82 | SUEWS_OUT_SUM7))
+         return set_err(SUEWS_E_BAD_ARG, "advance: SUEWS_OUT_AGG cannot be combined with the running-sum policies");
+      // nlinesOut = INT(nsh/(60.*60/outFreq_s)), suews_ctrl_output.f95:922
+      const int nsh = 3600 / h->tstep;
+      const int nlines = (int)((float)nsh / (60.f * 60 / (float)h->out_freq_s));
+      if (nlines < 1) return set_err(SUEWS_E_BAD_ARG, "advance: output frequency %d s is finer than the timestep", h->out_freq_s);
+      const int rows = nsteps / nlines;
+      const size_t need = (size_t)(rows ? rows : 1) * (SUEWS_NCOL_SUEWS + 5) * (size_t)h->stride;
+      if (h->agg_cap < need) {
+         if (h->d_agg) { cudaFree(h->d_agg); h->d_agg = nullptr; }
+         h->agg_cap = 0;
+         if (cudaMalloc((void **)&h->d_agg, sizeof(double) * need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(SUEWS_E_BAD_ARG, "advance: the aggregated block needs %.1f GB of device memory (%d rows x 87 x %d cells)",
+                           (double)need * 8e-9, rows, h->ncell);
+         }
+         h->agg_cap = need;
+      }
+      h->agg_rows = rows;
+      a.agg = h->d_agg;
+      a.agg_nlines = nlines;
+   }
    a.classes = h->d_classes; a.class_of_cell = h->d_cls; a.tz_of_cell = h->d_tz; a.order = h->d_order; a.cellp = h->d_cellp; a.state = h->d_state;
    a.steps = h->d_steps + step0;
    a.ephem = h->d_ephem + step0;
@@ -939,6 +1002,43 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
    h->dt_since_start += nsteps * h->tstep;
    h->tstep_prev = h->tstep;
+   return SUEWS_OK;
+}
+
+int suews_b200_set_output_freq(suews_b200_handle h, int out_freq_s)
+{
+   if (!h || out_freq_s <= 0) return set_err(SUEWS_E_BAD_ARG, "set_output_freq: bad arguments");
+   h->out_freq_s = out_freq_s;
+   return SUEWS_OK;
+}
+
+// One cell's aggregated SUEWS block [nrows x 87], column-major, as SUEWS_Output_Agg returns it
+int suews_b200_get_agg_block(suews_b200_handle h, int cell, double *block, int nrows)
+{
+   if (!h || !block || !h->d_agg || nrows != h->agg_rows || cell < 0 || cell >= h->ncell)
+      return set_err(SUEWS_E_BAD_SIZE, "get_agg_block: the aggregated block is [%d x 87] per cell", h ? h->agg_rows : 0);
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   const int ncol = SUEWS_NCOL_SUEWS + 5;
+   std::vector<double> tmp((size_t)nrows * ncol);   // [row][col]
+   CUDA_OK(cudaMemcpy2D(tmp.data(), sizeof(double), h->d_agg + h->slot_of_cell[(size_t)cell], sizeof(double) * (size_t)h->stride,
+                        sizeof(double), (size_t)nrows * ncol, cudaMemcpyDeviceToHost));
+   for (int r = 0; r < nrows; r++)
+      for (int c = 0; c < ncol; c++) block[(size_t)r + (size_t)nrows * c] = tmp[(size_t)r * ncol + c];
+   return SUEWS_OK;
+}
+
+// One column of one aggregated row for every cell (a map), [ncell]
+int suews_b200_get_agg_column(suews_b200_handle h, int row, int col, double *vals)
+{
+   if (!h || !vals || !h->d_agg || row < 0 || row >= h->agg_rows || col < 0 || col >= SUEWS_NCOL_SUEWS + 5)
+      return set_err(SUEWS_E_BAD_SIZE, "get_agg_column: row/column outside the [%d x 87] aggregated block", h ? h->agg_rows : 0);
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   std::vector<double> tmp((size_t)h->ncell);
+   CUDA_OK(cudaMemcpy(tmp.data(), h->d_agg + ((size_t)row * (SUEWS_NCOL_SUEWS + 5) + col) * (size_t)h->stride,
+                      sizeof(double) * (size_t)h->ncell, cudaMemcpyDeviceToHost));
+   for (int c = 0; c < h->ncell; c++) vals[c] = tmp[(size_t)h->slot_of_cell[(size_t)c]];
    return SUEWS_OK;
 }
 

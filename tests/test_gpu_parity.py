@@ -534,8 +534,7 @@ def test_device_disaggregation_is_bit_identical(year, method):
     from suews_b200.forcing import disaggregate_met, read_met
     path = os.path.join(fx.GOLDEN, "forcing_%d_60min.txt" % year)
     host = disaggregate_met(read_met(path), disagg_method=method)
-    raw = read_met(path)
-    raw[:, 12] = raw[:, 12] / 10.0          # back to the file's kPa: the device applies MetRead's conversion
+    # the file's own values (pressure in kPa): the device applies MetRead's conversions
     rows = [ln.split()[:24] for ln in open(path).readlines()[1:] if len(ln.split()) >= 24 and not ln.startswith("-9")]
     raw = np.array(rows, dtype=np.float64)  # exactly what the file holds
     b = SuewsBatch(1, 1)
@@ -570,3 +569,64 @@ def test_run_from_device_disaggregated_forcing_equals_host_path():
         sums.append(b.sums().copy())
         b.close()
     assert np.array_equal(sums[0], sums[1])
+
+
+# ---- output policy P1: SUEWS_Output_Agg (suews_ctrl_output.f95:912-957) inside the kernel
+def _agg_sequential(block, nper):
+    """mean / sum / last per column with the additions in row order, as the reference's SUM over a column slice"""
+    vl = fx.varlist("SUEWS")
+    n = block.shape[0] // nper
+    out = np.zeros((n, block.shape[1]))
+    out[:, :5] = block[nper - 1::nper, :5][:n]
+    for c in range(block.shape[1] - 5):
+        col = block[: n * nper, 5 + c].reshape(n, nper)
+        a = vl[c]["aggreg"]
+        s = np.cumsum(col, axis=1)[:, -1]
+        out[:, 5 + c] = s / nper if a == "A" else (s if a == "S" else col[:, -1])
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("freq", [3600, 1800])
+def test_in_kernel_aggregation_equals_aggregating_the_full_block(gpu_and_ref_2005, freq):
+    from suews_b200 import OUT_AGG, SuewsBatch
+    bfull, ref, _cell, met = gpu_and_ref_2005
+    n = met.shape[0]
+    nper = freq // 300
+    full = bfull.block("SUEWS", 0, n)
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(fx.state_init(2005))
+    b.upload()
+    b.set_forcing(met)
+    b.set_output_freq(freq)
+    b.advance(0, n, OUT_AGG)
+    got = b.agg_block(0, n // nper)
+    want = _agg_sequential(full, nper)
+    assert np.array_equal(got, want)                      # same kernel arithmetic, same order of additions: bit for bit
+    oracle = _agg_sequential(ref["SUEWS"], nper)
+    assert np.array_equal(got[:, :5], oracle[:, :5])
+    assert float(rel_err(got[:288 // nper, 5:], oracle[:288 // nper, 5:], "SUEWS").max()) <= TOL_DAY1
+    assert np.array_equal(b.agg_column(3, 5 + 5), got[3:4, 5 + 5])
+    b.close()
+
+
+@pytest.mark.gpu
+def test_hourly_aggregates_match_the_reference_golden_file():
+    """the reference's own hourly output (Test/BaseRun/2020b, 120 h x 82 columns, 4-6 decimals)"""
+    from suews_b200 import OUT_AGG, SuewsBatch
+    met = fx.forcing(2005)
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(fx.state_init(2005))
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, met.shape[0], OUT_AGG)
+    got = b.agg_block(0, met.shape[0] // 12)
+    hdr, gold = fx.load_ref_table("ref_2005_SUEWS_60.txt")
+    assert got.shape == gold.shape == (120, 87)
+    assert np.array_equal(got[:, :4], gold[:, :4])
+    tol = fx.text_tolerance("SUEWS", 82)
+    for c in range(82):
+        r = gold[:, 5 + c]
+        ok = np.isnan(r) | (np.abs(got[:, 5 + c] - r) <= tol[c] + 1e-9 * np.abs(np.nan_to_num(r)))
+        assert ok.all(), (hdr[5 + c], int(np.argmin(ok)), got[~ok, 5 + c][:3], r[~ok][:3])
+    b.close()
