@@ -86,6 +86,10 @@ def _cpu_worker(args):
     base, met = load_inputs(1)
     d = synth.base_with_scheme(base, scheme)
     site = synth.cell_site_arrays(worker * max_cells, max_cells, d)
+    ts5 = None
+    if synth.SCHEMES[scheme]["storageheatmethod"] in (4, 14):
+        d.update({k.lower(): v for k, v in synth.estm_example(d["surfacearea"][0]).items()})
+        ts5 = synth.estm_ts_forcing(met)
     t0 = time.perf_counter()
     done = 0
     for c in range(max_cells):
@@ -96,7 +100,9 @@ def _cpu_worker(args):
         m = met.copy()
         m[:, 11] += site["dTemp_C"][c]
         m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + site["dRH"][c]))
-        cell.run(m, want=())
+        if ts5 is not None:
+            cell.estm_start(ts5[0])
+        cell.run(m, want=(), ts5=ts5)
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
@@ -128,8 +134,9 @@ def main():
     ap.add_argument("--scheme", default="default")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sums", default="parity7", choices=["parity7", "all82"],
-                    help="on-device output reduction: P0 = running sums of the 7 parity fluxes (SURVEY 8d), or of all 82 columns")
+    ap.add_argument("--sums", default="parity7", choices=["parity7", "all82", "hourly"],
+                    help="on-device output reduction: P0 = running sums of the 7 parity fluxes (SURVEY 8d), of all 82 columns, "
+                         "or P1 = the hourly-aggregated 87-column SUEWS block of every cell (SUEWS_Output_Agg in the kernel)")
     a = ap.parse_args()
     K, W = a.steps, max(a.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -168,20 +175,22 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from suews_b200 import OUT_SUM7, OUT_SUM82, SuewsBatch, synth
+    from suews_b200 import OUT_AGG, OUT_SUM7, OUT_SUM82, SuewsBatch, synth
     from suews_b200 import _lib
     from suews_b200.batch import all_fields
     global N_STATE, N_CELL
     N_STATE = sum(n for _nm, kind, n in all_fields() if kind == 3)
     N_CELL = sum(n for _nm, kind, n in all_fields() if kind == 2)
 
-    OUT = OUT_SUM7 if a.sums == "parity7" else OUT_SUM82
+    OUT = {"parity7": OUT_SUM7, "all82": OUT_SUM82, "hourly": OUT_AGG}[a.sums]
     n_sum = 7 if a.sums == "parity7" else N_SUM
+    use_estm = synth.SCHEMES[a.scheme]["storageheatmethod"] in (4, 14)
     ndays = 2 * (W + K)
     base, met = load_inputs(ndays)
     ncell = a.cells_per_gpu
     b = SuewsBatch(ncell, 1, device=local_rank)
-    synth.build_batch(b, base, cell0=rank * ncell, scheme=a.scheme)
+    ts5 = synth.estm_ts_forcing(met) if use_estm else None   # synthetic Ts forcing = air temperature
+    synth.build_batch(b, base, cell0=rank * ncell, scheme=a.scheme, ts_row0=ts5[0] if use_estm else None)
     b.upload()
 
     def barrier():
@@ -193,6 +202,8 @@ def main():
 
     # ---------------- device-resident timing
     b.set_forcing(met[: (W + K) * 288])
+    if use_estm:
+        b.set_estm_forcing(ts5[: (W + K) * 288])
     for i in range(W):
         b.advance(i * 288, 288, OUT, sync=False)
     barrier()
@@ -225,8 +236,13 @@ def main():
             e2e_t0 = time.perf_counter()
         day = met[(W + K + i) * 288:(W + K + i + 1) * 288]
         b.set_forcing(day)                      # host -> device (pinned staging) + ephemeris kernel
+        if use_estm:
+            b.set_estm_forcing(ts5[(W + K + i) * 288:(W + K + i + 1) * 288])
         b.advance(0, 288, OUT, sync=False)
-        res = b.sums_cols(cols)                 # device -> host (pinned staging), waits for the kernel
+        if a.sums == "hourly":                  # device -> host: the last hour's QN..QE maps of all cells
+            res = np.stack([b.agg_column(23, 5 + c) for c in cols], axis=1)
+        else:
+            res = b.sums_cols(cols)             # device -> host (pinned staging), waits for the kernel
     barrier()
     e2e_s = time.perf_counter() - e2e_t0
     if dist is not None:
@@ -250,6 +266,8 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     # algorithmic bytes per launch: state read+write, cell params read, sums read+write, per cell; forcing shared
     bytes_per_launch = ncell * 8.0 * (2 * N_STATE + N_CELL + 2 * n_sum) + 288 * 160.0
+    if a.sums == "hourly":   # P1: no sums in/out; 24 aggregated rows x 87 columns written per cell
+        bytes_per_launch = ncell * 8.0 * (2 * N_STATE + N_CELL + 24 * 87) + 288 * 160.0
     launch_s = dev_s / K
     ach_gbs = bytes_per_launch / launch_s / 1e9
     prof = {}
@@ -272,8 +290,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "cells_per_gpu": ncell, "timesteps_per_step": 288, "output_policy": ("P0: per-cell running sums of the 7 parity fluxes QN,QF,QS,QH,QE,RO,SWE" if a.sums == "parity7"
-                                     else "P0+: per-cell running sums of all 82 SUEWS columns"),
+        "config": {"workload": workload, "cells_per_gpu": ncell, "timesteps_per_step": 288, "output_policy": {
+                       "parity7": "P0: per-cell running sums of the 7 parity fluxes QN,QF,QS,QH,QE,RO,SWE",
+                       "all82": "P0+: per-cell running sums of all 82 SUEWS columns",
+                       "hourly": "P1: hourly-aggregated 87-column SUEWS block of every cell, aggregated in the kernel"}[a.sums],
                    "l2": "inputs (state+params %.0f MB/GPU) larger than L2" % (ncell * 8.0 * (N_STATE + N_CELL + N_SUM) / 1e6),
                    "tsurf_iterations_per_step": float(iters.sum()) / (ncell * 288.0 * (2 * (W + K))), "wall_s_timed": wall,
                    "checksum_QN": checksum, "fatal_cells": int((fatal != 0).sum())},

@@ -76,15 +76,15 @@ __global__ void suews_disagg_kernel(SuDisaggArgs a)
    for (int c = 4; c < SUEWS_NCOL_MET; c++) {
       double v = -999.0;
       const bool missing = (a.all_missing >> c) & 1u;
-      if (c == 13 || c == 15) {   // rain and snow: spread evenly over the nper sub-intervals
-         if (c == 15 && missing) {
-            v = 0.0;             // ctrl_input.f95:1545-1549 and the final reset of an all -999 snow column
-         } else {
-            const double s = su_slow_at(a, i0, c);
-            v = (s > 0) ? s / nper : 0.0;
-         }
+      if (c == 13) {   // rain: spread evenly over the nper sub-intervals (DisaggP_amongN with amongN = Nper)
+         const double s = su_slow_at(a, i0, c);
+         v = (s > 0) ? s / nper : 0.0;
+      } else if (c == 15 && missing) {
+         v = 0.0;                // an all -999 snow column ends as 0 (ctrl_input.f95:1507-1508, :1611-1613)
       } else if (c == 23 || missing) {
          v = -999.0;             // wind direction is not disaggregated; missing columns stay missing
+         // (a snow column that is present is first spread like rain inside the ii == 14 branch and then overwritten
+         //  by Disagg_Lin when the loop reaches ii == 16, ctrl_input.f95:1503-1563: only the second result survives)
       } else if (!((a.type20 >> c) & 1u)) {
          // type 10: the original value is the average of the period that ends at its time stamp
          long long q = r - half;

@@ -61,45 +61,5 @@ def text_tolerance(group, ncol):
     return tol
 
 
-C2K = float(np.float32(273.15))   # REAL(KIND(1d0)), PARAMETER :: C2K = 273.15 (a REAL(4) literal)
-
-
-def estm_example(surface_area, **over):
-    """An ESTM (StorageHeatMethod 4) parameter set as the reference's SUEWS_Translate / ESTM_initials leave it in
-    MODULE ESTM_data for the BaseRun site: building class 801 and paved class 807 of
-    Test/BaseRun/2020b/Input/SUEWS_ESTMCoefficients.txt, ESTMinput.nml of the same directory, the internal view
-    factors and floor temperature hard-coded in ESTM_translate (suews_phys_estm.f95:673-692).  AreaWall is -999 in
-    that SiteSelect row (ESTM is off in the BaseRun); 0.4 x SurfaceArea is used here."""
-    def pad(v):
-        return list(v) + [-999.0] * (5 - len(v))
-    d = dict(
-        evolveTibld=[0], TsurfChoice=[0], ibldCHmod=[0], Nibld=[3], Nwall=[3], Nroof=[3], Nground=[4],
-        LBC_soil=[8.5], THEAT_ON=[18.0 + C2K], THEAT_OFF=[22.0 + C2K], THEAT_fix=[19.0 + C2K],
-        ivf_iw=[float(np.float32(0.1))], ivf_ir=[0.0], ivf_ii=[float(np.float32(0.9))], ivf_if=[0.0],
-        ivf_ww=[float(np.float32(0.05))], ivf_wr=[0.0], ivf_wi=[float(np.float32(0.95))], ivf_wf=[0.0],
-        ivf_rw=[float(np.float32(0.05))], ivf_ri=[float(np.float32(0.95))], ivf_rf=[0.0],
-        ivf_fw=[float(np.float32(0.05))], ivf_fr=[0.0], ivf_fi=[float(np.float32(0.95))],
-        zibld=pad([0.035] * 3), kibld=pad([0.93] * 3), ribld=pad([1500000.0] * 3),
-        zwall=pad([0.087, 0.0497, 0.0497]), kwall=pad([0.760645, 0.93, 0.93]), rwall=pad([1046908.363, 1500000.0, 1500000.0]),
-        zroof=pad([0.05, 0.15, 0.12]), kroof=pad([1.142, 0.93, 0.05]), rroof=pad([1606620.0, 1500000.0, 290000.0]),
-        zground=pad([0.05, 0.10, 0.5, 0.7]), kground=pad([1.16, 1.16, 0.63, 0.63]),
-        rground=pad([2285607.0, 2285607.0, 1200000.0, 1200000.0]),
-        nroom=[10.0], alb_ibld=[0.5], em_ibld=[1.0], CH_iroof=[0.0015], CH_iwall=[0.0015], CH_ibld=[0.0015],
-        AreaWall=[0.4 * float(surface_area)], Tfloor=[float(np.float32(20.0)) + C2K],
-    )
-    for k, v in over.items():
-        d[k] = list(np.atleast_1d(v))
-    return d
-
-
-def estm_ts_forcing(met, tiair=20.0, offsets=(0.0, 1.0, 2.0, 0.5, -0.5, 0.3, 0.8, 0.1)):
-    """Synthetic ESTM surface-temperature forcing [len_sim, 13] (iy id it imin Tiair Tsurf Troof Troad Twall
-    Twall_n Twall_e Twall_s Twall_w): the air temperature of the met block plus a fixed offset per column
-    ("synthetic Ts forcing = air temperature")."""
-    met = np.asarray(met)
-    ts = np.zeros((met.shape[0], 13))
-    ts[:, :4] = met[:, :4]
-    ts[:, 4] = tiair
-    for j, off in enumerate(offsets):
-        ts[:, 5 + j] = met[:, 11] + off
-    return ts
+# ESTM example parameter set / synthetic surface-temperature forcing: shared with the bench's scheme sweep
+from suews_b200.synth import C2K, estm_example, estm_ts_forcing  # noqa: E402,F401
