@@ -19,7 +19,7 @@ SU_DEV double sat_vap_press(double TK, double P)
 // rewrite is a separate inline step (su_fix_T) and the evaluation takes T by value.  Warnings 28/29 are
 // raised by the callers through sat_vap_press_warn.
 SU_INL double su_fix_T(double T) { return (fabs(T) < F(0.001000)) ? (double)F(0.001000) : T; }
-SU_DEV double sat_vap_press_v(double T, double Press_hPa)   // T already through su_fix_T
+SU_HOT double sat_vap_press_v(double T, double Press_hPa)   // T already through su_fix_T
 {
    // water (T >= 0.001) and ice (T <= -0.001) branches of meteo.f95:171-186 differ only in seven constants;
    // selecting the constants keeps a warp whose cells straddle 0 degC on one instruction stream
@@ -173,7 +173,7 @@ SU_DEV void cal_AtmMoist(SuDiag &dg, double &Temp_C, double Press_hPa, double av
 #define SU_PIOVER2 ((double)(3.14159274f / 2.f))   // ACOS(-1.)/2. in REAL(4)
 
 // atmmoiststab.f95:252-331.  SM is a template parameter where the caller knows the scheme.
-SU_DEV double stab_psi_mom(int sm, double zl)   // by value: the reference's in-place clip of zL (sm = 2) never outlives its callers' own clips
+SU_HOT double stab_psi_mom(int sm, double zl)   // by value: the reference's in-place clip of zL (sm = 2) never outlives its callers' own clips
 {
    double psim = 0, x, x2;
    if (fabs(zl) < SU_NEUT_LIMIT) {

@@ -24,12 +24,24 @@
 
 #ifndef SU_INLINE_ALL
 #include "dev_math.cuh"
-#ifdef SU_LIBM_EXPLOG
-SU_DEVNI double su_exp(double x) { return exp(x); }
-SU_DEVNI double su_log(double x) { return log(x); }
+// tuning switches (tools/variants.sh): SU_EXPLOG_INLINE inlines exp/log at their call sites, SU_HOT_INLINE does the
+// same for the small physics helpers that are called dozens of times per step (SU_HOT)
+#ifdef SU_EXPLOG_INLINE
+#define SU_EXPLOG_ATTR SU_INL
 #else
-SU_DEVNI double su_exp(double x) { return su_exp_fast(x); }
-SU_DEVNI double su_log(double x) { return su_log_fast(x); }
+#define SU_EXPLOG_ATTR SU_DEVNI
+#endif
+#ifdef SU_HOT_INLINE
+#define SU_HOT SU_INL
+#else
+#define SU_HOT SU_DEV
+#endif
+#ifdef SU_LIBM_EXPLOG
+SU_EXPLOG_ATTR double su_exp(double x) { return exp(x); }
+SU_EXPLOG_ATTR double su_log(double x) { return log(x); }
+#else
+SU_EXPLOG_ATTR double su_exp(double x) { return su_exp_fast(x); }
+SU_EXPLOG_ATTR double su_log(double x) { return su_log_fast(x); }
 #endif
 SU_DEVNI double su_pow_general(double x, double y) { return pow(x, y); }
 // x**0.5, x**0.25, x**(-0.25), x**(-0.5), x**1.5 -- the exponents of the stability functions, NARP's

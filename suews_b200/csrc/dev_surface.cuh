@@ -471,7 +471,7 @@ SU_DEV void cal_SoilState(SuDiag &dg, int SMDMethod, double xsmd, double NonWate
 }
 
 // van Genuchten (1980) matric potential and conductivity of one store, waterdist.f95:707-762
-SU_DEV void vg_store(double soilstore, double SoilStoreCap, double SoilDepth, double Ksat, double &MatPot, double &Km)
+SU_HOT void vg_store(double soilstore, double SoilStoreCap, double SoilDepth, double Ksat, double &MatPot, double &Km)
 {
    const double alphavG = F(0.0005);
    double capVol = SoilStoreCap / SoilDepth;
