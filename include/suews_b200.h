@@ -176,6 +176,14 @@ int suews_cal_sunposition_c(double year, double idectime, double UTC, double loc
 int suews_output_size(int *nVar);
 int suews_output_name_n(int i, char name[16], char group[16], char aggreg[16], int *outlevel);
 
+/* The text form of an output block, as SUEWS_Output_Init + SUEWS_Write_txt write it (suews_ctrl_output.f95:737-1023):
+ * block is column-major [nrows x ncol] (5 datetime columns first; e.g. what suews_b200_get_agg_block or a
+ * SUEWS_cal_multitsteps block aggregated by the caller holds), group one of "SUEWS", "snow", "ESTM", "RSL", "SOLWEIG",
+ * "DailyState", outlevel the WriteOutOption level (0, 1, 2).  Writes at most buflen - 1 bytes + NUL into buf (buf may be
+ * NULL to size it) and returns the full length, or a negative SUEWS_E_* value. */
+long long suews_write_txt(const double *block, int nrows, int ncol, const char *group, int outlevel, int with_header, char *buf,
+                          long long buflen);
+
 /* Diagnostic: compares the library's own exp/log (suews_b200/csrc/dev_math.cuh) with the CUDA math library
  * bit for bit on n pseudo-random arguments; returns the mismatch counts (expected 0 and 0). */
 int suews_b200_selftest_math(long long n, unsigned long long seed, long long *bad_exp, long long *bad_log);

@@ -47,8 +47,9 @@ const char *const kMultiNames[] = {SUEWS_CAL_MULTITSTEPS_ARGS(X)};
 struct VarRow {
    const char *header, *unit, *aggreg, *group;
    int level;
+   const char *fmt;   // 'i0004,1X' / 'f10.4,1X' ... (suews_ctrl_output.f95:39-46)
 };
-#define V(h, u, a, g, l) {h, u, a, g, l},
+#define V(h, u, a, g, l, f) {h, u, a, g, l, f},
 const VarRow kVarList[] = {
 #include "suews_varlist.inc"
 };
@@ -338,6 +339,73 @@ int suews_output_name_n(int i, char name[16], char group[16], char aggreg[16], i
       *outlevel = v.level;
    }
    return SUEWS_OK;
+}
+
+// ---- SUEWS_Output_Init + SUEWS_Write_txt (suews_ctrl_output.f95:737-1023): the text form of an output block.
+// Columns: the five datetime variables followed by the variables of `group` in varListAll order; those with
+// level <= outlevel are written.  Header fields are right-aligned in the width of the column's format and every
+// field but the last is followed by one blank ('...,1X': a trailing X edit descriptor moves the position without
+// writing, so lines do not end in a blank).  Reals go through
+// Fortran's Fw.d edit descriptor: correctly rounded decimal, asterisks when the value does not fit, no leading
+// zero dropped while the field has room (gfortran).  Returns the number of bytes the text needs (excluding the
+// terminating NUL) and writes at most buflen - 1 of them; a negative value is an error.
+long long suews_write_txt(const double *block, int nrows, int ncol, const char *group, int outlevel, int with_header, char *buf,
+                          long long buflen)
+{
+   if (!block || !group || nrows < 0) return -SUEWS_E_BAD_ARG;
+   std::vector<const VarRow *> cols;
+   for (int i = 0; i < kNVar; i++)
+      if (strcmp(kVarList[i].group, "datetime") == 0) cols.push_back(&kVarList[i]);
+   for (int i = 0; i < kNVar; i++)
+      if (strcasecmp(kVarList[i].group, group) == 0) cols.push_back(&kVarList[i]);
+   if ((int)cols.size() <= 5) return -SUEWS_E_BAD_NAME;
+   if ((int)cols.size() > ncol) cols.resize((size_t)ncol);   // varListAll may list more names than the block has columns
+   long long pos = 0;
+   auto put = [&](const char *t, size_t n) {
+      for (size_t k = 0; k < n; k++, pos++)
+         if (buf && pos < buflen - 1) buf[pos] = t[k];
+   };
+   auto width_dec = [](const char *fmt, int &w, int &d, bool &is_int) {
+      is_int = (fmt[0] == 'i' || fmt[0] == 'I');
+      w = atoi(fmt + 1);
+      const char *dot = strchr(fmt, '.');
+      d = (dot && !is_int) ? atoi(dot + 1) : 0;
+   };
+   char tmp[512];
+   if (with_header) {
+      for (size_t c = 0; c < cols.size(); c++) {
+         if (cols[c]->level > outlevel) continue;
+         int w, d; bool is_int;
+         width_dec(cols[c]->fmt, w, d, is_int);
+         const int n = snprintf(tmp, sizeof tmp, "%*s ", w, cols[c]->header);   // ADJUSTR into (aW,1x); longer names are cut
+         if ((int)strlen(cols[c]->header) > w) { memcpy(tmp, cols[c]->header, (size_t)w); tmp[w] = ' '; put(tmp, (size_t)w + 1); }
+         else put(tmp, (size_t)n);
+      }
+      if (pos > 0) pos--;   // the trailing 1X writes nothing
+      put("\n", 1);
+   }
+   for (int r = 0; r < nrows; r++) {
+      for (size_t c = 0; c < cols.size(); c++) {
+         if (cols[c]->level > outlevel) continue;
+         int w, d; bool is_int;
+         width_dec(cols[c]->fmt, w, d, is_int);
+         const double v = block[(size_t)r + (size_t)nrows * c];
+         int n;
+         if (is_int || c < 4) n = snprintf(tmp, sizeof tmp, "%*d", w, (int)v);   // INT(dataOutSel(i, 1:4))
+         else {
+            n = snprintf(tmp, sizeof tmp, "%*.*f", w, d, v);
+            if (n == w + 1 && tmp[0] == '0') { memmove(tmp, tmp + 1, (size_t)n); n--; }                       // 0.xxxx -> .xxxx
+            else if (n == w + 1 && tmp[0] == '-' && tmp[1] == '0') { memmove(tmp + 1, tmp + 2, (size_t)n - 1); n--; }   // -0.x -> -.x
+         }
+         if (n != w) { memset(tmp, '*', (size_t)w); n = w; }
+         tmp[n] = ' ';
+         put(tmp, (size_t)n + 1);
+      }
+      if (pos > 0) pos--;
+      put("\n", 1);
+   }
+   if (buf && buflen > 0) buf[pos < buflen - 1 ? pos : buflen - 1] = 0;
+   return pos;
 }
 
 void suews_refapi_reset_hidden(void)

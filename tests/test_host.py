@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "suews_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|void)\s+(suews_\w+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(?:int|void|long long)\s+(suews_\w+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():

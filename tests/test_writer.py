@@ -1,0 +1,78 @@
+"""The text writer (SUEWS_Output_Init + SUEWS_Write_txt, suews_ctrl_output.f95:737-1023) against the reference's own
+output files: the oracle's run of the BaseRun case, aggregated as SUEWS_Output_Agg does and formatted by the library,
+must reproduce the golden text byte for byte wherever the printed digits agree (they do everywhere but for values
+sitting on a rounding boundary of the last printed decimal)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import fixtures as fx
+import oracle_lib as ol
+
+
+def _write_txt(block, group, outlevel=1, header=True):
+    from suews_b200 import _lib
+    L = C.CDLL(_lib.LIB_PATH)
+    f = L.suews_write_txt
+    f.restype = C.c_longlong
+    f.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_longlong]
+    b = np.asfortranarray(block, dtype=np.float64)
+    n = f(b.ctypes.data_as(C.POINTER(C.c_double)), b.shape[0], b.shape[1], group.encode(), outlevel, int(header), None, 0)
+    assert n > 0
+    buf = C.create_string_buffer(n + 1)
+    assert f(b.ctypes.data_as(C.POINTER(C.c_double)), b.shape[0], b.shape[1], group.encode(), outlevel, int(header), buf, n + 1) == n
+    return buf.value.decode()
+
+
+def _agg(block, group, nper=12):
+    vl = fx.varlist(group)
+    n = block.shape[0] // nper
+    out = np.zeros((n, block.shape[1]))
+    out[:, :5] = block[nper - 1::nper, :5][:n]
+    for c in range(block.shape[1] - 5):
+        col = block[: n * nper, 5 + c].reshape(n, nper)
+        a = vl[c]["aggreg"] if c < len(vl) else "A"
+        # additions in row order starting from +0, as the reference's SUM (0 + (-0) = +0: the sign shows in the text)
+        s = np.cumsum(np.concatenate([np.zeros((n, 1)), col], axis=1), axis=1)[:, -1]
+        out[:, 5 + c] = s / nper if a == "A" else (s if a == "S" else col[:, -1])
+    return out
+
+
+@pytest.fixture(scope="module")
+def run2005():
+    cell = ol.Cell(fx.state_init(2005))
+    return cell.run(fx.forcing(2005), want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
+
+
+@pytest.mark.parametrize("group,fname,level", [("SUEWS", "ref_2005_SUEWS_60.txt", 2), ("snow", "ref_2005_snow_60.txt", 2),
+                                               ("SOLWEIG", "ref_2005_SOLWEIG_60.txt", 2)])
+def test_text_output_reproduces_the_reference_files(run2005, group, fname, level):
+    gold = open(os.path.join(fx.GOLDEN, fname)).read().splitlines()
+    ours = _write_txt(_agg(run2005[group], group), group, outlevel=level).splitlines()
+    assert len(ours) == len(gold)
+    assert ours[0] == gold[0]                                   # header line: names right-aligned in the column widths
+    assert [len(x) for x in ours] == [len(x) for x in gold]     # every field has the reference's width
+    # SOLWEIG's I0 is an unassigned variable at night in the reference (DESIGN.md "(a)"): whatever its stack slot held
+    skip = {gold[0].split().index("I0")} if group == "SOLWEIG" else set()
+    nfield = nbad = 0
+    for a, b in zip(ours[1:], gold[1:]):
+        fa, fb = a.split(), b.split()
+        assert fa[:4] == fb[:4]
+        nfield += len(fa)
+        nbad += sum(x != y for c, (x, y) in enumerate(zip(fa, fb)) if c not in skip)
+    # printed digits: identical but for last-decimal roundings of values on a rounding boundary (none in these files)
+    assert nbad <= 1e-3 * nfield, (nbad, nfield)
+    if not skip:
+        assert nbad == 0 and "\n".join(ours) == "\n".join(gold)     # byte for byte
+
+
+def test_overflow_and_negative_zero_follow_fortran():
+    blk = np.zeros((1, 87))
+    blk[0, :5] = [2005, 1, 1, 0, 0.0417]
+    blk[0, 5] = 123456.78901          # f10.4: 11 characters -> asterisks
+    blk[0, 6] = -0.00001              # rounds to -0.0000
+    txt = _write_txt(blk, "SUEWS", header=False)
+    f = txt.split()
+    assert f[5] == "*" * 10 and f[6] == "-0.0000"
