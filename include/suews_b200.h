@@ -184,6 +184,13 @@ int suews_output_name_n(int i, char name[16], char group[16], char aggreg[16], i
 long long suews_write_txt(const double *block, int nrows, int ncol, const char *group, int outlevel, int with_header, char *buf,
                           long long buflen);
 
+/* The InitialConditions namelist NextInitial writes at the end of a year / run (suews_ctrl_init.f95:2022-2149), in
+ * gfortran's list-directed layout.  v54: DaysSinceRain (HDD_id(12)), Temp_C0 (HDD_id(9)), GDD_id(1:2), LAI_id(1:3),
+ * albEveTr_id, albDecTr_id, albGrass_id, DecidCap_id, porosity_id, soilstore_id(1:6), state_id(1:7), SnowWater(1:7),
+ * SnowPack(1:7), SnowFrac(1:7), SnowDens(1:7), SnowAlb; the snow entries are written when snow_use = 1.
+ * Returns the text length (buf may be NULL), or a negative SUEWS_E_* value. */
+long long suews_write_initial_conditions(const double *v54, int snow_use, char *buf, long long buflen);
+
 /* Diagnostic: compares the library's own exp/log (suews_b200/csrc/dev_math.cuh) with the CUDA math library
  * bit for bit on n pseudo-random arguments; returns the mismatch counts (expected 0 and 0). */
 int suews_b200_selftest_math(long long n, unsigned long long seed, long long *bad_exp, long long *bad_log);

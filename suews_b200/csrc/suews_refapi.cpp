@@ -13,7 +13,9 @@
 #include "../../include/suews_b200.h"
 #include "suews_refargs.inc"
 
+#include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -406,6 +408,73 @@ long long suews_write_txt(const double *block, int nrows, int ncol, const char *
    }
    if (buf && buflen > 0) buf[pos < buflen - 1 ? pos : buflen - 1] = 0;
    return pos;
+}
+
+// ---- NextInitial (suews_ctrl_init.f95:2022-2149): the InitialConditions namelist a following run starts from, in
+// gfortran's list-directed layout: a leading blank, INTEGER in 12 columns, REAL(8) with 17 significant digits in 26
+// columns -- F editing followed by five blanks for 0.1 <= |x| < 1e17 (and for 0), 1PE25.17E3 otherwise.
+static int fmt_list_real(double v, char *out)
+{
+   char num[64];
+   int n;
+   const double a = fabs(v);
+   if (v == 0.0 || (a >= 0.1 && a < 1e17)) {
+      int k = 1;   // 10^(k-1) <= a < 10^k after rounding to 17 significant digits
+      if (v != 0.0) {
+         char e[64];
+         snprintf(e, sizeof e, "%.16e", a);   // d.dddddddddddddddde+XX : the decimal exponent after rounding
+         k = atoi(strchr(e, 'e') + 1) + 1;
+      }
+      if (k < 0) k = 0;
+      n = snprintf(num, sizeof num, "%.*f", 17 - k, v);
+      return snprintf(out, 64, "%*s     ", 21, num);
+   }
+   char e[64];
+   snprintf(e, sizeof e, "%.16E", v);
+   char *ex = strchr(e, 'E');
+   const int x = atoi(ex + 1);
+   *ex = 0;
+   n = snprintf(num, sizeof num, "%sE%c%03d", e, x < 0 ? '-' : '+', x < 0 ? -x : x);
+   (void)n;
+   return snprintf(out, 64, "%*s", 26, num);
+}
+
+long long suews_write_initial_conditions(const double *v54, int snow_use, char *buf, long long buflen)
+{
+   if (!v54) return -SUEWS_E_BAD_ARG;
+   static const char *const surf[7] = {"Paved", "Bldgs", "EveTr", "DecTr", "Grass", "BSoil", "Water"};
+   std::string t = " &InitialConditions\n";
+   char f[64], nm[64];
+   snprintf(f, sizeof f, " DaysSinceRain=%12d\n", (int)v54[0]);
+   t += f;
+   static const char *const head[11] = {"Temp_C0", "GDD_1_0", "GDD_2_0", "LAIinitialEveTr", "LAIinitialDecTr", "LAIinitialGrass",
+                                         "AlbEveTr0", "AlbDecTr0", "AlbGrass0", "DecidCap0", "Porosity0"};
+   int k = 1;
+   auto line = [&](const char *name, double v) {
+      fmt_list_real(v, f);
+      t += " ";
+      t += name;
+      t += "=";
+      t += f;
+      t += "\n";
+   };
+   for (int i = 0; i < 11; i++) line(head[i], v54[k++]);
+   for (int i = 0; i < 6; i++) { snprintf(nm, sizeof nm, "SoilStore%sState", surf[i]); line(nm, v54[k++]); }
+   for (int i = 0; i < 7; i++) { snprintf(nm, sizeof nm, "%sState", surf[i]); line(nm, v54[k++]); }
+   if (snow_use == 1) {   // only when the snow part is running (init.f95:2106)
+      for (int i = 0; i < 7; i++) { snprintf(nm, sizeof nm, "SnowWater%sState", surf[i]); line(nm, v54[k++]); }
+      for (int i = 0; i < 7; i++) { snprintf(nm, sizeof nm, "SnowPack%s", surf[i]); line(nm, v54[k++]); }
+      for (int i = 0; i < 7; i++) { snprintf(nm, sizeof nm, "SnowFrac%s", surf[i]); line(nm, v54[k++]); }
+      for (int i = 0; i < 7; i++) { snprintf(nm, sizeof nm, "SnowDens%s", surf[i]); line(nm, v54[k++]); }
+      line("SnowAlb0", v54[k++]);
+   }
+   t += " /\n";
+   if (buf && buflen > 0) {
+      const size_t n = t.size() < (size_t)buflen - 1 ? t.size() : (size_t)buflen - 1;
+      memcpy(buf, t.data(), n);
+      buf[n] = 0;
+   }
+   return (long long)t.size();
 }
 
 void suews_refapi_reset_hidden(void)

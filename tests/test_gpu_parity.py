@@ -93,6 +93,17 @@ def test_flux_sums_and_state(gpu_and_ref_2005):
     assert sw == int(sd["lv_switch1"][0]) + 2 * int(sd["lv_switch2"][0])
 
 
+def test_state_after_the_2005_leg_against_the_reference_checkpoint(gpu_and_ref_2005):
+    """the reference's own end-of-run InitialConditions namelist (17 significant digits) after the same 1440 steps"""
+    from suews_b200 import checkpoint
+    b = gpu_and_ref_2005[0]
+    ref_nml = checkpoint.read(fx.GOLDEN + "/ref_InitialConditions_2005_EndofRun.nml")
+    ours = checkpoint.read_text(checkpoint.write_text(checkpoint.state_vector(lambda n: b.get_state(n)[0]), snow_use=1))
+    assert ours.keys() == ref_nml.keys()
+    worst = max(abs(ours[k] - r) / max(abs(r), 1e-3) for k, r in ref_nml.items())
+    assert worst <= 1e-9, worst
+
+
 def test_parity_sums_policy_equals_full_sums(gpu_and_ref_2005):
     """output policy P0 (seven parity fluxes) accumulates exactly what the 82-column policy holds in those columns"""
     from suews_b200 import OUT_SUM7, SuewsBatch
@@ -316,6 +327,14 @@ def test_annual_flux_sums_match_oracle():
         if nm in ("dt_since_start", "tstep_prev", "lv_switch1", "lv_switch2"):
             continue
         assert np.allclose(b.get_state(nm)[0], v, rtol=1e-7, atol=1e-9), nm
+    # ... and against the REFERENCE itself: the InitialConditions namelist it wrote at the end of its own 2004 leg holds
+    # the exact doubles of 54 state variables (tests/test_oracle_golden.py: the oracle equals them bit for bit)
+    from suews_b200 import checkpoint
+    ref_nml = checkpoint.read(fx.GOLDEN + "/ref_InitialConditions_2005.nml")
+    ours = checkpoint.read_text(checkpoint.write_text(checkpoint.state_vector(lambda n: b.get_state(n)[0]), snow_use=1))
+    assert ours.keys() == ref_nml.keys()
+    for k, r in ref_nml.items():
+        assert abs(ours[k] - r) <= 1e-7 * max(abs(r), 1e-3), (k, ours[k], r)
     b.close()
 
 

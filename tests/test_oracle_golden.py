@@ -113,3 +113,55 @@ def test_sun_position_golden_quirk():
     dectime = (1 - 1) + 13 / 24.0
     az, zen = ol.sun_position(2005.0, dectime - 150, 2.0, 57.77, 11.87, 15.0)
     assert abs(zen - row[zen_col]) < 0.6e-4
+
+
+# ---- the sharpest pin in the reference repository: the InitialConditions namelists NextInitial wrote at the end of
+# the 2004 leg (105 408 steps) and of the 2005 leg (1 440 steps) of the golden run, list-directed = 17 significant
+# digits = the exact doubles of 54 state variables (surface and soil stores, snow pack / fraction / density / water,
+# albedos, LAI, porosity, the 5-day mean temperature).  The oracle reproduces every one of them BIT FOR BIT.
+def _nml_pairs(cell, nml):
+    from suews_b200 import checkpoint
+    v = checkpoint.state_vector(cell.get_state)
+    names = (["DaysSinceRain", "Temp_C0", "GDD_1_0", "GDD_2_0", "LAIinitialEveTr", "LAIinitialDecTr", "LAIinitialGrass",
+              "AlbEveTr0", "AlbDecTr0", "AlbGrass0", "DecidCap0", "Porosity0"] +
+             ["SoilStore%sState" % s for s in checkpoint.SURF[:6]] + ["%sState" % s for s in checkpoint.SURF] +
+             ["SnowWater%sState" % s for s in checkpoint.SURF] + ["SnowPack%s" % s for s in checkpoint.SURF] +
+             ["SnowFrac%s" % s for s in checkpoint.SURF] + ["SnowDens%s" % s for s in checkpoint.SURF] + ["SnowAlb0"])
+    assert len(names) == v.size == 54
+    return names, v, np.array([nml[k] for k in names])
+
+
+@pytest.fixture(scope="module")
+def cell_after_2004():
+    cell = ol.Cell(fx.state_init(2004))
+    cell.run(fx.forcing(2004), want=())
+    return cell
+
+
+def test_state_after_2005_leg_is_the_reference_s_bit_for_bit():
+    from suews_b200 import checkpoint
+    cell = ol.Cell(fx.state_init(2005))
+    cell.run(fx.forcing(2005), want=())
+    names, ours, ref = _nml_pairs(cell, checkpoint.read(fx.GOLDEN + "/ref_InitialConditions_2005_EndofRun.nml"))
+    bad = [(n, a, b) for n, a, b in zip(names, ours, ref) if a != b]
+    assert not bad, bad
+
+
+def test_state_after_full_year_2004_is_the_reference_s_bit_for_bit(cell_after_2004):
+    from suews_b200 import checkpoint
+    names, ours, ref = _nml_pairs(cell_after_2004, checkpoint.read(fx.GOLDEN + "/ref_InitialConditions_2005.nml"))
+    bad = [(n, a, b) for n, a, b in zip(names, ours, ref) if a != b]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("fname,year", [("ref_InitialConditions_2005_EndofRun.nml", 2005), ("ref_InitialConditions_2005.nml", 2004)])
+def test_checkpoint_writer_reproduces_the_reference_file(fname, year, cell_after_2004):
+    """NextInitial's list-directed text (suews_ctrl_init.f95:2022-2149) from the library's writer: byte for byte"""
+    from suews_b200 import checkpoint
+    if year == 2004:
+        cell = cell_after_2004
+    else:
+        cell = ol.Cell(fx.state_init(2005))
+        cell.run(fx.forcing(2005), want=())
+    text = checkpoint.write_text(checkpoint.state_vector(cell.get_state), snow_use=1)
+    assert text == open(fx.GOLDEN + "/" + fname).read()
