@@ -106,6 +106,10 @@ int suews_b200_get_forcing_block(suews_b200_handle h, double *met_fast, int nste
  * (suews_ctrl_translate.f95:1264-1265): ts5 is [nsteps x 13] column-major (iy id it imin Tiair Tsurf Troof Troad
  * Twall Twall_n Twall_e Twall_s Twall_w), shared by all cells, the same rows as the forcing block set before it. */
 int suews_b200_set_estm_forcing(suews_b200_handle h, const double *ts5, int nsteps);
+/* ... or at file resolution ([nrows x 13], e.g. hourly): DisaggregateESTM (suews_ctrl_input.f95:1650-1849) on the device,
+ * DisaggMethodESTM 1 (period averages) or 2 (instantaneous values); get_estm_forcing_block reads the result back. */
+int suews_b200_set_estm_forcing_orig(suews_b200_handle h, const double *ts_orig, int nrows, int resolution_in_s, int disagg_method);
+int suews_b200_get_estm_forcing_block(suews_b200_handle h, double *ts_fast, int nsteps);
 
 /* Advance all cells over forcing rows [step0, step0 + nsteps).  One kernel launch.  Asynchronous
  * with respect to the host; suews_b200_sync waits and returns the first fatal cell error (0 if none). */

@@ -163,6 +163,16 @@ class SuewsBatch:
         assert t.shape == (self.nsteps, 13)
         check(self.L.suews_b200_set_estm_forcing(self.h, t.ctypes.data_as(dp), t.shape[0]))
 
+    def set_estm_forcing_orig(self, ts_orig, resolution_in=3600, disagg_method=1):
+        """ESTM surface temperatures at file resolution [nrows, 13], disaggregated on the device (DisaggregateESTM,
+        suews_ctrl_input.f95:1650-1849).  Returns the [nsteps, 13] block the device built."""
+        t = np.asfortranarray(np.asarray(ts_orig, dtype=np.float64))
+        assert t.shape[1] == 13
+        check(self.L.suews_b200_set_estm_forcing_orig(self.h, t.ctypes.data_as(dp), t.shape[0], int(resolution_in), int(disagg_method)))
+        b = np.zeros((self.nsteps, 13), order="F")
+        check(self.L.suews_b200_get_estm_forcing_block(self.h, b.ctypes.data_as(dp), self.nsteps))
+        return b
+
     def advance(self, step0, nsteps, out_flags=OUT_SUM82, sync=True):
         check(self.L.suews_b200_advance(self.h, int(step0), int(nsteps), int(out_flags)))
         if sync:

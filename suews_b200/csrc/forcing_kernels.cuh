@@ -16,9 +16,11 @@
 #include "suews_fields.h"
 
 struct SuDisaggArgs {
-   const double *slow;   // [n x 24] column-major, as read from the file
-   double *fast;         // [n*nper x 24] column-major
+   const double *slow;   // [n x ncol] column-major, as read from the file
+   double *fast;         // [n*nper x ncol] column-major
    int n, nper, tstep;
+   int ncol;             // 24: met forcing (DisaggregateMet); 13: ESTM surface temperatures (DisaggregateESTM, :1650-1849)
+   int rain_col, snow_col, skip_col;   // 0-based special columns of the met block (13, 15, 23), -1 when there are none
    int raw_units;        // 1: column 13 (pressure) is in kPa -> hPa (ctrl_input.f95:109)
    int smd_method;       // 0: xsmd = -999 (ctrl_input.f95:96-102)
    unsigned all_missing; // bit c set: column c of the input is -999 throughout (ctrl_input.f95:1524, :1545)
@@ -37,8 +39,10 @@ __host__ __device__ inline int su_days_in_year(int y)
 __device__ __forceinline__ double su_slow_at(const SuDisaggArgs &a, int i, int c)
 {
    double v = a.slow[(size_t)i + (size_t)a.n * c];
-   if (c == 12 && a.raw_units) v = v * 10.0;       // Pres_hPa = Pres_kPa*10.
-   if (c == 19 && a.smd_method == 0) v = -999.0;   // no soil-moisture observations
+   if (a.ncol == SUEWS_NCOL_MET) {
+      if (c == 12 && a.raw_units) v = v * 10.0;       // Pres_hPa = Pres_kPa*10.
+      if (c == 19 && a.smd_method == 0) v = -999.0;   // no soil-moisture observations
+   }
    return v;
 }
 
@@ -73,15 +77,15 @@ __global__ void suews_disagg_kernel(SuDisaggArgs a)
    }
    const int xn = (nper % 2 == 0) ? 2 : 1;
    const int half = nper / 2;
-   for (int c = 4; c < SUEWS_NCOL_MET; c++) {
+   for (int c = 4; c < a.ncol; c++) {
       double v = -999.0;
       const bool missing = (a.all_missing >> c) & 1u;
-      if (c == 13) {   // rain: spread evenly over the nper sub-intervals (DisaggP_amongN with amongN = Nper)
+      if (c == a.rain_col) {   // rain: spread evenly over the nper sub-intervals (DisaggP_amongN with amongN = Nper)
          const double s = su_slow_at(a, i0, c);
          v = (s > 0) ? s / nper : 0.0;
-      } else if (c == 15 && missing) {
+      } else if (c == a.snow_col && missing) {
          v = 0.0;                // an all -999 snow column ends as 0 (ctrl_input.f95:1507-1508, :1611-1613)
-      } else if (c == 23 || missing) {
+      } else if (c == a.skip_col || missing) {
          v = -999.0;             // wind direction is not disaggregated; missing columns stay missing
          // (a snow column that is present is first spread like rain inside the ii == 14 branch and then overwritten
          //  by Disagg_Lin when the loop reaches ii == 16, ctrl_input.f95:1503-1563: only the second result survives)

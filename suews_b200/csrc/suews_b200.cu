@@ -502,6 +502,7 @@ struct suews_b200_handle_s {
    std::vector<double> cellp, state;   // SoA [field][stride]
    std::vector<double> estm;           // ESTM state SoA [SUEWS_N_ESTM_DBL][stride]; empty until ESTM is used
    std::vector<double> ts5;            // ESTM surface-temperature forcing [nsteps][SUEWS_N_TS5]
+   std::vector<double> ts5_block;      // ... as disaggregated on the device, [nsteps x 13] column-major
    double *d_estm = nullptr, *d_ts5 = nullptr;
    double *d_met_orig = nullptr, *d_met_fast = nullptr;   // forcing at file resolution / disaggregated on the device
    double *d_agg = nullptr;                               // aggregated SUEWS block [rows][87][stride] (thread-slot order)
@@ -879,6 +880,7 @@ int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int
    if (nfast > (size_t)0x7fffffff) return set_err(SUEWS_E_BAD_ARG, "set_forcing_orig: too many timesteps");
    SuDisaggArgs a;
    a.n = nrows; a.nper = nper; a.tstep = tstep; a.raw_units = raw_units; a.smd_method = smd_method;
+   a.ncol = SUEWS_NCOL_MET; a.rain_col = 13; a.snow_col = 15; a.skip_col = 23;
    a.all_missing = 0; a.type20 = 0;
    for (int c = 4; c < SUEWS_NCOL_MET; c++) {
       bool all = true;
@@ -917,6 +919,56 @@ int suews_b200_get_forcing_block(suews_b200_handle h, double *met_fast, int nste
       return set_err(SUEWS_E_BAD_ARG, "get_forcing_block: no device-disaggregated block of %d rows", nsteps);
    CUDA_OK(cudaSetDevice(h->device));
    CUDA_OK(cudaMemcpy(met_fast, h->d_met_fast, sizeof(double) * (size_t)nsteps * SUEWS_NCOL_MET, cudaMemcpyDeviceToHost));
+   return SUEWS_OK;
+}
+
+// ESTM surface temperatures at file resolution -> model timestep on the device (DisaggregateESTM, ctrl_input.f95:1650-1849:
+// the date/time and Disagg_Lin of the met block, DisaggMethodESTM 1 = period averages, 2 = instantaneous values)
+int suews_b200_set_estm_forcing_orig(suews_b200_handle h, const double *ts_orig, int nrows, int resolution_in_s, int disagg_method)
+{
+   if (!h || !ts_orig || nrows < 2 || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "set_estm_forcing_orig: bad arguments");
+   const int tstep = h->tstep;
+   if (resolution_in_s <= 0 || resolution_in_s % tstep != 0)
+      return set_err(SUEWS_E_BAD_ARG, "set_estm_forcing_orig: ResolutionFilesInESTM %d is not a multiple of tstep %d", resolution_in_s, tstep);
+   if (disagg_method != 1 && disagg_method != 2)
+      return set_err(2, "Problem in SUEWS_ESTMDisagg: DisaggMethodESTM value should be 1 or 2 (got %d)", disagg_method);
+   const int nper = resolution_in_s / tstep;
+   const size_t n = (size_t)nrows, nfast = n * (size_t)nper;
+   if ((int)nfast != h->nsteps)
+      return set_err(SUEWS_E_BAD_ARG, "set_estm_forcing_orig: %zu timesteps, but the forcing block has %d (set the forcing first)", nfast, h->nsteps);
+   CUDA_OK(cudaSetDevice(h->device));
+   SuDisaggArgs a;
+   a.n = nrows; a.nper = nper; a.tstep = tstep; a.raw_units = 0; a.smd_method = 1;
+   a.ncol = 13; a.rain_col = -1; a.snow_col = -1; a.skip_col = -1;
+   a.all_missing = 0; a.type20 = 0;
+   for (int c = 4; c < 13; c++) {
+      bool all = true;
+      for (size_t i = 0; i < n && all; i++) all = (ts_orig[i + n * c] == -999.0);
+      if (all) a.all_missing |= (1u << c);
+      if (disagg_method == 2) a.type20 |= (1u << c);
+   }
+   double *d_slow = nullptr, *d_fast = nullptr;
+   CUDA_OK(dev_alloc(&d_slow, n * 13));
+   CUDA_OK(dev_alloc(&d_fast, nfast * 13));
+   a.slow = d_slow; a.fast = d_fast;
+   CUDA_OK(cudaMemcpyAsync(d_slow, ts_orig, sizeof(double) * n * 13, cudaMemcpyHostToDevice, h->stream));
+   suews_disagg_kernel<<<(unsigned)((nfast + 255) / 256), 256, 0, h->stream>>>(a);
+   CUDA_OK(cudaGetLastError());
+   h->ts5_block.resize(nfast * 13);
+   CUDA_OK(cudaMemcpyAsync(h->ts5_block.data(), d_fast, sizeof(double) * nfast * 13, cudaMemcpyDeviceToHost, h->stream));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   cudaFree(d_slow);
+   cudaFree(d_fast);
+   // the [nsteps][9] layout the timestep kernel reads (a few hundred KB: repacked through the host copy kept for readback)
+   return suews_b200_set_estm_forcing(h, h->ts5_block.data(), (int)nfast);
+}
+
+// the disaggregated surface-temperature block [nsteps x 13], column-major
+int suews_b200_get_estm_forcing_block(suews_b200_handle h, double *ts_fast, int nsteps)
+{
+   if (!h || !ts_fast || h->ts5_block.size() != (size_t)nsteps * 13)
+      return set_err(SUEWS_E_BAD_ARG, "get_estm_forcing_block: no device-disaggregated block of %d rows", nsteps);
+   memcpy(ts_fast, h->ts5_block.data(), sizeof(double) * (size_t)nsteps * 13);
    return SUEWS_OK;
 }
 

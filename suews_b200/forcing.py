@@ -126,6 +126,33 @@ def _disagg_p_among_n(slow, among_n, nper):
     return fast
 
 
+def read_estm_ts(path):
+    """An ESTM surface-temperature file (iy id it imin Tiair Tsurf Troof Troad Twall Twall_n/e/s/w), any resolution."""
+    rows = []
+    with open(path) as fh:
+        fh.readline()
+        for ln in fh:
+            t = ln.split()
+            if len(t) >= 13 and not t[0].startswith("-9"):
+                rows.append([float(x) for x in t[:13]])
+    return np.array(rows, dtype=np.float64)
+
+
+def disaggregate_estm(ts_orig, tstep=300, resolution_in=3600, disagg_method=1):
+    """DisaggregateESTM (suews_ctrl_input.f95:1650-1849), whole-file semantics: the date/time and Disagg_Lin of the met
+    block applied to the nine temperature columns; DisaggMethodESTM 1 = period averages, 2 = instantaneous values."""
+    ts_orig = np.asarray(ts_orig, dtype=np.float64)
+    if disagg_method not in (1, 2):
+        raise ValueError("DisaggMethodESTM value should be 1 or 2")  # ErrorHint 2
+    nper = resolution_in // tstep
+    out = np.full((ts_orig.shape[0] * nper, 13), -999.0)
+    out[:, 0:4] = _disagg_datetime(ts_orig[:, 0:4], tstep, nper)
+    for c in range(4, 13):
+        if not np.all(ts_orig[:, c] == -999):
+            out[:, c] = _disagg_lin(ts_orig[:, c], -999.0, -999.0, 10 if disagg_method == 1 else 20, nper)
+    return out
+
+
 def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, rain_disagg_method=100,
                      first_block=True, last_block=True, prev_row=None, next_row=None):
     """Disaggregate an original-resolution met block (already passed through ``read_met``)."""

@@ -103,3 +103,14 @@ def test_estm_without_forcing_rows_is_a_no_data_run():
     cell.estm_start(fx.estm_ts_forcing(fx.forcing(2005)[:1])[0])
     out = cell.run(fx.forcing(2005)[:3], want=("ESTM",))
     assert out["ESTM"].shape == (3, 32)
+
+
+def test_estm_forcing_disaggregation_matches_the_reference_5min_file():
+    """DisaggregateESTM (suews_ctrl_input.f95:1650-1849): the reference wrote its 5-min series (f9.4) next to the hourly
+    input in Release/InputTables/2020a; the numpy restatement reproduces every printed digit and every time stamp"""
+    from suews_b200.forcing import disaggregate_estm, read_estm_ts
+    fast = disaggregate_estm(read_estm_ts(fx.GOLDEN + "/estm_ts_2005_60min.txt"))
+    ref = read_estm_ts(fx.GOLDEN + "/ref_estm_ts_2005_5min.txt")
+    assert fast.shape == ref.shape == (1440, 13)
+    assert np.array_equal(fast[:, :4], ref[:, :4])
+    assert np.abs(fast[:, 4:] - ref[:, 4:]).max() <= 0.5e-4 + 1e-12

@@ -649,3 +649,33 @@ def test_hourly_aggregates_match_the_reference_golden_file():
         ok = np.isnan(r) | (np.abs(got[:, 5 + c] - r) <= tol[c] + 1e-9 * np.abs(np.nan_to_num(r)))
         assert ok.all(), (hdr[5 + c], int(np.argmin(ok)), got[~ok, 5 + c][:3], r[~ok][:3])
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", [1, 2])
+def test_device_estm_forcing_disaggregation(method):
+    """DisaggregateESTM on the device: bit-identical to the numpy restatement (itself pinned to the reference's 5-min
+    file), and an ESTM run driven by it equals the run driven by the host-disaggregated block"""
+    import os
+    from suews_b200 import OUT_SUM82, SuewsBatch, estm
+    from suews_b200.forcing import disaggregate_estm, read_estm_ts, read_met
+    d, ep = _estm_case({})
+    ts_h = read_estm_ts(os.path.join(fx.GOLDEN, "estm_ts_2005_60min.txt"))
+    host = disaggregate_estm(ts_h, disagg_method=method)
+    sums = []
+    for dev_path in (True, False):
+        b = SuewsBatch(1, 1)
+        b.load_reference_args(d)
+        for k, v in estm.initial_state(ep, d["sfr"], d["emis"], host[0]).items():
+            b.set_state(k, v)
+        b.upload()
+        b.set_forcing_orig(read_met(os.path.join(fx.GOLDEN, "forcing_2005_60min.txt")))
+        if dev_path:
+            dev = b.set_estm_forcing_orig(ts_h, disagg_method=method)
+            assert np.array_equal(dev, host)
+        else:
+            b.set_estm_forcing(host)
+        b.advance(0, 288, OUT_SUM82)
+        sums.append(b.sums().copy())
+        b.close()
+    assert np.array_equal(sums[0], sums[1])
