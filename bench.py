@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--scheme", default="default")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flux-only", action="store_true", help="skip the side measurement with SUEWS_OUT_FLUX_ONLY")
     ap.add_argument("--sums", default="parity7", choices=["parity7", "all82", "hourly"],
                     help="on-device output reduction: P0 = running sums of the 7 parity fluxes (SURVEY 8d), of all 82 columns, "
                          "or P1 = the hourly-aggregated 87-column SUEWS block of every cell (SUEWS_Output_Agg in the kernel)")
@@ -227,6 +228,26 @@ def main():
     total_cs = float(world) * ncell * 288 * K
     value = total_cs / dev_s
 
+    # ---------------- side measurement (not the headline): the same days with the opt-in SUEWS_OUT_FLUX_ONLY policy, which
+    # skips the roughness-sublayer diagnostics T2/q2/U10/RH2 -- nothing the seven flux sums or the state depend on
+    flux_only = None
+    if a.sums == "parity7" and not a.no_flux_only:
+        from suews_b200 import OUT_FLUX_ONLY
+        ms2 = []
+        for i in range(W, W + K):
+            b.advance(i * 288, 288, OUT | OUT_FLUX_ONLY, sync=False)
+            ms2.append(b.last_ms())
+        barrier()
+        fo_s = sum(ms2) * 1e-3
+        if dist is not None:
+            import torch
+            t = torch.tensor([fo_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fo_s = float(t[0])
+        flux_only = {"value": total_cs / fo_s, "unit": UNIT,
+                     "note": "opt-in SUEWS_OUT_FLUX_ONLY: RSL diagnostics (T2, q2, U10, RH2) skipped; identical flux sums and state; "
+                             "same forcing days re-run from the advanced state; NOT the headline value"}
+
     # ---------------- end-to-end through the host API (host buffers in, host results out)
     e2e_t0 = None
     cols = PARITY_COLS
@@ -305,6 +326,8 @@ def main():
                      "note": "kernel is FP64-pipe / latency bound, not HBM bound (SURVEY 8d); see fp64"},
         "fp64": fp64,
     }
+    if flux_only:
+        line["flux_only"] = flux_only
     if world == 1 and not a.no_cpu_baseline:
         r, cores, cells, slowest, _ = cpu_arm(a.cpu_budget, a.scheme)
         line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",

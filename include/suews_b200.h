@@ -53,6 +53,9 @@ enum {
    SUEWS_OUT_FULL = 2,    /* keep every output block of every step (reference SUEWS_cal_multitsteps semantics) */
    SUEWS_OUT_SUM7 = 4,    /* accumulate only the seven parity fluxes QN, QF, QS, QH, QE, RO, SWE (columns 5-9, 16, 71
                              of the same [ncell][82] sums array; the other columns are left untouched) */
+   SUEWS_OUT_FLUX_ONLY = 16, /* with SUEWS_OUT_SUM7 only: skip the stages whose results the seven flux sums and the state do
+                             not depend on -- the roughness-sublayer diagnostics T2/q2/U10/RH2 (RSLProfile feeds nothing
+                             back, driver.f95:943-949).  Off by default: every launch does the reference's full work. */
    SUEWS_OUT_AGG = 8      /* output policy P1: the SUEWS block aggregated to the output frequency (default hourly) inside
                              the kernel, as SUEWS_Output_Agg does after the run (suews_ctrl_output.f95:912-957: mean /
                              sum / last value per column as varListAll says); exclusive with the running sums */

@@ -242,7 +242,8 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
 __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
                           SuewsCellState &S, double *acc82, double *acc7, const SuLines &L, SuewsEstmState *ES = nullptr,
-                          const double *ts9 = nullptr, unsigned long long last_lo = 0, unsigned long long last_hi = 0)
+                          const double *ts9 = nullptr, unsigned long long last_lo = 0, unsigned long long last_hi = 0,
+                          bool flux_only = false)
 {
    const double *sfr = C.sfr.v;
    const int sm = P.StabilityMethod;
@@ -492,7 +493,9 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    SuRSL rs;
    rs.T2_C = 0; rs.q2_gkg = 0; rs.U10_ms = 0; rs.RH2 = 0;
    double Fc_biogen = 0, Fc_photo = 0, Fc_respi = 0;
-   if (live && dg.fatal == 0) {
+   // flux_only (SUEWS_OUT_FLUX_ONLY, opt-in): T2/q2/U10/RH2 reach no flux sum and no state; the biogenic CO2 families that
+   // read the modelled 2 m temperature (EmissionsMethod >= 11) keep the stage
+   if (live && dg.fatal == 0 && !(flux_only && P.EmissionsMethod < 11 && !L.rsl133 && !L.suews82 && !acc82)) {
       RSLProfile(sm, zH, z0m, zdm, L_mod, sfr, FAI, A.avcp, A.lv_J_kg, A.avdens, avU1, Temp_C, avRh, Press_hPa, C.Z, qh, qe,
                  S.rsl_cache.v, rs, L.rsl133);
       // SUEWS_cal_BiogenCO2 driver.f95:1156-1286: zero for EmissionsMethod 0-6, CO2_biogen for >= 11.  It sees the

@@ -52,6 +52,7 @@ struct SuRunArgs {
    long long ephem_tz_stride;
    double *sums;                // [82][stride] or NULL
    int sum7;                    // 1: accumulate only the seven parity columns (SUEWS_OUT_SUM7)
+   int flux_only;               // 1: SUEWS_OUT_FLUX_ONLY (diagnostics no requested output depends on are skipped)
    int *fatal;                  // [ncell]
    unsigned long long *warn;    // [2][stride]
    long long *iters;            // [ncell]
@@ -270,7 +271,8 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
          // every thread of the block enters the step (phase barriers inside); only live cells compute
          iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
                              (a.agg || (a.sums && !a.sum7)) ? acc : nullptr, (!a.agg && a.sums && a.sum7) ? acc7 : nullptr, L,
-                             a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi);
+                             a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
+                             a.flux_only != 0);
          if (a.agg && (gs + 1) % a.agg_nlines == 0) {   // SUEWS_Output_Agg: rows i-nlinesOut+1 .. i -> row i/nlinesOut
             if (live && dg.fatal == 0) {
                const SuewsStepRec &R = sm_steps[buf][t];
@@ -1039,6 +1041,7 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.ephem_tz_stride = h->nsteps;
    a.sums = (out_flags & (SUEWS_OUT_SUM82 | SUEWS_OUT_SUM7)) ? h->d_sums : nullptr;
    a.sum7 = ((out_flags & SUEWS_OUT_SUM7) && !(out_flags & SUEWS_OUT_SUM82)) ? 1 : 0;
+   a.flux_only = ((out_flags & SUEWS_OUT_FLUX_ONLY) && a.sum7 && !full && !(out_flags & SUEWS_OUT_AGG)) ? 1 : 0;
    a.fatal = h->d_fatal; a.warn = h->d_warn; a.iters = h->d_iters;
    a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3]; a.blkSOL = h->d_blk[4];
    a.blkESTM = h->d_estm ? h->d_blk[5] : nullptr;

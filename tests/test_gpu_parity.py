@@ -339,27 +339,36 @@ def test_annual_flux_sums_match_oracle():
 
 
 def test_replicated_cells_equal_single_cell():
-    """BASELINE configs[1]: the BaseRun cell replicated to 10 000 grids -- the reference's multi-grid == single-grid
-    property (Test/code/Test_SUEWS.py:384), here bit for bit"""
-    from suews_b200 import OUT_SUM82, SuewsBatch
+    """BASELINE configs[1]: the BaseRun cell replicated to 10 000 grids over the whole 2005 leg of the golden run -- the
+    reference's multi-grid == single-grid property (Test/code/Test_SUEWS.py:384), here bit for bit, and every grid ends
+    on the checkpoint the reference wrote after the same 1440 steps"""
+    from suews_b200 import OUT_SUM82, SuewsBatch, checkpoint
     d = fx.state_init(2005)
-    met = fx.forcing(2005)[:288]
+    met = fx.forcing(2005)
     n = 10000
     b = SuewsBatch(n, 1)
     b.load_reference_args(d)
     b.upload()
     b.set_forcing(met)
-    b.advance(0, 288, OUT_SUM82)
+    b.advance(0, met.shape[0], OUT_SUM82)
     sums = b.sums()
     assert np.array_equal(sums, np.broadcast_to(sums[0], sums.shape))
-    st = b.get_state("state_id")
-    assert np.array_equal(st, np.broadcast_to(st[0], st.shape))
+    for nm in ("state_id", "soilstore_id", "SnowPack", "SnowDens", "HDD_id"):
+        st = b.get_state(nm)
+        assert np.array_equal(st, np.broadcast_to(st[0], st.shape)), nm
     b1 = SuewsBatch(1, 1)
     b1.load_reference_args(d)
     b1.upload()
     b1.set_forcing(met)
-    b1.advance(0, 288, OUT_SUM82)
+    b1.advance(0, met.shape[0], OUT_SUM82)
     assert np.array_equal(b1.sums()[0], sums[0])
+    ref_nml = checkpoint.read(fx.GOLDEN + "/ref_InitialConditions_2005_EndofRun.nml")
+    states = {nm: b.get_state(nm) for nm in ("HDD_id", "GDD_id", "LAI_id", "albEveTr_id", "albDecTr_id", "albGrass_id", "DecidCap_id",
+                                             "porosity_id", "soilstore_id", "state_id", "SnowWater", "SnowPack", "SnowFrac",
+                                             "SnowDens", "SnowAlb")}
+    for cell in (0, 4999, 9999):
+        ours = checkpoint.read_text(checkpoint.write_text(checkpoint.state_vector(lambda k: states[k][cell]), snow_use=1))
+        assert max(abs(ours[k] - r) / max(abs(r), 1e-3) for k, r in ref_nml.items()) <= 1e-9
     b.close()
     b1.close()
 
@@ -679,3 +688,26 @@ def test_device_estm_forcing_disaggregation(method):
         sums.append(b.sums().copy())
         b.close()
     assert np.array_equal(sums[0], sums[1])
+
+
+@pytest.mark.gpu
+def test_flux_only_policy_changes_no_flux_and_no_state():
+    """SUEWS_OUT_FLUX_ONLY skips the roughness-sublayer diagnostics: the seven flux sums and the evolving state are
+    bit-identical to the full step's (only the library's own z0_RSL memo differs)"""
+    from suews_b200 import OUT_FLUX_ONLY, OUT_SUM7, SuewsBatch, synth
+    base = fx.state_init(2005)
+    met = fx.forcing(2005)[:576]
+    res = []
+    for flags in (OUT_SUM7, OUT_SUM7 | OUT_FLUX_ONLY):
+        b = SuewsBatch(256, 1)
+        synth.build_batch(b, base, cell0=0, scheme="default")
+        b.upload()
+        b.set_forcing(met)
+        b.advance(0, 576, flags)
+        st = {nm: b.get_state(nm).copy() for nm, kind, _n in __import__("suews_b200.batch", fromlist=["all_fields"]).all_fields()
+              if kind == 3 and nm != "rsl_cache"}
+        res.append((b.sums()[:, list(PARITY_COLS.values())].copy(), st, b.last_ms()))
+        b.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    for nm in res[0][1]:
+        assert np.array_equal(res[0][1][nm], res[1][1][nm]), nm
