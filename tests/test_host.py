@@ -192,3 +192,23 @@ def test_two_rank_sharding_gloo(tmp_path):
     import json
     res = json.loads(line)
     assert res["ok"] and res["tmax"] == 2.0
+
+
+def test_fortran_interface_module_binds_existing_symbols():
+    """include/suews_b200_mod.f90 (ISO_C_BINDING): every BIND(C, name=...) is a symbol of the library, with the argument
+    count of its C prototype"""
+    from suews_b200 import _lib
+    L = C.CDLL(_lib.LIB_PATH)
+    f90 = open(os.path.join(ROOT, "include", "suews_b200_mod.f90")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "suews_b200.h")).read(), flags=re.S)
+    f90 = re.sub(r"&\s*\n\s*", " ", f90)
+    binds = re.findall(r"FUNCTION\s+(\w+)\s*\(([^)]*)\)\s*BIND\(C,\s*name='(\w+)'\)", f90)
+    assert len(binds) >= 25
+    for fname, args, cname in binds:
+        assert fname == cname
+        assert hasattr(L, cname), cname
+        m = re.search(r"\b%s\s*\(([^;]*)\)\s*;" % cname, hdr, flags=re.S)
+        assert m, cname
+        cargs = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+        fargs = [a for a in args.split(",") if a.strip()]
+        assert len(cargs) == len(fargs), (cname, cargs, fargs)
