@@ -16,10 +16,16 @@
 // wrappers, and only leaf helpers are inlined (SU_INL).
 #define SU_INL __device__ __forceinline__
 #define SU_DEVNI __device__ __noinline__
-#ifdef SU_INLINE_ALL
+#if defined(SU_INLINE_ALL) || defined(SU_DEV_INLINE)   // SU_DEV_INLINE: physics routines inlined, libm wrappers still shared
 #define SU_DEV __device__ __forceinline__
 #else
 #define SU_DEV __device__ __noinline__
+#endif
+
+#if defined(SU_HOT_INLINE) || defined(SU_INLINE_ALL)
+#define SU_HOT SU_INL
+#else
+#define SU_HOT SU_DEV
 #endif
 
 #ifndef SU_INLINE_ALL
@@ -30,11 +36,6 @@
 #define SU_EXPLOG_ATTR SU_INL
 #else
 #define SU_EXPLOG_ATTR SU_DEVNI
-#endif
-#ifdef SU_HOT_INLINE
-#define SU_HOT SU_INL
-#else
-#define SU_HOT SU_DEV
 #endif
 #ifdef SU_LIBM_EXPLOG
 SU_EXPLOG_ATTR double su_exp(double x) { return exp(x); }
