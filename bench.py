@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flux-only", action="store_true", help="skip the side measurement with SUEWS_OUT_FLUX_ONLY")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the end-to-end region (default: --steps)")
     ap.add_argument("--sums", default="parity7", choices=["parity7", "all82", "hourly"],
                     help="on-device output reduction: P0 = running sums of the 7 parity fluxes (SURVEY 8d), of all 82 columns, "
                          "or P1 = the hourly-aggregated 87-column SUEWS block of every cell (SUEWS_Output_Agg in the kernel)")
@@ -186,7 +187,7 @@ def main():
     OUT = {"parity7": OUT_SUM7, "all82": OUT_SUM82, "hourly": OUT_AGG}[a.sums]
     n_sum = 7 if a.sums == "parity7" else N_SUM
     use_estm = synth.SCHEMES[a.scheme]["storageheatmethod"] in (4, 14)
-    ndays = 2 * (W + K)
+    ndays = 2 * (W + K)   # device-resident region + end-to-end region (which may use fewer days: --e2e-steps)
     base, met = load_inputs(ndays)
     ncell = a.cells_per_gpu
     b = SuewsBatch(ncell, 1, device=local_rank)
@@ -251,7 +252,8 @@ def main():
     # ---------------- end-to-end through the host API (host buffers in, host results out)
     e2e_t0 = None
     cols = PARITY_COLS
-    for i in range(W + K):
+    Ke = a.e2e_steps if a.e2e_steps > 0 else K
+    for i in range(W + Ke):
         if i == W:
             barrier()
             e2e_t0 = time.perf_counter()
@@ -271,7 +273,7 @@ def main():
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
-    e2e_val = total_cs / e2e_s
+    e2e_val = float(world) * ncell * 288 * Ke / e2e_s
     checksum = float(np.sum(res[:, 0]))
     fatal, warn, iters = b.diag()
 
@@ -316,7 +318,7 @@ def main():
                        "all82": "P0+: per-cell running sums of all 82 SUEWS columns",
                        "hourly": "P1: hourly-aggregated 87-column SUEWS block of every cell, aggregated in the kernel"}[a.sums],
                    "l2": "inputs (state+params %.0f MB/GPU) larger than L2" % (ncell * 8.0 * (N_STATE + N_CELL + N_SUM) / 1e6),
-                   "tsurf_iterations_per_step": float(iters.sum()) / (ncell * 288.0 * (2 * (W + K))), "wall_s_timed": wall,
+                   "tsurf_iterations_per_step": float(iters.sum()) / (ncell * 288.0 * ((W + K) + (K if flux_only else 0) + (W + Ke))), "wall_s_timed": wall,
                    "checksum_QN": checksum, "fatal_cells": int((fatal != 0).sum())},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 288 * 160, "d2h_bytes_per_step": ncell * len(cols) * 8},
         "gpu_launches": K,
