@@ -44,7 +44,7 @@ SU_INL double sat_vap_press_x(SuDiag &dg, double &T, double Press_hPa, int from)
 }
 
 // suews_util_meteo.f95:195-228
-SU_DEV double sat_vap_pressIce(SuDiag &dg, double &T, double Press_hPa, int from)
+SU_COLD double sat_vap_pressIce(SuDiag &dg, double &T, double Press_hPa, int from)
 {
    double es_hPa = 10;
    if (fabs(T) < F(0.001000)) {
@@ -273,7 +273,7 @@ SU_INL double stab_phi_heat(int sm, double zl)
 
 // atmmoiststab.f95:104-248: fixed-point iteration for the Obukhov length (<= 329 trips).
 // log(zzd/z0m) is loop-invariant and evaluated once.
-SU_DEVNI void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double avU1, double Temp_C, double QH_init,
+SU_BIG1 void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double avU1, double Temp_C, double QH_init,
                        double avdens, double avcp, double &L_MOD_out, double &TStar_out, double &UStar_out, double &zL_out)
 {
    // the iteration runs on register copies; the by-reference results (stack slots of the caller) are written once

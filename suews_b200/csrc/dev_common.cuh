@@ -22,6 +22,45 @@
 #define SU_DEV __device__ __noinline__
 #endif
 
+// routines the default scheme set never enters (ESTM, biogenic CO2, ice saturation pressure): out of line in every build,
+// so they take no room in the instruction stream of the hot phases
+#define SU_COLD __device__ __noinline__
+// the large routines that are called once or twice per step (tuning switch SU_BIG_INLINE)
+#if defined(SU_BIG_INLINE) || defined(SU_INLINE_ALL)
+#define SU_BIG __device__ __forceinline__
+#else
+#define SU_BIG __device__ __noinline__
+#endif
+// per-routine switch: SU_BIG_MASK bit k-1 inlines group k (1 cal_Stab, 2 cal_HorizontalSoilWater, 3 NARP + sun position,
+// 4 RSLProfile, 5 cal_psim_hat_zh)
+#ifndef SU_BIG_MASK
+#define SU_BIG_MASK 0
+#endif
+#if (SU_BIG_MASK & 1)
+#define SU_BIG1 __device__ __forceinline__
+#else
+#define SU_BIG1 SU_BIG
+#endif
+#if (SU_BIG_MASK & 2)
+#define SU_BIG2 __device__ __forceinline__
+#else
+#define SU_BIG2 SU_BIG
+#endif
+#if (SU_BIG_MASK & 4)
+#define SU_BIG3 __device__ __forceinline__
+#else
+#define SU_BIG3 SU_BIG
+#endif
+#if (SU_BIG_MASK & 8)
+#define SU_BIG4 __device__ __forceinline__
+#else
+#define SU_BIG4 SU_BIG
+#endif
+#if (SU_BIG_MASK & 16)
+#define SU_BIG5 __device__ __forceinline__
+#else
+#define SU_BIG5 SU_BIG
+#endif
 #if defined(SU_HOT_INLINE) || defined(SU_INLINE_ALL)
 #define SU_HOT SU_INL
 #else

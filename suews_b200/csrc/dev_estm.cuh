@@ -86,7 +86,7 @@ SU_DEV double heatcond1d(double *T, const double *dx, double dt, const double *k
 }
 
 // estm.f95:970-1605.  Ts: Ts5mindata_ir(5:13).  o: dataOutLineESTM (27) or nullptr.  Returns QS.
-SU_DEV double ESTM(const SuewsClassParams &P, const SuewsCellParams &C, SuewsEstmState &E, double avu1, double temp_c,
+SU_COLD double ESTM(const SuewsClassParams &P, const SuewsCellParams &C, SuewsEstmState &E, double avu1, double temp_c,
                    double avrh, double press_hpa, const double *Ts, double Tair_av, double *o)
 {
    const double *sfr = C.sfr.v;

@@ -177,7 +177,7 @@ __device__ void spa_time_part(double year, double idectime, double UTC, SuewsEph
 }
 
 // NARP_cal_SunPosition steps 11-14, narp.f95:1086-1217.  COS(altitude*pi/180) in x is the reference's.
-SU_DEVNI void spa_location_part(const SuewsEphem &e, double lat, double lng, double alt, double &sunazimuth,
+SU_BIG3 void spa_location_part(const SuewsEphem &e, double lat, double lng, double alt, double &sunazimuth,
                                 double &sunzenith)
 {
    double obs_hour = set_to_range(e.app_stime + lng - e.sun_ra);
@@ -243,7 +243,7 @@ struct SuRad {
 
 // narp.f95:105-457.  ea_hPa is what SUEWS_cal_Qn hands to NARP's Press_hPa slot (driver.f95:1437).
 // PRATA_EMIS / WC_fraction do not depend on the surface and are evaluated once, not 7 times.
-SU_DEVNI void NARP(const double *sfr, const double *SnowFrac, const double *alb, const double *emis,
+SU_BIG3 void NARP(const double *sfr, const double *SnowFrac, const double *alb, const double *emis,
                    const double *IceFrac, double NARP_EMIS_SNOW, double ZENITH_deg, double tsurf_0, double kdown,
                    double Temp_C, double RH, double ea_hPa, double qn1_obs, double SnowAlb, int AlbedoChoice,
                    int ldown_option, int nrm_use, SuRad &r)

@@ -35,7 +35,7 @@ SU_DEV void cal_ch(int sm, double zh, double zd, double beta, double L_MOD, doub
 }
 
 // cal_psim_hat(z = zh), rslprof.f95:366-424, as a loop.
-SU_DEVNI double cal_psim_hat_zh(int sm, double zh, double L_MOD, double beta, double Lc)
+SU_BIG5 double cal_psim_hat_zh(int sm, double zh, double L_MOD, double beta, double Lc)
 {
    const double dzh = F(0.1) / F(2.);
    const double zd = cal_zd_RSL(zh, beta, Lc);
@@ -160,7 +160,7 @@ SU_INL void bracket_grid(double z_x, const SuRslGrid &g, int &idx_low, int &idx_
 }
 
 // RSLProfile, rslprof.f95:13-313.  line133 may be NULL when the 133-column profile is not wanted.
-SU_DEVNI void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD, const double *sfr, double FAI,
+SU_BIG4 void RSLProfile(int sm, double Zh, double z0m, double zdm, double L_MOD, const double *sfr, double FAI,
                          double avcp, double lv_J_kg, double avdens, double avU1, double Temp_C, double avRH,
                          double Press_hPa, double zMeas, double qh, double qe, double *cache10, SuRSL &o, double *line133)
 {

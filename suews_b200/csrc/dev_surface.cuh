@@ -201,7 +201,7 @@ SU_INL void evap_surface(SuEvapTrip &e, double state_is, double WetThresh_is, do
 // Photosynthesis by the four model families selected by the decade of EmissionsMethod (11-16 rectangular
 // hyperbola, 21-26 non-rectangular hyperbola, 31-36 bulk non-rectangular, 41-46 conductance based) and
 // temperature-driven respiration.  Returns Fc_biogen; Fc_photo / Fc_respi through the references.
-SU_DEV double CO2_biogen(const SuewsClassParams &P, const double *sfr, const double *SnowFrac, const double *LAI_id,
+SU_COLD double CO2_biogen(const SuewsClassParams &P, const double *sfr, const double *SnowFrac, const double *LAI_id,
                          double avkdn, double gfunc, double gfunc2, double t2, double Temp_C, double &Fc_photo,
                          double &Fc_respi)
 {
@@ -496,7 +496,7 @@ SU_HOT void vg_store(double soilstore, double SoilStoreCap, double SoilDepth, do
 
 // waterdist.f95:622-855: horizontal flow between the 15 pairs of soil stores.  sqrt(sfr*SurfaceArea) is a
 // per-cell constant, evaluated per pair by the reference and once per surface here.
-SU_DEVNI void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *sfr, double SurfaceArea,
+SU_BIG2 void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *sfr, double SurfaceArea,
                                       double NonWaterFraction, double tstep_real, double *soilstore_id,
                                       double *runoffSoil, double &runoffSoil_per_tstep)
 {
