@@ -29,6 +29,13 @@
 #include "dev_solweig.cuh"
 #include "dev_estm.cuh"
 
+// the three per-surface loops of the step are kept rolled (code size); SU_UNROLL_SURF lets the compiler unroll them
+#ifdef SU_UNROLL_SURF
+#define SU_UNROLL1
+#else
+#define SU_UNROLL1 _Pragma("unroll 1")
+#endif
+
 #ifdef SU_PHASE_SYNC
 #define SU_SYNC() __syncthreads()
 #define SU_SYNC_OR(p) __syncthreads_or(p)
@@ -129,7 +136,7 @@ SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, const SuewsCel
    // SUEWS_cal_Water driver.f95:1614-1694 (StoreDrainPrm_next differs from _prev in (6,Decid) only)
    if (NonWaterFraction != 0) {
       double s = 0;
-#pragma unroll 1
+SU_UNROLL1
       for (int is = 0; is < NSURF - 1; is++) {
          double cap = (is == DECID) ? H.d.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
          H.drain[is] = drainage(dg, S.state_id[is], cap, SU_SDP(S.StoreDrainPrm.v, 1, is), SU_SDP(S.StoreDrainPrm.v, 2, is),
@@ -181,7 +188,7 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPa
    evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
    T.ev_per_tstep = 0; T.surf_chang_per_tstep = 0; T.runoff_per_tstep = 0; T.state_per_tstep = 0; T.NWstate_per_tstep = 0;
    T.chSnow_per_interval = 0;
-#pragma unroll 1
+SU_UNROLL1
    for (int is = 0; is < NSURF; is++) {
       const double cap = (is == DECID) ? H.d.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
       if (P.snowUse == 1 && Hs.snowCalcSwitch[is] == 1) {
@@ -227,7 +234,7 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
    double qe = 0, ev = 0, qe_surf = 0;
    SuEvapTrip et;
    evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
-#pragma unroll 1
+SU_UNROLL1
    for (int is = 0; is < NSURF; is++) {
       const double cap = (is == DECID) ? H.d.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
       evap_surface<false>(et, S.state_id[is], P.WetThresh[is], cap, ev, qe_surf);
