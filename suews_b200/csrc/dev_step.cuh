@@ -80,7 +80,6 @@ struct SuLines {
 // Tsurf-independent quantities of a step
 struct SuHoist {
    double Tair_av_next;
-   SuDaily d;
    double wu_nsurf[NSURF], wu_int, wu_ext;
    SuAnthro an;
    double SoilMoistCap, vsmd, smd0;
@@ -104,41 +103,38 @@ SU_INL double cal_tair_av(double tair_av_prev, int dt_since_start, int tstep, do
 }
 
 // The stages ahead of cal_AtmMoist (driver.f95:670-716): 24 h mean air temperature and DailyState.
+// D is the cell's daily state, resident across the steps of a launch: it enters holding the values committed by the
+// previous step and leaves holding this step's *_next values (cal_DailyState works in place).  Within a day only the
+// running sums HDD_id(1:6), Tmin, Tmax and the day length move; everything else is rewritten on the last step of the
+// day (dailystate.f95:355-493), so nothing has to be copied from step to step.
 SU_DEV void stage_pre_atm(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, const SuewsStepRec &R,
                           const SuewsCellState &S, int dt_since_start, int tstep_prev, double nsh_real, double Temp_C,
-                          SuHoist &H)
+                          SuHoist &H, SuDaily &D)
 {
    H.Tair_av_next = cal_tair_av(S.Tair_av, dt_since_start, P.tstep, Temp_C);
-   for (int i = 0; i < 12; i++) H.d.HDD_id[i] = S.HDD_id[i];
-   for (int i = 0; i < 3; i++) { H.d.GDD_id[i] = S.GDD_id[i]; H.d.SDD_id[i] = S.SDD_id[i]; H.d.LAI_id[i] = S.LAI_id[i]; }
-   for (int i = 0; i < 9; i++) H.d.WUDay_id[i] = S.WUDay_id[i];
-   H.d.Tmin_id = S.Tmin_id; H.d.Tmax_id = S.Tmax_id; H.d.lenDay_id = S.lenDay_id;
-   H.d.DecidCap_id = S.DecidCap_id; H.d.albDecTr_id = S.albDecTr_id; H.d.albEveTr_id = S.albEveTr_id;
-   H.d.albGrass_id = S.albGrass_id; H.d.porosity_id = S.porosity_id;
-   H.d.DecidStoreCap = SU_SDP(S.StoreDrainPrm.v, 5, DECID);
-   H.d.deltaLAI = 0;
+   D.deltaLAI = 0;
    cal_DailyState(dg, P, C.lat, R.id, R.it, R.imin, 0, R.dow, tstep_prev, dt_since_start, nsh_real, R.avkdn, Temp_C,
-                  R.Precip, R.LAI_obs, S.state_id.v, S.soilstore_id.v, H.d);
+                  R.Precip, R.LAI_obs, S.state_id.v, S.soilstore_id.v, D);
 }
 
 // Tsurf-independent stages that follow cal_AtmMoist (driver.f95:727-755, :827-834 and SurfaceResistance of :838)
 SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, const SuewsStepRec &R,
                            const SuewsCellState &S, const SuAtm &A, int DLS, int nsh, double nsh_real, double Temp_C,
-                           double NonWaterFraction, const double *SnowFrac_res, SuHoist &H)
+                           double NonWaterFraction, const double *SnowFrac_res, SuHoist &H, const SuDaily &D)
 {
    const double *sfr = C.sfr.v;
    double SoilState;
    update_SoilMoist(NonWaterFraction, P.SoilStoreCap.v, sfr, S.soilstore_id.v, H.SoilMoistCap, SoilState, H.vsmd, H.smd0);
-   cal_WaterUse(P, C, nsh_real, R.wu_m3, R.dow, H.d.HDD_id, H.d.WUDay_id, nsh, R.it, R.imin, DLS, H.wu_nsurf, H.wu_int,
+   cal_WaterUse(P, C, nsh_real, R.wu_m3, R.dow, D.HDD_id, D.WUDay_id, nsh, R.it, R.imin, DLS, H.wu_nsurf, H.wu_int,
                 H.wu_ext);
-   cal_AnthropogenicEmission(dg, P, C, R.dow, DLS, H.d.HDD_id, R.it, R.imin, R.qf_obs, Temp_C, H.an);
+   cal_AnthropogenicEmission(dg, P, C, R.dow, DLS, D.HDD_id, R.it, R.imin, R.qf_obs, Temp_C, H.an);
    H.SnowAlb_q = update_snow_albedo(P.tstep, S.SnowPack.v, S.SnowAlb, Temp_C, P.tau_a, P.tau_f, P.SnowAlbMax, P.SnowAlbMin);
    // SUEWS_cal_Water driver.f95:1614-1694 (StoreDrainPrm_next differs from _prev in (6,Decid) only)
    if (NonWaterFraction != 0) {
       double s = 0;
 SU_UNROLL1
       for (int is = 0; is < NSURF - 1; is++) {
-         double cap = (is == DECID) ? H.d.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
+         double cap = (is == DECID) ? D.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
          H.drain[is] = drainage(dg, S.state_id[is], cap, SU_SDP(S.StoreDrainPrm.v, 1, is), SU_SDP(S.StoreDrainPrm.v, 2, is),
                                 SU_SDP(S.StoreDrainPrm.v, 3, is), nsh_real);
          s += H.drain[is] * sfr[is];
@@ -150,7 +146,7 @@ SU_UNROLL1
    }
    H.drain[WATER] = 0;
    ReDistributeWater(P.snowUse, P.WaterDist.v, sfr, H.drain, H.AddWaterRunoff, H.AddWater);
-   SurfaceResistance(dg, P, sfr, SnowFrac_res, R.avkdn, Temp_C, A.dq, R.xsmd, H.vsmd, H.d.LAI_id, H.gfunc, H.gsc, H.ResistSurf);
+   SurfaceResistance(dg, P, sfr, SnowFrac_res, R.avkdn, Temp_C, A.dq, R.xsmd, H.vsmd, D.LAI_id, H.gfunc, H.gsc, H.ResistSurf);
 }
 
 // SUEWS_cal_QE driver.f95:1744-2082: per-surface evaporation + surface/soil/snow state update.
@@ -159,7 +155,7 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPa
                         const double *Tsurf_ind, const double *SnowPack_m, const double *SnowFrac_q,
                         const double *SnowDens_m, double Temp_C, double avRh, double RA, double RAsnow, double rb,
                         double qn_e, double PervFraction, double VegFraction, double NonWaterFraction, bool snow_arrays,
-                        SuQEWork &W, SuQETot &T)
+                        SuQEWork &W, SuQETot &T, const SuDaily &D)
 {
    const double *sfr = C.sfr.v;
    for (int is = 0; is < NSURF; is++) {
@@ -190,7 +186,7 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPa
    T.chSnow_per_interval = 0;
 SU_UNROLL1
    for (int is = 0; is < NSURF; is++) {
-      const double cap = (is == DECID) ? H.d.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
+      const double cap = (is == DECID) ? D.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
       if (P.snowUse == 1 && Hs.snowCalcSwitch[is] == 1) {
          if (sfr[is] != 0) {
             double chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot;
@@ -228,7 +224,7 @@ SU_UNROLL1
 
 // QE of a trip when no surface takes the snow branch: the sum the full routine forms, without the state update
 SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, const SuewsCellState &S, const SuAtm &A,
-                           const SuLumps &Lm, const SuHoist &H, double RA, double rb, double qn_e)
+                           const SuLumps &Lm, const SuHoist &H, double RA, double rb, double qn_e, const SuDaily &D)
 {
    const double tlv = A.lv_J_kg / (P.tstep * 1.0);
    double qe = 0, ev = 0, qe_surf = 0;
@@ -236,7 +232,7 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
    evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
 SU_UNROLL1
    for (int is = 0; is < NSURF; is++) {
-      const double cap = (is == DECID) ? H.d.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
+      const double cap = (is == DECID) ? D.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
       evap_surface<false>(et, S.state_id[is], P.WetThresh[is], cap, ev, qe_surf);
       qe = qe + qe_surf * C.sfr[is];
    }
@@ -248,7 +244,7 @@ SU_UNROLL1
 // Returns the number of Tsurf iterations used.
 __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
-                          SuewsCellState &S, double *acc82, double *acc7, const SuLines &L, SuewsEstmState *ES = nullptr,
+                          SuewsCellState &S, SuDaily &D, double *acc82, double *acc7, const SuLines &L, SuewsEstmState *ES = nullptr,
                           const double *ts9 = nullptr, unsigned long long last_lo = 0, unsigned long long last_hi = 0,
                           bool flux_only = false)
 {
@@ -278,6 +274,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    double SnowfallCum_next = S.SnowfallCum, SnowAlb_next = S.SnowAlb;
    double alb_next[NSURF];
    SuHoist H;
+   SuDaily D_prev;   // only filled when Temp_C is about to be rewritten (rare)
    SuAtm A;
    SuRad Rd;
    SuSnowHeat Hs;
@@ -305,7 +302,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
    // ================= phase P0: geometry, sun, daily state =================
    if (live) {
       for (int is = 0; is < NSURF; is++) { deltaQi[is] = 0; smd_nsurf[is] = 0; SnowWater_in[is] = S.SnowWater[is]; }
-      cal_RoughnessParameters(dg, P.RoughLenMomMethod, C, S.porosity_id, FAI, zH, z0m, zdm, ZZD);
+      cal_RoughnessParameters(dg, P.RoughLenMomMethod, C, D.porosity_id, FAI, zH, z0m, zdm, ZZD);
       spa_location_part(E, C.lat, C.lng, C.alt, azimuth, zenith_deg);
       RadMethod(dg, P.NetRadiationMethod, snowUse, nrm_use, AlbedoChoice, ldown_option);
       // Tsurf enters NARP only through the iteration-based methods (narp.f95:337-346); ESTM advances its element
@@ -314,7 +311,10 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       // snow fraction seen by SurfaceResistance = SnowFrac_next after Snow_cal_MeltHeat (driver.f95:848)
       for (int is = 0; is < NSURF; is++)
          SnowFrac_res[is] = (snowUse == 1) ? ((nrm_use > 0) ? S.SnowFrac[is] : R.snowFrac_obs) : 0.0;
-      stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H);
+      // the reference runs the stages ahead of cal_AtmMoist again on trips >= 2 when sat_vap_press_x rewrites Temp_C
+      // (|Temp_C| < 0.001, see phase L1): only then is a copy of the daily state kept to restart from
+      if (temp_will_rewrite) D_prev = D;
+      stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
    }
    SU_SYNCN(0);
    SU_CLK(0);
@@ -324,7 +324,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       cal_AtmMoist(dg, Temp_C, Press_hPa, avRh, lv_sw, A);   // may rewrite Temp_C
       lv_memo[sw_in] = A.lv_J_kg;
       lv_exit[sw_in] = lv_sw;
-      stage_post_atm(dg, P, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H);
+      stage_post_atm(dg, P, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
       qf = H.an.qf;
    }
 
@@ -343,8 +343,9 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       if (run) {
          if (i_iter > 1) {
             if (i_iter == 2 && temp_will_rewrite) {   // trips >= 2 run the early stages with the rewritten Temp_C
-               stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H);
-               stage_post_atm(dg, P, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H);
+               D = D_prev;
+               stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
+               stage_post_atm(dg, P, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
                qf = H.an.qf;
                rad_done = false;
             }
@@ -366,9 +367,9 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
                   for (int is = 0; is < NSURF; is++) SnowFrac_q[is] = 0;
                Rd.ldown = (ldown_option == 1) ? R.ldown_obs : -9.0;
                if (ldown_option == 2) Rd.fcld = R.fcld_obs;
-               alb_next[DECID] = H.d.albDecTr_id;
-               alb_next[CONIF] = H.d.albEveTr_id;
-               alb_next[GRASS] = H.d.albGrass_id;
+               alb_next[DECID] = D.albDecTr_id;
+               alb_next[CONIF] = D.albEveTr_id;
+               alb_next[GRASS] = D.albGrass_id;
                NARP(sfr, SnowFrac_q, alb_next, P.emis.v, S.IceFrac.v, P.NARP_EMIS_SNOW, zenith_deg, Ts_iter, avkdn, Temp_C,
                     avRh, A.Ea_hPa, R.qn1_obs, H.SnowAlb_q, AlbedoChoice, ldown_option, nrm_use, Rd);
                qn1 = Rd.qn1; qn1_snowfree = Rd.qn1_snowfree; qn1_S = Rd.qn1_S;
@@ -384,7 +385,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
                qs = R.qs_obs;
             } else if (P.StorageHeatMethod == 1) {
                OHM(dg, P, sfr, qn1_use, S.qn1_av, S.dqndt, qn1_av_next, dqndt_next, qn1_S, S.qn1_s_av, S.dqnsdt, qn1_s_av_next,
-                   dqnsdt_next, dt_since_start, H.d.HDD_id[9], S.soilstore_id.v, S.state_id.v, SnowFrac_q, a1, a2, a3, qs,
+                   dqnsdt_next, dt_since_start, D.HDD_id[9], S.soilstore_id.v, S.state_id.v, SnowFrac_q, a1, a2, a3, qs,
                    deltaQi);
             } else if (use_estm) {
                // ESTM (driver.f95:1598-1606): parameters and element temperatures live in MODULE ESTM_data in the
@@ -419,7 +420,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
          }
          rad_done = true;
          if (i_iter == 1)   // LUMPS first guess (driver.f95:809-824)
-            LUMPS_cal_QHQE(dg, P, sfr, qn1, qf, qs, Hs.Qm, Temp_C, Hs.veg_fr, A.avcp, Press_hPa, A.lv_J_kg, H.d.LAI_id, Lm);
+            LUMPS_cal_QHQE(dg, P, sfr, qn1, qf, qs, Hs.Qm, Temp_C, Hs.veg_fr, A.avcp, Press_hPa, A.lv_J_kg, D.LAI_id, Lm);
       }
       SU_SYNCN(1);
       SU_CLK(2);
@@ -443,11 +444,11 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
             for (int is = 0; is < NSURF; is++) snow_branch = snow_branch || (Hs.snowCalcSwitch[is] == 1);
          if (snow_branch) {
             cal_QE_full(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow,
-                        rb, qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT);
+                        rb, qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
             qe = QT.qe;
             qe_full_done = true;
          } else {
-            qe = cal_QE_light(P, C, S, A, Lm, H, RA, rb, qn_e);
+            qe = cal_QE_light(P, C, S, A, Lm, H, RA, rb, qn_e, D);
             qe_full_done = false;
          }
          // SUEWS_cal_QH driver.f95:2084-2131 (QHMethod = 1) and cal_tsfc :3558
@@ -484,7 +485,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       if (!qe_full_done) {
          const double qn_e = qn1_snowfree + qf - qs;
          cal_QE_full(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow, rb,
-                     qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT);
+                     qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
       }
       qh_resist = (RA != 0) ? A.avdens * A.avcp * (Rd.tsurf - Temp_C) / RA : -999.0;
       double soilstoreOld[NSURF];
@@ -515,12 +516,12 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
             SuAtm A2;
             cal_AtmMoist(dg, t2, Press_hPa, avRh, lv_sw, A2);
             double gsc2, rs2;
-            SurfaceResistance(dg, P, sfr, S.SnowFrac.v, avkdn, t2, A2.dq, R.xsmd, H.vsmd, H.d.LAI_id, gfunc2, gsc2, rs2);
+            SurfaceResistance(dg, P, sfr, S.SnowFrac.v, avkdn, t2, A2.dq, R.xsmd, H.vsmd, D.LAI_id, gfunc2, gsc2, rs2);
          }
          // SUEWS_cal_Main's own `gfunc` (driver.f95:374) is never assigned -- SUEWS_cal_Resistance keeps its gfunc
          // to itself (driver.f95:2199) -- so the conductance-based family with gsModel 1/2 multiplies by an
          // uninitialised local there; like the oracle, this takes it as 0
-         Fc_biogen = CO2_biogen(P, sfr, S.SnowFrac.v, H.d.LAI_id, avkdn, 0.0, gfunc2, t2, Temp_C, Fc_photo, Fc_respi);
+         Fc_biogen = CO2_biogen(P, sfr, S.SnowFrac.v, D.LAI_id, avkdn, 0.0, gfunc2, t2, Temp_C, Fc_photo, Fc_respi);
       }
    }
    SU_SYNCN(5);
@@ -541,19 +542,10 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       S.soilstore_id[is] = W.soilstore_id[is];
       S.state_id[is] = W.state_id[is]; S.alb[is] = alb_next[is];
    }
-   // Daily state: within a day only the running degree-day sums HDD_id(1:6), Tmin, Tmax and the day length move
-   // (update_DailyState_Day, dailystate.f95:496-575); everything else is rewritten by update_DailyState_End
-   // on the last step of the day only (dailystate.f95:355-493)
-   S.Tair_av = H.Tair_av_next; S.Tmin_id = H.d.Tmin_id; S.Tmax_id = H.d.Tmax_id; S.lenDay_id = H.d.lenDay_id;
-   for (int i = 0; i < 6; i++) S.HDD_id[i] = H.d.HDD_id[i];
-   if ((R.it * 3600 + R.imin * 60 + P.tstep) >= 86400) {
-      for (int i = 6; i < 12; i++) S.HDD_id[i] = H.d.HDD_id[i];
-      for (int i = 0; i < 3; i++) { S.GDD_id[i] = H.d.GDD_id[i]; S.SDD_id[i] = H.d.SDD_id[i]; S.LAI_id[i] = H.d.LAI_id[i]; }
-      S.DecidCap_id = H.d.DecidCap_id; S.albDecTr_id = H.d.albDecTr_id; S.albEveTr_id = H.d.albEveTr_id;
-      S.albGrass_id = H.d.albGrass_id; S.porosity_id = H.d.porosity_id;
-      SU_SDP(S.StoreDrainPrm.v, 5, DECID) = H.d.DecidStoreCap;
-      for (int i = 0; i < 9; i++) S.WUDay_id[i] = H.d.WUDay_id[i];
-   }
+   // Daily state: D already holds this step's values (stage_pre_atm); on the last step of the day the one element of
+   // StoreDrainPrm that evolves follows (dailystate.f95:671)
+   S.Tair_av = H.Tair_av_next;
+   if ((R.it * 3600 + R.imin * 60 + P.tstep) >= 86400) SU_SDP(S.StoreDrainPrm.v, 5, DECID) = D.DecidStoreCap;
    S.lv_switch = (double)lv_sw;
    S.alb1_hidden = Rd.alb1;
 
@@ -575,7 +567,7 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       k++;                                         \
    } while (0)
       const bool rad = nrm_use > 0;
-      const double LAI_wt = S.LAI_id[0] * sfr[2] + S.LAI_id[1] * sfr[3] + S.LAI_id[2] * sfr[4];
+      const double LAI_wt = D.LAI_id[0] * sfr[2] + D.LAI_id[1] * sfr[3] + D.LAI_id[2] * sfr[4];
       double bulkalbedo = 0;
       for (int is = 0; is < NSURF; is++) bulkalbedo += S.alb[is] * sfr[is];
       SU_OUT(avkdn); SU_OUT(rad ? Rd.kup : -999.0); SU_OUT(rad ? Rd.ldown : -999.0); SU_OUT(rad ? Rd.lup : -999.0);
@@ -639,14 +631,14 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       for (int i = 0; i < SUEWS_NCOL_DAILY; i++) o[i] = -999;
       if (R.it == 23 && R.imin == (nsh_real - 1) / nsh_real * 60) {
          int k = 0;
-         for (int i = 0; i < 6; i++) o[k++] = S.HDD_id[i];
-         for (int i = 0; i < 3; i++) o[k++] = S.GDD_id[i];
-         for (int i = 0; i < 3; i++) o[k++] = S.SDD_id[i];
-         o[k++] = S.Tmin_id; o[k++] = S.Tmax_id; o[k++] = S.lenDay_id;
-         for (int i = 0; i < 3; i++) o[k++] = S.LAI_id[i];
-         o[k++] = S.DecidCap_id; o[k++] = S.porosity_id; o[k++] = S.albEveTr_id; o[k++] = S.albDecTr_id; o[k++] = S.albGrass_id;
-         for (int i = 0; i < 9; i++) o[k++] = S.WUDay_id[i];
-         o[k++] = H.d.deltaLAI; o[k++] = Lm.VegPhenLumps; o[k++] = S.SnowAlb;
+         for (int i = 0; i < 6; i++) o[k++] = D.HDD_id[i];
+         for (int i = 0; i < 3; i++) o[k++] = D.GDD_id[i];
+         for (int i = 0; i < 3; i++) o[k++] = D.SDD_id[i];
+         o[k++] = D.Tmin_id; o[k++] = D.Tmax_id; o[k++] = D.lenDay_id;
+         for (int i = 0; i < 3; i++) o[k++] = D.LAI_id[i];
+         o[k++] = D.DecidCap_id; o[k++] = D.porosity_id; o[k++] = D.albEveTr_id; o[k++] = D.albDecTr_id; o[k++] = D.albGrass_id;
+         for (int i = 0; i < 9; i++) o[k++] = D.WUDay_id[i];
+         o[k++] = D.deltaLAI; o[k++] = Lm.VegPhenLumps; o[k++] = S.SnowAlb;
          for (int is = 0; is < NSURF; is++) o[k++] = S.SnowDens[is];
          o[k++] = a1; o[k++] = a2; o[k++] = a3;
       }

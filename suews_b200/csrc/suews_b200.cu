@@ -242,6 +242,15 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
    if (a.agg)
       for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
          if (su_agg82[c] == 2) { if (c < 64) last_lo |= 1ull << c; else last_hi |= 1ull << (c - 64); }
+   // the daily state lives in its own record for the length of the launch (dev_step.cuh, stage_pre_atm)
+   SuDaily D;
+   for (int i = 0; i < 12; i++) D.HDD_id[i] = S.HDD_id[i];
+   for (int i = 0; i < 3; i++) { D.GDD_id[i] = S.GDD_id[i]; D.SDD_id[i] = S.SDD_id[i]; D.LAI_id[i] = S.LAI_id[i]; }
+   for (int i = 0; i < 9; i++) D.WUDay_id[i] = S.WUDay_id[i];
+   D.Tmin_id = S.Tmin_id; D.Tmax_id = S.Tmax_id; D.lenDay_id = S.lenDay_id; D.DecidCap_id = S.DecidCap_id;
+   D.albDecTr_id = S.albDecTr_id; D.albEveTr_id = S.albEveTr_id; D.albGrass_id = S.albGrass_id; D.porosity_id = S.porosity_id;
+   D.DecidStoreCap = SU_SDP(S.StoreDrainPrm.v, 5, DECID);
+   D.deltaLAI = 0;
    const SuewsClassParams &P = a.classes[cls];
    const SuewsEphem *eph = a.ephem + (size_t)tz * a.ephem_tz_stride;
    int dt_since_start = a.dt_since_start;
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
          double l_es[SUEWS_NCOL_ESTM];
          if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; L.estm27 = l_es; }
          // every thread of the block enters the step (phase barriers inside); only live cells compute
-         iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S,
+         iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S, D,
                              (a.agg || (a.sums && !a.sum7)) ? acc : nullptr, (!a.agg && a.sums && a.sum7) ? acc7 : nullptr, L,
                              a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
                              a.flux_only != 0);
@@ -320,6 +329,11 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
    }
 
    if (active) {
+      for (int i = 0; i < 12; i++) S.HDD_id[i] = D.HDD_id[i];
+      for (int i = 0; i < 3; i++) { S.GDD_id[i] = D.GDD_id[i]; S.SDD_id[i] = D.SDD_id[i]; S.LAI_id[i] = D.LAI_id[i]; }
+      for (int i = 0; i < 9; i++) S.WUDay_id[i] = D.WUDay_id[i];
+      S.Tmin_id = D.Tmin_id; S.Tmax_id = D.Tmax_id; S.lenDay_id = D.lenDay_id; S.DecidCap_id = D.DecidCap_id;
+      S.albDecTr_id = D.albDecTr_id; S.albEveTr_id = D.albEveTr_id; S.albGrass_id = D.albGrass_id; S.porosity_id = D.porosity_id;
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
       for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + cell] = sp[j];
