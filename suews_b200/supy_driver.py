@@ -119,6 +119,37 @@ class _SuewsDriver:
             raise SuewsError(rc, msg)
         return az.value, zen.value
 
+    # ---- the small pure functions f2py also exposes on suews_driver (scalar arithmetic, host side)
+    @staticmethod
+    def set_nan(x):
+        """set_nan (driver.f95:2737): values beyond +-30000 become -999."""
+        a = np.asarray(x, dtype=np.float64)
+        r = np.where(np.abs(a) > 30000.0, -999.0, a)
+        return float(r) if r.ndim == 0 else r
+
+    @staticmethod
+    def square(x):
+        """square (driver.f95:2753): the f2py conversion test function."""
+        return float(x) * float(x)
+
+    @staticmethod
+    def square_real(x):
+        """square_real (driver.f95:2765): the REAL(4) twin of square."""
+        return float(np.float32(x) * np.float32(x))
+
+    @staticmethod
+    def cal_tair_av(tair_av_prev, dt_since_start, tstep, temp_c):
+        """cal_tair_av (driver.f95:3530): running 24 h mean air temperature [K]; 273.15 and tstep*1. are REAL(4)."""
+        len_day_s = 24.0 * 3600.0
+        len_cal_s = len_day_s if dt_since_start > len_day_s else float(int(dt_since_start) + int(tstep))
+        temp_k = float(temp_c) + float(np.float32(273.15))
+        return float(tair_av_prev) * (len_cal_s - float(np.float32(tstep) * np.float32(1.0))) / len_cal_s + temp_k * int(tstep) / len_cal_s
+
+    @staticmethod
+    def cal_tsfc(qh, avdens, avcp, ra, temp_c):
+        """cal_tsfc (driver.f95:3558): surface temperature from the sensible heat flux [degC]."""
+        return float(qh) / (float(avdens) * float(avcp)) * float(ra) + float(temp_c)
+
     def reset_hidden_state(self):
         """A fresh reference process starts with the SAVE'd Lat_vap switches and NARP alb1 cleared (and an empty
         MODULE ESTM_data)."""

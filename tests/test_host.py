@@ -212,3 +212,17 @@ def test_fortran_interface_module_binds_existing_symbols():
         cargs = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
         fargs = [a for a in args.split(",") if a.strip()]
         assert len(cargs) == len(fargs), (cname, cargs, fargs)
+
+
+def test_small_driver_functions_like_f2py_exposes_them():
+    """set_nan / square / square_real / cal_tair_av / cal_tsfc of suews_driver (driver.f95:2737-2776, :3530-3571)"""
+    import oracle_lib as ol
+    from suews_b200.supy_driver import suews_driver as sd
+    assert sd.set_nan(30000.5) == -999.0 and sd.set_nan(-29999.0) == -29999.0
+    assert sd.square(3.0) == 9.0 and sd.square_real(1.1) == float(np.float32(1.1) * np.float32(1.1))
+    assert sd.cal_tsfc(120.0, 1.2, 1005.0, 35.0, 11.5) == 120.0 / (1.2 * 1005.0) * 35.0 + 11.5
+    L = ol.lib()
+    L.so_cal_tair_av.restype = C.c_double
+    L.so_cal_tair_av.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double]
+    for dt in (0, 300, 86100, 86400, 86700, 31622400):
+        assert sd.cal_tair_av(279.3, dt, 300, 4.25) == L.so_cal_tair_av(279.3, dt, 300, 4.25), dt
