@@ -711,3 +711,56 @@ def test_flux_only_policy_changes_no_flux_and_no_state():
     assert np.array_equal(res[0][0], res[1][0])
     for nm in res[0][1]:
         assert np.array_equal(res[0][1][nm], res[1][1][nm]), nm
+
+
+@pytest.mark.gpu
+def test_mixed_scheme_classes_in_one_batch():
+    """Several parameter classes in one batch (the code-keyed tables of the reference: cells of different scheme sets and
+    surface properties side by side).  upload() groups the threads by class; every cell must come out exactly as in a
+    single-class batch of its own scheme."""
+    from suews_b200 import OUT_SUM82, SuewsBatch, synth
+    from suews_b200.batch import all_fields, KIND_CELL, KIND_STATE
+    base = fx.state_init(2005)
+    met = fx.forcing(2005)[:288]
+    schemes = ["default", "baserun", "stab2"]
+    ncell = 96
+    cls_of = np.arange(ncell) % 3
+    site = synth.cell_site_arrays(0, ncell, {k.lower(): v for k, v in base.items()})
+    dicts = [synth.base_with_scheme(base, s) for s in schemes]
+    # reference: one single-class batch per scheme over all 96 cells
+    want_sums, want_state = [], []
+    for d in dicts:
+        b = SuewsBatch(ncell, 1)
+        b.load_reference_args(d)
+        for k, v in site.items():
+            b.set_cell_param(k, v if v.ndim == 2 else v.reshape(-1, 1))
+        b.upload()
+        b.set_forcing(met)
+        b.advance(0, 288, OUT_SUM82)
+        want_sums.append(b.sums().copy())
+        want_state.append({nm: b.get_state(nm).copy() for nm in ("state_id", "soilstore_id", "SnowPack", "alb", "HDD_id")})
+        b.close()
+    # the mixed batch
+    b = SuewsBatch(ncell, 3)
+    for k, d in enumerate(dicts):
+        b.load_reference_args(d, cls=k, cells=(k == 0))
+    for k, v in site.items():
+        b.set_cell_param(k, v if v.ndim == 2 else v.reshape(-1, 1))
+    for nm, kind, n in all_fields():           # per-cell state follows the cell's class (snow-free start for snow-off sets)
+        if kind == KIND_STATE and nm.lower() in dicts[0]:
+            vals = np.stack([np.asarray(dicts[c][nm.lower()], dtype=float).ravel() for c in cls_of])
+            b.set_state(nm, vals)
+    b.set_cell_class(cls_of)
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, 288, OUT_SUM82)
+    sums = b.sums()
+    fatal, _w, _it = b.diag()
+    assert not fatal.any()
+    for c in range(ncell):
+        assert np.array_equal(sums[c], want_sums[cls_of[c]][c]), c
+    for nm in want_state[0]:
+        st = b.get_state(nm)
+        for c in range(ncell):
+            assert np.array_equal(st[c], want_state[cls_of[c]][nm][c]), (nm, c)
+    b.close()
