@@ -226,3 +226,13 @@ def test_small_driver_functions_like_f2py_exposes_them():
     L.so_cal_tair_av.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double]
     for dt in (0, 300, 86100, 86400, 86700, 31622400):
         assert sd.cal_tair_av(279.3, dt, 300, 4.25) == L.so_cal_tair_av(279.3, dt, 300, 4.25), dt
+
+
+def test_generated_fortran_driver_interface_matches_the_argument_table():
+    """include/suews_cal_main_iface.f90 lists the 220 / 200 dummies of the reference-shaped calls in table order"""
+    from suews_b200.supy_driver import arg_table
+    f90 = re.sub(r"&\s*\n\s*", " ", open(os.path.join(ROOT, "include", "suews_cal_main_iface.f90")).read())
+    for which, sub, cname in ((0, "SUEWS_cal_Main", "suews_cal_main_"), (1, "SUEWS_cal_multitsteps", "suews_cal_multitsteps_")):
+        m = re.search(r"SUBROUTINE %s\(([^)]*)\)\s*BIND\(C, name='%s'\)" % (sub, cname), f90)
+        names = [a.strip() for a in m.group(1).split(",")]
+        assert names == [r[0] for r in arg_table(which)]
