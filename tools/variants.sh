@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds tuning variants of libsuews_b200.so into scratch/variants/ (launch geometry, inlining switches); time them on
-# the GPU box with scratch/run_variants.sh (SUEWS_B200_LIB selects the library a process loads).
+# the GPU box with tools/run_variants.sh (SUEWS_B200_LIB selects the library a process loads).
 #   usage: tools/variants.sh "name:-DFLAG1 -DFLAG2" ...
 set -e
 cd "$(dirname "$0")/../suews_b200/csrc"
