@@ -1046,6 +1046,8 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
          h->agg_cap = need;
       }
       h->agg_rows = rows;
+      // rows of cells that stop on a fatal error are never written: they read as NaN, not as a previous launch's values
+      CUDA_OK(cudaMemsetAsync(h->d_agg, 0xFF, sizeof(double) * need, h->stream));
       a.agg = h->d_agg;
       a.agg_nlines = nlines;
    }
