@@ -413,9 +413,9 @@ long long suews_write_txt(const double *block, int nrows, int ncol, const char *
 // ---- NextInitial (suews_ctrl_init.f95:2022-2149): the InitialConditions namelist a following run starts from, in
 // gfortran's list-directed layout: a leading blank, INTEGER in 12 columns, REAL(8) with 17 significant digits in 26
 // columns -- F editing followed by five blanks for 0.1 <= |x| < 1e17 (and for 0), 1PE25.17E3 otherwise.
-static int fmt_list_real(double v, char *out)
+static int fmt_list_real(double v, char *out /* at least 128 bytes */)
 {
-   char num[64];
+   char num[96];
    int n;
    const double a = fabs(v);
    if (v == 0.0 || (a >= 0.1 && a < 1e17)) {
@@ -427,7 +427,7 @@ static int fmt_list_real(double v, char *out)
       }
       if (k < 0) k = 0;
       n = snprintf(num, sizeof num, "%.*f", 17 - k, v);
-      return snprintf(out, 64, "%*s     ", 21, num);
+      return snprintf(out, 128, "%*s     ", 21, num);
    }
    char e[64];
    snprintf(e, sizeof e, "%.16E", v);
@@ -436,7 +436,7 @@ static int fmt_list_real(double v, char *out)
    *ex = 0;
    n = snprintf(num, sizeof num, "%sE%c%03d", e, x < 0 ? '-' : '+', x < 0 ? -x : x);
    (void)n;
-   return snprintf(out, 64, "%*s", 26, num);
+   return snprintf(out, 128, "%*s", 26, num);
 }
 
 long long suews_write_initial_conditions(const double *v54, int snow_use, char *buf, long long buflen)
@@ -444,7 +444,7 @@ long long suews_write_initial_conditions(const double *v54, int snow_use, char *
    if (!v54) return -SUEWS_E_BAD_ARG;
    static const char *const surf[7] = {"Paved", "Bldgs", "EveTr", "DecTr", "Grass", "BSoil", "Water"};
    std::string t = " &InitialConditions\n";
-   char f[64], nm[64];
+   char f[128], nm[64];
    snprintf(f, sizeof f, " DaysSinceRain=%12d\n", (int)v54[0]);
    t += f;
    static const char *const head[11] = {"Temp_C0", "GDD_1_0", "GDD_2_0", "LAIinitialEveTr", "LAIinitialDecTr", "LAIinitialGrass",
