@@ -963,18 +963,19 @@ int suews_b200_set_estm_forcing_orig(suews_b200_handle h, const double *ts_orig,
       if (all) a.all_missing |= (1u << c);
       if (disagg_method == 2) a.type20 |= (1u << c);
    }
-   double *d_slow = nullptr, *d_fast = nullptr;
-   CUDA_OK(dev_alloc(&d_slow, n * 13));
-   CUDA_OK(dev_alloc(&d_fast, nfast * 13));
-   a.slow = d_slow; a.fast = d_fast;
-   CUDA_OK(cudaMemcpyAsync(d_slow, ts_orig, sizeof(double) * n * 13, cudaMemcpyHostToDevice, h->stream));
+   struct Scratch {   // freed on every path out of this function
+      double *slow = nullptr, *fast = nullptr;
+      ~Scratch() { cudaFree(slow); cudaFree(fast); }
+   } sc;
+   CUDA_OK(dev_alloc(&sc.slow, n * 13));
+   CUDA_OK(dev_alloc(&sc.fast, nfast * 13));
+   a.slow = sc.slow; a.fast = sc.fast;
+   CUDA_OK(cudaMemcpyAsync(sc.slow, ts_orig, sizeof(double) * n * 13, cudaMemcpyHostToDevice, h->stream));
    suews_disagg_kernel<<<(unsigned)((nfast + 255) / 256), 256, 0, h->stream>>>(a);
    CUDA_OK(cudaGetLastError());
    h->ts5_block.resize(nfast * 13);
-   CUDA_OK(cudaMemcpyAsync(h->ts5_block.data(), d_fast, sizeof(double) * nfast * 13, cudaMemcpyDeviceToHost, h->stream));
+   CUDA_OK(cudaMemcpyAsync(h->ts5_block.data(), sc.fast, sizeof(double) * nfast * 13, cudaMemcpyDeviceToHost, h->stream));
    CUDA_OK(cudaStreamSynchronize(h->stream));
-   cudaFree(d_slow);
-   cudaFree(d_fast);
    // the [nsteps][9] layout the timestep kernel reads (a few hundred KB: repacked through the host copy kept for readback)
    return suews_b200_set_estm_forcing(h, h->ts5_block.data(), (int)nfast);
 }
