@@ -89,7 +89,7 @@ SU_DEVNI void Snow_cal_MeltHeat(const SuewsClassParams &P, const double *sfr, do
                   h.FreezMelt[is] = -mw;
                   mw = 0;
                   if (h.FreezMelt[is] > SnowWater[is]) h.FreezMelt[is] = SnowWater[is];
-                  h.Qm_melt[is] = SU_WATERDENS * ((-h.FreezMelt[is] / tstep_real) / 1000) * (lvS_J_kg - lv_J_kg);
+                  h.Qm_melt[is] = SU_WATERDENS * su_div0(su_div0(-h.FreezMelt[is], tstep_real), 1000) * (lvS_J_kg - lv_J_kg);
                }
                h.mw_ind[is] = mw;
                if (Temp_C >= P.PrecipLimit && Precip > 0) {
@@ -105,7 +105,7 @@ SU_DEVNI void Snow_cal_MeltHeat(const SuewsClassParams &P, const double *sfr, do
                   if (fs > state_id[is]) fs = state_id[is];
                   double fsv;
                   if (SnowPack[is] == 0 || SnowFrac[is] == 0) fsv = fs;
-                  else fsv = fs * (1 - SnowFrac[is]) / SnowFrac[is];
+                  else fsv = su_div0(fs * (1 - SnowFrac[is]), SnowFrac[is]);
                   if (fsv < F(0.00000000001) && fs < state_id[is]) { fs = 0; fsv = 0; }
                   h.FreezState[is] = fs;
                   h.FreezStateVol[is] = fsv;
@@ -229,13 +229,13 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
       double EaIce = avRh / 100 * esIce;
       double vdrcIce = (esIce - EaIce) * avdens * avcp;
       tlv_sub = lvS_J_kg / (double)P.tstep;
-      double e_snow = sae_snow + vdrcIce / RAsnow;
-      double qe_snow = e_snow / (sIce_hPa + psyc_hPa);
-      ev_snow = qe_snow / tlv_sub;
+      double e_snow = sae_snow + su_div0(vdrcIce, RAsnow);   // zero numerators are the rule here (su_div0)
+      double qe_snow = su_div0(e_snow, sIce_hPa + psyc_hPa);
+      ev_snow = su_div0(qe_snow, tlv_sub);
    }
 
    if (is > 1 && PervFraction != 0)
-      EvPart = (w.SurplusEvap[PAV] * sfr[PAV] + w.SurplusEvap[BLDG] * sfr[BLDG]) / PervFraction;
+      EvPart = su_div0(w.SurplusEvap[PAV] * sfr[PAV] + w.SurplusEvap[BLDG] * sfr[BLDG], PervFraction);
 
    if (is == WATER && sfr[WATER] > 0) {
       // label 606, snow.f95:1083-1146

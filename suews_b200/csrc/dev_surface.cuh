@@ -109,7 +109,7 @@ SU_DEV void cal_evap(int EvapMethod, double state_is, double WetThresh_is, doubl
                      double avdens, double avcp, double qn_e, double s_hPa, double psyc_hPa, double ResistSurf, double RA,
                      double rb, double tlv, double &ev, double &qe)
 {
-   double numPM = s_hPa * qn_e + vpd_hPa * avdens * avcp / RA;
+   double numPM = s_hPa * qn_e + su_div0(vpd_hPa * avdens * avcp, RA);
    if (state_is <= F(0.001)) {
       qe = numPM / (s_hPa + psyc_hPa * (1 + ResistSurf / RA));
       ev = qe / tlv;
