@@ -305,9 +305,9 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
       cal_RoughnessParameters(dg, P.RoughLenMomMethod, C, D.porosity_id, FAI, zH, z0m, zdm, ZZD);
       spa_location_part(E, C.lat, C.lng, C.alt, azimuth, zenith_deg);
       RadMethod(dg, P.NetRadiationMethod, snowUse, nrm_use, AlbedoChoice, ldown_option);
-      // Tsurf enters NARP only through the iteration-based methods (narp.f95:337-346); ESTM advances its element
-      // temperatures on every call of SUEWS_cal_Qs, i.e. on every trip (dev_estm.cuh)
-      rad_invariant = (nrm_use < 10) && !use_estm;
+      // Tsurf enters NARP only through the iteration-based methods (narp.f95:337-346).  (ESTM, which advances its
+      // element temperatures on every call of SUEWS_cal_Qs, is run per trip below whatever the radiation scheme.)
+      rad_invariant = (nrm_use < 10);
       // snow fraction seen by SurfaceResistance = SnowFrac_next after Snow_cal_MeltHeat (driver.f95:848)
       for (int is = 0; is < NSURF; is++)
          SnowFrac_res[is] = (snowUse == 1) ? ((nrm_use > 0) ? S.SnowFrac[is] : R.snowFrac_obs) : 0.0;
@@ -387,14 +387,17 @@ __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, cons
                OHM(dg, P, sfr, qn1_use, S.qn1_av, S.dqndt, qn1_av_next, dqndt_next, qn1_S, S.qn1_s_av, S.dqnsdt, qn1_s_av_next,
                    dqnsdt_next, dt_since_start, D.HDD_id[9], S.soilstore_id.v, S.state_id.v, SnowFrac_q, a1, a2, a3, qs,
                    deltaQi);
-            } else if (use_estm) {
-               // ESTM (driver.f95:1598-1606): parameters and element temperatures live in MODULE ESTM_data in the
-               // reference, in the class record and the per-cell ESTM state here; Tair_av is Tair_av_next (:784)
-               if (ES && ts9) qs = ESTM(P, C, *ES, avU1, Temp_C, avRh, Press_hPa, ts9, H.Tair_av_next, L.estm27);
-               else su_fatal(dg, 1005);   // ESTM selected but no ESTM state / surface-temperature forcing was supplied
-            } else {
+            } else if (!use_estm) {
                su_fatal(dg, 1003);   // AnOHM needs module state outside the cal_Main argument list
             }
+         }
+         if (use_estm) {
+            // ESTM (driver.f95:1598-1606), once per trip: it reads none of cal_Qn's results (the surface temperatures are
+            // forcing), so the radiation above stays hoisted when the scheme allows.  Parameters and element temperatures
+            // live in MODULE ESTM_data in the reference, in the class record and the per-cell ESTM state here; Tair_av is
+            // Tair_av_next (:784)
+            if (ES && ts9) qs = ESTM(P, C, *ES, avU1, Temp_C, avRh, Press_hPa, ts9, H.Tair_av_next, L.estm27);
+            else su_fatal(dg, 1005);   // ESTM selected but no ESTM state / surface-temperature forcing was supplied
          }
          if (redo_rad || A.lv_J_kg != lv_at_melt) {
             // ---------------- Snow_cal_MeltHeat driver.f95:793-805 (SnowFrac / SnowAlb alias in and out)
