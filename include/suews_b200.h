@@ -141,7 +141,9 @@ int suews_b200_get_diag(suews_b200_handle h, int *fatal_code_per_cell, unsigned 
                         long long *tsurf_iterations_per_cell);
 /* device time (ms) of the last advance, measured with CUDA events on the library's stream */
 int suews_b200_last_advance_ms(suews_b200_handle h, float *ms);
-/* raw device pointers for callers that keep forcing / results on the GPU (bench, multi-GPU hosts) */
+/* raw device pointers for callers that keep results on the GPU (multi-GPU hosts): d_sums is [82][cell_stride] in cell
+ * order; d_state is [field][cell_stride] in the library's thread order (the cost-sorted order the kernel walks, so that its
+ * loads coalesce) -- use suews_b200_get_state for cell order */
 int suews_b200_device_ptrs(suews_b200_handle h, void **d_state, void **d_sums, long long *cell_stride);
 
 /* ---- reference-shaped entry points --------------------------------------------------------- */

@@ -214,17 +214,17 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
    if (active && a.estm) {
       double *ep = reinterpret_cast<double *>(&ES);
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) ep[j] = a.estm[(size_t)j * a.stride + cell];
+      for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) ep[j] = a.estm[(size_t)j * a.stride + slot];
    }
    if (active) {
       cls = a.class_of_cell[cell];
       tz = a.tz_of_cell[cell];
       double *cp = reinterpret_cast<double *>(&C);
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_CELL_DBL; j++) cp[j] = a.cellp[(size_t)j * a.stride + cell];
+      for (int j = 0; j < SUEWS_N_CELL_DBL; j++) cp[j] = a.cellp[(size_t)j * a.stride + slot];   // slot order: coalesced
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) sp[j] = a.state[(size_t)j * a.stride + cell];
+      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) sp[j] = a.state[(size_t)j * a.stride + slot];
       dg.fatal = a.fatal[cell];
       dg.warn[0] = a.warn[cell];
       dg.warn[1] = a.warn[a.stride + cell];
@@ -336,11 +336,11 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
       S.albDecTr_id = D.albDecTr_id; S.albEveTr_id = D.albEveTr_id; S.albGrass_id = D.albGrass_id; S.porosity_id = D.porosity_id;
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + cell] = sp[j];
+      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + slot] = sp[j];
       if (a.estm) {
          double *ep = reinterpret_cast<double *>(&ES);
 #pragma unroll 1
-         for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) a.estm[(size_t)j * a.stride + cell] = ep[j];
+         for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) a.estm[(size_t)j * a.stride + slot] = ep[j];
       }
       a.fatal[cell] = dg.fatal;
       a.warn[cell] = dg.warn[0];
@@ -524,7 +524,8 @@ struct suews_b200_handle_s {
    double *d_agg = nullptr;                               // aggregated SUEWS block [rows][87][stride] (thread-slot order)
    size_t agg_cap = 0;
    int agg_rows = 0, out_freq_s = 3600;
-   std::vector<int> slot_of_cell;
+   std::vector<int> slot_of_cell, cell_of_slot;
+   std::vector<double> xfer;   // staging for the cell-order <-> slot-order moves
    int ts5_nsteps = 0;
    std::vector<int> cls_of_cell, tz_of_cell;
    std::vector<double> tz_list;
@@ -555,6 +556,29 @@ template <typename T> static cudaError_t dev_alloc(T **p, size_t n)
 {
    if (*p) { cudaFree(*p); *p = nullptr; }
    return cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
+}
+
+// Device copies of the per-cell SoA arrays (cell parameters, state, ESTM state) are stored in THREAD-SLOT order -- the
+// cost-sorted order the kernel walks -- so that a warp's load of one field is one contiguous 256 B line.  The host
+// keeps cell order; these two move a block of fields across, through h->slot_of_cell / the order map.
+static void to_slot_order(const double *cell_major, double *slot_major, const std::vector<int> &order, size_t nfield, size_t stride)
+{
+   const size_t n = order.size();
+   for (size_t j = 0; j < nfield; j++) {
+      const double *src = cell_major + j * stride;
+      double *dst = slot_major + j * stride;
+      for (size_t sl = 0; sl < n; sl++) dst[sl] = src[(size_t)order[sl]];
+      for (size_t sl = n; sl < stride; sl++) dst[sl] = 0.0;
+   }
+}
+static void to_cell_order(const double *slot_major, double *cell_major, const std::vector<int> &order, size_t nfield, size_t stride)
+{
+   const size_t n = order.size();
+   for (size_t j = 0; j < nfield; j++) {
+      const double *src = slot_major + j * stride;
+      double *dst = cell_major + j * stride;
+      for (size_t sl = 0; sl < n; sl++) dst[(size_t)order[sl]] = src[sl];
+   }
 }
 
 extern "C" {
@@ -711,8 +735,10 @@ int suews_b200_get_state(suews_b200_handle h, const char *name, double *vals, in
       if (h->uploaded && h->d_estm) {
          CUDA_OK(cudaSetDevice(h->device));
          CUDA_OK(cudaStreamSynchronize(h->stream));
-         CUDA_OK(cudaMemcpy(&h->estm[f->off * (size_t)h->stride], h->d_estm + f->off * (size_t)h->stride,
+         h->xfer.resize(std::max(h->xfer.size(), (size_t)f->n * (size_t)h->stride));
+         CUDA_OK(cudaMemcpy(h->xfer.data(), h->d_estm + f->off * (size_t)h->stride,
                             sizeof(double) * (size_t)f->n * (size_t)h->stride, cudaMemcpyDeviceToHost));
+         to_cell_order(h->xfer.data(), &h->estm[f->off * (size_t)h->stride], h->cell_of_slot, (size_t)f->n, (size_t)h->stride);
       }
       for (int k = 0; k < f->n; k++) {
          const double *src = &h->estm[(f->off + (size_t)k) * (size_t)h->stride];
@@ -723,8 +749,10 @@ int suews_b200_get_state(suews_b200_handle h, const char *name, double *vals, in
    if (h->uploaded) {
       CUDA_OK(cudaSetDevice(h->device));
       CUDA_OK(cudaStreamSynchronize(h->stream));
-      CUDA_OK(cudaMemcpy(&h->state[f->off * (size_t)h->stride], h->d_state + f->off * (size_t)h->stride,
+      h->xfer.resize(std::max(h->xfer.size(), (size_t)f->n * (size_t)h->stride));
+      CUDA_OK(cudaMemcpy(h->xfer.data(), h->d_state + f->off * (size_t)h->stride,
                          sizeof(double) * (size_t)f->n * (size_t)h->stride, cudaMemcpyDeviceToHost));
+      to_cell_order(h->xfer.data(), &h->state[f->off * (size_t)h->stride], h->cell_of_slot, (size_t)f->n, (size_t)h->stride);
    }
    for (int k = 0; k < f->n; k++) {
       const double *src = &h->state[(f->off + (size_t)k) * (size_t)h->stride];
@@ -798,6 +826,7 @@ int suews_b200_upload(suews_b200_handle h)
    }
    h->slot_of_cell.assign((size_t)h->ncell, 0);
    for (int sl = 0; sl < h->ncell; sl++) h->slot_of_cell[(size_t)order[(size_t)sl]] = sl;
+   h->cell_of_slot = order;
    const size_t st = (size_t)h->stride;
    CUDA_OK(dev_alloc(&h->d_order, st));
    CUDA_OK(cudaMemcpy(h->d_order, order.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
@@ -814,8 +843,11 @@ int suews_b200_upload(suews_b200_handle h)
    CUDA_OK(cudaMemcpy(h->d_classes, h->classes.data(), sizeof(SuewsClassParams) * (size_t)h->nclass, cudaMemcpyHostToDevice));
    CUDA_OK(cudaMemcpy(h->d_cls, h->cls_of_cell.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
    CUDA_OK(cudaMemcpy(h->d_tz, h->tz_of_cell.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
-   CUDA_OK(cudaMemcpy(h->d_cellp, h->cellp.data(), sizeof(double) * h->cellp.size(), cudaMemcpyHostToDevice));
-   CUDA_OK(cudaMemcpy(h->d_state, h->state.data(), sizeof(double) * h->state.size(), cudaMemcpyHostToDevice));
+   h->xfer.resize(std::max(h->cellp.size(), h->state.size()));
+   to_slot_order(h->cellp.data(), h->xfer.data(), order, SUEWS_N_CELL_DBL, st);
+   CUDA_OK(cudaMemcpy(h->d_cellp, h->xfer.data(), sizeof(double) * h->cellp.size(), cudaMemcpyHostToDevice));
+   to_slot_order(h->state.data(), h->xfer.data(), order, SUEWS_N_STATE_DBL, st);
+   CUDA_OK(cudaMemcpy(h->d_state, h->xfer.data(), sizeof(double) * h->state.size(), cudaMemcpyHostToDevice));
    CUDA_OK(cudaMemcpy(h->d_tzlist, h->tz_list.data(), sizeof(double) * h->tz_list.size(), cudaMemcpyHostToDevice));
    {   // ESTM state travels only when some class runs ESTM
       bool any_estm = false;
@@ -823,7 +855,8 @@ int suews_b200_upload(suews_b200_handle h)
       if (any_estm) {
          if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
          CUDA_OK(dev_alloc(&h->d_estm, (size_t)SUEWS_N_ESTM_DBL * st));
-         CUDA_OK(cudaMemcpy(h->d_estm, h->estm.data(), sizeof(double) * h->estm.size(), cudaMemcpyHostToDevice));
+         to_slot_order(h->estm.data(), h->xfer.data(), order, SUEWS_N_ESTM_DBL, st);
+         CUDA_OK(cudaMemcpy(h->d_estm, h->xfer.data(), sizeof(double) * h->estm.size(), cudaMemcpyHostToDevice));
       } else if (h->d_estm) {
          cudaFree(h->d_estm);
          h->d_estm = nullptr;
