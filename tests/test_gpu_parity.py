@@ -764,3 +764,19 @@ def test_mixed_scheme_classes_in_one_batch():
         for c in range(ncell):
             assert np.array_equal(st[c], want_state[cls_of[c]][nm][c], equal_nan=True), (nm, c)
     b.close()
+
+
+@pytest.mark.gpu
+def test_baserun_output_files_from_the_gpu_path(tmp_path):
+    """examples/baserun_2005.py: hourly forcing file in, the reference's own output file and checkpoint out.  The CUDA
+    path differs from the reference by libm ulps, so a printed digit can only differ for a value sitting on a rounding
+    boundary of its last decimal"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("baserun_2005", os.path.join(os.path.dirname(fx.GOLDEN), "..", "examples", "baserun_2005.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    bad, fields, worst = mod.main(str(tmp_path))
+    assert fields == 120 * 87
+    assert bad <= 3, bad
+    assert worst <= 1e-9
