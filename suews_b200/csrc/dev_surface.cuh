@@ -503,13 +503,25 @@ SU_BIG2 void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *sf
    double rt[NSURF - 1];
    for (int is = 0; is < NSURF - 1; is++) rt[is] = sqrt(sfr[is] * SurfaceArea / 1.0);
    runoffSoil_per_tstep = 0;
+   // The reference evaluates the van Genuchten pair of BOTH stores for each of the 15 pairs (30 evaluations); a store's
+   // pair is a pure function of its content, which a pair only changes when water actually flows (equal matric
+   // potentials -- e.g. two saturated stores -- give dI = 0).  Each store's last evaluation is kept with the content it
+   // was made for and reused while the content is bit-identical.
+   double vg_at[NSURF - 1], vg_mp[NSURF - 1], vg_km[NSURF - 1];
+   for (int is = 0; is < NSURF - 1; is++) vg_at[is] = -1.0;   // soil stores are never negative
    for (int is = 0; is < NSURF - 1; is++) {
       if (sfr[is] != 0 && P.SoilStoreCap[is] > 0) {
          for (int jj = is + 1; jj < NSURF - 1; jj++) {
             if (sfr[jj] != 0 && P.SoilStoreCap[jj] > 0) {
-               double MatPot1, Km1, MatPot2, Km2;
-               vg_store(soilstore_id[is], P.SoilStoreCap[is], P.SoilDepth[is], P.SatHydraulicConduct[is], MatPot1, Km1);
-               vg_store(soilstore_id[jj], P.SoilStoreCap[jj], P.SoilDepth[jj], P.SatHydraulicConduct[jj], MatPot2, Km2);
+               if (vg_at[is] != soilstore_id[is]) {
+                  vg_store(soilstore_id[is], P.SoilStoreCap[is], P.SoilDepth[is], P.SatHydraulicConduct[is], vg_mp[is], vg_km[is]);
+                  vg_at[is] = soilstore_id[is];
+               }
+               if (vg_at[jj] != soilstore_id[jj]) {
+                  vg_store(soilstore_id[jj], P.SoilStoreCap[jj], P.SoilDepth[jj], P.SatHydraulicConduct[jj], vg_mp[jj], vg_km[jj]);
+                  vg_at[jj] = soilstore_id[jj];
+               }
+               const double MatPot1 = vg_mp[is], Km1 = vg_km[is], MatPot2 = vg_mp[jj], Km2 = vg_km[jj];
                double Distance = (rt[is] + rt[jj]) / 2;
                double KmWeight = (sfr[is] * Km1 + sfr[jj] * Km2) / (sfr[is] + sfr[jj]);
                double dI_dt = su_div0(-(KmWeight) * (-MatPot1 + MatPot2), Distance * 1000);

@@ -1100,6 +1100,14 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
    a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;
    const int grid = (h->ncell + SU_BLOCK - 1) / SU_BLOCK;
+   {   // the kernel stages 11 KB of forcing in shared memory and lives off L1 for its stack: ask for the largest L1
+      static bool carveout_set = false;
+      if (!carveout_set && !getenv("SUEWS_B200_DEFAULT_CARVEOUT")) {
+         cudaFuncSetAttribute(suews_run_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+         cudaFuncSetAttribute(suews_run_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+         carveout_set = true;
+      }
+   }
    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
    if (full) suews_run_kernel<true><<<grid, SU_BLOCK, 0, h->stream>>>(a);
    else suews_run_kernel<false><<<grid, SU_BLOCK, 0, h->stream>>>(a);
