@@ -62,5 +62,31 @@ def main(outdir):
     return bad, fields, worst
 
 
+def year_2004(outdir):
+    """The 2004 leg of the same golden run: 105 408 steps, then the checkpoint the next year starts from."""
+    from suews_b200 import OUT_SUM7
+    os.makedirs(outdir, exist_ok=True)
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(fx.state_init(2004))
+    b.upload()
+    nsteps = b.set_forcing_orig(read_met(os.path.join(fx.GOLDEN, "forcing_2004_60min.txt")), resolution_in=3600)
+    for day0 in range(0, 366, 61):
+        b.advance(day0 * 288, 61 * 288, OUT_SUM7)
+    nml = checkpoint.write_text(checkpoint.state_vector(lambda n: b.get_state(n)[0]), snow_use=1)
+    open(os.path.join(outdir, "InitialConditionstest1_2005.nml"), "w").write(nml)
+    b.close()
+    ref_text = open(os.path.join(fx.GOLDEN, "ref_InitialConditions_2005.nml")).read()
+    ref_nml, ours = checkpoint.read_text(ref_text), checkpoint.read_text(nml)
+    diffs = {k: abs(ours[k] - r) / max(abs(r), 1e-3) for k, r in ref_nml.items()}
+    worst = max(diffs, key=diffs.get)
+    print("2004 (%d steps) -> InitialConditions_2005.nml: %d of 54 values bit-identical to the reference's, largest relative "
+          "difference %.2e (%s)%s" % (nsteps, sum(v == 0 for v in diffs.values()), diffs[worst], worst,
+                                      ", file byte-identical" if nml == ref_text else ""))
+    return diffs
+
+
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "scratch", "baserun_2005_out"))
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "scratch", "baserun_2005_out")
+    main(out)
+    if "--year-2004" in sys.argv:
+        year_2004(out)
