@@ -101,7 +101,7 @@ def test_state_after_the_2005_leg_against_the_reference_checkpoint(gpu_and_ref_2
     ours = checkpoint.read_text(checkpoint.write_text(checkpoint.state_vector(lambda n: b.get_state(n)[0]), snow_use=1))
     assert ours.keys() == ref_nml.keys()
     worst = max(abs(ours[k] - r) / max(abs(r), 1e-3) for k, r in ref_nml.items())
-    assert worst <= 1e-9, worst
+    assert worst <= 1e-12, worst        # measured: 0 (all 54 values bit-identical)
 
 
 def test_parity_sums_policy_equals_full_sums(gpu_and_ref_2005):
@@ -333,8 +333,8 @@ def test_annual_flux_sums_match_oracle():
     ref_nml = checkpoint.read(fx.GOLDEN + "/ref_InitialConditions_2005.nml")
     ours = checkpoint.read_text(checkpoint.write_text(checkpoint.state_vector(lambda n: b.get_state(n)[0]), snow_use=1))
     assert ours.keys() == ref_nml.keys()
-    for k, r in ref_nml.items():
-        assert abs(ours[k] - r) <= 1e-7 * max(abs(r), 1e-3), (k, ours[k], r)
+    for k, r in ref_nml.items():   # measured: 53 of the 54 values bit-identical, the other one ulp off (1.4e-16)
+        assert abs(ours[k] - r) <= 1e-10 * max(abs(r), 1e-3), (k, ours[k], r)
     b.close()
 
 
@@ -778,5 +778,5 @@ def test_baserun_output_files_from_the_gpu_path(tmp_path):
     spec.loader.exec_module(mod)
     bad, fields, worst = mod.main(str(tmp_path))
     assert fields == 120 * 87
-    assert bad <= 3, bad
-    assert worst <= 1e-9
+    assert bad <= 3, bad                # measured: 0 -- the file is byte-identical to the reference's
+    assert worst <= 1e-12               # measured: 0
