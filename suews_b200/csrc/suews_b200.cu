@@ -1133,6 +1133,7 @@ int suews_b200_get_agg_block(suews_b200_handle h, int cell, double *block, int n
    CUDA_OK(cudaSetDevice(h->device));
    CUDA_OK(cudaStreamSynchronize(h->stream));
    const int ncol = SUEWS_NCOL_SUEWS + 5;
+   if (nrows == 0) return SUEWS_OK;   // fewer steps than one output period
    std::vector<double> tmp((size_t)nrows * ncol);   // [row][col]
    CUDA_OK(cudaMemcpy2D(tmp.data(), sizeof(double), h->d_agg + h->slot_of_cell[(size_t)cell], sizeof(double) * (size_t)h->stride,
                         sizeof(double), (size_t)nrows * ncol, cudaMemcpyDeviceToHost));
