@@ -125,6 +125,11 @@ int suews_b200_sync(suews_b200_handle h);
 int suews_b200_set_output_freq(suews_b200_handle h, int out_freq_s);
 int suews_b200_get_agg_block(suews_b200_handle h, int cell, double *block, int nrows);
 int suews_b200_get_agg_column(suews_b200_handle h, int row, int col, double *vals);
+/* The same launch also keeps the DailyState line of every day that ends inside it (it exists on the last step of a day
+ * only, dailystate.f95:1094-1111): agg_daily_rows reports how many, get_agg_daily_block returns one cell's [nrows x 50]
+ * block, column-major -- the rows SUEWS_Output writes to <site>_DailyState.txt. */
+int suews_b200_agg_daily_rows(suews_b200_handle h, int *nrows);
+int suews_b200_get_agg_daily_block(suews_b200_handle h, int cell, double *block, int nrows);
 
 /* Results.  sums: [ncell][82] (cell-major).  Full blocks (after SUEWS_OUT_FULL): per cell a
  * column-major [nsteps x ncol] block as SUEWS_cal_multitsteps returns it (87/103/138/50/31/32 columns). */

@@ -179,6 +179,20 @@ MODULE suews_b200
          REAL(C_DOUBLE), INTENT(OUT) :: block(*)
       END FUNCTION
 
+      INTEGER(C_INT) FUNCTION suews_b200_agg_daily_rows(h, nrows) BIND(C, name='suews_b200_agg_daily_rows')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: h
+         INTEGER(C_INT), INTENT(OUT) :: nrows
+      END FUNCTION
+
+      ! block(nrows, 50): the DailyState rows of the days that ended inside the last SUEWS_OUT_AGG launch
+      INTEGER(C_INT) FUNCTION suews_b200_get_agg_daily_block(h, cell, block, nrows) BIND(C, name='suews_b200_get_agg_daily_block')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: h
+         INTEGER(C_INT), VALUE :: cell, nrows
+         REAL(C_DOUBLE), INTENT(OUT) :: block(*)
+      END FUNCTION
+
       ! sums(82, ncell)
       INTEGER(C_INT) FUNCTION suews_b200_get_sums(h, sums) BIND(C, name='suews_b200_get_sums')
          IMPORT :: C_INT, C_PTR, C_DOUBLE

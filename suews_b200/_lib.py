@@ -54,6 +54,8 @@ def lib():
         L.suews_b200_set_output_freq.argtypes = [H, C.c_int]
         L.suews_b200_get_agg_block.argtypes = [H, C.c_int, dp, C.c_int]
         L.suews_b200_get_agg_column.argtypes = [H, C.c_int, C.c_int, dp]
+        L.suews_b200_agg_daily_rows.argtypes = [H, ip]
+        L.suews_b200_get_agg_daily_block.argtypes = [H, C.c_int, dp, C.c_int]
         L.suews_b200_get_sums.argtypes = [H, dp]
         L.suews_b200_reset_sums.argtypes = [H]
         L.suews_b200_get_sums_cols.argtypes = [H, ip, C.c_int, dp]

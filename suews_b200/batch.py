@@ -191,6 +191,14 @@ class SuewsBatch:
         check(self.L.suews_b200_get_agg_block(self.h, int(cell), b.ctypes.data_as(dp), int(nrows)))
         return b
 
+    def agg_daily_block(self, cell):
+        """One cell's DailyState rows (one per day that ended inside the last OUT_AGG launch), [ndays, 50]."""
+        n = C.c_int()
+        check(self.L.suews_b200_agg_daily_rows(self.h, C.byref(n)))
+        b = np.zeros((n.value, 50), order="F")
+        check(self.L.suews_b200_get_agg_daily_block(self.h, int(cell), b.ctypes.data_as(dp), n.value))
+        return b
+
     def agg_column(self, row, col):
         a = np.zeros(self.ncell)
         check(self.L.suews_b200_get_agg_column(self.h, int(row), int(col), a.ctypes.data_as(dp)))

@@ -66,6 +66,8 @@ struct SuRunArgs {
    // does (suews_ctrl_output.f95:912-957), [row][87][stride] indexed by thread slot so that a warp writes 256 B lines
    double *agg;
    int agg_nlines;
+   double *agg_daily;           // with agg: one DailyState row per day that ends inside the launch, [row][50][stride] (thread order)
+   int agg_daily_rows;
    int ncell;
    long long stride;
    int nsteps;
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
    const SuewsEphem *eph = a.ephem + (size_t)tz * a.ephem_tz_stride;
    int dt_since_start = a.dt_since_start;
    int tstep_prev = a.tstep_prev;
+   int n_day_rows = 0;
 
    for (int ch = 0; ch < nchunk; ch++) {
       const int buf = ch & 1;
@@ -277,11 +280,25 @@ __global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRun
          double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY], l_so[SUEWS_NCOL_SOLWEIG];
          double l_es[SUEWS_NCOL_ESTM];
          if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; L.estm27 = l_es; }
+         // policy P1 also keeps the DailyState line, which only exists on the last step of a day (dailystate.f95:1094)
+         const bool day_end = a.agg_daily && (sm_steps[buf][t].it * 3600 + sm_steps[buf][t].imin * 60 + a.tstep) >= 86400;
+         if (day_end) L.daily45 = l_da;
          // every thread of the block enters the step (phase barriers inside); only live cells compute
          iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S, D,
                              (a.agg || (a.sums && !a.sum7)) ? acc : nullptr, (!a.agg && a.sums && a.sum7) ? acc7 : nullptr, L,
                              a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
                              a.flux_only != 0);
+         if (day_end) {
+            if (live && dg.fatal == 0 && n_day_rows < a.agg_daily_rows) {
+               const SuewsStepRec &R = sm_steps[buf][t];
+               double *o = a.agg_daily + (size_t)n_day_rows * (SUEWS_NCOL_DAILY + 5) * (size_t)a.stride + slot;
+               o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
+               o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
+#pragma unroll 1
+               for (int c = 0; c < SUEWS_NCOL_DAILY; c++) o[(size_t)(5 + c) * a.stride] = l_da[c];
+            }
+            n_day_rows++;
+         }
          if (a.agg && (gs + 1) % a.agg_nlines == 0) {   // SUEWS_Output_Agg: rows i-nlinesOut+1 .. i -> row i/nlinesOut
             if (live && dg.fatal == 0) {
                const SuewsStepRec &R = sm_steps[buf][t];
@@ -522,6 +539,10 @@ struct suews_b200_handle_s {
    double *d_estm = nullptr, *d_ts5 = nullptr;
    double *d_met_orig = nullptr, *d_met_fast = nullptr;   // forcing at file resolution / disaggregated on the device
    double *d_agg = nullptr;                               // aggregated SUEWS block [rows][87][stride] (thread-slot order)
+   double *d_agg_daily = nullptr;                         // DailyState rows of the same launch [rows][50][stride]
+   size_t agg_daily_cap = 0;
+   int agg_daily_rows = 0;
+   std::vector<unsigned char> day_end_of_step;            // 1 where a forcing row is the last step of its day
    size_t agg_cap = 0;
    int agg_rows = 0, out_freq_s = 3600;
    std::vector<int> slot_of_cell, cell_of_slot;
@@ -645,7 +666,7 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
    for (int i = 0; i < 6; i++) cudaFree(h->d_blk[i]);
-   cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg);
+   cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg); cudaFree(h->d_agg_daily);
 }
 
 int suews_b200_destroy(suews_b200_handle h)
@@ -1059,7 +1080,7 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
       h->blk_nsteps = nsteps;
    }
    SuRunArgs a;
-   a.agg = nullptr; a.agg_nlines = 1;
+   a.agg = nullptr; a.agg_nlines = 1; a.agg_daily = nullptr; a.agg_daily_rows = 0;
    if (out_flags & SUEWS_OUT_AGG) {
       if (out_flags & (SUEWS_OUT_SUM82 | SUEWS_OUT_SUM7))
          return set_err(SUEWS_E_BAD_ARG, "advance: SUEWS_OUT_AGG cannot be combined with the running-sum policies");
@@ -1078,6 +1099,23 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
                            (double)need * 8e-9, rows, h->ncell);
          }
          h->agg_cap = need;
+      }
+      {   // DailyState rows: one per day that ends inside [step0, step0 + nsteps)
+         std::vector<SuewsStepRec> recs((size_t)nsteps);
+         CUDA_OK(cudaMemcpy(recs.data(), h->d_steps + step0, sizeof(SuewsStepRec) * (size_t)nsteps, cudaMemcpyDeviceToHost));
+         int nd = 0;
+         for (const auto &r : recs) nd += (r.it * 3600 + r.imin * 60 + h->tstep) >= 86400;
+         const size_t need_d = (size_t)(nd ? nd : 1) * (SUEWS_NCOL_DAILY + 5) * (size_t)h->stride;
+         if (h->agg_daily_cap < need_d) {
+            if (h->d_agg_daily) { cudaFree(h->d_agg_daily); h->d_agg_daily = nullptr; }
+            h->agg_daily_cap = 0;
+            CUDA_OK(cudaMalloc((void **)&h->d_agg_daily, sizeof(double) * need_d));
+            h->agg_daily_cap = need_d;
+         }
+         CUDA_OK(cudaMemsetAsync(h->d_agg_daily, 0xFF, sizeof(double) * need_d, h->stream));
+         h->agg_daily_rows = nd;
+         a.agg_daily = h->d_agg_daily;
+         a.agg_daily_rows = nd;
       }
       h->agg_rows = rows;
       // rows of cells that stop on a fatal error are never written: they read as NaN, not as a previous launch's values
@@ -1139,6 +1177,29 @@ int suews_b200_get_agg_block(suews_b200_handle h, int cell, double *block, int n
                         sizeof(double), (size_t)nrows * ncol, cudaMemcpyDeviceToHost));
    for (int r = 0; r < nrows; r++)
       for (int c = 0; c < ncol; c++) block[(size_t)r + (size_t)nrows * c] = tmp[(size_t)r * ncol + c];
+   return SUEWS_OK;
+}
+
+// One cell's DailyState rows of the last SUEWS_OUT_AGG launch [nrows x 50], column-major
+int suews_b200_get_agg_daily_block(suews_b200_handle h, int cell, double *block, int nrows)
+{
+   if (!h || !block || !h->d_agg_daily || nrows != h->agg_daily_rows || cell < 0 || cell >= h->ncell)
+      return set_err(SUEWS_E_BAD_SIZE, "get_agg_daily_block: the DailyState block is [%d x 50] per cell", h ? h->agg_daily_rows : 0);
+   if (nrows == 0) return SUEWS_OK;
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   const int ncol = SUEWS_NCOL_DAILY + 5;
+   std::vector<double> tmp((size_t)nrows * ncol);
+   CUDA_OK(cudaMemcpy2D(tmp.data(), sizeof(double), h->d_agg_daily + h->slot_of_cell[(size_t)cell], sizeof(double) * (size_t)h->stride,
+                        sizeof(double), (size_t)nrows * ncol, cudaMemcpyDeviceToHost));
+   for (int r = 0; r < nrows; r++)
+      for (int c = 0; c < ncol; c++) block[(size_t)r + (size_t)nrows * c] = tmp[(size_t)r * ncol + c];
+   return SUEWS_OK;
+}
+int suews_b200_agg_daily_rows(suews_b200_handle h, int *nrows)
+{
+   if (!h || !nrows) return set_err(SUEWS_E_BAD_ARG, "null argument");
+   *nrows = h->agg_daily_rows;
    return SUEWS_OK;
 }
 

@@ -635,6 +635,9 @@ def test_in_kernel_aggregation_equals_aggregating_the_full_block(gpu_and_ref_200
     assert np.array_equal(got[:, :5], oracle[:, :5])
     assert float(rel_err(got[:288 // nper, 5:], oracle[:288 // nper, 5:], "SUEWS").max()) <= TOL_DAY1
     assert np.array_equal(b.agg_column(3, 5 + 5), got[3:4, 5 + 5])
+    # the DailyState rows of the same launch: the rows of the full block that carry data, bit for bit
+    fd = bfull.block("DailyState", 0, n)
+    assert np.array_equal(b.agg_daily_block(0), fd[fd[:, 5] != -999])
     b.close()
 
 
@@ -657,6 +660,16 @@ def test_hourly_aggregates_match_the_reference_golden_file():
         r = gold[:, 5 + c]
         ok = np.isnan(r) | (np.abs(got[:, 5 + c] - r) <= tol[c] + 1e-9 * np.abs(np.nan_to_num(r)))
         assert ok.all(), (hdr[5 + c], int(np.argmin(ok)), got[~ok, 5 + c][:3], r[~ok][:3])
+    # ... and its DailyState file, through the library's writer: byte for byte
+    import ctypes as C
+    from suews_b200 import _lib
+    f = _lib.lib().suews_write_txt
+    f.restype = C.c_longlong
+    f.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_longlong]
+    d = np.asfortranarray(b.agg_daily_block(0))
+    buf = C.create_string_buffer(1 << 16)
+    f(d.ctypes.data_as(C.POINTER(C.c_double)), d.shape[0], d.shape[1], b"DailyState", 2, 1, buf, 1 << 16)
+    assert buf.value.decode() == open(fx.GOLDEN + "/ref_2005_DailyState.txt").read()
     b.close()
 
 
