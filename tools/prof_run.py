@@ -13,7 +13,7 @@ ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 37888
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 48
 scheme = sys.argv[3] if len(sys.argv) > 3 else "default"
 row0 = int(sys.argv[4]) if len(sys.argv) > 4 else 120   # start at 10:00 so day-time physics is in the sample
-base, met = bench.load_inputs(2)
+base, met = bench.load_inputs(max(2, (row0 + 3 * nsteps + 287) // 288))
 b = SuewsBatch(ncell, 1)
 synth.build_batch(b, base, scheme=scheme)
 b.upload()
