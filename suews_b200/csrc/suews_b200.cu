@@ -180,8 +180,13 @@ __global__ void suews_ephem_kernel(const SuewsStepRec *steps, int nsteps, const 
    spa_time_part((double)steps[s].iy, steps[s].dectime - (double)(tstep / 2), tz_list[z], ephem[(size_t)z * nsteps + s]);
 }
 
-template <bool FULL>
-__global__ void __launch_bounds__(SU_BLOCK, SU_MINBLOCKS) suews_run_kernel(SuRunArgs a)
+// A second launch geometry for batches that do not fill the chip with 1024-cell blocks: 256-thread blocks, two per SM
+// (128 registers).  A 10 000-cell batch -- supy's scale -- occupies 40 SMs this way instead of 10.
+#define SU_BLOCK_SMALL 256
+#define SU_MINBLOCKS_SMALL 2
+
+template <bool FULL, int BLOCK, int MINBLOCKS>
+__global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a)
 {
    __shared__ alignas(128) SuewsStepRec sm_steps[2][SU_CHUNK];
    __shared__ alignas(8) uint64_t sm_bar[2];
@@ -1137,18 +1142,33 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.ts5 = (h->d_estm && h->ts5_nsteps == h->nsteps) ? h->d_ts5 + (size_t)step0 * SUEWS_N_TS5 : nullptr;
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
    a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;
-   const int grid = (h->ncell + SU_BLOCK - 1) / SU_BLOCK;
+   // launch geometry: 1024-cell blocks, one per SM, once they can occupy most of the chip; 256-cell blocks below that
+   int nsm = 148;
+   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+   // measured on B200 (cell-steps/s, large vs small geometry): 10 240 cells 0.87e7 / 1.7e7 (full output), 37 888 cells
+   // 6.4e7 / 1.05e8, 75 776 cells 1.23e8 / 1.11e8 -- the crossover sits near 1.5 small blocks per SM
+   bool small = (long long)h->ncell * 2 <= (long long)nsm * SU_BLOCK_SMALL * 3;
+   if (const char *e = getenv("SUEWS_B200_GEOMETRY")) small = (strcmp(e, "small") == 0) ? true : ((strcmp(e, "large") == 0) ? false : small);
+   const int blk = small ? SU_BLOCK_SMALL : SU_BLOCK;
+   const int grid = (h->ncell + blk - 1) / blk;
    {   // the kernel stages 11 KB of forcing in shared memory and lives off L1 for its stack: ask for the largest L1
       static bool carveout_set = false;
       if (!carveout_set && !getenv("SUEWS_B200_DEFAULT_CARVEOUT")) {
-         cudaFuncSetAttribute(suews_run_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-         cudaFuncSetAttribute(suews_run_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+         cudaFuncSetAttribute(suews_run_kernel<true, SU_BLOCK, SU_MINBLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+         cudaFuncSetAttribute(suews_run_kernel<false, SU_BLOCK, SU_MINBLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+         cudaFuncSetAttribute(suews_run_kernel<true, SU_BLOCK_SMALL, SU_MINBLOCKS_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+         cudaFuncSetAttribute(suews_run_kernel<false, SU_BLOCK_SMALL, SU_MINBLOCKS_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
          carveout_set = true;
       }
    }
    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
-   if (full) suews_run_kernel<true><<<grid, SU_BLOCK, 0, h->stream>>>(a);
-   else suews_run_kernel<false><<<grid, SU_BLOCK, 0, h->stream>>>(a);
+   if (small) {
+      if (full) suews_run_kernel<true, SU_BLOCK_SMALL, SU_MINBLOCKS_SMALL><<<grid, blk, 0, h->stream>>>(a);
+      else suews_run_kernel<false, SU_BLOCK_SMALL, SU_MINBLOCKS_SMALL><<<grid, blk, 0, h->stream>>>(a);
+   } else {
+      if (full) suews_run_kernel<true, SU_BLOCK, SU_MINBLOCKS><<<grid, blk, 0, h->stream>>>(a);
+      else suews_run_kernel<false, SU_BLOCK, SU_MINBLOCKS><<<grid, blk, 0, h->stream>>>(a);
+   }
    CUDA_OK(cudaGetLastError());
    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
    h->dt_since_start += nsteps * h->tstep;

@@ -4,7 +4,7 @@ usage: tools/ncu_by_function.py report.ncu-rep library.so [kernel-substring]
 Function address ranges come from the ELF symbol table of the kernel's .text section."""
 import csv, subprocess, sys, io, re
 rep, lib = sys.argv[1], sys.argv[2]
-kern = sys.argv[3] if len(sys.argv) > 3 else "suews_run_kernelILb0"
+kern = sys.argv[3] if len(sys.argv) > 3 else "suews_run_kernelILb0ELi1024ELi1"
 elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
 secidx = None
 for ln in elf.splitlines():

@@ -8,7 +8,7 @@ elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True)
 secidx = None
 for ln in elf.splitlines():
     t = ln.split()
-    if len(t) >= 9 and t[-1] == ".text._Z16suews_run_kernelILb0EEv9SuRunArgs" and "PROGBITS" in ln:
+    if len(t) >= 9 and t[-1] == ".text._Z16suews_run_kernelILb0ELi1024ELi1EEv9SuRunArgs" and "PROGBITS" in ln:
         secidx = "0x" + t[0]
 funcs = []
 for ln in elf.splitlines():
