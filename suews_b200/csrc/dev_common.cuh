@@ -15,21 +15,22 @@
 // real functions (SU_DEV = noinline), the double-precision libm entry points are shared out-of-line
 // wrappers, and only leaf helpers are inlined (SU_INL).
 #define SU_INL __device__ __forceinline__
-#define SU_DEVNI __device__ __noinline__
+// (static: the headers are compiled into two translation units, suews_b200.cu and suews_kernel_small.cu)
+#define SU_DEVNI static __device__ __noinline__
 #if defined(SU_INLINE_ALL) || defined(SU_DEV_INLINE)   // SU_DEV_INLINE: physics routines inlined, libm wrappers still shared
 #define SU_DEV __device__ __forceinline__
 #else
-#define SU_DEV __device__ __noinline__
+#define SU_DEV static __device__ __noinline__
 #endif
 
 // routines the default scheme set never enters (ESTM, biogenic CO2, ice saturation pressure): out of line in every build,
 // so they take no room in the instruction stream of the hot phases
-#define SU_COLD __device__ __noinline__
+#define SU_COLD static __device__ __noinline__
 // the large routines that are called once or twice per step (tuning switch SU_BIG_INLINE)
 #if defined(SU_BIG_INLINE) || defined(SU_INLINE_ALL)
 #define SU_BIG __device__ __forceinline__
 #else
-#define SU_BIG __device__ __noinline__
+#define SU_BIG static __device__ __noinline__
 #endif
 // per-routine switch: SU_BIG_MASK bit k-1 inlines group k (1 cal_Stab, 2 cal_HorizontalSoilWater, 3 NARP + sun position,
 // 4 RSLProfile, 5 cal_psim_hat_zh)

@@ -57,7 +57,7 @@ SU_INL int day_of_week(int date, int month, int year)
 
 // NARP_cal_SunPosition steps 1-10, narp.f95:460-541 + helpers :568-1100.
 // idectime is what the reference passes: dectime - tstep/2 with the INTEGER tstep/2 (driver.f95:689).
-__device__ void spa_time_part(double year, double idectime, double UTC, SuewsEphem &e)
+static __device__ void spa_time_part(double year, double idectime, double UTC, SuewsEphem &e)
 {
    // dectime_to_timevec util_time.f95:202
    int doy = (int)floor(idectime);

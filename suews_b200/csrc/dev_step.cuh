@@ -52,7 +52,7 @@
 // Profiling build only (-DSU_PHASE_CLOCKS): SM cycles per phase, as seen by thread 0 of each block after the
 // phase's barrier (so a phase's time is that of its slowest warp).  tools/prof_run.py prints them.
 #ifdef SU_PHASE_CLOCKS
-__device__ unsigned long long su_phase_clk[16];
+static __device__ unsigned long long su_phase_clk[16];
 #define SU_CLK_DECL long long clk_ = clock64()
 #define SU_CLK(i)                                                              \
    do {                                                                        \
@@ -242,7 +242,7 @@ SU_UNROLL1
 // Advances S by one step.  R: clock + forcing of this step; E: solar ephemeris of this step.
 // `live` is false for padding threads and for cells stopped by a fatal error; they only keep the barriers.
 // Returns the number of Tsurf iterations used.
-__device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
+static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
                           SuewsCellState &S, SuDaily &D, double *acc82, double *acc7, const SuLines &L, SuewsEstmState *ES = nullptr,
                           const double *ts9 = nullptr, unsigned long long last_lo = 0, unsigned long long last_hi = 0,

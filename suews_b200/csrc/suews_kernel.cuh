@@ -1,0 +1,304 @@
+// suews_kernel.cuh -- the timestep kernel of libsuews_b200.so: launch arguments, shared-memory staging helpers and
+// suews_run_kernel<FULL, BLOCK, MINBLOCKS>.  Included by suews_b200.cu (host side + the 1024-thread geometry) and by
+// suews_kernel_small.cu (the 256-thread geometry), so that the two instantiations compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "suews_fields.h"
+#include "dev_step.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// One 1024-thread block per SM (64 registers): all 32 warps of an SM walk the same phase of the step
+// together, which keeps instruction fetch off the critical path, and 32 warps hide the FP64 dependency
+// and local-memory latencies better than 16 warps with 128 registers did (profiles/r1_ncu_notes.md:
+// 512x1 1.01e8, 512x2 1.10e8, 768x2 1.23e8, 1024x1 1.29e8, 1024x2 1.14e8 cell-steps/s).
+#ifndef SU_BLOCK
+#define SU_BLOCK 1024
+#endif
+#ifndef SU_MINBLOCKS
+#define SU_MINBLOCKS 1
+#endif
+#define SU_CHUNK 32   // timesteps staged per bulk copy (32 x 160 B = 5 KB)
+
+struct SuRunArgs {
+   const SuewsClassParams *classes;
+   const int *class_of_cell;
+   const int *tz_of_cell;
+   const int *order;            // thread slot -> cell (cells of similar cost share a warp, see upload)
+   const double *cellp;
+   double *state;
+   const SuewsStepRec *steps;   // already offset to step0
+   const SuewsEphem *ephem;     // [ntz][nsteps_total], offset to step0 inside
+   long long ephem_tz_stride;
+   double *sums;                // [82][stride] or NULL
+   int sum7;                    // 1: accumulate only the seven parity columns (SUEWS_OUT_SUM7)
+   int flux_only;               // 1: SUEWS_OUT_FLUX_ONLY (diagnostics no requested output depends on are skipped)
+   int *fatal;                  // [ncell]
+   unsigned long long *warn;    // [2][stride]
+   long long *iters;            // [ncell]
+   // full output (SUEWS_OUT_FULL): per cell column-major [nsteps x ncol]
+   double *blkSUEWS, *blkSnow, *blkRSL, *blkDaily, *blkSOL, *blkESTM;
+   // ESTM (StorageHeatMethod 4/14): per-cell element temperatures [SUEWS_N_ESTM_DBL][stride] and the shared
+   // surface-temperature forcing [nsteps][SUEWS_N_TS5], offset to step0; NULL when no class runs ESTM
+   double *estm;
+   const double *ts5;
+   // output policy P1 (SUEWS_OUT_AGG): the SUEWS block aggregated over every agg_nlines steps as SUEWS_Output_Agg
+   // does (suews_ctrl_output.f95:912-957), [row][87][stride] indexed by thread slot so that a warp writes 256 B lines
+   double *agg;
+   int agg_nlines;
+   double *agg_daily;           // with agg: one DailyState row per day that ends inside the launch, [row][50][stride] (thread order)
+   int agg_daily_rows;
+   int ncell;
+   long long stride;
+   int nsteps;
+   int dt_since_start, tstep_prev, tstep;
+};
+
+// QN, QF, QS, QH, QE, RO, SWE in the 82-column SUEWS line (0-based)
+// aggregation method of the 82 SUEWS columns (varListAll, suews_ctrl_output.f95:80-166): 0 mean, 1 sum, 2 last
+static __constant__ unsigned char su_agg82[SUEWS_NCOL_SUEWS] = {
+#include "suews_agg82.inc"
+};
+
+__host__ __device__ __forceinline__ int su_parity_col(int i)
+{
+   return i < 5 ? 5 + i : (i == 5 ? 16 : 71);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+
+// A second launch geometry for batches that do not fill the chip with 1024-cell blocks: 256-thread blocks, two per SM
+// (128 registers).  A 10 000-cell batch -- supy's scale -- occupies 40 SMs this way instead of 10.
+#define SU_BLOCK_SMALL 256
+#define SU_MINBLOCKS_SMALL 2
+// defined in suews_kernel_small.cu (its own translation unit, so the two geometries compile side by side)
+cudaError_t suews_launch_small(bool full, int grid, cudaStream_t stream, const struct SuRunArgs &a);
+
+template <bool FULL, int BLOCK, int MINBLOCKS>
+__global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a)
+{
+   __shared__ alignas(128) SuewsStepRec sm_steps[2][SU_CHUNK];
+   __shared__ alignas(8) uint64_t sm_bar[2];
+
+   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool active = slot < a.ncell;
+   const int cell = active ? a.order[slot] : 0;
+   const int nchunk = (a.nsteps + SU_CHUNK - 1) / SU_CHUNK;
+
+   if (threadIdx.x == 0) {
+      mbar_init(&sm_bar[0], 1);
+      mbar_init(&sm_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   if (threadIdx.x == 0 && nchunk > 0) {
+      uint32_t n0 = (uint32_t)min(SU_CHUNK, a.nsteps) * (uint32_t)sizeof(SuewsStepRec);
+      mbar_expect_tx(&sm_bar[0], n0);
+      bulk_g2s(&sm_steps[0][0], a.steps, n0, &sm_bar[0]);
+   }
+
+   // ---- per-thread residents: cell parameters, state, accumulators
+   SuewsCellParams C;
+   SuewsCellState S;
+   SuDiag dg;
+   dg.fatal = 0; dg.warn[0] = 0; dg.warn[1] = 0;
+   double acc[SUEWS_NCOL_SUEWS];
+   double acc7[7] = {0, 0, 0, 0, 0, 0, 0};
+   long long iters = 0;
+   int cls = 0, tz = 0;
+   SuewsEstmState ES;
+   if (active && a.estm) {
+      double *ep = reinterpret_cast<double *>(&ES);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) ep[j] = a.estm[(size_t)j * a.stride + slot];
+   }
+   if (active) {
+      cls = a.class_of_cell[cell];
+      tz = a.tz_of_cell[cell];
+      double *cp = reinterpret_cast<double *>(&C);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_CELL_DBL; j++) cp[j] = a.cellp[(size_t)j * a.stride + slot];   // slot order: coalesced
+      double *sp = reinterpret_cast<double *>(&S);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) sp[j] = a.state[(size_t)j * a.stride + slot];
+      dg.fatal = a.fatal[cell];
+      dg.warn[0] = a.warn[cell];
+      dg.warn[1] = a.warn[a.stride + cell];
+      if (a.agg) {
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = 0.0;
+      } else if (a.sums && !a.sum7) {
+#pragma unroll 1
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = a.sums[(size_t)c * a.stride + cell];
+      } else if (a.sums) {
+         for (int c = 0; c < 7; c++) acc7[c] = a.sums[(size_t)su_parity_col(c) * a.stride + cell];
+      }
+   }
+   // "last value" columns as a bit mask; only the aggregating policy overwrites instead of summing
+   unsigned long long last_lo = 0, last_hi = 0;
+   if (a.agg)
+      for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
+         if (su_agg82[c] == 2) { if (c < 64) last_lo |= 1ull << c; else last_hi |= 1ull << (c - 64); }
+   // the daily state lives in its own record for the length of the launch (dev_step.cuh, stage_pre_atm)
+   SuDaily D;
+   for (int i = 0; i < 12; i++) D.HDD_id[i] = S.HDD_id[i];
+   for (int i = 0; i < 3; i++) { D.GDD_id[i] = S.GDD_id[i]; D.SDD_id[i] = S.SDD_id[i]; D.LAI_id[i] = S.LAI_id[i]; }
+   for (int i = 0; i < 9; i++) D.WUDay_id[i] = S.WUDay_id[i];
+   D.Tmin_id = S.Tmin_id; D.Tmax_id = S.Tmax_id; D.lenDay_id = S.lenDay_id; D.DecidCap_id = S.DecidCap_id;
+   D.albDecTr_id = S.albDecTr_id; D.albEveTr_id = S.albEveTr_id; D.albGrass_id = S.albGrass_id; D.porosity_id = S.porosity_id;
+   D.DecidStoreCap = SU_SDP(S.StoreDrainPrm.v, 5, DECID);
+   D.deltaLAI = 0;
+   const SuewsClassParams &P = a.classes[cls];
+   const SuewsEphem *eph = a.ephem + (size_t)tz * a.ephem_tz_stride;
+   int dt_since_start = a.dt_since_start;
+   int tstep_prev = a.tstep_prev;
+   int n_day_rows = 0;
+
+   for (int ch = 0; ch < nchunk; ch++) {
+      const int buf = ch & 1;
+      // prefetch the next chunk into the other buffer (its readers finished at the previous barrier)
+      if (threadIdx.x == 0 && ch + 1 < nchunk) {
+         int s1 = (ch + 1) * SU_CHUNK;
+         uint32_t n1 = (uint32_t)min(SU_CHUNK, a.nsteps - s1) * (uint32_t)sizeof(SuewsStepRec);
+         mbar_expect_tx(&sm_bar[buf ^ 1], n1);
+         bulk_g2s(&sm_steps[buf ^ 1][0], a.steps + s1, n1, &sm_bar[buf ^ 1]);
+      }
+      mbar_wait(&sm_bar[buf], (uint32_t)((ch >> 1) & 1));
+      const int s0 = ch * SU_CHUNK;
+      const int ns = min(SU_CHUNK, a.nsteps - s0);
+      for (int t = 0; t < ns; t++) {
+         const int gs = s0 + t;
+         const bool live = active && dg.fatal == 0;
+         SuLines L;
+         L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr; L.sol26 = nullptr;
+         L.estm27 = nullptr;
+         double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY], l_so[SUEWS_NCOL_SOLWEIG];
+         double l_es[SUEWS_NCOL_ESTM];
+         if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; L.estm27 = l_es; }
+         // policy P1 also keeps the DailyState line, which only exists on the last step of a day (dailystate.f95:1094)
+         const bool day_end = a.agg_daily && (sm_steps[buf][t].it * 3600 + sm_steps[buf][t].imin * 60 + a.tstep) >= 86400;
+         if (day_end) L.daily45 = l_da;
+         // every thread of the block enters the step (phase barriers inside); only live cells compute
+         iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S, D,
+                             (a.agg || (a.sums && !a.sum7)) ? acc : nullptr, (!a.agg && a.sums && a.sum7) ? acc7 : nullptr, L,
+                             a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
+                             a.flux_only != 0);
+         if (day_end) {
+            if (live && dg.fatal == 0 && n_day_rows < a.agg_daily_rows) {
+               const SuewsStepRec &R = sm_steps[buf][t];
+               double *o = a.agg_daily + (size_t)n_day_rows * (SUEWS_NCOL_DAILY + 5) * (size_t)a.stride + slot;
+               o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
+               o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
+#pragma unroll 1
+               for (int c = 0; c < SUEWS_NCOL_DAILY; c++) o[(size_t)(5 + c) * a.stride] = l_da[c];
+            }
+            n_day_rows++;
+         }
+         if (a.agg && (gs + 1) % a.agg_nlines == 0) {   // SUEWS_Output_Agg: rows i-nlinesOut+1 .. i -> row i/nlinesOut
+            if (live && dg.fatal == 0) {
+               const SuewsStepRec &R = sm_steps[buf][t];
+               double *o = a.agg + (size_t)((gs + 1) / a.agg_nlines - 1) * (SUEWS_NCOL_SUEWS + 5) * (size_t)a.stride + slot;
+               o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
+               o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
+#pragma unroll 1
+               for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
+                  o[(size_t)(5 + c) * a.stride] = (su_agg82[c] == 0) ? acc[c] / a.agg_nlines : acc[c];
+            }
+            for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = 0.0;
+         }
+         if (FULL && live && dg.fatal == 0) {
+            const size_t n = (size_t)a.nsteps;
+            double *b;
+            b = a.blkSUEWS + (size_t)cell * n * (SUEWS_NCOL_SUEWS + 5);
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) b[gs + n * (5 + c)] = l_su[c];
+            b = a.blkRSL + (size_t)cell * n * (SUEWS_NCOL_RSL + 5);
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_RSL; c++) b[gs + n * (5 + c)] = l_rs[c];
+            b = a.blkDaily + (size_t)cell * n * (SUEWS_NCOL_DAILY + 5);
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_DAILY; c++) b[gs + n * (5 + c)] = l_da[c];
+            b = a.blkSOL + (size_t)cell * n * (SUEWS_NCOL_SOLWEIG + 5);   // SUEWS_update_output with set_nan, driver.f95:2497
+            for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+            for (int c = 0; c < SUEWS_NCOL_SOLWEIG; c++) b[gs + n * (5 + c)] = (fabs(l_so[c]) > 30000) ? -999.0 : l_so[c];
+            // the reference stores the ESTM line for StorageHeatMethod 4 only (driver.f95:2503-2505); the line itself is
+            // also formed for 14 and is kept here for both (the reference-shaped block call filters on 4)
+            if ((P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14) && a.blkESTM) {
+               b = a.blkESTM + (size_t)cell * n * (SUEWS_NCOL_ESTM + 5);
+               for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+               for (int c = 0; c < SUEWS_NCOL_ESTM; c++) b[gs + n * (5 + c)] = (fabs(l_es[c]) > 30000) ? -999.0 : l_es[c];
+            }
+            if (P.snowUse == 1) {   // SUEWS_update_output, driver.f95:2499-2501 (with set_nan :2737)
+               b = a.blkSnow + (size_t)cell * n * (SUEWS_NCOL_SNOW + 5);
+               for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+               for (int c = 0; c < SUEWS_NCOL_SNOW; c++) b[gs + n * (5 + c)] = (fabs(l_sn[c]) > 30000) ? -999.0 : l_sn[c];
+            }
+         }
+         dt_since_start += a.tstep;   // caller-side clock, driver.f95:3483
+         tstep_prev = a.tstep;
+      }
+      __syncthreads();   // everyone is done with buffer `buf` before it is refilled two chunks later
+   }
+
+   if (active) {
+      for (int i = 0; i < 12; i++) S.HDD_id[i] = D.HDD_id[i];
+      for (int i = 0; i < 3; i++) { S.GDD_id[i] = D.GDD_id[i]; S.SDD_id[i] = D.SDD_id[i]; S.LAI_id[i] = D.LAI_id[i]; }
+      for (int i = 0; i < 9; i++) S.WUDay_id[i] = D.WUDay_id[i];
+      S.Tmin_id = D.Tmin_id; S.Tmax_id = D.Tmax_id; S.lenDay_id = D.lenDay_id; S.DecidCap_id = D.DecidCap_id;
+      S.albDecTr_id = D.albDecTr_id; S.albEveTr_id = D.albEveTr_id; S.albGrass_id = D.albGrass_id; S.porosity_id = D.porosity_id;
+      double *sp = reinterpret_cast<double *>(&S);
+#pragma unroll 1
+      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + slot] = sp[j];
+      if (a.estm) {
+         double *ep = reinterpret_cast<double *>(&ES);
+#pragma unroll 1
+         for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) a.estm[(size_t)j * a.stride + slot] = ep[j];
+      }
+      a.fatal[cell] = dg.fatal;
+      a.warn[cell] = dg.warn[0];
+      a.warn[a.stride + cell] = dg.warn[1];
+      a.iters[cell] += iters;
+      if (a.agg) {
+         // partial periods at the end of a block are dropped, as INT(irMax/nlinesOut) drops them
+      } else if (a.sums && !a.sum7) {
+#pragma unroll 1
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) a.sums[(size_t)c * a.stride + cell] = acc[c];
+      } else if (a.sums) {
+         for (int c = 0; c < 7; c++) a.sums[(size_t)su_parity_col(c) * a.stride + cell] = acc7[c];
+      }
+   }
+}
+
