@@ -69,7 +69,7 @@ int suews_b200_destroy(suews_b200_handle h);
 /* Parameters by reference argument name (case-insensitive; driver.f95:45-91).  Integer-typed
  * arguments are passed as doubles holding integral values.  Class fields: one class at a time.
  * Cell fields and state: vals is [ncell][n] (cell-major).  suews_b200_field_info reports where a
- * name lives: kind 0 = class int, 1 = class double, 2 = per-cell double, 3 = state; returns n or -1. */
+ * name lives: kind 0 = class int, 1 = class double, 2 = per-cell double, 3 = state, 4 = ESTM state; returns n or -1. */
 int suews_b200_field_info(const char *name, int *kind);
 int suews_b200_set_class_param(suews_b200_handle h, int cls, const char *name, const double *vals, int n);
 int suews_b200_set_cell_param(suews_b200_handle h, const char *name, const double *vals, int n);
@@ -121,7 +121,8 @@ int suews_b200_sync(suews_b200_handle h);
 /* Output policy P1.  set_output_freq: ResolutionFilesOut in seconds (default 3600); every advance with SUEWS_OUT_AGG
  * aggregates its own rows [step0, step0 + nsteps) into INT(nsteps / nlinesOut) rows (a trailing partial period is
  * dropped, as in the reference).  get_agg_block: one cell's [nrows x 87] block, column-major, datetime columns =
- * the last step of each period (rows a cell did not reach because it stopped on a fatal error are NaN); get_agg_column: one column (0-based, 0-4 datetime) of one row for all cells. */
+ * the last step of each period (rows a cell did not reach because it stopped on a fatal error are NaN);
+ * get_agg_column: one column (0-based, 0-4 datetime) of one row for all cells. */
 int suews_b200_set_output_freq(suews_b200_handle h, int out_freq_s);
 int suews_b200_get_agg_block(suews_b200_handle h, int cell, double *block, int nrows);
 int suews_b200_get_agg_column(suews_b200_handle h, int row, int col, double *vals);
