@@ -14,7 +14,7 @@ for ln in elf.splitlines():
     t = ln.split()
     if len(t) >= 7 and t[5] == secidx and t[3] in ("0x2", "0x22", "0x12"):
         try:
-            funcs.append((int(t[1], 16), int(t[2], 16), re.sub(r"^\$_Z16\w+?SuRunArgs\$", "", t[6])))
+            funcs.append((int(t[1], 16), int(t[2], 16), re.sub(r"_ZN\d+_INTERNAL_[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]{8}", "_Z", re.sub(r"^\$_Z16\w+?SuRunArgs\$", "", t[6]))))
         except ValueError:
             pass
 target = [f for f in funcs if callee in f[2]][0]
