@@ -257,10 +257,11 @@ def main():
         if i == W:
             barrier()
             e2e_t0 = time.perf_counter()
-        day = met[(W + K + i) * 288:(W + K + i + 1) * 288]
+        d0 = (W + K + i) % (met.shape[0] // 288)    # (wraps when the device-resident region already used the whole series)
+        day = met[d0 * 288:(d0 + 1) * 288]
         b.set_forcing(day)                      # host -> device (pinned staging) + ephemeris kernel
         if use_estm:
-            b.set_estm_forcing(ts5[(W + K + i) * 288:(W + K + i + 1) * 288])
+            b.set_estm_forcing(ts5[d0 * 288:(d0 + 1) * 288])
         b.advance(0, 288, OUT, sync=False)
         if a.sums == "hourly":                  # device -> host: the last hour's QN..QE maps of all cells
             res = np.stack([b.agg_column(23, 5 + c) for c in cols], axis=1)
