@@ -236,3 +236,17 @@ def test_generated_fortran_driver_interface_matches_the_argument_table():
         m = re.search(r"SUBROUTINE %s\(([^)]*)\)\s*BIND\(C, name='%s'\)" % (sub, cname), f90)
         names = [a.strip() for a in m.group(1).split(",")]
         assert names == [r[0] for r in arg_table(which)]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-budget", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "cell_timesteps_per_s" and line["unit"] == "cell-timesteps/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["dtype"] == "f64"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
