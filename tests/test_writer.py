@@ -97,3 +97,26 @@ def test_rsl_rows_are_identical(run2005):
     gold = open(os.path.join(fx.GOLDEN, "ref_2005_RSL_60.txt")).read().splitlines()
     ours = _write_txt(_agg(run2005["RSL"], "RSL"), "RSL", outlevel=2).splitlines()
     assert len(ours) == len(gold) and ours[1:] == gold[1:]
+
+
+def test_real_fields_follow_fw_d_editing_on_random_values():
+    """Fw.d: correctly rounded decimal, right-aligned, asterisks when the value does not fit (same rounding as the C
+    library's %w.df, which the reference files confirm above)"""
+    rng = np.random.default_rng(7)
+    vals = np.concatenate([rng.normal(0, 50, 300), rng.normal(0, 1e-3, 100), 10.0 ** rng.uniform(-8, 7, 200) * rng.choice([-1, 1], 200),
+                           [0.0, -0.0, 0.00005, -0.00005, 99999.99995, 9999.99995, -9999.99995, 0.5, 1e300, -1e300]])
+    blk = np.zeros((vals.size, 87))
+    blk[:, :5] = [2005, 1, 1, 0, 0.5]
+    blk[:, 5] = vals          # Kdown   f10.4
+    blk[:, 5 + 17] = vals     # TotCh   f14.6
+    rows = _write_txt(blk, "SUEWS", outlevel=2, header=False).splitlines()
+    for v, ln in zip(vals, rows):
+        assert ln[:24] == "2005    1    1    0   0.5000"[:24]
+        f104, f146 = ln[29:39], None
+        want = "%10.4f" % v
+        assert f104 == (want if len(want) == 10 else "*" * 10), (v, f104, want)
+        # locate the f14.6 field: 5 datetime fields (4+1)*4 + 8+1, then 17 fields of 11 characters
+        start = 29 + 17 * 11
+        f146 = ln[start:start + 14]
+        want = "%14.6f" % v
+        assert f146 == (want if len(want) == 14 else "*" * 14), (v, f146, want)
