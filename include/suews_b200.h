@@ -53,9 +53,12 @@ enum {
    SUEWS_OUT_FULL = 2,    /* keep every output block of every step (reference SUEWS_cal_multitsteps semantics) */
    SUEWS_OUT_SUM7 = 4,    /* accumulate only the seven parity fluxes QN, QF, QS, QH, QE, RO, SWE (columns 5-9, 16, 71
                              of the same [ncell][82] sums array; the other columns are left untouched) */
-   SUEWS_OUT_FLUX_ONLY = 16, /* with SUEWS_OUT_SUM7 only: skip the stages whose results the seven flux sums and the state do
-                             not depend on -- the roughness-sublayer diagnostics T2/q2/U10/RH2 (RSLProfile feeds nothing
-                             back, driver.f95:943-949).  Off by default: every launch does the reference's full work. */
+   SUEWS_OUT_FLUX_ONLY = 16, /* kept for callers of the first release: this is now what SUEWS_OUT_SUM7 alone does */
+   SUEWS_OUT_ALL_STAGES = 32, /* A launch evaluates the stages its requested outputs (and the state) depend on.  Policy P0
+                             (SUEWS_OUT_SUM7 alone) requests seven flux sums: the roughness-sublayer diagnostics T2 / q2 /
+                             U10 / RH2 (RSLProfile, driver.f95:943-949) feed neither those nor the state and are skipped,
+                             unless a class runs EmissionsMethod >= 11, whose biogenic CO2 reads the modelled 2 m
+                             temperature.  This bit makes such a launch run every stage of SUEWS_cal_Main regardless. */
    SUEWS_OUT_AGG = 8      /* output policy P1: the SUEWS block aggregated to the output frequency (default hourly) inside
                              the kernel, as SUEWS_Output_Agg does after the run (suews_ctrl_output.f95:912-957: mean /
                              sum / last value per column as varListAll says); exclusive with the running sums */
@@ -117,6 +120,14 @@ int suews_b200_get_estm_forcing_block(suews_b200_handle h, double *ts_fast, int 
 /* Advance all cells over forcing rows [step0, step0 + nsteps).  One kernel launch.  Asynchronous
  * with respect to the host; suews_b200_sync waits and returns the first fatal cell error (0 if none). */
 int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags);
+/* A setter called after an advance keeps the run: the host copy of the state is refreshed from the device first, and the
+ * running sums and per-cell diagnostics carry over the re-upload.  suews_b200_restart forgets the run instead (fresh sums
+ * and diagnostics, state as set by the caller) -- what the reference-shaped calls do with their resident handle. */
+int suews_b200_restart(suews_b200_handle h);
+/* tstep_prev seen by the steps of a launch (SUEWS_cal_DailyState's first-step-of-day test, dailystate.f95:266): rolls = 1
+ * (default) -> tstep after the first step of a run; rolls = 0 -> the set_clock value for every step, as
+ * SUEWS_cal_multitsteps passes its INTENT(IN) tstep_prev to every SUEWS_cal_Main call (driver.f95:3445). */
+int suews_b200_set_tstep_prev_rolls(suews_b200_handle h, int rolls);
 int suews_b200_sync(suews_b200_handle h);
 /* Output policy P1.  set_output_freq: ResolutionFilesOut in seconds (default 3600); every advance with SUEWS_OUT_AGG
  * aggregates its own rows [step0, step0 + nsteps) into INT(nsteps / nlinesOut) rows (a trailing partial period is
@@ -209,6 +220,10 @@ long long suews_write_initial_conditions(const double *v54, int snow_use, char *
 /* Diagnostic: compares the library's own exp/log (suews_b200/csrc/dev_math.cuh) with the CUDA math library
  * bit for bit on n pseudo-random arguments; returns the mismatch counts (expected 0 and 0). */
 int suews_b200_selftest_math(long long n, unsigned long long seed, long long *bad_exp, long long *bad_log);
+/* Diagnostic: the wet-bulb search of Lat_vap (suews_util_meteo.f95:277-346) with its single-precision screening of the
+ * three-way decision against the plain loop, on n pseudo-random (Temp_C, RH, Press, cp, switch state) tuples; returns the
+ * number of tuples whose latent heat, exit switches or warnings differ (expected 0). */
+int suews_b200_selftest_latvap(long long n, unsigned long long seed, long long *bad);
 
 /* last error of the calling thread: code and human-readable message */
 int suews_last_error(int *code, char *buf, int len);

@@ -15,7 +15,8 @@ NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50, "SOLWEIG": 31, "
 OUT_SUM82 = 1
 OUT_FULL = 2
 OUT_SUM7 = 4   # only the seven parity fluxes (output policy P0)
-OUT_FLUX_ONLY = 16   # with OUT_SUM7: skip diagnostics the flux sums and the state do not depend on (opt-in)
+OUT_FLUX_ONLY = 16   # (first release; OUT_SUM7 alone now skips the diagnostics its seven sums cannot observe)
+OUT_ALL_STAGES = 32  # with OUT_SUM7: run every stage of SUEWS_cal_Main anyway (T2/q2/U10/RH2 included)
 OUT_AGG = 8    # SUEWS block aggregated to the output frequency inside the kernel (output policy P1)
 
 KIND_CLASS_INT, KIND_CLASS_DBL, KIND_CELL, KIND_STATE, KIND_ESTM_STATE = 0, 1, 2, 3, 4

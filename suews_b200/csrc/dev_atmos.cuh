@@ -101,7 +101,25 @@ SU_DEV double qa2RH(double qa_gkg, double pres_hPa, double Ta_degC)
 
 // suews_util_meteo.f95:277-346.  The reference keeps switch1/switch2 in implicit-SAVE locals, so
 // their exit values seed the next call; here they are per-cell state (sw = switch1 | switch2 << 1).
-SU_INL double Lat_vap(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
+//
+// The wet-bulb search takes ~21 trips on the bench forcing, each with a full sat_vap_press (EXP) and a division, and
+// all it keeps of them is a three-way decision: |ea_est - ea_fix| < 0.001, ea_est above, ea_est below.  The result
+// (tw, hence lv, and the two switches) depends on those decisions only.  So each trip first forms ea_est in single
+// precision (fast intrinsics; relative error <= ~1.5e-6 of the terms' magnitudes) and takes the decision from it when it clears the 0.001
+// threshold by a margin several times that error; only the last one to three trips, where the estimate is within a few
+// thousandths of a hPa of the target, evaluate the reference expression in double.  Same decisions, same tw sequence
+// (the additions tw +- incr are the reference's), same bits (checked against the plain loop on random arguments by
+// suews_b200_selftest_latvap).  SU_LATVAP_PLAIN builds the plain loop.
+SU_INL float su_es_single(float T, float Press_kPa)
+{
+   const bool w = (T >= 0.001f);
+   const float c0 = w ? 6.1121f : 6.1115f, c1 = w ? 18.678f : 23.036f, c2 = w ? 234.5f : 333.7f, c3 = w ? 257.14f : 279.82f,
+               f0 = w ? 1.00072f : 1.00022f, f1 = w ? 3.2E-6f : 3.83E-6f, f2 = w ? 5.9E-10f : 6.4E-10f;
+   // fast intrinsics (MUFU): __expf <= 6 ulp for arguments below 4, __fdividef <= 2 ulp
+   return (c0 * __expf(__fdividef((c1 - __fdividef(T, c2)) * T, T + c3))) * (f0 + Press_kPa * (f1 + f2 * (T * T)));
+}
+template <bool PLAIN>
+SU_INL double Lat_vap_t(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
 {
    bool switch1 = (sw & 1) != 0, switch2 = (sw & 2) != 0;
    const double ea_fix = Ea_hPa;
@@ -109,28 +127,53 @@ SU_INL double Lat_vap(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa
    double tw = Temp_C / F(2.);
    double incr = F(3.);
    if (Press_hPa < 900) su_warn(dg, 45);
+   const float Tf = (float)Temp_C, eaf = (float)Ea_hPa, pkf = (float)(Press_hPa / 10), cpPf = (float)(cp * Press_hPa);
    for (int ii = 1; ii <= 100; ii++) {
-      double es_tw = sat_vap_press_x(dg, tw, Press_hPa, 2);
-      double psyc = psyc_const(dg, cp, Press_hPa, lv_J_kg);
-      double ea_est = es_tw - psyc * (Temp_C - tw);
+      int dec = 2;   // 0: within 0.001, 1: ea_est above, -1: below, 2: not decided yet
+      if (!PLAIN && tw < 49 && tw > -39 && !(fabs(tw) < F(0.001000))) {
+         const float twf = (float)tw;
+         const float es_a = su_es_single(twf, pkf);
+         const float pt_a = __fdividef(cpPf, 0.62197f * (float)lv_J_kg) * (Tf - twf);
+         const float d = (es_a - pt_a) - eaf;
+         const float margin = 0.002f + 8e-6f * (fabsf(es_a) + fabsf(pt_a) + fabsf(eaf));
+         if (d > margin) dec = 1;
+         else if (d < -margin) dec = -1;
+         if (dec != 2) {   // the side effects of the calls not made: warnings 28 (never: tw is in range here) and 19
+            if (cp * Press_hPa < 900 || lv_J_kg < 10000) su_warn(dg, 19);
+         }
+      }
+      if (dec == 2) {
+         double es_tw = sat_vap_press_x(dg, tw, Press_hPa, 2);
+         double psyc = psyc_const(dg, cp, Press_hPa, lv_J_kg);
+         double ea_est = es_tw - psyc * (Temp_C - tw);
+         dec = (fabs(ea_est - ea_fix) < F(0.001000)) ? 0 : ((ea_est > ea_fix) ? 1 : ((ea_est < ea_fix) ? -1 : 3));
+      }
       lv_J_kg = (F(2500.25) - F(2.365) * tw) * F(1e3);
       if (switch1 && switch2) {
          incr = incr / F(10.);
          switch1 = false;
          switch2 = false;
       }
-      if (fabs(ea_est - ea_fix) < F(0.001000)) {
+      if (dec == 0) {
          break;
-      } else if (ea_est > ea_fix) {
+      } else if (dec == 1) {
          tw = tw - incr;
          switch1 = true;
-      } else if (ea_est < ea_fix) {
+      } else if (dec == -1) {
          tw = tw + incr;
          switch2 = true;
       }
    }
    sw = (switch1 ? 1 : 0) | (switch2 ? 2 : 0);
    return lv_J_kg;
+}
+SU_INL double Lat_vap(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
+{
+#ifdef SU_LATVAP_PLAIN
+   return Lat_vap_t<true>(dg, Temp_C, Ea_hPa, Press_hPa, cp, sw);
+#else
+   return Lat_vap_t<false>(dg, Temp_C, Ea_hPa, Press_hPa, cp, sw);
+#endif
 }
 
 struct SuAtm {
@@ -272,8 +315,8 @@ SU_INL double stab_phi_heat(int sm, double zl)
 }
 
 // atmmoiststab.f95:104-248: fixed-point iteration for the Obukhov length (<= 329 trips).
-// log(zzd/z0m) is loop-invariant and evaluated once.
-SU_BIG1 void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double avU1, double Temp_C, double QH_init,
+// log(zzd/z0m) is step-invariant: evaluated once per step by the caller (lg).
+SU_BIG1 void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double lg, double avU1, double Temp_C, double QH_init,
                        double avdens, double avcp, double &L_MOD_out, double &TStar_out, double &UStar_out, double &zL_out)
 {
    // the iteration runs on register copies; the by-reference results (stack slots of the caller) are written once
@@ -282,7 +325,10 @@ SU_BIG1 void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double avU1, d
    double G_T_K = (grav / (Temp_C + F(273.16))) * k;
    double KUZ = k * avU1;
    if (zzd < 0) su_fatal(dg, 32);
-   const double lg = log(zzd / z0m);
+   // lg = log(zzd / z0m): the same for every trip of the step, evaluated once by the caller
+#ifdef SU_NO_LG_HOIST
+   lg = log(zzd / z0m);
+#endif
    double UStar = KUZ / lg;
    double h = (fabs(H_init) < F(0.001)) ? F(0.001) : H_init;
    double TStar = (-h / UStar);
@@ -316,14 +362,15 @@ SU_BIG1 void cal_Stab(SuDiag &dg, int sm, double zzd, double z0m, double avU1, d
 
 // ------------------------------------------------------------------ resistances
 // resist.f95:514-551
-SU_DEV double cal_z0V(int RoughLenHeatMethod, double z0m, double VegFraction, double UStar)
+// veg029 = VegFraction**0.29 (a site constant, evaluated once per launch)
+SU_DEV double cal_z0V(int RoughLenHeatMethod, double z0m, double VegFraction, double veg029, double UStar)
 {
    const double muu = F(1.46e-5);
    double z0V = F(0.01);
    if (RoughLenHeatMethod == 1) {
       z0V = z0m / 10;
    } else if (RoughLenHeatMethod == 2 || (RoughLenHeatMethod == 5 && !(VegFraction > F(.999)))) {
-      z0V = z0m * exp(2 - (F(1.2) - F(0.9) * pow(VegFraction, F(0.29))) * pow(UStar * z0m / muu, F(0.25)));
+      z0V = z0m * exp(2 - (F(1.2) - F(0.9) * veg029) * pow(UStar * z0m / muu, F(0.25)));
    } else if (RoughLenHeatMethod == 3) {
       z0V = z0m * 0x1.1b4866p-29;   // EXP(-20.) folded in REAL(4) by the reference compiler
    } else if (RoughLenHeatMethod == 4) {
@@ -335,25 +382,31 @@ SU_DEV double cal_z0V(int RoughLenHeatMethod, double z0m, double VegFraction, do
 }
 
 // resist.f95:5-104.  psim/psih for method 2 are passed in when already known (same zL for RA and RAsnow).
-SU_DEV double AerodynamicResistance(SuDiag &dg, double ZZD, double z0m, double AVU1, double L_mod, double UStar,
-                                    double VegFraction, int ARMethod, int sm, int RoughLenHeatMethod)
+SU_DEV double AerodynamicResistance(SuDiag &dg, double ZZD, double z0m, double lg_zz0, double AVU1, double L_mod, double UStar,
+                                    double VegFraction, double veg029, int ARMethod, int sm, int RoughLenHeatMethod)
 {
    const double k2 = F(0.16);
    double RA = 0;
    if (ARMethod == 1) {
-      double lg = log(ZZD / z0m);
+      double lg = lg_zz0;   // log(ZZD / z0m)
       RA = (lg * lg) / (k2 * AVU1);
    } else if (ARMethod == 2) {
       double psim = stab_psi_mom_v(sm, ZZD / L_mod);
       double psih = stab_psi_heat(sm, ZZD / L_mod);
-      double z0V = cal_z0V(RoughLenHeatMethod, z0m, VegFraction, UStar);
+#ifdef SU_NO_SITE_HOIST
+      veg029 = pow(VegFraction, F(0.29));
+#endif
+#ifdef SU_NO_LG_HOIST
+      lg_zz0 = log(ZZD / z0m);
+#endif
+      double z0V = cal_z0V(RoughLenHeatMethod, z0m, VegFraction, veg029, UStar);
       if (ZZD / L_mod == 0 || UStar == 0) {
-         RA = (log(ZZD / z0m) * log(ZZD / z0V)) / (k2 * AVU1);
+         RA = (lg_zz0 * log(ZZD / z0V)) / (k2 * AVU1);
       } else {
-         RA = ((log(ZZD / z0m) - psim) * (log(ZZD / z0V) - psih)) / (k2 * AVU1);
+         RA = ((lg_zz0 - psim) * (log(ZZD / z0V) - psih)) / (k2 * AVU1);
       }
    } else if (ARMethod == 3) {
-      double lg = log(ZZD / z0m);
+      double lg = lg_zz0;
       RA = (F(4.72) * (lg * lg)) / (1 + F(0.54) * AVU1);
    }
    if (RA > 200) {

@@ -177,14 +177,24 @@ static __device__ void spa_time_part(double year, double idectime, double UTC, S
 }
 
 // NARP_cal_SunPosition steps 11-14, narp.f95:1086-1217.  COS(altitude*pi/180) in x is the reference's.
-SU_BIG3 void spa_location_part(const SuewsEphem &e, double lat, double lng, double alt, double &sunazimuth,
-                                double &sunzenith)
+// The observer terms of the parallax step (narp.f95:1105-1119) and sin/cos of the latitude depend on the site only:
+// SuSpaSite holds them, evaluated once per launch with the reference's expressions (6 sin/cos + tan + atan per step saved).
+struct SuSpaSite {
+   double x, y, sin_lat, cos_lat;
+};
+SU_DEV void spa_site_part(double lat, double alt, SuSpaSite &s)
+{
+   double u = atan(F(0.99664719) * tan(lat * SU_PI / 180));
+   s.x = cos(u) + ((alt / 6378140) * cos(alt * SU_PI / 180));
+   s.y = (0.99664719 * sin(u)) + ((alt / 6378140) * sin(lat * SU_PI / 180));
+   s.sin_lat = sin(lat * SU_PI / F(180.0));
+   s.cos_lat = cos(lat * SU_PI / F(180.0));
+}
+SU_BIG3 void spa_location_part(const SuewsEphem &e, const SuSpaSite &s, double lng, double &sunazimuth, double &sunzenith)
 {
    double obs_hour = set_to_range(e.app_stime + lng - e.sun_ra);
    double eq_par = F(8.794) / (3600 * e.eh_rad);
-   double u = atan(F(0.99664719) * tan(lat * SU_PI / 180));
-   double x = cos(u) + ((alt / 6378140) * cos(alt * SU_PI / 180));
-   double y = (0.99664719 * sin(u)) + ((alt / 6378140) * sin(lat * SU_PI / 180));
+   const double x = s.x, y = s.y;
    double sin_par = sin(eq_par * SU_PI / F(180.0));
    double sin_h = sin(obs_hour * SU_PI / F(180.0)), cos_h = cos(obs_hour * SU_PI / F(180.0));
    double sin_d = sin(e.sun_dec * SU_PI / F(180.0)), cos_d = cos(e.sun_dec * SU_PI / F(180.0));
@@ -197,7 +207,7 @@ SU_BIG3 void spa_location_part(const SuewsEphem &e, double lat, double lng, doub
    double topo_dec = atan2(num, den) * F(180.0) / SU_PI;
    double topo_hour = obs_hour - topo_ra_par;
 
-   double sin_lat = sin(lat * SU_PI / F(180.0)), cos_lat = cos(lat * SU_PI / F(180.0));
+   const double sin_lat = s.sin_lat, cos_lat = s.cos_lat;
    double sin_th = sin(topo_hour * SU_PI / F(180.0)), cos_th = cos(topo_hour * SU_PI / F(180.0));
    double argument = (sin_lat * sin(topo_dec * SU_PI / F(180.0))) + (cos_lat * cos(topo_dec * SU_PI / F(180.0)) * cos_th);
    double corr_elev = asin(argument) * F(180.0) / SU_PI;
@@ -207,6 +217,12 @@ SU_BIG3 void spa_location_part(const SuewsEphem &e, double lat, double lng, doub
    num = sin_th;
    den = (cos_th * sin_lat) - (tan(topo_dec * SU_PI / F(180.0)) * cos_lat);
    sunazimuth = set_to_range((atan2(num, den) * F(180.0) / SU_PI) + F(180.0));
+}
+SU_INL void spa_location_part(const SuewsEphem &e, double lat, double lng, double alt, double &sunazimuth, double &sunzenith)
+{
+   SuSpaSite s;
+   spa_site_part(lat, alt, s);
+   spa_location_part(e, s, lng, sunazimuth, sunzenith);
 }
 
 // ------------------------------------------------------------------ NARP

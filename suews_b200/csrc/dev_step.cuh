@@ -36,10 +36,18 @@
 #define SU_UNROLL1 _Pragma("unroll 1")
 #endif
 
-#ifdef SU_PHASE_SYNC
+#if defined(SU_PHASE_SYNC) && defined(SU_WARP_LOOP)
+// the surface-temperature loop is warp-uniform: a warp leaves it as soon as its own 32 cells have converged and waits
+// at the barrier behind the loop; the phases inside the loop carry no block barrier (they are one ~40 KB code region)
+#define SU_SYNC() __syncthreads()
+#define SU_SYNC_OR(p) __any_sync(0xffffffffu, (p))
+#define SU_SYNC_LOOP() ((void)0)
+#elif defined(SU_PHASE_SYNC)
 #define SU_SYNC() __syncthreads()
 #define SU_SYNC_OR(p) __syncthreads_or(p)
+#define SU_SYNC_LOOP() __syncthreads()
 #else
+#define SU_SYNC_LOOP() ((void)0)
 #define SU_SYNC() ((void)0)
 #define SU_SYNC_OR(p) (p)
 #endif
@@ -48,6 +56,7 @@
 #define SU_NOSYNC_MASK 0
 #endif
 #define SU_SYNCN(k) do { if (!((SU_NOSYNC_MASK >> (k)) & 1)) SU_SYNC(); } while (0)
+#define SU_SYNCL(k) do { if (!((SU_NOSYNC_MASK >> (k)) & 1)) SU_SYNC_LOOP(); } while (0)
 
 // Profiling build only (-DSU_PHASE_CLOCKS): SM cycles per phase, as seen by thread 0 of each block after the
 // phase's barrier (so a phase's time is that of its slowest warp).  tools/prof_run.py prints them.
@@ -118,7 +127,7 @@ SU_DEV void stage_pre_atm(SuDiag &dg, const SuewsClassParams &P, const SuewsCell
 }
 
 // Tsurf-independent stages that follow cal_AtmMoist (driver.f95:727-755, :827-834 and SurfaceResistance of :838)
-SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, const SuewsStepRec &R,
+SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, int snowUse, const SuewsCellParams &C, const SuewsStepRec &R,
                            const SuewsCellState &S, const SuAtm &A, int DLS, int nsh, double nsh_real, double Temp_C,
                            double NonWaterFraction, const double *SnowFrac_res, SuHoist &H, const SuDaily &D)
 {
@@ -145,12 +154,12 @@ SU_UNROLL1
       H.drain_per_tstep = 0;
    }
    H.drain[WATER] = 0;
-   ReDistributeWater(P.snowUse, P.WaterDist.v, sfr, H.drain, H.AddWaterRunoff, H.AddWater);
+   ReDistributeWater(snowUse, P.WaterDist.v, sfr, H.drain, H.AddWaterRunoff, H.AddWater);
    SurfaceResistance(dg, P, sfr, SnowFrac_res, R.avkdn, Temp_C, A.dq, R.xsmd, H.vsmd, D.LAI_id, H.gfunc, H.gsc, H.ResistSurf);
 }
 
 // SUEWS_cal_QE driver.f95:1744-2082: per-surface evaporation + surface/soil/snow state update.
-SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, const SuewsStepRec &R,
+SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, int snowUse, const SuewsCellParams &C, const SuewsStepRec &R,
                         const SuewsCellState &S, const SuAtm &A, const SuLumps &Lm, const SuHoist &H, const SuSnowHeat &Hs,
                         const double *Tsurf_ind, const double *SnowPack_m, const double *SnowFrac_q,
                         const double *SnowDens_m, double Temp_C, double avRh, double RA, double RAsnow, double rb,
@@ -187,7 +196,7 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPa
 SU_UNROLL1
    for (int is = 0; is < NSURF; is++) {
       const double cap = (is == DECID) ? D.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
-      if (P.snowUse == 1 && Hs.snowCalcSwitch[is] == 1) {
+      if (snowUse == 1 && Hs.snowCalcSwitch[is] == 1) {
          if (sfr[is] != 0) {
             double chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot;
             SnowCalc(dg, P, C, is, R.imin, R.it, R.dow, nsh_r, A.lvS_J_kg, A.avdens, avRh, R.Press_hPa, Temp_C, RAsnow,
@@ -239,18 +248,38 @@ SU_UNROLL1
    return qe;
 }
 
+// Site constants of a launch (pure functions of the cell parameters, formed once by the kernel prologue)
+struct SuSite {
+   SuSpaSite spa;    // observer terms of the solar position
+   double veg029;    // VegFraction**0.29 of cal_z0V (resist.f95:530)
+};
+SU_DEV void su_site_consts(const SuewsCellParams &C, SuSite &site)
+{
+   spa_site_part(C.lat, C.alt, site.spa);
+   site.veg029 = pow(C.sfr[CONIF] + C.sfr[DECID] + C.sfr[GRASS], F(0.29));
+}
+
 // Advances S by one step.  R: clock + forcing of this step; E: solar ephemeris of this step.
 // `live` is false for padding threads and for cells stopped by a fatal error; they only keep the barriers.
 // Returns the number of Tsurf iterations used.
-static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C,
+// K / SNOW / ESTM: the kernel variant (suews_kernel.cuh) -- output kind, and the bucket's snowUse / ESTM switches as
+// compile-time constants (-1: read from the class record).
+template <int K, int SNOWK, int ESTMK>
+static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, const SuSite &site,
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
-                          SuewsCellState &S, SuDaily &D, double *acc82, double *acc7, const SuLines &L, SuewsEstmState *ES = nullptr,
+                          SuewsCellState &S, SuDaily &D, double *acc82_in, double *acc7, const SuLines &L_in, SuewsEstmState *ES = nullptr,
                           const double *ts9 = nullptr, unsigned long long last_lo = 0, unsigned long long last_hi = 0,
                           bool flux_only = false)
 {
+   // what the variant rules out is ruled out for the compiler as well: no accumulator of the 82-column line and no
+   // output line under policy P0, no per-step lines (bar the DailyState row of P1) when only accumulating
+   double *const acc82 = (K == 2) ? nullptr : acc82_in;
+   SuLines L = L_in;
+   if (K != 0) { L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.sol26 = nullptr; L.estm27 = nullptr; }
+   if (K == 2) L.daily45 = nullptr;
    const double *sfr = C.sfr.v;
    const int sm = P.StabilityMethod;
-   const int snowUse = P.snowUse;
+   const int snowUse = (SNOWK < 0) ? (int)P.snowUse : SNOWK;
    // ---------------- step invariants (driver.f95:645-691)
    const int nsh = 3600 / P.tstep;
    const double nsh_real = (double)((float)nsh * 1.0f);   // util_time.f95:295-297
@@ -259,7 +288,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    const double PervFraction = 1 - (sfr[PAV] + sfr[BLDG]);
    const double NonWaterFraction = 1 - sfr[WATER];
    const int DLS = (R.id > P.startDLS && R.id < P.endDLS) ? 1 : 0;
-   double FAI = 0, zH = 0, z0m = 0, zdm = 0, ZZD = 0, azimuth = 0, zenith_deg = 0;
+   double FAI = 0, zH = 0, z0m = 0, zdm = 0, ZZD = 0, lg_zz0 = 0, azimuth = 0, zenith_deg = 0;
    int nrm_use = 0, AlbedoChoice = 0, ldown_option = 0;
 
    double Temp_C = R.Temp_C + C.dTemp_C;   // forcing with the optional per-cell offsets of the synthetic configs
@@ -293,7 +322,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    int lv_exit[4] = {-1, -1, -1, -1};
    bool rad_invariant = false, rad_done = false, qe_full_done = false;
    // with snow off (and no snow output line wanted) the snow work arrays are neither formed nor committed
-   const bool use_estm = (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14);
+   const bool use_estm = (ESTMK != 0) && (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14);
    const bool want_snow_line = (L.snow98 != nullptr);
    const bool snow_arrays = (snowUse == 1) || want_snow_line;
    double lv_at_melt = 0;
@@ -303,7 +332,12 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    if (live) {
       for (int is = 0; is < NSURF; is++) { deltaQi[is] = 0; smd_nsurf[is] = 0; SnowWater_in[is] = S.SnowWater[is]; }
       cal_RoughnessParameters(dg, P.RoughLenMomMethod, C, D.porosity_id, FAI, zH, z0m, zdm, ZZD);
+      lg_zz0 = log(ZZD / z0m);   // cal_Stab and AerodynamicResistance of every trip (atmmoiststab.f95:223, resist.f95:60-84)
+#ifdef SU_NO_SITE_HOIST   // tuning switch: site terms of the solar position re-evaluated every step
       spa_location_part(E, C.lat, C.lng, C.alt, azimuth, zenith_deg);
+#else
+      spa_location_part(E, site.spa, C.lng, azimuth, zenith_deg);
+#endif
       RadMethod(dg, P.NetRadiationMethod, snowUse, nrm_use, AlbedoChoice, ldown_option);
       // Tsurf enters NARP only through the iteration-based methods (narp.f95:337-346).  (ESTM, which advances its
       // element temperatures on every call of SUEWS_cal_Qs, is run per trip below whatever the radiation scheme.)
@@ -324,7 +358,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       cal_AtmMoist(dg, Temp_C, Press_hPa, avRh, lv_sw, A);   // may rewrite Temp_C
       lv_memo[sw_in] = A.lv_J_kg;
       lv_exit[sw_in] = lv_sw;
-      stage_post_atm(dg, P, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
+      stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
       qf = H.an.qf;
    }
 
@@ -345,7 +379,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
             if (i_iter == 2 && temp_will_rewrite) {   // trips >= 2 run the early stages with the rewritten Temp_C
                D = D_prev;
                stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
-               stage_post_atm(dg, P, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
+               stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
                qf = H.an.qf;
                rad_done = false;
             }
@@ -425,19 +459,20 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          if (i_iter == 1)   // LUMPS first guess (driver.f95:809-824)
             LUMPS_cal_QHQE(dg, P, sfr, qn1, qf, qs, Hs.Qm, Temp_C, Hs.veg_fr, A.avcp, Press_hPa, A.lv_J_kg, D.LAI_id, Lm);
       }
-      SU_SYNCN(1);
+      SU_SYNCL(1);
       SU_CLK(2);
       // ================= phase L2: stability and resistances (driver.f95:2134-2270) =================
       if (run) {
          const double QH_Init = (i_iter == 1) ? Lm.QH_LUMPS : qh;
-         cal_Stab(dg, sm, ZZD, z0m, avU1, Temp_C, QH_Init, A.avdens, A.avcp, L_mod, TStar, UStar, zL);
-         RA = AerodynamicResistance(dg, ZZD, z0m, avU1, L_mod, UStar, VegFraction, P.AerodynamicResistanceMethod, sm,
-                                    P.RoughLenHeatMethod);
+         cal_Stab(dg, sm, ZZD, z0m, lg_zz0, avU1, Temp_C, QH_Init, A.avdens, A.avcp, L_mod, TStar, UStar, zL);
+         RA = AerodynamicResistance(dg, ZZD, z0m, lg_zz0, avU1, L_mod, UStar, VegFraction, site.veg029, P.AerodynamicResistanceMethod,
+                                    sm, P.RoughLenHeatMethod);
          if (snowUse == 1)
-            RAsnow = AerodynamicResistance(dg, ZZD, z0m, avU1, L_mod, UStar, VegFraction, P.AerodynamicResistanceMethod, sm, 3);
+            RAsnow = AerodynamicResistance(dg, ZZD, z0m, lg_zz0, avU1, L_mod, UStar, VegFraction, site.veg029,
+                                           P.AerodynamicResistanceMethod, sm, 3);
          rb = BoundaryLayerResistance(ZZD, z0m, avU1, UStar);
       }
-      SU_SYNCN(2);
+      SU_SYNCL(2);
       SU_CLK(3);
       // ================= phase L3: QE, QH, surface temperature, convergence =================
       if (run) {
@@ -446,7 +481,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          if (snowUse == 1)
             for (int is = 0; is < NSURF; is++) snow_branch = snow_branch || (Hs.snowCalcSwitch[is] == 1);
          if (snow_branch) {
-            cal_QE_full(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow,
+            cal_QE_full(dg, P, snowUse, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow,
                         rb, qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
             qe = QT.qe;
             qe_full_done = true;
@@ -487,7 +522,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    if (live && dg.fatal == 0) {
       if (!qe_full_done) {
          const double qn_e = qn1_snowfree + qf - qs;
-         cal_QE_full(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow, rb,
+         cal_QE_full(dg, P, snowUse, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow, rb,
                      qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
       }
       qh_resist = (RA != 0) ? A.avdens * A.avcp * (Rd.tsurf - Temp_C) / RA : -999.0;

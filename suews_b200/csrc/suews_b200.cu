@@ -87,6 +87,11 @@ __global__ void suews_ephem_kernel(const SuewsStepRec *steps, int nsteps, const 
    spa_time_part((double)steps[s].iy, steps[s].dectime - (double)(tstep / 2), tz_list[z], ephem[(size_t)z * nsteps + s]);
 }
 
+__global__ void suews_fill_kernel(double *p, size_t n, double v)
+{
+   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 __global__ void suews_dfma_kernel(double *out, int iters, double m)
 {
    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -128,6 +133,34 @@ __global__ void suews_math_selftest_kernel(long long n, unsigned long long seed,
    }
    if (be) atomicAdd(&bad[0], be);
    if (bl) atomicAdd(&bad[1], bl);
+}
+
+// The screened wet-bulb search of dev_atmos.cuh (Lat_vap) against the plain loop, on pseudo-random arguments over the whole
+// range the reference accepts and beyond it: latent heat (bit pattern), exit switch state and warning bits must agree.
+__global__ void suews_latvap_selftest_kernel(long long n, unsigned long long seed, unsigned long long *bad)
+{
+   unsigned long long st = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(blockIdx.x * (long long)blockDim.x + threadIdx.x + 1);
+   auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+   auto unif = [&]() { return (double)(next() >> 11) * 0x1p-53; };
+   unsigned long long nb = 0;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const int kind = (int)(next() & 7);
+      double T = (kind == 0) ? -60.0 + 130.0 * unif() : ((kind == 1) ? (unif() - 0.5) * 0.01 : -35.0 + 80.0 * unif());
+      double P = (kind == 2) ? 500.0 + 700.0 * unif() : 950.0 + 100.0 * unif();
+      double rh = (kind == 3) ? 100.0 * unif() * unif() * unif() : 100.0 * unif();
+      if (kind == 4) rh = 100.0 - 1e-3 * unif();
+      SuDiag d0, d1;
+      d0.fatal = 0; d0.warn[0] = 0; d0.warn[1] = 0; d1 = d0;
+      double Tx = su_fix_T(T);
+      const double es = sat_vap_press_v(Tx, P);
+      const double ea = rh / 100 * es;
+      const double cp = 1000.0 + 60.0 * unif();
+      int s0 = (int)(next() & 3), s1 = s0;
+      const double a = Lat_vap_t<true>(d0, T, ea, P, cp, s0);
+      const double b = Lat_vap_t<false>(d1, T, ea, P, cp, s1);
+      if (__double_as_longlong(a) != __double_as_longlong(b) || s0 != s1 || d0.warn[0] != d1.warn[0] || d0.warn[1] != d1.warn[1]) nb++;
+   }
+   if (nb) atomicAdd(bad, nb);
 }
 
 __global__ void suews_sunpos_kernel(double year, double idectime, double UTC, double lat, double lng, double alt, double *out)
@@ -261,11 +294,27 @@ struct suews_b200_handle_s {
    std::vector<int> slot_of_cell, cell_of_slot;
    std::vector<double> xfer;   // staging for the cell-order <-> slot-order moves
    int ts5_nsteps = 0;
-   std::vector<int> cls_of_cell, tz_of_cell;
+   std::vector<int> cls_of_cell, tz_of_cell;   // (cell order; the device copies d_cls / d_tz are in slot order)
    std::vector<double> tz_list;
    int dt_since_start = 0, tstep_prev = 0, tstep = 0;
    int nsteps = 0;
    bool uploaded = false;
+   // an advance ran since the last upload: the device holds the only current copy of state, sums and diagnostics
+   bool dev_dirty = false;
+   bool keep_diag = false;   // keep_* hold sums / diagnostics pulled back before a parameter-only re-upload
+   std::vector<double> keep_sums;
+   std::vector<int> keep_fatal;
+   std::vector<unsigned long long> keep_warn;
+   std::vector<long long> keep_iters;
+   // Buckets: thread slots are sorted by (bucket, class, canopy height); a bucket is a set of classes that agree on the
+   // switches the kernel variants specialise on (bit 2 ESTM, bit 1 snowUse = 1, bit 0 radiation scheme that feeds the
+   // surface temperature back, bit 3 neither snowUse 0 nor 1).  bucket_start[b] .. bucket_start[b + 1] are bucket b's slots.
+   int bucket_start[17] = {0};
+   cudaStream_t bstream[16] = {nullptr};   // side streams: the buckets of one advance run concurrently
+   cudaEvent_t bev[16] = {nullptr};
+   cudaEvent_t ev_fork = nullptr;
+   bool roll_tstep_prev = true;   // batched API: the library's own clock; the reference-shaped calls keep tstep_prev constant
+   unsigned carveout_done = 0;    // bit per kernel instance whose L1 carve-out was set on this handle's device
    // device
    SuewsClassParams *d_classes = nullptr;
    int *d_cls = nullptr, *d_tz = nullptr, *d_fatal = nullptr, *d_order = nullptr;
@@ -276,6 +325,7 @@ struct suews_b200_handle_s {
    SuewsEphem *d_ephem = nullptr;
    double *d_blk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SUEWS, snow, RSL, DailyState, SOLWEIG, ESTM
    int blk_nsteps = 0;
+   size_t blk_cap[6] = {0, 0, 0, 0, 0, 0};
    cudaStream_t stream = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    int first_fatal_code = 0, first_fatal_cell = -1;
@@ -313,6 +363,51 @@ static void to_cell_order(const double *slot_major, double *cell_major, const st
       double *dst = cell_major + j * stride;
       for (size_t sl = 0; sl < n; sl++) dst[(size_t)order[sl]] = src[sl];
    }
+}
+
+// A setter called after an advance must not roll the run back: the host mirror of the state (and of the ESTM
+// state) is refreshed from the device first, and the running sums and per-cell diagnostics are kept for the
+// re-upload that follows (they restart from zero only on the first upload or through suews_b200_reset_sums).
+static int pull_live(suews_b200_handle_s *h)
+{
+   if (!h->uploaded || !h->dev_dirty) return SUEWS_OK;
+   CUDA_OK(cudaSetDevice(h->device));
+   CUDA_OK(cudaStreamSynchronize(h->stream));
+   const size_t st = (size_t)h->stride;
+   h->xfer.resize(std::max(h->xfer.size(), h->state.size()));
+   CUDA_OK(cudaMemcpy(h->xfer.data(), h->d_state, sizeof(double) * h->state.size(), cudaMemcpyDeviceToHost));
+   to_cell_order(h->xfer.data(), h->state.data(), h->cell_of_slot, SUEWS_N_STATE_DBL, st);
+   if (h->d_estm && !h->estm.empty()) {
+      h->xfer.resize(std::max(h->xfer.size(), h->estm.size()));
+      CUDA_OK(cudaMemcpy(h->xfer.data(), h->d_estm, sizeof(double) * h->estm.size(), cudaMemcpyDeviceToHost));
+      to_cell_order(h->xfer.data(), h->estm.data(), h->cell_of_slot, SUEWS_N_ESTM_DBL, st);
+   }
+   // sums and diagnostics: device slot order -> cell order (the next upload may sort the slots differently)
+   h->keep_sums.resize((size_t)SUEWS_NCOL_SUEWS * st);
+   h->keep_fatal.assign(st, 0);
+   h->keep_warn.assign(2 * st, 0ull);
+   h->keep_iters.assign(st, 0ll);
+   {
+      h->xfer.resize(std::max(h->xfer.size(), h->keep_sums.size()));
+      CUDA_OK(cudaMemcpy(h->xfer.data(), h->d_sums, sizeof(double) * h->keep_sums.size(), cudaMemcpyDeviceToHost));
+      to_cell_order(h->xfer.data(), h->keep_sums.data(), h->cell_of_slot, SUEWS_NCOL_SUEWS, st);
+      std::vector<int> f(st);
+      std::vector<unsigned long long> w(2 * st);
+      std::vector<long long> it(st);
+      CUDA_OK(cudaMemcpy(f.data(), h->d_fatal, sizeof(int) * st, cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(w.data(), h->d_warn, sizeof(unsigned long long) * 2 * st, cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(it.data(), h->d_iters, sizeof(long long) * st, cudaMemcpyDeviceToHost));
+      for (int sl = 0; sl < h->ncell; sl++) {
+         const size_t c = (size_t)h->cell_of_slot[(size_t)sl];
+         h->keep_fatal[c] = f[(size_t)sl];
+         h->keep_warn[c] = w[(size_t)sl];
+         h->keep_warn[st + c] = w[st + (size_t)sl];
+         h->keep_iters[c] = it[(size_t)sl];
+      }
+   }
+   h->keep_diag = true;
+   h->dev_dirty = false;
+   return SUEWS_OK;
 }
 
 extern "C" {
@@ -388,6 +483,11 @@ int suews_b200_destroy(suews_b200_handle h)
    free_dev(h);
    if (h->pinned) cudaFreeHost(h->pinned);
    if (h->pinned_in) cudaFreeHost(h->pinned_in);
+   for (int k = 0; k < 16; k++) {
+      if (h->bstream[k]) cudaStreamDestroy(h->bstream[k]);
+      if (h->bev[k]) cudaEventDestroy(h->bev[k]);
+   }
+   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
    if (h->stream) cudaStreamDestroy(h->stream);
    if (h->ev0) cudaEventDestroy(h->ev0);
    if (h->ev1) cudaEventDestroy(h->ev1);
@@ -409,6 +509,7 @@ int suews_b200_set_class_param(suews_b200_handle h, int cls, const char *name, c
       double *base = reinterpret_cast<double *>(&P.AlbMax_DecTr);
       for (int i = 0; i < n; i++) base[f->off + i] = vals[i];
    }
+   { int rc_ = pull_live(h); if (rc_) return rc_; }
    h->uploaded = false;
    return SUEWS_OK;
 }
@@ -428,6 +529,7 @@ int suews_b200_set_cell_param(suews_b200_handle h, const char *name, const doubl
    const FieldDesc *f = find_field(name);
    if (!f || f->kind != 2) return set_err(SUEWS_E_BAD_NAME, "set_cell_param: '%s' is not a per-cell field", name);
    if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "set_cell_param: '%s' has %d values per cell, got %d", name, f->n, n);
+   { int rc_ = pull_live(h); if (rc_) return rc_; }
    h->uploaded = false;
    return set_soa(h->cellp, h->stride, h->ncell, f, vals);
 }
@@ -440,6 +542,7 @@ int suews_b200_set_cell_class(suews_b200_handle h, const int *class_of_cell)
          return set_err(SUEWS_E_BAD_ARG, "set_cell_class: cell %d has class %d of %d", c, class_of_cell[c], h->nclass);
       h->cls_of_cell[(size_t)c] = class_of_cell[c];
    }
+   { int rc_ = pull_live(h); if (rc_) return rc_; }
    h->uploaded = false;
    return SUEWS_OK;
 }
@@ -450,6 +553,7 @@ int suews_b200_set_state(suews_b200_handle h, const char *name, const double *va
    const FieldDesc *f = find_field(name);
    if (!f || (f->kind != 3 && f->kind != 4)) return set_err(SUEWS_E_BAD_NAME, "set_state: '%s' is not a state field", name);
    if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "set_state: '%s' has %d values per cell, got %d", name, f->n, n);
+   { int rc_ = pull_live(h); if (rc_) return rc_; }
    h->uploaded = false;
    if (f->kind == 4) {
       if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
@@ -495,6 +599,25 @@ int suews_b200_get_state(suews_b200_handle h, const char *name, double *vals, in
    return SUEWS_OK;
 }
 
+// Forget the run on the device: the next upload starts the sums and diagnostics from zero and does not read the device
+// state back (the reference-shaped calls reuse one resident handle and pass every argument anew).
+int suews_b200_restart(suews_b200_handle h)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   h->dev_dirty = false;
+   h->keep_diag = false;
+   h->uploaded = false;
+   return SUEWS_OK;
+}
+// tstep_prev of SUEWS_cal_Main: rolls = 1 (default) lets the library's own clock set it to tstep after the first step of
+// a run; rolls = 0 keeps the value of set_clock for every step, as SUEWS_cal_multitsteps does with its INTENT(IN) argument
+int suews_b200_set_tstep_prev_rolls(suews_b200_handle h, int rolls)
+{
+   if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   h->roll_tstep_prev = rolls != 0;
+   return SUEWS_OK;
+}
+
 int suews_b200_set_clock(suews_b200_handle h, int dt_since_start, int tstep_prev)
 {
    if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
@@ -529,6 +652,7 @@ int suews_b200_upload(suews_b200_handle h)
          return set_err(SUEWS_E_BAD_ARG, "upload: all classes must share one positive tstep (got %d and %d)", h->tstep, (int)P.tstep);
    }
    // distinct time zones -> ephemeris index per cell
+   const std::vector<double> tz_before = h->tz_list;
    h->tz_list.clear();
    const FieldDesc *ftz = find_field("timezone");
    for (int c = 0; c < h->ncell; c++) {
@@ -539,10 +663,24 @@ int suews_b200_upload(suews_b200_handle h)
       if (idx < 0) { idx = (int)h->tz_list.size(); h->tz_list.push_back(tz); }
       h->tz_of_cell[(size_t)c] = idx;
    }
-   // Divergence control: warps are filled with cells of the same class and similar canopy height.  The
-   // roughness-sublayer search (cal_psim_hat, rslprof.f95:366) walks ln(100/zH)/ln(1.01) levels and is
-   // skipped for zH <= 6 m, so zH is the per-cell cost driver; scheme flags are class constants.
+   // Divergence control.  Thread slots are sorted by (bucket, class, canopy height): a bucket is the set of classes that
+   // agree on snowUse, ESTM and on whether the radiation scheme feeds the surface temperature back -- each bucket is
+   // launched on its own with the kernel instance compiled for those switches (suews_kernel.cuh), so no block ever mixes
+   // scheme sets; inside a bucket warps are filled with cells of one class and similar canopy height.  The
+   // roughness-sublayer search (cal_psim_hat, rslprof.f95:366) walks ln(100/zH)/ln(1.01) levels and is skipped for
+   // zH <= 6 m, so zH is the per-cell cost driver.
    std::vector<int> order((size_t)h->ncell);
+   std::vector<int> bucket_of_class((size_t)h->nclass);
+   for (int k = 0; k < h->nclass; k++) {
+      const SuewsClassParams &P = h->classes[(size_t)k];
+      const int nrm = P.NetRadiationMethod;
+      int b = 0;
+      if (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14) b |= 4;
+      if (P.snowUse == 1) b |= 2;
+      else if (P.snowUse != 0) b |= 8;
+      if (nrm >= 10 && nrm < 100) b |= 1;   // RadMethod: nrm_use >= 10 iterates on the surface temperature (narp.f95:337)
+      bucket_of_class[(size_t)k] = b;
+   }
    {
       const FieldDesc *fs = find_field("sfr"), *fb = find_field("bldgH"), *fe = find_field("EveTreeH"),
                       *fd = find_field("DecTreeH"), *fp = find_field("porosity_id");
@@ -553,10 +691,14 @@ int suews_b200_upload(suews_b200_handle h)
          double a = s1 + s2 + s3;
          double zh = (a != 0) ? (h->cellp[fb->off * sd + c] * s1 + h->cellp[fe->off * sd + c] * s2 +
                                  h->cellp[fd->off * sd + c] * (1 - h->state[fp->off * sd + c]) * s3) / a : 0.0;
-         key[(size_t)c] = (double)h->cls_of_cell[(size_t)c] * 1e6 + zh;
+         const int k = h->cls_of_cell[(size_t)c];
+         key[(size_t)c] = ((double)bucket_of_class[(size_t)k] * 1e6 + (double)k) * 1e6 + zh;
          order[(size_t)c] = c;
       }
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[(size_t)x] < key[(size_t)y]; });
+      for (int b = 0; b <= 16; b++) h->bucket_start[b] = 0;
+      for (int c = 0; c < h->ncell; c++) h->bucket_start[bucket_of_class[(size_t)h->cls_of_cell[(size_t)c]] + 1]++;
+      for (int b = 0; b < 16; b++) h->bucket_start[b + 1] += h->bucket_start[b];
    }
    h->slot_of_cell.assign((size_t)h->ncell, 0);
    for (int sl = 0; sl < h->ncell; sl++) h->slot_of_cell[(size_t)order[(size_t)sl]] = sl;
@@ -575,8 +717,13 @@ int suews_b200_upload(suews_b200_handle h)
    CUDA_OK(dev_alloc(&h->d_iters, st));
    CUDA_OK(dev_alloc(&h->d_tzlist, h->tz_list.size()));
    CUDA_OK(cudaMemcpy(h->d_classes, h->classes.data(), sizeof(SuewsClassParams) * (size_t)h->nclass, cudaMemcpyHostToDevice));
-   CUDA_OK(cudaMemcpy(h->d_cls, h->cls_of_cell.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
-   CUDA_OK(cudaMemcpy(h->d_tz, h->tz_of_cell.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
+   {   // class and time-zone index per thread slot
+      std::vector<int> tmp((size_t)h->ncell);
+      for (int sl = 0; sl < h->ncell; sl++) tmp[(size_t)sl] = h->cls_of_cell[(size_t)order[(size_t)sl]];
+      CUDA_OK(cudaMemcpy(h->d_cls, tmp.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
+      for (int sl = 0; sl < h->ncell; sl++) tmp[(size_t)sl] = h->tz_of_cell[(size_t)order[(size_t)sl]];
+      CUDA_OK(cudaMemcpy(h->d_tz, tmp.data(), sizeof(int) * (size_t)h->ncell, cudaMemcpyHostToDevice));
+   }
    h->xfer.resize(std::max(h->cellp.size(), h->state.size()));
    to_slot_order(h->cellp.data(), h->xfer.data(), order, SUEWS_N_CELL_DBL, st);
    CUDA_OK(cudaMemcpy(h->d_cellp, h->xfer.data(), sizeof(double) * h->cellp.size(), cudaMemcpyHostToDevice));
@@ -600,8 +747,30 @@ int suews_b200_upload(suews_b200_handle h)
    CUDA_OK(cudaMemset(h->d_fatal, 0, sizeof(int) * st));
    CUDA_OK(cudaMemset(h->d_warn, 0, sizeof(unsigned long long) * 2 * st));
    CUDA_OK(cudaMemset(h->d_iters, 0, sizeof(long long) * st));
+   if (h->keep_diag) {   // parameter-only re-upload in the middle of a run (pull_live): sums and diagnostics carry on
+      h->xfer.resize(std::max(h->xfer.size(), h->keep_sums.size()));
+      to_slot_order(h->keep_sums.data(), h->xfer.data(), order, SUEWS_NCOL_SUEWS, st);
+      CUDA_OK(cudaMemcpy(h->d_sums, h->xfer.data(), sizeof(double) * h->keep_sums.size(), cudaMemcpyHostToDevice));
+      std::vector<int> f(st, 0);
+      std::vector<unsigned long long> w(2 * st, 0ull);
+      std::vector<long long> it(st, 0ll);
+      for (int sl = 0; sl < h->ncell; sl++) {
+         const size_t c = (size_t)order[(size_t)sl];
+         f[(size_t)sl] = h->keep_fatal[c];
+         w[(size_t)sl] = h->keep_warn[c];
+         w[st + (size_t)sl] = h->keep_warn[st + c];
+         it[(size_t)sl] = h->keep_iters[c];
+      }
+      CUDA_OK(cudaMemcpy(h->d_fatal, f.data(), sizeof(int) * st, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(h->d_warn, w.data(), sizeof(unsigned long long) * 2 * st, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(h->d_iters, it.data(), sizeof(long long) * st, cudaMemcpyHostToDevice));
+      h->keep_diag = false;
+   }
+   h->dev_dirty = false;
    h->uploaded = true;
-   h->steps_cap = 0;   // the ephemeris table is sized by the number of distinct time zones
+   // the ephemeris table is laid out by distinct time zone: a forcing block staged before a re-upload stays usable only
+   // while that list is unchanged
+   if (h->tz_list != tz_before) { h->steps_cap = 0; h->nsteps = 0; }
    h->first_fatal_code = 0;
    h->first_fatal_cell = -1;
    return SUEWS_OK;
@@ -785,11 +954,14 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
       for (int i = 0; i < 6; i++) {
          if (i == 5 && !h->d_estm) continue;   // the ESTM block exists only when ESTM runs
          size_t cnt = (size_t)h->ncell * (size_t)nsteps * (size_t)ncol[i];
-         CUDA_OK(dev_alloc(&h->d_blk[i], cnt));
+         if (h->blk_cap[i] < cnt) {
+            CUDA_OK(dev_alloc(&h->d_blk[i], cnt));
+            h->blk_cap[i] = cnt;
+         }
          // unwritten rows (snow block when snowUse = 0) are left unassigned by the reference; -999 here
-         std::vector<double> fill(cnt, -999.0);
-         CUDA_OK(cudaMemcpy(h->d_blk[i], fill.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice));
+         suews_fill_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16), 256, 0, h->stream>>>(h->d_blk[i], cnt, -999.0);
       }
+      CUDA_OK(cudaGetLastError());
       h->blk_nsteps = nsteps;
    }
    SuRunArgs a;
@@ -836,13 +1008,14 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
       a.agg = h->d_agg;
       a.agg_nlines = nlines;
    }
-   a.classes = h->d_classes; a.class_of_cell = h->d_cls; a.tz_of_cell = h->d_tz; a.order = h->d_order; a.cellp = h->d_cellp; a.state = h->d_state;
+   a.classes = h->d_classes; a.class_of_slot = h->d_cls; a.tz_of_slot = h->d_tz; a.order = h->d_order; a.cellp = h->d_cellp; a.state = h->d_state;
    a.steps = h->d_steps + step0;
    a.ephem = h->d_ephem + step0;
    a.ephem_tz_stride = h->nsteps;
    a.sums = (out_flags & (SUEWS_OUT_SUM82 | SUEWS_OUT_SUM7)) ? h->d_sums : nullptr;
    a.sum7 = ((out_flags & SUEWS_OUT_SUM7) && !(out_flags & SUEWS_OUT_SUM82)) ? 1 : 0;
-   a.flux_only = ((out_flags & SUEWS_OUT_FLUX_ONLY) && a.sum7 && !full && !(out_flags & SUEWS_OUT_AGG)) ? 1 : 0;
+   // policy P0 observes seven flux sums only: stages nothing requested depends on are skipped (SUEWS_OUT_ALL_STAGES keeps them)
+   a.flux_only = ((a.sum7 || !a.sums) && !full && !(out_flags & (SUEWS_OUT_AGG | SUEWS_OUT_ALL_STAGES))) ? 1 : 0;
    a.fatal = h->d_fatal; a.warn = h->d_warn; a.iters = h->d_iters;
    a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3]; a.blkSOL = h->d_blk[4];
    a.blkESTM = h->d_estm ? h->d_blk[5] : nullptr;
@@ -850,34 +1023,60 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.ts5 = (h->d_estm && h->ts5_nsteps == h->nsteps) ? h->d_ts5 + (size_t)step0 * SUEWS_N_TS5 : nullptr;
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
    a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;
-   // launch geometry: 1024-cell blocks, one per SM, once they can occupy most of the chip; 256-cell blocks below that
+   a.roll_tstep_prev = h->roll_tstep_prev ? 1 : 0;
    int nsm = 148;
    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-   // measured on B200 (cell-steps/s, large vs small geometry): 10 240 cells 0.87e7 / 1.7e7 (full output), 37 888 cells
-   // 6.4e7 / 1.05e8, 75 776 cells 1.23e8 / 1.11e8 -- the crossover sits near 1.5 small blocks per SM
-   bool small = (long long)h->ncell * 2 <= (long long)nsm * SU_BLOCK_SMALL * 3;
-   if (const char *e = getenv("SUEWS_B200_GEOMETRY")) small = (strcmp(e, "small") == 0) ? true : ((strcmp(e, "large") == 0) ? false : small);
-   const int blk = small ? SU_BLOCK_SMALL : SU_BLOCK;
-   const int grid = (h->ncell + blk - 1) / blk;
-   {   // the kernel stages 11 KB of forcing in shared memory and lives off L1 for its stack: ask for the largest L1
-      static bool carveout_set = false;
-      if (!carveout_set && !getenv("SUEWS_B200_DEFAULT_CARVEOUT")) {
-         cudaFuncSetAttribute(suews_run_kernel<true, SU_BLOCK, SU_MINBLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-         cudaFuncSetAttribute(suews_run_kernel<false, SU_BLOCK, SU_MINBLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-         carveout_set = true;
-      }
-   }
+   // One launch per non-empty bucket, each with the kernel instance compiled for the bucket's switches and the requested
+   // output kind (suews_kernel.cuh); the buckets of an advance run side by side on their own streams.
+   const int kind = full ? SU_K_FULL : (((out_flags & (SUEWS_OUT_SUM82 | SUEWS_OUT_AGG)) || (out_flags & SUEWS_OUT_ALL_STAGES)) ? SU_K_ACC : SU_K_P0);
+   int nb = 0;
+   for (int b = 0; b < 16; b++) nb += (h->bucket_start[b + 1] > h->bucket_start[b]);
    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
-   if (small) {
-      CUDA_OK(suews_launch_small(full, grid, h->stream, a));
-   } else {
-      if (full) suews_run_kernel<true, SU_BLOCK, SU_MINBLOCKS><<<grid, blk, 0, h->stream>>>(a);
-      else suews_run_kernel<false, SU_BLOCK, SU_MINBLOCKS><<<grid, blk, 0, h->stream>>>(a);
+   if (nb > 1) {
+      if (!h->ev_fork) CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
    }
+   int side = 0;
+   for (int b = 0; b < 16; b++) {
+      const int n = h->bucket_start[b + 1] - h->bucket_start[b];
+      if (n <= 0) continue;
+      a.slot0 = h->bucket_start[b];
+      a.nslot = n;
+      const bool estm = (b & 4) != 0, snow1 = (b & 2) != 0, snow_rt = (b & 8) != 0;
+      // launch geometry: 1024-cell blocks, one per SM, once they can occupy most of the chip; 256-cell blocks below that.
+      // measured on B200 (cell-steps/s, large vs small geometry): 10 240 cells 0.87e7 / 1.7e7 (full output), 37 888 cells
+      // 6.4e7 / 1.05e8, 75 776 cells 1.23e8 / 1.11e8 -- the crossover sits near 1.5 small blocks per SM
+      bool small = (long long)n * 2 <= (long long)nsm * SU_BLOCK_SMALL * 3;
+      if (const char *e = getenv("SUEWS_B200_GEOMETRY")) small = (strcmp(e, "small") == 0) ? true : ((strcmp(e, "large") == 0) ? false : small);
+      cudaError_t (*launch)(int, cudaStream_t, const SuRunArgs &) = nullptr;
+      if (kind == SU_K_FULL) launch = small ? SU_LAUNCHER_NAME(0, m1, m1, 256) : SU_LAUNCHER_NAME(0, m1, m1, 1024);
+      else if (small || estm || snow_rt) launch = small ? SU_LAUNCHER_NAME(1, m1, m1, 256) : SU_LAUNCHER_NAME(1, m1, m1, 1024);
+      else if (kind == SU_K_ACC) launch = snow1 ? SU_LAUNCHER_NAME(1, m1, m1, 1024) : SU_LAUNCHER_NAME(1, 0, 0, 1024);
+      else launch = snow1 ? SU_LAUNCHER_NAME(2, 1, 0, 1024) : SU_LAUNCHER_NAME(2, 0, 0, 1024);
+      const int blk = small ? SU_BLOCK_SMALL : SU_BLOCK;
+      const int grid = (n + blk - 1) / blk;
+      cudaStream_t st = h->stream;
+      if (nb > 1 && side > 0) {   // first bucket on the main stream, the others fork off it and join again below
+         const int k = side - 1;
+         if (!h->bstream[k]) {
+            CUDA_OK(cudaStreamCreateWithFlags(&h->bstream[k], cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&h->bev[k], cudaEventDisableTiming));
+         }
+         CUDA_OK(cudaStreamWaitEvent(h->bstream[k], h->ev_fork, 0));
+         st = h->bstream[k];
+      }
+      CUDA_OK(launch(grid, st, a));
+      if (st != h->stream) {
+         CUDA_OK(cudaEventRecord(h->bev[side - 1], st));
+      }
+      side++;
+   }
+   for (int k = 0; k + 1 < side; k++) CUDA_OK(cudaStreamWaitEvent(h->stream, h->bev[k], 0));
    CUDA_OK(cudaGetLastError());
    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
    h->dt_since_start += nsteps * h->tstep;
-   h->tstep_prev = h->tstep;
+   if (h->roll_tstep_prev) h->tstep_prev = h->tstep;
+   h->dev_dirty = true;
    return SUEWS_OK;
 }
 
@@ -947,14 +1146,16 @@ int suews_b200_sync(suews_b200_handle h)
    if (!h) return set_err(SUEWS_E_BAD_ARG, "null handle");
    CUDA_OK(cudaSetDevice(h->device));
    CUDA_OK(cudaStreamSynchronize(h->stream));
-   std::vector<int> fatal((size_t)h->ncell);
+   std::vector<int> fatal((size_t)h->ncell);   // slot order on the device; the lowest failing cell index is reported
    CUDA_OK(cudaMemcpy(fatal.data(), h->d_fatal, sizeof(int) * (size_t)h->ncell, cudaMemcpyDeviceToHost));
-   for (int c = 0; c < h->ncell; c++)
-      if (fatal[(size_t)c] != 0) {
-         h->first_fatal_code = fatal[(size_t)c];
-         h->first_fatal_cell = c;
-         return set_err(fatal[(size_t)c], "Fatal error in SUEWS! code %d in cell %d: %s", fatal[(size_t)c], c, fatal_text(fatal[(size_t)c]));
-      }
+   int best = -1, code = 0;
+   for (int sl = 0; sl < h->ncell; sl++)
+      if (fatal[(size_t)sl] != 0 && (best < 0 || h->cell_of_slot[(size_t)sl] < best)) { best = h->cell_of_slot[(size_t)sl]; code = fatal[(size_t)sl]; }
+   if (best >= 0) {
+      h->first_fatal_code = code;
+      h->first_fatal_cell = best;
+      return set_err(code, "Fatal error in SUEWS! code %d in cell %d: %s", code, best, fatal_text(code));
+   }
    return SUEWS_OK;
 }
 
@@ -974,8 +1175,10 @@ int suews_b200_get_sums(suews_b200_handle h, double *sums)
    CUDA_OK(cudaStreamSynchronize(h->stream));
    std::vector<double> tmp((size_t)SUEWS_NCOL_SUEWS * (size_t)h->stride);
    CUDA_OK(cudaMemcpy(tmp.data(), h->d_sums, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
-   for (int c = 0; c < h->ncell; c++)
-      for (int k = 0; k < SUEWS_NCOL_SUEWS; k++) sums[(size_t)c * SUEWS_NCOL_SUEWS + k] = tmp[(size_t)k * h->stride + c];
+   for (int c = 0; c < h->ncell; c++) {
+      const size_t sl = (size_t)h->slot_of_cell[(size_t)c];
+      for (int k = 0; k < SUEWS_NCOL_SUEWS; k++) sums[(size_t)c * SUEWS_NCOL_SUEWS + k] = tmp[(size_t)k * h->stride + sl];
+   }
    return SUEWS_OK;
 }
 
@@ -998,8 +1201,10 @@ int suews_b200_get_sums_cols(suews_b200_handle h, const int *cols, int ncols, do
                               sizeof(double) * (size_t)h->ncell, cudaMemcpyDeviceToHost, h->stream));
    }
    CUDA_OK(cudaStreamSynchronize(h->stream));
-   for (int c = 0; c < h->ncell; c++)
-      for (int k = 0; k < ncols; k++) out[(size_t)c * ncols + k] = pin[(size_t)k * h->stride + c];
+   for (int c = 0; c < h->ncell; c++) {
+      const size_t sl = (size_t)h->slot_of_cell[(size_t)c];
+      for (int k = 0; k < ncols; k++) out[(size_t)c * ncols + k] = pin[(size_t)k * h->stride + sl];
+   }
    return SUEWS_OK;
 }
 
@@ -1075,14 +1280,24 @@ int suews_b200_get_diag(suews_b200_handle h, int *fatal, unsigned long long *war
    if (!h || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "get_diag: nothing uploaded");
    CUDA_OK(cudaSetDevice(h->device));
    CUDA_OK(cudaStreamSynchronize(h->stream));
-   if (fatal) CUDA_OK(cudaMemcpy(fatal, h->d_fatal, sizeof(int) * (size_t)h->ncell, cudaMemcpyDeviceToHost));
-   if (iters) CUDA_OK(cudaMemcpy(iters, h->d_iters, sizeof(long long) * (size_t)h->ncell, cudaMemcpyDeviceToHost));
+   const size_t n = (size_t)h->ncell;   // device arrays are in slot order
+   if (fatal) {
+      std::vector<int> tmp(n);
+      CUDA_OK(cudaMemcpy(tmp.data(), h->d_fatal, sizeof(int) * n, cudaMemcpyDeviceToHost));
+      for (size_t sl = 0; sl < n; sl++) fatal[(size_t)h->cell_of_slot[sl]] = tmp[sl];
+   }
+   if (iters) {
+      std::vector<long long> tmp(n);
+      CUDA_OK(cudaMemcpy(tmp.data(), h->d_iters, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+      for (size_t sl = 0; sl < n; sl++) iters[(size_t)h->cell_of_slot[sl]] = tmp[sl];
+   }
    if (warn2) {
       std::vector<unsigned long long> tmp(2 * (size_t)h->stride);
       CUDA_OK(cudaMemcpy(tmp.data(), h->d_warn, sizeof(unsigned long long) * tmp.size(), cudaMemcpyDeviceToHost));
-      for (int c = 0; c < h->ncell; c++) {
-         warn2[2 * (size_t)c] = tmp[(size_t)c];
-         warn2[2 * (size_t)c + 1] = tmp[(size_t)h->stride + c];
+      for (size_t sl = 0; sl < n; sl++) {
+         const size_t c = (size_t)h->cell_of_slot[sl];
+         warn2[2 * c] = tmp[sl];
+         warn2[2 * c + 1] = tmp[(size_t)h->stride + sl];
       }
    }
    return SUEWS_OK;
@@ -1124,6 +1339,21 @@ int suews_b200_selftest_math(long long n, unsigned long long seed, long long *ba
    cudaFree(d);
    if (bad_exp) *bad_exp = (long long)h[0];
    if (bad_log) *bad_log = (long long)h[1];
+   return SUEWS_OK;
+}
+
+int suews_b200_selftest_latvap(long long n, unsigned long long seed, long long *bad)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(SUEWS_E_NO_DEVICE, "no CUDA device");
+   unsigned long long *d = nullptr, h = 0;
+   CUDA_OK(cudaMalloc(&d, sizeof(h)));
+   CUDA_OK(cudaMemset(d, 0, sizeof(h)));
+   suews_latvap_selftest_kernel<<<148 * 4, 256>>>(n, seed, d);
+   CUDA_OK(cudaGetLastError());
+   CUDA_OK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+   cudaFree(d);
+   if (bad) *bad = (long long)h;
    return SUEWS_OK;
 }
 

@@ -1,6 +1,6 @@
 // suews_kernel.cuh -- the timestep kernel of libsuews_b200.so: launch arguments, shared-memory staging helpers and
-// suews_run_kernel<FULL, BLOCK, MINBLOCKS>.  Included by suews_b200.cu (host side + the 1024-thread geometry) and by
-// suews_kernel_small.cu (the 256-thread geometry), so that the two instantiations compile in parallel.
+// suews_run_kernel<K, SNOW, ESTM, BLOCK, MINBLOCKS>.  Included by suews_b200.cu (host side) and by suews_kernel_inst.cu,
+// which the Makefile compiles once per kernel instance (separate translation units: they compile side by side).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -25,20 +25,22 @@
 
 struct SuRunArgs {
    const SuewsClassParams *classes;
-   const int *class_of_cell;
-   const int *tz_of_cell;
-   const int *order;            // thread slot -> cell (cells of similar cost share a warp, see upload)
+   const int *class_of_slot;    // per-cell arrays of the device are all in thread-slot order (see upload)
+   const int *tz_of_slot;
+   const int *order;            // thread slot -> cell (only the cell-ordered full blocks of policy P2 need it)
+   int slot0, nslot;            // the bucket of thread slots this launch covers
+   int roll_tstep_prev;         // 1: tstep_prev follows the steps of the launch (batched API); 0: constant (reference-shaped call)
    const double *cellp;
    double *state;
    const SuewsStepRec *steps;   // already offset to step0
    const SuewsEphem *ephem;     // [ntz][nsteps_total], offset to step0 inside
    long long ephem_tz_stride;
-   double *sums;                // [82][stride] or NULL
+   double *sums;                // [82][stride] (slot order) or NULL
    int sum7;                    // 1: accumulate only the seven parity columns (SUEWS_OUT_SUM7)
    int flux_only;               // 1: SUEWS_OUT_FLUX_ONLY (diagnostics no requested output depends on are skipped)
-   int *fatal;                  // [ncell]
+   int *fatal;                  // [stride] (slot order)
    unsigned long long *warn;    // [2][stride]
-   long long *iters;            // [ncell]
+   long long *iters;            // [stride] (slot order)
    // full output (SUEWS_OUT_FULL): per cell column-major [nsteps x ncol]
    double *blkSUEWS, *blkSnow, *blkRSL, *blkDaily, *blkSOL, *blkESTM;
    // ESTM (StorageHeatMethod 4/14): per-cell element temperatures [SUEWS_N_ESTM_DBL][stride] and the shared
@@ -105,18 +107,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 // (128 registers).  A 10 000-cell batch -- supy's scale -- occupies 40 SMs this way instead of 10.
 #define SU_BLOCK_SMALL 256
 #define SU_MINBLOCKS_SMALL 2
-// defined in suews_kernel_small.cu (its own translation unit, so the two geometries compile side by side)
-cudaError_t suews_launch_small(bool full, int grid, cudaStream_t stream, const struct SuRunArgs &a);
 
-template <bool FULL, int BLOCK, int MINBLOCKS>
+// Kernel variants.  A launch covers one BUCKET of cells (upload() sorts the thread slots by bucket, class and canopy
+// height): cells whose classes agree on snowUse and on ESTM, so that those switches -- and the output policy -- are
+// template parameters and the code of the schemes a bucket does not run is not in its instruction stream at all.
+//   K     output kind: SU_K_FULL every output line of every step (reference SUEWS_cal_multitsteps semantics, policy P2),
+//         SU_K_ACC the 82-column line accumulated (running sums P0+, or the in-kernel aggregation P1; also P0 for the
+//         buckets without a specialised instance), SU_K_P0 the seven parity sums only (policy P0: no output line is formed)
+//   SNOW  1 / 0: every / no class of the bucket has snowUse = 1; -1: decided per class at run time
+//   ESTM  0: no class of the bucket runs StorageHeatMethod 4/14; -1: decided per class at run time
+enum { SU_K_FULL = 0, SU_K_ACC = 1, SU_K_P0 = 2 };
+// the launchers are generated by suews_kernel_inst.cu, one translation unit per instance (they compile side by side)
+#define SU_LAUNCHER_NAME_(k, s, e, b) suews_launch_k##k##_s##s##_e##e##_b##b
+#define SU_LAUNCHER_NAME(k, s, e, b) SU_LAUNCHER_NAME_(k, s, e, b)
+#define SU_DECL_LAUNCHER(k, s, e, b) cudaError_t SU_LAUNCHER_NAME(k, s, e, b)(int grid, cudaStream_t stream, const struct SuRunArgs &a)
+// (template arguments -1 are spelled m1 in the launcher names)
+SU_DECL_LAUNCHER(0, m1, m1, 1024);
+SU_DECL_LAUNCHER(0, m1, m1, 256);
+SU_DECL_LAUNCHER(1, m1, m1, 1024);
+SU_DECL_LAUNCHER(1, m1, m1, 256);
+SU_DECL_LAUNCHER(1, 0, 0, 1024);
+SU_DECL_LAUNCHER(2, 0, 0, 1024);
+SU_DECL_LAUNCHER(2, 1, 0, 1024);
+
+template <int K, int SNOWK, int ESTMK, int BLOCK, int MINBLOCKS>
 __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a)
 {
+   constexpr bool FULL = (K == SU_K_FULL);
    __shared__ alignas(128) SuewsStepRec sm_steps[2][SU_CHUNK];
    __shared__ alignas(8) uint64_t sm_bar[2];
 
-   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-   const bool active = slot < a.ncell;
-   const int cell = active ? a.order[slot] : 0;
+   const int slot = a.slot0 + blockIdx.x * blockDim.x + threadIdx.x;
+   const bool active = slot < a.slot0 + a.nslot;
    const int nchunk = (a.nsteps + SU_CHUNK - 1) / SU_CHUNK;
 
    if (threadIdx.x == 0) {
@@ -131,45 +153,47 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
       bulk_g2s(&sm_steps[0][0], a.steps, n0, &sm_bar[0]);
    }
 
-   // ---- per-thread residents: cell parameters, state, accumulators
+   // ---- per-thread residents: cell parameters, state, accumulators.  Every per-cell array of the device is in
+   // thread-slot order, so each of these loads and stores is one contiguous line per warp.
    SuewsCellParams C;
    SuewsCellState S;
    SuDiag dg;
    dg.fatal = 0; dg.warn[0] = 0; dg.warn[1] = 0;
-   double acc[SUEWS_NCOL_SUEWS];
+   double acc[(K == SU_K_P0) ? 1 : SUEWS_NCOL_SUEWS];
    double acc7[7] = {0, 0, 0, 0, 0, 0, 0};
    long long iters = 0;
    int cls = 0, tz = 0;
    SuewsEstmState ES;
-   if (active && a.estm) {
+   const bool estm_on = (ESTMK != 0) && a.estm;
+   if (active && estm_on) {
       double *ep = reinterpret_cast<double *>(&ES);
 #pragma unroll 1
       for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) ep[j] = a.estm[(size_t)j * a.stride + slot];
    }
    if (active) {
-      cls = a.class_of_cell[cell];
-      tz = a.tz_of_cell[cell];
+      cls = a.class_of_slot[slot];
+      tz = a.tz_of_slot[slot];
       double *cp = reinterpret_cast<double *>(&C);
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_CELL_DBL; j++) cp[j] = a.cellp[(size_t)j * a.stride + slot];   // slot order: coalesced
+      for (int j = 0; j < SUEWS_N_CELL_DBL; j++) cp[j] = a.cellp[(size_t)j * a.stride + slot];
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
       for (int j = 0; j < SUEWS_N_STATE_DBL; j++) sp[j] = a.state[(size_t)j * a.stride + slot];
-      dg.fatal = a.fatal[cell];
-      dg.warn[0] = a.warn[cell];
-      dg.warn[1] = a.warn[a.stride + cell];
-      if (a.agg) {
+      dg.fatal = a.fatal[slot];
+      dg.warn[0] = a.warn[slot];
+      dg.warn[1] = a.warn[a.stride + slot];
+      if (K != SU_K_P0 && a.agg) {
          for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = 0.0;
-      } else if (a.sums && !a.sum7) {
+      } else if (K != SU_K_P0 && a.sums && !a.sum7) {
 #pragma unroll 1
-         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = a.sums[(size_t)c * a.stride + cell];
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = a.sums[(size_t)c * a.stride + slot];
       } else if (a.sums) {
-         for (int c = 0; c < 7; c++) acc7[c] = a.sums[(size_t)su_parity_col(c) * a.stride + cell];
+         for (int c = 0; c < 7; c++) acc7[c] = a.sums[(size_t)su_parity_col(c) * a.stride + slot];
       }
    }
    // "last value" columns as a bit mask; only the aggregating policy overwrites instead of summing
    unsigned long long last_lo = 0, last_hi = 0;
-   if (a.agg)
+   if (K != SU_K_P0 && a.agg)
       for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
          if (su_agg82[c] == 2) { if (c < 64) last_lo |= 1ull << c; else last_hi |= 1ull << (c - 64); }
    // the daily state lives in its own record for the length of the launch (dev_step.cuh, stage_pre_atm)
@@ -182,10 +206,14 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    D.DecidStoreCap = SU_SDP(S.StoreDrainPrm.v, 5, DECID);
    D.deltaLAI = 0;
    const SuewsClassParams &P = a.classes[cls];
+   SuSite site;
+   site.spa.x = 0; site.spa.y = 0; site.spa.sin_lat = 0; site.spa.cos_lat = 1; site.veg029 = 0;
+   if (active) su_site_consts(C, site);
    const SuewsEphem *eph = a.ephem + (size_t)tz * a.ephem_tz_stride;
    int dt_since_start = a.dt_since_start;
    int tstep_prev = a.tstep_prev;
    int n_day_rows = 0;
+   const int cell = (FULL && active) ? a.order[slot] : 0;   // the reference-shaped blocks of policy P2 are in cell order
 
    for (int ch = 0; ch < nchunk; ch++) {
       const int buf = ch & 1;
@@ -205,39 +233,45 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
          SuLines L;
          L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr; L.sol26 = nullptr;
          L.estm27 = nullptr;
-         double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY], l_so[SUEWS_NCOL_SOLWEIG];
-         double l_es[SUEWS_NCOL_ESTM];
+         double l_dt[FULL ? 5 : 1], l_su[FULL ? SUEWS_NCOL_SUEWS : 1], l_sn[FULL ? SUEWS_NCOL_SNOW : 1], l_rs[FULL ? SUEWS_NCOL_RSL : 1],
+            l_da[(K != SU_K_P0) ? SUEWS_NCOL_DAILY : 1], l_so[FULL ? SUEWS_NCOL_SOLWEIG : 1];
+         double l_es[FULL ? SUEWS_NCOL_ESTM : 1];
          if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; L.estm27 = l_es; }
          // policy P1 also keeps the DailyState line, which only exists on the last step of a day (dailystate.f95:1094)
-         const bool day_end = a.agg_daily && (sm_steps[buf][t].it * 3600 + sm_steps[buf][t].imin * 60 + a.tstep) >= 86400;
+         const bool day_end = (K != SU_K_P0) && a.agg_daily &&
+                              (sm_steps[buf][t].it * 3600 + sm_steps[buf][t].imin * 60 + a.tstep) >= 86400;
          if (day_end) L.daily45 = l_da;
          // every thread of the block enters the step (phase barriers inside); only live cells compute
-         iters += suews_step(live, dg, P, C, sm_steps[buf][t], eph[gs], dt_since_start, tstep_prev, S, D,
-                             (a.agg || (a.sums && !a.sum7)) ? acc : nullptr, (!a.agg && a.sums && a.sum7) ? acc7 : nullptr, L,
-                             a.estm ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
-                             a.flux_only != 0);
-         if (day_end) {
-            if (live && dg.fatal == 0 && n_day_rows < a.agg_daily_rows) {
-               const SuewsStepRec &R = sm_steps[buf][t];
-               double *o = a.agg_daily + (size_t)n_day_rows * (SUEWS_NCOL_DAILY + 5) * (size_t)a.stride + slot;
-               o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
-               o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
+         iters += suews_step<K, SNOWK, ESTMK>(live, dg, P, C, site, sm_steps[buf][t], eph[gs], dt_since_start,
+                                            a.roll_tstep_prev ? tstep_prev : a.tstep_prev, S, D,
+                                            (K != SU_K_P0 && (a.agg || (a.sums && !a.sum7))) ? acc : nullptr,
+                                            ((K == SU_K_P0 || !a.agg) && a.sums && a.sum7) ? acc7 : nullptr, L,
+                                            estm_on ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
+                                            a.flux_only != 0);
+         if (K != SU_K_P0) {
+            if (day_end) {
+               if (live && dg.fatal == 0 && n_day_rows < a.agg_daily_rows) {
+                  const SuewsStepRec &R = sm_steps[buf][t];
+                  double *o = a.agg_daily + (size_t)n_day_rows * (SUEWS_NCOL_DAILY + 5) * (size_t)a.stride + slot;
+                  o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
+                  o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
 #pragma unroll 1
-               for (int c = 0; c < SUEWS_NCOL_DAILY; c++) o[(size_t)(5 + c) * a.stride] = l_da[c];
+                  for (int c = 0; c < SUEWS_NCOL_DAILY; c++) o[(size_t)(5 + c) * a.stride] = l_da[c];
+               }
+               n_day_rows++;
             }
-            n_day_rows++;
-         }
-         if (a.agg && (gs + 1) % a.agg_nlines == 0) {   // SUEWS_Output_Agg: rows i-nlinesOut+1 .. i -> row i/nlinesOut
-            if (live && dg.fatal == 0) {
-               const SuewsStepRec &R = sm_steps[buf][t];
-               double *o = a.agg + (size_t)((gs + 1) / a.agg_nlines - 1) * (SUEWS_NCOL_SUEWS + 5) * (size_t)a.stride + slot;
-               o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
-               o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
+            if (a.agg && (gs + 1) % a.agg_nlines == 0) {   // SUEWS_Output_Agg: rows i-nlinesOut+1 .. i -> row i/nlinesOut
+               if (live && dg.fatal == 0) {
+                  const SuewsStepRec &R = sm_steps[buf][t];
+                  double *o = a.agg + (size_t)((gs + 1) / a.agg_nlines - 1) * (SUEWS_NCOL_SUEWS + 5) * (size_t)a.stride + slot;
+                  o[0] = (double)R.iy; o[(size_t)a.stride] = (double)R.id; o[2 * (size_t)a.stride] = (double)R.it;
+                  o[3 * (size_t)a.stride] = (double)R.imin; o[4 * (size_t)a.stride] = R.dectime;
 #pragma unroll 1
-               for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
-                  o[(size_t)(5 + c) * a.stride] = (su_agg82[c] == 0) ? acc[c] / a.agg_nlines : acc[c];
+                  for (int c = 0; c < SUEWS_NCOL_SUEWS; c++)
+                     o[(size_t)(5 + c) * a.stride] = (su_agg82[c] == 0) ? acc[c] / a.agg_nlines : acc[c];
+               }
+               for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = 0.0;
             }
-            for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) acc[c] = 0.0;
          }
          if (FULL && live && dg.fatal == 0) {
             const size_t n = (size_t)a.nsteps;
@@ -282,23 +316,22 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
       for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + slot] = sp[j];
-      if (a.estm) {
+      if (estm_on) {
          double *ep = reinterpret_cast<double *>(&ES);
 #pragma unroll 1
          for (int j = 0; j < SUEWS_N_ESTM_DBL; j++) a.estm[(size_t)j * a.stride + slot] = ep[j];
       }
-      a.fatal[cell] = dg.fatal;
-      a.warn[cell] = dg.warn[0];
-      a.warn[a.stride + cell] = dg.warn[1];
-      a.iters[cell] += iters;
-      if (a.agg) {
+      a.fatal[slot] = dg.fatal;
+      a.warn[slot] = dg.warn[0];
+      a.warn[a.stride + slot] = dg.warn[1];
+      a.iters[slot] += iters;
+      if (K != SU_K_P0 && a.agg) {
          // partial periods at the end of a block are dropped, as INT(irMax/nlinesOut) drops them
-      } else if (a.sums && !a.sum7) {
+      } else if (K != SU_K_P0 && a.sums && !a.sum7) {
 #pragma unroll 1
-         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) a.sums[(size_t)c * a.stride + cell] = acc[c];
+         for (int c = 0; c < SUEWS_NCOL_SUEWS; c++) a.sums[(size_t)c * a.stride + slot] = acc[c];
       } else if (a.sums) {
-         for (int c = 0; c < 7; c++) a.sums[(size_t)su_parity_col(c) * a.stride + cell] = acc7[c];
+         for (int c = 0; c < 7; c++) a.sums[(size_t)su_parity_col(c) * a.stride + slot] = acc7[c];
       }
    }
 }
-

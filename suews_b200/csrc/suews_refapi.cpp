@@ -87,8 +87,12 @@ std::string lower(const char *s)
 
 int ensure_handle()
 {
-   if (g_h) return SUEWS_OK;
-   return suews_b200_create(1, 1, 0, &g_h);
+   if (!g_h) {
+      int rc = suews_b200_create(1, 1, 0, &g_h);
+      if (rc) return rc;
+      suews_b200_set_tstep_prev_rolls(g_h, 0);   // tstep_prev is INTENT(IN): the same value for every step of a call
+   }
+   return suews_b200_restart(g_h);   // every call passes all of its arguments: nothing of the previous call is kept
 }
 
 // Push every argument that is a library field (parameters and evolving state) into the batch.
@@ -307,15 +311,26 @@ int suews_cal_main_c(void *const *args, int nargs)
 // gfortran external-procedure ABI (lower-case name + underscore, everything by reference): a reference build
 // that drops its own SUEWS_cal_Main / SUEWS_cal_multitsteps links against these without source changes
 // beyond the CALL site.  Errors: suews_last_error().
+// A non-zero return is the reference's STOP (ErrorHint fatal, suews_ctrl_error.f95:392-415): the message goes to stderr
+// and the process ends, unless SUEWS_B200_NO_STOP is set, in which case the caller must check suews_last_error().
+static void fortran_stop(int rc)
+{
+   if (rc == 0 || getenv("SUEWS_B200_NO_STOP")) return;
+   char msg[256];
+   int code = 0;
+   suews_last_error(&code, msg, (int)sizeof(msg));
+   fprintf(stderr, " ERROR! Program stopped! See problems.txt.\n %s\nSTOP Fatal error in SUEWS!\n", msg);
+   exit(1);
+}
 void suews_cal_main_(SUEWS_CAL_MAIN_PARAMS)
 {
    void *p[] = {SUEWS_CAL_MAIN_PTRS};
-   (void)suews_cal_main_c(p, (int)(sizeof(p) / sizeof(p[0])));
+   fortran_stop(suews_cal_main_c(p, (int)(sizeof(p) / sizeof(p[0]))));
 }
 void suews_cal_multitsteps_(SUEWS_CAL_MULTITSTEPS_PARAMS)
 {
    void *p[] = {SUEWS_CAL_MULTITSTEPS_PTRS};
-   (void)suews_cal_multitsteps_c(p, (int)(sizeof(p) / sizeof(p[0])));
+   fortran_stop(suews_cal_multitsteps_c(p, (int)(sizeof(p) / sizeof(p[0]))));
 }
 
 int suews_output_size(int *nVar)

@@ -705,13 +705,14 @@ def test_device_estm_forcing_disaggregation(method):
 
 @pytest.mark.gpu
 def test_flux_only_policy_changes_no_flux_and_no_state():
-    """SUEWS_OUT_FLUX_ONLY skips the roughness-sublayer diagnostics: the seven flux sums and the evolving state are
-    bit-identical to the full step's (only the library's own z0_RSL memo differs)"""
-    from suews_b200 import OUT_FLUX_ONLY, OUT_SUM7, SuewsBatch, synth
+    """Policy P0 (SUEWS_OUT_SUM7 alone) skips the roughness-sublayer diagnostics, which its seven sums cannot observe:
+    the flux sums and the evolving state are bit-identical to those of a launch that runs every stage
+    (SUEWS_OUT_ALL_STAGES); only the library's own z0_RSL memo differs"""
+    from suews_b200 import OUT_ALL_STAGES, OUT_SUM7, SuewsBatch, synth
     base = fx.state_init(2005)
     met = fx.forcing(2005)[:576]
     res = []
-    for flags in (OUT_SUM7, OUT_SUM7 | OUT_FLUX_ONLY):
+    for flags in (OUT_SUM7 | OUT_ALL_STAGES, OUT_SUM7):
         b = SuewsBatch(256, 1)
         synth.build_batch(b, base, cell0=0, scheme="default")
         b.upload()

@@ -7,7 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 from suews_b200 import OUT_SUM7, OUT_SUM82, SuewsBatch, synth
+from suews_b200.batch import OUT_ALL_STAGES
 OUT = OUT_SUM82 if os.environ.get('SU_SUMS', '7') == '82' else OUT_SUM7   # output policy of the profiled launches
+if os.environ.get('SU_ALL_STAGES', '0') == '1':   # P0 with the diagnostics its sums cannot observe (T2/q2/U10/RH2) kept
+    OUT |= OUT_ALL_STAGES
 
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 37888
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 48
