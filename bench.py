@@ -4,8 +4,11 @@
 Workload (BASELINE.json configs[2]): synthetic 1 048 576 cells per GPU, BaseRun cell with per-cell
 surface fractions / location / morphology / forcing offsets, default scheme set
 (NetRadiationMethod 3, OHM, LUMPS first guess, StabilityMethod 3, snow off), forcing = the reference's
-2004 hourly series disaggregated to 5 min.  One bench "step" advances every cell by one day
-(288 timesteps) in ONE kernel launch; consecutive steps are consecutive days.
+2004 hourly series disaggregated to 5 min (the whole leap year, 105 408 rows, resident on the device).
+One bench "step" advances every cell by one day (288 timesteps) in ONE kernel launch.  The K timed days are spread
+evenly over the year (day 366*i/K of 2004: with the driver's --steps 20 every 18th day), so that the figure is the
+year's mix of winter / summer, day / night physics and not that of one month; the state is carried from launch to
+launch, only the forcing rows jump.
 
   value  whole-job cell-timesteps/s with forcing + state resident in HBM (CUDA-event time of the
          kernel launches, max over ranks)
@@ -79,20 +82,24 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------ CPU arm (oracle)
 def _cpu_worker(args):
-    worker, budget_s, max_cells, scheme = args
+    worker, budget_s, max_cells, scheme, days = args
     import fixtures as fx
     import oracle_lib as ol
     from suews_b200 import synth
-    base, met = load_inputs(1)
+    base, met_year = load_inputs(366)
     d = synth.base_with_scheme(base, scheme)
     site = synth.cell_site_arrays(worker * max_cells, max_cells, d)
-    ts5 = None
+    ts5 = ts5_year = None
     if synth.SCHEMES[scheme]["storageheatmethod"] in (4, 14):
         d.update({k.lower(): v for k, v in synth.estm_example(d["surfacearea"][0]).items()})
-        ts5 = synth.estm_ts_forcing(met)
+        ts5_year = synth.estm_ts_forcing(met_year)
     t0 = time.perf_counter()
     done = 0
     for c in range(max_cells):
+        day = days[c % len(days)]                      # one day per cell, cycling through the bench's days of the year
+        met = met_year[day * 288:(day + 1) * 288]
+        if ts5_year is not None:
+            ts5 = ts5_year[day * 288:(day + 1) * 288]
         dd = dict(d)
         for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
             dd[k.lower()] = np.atleast_1d(site[k][c])
@@ -109,18 +116,50 @@ def _cpu_worker(args):
     return done, time.perf_counter() - t0
 
 
-def cpu_arm(budget_s, scheme, cores=None):
+def cpu_arm(budget_s, scheme, cores=None, days=(0,)):
     import multiprocessing as mp
     import oracle_lib as ol
     ol.build()
     cores = cores or os.cpu_count() or 1
     with mp.get_context("fork").Pool(cores) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(w, budget_s, 4096, scheme) for w in range(cores)])
+        res = pool.map(_cpu_worker, [(w, budget_s, 4096, scheme, list(days)) for w in range(cores)])
         wall = time.perf_counter() - t0
     cells = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
     return cells * 288 / slowest, cores, cells, slowest, wall
+
+
+def year_days(K, W, ndays_year=366):
+    """forcing day of each launch: W warm-up days ahead of the first timed day, then K days spread over the year"""
+    timed = [min(ndays_year - 1, (i * ndays_year) // max(K, 1)) for i in range(K)]
+    warm = [(timed[0] + ndays_year - W + i) % ndays_year for i in range(W)] if K else list(range(W))
+    return warm, timed
+
+
+def run_scheme(SuewsBatch, synth, base, met, ncell, rank, local_rank, scheme, days_warm, days_timed, OUT, barrier_extra=None):
+    """device-resident timing of one scheme set on the given forcing days; returns (seconds, trips per step, fatal cells)"""
+    use_estm = synth.SCHEMES[scheme]["storageheatmethod"] in (4, 14)
+    b = SuewsBatch(ncell, 1, device=local_rank)
+    ts5 = synth.estm_ts_forcing(met) if use_estm else None
+    synth.build_batch(b, base, cell0=rank * ncell, scheme=scheme, ts_row0=ts5[0] if use_estm else None)
+    b.upload()
+    b.set_forcing(met)
+    if use_estm:
+        b.set_estm_forcing(ts5)
+    for d in days_warm:
+        b.advance(d * 288, 288, OUT, sync=False)
+    b.device_sync()
+    ms = []
+    for d in days_timed:
+        b.advance(d * 288, 288, OUT, sync=False)
+        ms.append(b.last_ms())
+    b.device_sync()
+    fatal, _warn, iters = b.diag()
+    nl = len(days_warm) + len(days_timed)
+    out = (sum(ms) * 1e-3, float(iters.sum()) / (ncell * 288.0 * nl), int((fatal != 0).sum()))
+    b.close()
+    return out
 
 
 # ------------------------------------------------------------------ main
@@ -134,8 +173,13 @@ def main():
     ap.add_argument("--scheme", default="default")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-flux-only", action="store_true", help="skip the side measurement with SUEWS_OUT_FLUX_ONLY")
+    ap.add_argument("--no-flux-only", action="store_true", help="skip the side measurement with SUEWS_OUT_ALL_STAGES")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the end-to-end region (default: --steps)")
+    ap.add_argument("--consecutive-days", type=int, default=-1,
+                    help="time K consecutive days starting at this day of 2004 instead of K days spread over the year")
+    ap.add_argument("--scheme-steps", type=int, default=4,
+                    help="timed days (spread over the year) of each extra scheme set in the `schemes` object; 0 = skip it")
+    ap.add_argument("--schemes", default="baserun,snow,estm,netrad13", help="scheme sets of the `schemes` object (configs[3])")
     ap.add_argument("--sums", default="parity7", choices=["parity7", "all82", "hourly"],
                     help="on-device output reduction: P0 = running sums of the 7 parity fluxes (SURVEY 8d), of all 82 columns, "
                          "or P1 = the hourly-aggregated 87-column SUEWS block of every cell (SUEWS_Output_Agg in the kernel)")
@@ -144,15 +188,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = "synthetic %d cells/GPU x 288 five-minute steps per bench step, %s schemes, shared 2004 forcing + per-cell dT/dRH" % (
-        a.cells_per_gpu, a.scheme)
+    if a.consecutive_days >= 0:
+        days_warm = [(a.consecutive_days + i) % 366 for i in range(W)]
+        days_timed = [(a.consecutive_days + W + i) % 366 for i in range(K)]
+    else:
+        days_warm, days_timed = year_days(K, W)
+    workload = ("synthetic %d cells/GPU x 1 year (2004) of 5-min forcing sampled as %d one-day launches of 288 steps (days-of-year %s; "
+                "warm-up days %s), %s scheme set (%s), shared forcing + per-cell dT/dRH") % (
+        a.cells_per_gpu, K, ",".join(str(d + 1) for d in days_timed), ",".join(str(d + 1) for d in days_warm), a.scheme,
+        "see suews_b200/synth.py SCHEMES")
 
     if a.impl == "reference":
         if rank != 0:
             return
         rates, info = [], None
         for i in range(W + K):
-            r, cores, cells, slowest, wall = cpu_arm(max(2.0, a.cpu_budget / 2), a.scheme)
+            r, cores, cells, slowest, wall = cpu_arm(max(2.0, a.cpu_budget / 2), a.scheme, days=days_timed)
             if i >= W:
                 rates.append((cells * 288, slowest))
             info = (cores, cells)
@@ -187,8 +238,10 @@ def main():
     OUT = {"parity7": OUT_SUM7, "all82": OUT_SUM82, "hourly": OUT_AGG}[a.sums]
     n_sum = 7 if a.sums == "parity7" else N_SUM
     use_estm = synth.SCHEMES[a.scheme]["storageheatmethod"] in (4, 14)
-    ndays = 2 * (W + K)   # device-resident region + end-to-end region (which may use fewer days: --e2e-steps)
-    base, met = load_inputs(ndays)
+    base, met = load_inputs(366)   # the whole year 2004 at 5 min: 105 408 rows, 16.9 MB of step records on the device
+    sch = synth.SCHEMES[a.scheme]
+    workload = workload.replace("see suews_b200/synth.py SCHEMES", "snowUse %d, NetRadiationMethod %d, StorageHeatMethod %d, StabilityMethod %d, EmissionsMethod %d" % (
+        sch["snowuse"], sch["netradiationmethod"], sch["storageheatmethod"], sch["stabilitymethod"], sch["emissionsmethod"]))
     ncell = a.cells_per_gpu
     b = SuewsBatch(ncell, 1, device=local_rank)
     ts5 = synth.estm_ts_forcing(met) if use_estm else None   # synthetic Ts forcing = air temperature
@@ -203,18 +256,20 @@ def main():
             torch.cuda.synchronize()
 
     # ---------------- device-resident timing
-    b.set_forcing(met[: (W + K) * 288])
+    b.set_forcing(met)
     if use_estm:
-        b.set_estm_forcing(ts5[: (W + K) * 288])
-    for i in range(W):
-        b.advance(i * 288, 288, OUT, sync=False)
+        b.set_estm_forcing(ts5)
+    for d in days_warm:
+        b.advance(d * 288, 288, OUT, sync=False)
+    barrier()
+    _f0, _w0, iters_before = b.diag()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0 = time.perf_counter()
     ms = []
-    for i in range(W, W + K):
-        b.advance(i * 288, 288, OUT, sync=False)
+    for d in days_timed:
+        b.advance(d * 288, 288, OUT, sync=False)
         ms.append(b.last_ms())   # CUDA events recorded on the library's launch stream
     barrier()
     wall = time.perf_counter() - t0
@@ -229,14 +284,18 @@ def main():
     total_cs = float(world) * ncell * 288 * K
     value = total_cs / dev_s
 
-    # ---------------- side measurement (not the headline): the same days with the opt-in SUEWS_OUT_FLUX_ONLY policy, which
-    # skips the roughness-sublayer diagnostics T2/q2/U10/RH2 -- nothing the seven flux sums or the state depend on
-    flux_only = None
+    _f0, _w0, iters_after = b.diag()
+    trips_per_step = float(iters_after.sum() - iters_before.sum()) / (ncell * 288.0 * max(K, 1))
+
+    # ---------------- side measurement (not the headline): policy P0 forms only what its seven sums can observe, so the
+    # roughness-sublayer diagnostics T2/q2/U10/RH2 are not evaluated; SUEWS_OUT_ALL_STAGES runs them anyway
+    all_stages = None
     if a.sums == "parity7" and not a.no_flux_only:
-        from suews_b200 import OUT_FLUX_ONLY
+        from suews_b200.batch import OUT_ALL_STAGES
         ms2 = []
-        for i in range(W, W + K):
-            b.advance(i * 288, 288, OUT | OUT_FLUX_ONLY, sync=False)
+        sub = days_timed[:: max(1, len(days_timed) // 4)][:4]
+        for d in sub:
+            b.advance(d * 288, 288, OUT | OUT_ALL_STAGES, sync=False)
             ms2.append(b.last_ms())
         barrier()
         fo_s = sum(ms2) * 1e-3
@@ -245,19 +304,20 @@ def main():
             t = torch.tensor([fo_s], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             fo_s = float(t[0])
-        flux_only = {"value": total_cs / fo_s, "unit": UNIT,
-                     "note": "opt-in SUEWS_OUT_FLUX_ONLY: RSL diagnostics (T2, q2, U10, RH2) skipped; identical flux sums and state; "
-                             "same forcing days re-run from the advanced state; NOT the headline value"}
+        all_stages = {"value": float(world) * ncell * 288 * len(sub) / fo_s, "unit": UNIT,
+                      "note": "SUEWS_OUT_ALL_STAGES: every stage of SUEWS_cal_Main, including the RSL diagnostics T2/q2/U10/RH2 that the seven "
+                              "flux sums of policy P0 cannot observe; identical sums and state; days-of-year %s re-run from the advanced "
+                              "state; NOT the headline value" % ",".join(str(d + 1) for d in sub)}
 
     # ---------------- end-to-end through the host API (host buffers in, host results out)
     e2e_t0 = None
     cols = PARITY_COLS
     Ke = a.e2e_steps if a.e2e_steps > 0 else K
-    for i in range(W + Ke):
+    e2e_days = days_warm + [days_timed[i % max(K, 1)] for i in range(Ke)]   # the same days again, forcing from the host
+    for i, d0 in enumerate(e2e_days):
         if i == W:
             barrier()
             e2e_t0 = time.perf_counter()
-        d0 = (W + K + i) % (met.shape[0] // 288)    # (wraps when the device-resident region already used the whole series)
         day = met[d0 * 288:(d0 + 1) * 288]
         b.set_forcing(day)                      # host -> device (pinned staging) + ephemeris kernel
         if use_estm:
@@ -276,7 +336,23 @@ def main():
         e2e_s = float(t[0])
     e2e_val = float(world) * ncell * 288 * Ke / e2e_s
     checksum = float(np.sum(res[:, 0]))
+    nonfinite_cells = int((~np.isfinite(res).all(axis=1)).sum())
     fatal, warn, iters = b.diag()
+    b.close()
+
+    # ---------------- BASELINE configs[3]: the other scheme sets on the same cells, days spread over the year (N = 1 only)
+    schemes = None
+    if world == 1 and a.scheme_steps > 0 and a.sums == "parity7":
+        schemes = {}
+        _w, sdays = year_days(a.scheme_steps, 0)
+        sdays = [min(365, d + 9) for d in sdays]   # (days 10, 101, 192, 284 for 4 steps: mid-winter to autumn)
+        for name in [x for x in a.schemes.split(",") if x]:
+            sec, trips, nfatal = run_scheme(SuewsBatch, synth, base, met, ncell, rank, local_rank, name, [sdays[0] - 1], sdays, OUT)
+            sc = synth.SCHEMES[name]
+            schemes[name] = {"value": ncell * 288.0 * len(sdays) / sec, "unit": UNIT, "steps": len(sdays), "warmup": 1,
+                             "days_of_year": [d + 1 for d in sdays], "tsurf_iterations_per_step": trips, "fatal_cells": nfatal,
+                             "switches": "snowUse %d, NetRadiationMethod %d, StorageHeatMethod %d" % (
+                                 sc["snowuse"], sc["netradiationmethod"], sc["storageheatmethod"])}
 
     if rank != 0:
         return
@@ -319,8 +395,8 @@ def main():
                        "all82": "P0+: per-cell running sums of all 82 SUEWS columns",
                        "hourly": "P1: hourly-aggregated 87-column SUEWS block of every cell, aggregated in the kernel"}[a.sums],
                    "l2": "inputs (state+params %.0f MB/GPU) larger than L2" % (ncell * 8.0 * (N_STATE + N_CELL + N_SUM) / 1e6),
-                   "tsurf_iterations_per_step": float(iters.sum()) / (ncell * 288.0 * ((W + K) + (K if flux_only else 0) + (W + Ke))), "wall_s_timed": wall,
-                   "checksum_QN": checksum, "fatal_cells": int((fatal != 0).sum())},
+                   "tsurf_iterations_per_step": trips_per_step, "wall_s_timed": wall,
+                   "checksum_QN": checksum, "fatal_cells": int((fatal != 0).sum()), "nonfinite_sum_cells": nonfinite_cells},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 288 * 160, "d2h_bytes_per_step": ncell * len(cols) * 8},
         "gpu_launches": K,
         "clocks": sampler.summary(),
@@ -329,14 +405,15 @@ def main():
                      "note": "kernel is FP64-pipe / latency bound, not HBM bound (SURVEY 8d); see fp64"},
         "fp64": fp64,
     }
-    if flux_only:
-        line["flux_only"] = flux_only
+    if all_stages:
+        line["all_stages"] = all_stages
+    if schemes:
+        line["schemes"] = schemes
     if world == 1 and not a.no_cpu_baseline:
-        r, cores, cells, slowest, _ = cpu_arm(a.cpu_budget, a.scheme)
+        r, cores, cells, slowest, _ = cpu_arm(a.cpu_budget, a.scheme, days=days_timed)
         line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d cells x 288 steps of the same synthetic workload, one process per core (%.1f s)" % (cells, slowest)}
+                                "sample": "%d cells x 288 steps (one day each, cycling through the bench's days of the year) of the same synthetic cells, one process per core (%.1f s)" % (cells, slowest)}
     print(json.dumps(line))
-    b.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -228,6 +228,40 @@ int suews_b200_selftest_latvap(long long n, unsigned long long seed, long long *
 /* last error of the calling thread: code and human-readable message */
 int suews_last_error(int *code, char *buf, int len);
 
+/* ---- several GPUs of one box behind one handle ---------------------------------------------------
+ * Cells are independent (driver.f95:478-486: the inter-grid terms are zero; Test_SUEWS.py:384 checks multi-grid ==
+ * single-grid), so a run is partitioned in contiguous blocks of the cell index, one block per device, with no exchange
+ * while the steps advance: one host thread drives every device through its own stream (all calls below are
+ * asynchronous launches), the forcing block is replicated (20 MB per year), and the only cross-device traffic is the
+ * final gather of the reduced outputs -- the per-cell running sums, 8 B per cell and column -- to the first device over
+ * NVLink (cudaMemcpyPeerAsync) and from there to the host.  This is what the reference's serial grid loop
+ * (suews_program.f95:606-623) becomes on an 8-GPU box; a Fortran or Python host needs no process per GPU.
+ * devices == NULL: devices 0 .. ndev-1.  A device may be listed more than once (two blocks on one GPU).
+ * Setters take the arrays of the WHOLE run, [ncell][n] cell-major, exactly like the single-device calls. */
+typedef struct suews_b200_multi_s *suews_b200_multi;
+int suews_b200_multi_create(int ncell, int nclass, int ndev, const int *devices, suews_b200_multi *out);
+int suews_b200_multi_destroy(suews_b200_multi m);
+int suews_b200_multi_ndev(suews_b200_multi m, int *ndev);
+/* block d of the partition: its single-device handle, first cell and cell count */
+int suews_b200_multi_part(suews_b200_multi m, int d, suews_b200_handle *h, int *cell0, int *ncell);
+int suews_b200_multi_set_class_param(suews_b200_multi m, int cls, const char *name, const double *vals, int n);
+int suews_b200_multi_set_cell_param(suews_b200_multi m, const char *name, const double *vals, int n);
+int suews_b200_multi_set_cell_class(suews_b200_multi m, const int *class_of_cell);
+int suews_b200_multi_set_state(suews_b200_multi m, const char *name, const double *vals, int n);
+int suews_b200_multi_get_state(suews_b200_multi m, const char *name, double *vals, int n);
+int suews_b200_multi_set_clock(suews_b200_multi m, int dt_since_start, int tstep_prev);
+int suews_b200_multi_upload(suews_b200_multi m);
+int suews_b200_multi_set_forcing(suews_b200_multi m, const double *met, int nsteps);
+int suews_b200_multi_advance(suews_b200_multi m, int step0, int nsteps, int out_flags);   /* every device, asynchronous */
+int suews_b200_multi_sync(suews_b200_multi m);
+/* device time of the last advance: the slowest device's (CUDA events on each device's launch stream) */
+int suews_b200_multi_last_advance_ms(suews_b200_multi m, float *ms);
+/* The final gather: the selected columns of the running sums of every cell, [ncell][ncols] cell-major on the host.  Each
+ * device packs its block in cell order, the blocks travel device -> first device (peer copies) and the whole array goes
+ * to the host in one copy.  gather_ms (may be NULL): wall time of the call in milliseconds. */
+int suews_b200_multi_gather_sums(suews_b200_multi m, const int *cols, int ncols, double *out, float *gather_ms);
+int suews_b200_multi_get_diag(suews_b200_multi m, int *fatal, unsigned long long *warn2, long long *iters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,24 @@ def lib():
         L.suews_b200_get_diag.argtypes = [H, ip, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
         L.suews_b200_last_advance_ms.argtypes = [H, C.POINTER(C.c_float)]
         L.suews_b200_device_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+        M = C.c_void_p
+        L.suews_b200_multi_create.argtypes = [C.c_int, C.c_int, C.c_int, ip, C.POINTER(M)]
+        L.suews_b200_multi_destroy.argtypes = [M]
+        L.suews_b200_multi_ndev.argtypes = [M, ip]
+        L.suews_b200_multi_part.argtypes = [M, C.c_int, C.POINTER(H), ip, ip]
+        L.suews_b200_multi_set_class_param.argtypes = [M, C.c_int, C.c_char_p, dp, C.c_int]
+        L.suews_b200_multi_set_cell_param.argtypes = [M, C.c_char_p, dp, C.c_int]
+        L.suews_b200_multi_set_cell_class.argtypes = [M, ip]
+        L.suews_b200_multi_set_state.argtypes = [M, C.c_char_p, dp, C.c_int]
+        L.suews_b200_multi_get_state.argtypes = [M, C.c_char_p, dp, C.c_int]
+        L.suews_b200_multi_set_clock.argtypes = [M, C.c_int, C.c_int]
+        L.suews_b200_multi_upload.argtypes = [M]
+        L.suews_b200_multi_set_forcing.argtypes = [M, dp, C.c_int]
+        L.suews_b200_multi_advance.argtypes = [M, C.c_int, C.c_int, C.c_int]
+        L.suews_b200_multi_sync.argtypes = [M]
+        L.suews_b200_multi_last_advance_ms.argtypes = [M, C.POINTER(C.c_float)]
+        L.suews_b200_multi_gather_sums.argtypes = [M, ip, C.c_int, dp, C.POINTER(C.c_float)]
+        L.suews_b200_multi_get_diag.argtypes = [M, ip, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
         L.suews_cal_sunposition_c.argtypes = [C.c_double] * 6 + [dp, dp]
         L.suews_last_error.argtypes = [ip, C.c_char_p, C.c_int]
         _lib = L

@@ -241,6 +241,118 @@ class SuewsBatch:
         return fatal, warn, iters
 
 
+class SuewsMultiBatch(SuewsBatch):
+    """The cells of one run spread over several GPUs of one box behind one handle (suews_b200_multi_*,
+    include/suews_b200.h): contiguous blocks of the cell index, one per device, one host thread, no exchange while the
+    steps advance; gather_sums() is the final gather (device -> first device over NVLink -> host).  Setters take the arrays
+    of the whole run, like SuewsBatch."""
+
+    def __init__(self, ncell, nclass=1, devices=None, ndev=None):
+        self.L = _lib.lib()
+        if devices is None:
+            devices = list(range(int(ndev) if ndev else max(1, self.L.suews_b200_device_count())))
+        self.devices = [int(d) for d in devices]
+        self.ncell, self.nclass = int(ncell), int(nclass)
+        self.h = C.c_void_p()
+        dv = (C.c_int * len(self.devices))(*self.devices)
+        check(self.L.suews_b200_multi_create(self.ncell, self.nclass, len(self.devices), dv, C.byref(self.h)))
+        self.nsteps = 0
+        self._class_cache = {}
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.suews_b200_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def parts(self):
+        """[(device, first cell, cell count)] of the partition"""
+        out = []
+        for d in range(len(self.devices)):
+            c0, n = C.c_int(), C.c_int()
+            check(self.L.suews_b200_multi_part(self.h, d, None, C.byref(c0), C.byref(n)))
+            out.append((self.devices[d], c0.value, n.value))
+        return out
+
+    def set_class_param(self, cls, name, vals):
+        a = _arr(np.atleast_1d(vals)).ravel()
+        if int(cls) == 0 and a.size == 1:
+            self._class_cache[name.lower()] = float(a[0])
+        check(self.L.suews_b200_multi_set_class_param(self.h, int(cls), name.encode(), a.ctypes.data_as(dp), a.size))
+
+    def _per_cell(self, name, vals):
+        kind, n = field_info(name)
+        a = _arr(vals)
+        if a.ndim <= 1 and a.size == n:
+            a = np.broadcast_to(a.reshape(1, n), (self.ncell, n))
+        return _arr(a).reshape(self.ncell, n), n
+
+    def set_cell_param(self, name, vals):
+        a, n = self._per_cell(name, vals)
+        check(self.L.suews_b200_multi_set_cell_param(self.h, name.encode(), a.ctypes.data_as(dp), n))
+
+    def set_state(self, name, vals):
+        a, n = self._per_cell(name, vals)
+        check(self.L.suews_b200_multi_set_state(self.h, name.encode(), a.ctypes.data_as(dp), n))
+
+    def get_state(self, name):
+        kind, n = field_info(name)
+        a = np.zeros((self.ncell, n))
+        check(self.L.suews_b200_multi_get_state(self.h, name.encode(), a.ctypes.data_as(dp), n))
+        return a
+
+    def set_cell_class(self, ids):
+        a = np.ascontiguousarray(np.asarray(ids, dtype=np.int32))
+        assert a.size == self.ncell
+        check(self.L.suews_b200_multi_set_cell_class(self.h, a.ctypes.data_as(ip)))
+
+    def set_clock(self, dt_since_start, tstep_prev):
+        check(self.L.suews_b200_multi_set_clock(self.h, int(dt_since_start), int(tstep_prev)))
+
+    def upload(self):
+        check(self.L.suews_b200_multi_upload(self.h))
+
+    def set_forcing(self, met):
+        m = np.asfortranarray(np.asarray(met, dtype=np.float64))
+        assert m.shape[1] == 24
+        check(self.L.suews_b200_multi_set_forcing(self.h, m.ctypes.data_as(dp), m.shape[0]))
+        self.nsteps = m.shape[0]
+
+    def advance(self, step0, nsteps, out_flags=OUT_SUM7, sync=True):
+        check(self.L.suews_b200_multi_advance(self.h, int(step0), int(nsteps), int(out_flags)))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        check(self.L.suews_b200_multi_sync(self.h))
+
+    def last_ms(self):
+        ms = C.c_float()
+        check(self.L.suews_b200_multi_last_advance_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def gather_sums(self, cols):
+        """the final gather: [ncell, len(cols)] on the host; returns (array, milliseconds the gather took)"""
+        c = np.ascontiguousarray(np.asarray(cols, dtype=np.int32))
+        a = np.zeros((self.ncell, c.size))
+        ms = C.c_float()
+        check(self.L.suews_b200_multi_gather_sums(self.h, c.ctypes.data_as(ip), c.size, a.ctypes.data_as(dp), C.byref(ms)))
+        return a, ms.value
+
+    def sums_cols(self, cols):
+        return self.gather_sums(cols)[0]
+
+    def diag(self):
+        fatal = np.zeros(self.ncell, dtype=np.int32)
+        warn = np.zeros((self.ncell, 2), dtype=np.uint64)
+        iters = np.zeros(self.ncell, dtype=np.int64)
+        check(self.L.suews_b200_multi_get_diag(self.h, fatal.ctypes.data_as(ip), warn.ctypes.data_as(C.POINTER(C.c_ulonglong)),
+                                               iters.ctypes.data_as(C.POINTER(C.c_longlong))))
+        return fatal, warn, iters
+
+    def device_sync(self):
+        self.sync()
+
+
 _FIELDS = None
 
 
@@ -252,9 +364,11 @@ def all_fields():
         import re
         hdr = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "suews_fields.h")).read()
         out = []
-        for macro, kind in (("SUEWS_CLASS_INT_FIELDS", 0), ("SUEWS_CLASS_DBL_FIELDS", 1), ("SUEWS_CELL_DBL_FIELDS", 2),
-                            ("SUEWS_STATE_DBL_FIELDS", 3), ("SUEWS_ESTM_STATE_FIELDS", 4)):
-            m = re.search(r"#define %s\(X\)(.*?)\n\n" % macro, hdr, re.S)
+        # (cell parameters and state are listed as COLD fields then HOT fields: the order of the handle's SoA arrays)
+        for macro, kind in (("SUEWS_CLASS_INT_FIELDS", 0), ("SUEWS_CLASS_DBL_FIELDS", 1), ("SUEWS_CELL_COLD_FIELDS", 2),
+                            ("SUEWS_CELL_HOT_FIELDS", 2), ("SUEWS_STATE_COLD_FIELDS", 3), ("SUEWS_STATE_HOT_FIELDS", 3),
+                            ("SUEWS_ESTM_STATE_FIELDS", 4)):
+            m = re.search(r"#define %s\(X\)((?:[^\n]*\\\n)*[^\n]*)\n" % macro, hdr)   # the macro body with its continuation lines
             for nm, n in re.findall(r"X\((\w+),\s*(\d+)\)", m.group(1)):
                 out.append((nm, kind, int(n)))
         _FIELDS = out

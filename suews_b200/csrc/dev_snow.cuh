@@ -188,6 +188,15 @@ struct SuQEWork {
 };
 
 // snow.f95:477-1148 for surface `is` (0-based).  Outputs the five *_tot contributions.
+// The routine only ever touches element `is` of the per-surface work arrays (plus the evaporation surplus of the two
+// impervious surfaces and the flood totals), so it works on register copies of those elements: `in` says where their
+// entry values are read from, and with COMMIT they are written back to w at the end.  COMMIT = false is the evaluation a
+// trip of the surface-temperature loop needs -- qe_tot (and SurplusEvap[is]) by the very same statements, nothing stored:
+// the reference restarts every trip from the *_prev state, so only the last trip's update survives (dev_step.cuh).
+struct SuQEIn {
+   const double *state_id, *soilstore_id, *SnowPack, *SnowFrac, *SnowWater, *SnowDens;
+};
+template <bool COMMIT>
 SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, int is, int imin, int it, int dow,
                        double nsh_real, double lvS_J_kg, double avdens, double avRh, double Press_hPa, double Temp_C,
                        double RAsnow, double psyc_hPa, double avcp, double sIce_hPa, double PervFraction,
@@ -195,7 +204,7 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
                        double rb, double tlv, double Precip, const double *drain, const double *stateOld,
                        const SuSnowHeat &h, const double *Tsurf_ind, const double *StoreDrainPrm, double capStore_is,
                        const double *AddWater,
-                       const double *AddWaterRunoff, SuQEWork &w, double &chSnow_tot, double &ev_tot, double &qe_tot,
+                       const double *AddWaterRunoff, const SuQEIn &in, double *SurplusEvap, SuQEWork &w, double &chSnow_tot, double &ev_tot, double &qe_tot,
                        double &runoff_tot, double &surf_chang_tot)
 {
    const double *sfr = C.sfr.v;
@@ -203,26 +212,40 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
    double runoffSnow = 0, runoff = 0, chang = 0, changSnow = 0, runoffTest = 0, SnowToSurf = 0, EvPart = 0, ev = 0,
           qe = 0, ev_snow = 0, tlv_sub = 0;
    double snowFracFresh1 = 0, snowFracFresh2 = 0, snowFracOld = 0;
-   double *SnowPack = w.SnowPack, *SnowFrac = w.SnowFrac, *SnowWater = w.SnowWater, *state_id = w.state_id,
-          *soilstore_id = w.soilstore_id, *SnowDens = w.SnowDens;
+   double sp_ = in.SnowPack[is], sf_ = in.SnowFrac[is], sw_ = in.SnowWater[is], st_ = in.state_id[is], so_ = in.soilstore_id[is],
+          sd_ = in.SnowDens[is], ic_ = 0;
+   bool ic_set = false;
+   SuFlood fl_local;   // (COMMIT = false: the flood totals are not formed)
+   SuFlood &fl = COMMIT ? w.fl : fl_local;
+   fl_local.runoffAGimpervious = 0; fl_local.surplusWaterBody = 0; fl_local.runoffAGveg = 0; fl_local.runoffPipes = 0; fl_local.runoffWaterBody = 0;
+#define SU_SNOW_COMMIT()                                                                                         \
+   do {                                                                                                          \
+      if (COMMIT) {                                                                                              \
+         w.SnowPack[is] = sp_; w.SnowFrac[is] = sf_; w.SnowWater[is] = sw_; w.state_id[is] = st_;               \
+         w.soilstore_id[is] = so_; w.SnowDens[is] = sd_;                                                         \
+         if (ic_set) w.iceFrac[is] = ic_;                                                                        \
+      }                                                                                                          \
+   } while (0)
    const double mw_ind = h.mw_ind[is], freezMelt = h.FreezMelt[is], FreezState = h.FreezState[is],
                 FreezStateVol = h.FreezStateVol[is], rainOnSnow = h.rainOnSnow[is];
    const int u = (dow == 1 || dow == 7) ? 1 : 0;
    const bool rem_time = (SU_PROF24(P.SnowProf_24hr.v, it, u) == 1 && is < 2 && (imin == (nsh_real - 1) / nsh_real * 60));
 
    ev_tot = 0; qe_tot = 0; runoff_tot = 0; surf_chang_tot = 0; chSnow_tot = 0;
-   w.runoffSoil[is] = 0;
-   for (int k = 0; k < NSURF; k++) w.SnowDepth[k] = 0;   // INTENT(OUT) array reset on every call
+   if (COMMIT) {
+      w.runoffSoil[is] = 0;
+      for (int k = 0; k < NSURF; k++) w.SnowDepth[k] = 0;   // INTENT(OUT) array reset on every call
+   }
 
-   const double snowTotInit = SnowPack[is] + SnowWater[is];
+   const double snowTotInit = sp_ + sw_;
    const double WaterHoldCapFrac =
-      (SnowDens[is] >= 200) ? P.CRWmin : P.CRWmin + (P.CRWmax - P.CRWmin) * (200 - SnowDens[is]) / 200;
+      (sd_ >= 200) ? P.CRWmin : P.CRWmin + (P.CRWmax - P.CRWmin) * (200 - sd_) / 200;
 
-   if (SnowFrac[is] < 1)
-      cal_evap(P.EvapMethod, state_id[is], P.WetThresh[is], capStore_is, vpd_hPa, avdens, avcp, qn_e,
+   if (sf_ < 1)
+      cal_evap(P.EvapMethod, st_, P.WetThresh[is], capStore_is, vpd_hPa, avdens, avcp, qn_e,
                s_hPa, psyc_hPa, ResistSurf, RA, rb, tlv, ev, qe);
 
-   if (SnowFrac[is] > 0) {   // Evap_SUEWS_Snow snow.f95:1154-1207
+   if (sf_ > 0) {   // Evap_SUEWS_Snow snow.f95:1154-1207
       double T = Temp_C;
       double sae_snow = sIce_hPa * (h.Qm_rain[is] - h.Qm_melt[is]);
       double esIce = sat_vap_pressIce(dg, T, Press_hPa, 1);
@@ -235,150 +258,151 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
    }
 
    if (is > 1 && PervFraction != 0)
-      EvPart = su_div0(w.SurplusEvap[PAV] * sfr[PAV] + w.SurplusEvap[BLDG] * sfr[BLDG], PervFraction);
+      EvPart = su_div0(SurplusEvap[PAV] * sfr[PAV] + SurplusEvap[BLDG] * sfr[BLDG], PervFraction);
 
    if (is == WATER && sfr[WATER] > 0) {
       // label 606, snow.f95:1083-1146
       const double lim = SU_SDP(StoreDrainPrm, 4, WATER);
       changSnow = (Precip + freezMelt + FreezState) - (mw_ind + ev_snow);
-      SnowPack[WATER] = SnowPack[WATER] + changSnow;
-      state_id[WATER] = state_id[WATER] + C.FlowChange - FreezState;
-      if (SnowPack[WATER] > 0) {
-         SnowWater[WATER] = SnowWater[WATER] + mw_ind - freezMelt;
-         double FWC = WaterHoldCapFrac * SnowPack[WATER];
-         if (SnowWater[WATER] >= FWC && Temp_C >= 0) {
-            state_id[WATER] = state_id[WATER] + (SnowWater[WATER] - FWC);
-            SnowWater[WATER] = FWC;
+      sp_ = sp_ + changSnow;
+      st_ = st_ + C.FlowChange - FreezState;
+      if (sp_ > 0) {
+         sw_ = sw_ + mw_ind - freezMelt;
+         double FWC = WaterHoldCapFrac * sp_;
+         if (sw_ >= FWC && Temp_C >= 0) {
+            st_ = st_ + (sw_ - FWC);
+            sw_ = FWC;
          }
-      } else if (SnowPack[WATER] < 0) {
-         SnowWater[WATER] = SnowWater[WATER] - freezMelt + mw_ind;
-         state_id[WATER] = state_id[WATER] + SnowWater[WATER] + SnowPack[WATER];
-         SnowPack[WATER] = 0;
-         if (state_id[WATER] < 0) ev_snow = ev_snow + state_id[WATER];
+      } else if (sp_ < 0) {
+         sw_ = sw_ - freezMelt + mw_ind;
+         st_ = st_ + sw_ + sp_;
+         sp_ = 0;
+         if (st_ < 0) ev_snow = ev_snow + st_;
       }
-      if (state_id[WATER] > lim) {
-         runoff = runoff + (state_id[WATER] - lim);
-         state_id[WATER] = lim;
-         w.fl.runoffWaterBody = w.fl.runoffWaterBody + runoff * sfr[WATER];
+      if (st_ > lim) {
+         runoff = runoff + (st_ - lim);
+         st_ = lim;
+         fl.runoffWaterBody = fl.runoffWaterBody + runoff * sfr[WATER];
       } else {
-         state_id[WATER] = state_id[WATER] + w.fl.surplusWaterBody;
-         if (state_id[WATER] > lim) {
-            w.fl.runoffWaterBody = w.fl.runoffWaterBody + (state_id[WATER] - lim) * sfr[WATER];
-            state_id[WATER] = lim;
+         st_ = st_ + fl.surplusWaterBody;
+         if (st_ > lim) {
+            fl.runoffWaterBody = fl.runoffWaterBody + (st_ - lim) * sfr[WATER];
+            st_ = lim;
          }
       }
-      chSnow_tot = ((SnowPack[WATER] + SnowWater[WATER]) - snowTotInit) * sfr[WATER];
-      surf_chang_tot = (state_id[WATER] - stateOld[WATER]) * sfr[WATER];
+      chSnow_tot = ((sp_ + sw_) - snowTotInit) * sfr[WATER];
+      surf_chang_tot = (st_ - stateOld[WATER]) * sfr[WATER];
       ev_tot = ev * sfr[WATER] + ev_snow * sfr[WATER];
       qe_tot = ev_snow * tlv_sub * sfr[WATER] + ev * tlv * sfr[WATER];
       runoff_tot = runoff;
-      SnowFrac[WATER] = (SnowPack[WATER] > 0) ? 1.0 : 0.0;
+      sf_ = (sp_ > 0) ? 1.0 : 0.0;
+      SU_SNOW_COMMIT();
       return;
    }
 
    // which arm of the IF / ELSEIF at snow.f95:727 / :781 this call takes (decided on entry values)
-   const bool armFull = (SnowPack[is] > 0 && SnowFrac[is] == 1);
-   const bool armPart = !armFull && (SnowFrac[is] < 1);
+   const bool armFull = (sp_ > 0 && sf_ == 1);
+   const bool armPart = !armFull && (sf_ < 1);
 
    if (armFull) {
       ev_snow = ev_snow + EvPart;
       changSnow = (Precip + freezMelt) - (mw_ind + ev_snow);
       if (rainOnSnow > 0) {
          changSnow = changSnow - Precip;
-         SnowWater[is] = SnowWater[is] + rainOnSnow;
+         sw_ = sw_ + rainOnSnow;
       }
-      SnowPack[is] = SnowPack[is] + changSnow;
-      if (SnowPack[is] > 0) {
-         SnowWater[is] = SnowWater[is] + mw_ind - freezMelt;
-         double FWC = WaterHoldCapFrac * SnowPack[is];
-         if (SnowWater[is] >= FWC) {
-            runoffSnow = runoffSnow + (SnowWater[is] - FWC);
-            SnowWater[is] = FWC;
+      sp_ = sp_ + changSnow;
+      if (sp_ > 0) {
+         sw_ = sw_ + mw_ind - freezMelt;
+         double FWC = WaterHoldCapFrac * sp_;
+         if (sw_ >= FWC) {
+            runoffSnow = runoffSnow + (sw_ - FWC);
+            sw_ = FWC;
          }
-      } else if (SnowPack[is] < 0) {
-         SnowWater[is] = SnowWater[is] - freezMelt + mw_ind + SnowPack[is];
-         SnowPack[is] = F(0.0);
+      } else if (sp_ < 0) {
+         sw_ = sw_ - freezMelt + mw_ind + sp_;
+         sp_ = F(0.0);
          snowFracOld = 1;
-         SnowFrac[is] = 0;
-         SnowDens[is] = 0;
-         if (SnowWater[is] < 0) {
-            ev_snow = ev_snow + SnowWater[is];
+         sf_ = 0;
+         sd_ = 0;
+         if (sw_ < 0) {
+            ev_snow = ev_snow + sw_;
             if (ev_snow < 0) ev_snow = 0;
-            changSnow = changSnow + SnowWater[is];
-            SnowWater[is] = 0;
+            changSnow = changSnow + sw_;
+            sw_ = 0;
          } else {
-            chang = SnowWater[is];
-            state_id[is] = state_id[is] + chang;
-            SnowWater[is] = 0;
+            chang = sw_;
+            st_ = st_ + chang;
+            sw_ = 0;
          }
       }
    } else if (armPart) {
-      if (SnowPack[is] > 0) {
+      if (sp_ > 0) {
          ev_snow = ev_snow + EvPart;
          changSnow = (Precip + freezMelt + FreezStateVol) - (mw_ind + ev_snow);
          if (rainOnSnow > 0) {
             changSnow = changSnow - Precip;
-            SnowWater[is] = SnowWater[is] + rainOnSnow;
+            sw_ = sw_ + rainOnSnow;
          }
-         SnowPack[is] = SnowPack[is] + changSnow;
+         sp_ = sp_ + changSnow;
          {   // snow.f95:810-820.  Written with named conditions: as an if / else-if / else-if chain on the array
              // element, nvcc 12.9 (sm_100a, -O3) dropped the third assignment (found by the 2004 annual parity run).
-            const double st_now = state_id[is];
+            const double st_now = st_;
             const bool c1 = (Precip > 0 && FreezState == st_now);
             const bool c2 = (Precip == 0 && FreezState > 0 && FreezState == st_now);
             const bool c3 = (FreezState > 0 && FreezState < st_now);
             if (c1 || c2) snowFracFresh1 = 1;
             else if (c3) snowFracFresh1 = F(0.95);
          }
-      } else if (SnowPack[is] == 0 && Tsurf_ind[is] < 0) {
-         if ((Precip > 0 && state_id[is] == 0) || (Precip == 0 && FreezState == state_id[is]) ||
-             (Precip > 0 && FreezState == state_id[is])) {
+      } else if (sp_ == 0 && Tsurf_ind[is] < 0) {
+         if ((Precip > 0 && st_ == 0) || (Precip == 0 && FreezState == st_) ||
+             (Precip > 0 && FreezState == st_)) {
             changSnow = Precip + FreezStateVol;
-            SnowPack[is] = SnowPack[is] + changSnow;
+            sp_ = sp_ + changSnow;
             snowFracFresh1 = 1;
-            w.iceFrac[is] = FreezState / (FreezState + Precip);
-            SnowDens[is] = P.SnowDensMin;
+            ic_ = FreezState / (FreezState + Precip); ic_set = true;
+            sd_ = P.SnowDensMin;
          }
-         if (FreezState > 0 && FreezState < state_id[is]) {
+         if (FreezState > 0 && FreezState < st_) {
             changSnow = Precip + FreezStateVol;
-            SnowPack[is] = SnowPack[is] + changSnow;
+            sp_ = sp_ + changSnow;
             snowFracFresh2 = F(0.95);
-            w.iceFrac[is] = 1;
-            SnowDens[is] = P.SnowDensMin;
+            ic_ = 1; ic_set = true;
+            sd_ = P.SnowDensMin;
          }
       }
-      if (SnowPack[is] > 0) {
-         SnowWater[is] = SnowWater[is] + mw_ind - freezMelt;
-         double FWC = WaterHoldCapFrac * SnowPack[is];
-         if (SnowWater[is] >= FWC) {
-            double MeltExcess = SnowWater[is] - FWC;
-            SnowWater[is] = FWC;
-            if ((SnowFrac[is] > F(0.9) && is != BLDG) || (is == BLDG)) runoffSnow = runoffSnow + MeltExcess;
-            else SnowToSurf = SnowToSurf + MeltExcess * SnowFrac[is] / (1 - SnowFrac[is]);
+      if (sp_ > 0) {
+         sw_ = sw_ + mw_ind - freezMelt;
+         double FWC = WaterHoldCapFrac * sp_;
+         if (sw_ >= FWC) {
+            double MeltExcess = sw_ - FWC;
+            sw_ = FWC;
+            if ((sf_ > F(0.9) && is != BLDG) || (is == BLDG)) runoffSnow = runoffSnow + MeltExcess;
+            else SnowToSurf = SnowToSurf + MeltExcess * sf_ / (1 - sf_);
          }
-      } else if (SnowPack[is] < 0) {
-         SnowWater[is] = SnowWater[is] - freezMelt + mw_ind + SnowPack[is];
-         SnowPack[is] = F(0.0);
+      } else if (sp_ < 0) {
+         sw_ = sw_ - freezMelt + mw_ind + sp_;
+         sp_ = F(0.0);
          snowFracFresh1 = 0;
          snowFracFresh2 = 0;
-         SnowDens[is] = 0;
-         if (SnowWater[is] < 0) {
-            ev_snow = ev_snow + SnowWater[is];
+         sd_ = 0;
+         if (sw_ < 0) {
+            ev_snow = ev_snow + sw_;
             if (ev_snow < 0) ev_snow = 0;
-            changSnow = changSnow + SnowWater[is];
-            SnowWater[is] = 0;
+            changSnow = changSnow + sw_;
+            sw_ = 0;
          } else {
-            SnowToSurf = SnowToSurf + SnowWater[is] * SnowFrac[is] / (1 - SnowFrac[is]);
-            SnowWater[is] = 0;
+            SnowToSurf = SnowToSurf + sw_ * sf_ / (1 - sf_);
+            sw_ = 0;
          }
       }
    }
    // snowRem snow.f95:1210-1240 (paved / buildings, last step of an hour flagged in SnowProf_24hr)
-   if (rem_time && (armFull || armPart) && SnowPack[is] > 0) {
+   if (rem_time && (armFull || armPart) && sp_ > 0) {
       double lim = (is == PAV) ? P.SnowLimPaved : P.SnowLimBldg;
-      if (SnowPack[is] > lim) {
-         w.SnowRemoval[is] = (SnowPack[is] - lim) * sfr[is] * SnowFrac[is];
-         SnowPack[is] = lim;
+      if (sp_ > lim) {
+         if (COMMIT) w.SnowRemoval[is] = (sp_ - lim) * sfr[is] * sf_;
+         sp_ = lim;
       }
    }
 
@@ -392,12 +416,12 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
          } else {
             chang = Precip + SnowToSurf + AddWater[is] - (drain[is] + ev + FreezState);
          }
-         state_id[is] = state_id[is] + chang;
+         st_ = st_ + chang;
          runoff = runoff + drain[is] * AddWaterRunoff[is];
-         if (state_id[is] < F(0.0)) {
-            w.SurplusEvap[is] = fabs(state_id[is]);
-            ev = ev - w.SurplusEvap[is];
-            state_id[is] = F(0.0);
+         if (st_ < F(0.0)) {
+            SurplusEvap[is] = fabs(st_);
+            ev = ev - SurplusEvap[is];
+            st_ = F(0.0);
          }
       } else {
          ev = ev + EvPart;
@@ -411,54 +435,62 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
          } else {
             chang = Precip + SnowToSurf + AddWater[is] - (drain[is] + ev + FreezState);
          }
-         state_id[is] = state_id[is] + chang;
-         if (Temp_C > 0) soilstore_id[is] = soilstore_id[is] + drain[is] * AddWaterRunoff[is] * (1 - SnowFrac[is]);
+         st_ = st_ + chang;
+         if (Temp_C > 0) so_ = so_ + drain[is] * AddWaterRunoff[is] * (1 - sf_);
          else runoff = runoff + drain[is] * AddWaterRunoff[is];
-         if (state_id[is] < F(0.0)) {
-            if ((soilstore_id[is] + state_id[is]) >= 0 && Temp_C > 0) {
-               soilstore_id[is] = soilstore_id[is] + state_id[is] * (1 - SnowFrac[is]);
-               state_id[is] = F(0.0);
+         if (st_ < F(0.0)) {
+            if ((so_ + st_) >= 0 && Temp_C > 0) {
+               so_ = so_ + st_ * (1 - sf_);
+               st_ = F(0.0);
             } else {
-               chang = chang + state_id[is];
-               ev = ev + state_id[is];
-               state_id[is] = F(0.0);
+               chang = chang + st_;
+               ev = ev + st_;
+               st_ = F(0.0);
             }
          }
-         if (soilstore_id[is] > P.SoilStoreCap[is]) {
-            runoffTest = runoffTest + (soilstore_id[is] - P.SoilStoreCap[is]);
-            soilstore_id[is] = P.SoilStoreCap[is];
-         } else if (soilstore_id[is] < 0) {
-            soilstore_id[is] = 0;
+         if (so_ > P.SoilStoreCap[is]) {
+            runoffTest = runoffTest + (so_ - P.SoilStoreCap[is]);
+            so_ = P.SoilStoreCap[is];
+         } else if (so_ < 0) {
+            so_ = 0;
          }
       }
    }
 
-   const double sfmax = SU_MAX(SnowFrac[is], snowFracOld);
+   const double sfmax = SU_MAX(sf_, snowFracOld);
    if (snowFracFresh2 > 0) {
-      surf_chang_tot = (state_id[is] - stateOld[is]) * sfr[is] * (1 - SnowFrac[is]) - Precip * sfr[is] * (1 - snowFracFresh2);
-      chSnow_tot = ((SnowPack[is] + SnowWater[is]) - snowTotInit) * sfr[is] * (1 - SnowFrac[is]) - Precip * sfr[is] * snowFracFresh2;
+      surf_chang_tot = (st_ - stateOld[is]) * sfr[is] * (1 - sf_) - Precip * sfr[is] * (1 - snowFracFresh2);
+      chSnow_tot = ((sp_ + sw_) - snowTotInit) * sfr[is] * (1 - sf_) - Precip * sfr[is] * snowFracFresh2;
    } else {
-      surf_chang_tot = (state_id[is] - stateOld[is]) * sfr[is] * (1 - SnowFrac[is]);
-      chSnow_tot = ((SnowPack[is] + SnowWater[is]) - snowTotInit) * sfr[is] * sfmax;
+      surf_chang_tot = (st_ - stateOld[is]) * sfr[is] * (1 - sf_);
+      chSnow_tot = ((sp_ + sw_) - snowTotInit) * sfr[is] * sfmax;
    }
-   ev_tot = ev * sfr[is] * (1 - SnowFrac[is]) + ev_snow * sfr[is] * sfmax;
-   if (is == BLDG || is == PAV) qe_tot = ev_snow * tlv_sub * sfr[is] * SnowFrac[is] + ev * tlv * sfr[is] * (1 - SnowFrac[is]);
-   else qe_tot = ev_snow * tlv_sub * sfr[is] * sfmax + ev * tlv * sfr[is] * (1 - SnowFrac[is]);
+   ev_tot = ev * sfr[is] * (1 - sf_) + ev_snow * sfr[is] * sfmax;
+   if (is == BLDG || is == PAV) qe_tot = ev_snow * tlv_sub * sfr[is] * sf_ + ev * tlv * sfr[is] * (1 - sf_);
+   else qe_tot = ev_snow * tlv_sub * sfr[is] * sfmax + ev * tlv * sfr[is] * (1 - sf_);
 
-   w.fl.runoffPipes = w.fl.runoffPipes + runoffSnow * sfr[is] * sfmax + runoff * sfr[is] * (1 - SnowFrac[is]) + runoffTest * sfr[is];
-   updateFlood(is, runoff, sfr, C.PipeCapacity, C.RunoffToWater, w.fl);
-   runoff_tot = runoffSnow * sfr[is] * sfmax + runoff * sfr[is] * (1 - SnowFrac[is]) + runoffTest * sfr[is];
-
-   if (SnowDens[is] != 0) w.SnowDepth[is] = SnowPack[is] * SU_WATERDENS / SnowDens[is];
-   w.swe = w.swe + SnowPack[is] * sfr[is] * sfmax;
-   w.mwstore = w.mwstore + SnowWater[is] * sfr[is] * sfmax;
-
-   if (snowFracFresh1 > 0) SnowFrac[is] = snowFracFresh1;
-   if (snowFracFresh2 > 0) SnowFrac[is] = snowFracFresh2;
-   if (SnowPack[is] > 0 && mw_ind > 0) {
-      SnowFrac[is] = SnowDepletionCurve(is, SnowPack[is], P.SnowPackLimit[is]);
-      if (SnowFrac[is] < F(0.001)) SnowFrac[is] = F(0.001);
-   } else if (SnowPack[is] == 0) {
-      SnowFrac[is] = 0;
+   if (COMMIT) {
+      fl.runoffPipes = fl.runoffPipes + runoffSnow * sfr[is] * sfmax + runoff * sfr[is] * (1 - sf_) + runoffTest * sfr[is];
+      updateFlood(is, runoff, sfr, C.PipeCapacity, C.RunoffToWater, fl);
    }
+   runoff_tot = runoffSnow * sfr[is] * sfmax + runoff * sfr[is] * (1 - sf_) + runoffTest * sfr[is];
+
+   if (COMMIT) {
+      if (sd_ != 0) w.SnowDepth[is] = sp_ * SU_WATERDENS / sd_;
+      w.swe = w.swe + sp_ * sfr[is] * sfmax;
+      w.mwstore = w.mwstore + sw_ * sfr[is] * sfmax;
+   }
+
+   if (COMMIT) {   // (the surface's new snow fraction: state only)
+      if (snowFracFresh1 > 0) sf_ = snowFracFresh1;
+      if (snowFracFresh2 > 0) sf_ = snowFracFresh2;
+      if (sp_ > 0 && mw_ind > 0) {
+         sf_ = SnowDepletionCurve(is, sp_, P.SnowPackLimit[is]);
+         if (sf_ < F(0.001)) sf_ = F(0.001);
+      } else if (sp_ == 0) {
+         sf_ = 0;
+      }
+   }
+   SU_SNOW_COMMIT();
+#undef SU_SNOW_COMMIT
 }

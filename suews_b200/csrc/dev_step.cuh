@@ -29,6 +29,9 @@
 #include "dev_solweig.cuh"
 #include "dev_estm.cuh"
 
+#ifndef SU_SKIP
+#define SU_SKIP 0
+#endif
 // the three per-surface loops of the step are kept rolled (code size); SU_UNROLL_SURF lets the compiler unroll them
 #ifdef SU_UNROLL_SURF
 #define SU_UNROLL1
@@ -62,7 +65,7 @@
 // phase's barrier (so a phase's time is that of its slowest warp).  tools/prof_run.py prints them.
 #ifdef SU_PHASE_CLOCKS
 static __device__ unsigned long long su_phase_clk[16];
-#define SU_CLK_DECL long long clk_ = clock64()
+#define SU_CLK_DECL long long clk_ = clock64(); const bool clkb_ = true
 #define SU_CLK(i)                                                              \
    do {                                                                        \
       if (threadIdx.x == 0) {                                                  \
@@ -75,10 +78,20 @@ static __device__ unsigned long long su_phase_clk[16];
    do {                                                                        \
       if (threadIdx.x == 0) atomicAdd(&su_phase_clk[i], (unsigned long long)(n)); \
    } while (0)
+// sub-stage clocks (slots 10-15) with their own barrier: only legal when every thread of the block is live, which the
+// profiling runs arrange (tools/prof_run.py uses whole blocks); their time is taken out of the enclosing phase's slot
+#define SU_CLKB(i) do { if (clkb_) { __syncthreads(); SU_CLK(i); } } while (0)
+#define SU_CLK_PARAM , long long &clk_, bool clkb_
+#define SU_CLK_PASS , clk_, true
+#define SU_CLK_PASS_NOBAR , clk_, false
 #else
 #define SU_CLK_DECL
 #define SU_CLK(i)
 #define SU_CNT(i, n)
+#define SU_CLKB(i)
+#define SU_CLK_PARAM
+#define SU_CLK_PASS
+#define SU_CLK_PASS_NOBAR
 #endif
 
 // Optional per-step output lines (reference layouts).  NULL = not wanted.
@@ -129,17 +142,33 @@ SU_DEV void stage_pre_atm(SuDiag &dg, const SuewsClassParams &P, const SuewsCell
 // Tsurf-independent stages that follow cal_AtmMoist (driver.f95:727-755, :827-834 and SurfaceResistance of :838)
 SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, int snowUse, const SuewsCellParams &C, const SuewsStepRec &R,
                            const SuewsCellState &S, const SuAtm &A, int DLS, int nsh, double nsh_real, double Temp_C,
-                           double NonWaterFraction, const double *SnowFrac_res, SuHoist &H, const SuDaily &D)
+                           double NonWaterFraction, const double *SnowFrac_res, SuHoist &H, const SuDaily &D SU_CLK_PARAM)
 {
    const double *sfr = C.sfr.v;
    double SoilState;
+   // (SU_SKIP: timing-only switches that drop one stage each -- the results are then wrong by construction; they price a
+   // stage with its memory traffic included, tools/variants.sh)
+#if !(SU_SKIP & 1)
    update_SoilMoist(NonWaterFraction, P.SoilStoreCap.v, sfr, S.soilstore_id.v, H.SoilMoistCap, SoilState, H.vsmd, H.smd0);
+#else
+   H.SoilMoistCap = 100; SoilState = 50; H.vsmd = 10; H.smd0 = 50;
+#endif
+#if !(SU_SKIP & 2)
    cal_WaterUse(P, C, nsh_real, R.wu_m3, R.dow, D.HDD_id, D.WUDay_id, nsh, R.it, R.imin, DLS, H.wu_nsurf, H.wu_int,
                 H.wu_ext);
+#else
+   for (int is = 0; is < NSURF; is++) H.wu_nsurf[is] = 0;
+   H.wu_int = 0; H.wu_ext = 0;
+#endif
+#if !(SU_SKIP & 4)
    cal_AnthropogenicEmission(dg, P, C, R.dow, DLS, D.HDD_id, R.it, R.imin, R.qf_obs, Temp_C, H.an);
+#else
+   H.an.qf = 20; H.an.Fc_anthro = 0; H.an.Fc_metab = 0; H.an.Fc_traff = 0; H.an.Fc_build = 0; H.an.Fc_point = 0;
+#endif
    H.SnowAlb_q = update_snow_albedo(P.tstep, S.SnowPack.v, S.SnowAlb, Temp_C, P.tau_a, P.tau_f, P.SnowAlbMax, P.SnowAlbMin);
+   SU_CLKB(11);
    // SUEWS_cal_Water driver.f95:1614-1694 (StoreDrainPrm_next differs from _prev in (6,Decid) only)
-   if (NonWaterFraction != 0) {
+   if (NonWaterFraction != 0 && !(SU_SKIP & 8)) {
       double s = 0;
 SU_UNROLL1
       for (int is = 0; is < NSURF - 1; is++) {
@@ -154,8 +183,19 @@ SU_UNROLL1
       H.drain_per_tstep = 0;
    }
    H.drain[WATER] = 0;
+   SU_CLKB(12);
+#if !(SU_SKIP & 16)
    ReDistributeWater(snowUse, P.WaterDist.v, sfr, H.drain, H.AddWaterRunoff, H.AddWater);
+#else
+   for (int is = 0; is < NSURF; is++) { H.AddWater[is] = 0; H.AddWaterRunoff[is] = 0.5; }
+#endif
+   SU_CLKB(13);
+#if !(SU_SKIP & 32)
    SurfaceResistance(dg, P, sfr, SnowFrac_res, R.avkdn, Temp_C, A.dq, R.xsmd, H.vsmd, D.LAI_id, H.gfunc, H.gsc, H.ResistSurf);
+#else
+   H.gfunc = 1; H.gsc = 0.01; H.ResistSurf = 100;
+#endif
+   SU_CLKB(14);
 }
 
 // SUEWS_cal_QE driver.f95:1744-2082: per-surface evaporation + surface/soil/snow state update.
@@ -191,6 +231,9 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, int snowUse, cons
    double qe_per_tstep = 0, ev = 0, qe_surf = 0;
    SuEvapTrip et;
    evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
+   SuQEIn win;   // SnowCalc reads the entry values of its surface from the work arrays it commits to
+   win.state_id = W.state_id; win.soilstore_id = W.soilstore_id; win.SnowPack = W.SnowPack; win.SnowFrac = W.SnowFrac;
+   win.SnowWater = W.SnowWater; win.SnowDens = W.SnowDens;
    T.ev_per_tstep = 0; T.surf_chang_per_tstep = 0; T.runoff_per_tstep = 0; T.state_per_tstep = 0; T.NWstate_per_tstep = 0;
    T.chSnow_per_interval = 0;
 SU_UNROLL1
@@ -199,10 +242,10 @@ SU_UNROLL1
       if (snowUse == 1 && Hs.snowCalcSwitch[is] == 1) {
          if (sfr[is] != 0) {
             double chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot;
-            SnowCalc(dg, P, C, is, R.imin, R.it, R.dow, nsh_r, A.lvS_J_kg, A.avdens, avRh, R.Press_hPa, Temp_C, RAsnow,
-                     Lm.psyc_hPa, A.avcp, Lm.sIce_hpa, PervFraction, VegFraction, A.VPd_hpa, qn_e, Lm.s_hPa, H.ResistSurf,
-                     RA, rb, tlv, R.Precip, H.drain, S.state_id.v, Hs, Tsurf_ind, S.StoreDrainPrm.v, cap, H.AddWater,
-                     H.AddWaterRunoff, W, chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot);
+            SnowCalc<true>(dg, P, C, is, R.imin, R.it, R.dow, nsh_r, A.lvS_J_kg, A.avdens, avRh, R.Press_hPa, Temp_C, RAsnow,
+                           Lm.psyc_hPa, A.avcp, Lm.sIce_hpa, PervFraction, VegFraction, A.VPd_hpa, qn_e, Lm.s_hPa, H.ResistSurf,
+                           RA, rb, tlv, R.Precip, H.drain, S.state_id.v, Hs, Tsurf_ind, S.StoreDrainPrm.v, cap, H.AddWater,
+                           H.AddWaterRunoff, win, W.SurplusEvap, W, chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot);
             T.ev_per_tstep = T.ev_per_tstep + ev_tot;
             qe_per_tstep = qe_per_tstep + qe_tot;
             T.runoff_per_tstep = T.runoff_per_tstep + runoff_tot;
@@ -246,6 +289,57 @@ SU_UNROLL1
       qe = qe + qe_surf * C.sfr[is];
    }
    return qe;
+}
+
+// QE of a trip when some surface takes the snow branch (snowUse = 1): the sum cal_QE_full forms, by the same statements
+// -- SnowCalc<false> for the surfaces in the snow branch, cal_evap for the others, and the evaporation surplus of the two
+// impervious surfaces that the vegetated ones pick up (waterdist.f95:181-187 / snow.f95:585) -- without the state update.
+SU_DEV double cal_QE_light_snow(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, const SuewsStepRec &R,
+                                const SuewsCellState &S, const SuAtm &A, const SuLumps &Lm, const SuHoist &H, const SuSnowHeat &Hs,
+                                const double *Tsurf_ind, const double *SnowPack_m, const double *SnowFrac_q, const double *SnowDens_m,
+                                double Temp_C, double avRh, double RA, double RAsnow, double rb, double qn_e, double PervFraction,
+                                double VegFraction, SuQEWork &Wdummy, const SuDaily &D)
+{
+   const double *sfr = C.sfr.v;
+   const double tstep_r = P.tstep * 1.0;
+   const double nsh_r = 3600 / tstep_r;
+   const double tlv = A.lv_J_kg / tstep_r;
+   const double pin = SU_MAX(F(0.), R.Precip);
+   double qe_per_tstep = 0, ev = 0, qe_surf = 0;
+   double SurplusEvap[NSURF];
+   for (int is = 0; is < NSURF; is++) SurplusEvap[is] = 0;
+   SuEvapTrip et;
+   evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
+   SuQEIn in;   // entry values of a trip: the *_prev state as Snow_cal_MeltHeat left it
+   in.state_id = S.state_id.v; in.soilstore_id = S.soilstore_id.v; in.SnowPack = SnowPack_m; in.SnowFrac = SnowFrac_q;
+   in.SnowWater = S.SnowWater.v; in.SnowDens = SnowDens_m;
+SU_UNROLL1
+   for (int is = 0; is < NSURF; is++) {
+      const double cap = (is == DECID) ? D.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
+      if (Hs.snowCalcSwitch[is] == 1) {
+         if (sfr[is] != 0) {
+            double chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot;
+            SnowCalc<false>(dg, P, C, is, R.imin, R.it, R.dow, nsh_r, A.lvS_J_kg, A.avdens, avRh, R.Press_hPa, Temp_C, RAsnow,
+                            Lm.psyc_hPa, A.avcp, Lm.sIce_hpa, PervFraction, VegFraction, A.VPd_hpa, qn_e, Lm.s_hPa, H.ResistSurf,
+                            RA, rb, tlv, R.Precip, H.drain, S.state_id.v, Hs, Tsurf_ind, S.StoreDrainPrm.v, cap, H.AddWater,
+                            H.AddWaterRunoff, in, SurplusEvap, Wdummy, chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot);
+            qe_per_tstep = qe_per_tstep + qe_tot;
+         }
+      } else {
+         evap_surface<true>(et, S.state_id[is], P.WetThresh[is], cap, ev, qe_surf);
+         if (is == PAV || is == BLDG) {   // cal_water_storage's impervious arm, as far as SurplusEvap (waterdist.f95:139-166)
+            const double IPT = 10 / nsh_r;
+            double p_mm = pin + H.wu_nsurf[is];
+            p_mm = p_mm + H.AddWater[is];
+            double chang = p_mm - (H.drain[is] + ev);
+            if (p_mm > IPT) chang = IPT - (H.drain[is] + ev);
+            const double state_is = S.state_id[is] + chang;
+            if (state_is < F(0.0)) SurplusEvap[is] = fabs(state_is);
+         }
+         qe_per_tstep = qe_per_tstep + qe_surf * sfr[is];
+      }
+   }
+   return qe_per_tstep;
 }
 
 // Site constants of a launch (pure functions of the cell parameters, formed once by the kernel prologue)
@@ -333,12 +427,11 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       for (int is = 0; is < NSURF; is++) { deltaQi[is] = 0; smd_nsurf[is] = 0; SnowWater_in[is] = S.SnowWater[is]; }
       cal_RoughnessParameters(dg, P.RoughLenMomMethod, C, D.porosity_id, FAI, zH, z0m, zdm, ZZD);
       lg_zz0 = log(ZZD / z0m);   // cal_Stab and AerodynamicResistance of every trip (atmmoiststab.f95:223, resist.f95:60-84)
-#ifdef SU_NO_SITE_HOIST   // tuning switch: site terms of the solar position re-evaluated every step
-      spa_location_part(E, C.lat, C.lng, C.alt, azimuth, zenith_deg);
-#else
-      spa_location_part(E, site.spa, C.lng, azimuth, zenith_deg);
-#endif
       RadMethod(dg, P.NetRadiationMethod, snowUse, nrm_use, AlbedoChoice, ldown_option);
+      // Sun position of the cell.  The zenith angle enters the energy balance only through NARP's zenith-dependent albedo
+      // (AlbedoChoice = 1, NetRadiationMethod 100-300; narp.f95:296-300) and ESTM; otherwise it is an output column.  Under
+      // policy P0 -- no output line, seven flux sums -- it is formed only where one of those reads it.
+      if (K != 2 || AlbedoChoice == 1 || use_estm) spa_location_part(E, site.spa, C.lng, azimuth, zenith_deg);
       // Tsurf enters NARP only through the iteration-based methods (narp.f95:337-346).  (ESTM, which advances its
       // element temperatures on every call of SUEWS_cal_Qs, is run per trip below whatever the radiation scheme.)
       rad_invariant = (nrm_use < 10);
@@ -348,7 +441,11 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       // the reference runs the stages ahead of cal_AtmMoist again on trips >= 2 when sat_vap_press_x rewrites Temp_C
       // (|Temp_C| < 0.001, see phase L1): only then is a copy of the daily state kept to restart from
       if (temp_will_rewrite) D_prev = D;
+#if !(SU_SKIP & 512)
       stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
+#else
+      H.Tair_av_next = S.Tair_av;
+#endif
    }
    SU_SYNCN(0);
    SU_CLK(0);
@@ -358,7 +455,8 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       cal_AtmMoist(dg, Temp_C, Press_hPa, avRh, lv_sw, A);   // may rewrite Temp_C
       lv_memo[sw_in] = A.lv_J_kg;
       lv_exit[sw_in] = lv_sw;
-      stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
+      SU_CLKB(10);
+      stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D SU_CLK_PASS);
       qf = H.an.qf;
    }
 
@@ -379,7 +477,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
             if (i_iter == 2 && temp_will_rewrite) {   // trips >= 2 run the early stages with the rewritten Temp_C
                D = D_prev;
                stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
-               stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D);
+               stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D SU_CLK_PASS_NOBAR);
                qf = H.an.qf;
                rad_done = false;
             }
@@ -481,10 +579,16 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          if (snowUse == 1)
             for (int is = 0; is < NSURF; is++) snow_branch = snow_branch || (Hs.snowCalcSwitch[is] == 1);
          if (snow_branch) {
+#ifdef SU_SNOW_FULL_TRIPS   // (first release: the full state update on every trip that has a surface in the snow branch)
             cal_QE_full(dg, P, snowUse, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow,
                         rb, qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
             qe = QT.qe;
             qe_full_done = true;
+#else
+            qe = cal_QE_light_snow(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA,
+                                   RAsnow, rb, qn_e, PervFraction, VegFraction, W, D);
+            qe_full_done = false;
+#endif
          } else {
             qe = cal_QE_light(P, C, S, A, Lm, H, RA, rb, qn_e, D);
             qe_full_done = false;
@@ -525,11 +629,14 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          cal_QE_full(dg, P, snowUse, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow, rb,
                      qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
       }
+      SU_CLKB(15);
       qh_resist = (RA != 0) ? A.avdens * A.avcp * (Rd.tsurf - Temp_C) / RA : -999.0;
       double soilstoreOld[NSURF];
       for (int is = 0; is < NSURF; is++) soilstoreOld[is] = S.soilstore_id[is];
+#if !(SU_SKIP & 128)
       cal_HorizontalSoilWater(P, sfr, C.SurfaceArea, NonWaterFraction, tstep_real, W.soilstore_id, W.runoffSoil,
                               runoffSoil_per_tstep);
+#endif
       cal_SoilState(dg, P.SMDMethod, R.xsmd, NonWaterFraction, H.SoilMoistCap, P.SoilStoreCap.v, QT.surf_chang_per_tstep,
                     W.soilstore_id, soilstoreOld, sfr, smd, smd_nsurf, tot_chang_per_tstep);
    }

@@ -416,8 +416,12 @@ SU_DEV void ReDistributeWater(int snowUse, const double *WaterDist, const double
    for (int ii = 0; ii < NSURF; ii++) {
       if (sfr[ii] != 0 && snowUse == 0) {
          double a = 0;
-         for (int jj = 0; jj < NSURF - 1; jj++)
-            if (Drain[jj] != 0) a = a + (Drain[jj] * sfr[jj] / sfr[ii]) * SU_WDIST(WaterDist, ii, jj);
+         for (int jj = 0; jj < NSURF - 1; jj++) {
+            // (most of the 7 x 6 WaterDist matrix is zero -- a surface hands its drainage to one or two others -- and a
+            // zero fraction adds +0 to a sum of non-negative terms: the division is only made for the others)
+            const double wd = SU_WDIST(WaterDist, ii, jj);
+            if (Drain[jj] != 0 && wd != 0) a = a + (Drain[jj] * sfr[jj] / sfr[ii]) * wd;
+         }
          AddWater[ii] = a;
       } else {
          AddWater[ii] = 0;
@@ -522,6 +526,10 @@ SU_BIG2 void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *sf
                   vg_at[jj] = soilstore_id[jj];
                }
                const double MatPot1 = vg_mp[is], Km1 = vg_km[is], MatPot2 = vg_mp[jj], Km2 = vg_km[jj];
+               // Equal matric potentials (two saturated stores, two dry ones): the gradient is an exact zero, dI = -0 and the
+               // pair exchanges nothing -- both stores, already capped by the water balance or by an earlier pair, keep their
+               // bits (x + -0 = x, x - -0 = x); with neither above its capacity the tests below do not fire either.  Nothing to do for this pair.
+               if (MatPot1 == MatPot2 && !(soilstore_id[is] > P.SoilStoreCap[is]) && !(soilstore_id[jj] > P.SoilStoreCap[jj])) continue;
                double Distance = (rt[is] + rt[jj]) / 2;
                double KmWeight = (sfr[is] * Km1 + sfr[jj] * Km2) / (sfr[is] + sfr[jj]);
                double dI_dt = su_div0(-(KmWeight) * (-MatPot1 + MatPot2), Distance * 1000);

@@ -18,6 +18,7 @@
 #include <strings.h>
 #include <algorithm>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "suews_fields.h"
@@ -85,6 +86,18 @@ __global__ void suews_ephem_kernel(const SuewsStepRec *steps, int nsteps, const 
    int s = i % nsteps, z = i / nsteps;
    // dectime [days] minus the INTEGER tstep/2 [seconds], exactly as the reference call (driver.f95:689)
    spa_time_part((double)steps[s].iy, steps[s].dectime - (double)(tstep / 2), tz_list[z], ephem[(size_t)z * nsteps + s]);
+}
+
+// Final gather, per device: selected columns of the slot-ordered running sums -> a compact cell-ordered block
+// [ncols][n] (reads are contiguous per warp; the writes scatter through the slot -> cell map)
+struct SuPackCols { int col[16]; int ncols; };
+__global__ void suews_pack_sums_kernel(const double *sums, const int *cell_of_slot, long long stride, int n, SuPackCols pc,
+                                       double *out)
+{
+   const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+   if (sl >= n) return;
+   const int c = cell_of_slot[sl];
+   for (int k = 0; k < pc.ncols; k++) out[(size_t)k * n + c] = sums[(size_t)pc.col[k] * stride + sl];
 }
 
 __global__ void suews_fill_kernel(double *p, size_t n, double v)
@@ -1053,8 +1066,6 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
       else if (small || estm || snow_rt) launch = small ? SU_LAUNCHER_NAME(1, m1, m1, 256) : SU_LAUNCHER_NAME(1, m1, m1, 1024);
       else if (kind == SU_K_ACC) launch = snow1 ? SU_LAUNCHER_NAME(1, m1, m1, 1024) : SU_LAUNCHER_NAME(1, 0, 0, 1024);
       else launch = snow1 ? SU_LAUNCHER_NAME(2, 1, 0, 1024) : SU_LAUNCHER_NAME(2, 0, 0, 1024);
-      const int blk = small ? SU_BLOCK_SMALL : SU_BLOCK;
-      const int grid = (n + blk - 1) / blk;
       cudaStream_t st = h->stream;
       if (nb > 1 && side > 0) {   // first bucket on the main stream, the others fork off it and join again below
          const int k = side - 1;
@@ -1065,7 +1076,7 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
          CUDA_OK(cudaStreamWaitEvent(h->bstream[k], h->ev_fork, 0));
          st = h->bstream[k];
       }
-      CUDA_OK(launch(grid, st, a));
+      CUDA_OK(launch(n, st, a));
       if (st != h->stream) {
          CUDA_OK(cudaEventRecord(h->bev[side - 1], st));
       }
@@ -1305,13 +1316,23 @@ int suews_b200_get_diag(suews_b200_handle h, int *fatal, unsigned long long *war
 
 #ifdef SU_PHASE_CLOCKS
 // profiling builds only: read (and optionally clear) the per-phase cycle counters of dev_step.cuh
+// (every kernel instance is its own translation unit with its own copy of the counters: each registers a reader)
+static su_clk_reader_t su_clk_readers[32];
+static int su_n_clk_readers = 0;
+void su_register_clk_reader(su_clk_reader_t f)
+{
+   for (int i = 0; i < su_n_clk_readers; i++)
+      if (su_clk_readers[i] == f) return;
+   if (su_n_clk_readers < 32) su_clk_readers[su_n_clk_readers++] = f;
+}
 int suews_b200_debug_phase_clocks(unsigned long long *out16, int reset)
 {
    CUDA_OK(cudaDeviceSynchronize());
-   if (out16) CUDA_OK(cudaMemcpyFromSymbol(out16, su_phase_clk, sizeof(unsigned long long) * 16));
-   if (reset) {
-      unsigned long long z[16] = {0};
-      CUDA_OK(cudaMemcpyToSymbol(su_phase_clk, z, sizeof(z)));
+   if (out16) for (int k = 0; k < 16; k++) out16[k] = 0;
+   for (int i = 0; i < su_n_clk_readers; i++) {
+      unsigned long long t[16] = {0};
+      CUDA_OK(su_clk_readers[i](t, reset));
+      if (out16) for (int k = 0; k < 16; k++) out16[k] += t[k];
    }
    return SUEWS_OK;
 }
@@ -1371,6 +1392,222 @@ int suews_cal_sunposition_c(double year, double idectime, double UTC, double lat
    CUDA_OK(e);
    if (az) *az = hbuf[0];
    if (zen) *zen = hbuf[1];
+   return SUEWS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs of one box behind one handle (include/suews_b200.h): contiguous blocks of cells, one per device, one host
+// thread, no exchange while the steps advance; the final gather goes device -> first device -> host
+// ------------------------------------------------------------------------------------------------
+struct suews_b200_multi_s {
+   int ncell = 0, nclass = 0, ndev = 0;
+   std::vector<suews_b200_handle> part;
+   std::vector<int> cell0, n;          // block d covers cells [cell0[d], cell0[d] + n[d])
+   std::vector<double *> d_pack;       // per device: compact cell-ordered sums block [ncols][n[d]]
+   std::vector<size_t> pack_cap;
+   double *d_gather = nullptr;         // on the first device: [ncols][ncell]
+   size_t gather_cap = 0;
+   double *pinned = nullptr;
+   size_t pinned_cap = 0;
+};
+
+int suews_b200_multi_create(int ncell, int nclass, int ndev, const int *devices, suews_b200_multi *out)
+{
+   if (!out || ncell <= 0 || nclass <= 0 || ndev <= 0 || ndev > ncell) return set_err(SUEWS_E_BAD_ARG, "multi_create: bad arguments");
+   suews_b200_multi_s *m = new suews_b200_multi_s;
+   m->ncell = ncell; m->nclass = nclass; m->ndev = ndev;
+   // equal contiguous blocks, the first ncell % ndev of them one cell longer
+   int c0 = 0;
+   for (int d = 0; d < ndev; d++) {
+      const int n = ncell / ndev + (d < ncell % ndev ? 1 : 0);
+      suews_b200_handle h = nullptr;
+      int rc = suews_b200_create(n, nclass, devices ? devices[d] : d, &h);
+      if (rc != SUEWS_OK) {
+         for (auto p : m->part) suews_b200_destroy(p);
+         delete m;
+         return rc;
+      }
+      m->part.push_back(h);
+      m->cell0.push_back(c0);
+      m->n.push_back(n);
+      c0 += n;
+   }
+   m->d_pack.assign((size_t)ndev, nullptr);
+   m->pack_cap.assign((size_t)ndev, 0);
+   // peer access towards the first device (the gather target); a refusal just means the copies are staged by the driver
+   for (int d = 1; d < ndev; d++) {
+      const int a = m->part[(size_t)d]->device, b = m->part[0]->device;
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+         cudaSetDevice(a);
+         if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();
+      }
+   }
+   *out = m;
+   return SUEWS_OK;
+}
+
+int suews_b200_multi_destroy(suews_b200_multi m)
+{
+   if (!m) return SUEWS_OK;
+   for (int d = 0; d < m->ndev; d++) {
+      if (m->d_pack[(size_t)d]) { cudaSetDevice(m->part[(size_t)d]->device); cudaFree(m->d_pack[(size_t)d]); }
+   }
+   if (m->d_gather) { cudaSetDevice(m->part[0]->device); cudaFree(m->d_gather); }
+   if (m->pinned) cudaFreeHost(m->pinned);
+   for (auto p : m->part) suews_b200_destroy(p);
+   delete m;
+   return SUEWS_OK;
+}
+
+int suews_b200_multi_ndev(suews_b200_multi m, int *ndev)
+{
+   if (!m || !ndev) return set_err(SUEWS_E_BAD_ARG, "null argument");
+   *ndev = m->ndev;
+   return SUEWS_OK;
+}
+
+int suews_b200_multi_part(suews_b200_multi m, int d, suews_b200_handle *h, int *cell0, int *ncell)
+{
+   if (!m || d < 0 || d >= m->ndev) return set_err(SUEWS_E_BAD_ARG, "multi_part: block %d of %d", d, m ? m->ndev : 0);
+   if (h) *h = m->part[(size_t)d];
+   if (cell0) *cell0 = m->cell0[(size_t)d];
+   if (ncell) *ncell = m->n[(size_t)d];
+   return SUEWS_OK;
+}
+
+#define MULTI_EACH(call)                                   \
+   do {                                                    \
+      if (!m) return set_err(SUEWS_E_BAD_ARG, "null handle"); \
+      for (int d = 0; d < m->ndev; d++) {                  \
+         suews_b200_handle h = m->part[(size_t)d];         \
+         const size_t c0 = (size_t)m->cell0[(size_t)d];    \
+         (void)c0;                                         \
+         int rc_ = (call);                                 \
+         if (rc_ != SUEWS_OK) return rc_;                  \
+      }                                                    \
+      return SUEWS_OK;                                     \
+   } while (0)
+
+int suews_b200_multi_set_class_param(suews_b200_multi m, int cls, const char *name, const double *vals, int n)
+{
+   MULTI_EACH(suews_b200_set_class_param(h, cls, name, vals, n));
+}
+int suews_b200_multi_set_cell_param(suews_b200_multi m, const char *name, const double *vals, int n)
+{
+   MULTI_EACH(suews_b200_set_cell_param(h, name, vals + c0 * (size_t)n, n));
+}
+int suews_b200_multi_set_cell_class(suews_b200_multi m, const int *class_of_cell)
+{
+   MULTI_EACH(suews_b200_set_cell_class(h, class_of_cell + c0));
+}
+int suews_b200_multi_set_state(suews_b200_multi m, const char *name, const double *vals, int n)
+{
+   MULTI_EACH(suews_b200_set_state(h, name, vals + c0 * (size_t)n, n));
+}
+int suews_b200_multi_get_state(suews_b200_multi m, const char *name, double *vals, int n)
+{
+   MULTI_EACH(suews_b200_get_state(h, name, vals + c0 * (size_t)n, n));
+}
+int suews_b200_multi_set_clock(suews_b200_multi m, int dt_since_start, int tstep_prev)
+{
+   MULTI_EACH(suews_b200_set_clock(h, dt_since_start, tstep_prev));
+}
+int suews_b200_multi_upload(suews_b200_multi m) { MULTI_EACH(suews_b200_upload(h)); }
+int suews_b200_multi_set_forcing(suews_b200_multi m, const double *met, int nsteps) { MULTI_EACH(suews_b200_set_forcing(h, met, nsteps)); }
+// every launch is asynchronous on its device's stream: one host thread keeps all devices busy
+int suews_b200_multi_advance(suews_b200_multi m, int step0, int nsteps, int out_flags) { MULTI_EACH(suews_b200_advance(h, step0, nsteps, out_flags)); }
+int suews_b200_multi_sync(suews_b200_multi m)
+{
+   if (!m) return set_err(SUEWS_E_BAD_ARG, "null handle");
+   int first = SUEWS_OK;
+   for (int d = 0; d < m->ndev; d++) {   // wait for every device before reporting the first failure
+      int rc = suews_b200_sync(m->part[(size_t)d]);
+      if (rc != SUEWS_OK && first == SUEWS_OK) {
+         first = rc;
+         if (m->part[(size_t)d]->first_fatal_cell >= 0)   // the cell index of the whole run, not of the block
+            set_err(rc, "Fatal error in SUEWS! code %d in cell %d: %s", rc, m->cell0[(size_t)d] + m->part[(size_t)d]->first_fatal_cell, fatal_text(rc));
+      }
+   }
+   return first;
+}
+int suews_b200_multi_last_advance_ms(suews_b200_multi m, float *ms)
+{
+   if (!m || !ms) return set_err(SUEWS_E_BAD_ARG, "null argument");
+   float worst = 0;
+   for (int d = 0; d < m->ndev; d++) {
+      float t = 0;
+      int rc = suews_b200_last_advance_ms(m->part[(size_t)d], &t);
+      if (rc != SUEWS_OK) return rc;
+      worst = std::max(worst, t);
+   }
+   *ms = worst;
+   return SUEWS_OK;
+}
+int suews_b200_multi_get_diag(suews_b200_multi m, int *fatal, unsigned long long *warn2, long long *iters)
+{
+   MULTI_EACH(suews_b200_get_diag(h, fatal ? fatal + c0 : nullptr, warn2 ? warn2 + 2 * c0 : nullptr, iters ? iters + c0 : nullptr));
+}
+
+int suews_b200_multi_gather_sums(suews_b200_multi m, const int *cols, int ncols, double *out, float *gather_ms)
+{
+   if (!m || !cols || !out || ncols <= 0 || ncols > 16) return set_err(SUEWS_E_BAD_ARG, "multi_gather_sums: 1..16 columns");
+   SuPackCols pc;
+   pc.ncols = ncols;
+   for (int k = 0; k < ncols; k++) {
+      if (cols[k] < 0 || cols[k] >= SUEWS_NCOL_SUEWS) return set_err(SUEWS_E_BAD_ARG, "multi_gather_sums: column %d", cols[k]);
+      pc.col[k] = cols[k];
+   }
+   const auto t0 = std::chrono::steady_clock::now();
+   suews_b200_handle h0 = m->part[0];
+   const size_t total = (size_t)ncols * (size_t)m->ncell;
+   CUDA_OK(cudaSetDevice(h0->device));
+   if (m->gather_cap < total) {
+      if (m->d_gather) cudaFree(m->d_gather);
+      m->d_gather = nullptr;
+      CUDA_OK(cudaMalloc((void **)&m->d_gather, sizeof(double) * total));
+      m->gather_cap = total;
+   }
+   if (m->pinned_cap < total) {
+      if (m->pinned) cudaFreeHost(m->pinned);
+      m->pinned = nullptr;
+      CUDA_OK(cudaHostAlloc((void **)&m->pinned, sizeof(double) * total, cudaHostAllocDefault));
+      m->pinned_cap = total;
+   }
+   // 1. every device packs its block in cell order, then sends it column by column to the first device.  Everything is
+   //    ordered on the source device's launch stream (behind the last advance), so nothing here blocks the host.
+   for (int d = 0; d < m->ndev; d++) {
+      suews_b200_handle h = m->part[(size_t)d];
+      if (!h->uploaded) return set_err(SUEWS_E_BAD_ARG, "multi_gather_sums: nothing uploaded");
+      const size_t n = (size_t)m->n[(size_t)d], need = (size_t)ncols * n;
+      CUDA_OK(cudaSetDevice(h->device));
+      if (m->pack_cap[(size_t)d] < need) {
+         if (m->d_pack[(size_t)d]) cudaFree(m->d_pack[(size_t)d]);
+         m->d_pack[(size_t)d] = nullptr;
+         CUDA_OK(cudaMalloc((void **)&m->d_pack[(size_t)d], sizeof(double) * need));
+         m->pack_cap[(size_t)d] = need;
+      }
+      suews_pack_sums_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_sums, h->d_order, h->stride, (int)n, pc, m->d_pack[(size_t)d]);
+      CUDA_OK(cudaGetLastError());
+      for (int k = 0; k < ncols; k++)
+         CUDA_OK(cudaMemcpyPeerAsync(m->d_gather + (size_t)k * m->ncell + (size_t)m->cell0[(size_t)d], h0->device,
+                                     m->d_pack[(size_t)d] + (size_t)k * n, h->device, sizeof(double) * n, h->stream));
+   }
+   // 2. the first device waits for all blocks, then one copy to the host
+   for (int d = 0; d < m->ndev; d++) {
+      CUDA_OK(cudaSetDevice(m->part[(size_t)d]->device));
+      CUDA_OK(cudaStreamSynchronize(m->part[(size_t)d]->stream));
+   }
+   CUDA_OK(cudaSetDevice(h0->device));
+   CUDA_OK(cudaMemcpyAsync(m->pinned, m->d_gather, sizeof(double) * total, cudaMemcpyDeviceToHost, h0->stream));
+   CUDA_OK(cudaStreamSynchronize(h0->stream));
+   // [ncols][ncell] -> [ncell][ncols], the layout of suews_b200_get_sums_cols
+   for (int k = 0; k < ncols; k++) {
+      const double *src = m->pinned + (size_t)k * m->ncell;
+      for (size_t c = 0; c < (size_t)m->ncell; c++) out[c * (size_t)ncols + k] = src[c];
+   }
+   if (gather_ms) *gather_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
    return SUEWS_OK;
 }
 

@@ -54,8 +54,12 @@
    X(em_ibld, 1) X(CH_iroof, 1) X(CH_iwall, 1) X(CH_ibld, 1) X(Tfloor, 1)
 
 // ---- per-cell doubles (the SUEWS_SiteSelect.txt site columns)
-#define SUEWS_CELL_DBL_FIELDS(X) \
-   X(lat, 1) X(lng, 1) X(timezone, 1) X(SurfaceArea, 1) X(alt, 1) X(Z, 1) X(sfr, 7) X(IrrFracPaved, 1) \
+// HOT fields are the small per-surface arrays every stage of a step indexes with a run-time surface number: on the device
+// they live in shared memory (a per-thread record of SUEWS_N_HOT_DBL doubles, suews_kernel.cuh), the COLD ones in the
+// thread's own frame.  The lists are COLD first, HOT last, and the SoA arrays of the handle follow that order.
+#define SUEWS_CELL_HOT_FIELDS(X) X(sfr, 7)
+#define SUEWS_CELL_COLD_FIELDS(X) \
+   X(lat, 1) X(lng, 1) X(timezone, 1) X(SurfaceArea, 1) X(alt, 1) X(Z, 1) X(IrrFracPaved, 1) \
    X(IrrFracBldgs, 1) X(IrrFracEveTr, 1) X(IrrFracDecTr, 1) X(IrrFracGrass, 1) X(IrrFracBSoil, 1) \
    X(IrrFracWater, 1) X(bldgH, 1) X(EveTreeH, 1) X(DecTreeH, 1) X(z0m_in, 1) X(zdm_in, 1) X(FAIBldg, 1) \
    X(FAIEveTree, 1) X(FAIDecTree, 1) X(PopDensDaytime, 2) X(PopDensNighttime, 1) X(TrafficRate, 2) \
@@ -63,15 +67,18 @@
    X(RunoffToWater, 1) X(PipeCapacity, 1) \
    X(dTemp_C, 1) X(dRH, 1) /* optional additive forcing offsets (synthetic configs) */ \
    X(AreaWall, 1)          /* ESTM: fwall = AreaWall / SurfaceArea (suews_ctrl_translate.f95:393-394) */
+#define SUEWS_CELL_DBL_FIELDS(X) SUEWS_CELL_COLD_FIELDS(X) SUEWS_CELL_HOT_FIELDS(X)
 
 // ---- evolving per-cell state (the 29 INTENT(INOUT) arguments, driver.f95:290-333, + hidden SAVEs)
-#define SUEWS_STATE_DBL_FIELDS(X) \
+#define SUEWS_STATE_HOT_FIELDS(X) X(state_id, 7) X(soilstore_id, 7)
+#define SUEWS_STATE_COLD_FIELDS(X) \
    X(qn1_av, 1) X(dqndt, 1) X(qn1_s_av, 1) X(dqnsdt, 1) X(SnowfallCum, 1) X(SnowAlb, 1) X(IceFrac, 7) \
-   X(SnowWater, 7) X(SnowDens, 7) X(SnowFrac, 7) X(SnowPack, 7) X(soilstore_id, 7) X(state_id, 7) \
+   X(SnowWater, 7) X(SnowDens, 7) X(SnowFrac, 7) X(SnowPack, 7) \
    X(StoreDrainPrm, 42) X(alb, 7) X(GDD_id, 3) X(SDD_id, 3) X(LAI_id, 3) X(Tmin_id, 1) X(Tmax_id, 1) \
    X(lenDay_id, 1) X(DecidCap_id, 1) X(albDecTr_id, 1) X(albEveTr_id, 1) X(albGrass_id, 1) X(porosity_id, 1) \
    X(HDD_id, 12) X(WUDay_id, 9) X(Tair_av, 1) X(alb1_hidden, 1) X(lv_switch, 1) \
    X(rsl_cache, 10) /* library-internal: last z0_RSL per stability sign (pure-function memo, dev_rsl.cuh) */
+#define SUEWS_STATE_DBL_FIELDS(X) SUEWS_STATE_COLD_FIELDS(X) SUEWS_STATE_HOT_FIELDS(X)
 
 // ---- ESTM state: what MODULE ESTM_data carries from call to call (the *_grids copies, estm.f95:1587-1603, and
 // the SAVE'd HVAC, Tair2Set and NewtonPolynomial's `converged`).  A separate SoA [field][cell], resident only when
@@ -87,7 +94,12 @@ enum {
    SUEWS_N_CLASS_INT = 0 SUEWS_CLASS_INT_FIELDS(SUEWS_COUNT_X),
    SUEWS_N_CLASS_DBL = 0 SUEWS_CLASS_DBL_FIELDS(SUEWS_COUNT_X),
    SUEWS_N_CELL_DBL = 0 SUEWS_CELL_DBL_FIELDS(SUEWS_COUNT_X),
-   SUEWS_N_STATE_DBL = 0 SUEWS_STATE_DBL_FIELDS(SUEWS_COUNT_X)
+   SUEWS_N_STATE_DBL = 0 SUEWS_STATE_DBL_FIELDS(SUEWS_COUNT_X),
+   SUEWS_N_CELL_HOT = 0 SUEWS_CELL_HOT_FIELDS(SUEWS_COUNT_X),
+   SUEWS_N_STATE_HOT = 0 SUEWS_STATE_HOT_FIELDS(SUEWS_COUNT_X),
+   SUEWS_N_CELL_COLD = SUEWS_N_CELL_DBL - SUEWS_N_CELL_HOT,
+   SUEWS_N_STATE_COLD = SUEWS_N_STATE_DBL - SUEWS_N_STATE_HOT,
+   SUEWS_N_HOT_DBL = SUEWS_N_CELL_HOT + SUEWS_N_STATE_HOT   /* 21: an odd stride in doubles keeps the per-thread records bank-conflict free */
 };
 
 // Output widths without the 5 datetime columns (suews_ctrl_const.f95:49-55)
@@ -113,8 +125,15 @@ template <typename T> struct SuewsFld<T, 1> {
    SUEWS_HD operator T() const { return v[0]; }
    SUEWS_HD SuewsFld &operator=(T x) { v[0] = x; return *this; }
 };
+// a HOT field: same spelling at the use sites (name[i], name.v), storage elsewhere (shared memory)
+template <typename T, int N> struct SuewsRef {
+   T *v;
+   SUEWS_HD T &operator[](int i) { return v[i]; }
+   SUEWS_HD const T &operator[](int i) const { return v[i]; }
+};
 #define SUEWS_DECL_INT(name, n) SuewsFld<int, n> name;
 #define SUEWS_DECL_DBL(name, n) SuewsFld<double, n> name;
+#define SUEWS_DECL_REF(name, n) SuewsRef<double, n> name;
 
 struct SuewsClassParams {
    SUEWS_CLASS_INT_FIELDS(SUEWS_DECL_INT)
@@ -124,12 +143,16 @@ struct SuewsClassParams {
    double prof_sum[6][2];   // sequential SUM of AH, HumAct, Pop, Traff, WUProfA, WUProfM (weekday, weekend)
 };
 
+// device-side records of one cell: the COLD fields by value (the first SUEWS_N_*_COLD doubles of the struct, in list
+// order), the HOT ones as references into the thread's shared-memory record
 struct SuewsCellParams {
-   SUEWS_CELL_DBL_FIELDS(SUEWS_DECL_DBL)
+   SUEWS_CELL_COLD_FIELDS(SUEWS_DECL_DBL)
+   SUEWS_CELL_HOT_FIELDS(SUEWS_DECL_REF)
 };
 
 struct SuewsCellState {
-   SUEWS_STATE_DBL_FIELDS(SUEWS_DECL_DBL)
+   SUEWS_STATE_COLD_FIELDS(SUEWS_DECL_DBL)
+   SUEWS_STATE_HOT_FIELDS(SUEWS_DECL_REF)
 };
 
 struct SuewsEstmState {

@@ -21,7 +21,20 @@
 #ifndef SU_MINBLOCKS
 #define SU_MINBLOCKS 1
 #endif
-#define SU_CHUNK 32   // timesteps staged per bulk copy (32 x 160 B = 5 KB)
+#define SU_CHUNK 16   // timesteps staged per bulk copy (16 x 160 B = 2.5 KB per buffer)
+// Shared memory of a block: the two forcing buffers (static) + one record of SUEWS_N_HOT_DBL doubles per thread (dynamic):
+// the per-surface arrays every stage indexes with a run-time surface number -- surface fractions, surface and soil stores.
+// In the thread's frame a run-time index makes them local-memory arrays whose every first touch of a step misses L1
+// (1024 threads x 4 KB of frame); here they are one LDS away.  Record stride 21 doubles (odd): the 16 lanes of a 64-bit
+// shared-memory transaction hit 16 distinct bank pairs.
+// (SU_HOT_N = 21 all three arrays, 14 sfr + surface stores, 7 sfr only, 0 none; the others stay in the frame.  Measured
+// on 606 208 cells x 288 steps, P0: 0 -> 3.63e8, 7 -> 3.82e8, 14 -> 3.93e8, 21 -> 3.84e8 cell-steps/s: beyond 14 the L1 that the
+// shared memory takes away costs more than the third array gains)
+#ifndef SU_HOT_N
+#define SU_HOT_N 14
+#endif
+#define SU_HOT_STRIDE (SU_HOT_N | 1)
+#define SU_HOT_BYTES(block) ((size_t)(block) * SU_HOT_STRIDE * sizeof(double))
 
 struct SuRunArgs {
    const SuewsClassParams *classes;
@@ -117,10 +130,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 //   SNOW  1 / 0: every / no class of the bucket has snowUse = 1; -1: decided per class at run time
 //   ESTM  0: no class of the bucket runs StorageHeatMethod 4/14; -1: decided per class at run time
 enum { SU_K_FULL = 0, SU_K_ACC = 1, SU_K_P0 = 2 };
+#ifdef SU_PHASE_CLOCKS
+typedef cudaError_t (*su_clk_reader_t)(unsigned long long *out16, int reset);
+extern "C" void su_register_clk_reader(su_clk_reader_t f);
+#endif
 // the launchers are generated by suews_kernel_inst.cu, one translation unit per instance (they compile side by side)
 #define SU_LAUNCHER_NAME_(k, s, e, b) suews_launch_k##k##_s##s##_e##e##_b##b
 #define SU_LAUNCHER_NAME(k, s, e, b) SU_LAUNCHER_NAME_(k, s, e, b)
-#define SU_DECL_LAUNCHER(k, s, e, b) cudaError_t SU_LAUNCHER_NAME(k, s, e, b)(int grid, cudaStream_t stream, const struct SuRunArgs &a)
+#define SU_DECL_LAUNCHER(k, s, e, b) cudaError_t SU_LAUNCHER_NAME(k, s, e, b)(int nslot, cudaStream_t stream, const struct SuRunArgs &a)
 // (template arguments -1 are spelled m1 in the launcher names)
 SU_DECL_LAUNCHER(0, m1, m1, 1024);
 SU_DECL_LAUNCHER(0, m1, m1, 256);
@@ -130,12 +147,19 @@ SU_DECL_LAUNCHER(1, 0, 0, 1024);
 SU_DECL_LAUNCHER(2, 0, 0, 1024);
 SU_DECL_LAUNCHER(2, 1, 0, 1024);
 
+#ifdef SU_CONST_CLASS   // tuning build: the (single) class record in the constant bank instead of behind a pointer
+static __constant__ SuewsClassParams su_c_class;
+#endif
 template <int K, int SNOWK, int ESTMK, int BLOCK, int MINBLOCKS>
 __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a)
 {
    constexpr bool FULL = (K == SU_K_FULL);
    __shared__ alignas(128) SuewsStepRec sm_steps[2][SU_CHUNK];
    __shared__ alignas(8) uint64_t sm_bar[2];
+   extern __shared__ double sm_hot[];
+   double hot_frame[SUEWS_N_HOT_DBL - SU_HOT_N + 1];   // (the arrays a tuning build keeps out of shared memory)
+   double *const hot_sm = sm_hot + (size_t)threadIdx.x * SU_HOT_STRIDE;
+#define SU_HOTP(j) (((j) < SU_HOT_N) ? (hot_sm + (j)) : (hot_frame + ((j) - SU_HOT_N)))
 
    const int slot = a.slot0 + blockIdx.x * blockDim.x + threadIdx.x;
    const bool active = slot < a.slot0 + a.nslot;
@@ -157,6 +181,10 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    // thread-slot order, so each of these loads and stores is one contiguous line per warp.
    SuewsCellParams C;
    SuewsCellState S;
+   C.sfr.v = SU_HOTP(0);
+   S.state_id.v = SU_HOTP(SUEWS_N_CELL_HOT);
+   S.soilstore_id.v = SU_HOTP(SUEWS_N_CELL_HOT + 7);
+   for (int j = 0; j < SUEWS_N_HOT_DBL; j++) *SU_HOTP(j) = 0.0;
    SuDiag dg;
    dg.fatal = 0; dg.warn[0] = 0; dg.warn[1] = 0;
    double acc[(K == SU_K_P0) ? 1 : SUEWS_NCOL_SUEWS];
@@ -173,12 +201,14 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    if (active) {
       cls = a.class_of_slot[slot];
       tz = a.tz_of_slot[slot];
-      double *cp = reinterpret_cast<double *>(&C);
+      double *cp = reinterpret_cast<double *>(&C);   // COLD fields by value, then the HOT ones into the shared-memory record
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_CELL_DBL; j++) cp[j] = a.cellp[(size_t)j * a.stride + slot];
+      for (int j = 0; j < SUEWS_N_CELL_COLD; j++) cp[j] = a.cellp[(size_t)j * a.stride + slot];
+      for (int j = 0; j < SUEWS_N_CELL_HOT; j++) *SU_HOTP(j) = a.cellp[(size_t)(SUEWS_N_CELL_COLD + j) * a.stride + slot];
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) sp[j] = a.state[(size_t)j * a.stride + slot];
+      for (int j = 0; j < SUEWS_N_STATE_COLD; j++) sp[j] = a.state[(size_t)j * a.stride + slot];
+      for (int j = 0; j < SUEWS_N_STATE_HOT; j++) *SU_HOTP(SUEWS_N_CELL_HOT + j) = a.state[(size_t)(SUEWS_N_STATE_COLD + j) * a.stride + slot];
       dg.fatal = a.fatal[slot];
       dg.warn[0] = a.warn[slot];
       dg.warn[1] = a.warn[a.stride + slot];
@@ -205,7 +235,11 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    D.albDecTr_id = S.albDecTr_id; D.albEveTr_id = S.albEveTr_id; D.albGrass_id = S.albGrass_id; D.porosity_id = S.porosity_id;
    D.DecidStoreCap = SU_SDP(S.StoreDrainPrm.v, 5, DECID);
    D.deltaLAI = 0;
+#ifdef SU_CONST_CLASS
+   const SuewsClassParams &P = su_c_class;
+#else
    const SuewsClassParams &P = a.classes[cls];
+#endif
    SuSite site;
    site.spa.x = 0; site.spa.y = 0; site.spa.sin_lat = 0; site.spa.cos_lat = 1; site.veg029 = 0;
    if (active) su_site_consts(C, site);
@@ -315,7 +349,8 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
       S.albDecTr_id = D.albDecTr_id; S.albEveTr_id = D.albEveTr_id; S.albGrass_id = D.albGrass_id; S.porosity_id = D.porosity_id;
       double *sp = reinterpret_cast<double *>(&S);
 #pragma unroll 1
-      for (int j = 0; j < SUEWS_N_STATE_DBL; j++) a.state[(size_t)j * a.stride + slot] = sp[j];
+      for (int j = 0; j < SUEWS_N_STATE_COLD; j++) a.state[(size_t)j * a.stride + slot] = sp[j];
+      for (int j = 0; j < SUEWS_N_STATE_HOT; j++) a.state[(size_t)(SUEWS_N_STATE_COLD + j) * a.stride + slot] = *SU_HOTP(SUEWS_N_CELL_HOT + j);
       if (estm_on) {
          double *ep = reinterpret_cast<double *>(&ES);
 #pragma unroll 1

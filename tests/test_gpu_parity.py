@@ -44,6 +44,29 @@ def rel_err(out, ref, group="SUEWS"):
     return e
 
 
+# The second measure: the plain per-value relative error |out - ref| / max(|ref|, floor) with an explicit absolute floor.
+# The floor says below which magnitude a value is compared absolutely (at floor * tol): 1e-3 in the column's unit for
+# fluxes, stores and everything else; for the columns that are differences of two ~273 K / ~1e4 W m-2 numbers (deg C
+# temperatures, QHresis) the last-ulp noise of the operands is ~5e-14 / ~2e-12 absolute whatever the value, so their
+# floor is 1 (deg C, W m-2).
+VALUE_FLOOR = 1e-3
+VALUE_FLOOR_CANCEL = 1.0
+
+
+def rel_err_value(out, ref, group="SUEWS"):
+    """out, ref: [nstep, ncol] without the 5 datetime columns -> per-value relative error with the absolute floors above"""
+    floor = np.full(ref.shape[1], VALUE_FLOOR)
+    for c in TEMP_COLS.get(group, []) + list(BIG_COLS.get(group, {}).keys()):
+        if c < floor.size:
+            floor[c] = VALUE_FLOOR_CANCEL
+    scale = np.maximum(np.abs(ref), floor[None, :])
+    same_nonfinite = (~np.isfinite(ref)) & (~np.isfinite(out)) & ((np.isnan(ref) == np.isnan(out)))
+    with np.errstate(invalid="ignore"):
+        e = np.abs(out - ref) / scale
+    e[same_nonfinite] = 0.0
+    return e
+
+
 @pytest.fixture(scope="module")
 def gpu_and_ref_2005():
     from suews_b200 import OUT_FULL, OUT_SUM82, SuewsBatch
@@ -70,6 +93,9 @@ def test_blocks_match_oracle(gpu_and_ref_2005, group):
     e = rel_err(out[:, 5:], r[:, 5:], group)
     assert e[:288].max() <= TOL_DAY1, (group, float(e[:288].max()), np.unravel_index(e[:288].argmax(), e[:288].shape))
     assert e.max() <= 1e-8, (group, float(e.max()))
+    ev = rel_err_value(out[:, 5:], r[:, 5:], group)      # per value, not per column scale
+    print("%s: worst error relative to the column scale %.3e, relative to the value itself %.3e (day 1)" % (group, e[:288].max(), ev[:288].max()))
+    assert ev[:288].max() <= TOL_DAY1, (group, float(ev[:288].max()), np.unravel_index(ev[:288].argmax(), ev[:288].shape))
     if group == "RSL":
         assert np.array_equal(out[:, -1], r[:, -1])             # flag_RSL
     if group == "DailyState":
@@ -794,3 +820,39 @@ def test_baserun_output_files_from_the_gpu_path(tmp_path):
     assert fields == 120 * 87
     assert bad <= 3, bad                # measured: 0 -- the file is byte-identical to the reference's
     assert worst <= 1e-12               # measured: 0
+
+
+@pytest.mark.gpu
+def test_multi_device_handle_equals_one_batch():
+    """suews_b200_multi_*: the cells of a run in contiguous blocks on several devices (here two blocks -- on two GPUs when
+    the box has them, else both on device 0), advanced side by side, sums gathered to the first device and to the host.
+    Cells are independent, so every cell must come out bit for bit as in one single-device batch."""
+    from suews_b200 import OUT_SUM7, SuewsBatch, SuewsMultiBatch, synth, _lib
+    base = fx.state_init(2005)
+    met = fx.forcing(2005)[:288]
+    ncell = 2500                                   # not a multiple of anything: blocks of 834 / 833 / 833 cells
+    ngpu = _lib.lib().suews_b200_device_count()
+    devices = [0, 1 % ngpu, 2 % ngpu]
+    cols = list(PARITY_COLS.values())
+    one = SuewsBatch(ncell, 1)
+    synth.build_batch(one, base, scheme="baserun")
+    one.upload()
+    one.set_forcing(met)
+    one.advance(0, 288, OUT_SUM7)
+    multi = SuewsMultiBatch(ncell, 1, devices=devices)
+    synth.build_batch(multi, base, scheme="baserun")
+    assert [p[1:] for p in multi.parts()] == [(0, 834), (834, 833), (1667, 833)]
+    multi.upload()
+    multi.set_forcing(met)
+    multi.advance(0, 144, OUT_SUM7, sync=False)    # two launches per device, asynchronous
+    multi.advance(144, 144, OUT_SUM7)
+    got, ms = multi.gather_sums(cols)
+    assert ms > 0
+    assert np.array_equal(got, one.sums_cols(cols))
+    for nm in ("state_id", "soilstore_id", "SnowPack", "HDD_id", "qn1_av"):
+        assert np.array_equal(multi.get_state(nm), one.get_state(nm)), nm
+    f1, _w1, it1 = one.diag()
+    f2, _w2, it2 = multi.diag()
+    assert np.array_equal(f1, f2) and np.array_equal(it1, it2)
+    one.close()
+    multi.close()

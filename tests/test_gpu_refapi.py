@@ -128,7 +128,7 @@ def test_gfortran_positional_symbol_equals_pointer_table_call():
     f.argtypes = [C.c_void_p] * len(ptrs)
     assert len(ptrs) == 200
     f(*ptrs)
-    assert last_error()[0] == 0 or True
+    # (a non-zero return code inside the shim is the reference's STOP: the process would have ended, suews_refapi.cpp fortran_stop)
     for a, b in zip(outs, ref):
         assert np.array_equal(a, b)
 

@@ -165,3 +165,27 @@ def test_checkpoint_writer_reproduces_the_reference_file(fname, year, cell_after
         cell.run(fx.forcing(2005), want=())
     text = checkpoint.write_text(checkpoint.state_vector(cell.get_state), snow_use=1)
     assert text == open(fx.GOLDEN + "/" + fname).read()
+
+
+def test_rsl_humidity_diagnostics_are_nan_exactly_where_the_reference_divides_zero_by_zero():
+    """RSLProfile forms the in-canopy humidity profile as (q_h*EXP(..) - q_h)/qStar_RSL (suews_phys_rslprof.f95:285) with
+    q_h = Scc*qStar_RSL/(beta*f) (:281) and qStar_RSL = -(qe/lv*avdens)/UStar (:266): when QE is exactly zero (saturated
+    air over frozen, snow-covered surfaces) that is 0/0, and the reference's q profile, q2 and RH2 are NaN for that step
+    (T2 and U10 are not).  The restatement keeps it; this pins where it happens: on those steps and on no other."""
+    from suews_b200 import synth
+    base = fx.state_init(2005)
+    met = fx.forcing(2005)[:288].copy()
+    d = synth.base_with_scheme(base, "baserun")
+    site = synth.cell_site_arrays(12, 1, {k.lower(): v for k, v in base.items()})   # a synthetic cell that saturates (RH + dRH >= 100)
+    for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
+        d[k.lower()] = np.atleast_1d(site[k][0])
+    met[:, 11] += site["dTemp_C"][0]
+    met[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), met[:, 10] + site["dRH"][0]))
+    out = ol.Cell(d).run(met, want=("SUEWS",))["SUEWS"][:, 5:]
+    q2_nan, rh2_nan = np.isnan(out[:, 79]), np.isnan(out[:, 81])
+    assert q2_nan.sum() > 0                                     # the case exists in this cell's first day
+    assert np.array_equal(q2_nan, rh2_nan)
+    assert np.array_equal(q2_nan, out[:, 9] == 0.0)             # exactly the steps with QE == 0
+    assert not np.isnan(out[:, 78]).any() and not np.isnan(out[:, 80]).any()   # T2, U10 stay finite
+    other = [c for c in range(82) if c not in (79, 81)]
+    assert not np.isnan(out[:, other]).any()

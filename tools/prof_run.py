@@ -37,7 +37,11 @@ for i in range(3):
     if has_clk:
         lib().suews_b200_debug_phase_clocks(clk, 0)
         tot = float(sum(clk[:8])) or 1.0
+        tot += float(sum(clk[10:16]))
         print("   block-steps %d, Tsurf trips/step %.2f; share of block cycles: " % (clk[9], clk[8] / max(clk[9], 1)) +
               ", ".join("%s %.1f%%" % (PH[k], 100.0 * clk[k] / tot) for k in range(8)))
+        SUB = ["P1a cal_AtmMoist (1st Lat_vap search)", "P1b soil moisture, water use, QF, snow albedo", "P1c drainage", "P1d ReDistributeWater",
+               "P1e SurfaceResistance", "F1a cal_QE_full (state update)"]
+        print("   sub-stages (own barrier; taken out of P1 / F1 above): " + ", ".join("%s %.1f%%" % (SUB[k], 100.0 * clk[10 + k] / tot) for k in range(6)))
 fatal, warn, iters = b.diag()
 print("fatal cells", int((fatal != 0).sum()), "iters/step", iters.sum() / (ncell * (row0 + 3.0 * nsteps)))
