@@ -36,7 +36,7 @@ struct SuSnowHeat {
 // snow.f95:33-193 (Snow_cal_MeltHeat) + :195-473 (MeltHeat) + :1454-1489 (update_snow_dens).
 // In/out arrays may alias exactly as in the reference call (driver.f95:793-805): inputs are read
 // before any output is written.
-SU_DEVNI void Snow_cal_MeltHeat(const SuewsClassParams &P, const double *sfr, double lvS_J_kg, double lv_J_kg,
+SU_DEV void Snow_cal_MeltHeat(const SuewsClassParams &P, const double *sfr, double lvS_J_kg, double lv_J_kg,
                                 double tstep_real, double Temp_C, double Precip, double nsh_real,
                                 const double *Tsurf_ind, const double *state_id, const double *qn1_ind_snow,
                                 const double *SnowWater, const double *deltaQi, const double *SnowPack_in,
@@ -196,15 +196,24 @@ struct SuQEWork {
 struct SuQEIn {
    const double *state_id, *soilstore_id, *SnowPack, *SnowFrac, *SnowWater, *SnowDens;
 };
+// Terms of Evap_SUEWS_Snow (snow.f95:1154-1207) that are the same for the seven surfaces of a trip: formed by the first
+// snow-covered surface that needs them (with the warnings the ice vapour pressure may raise), reused by the others.
+struct SuSnowIce {
+   bool have;
+   double vdrc_RA;   // vdrcIce / RAsnow
+   double tlv_sub;   // lvS_J_kg / tstep
+};
+// (inlined into its two callers -- the committing loop of cal_QE_full and the light loop of a trip: as a real function
+// its 45 arguments and five by-reference results travelled through the stack, 10 % of the snow kernel's local traffic)
 template <bool COMMIT>
-SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, int is, int imin, int it, int dow,
+SU_DEV void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellParams &C, int is, int imin, int it, int dow,
                        double nsh_real, double lvS_J_kg, double avdens, double avRh, double Press_hPa, double Temp_C,
                        double RAsnow, double psyc_hPa, double avcp, double sIce_hPa, double PervFraction,
                        double vegfraction, double vpd_hPa, double qn_e, double s_hPa, double ResistSurf, double RA,
                        double rb, double tlv, double Precip, const double *drain, const double *stateOld,
                        const SuSnowHeat &h, const double *Tsurf_ind, const double *StoreDrainPrm, double capStore_is,
                        const double *AddWater,
-                       const double *AddWaterRunoff, const SuQEIn &in, double *SurplusEvap, SuQEWork &w, double &chSnow_tot, double &ev_tot, double &qe_tot,
+                       const double *AddWaterRunoff, const SuQEIn &in, double *SurplusEvap, SuEvapTrip &et, SuSnowIce &ice, SuQEWork &w, double &chSnow_tot, double &ev_tot, double &qe_tot,
                        double &runoff_tot, double &surf_chang_tot)
 {
    const double *sfr = C.sfr.v;
@@ -229,7 +238,7 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
    const double mw_ind = h.mw_ind[is], freezMelt = h.FreezMelt[is], FreezState = h.FreezState[is],
                 FreezStateVol = h.FreezStateVol[is], rainOnSnow = h.rainOnSnow[is];
    const int u = (dow == 1 || dow == 7) ? 1 : 0;
-   const bool rem_time = (SU_PROF24(P.SnowProf_24hr.v, it, u) == 1 && is < 2 && (imin == (nsh_real - 1) / nsh_real * 60));
+   const bool rem_time = (is < 2 && SU_PROF24(P.SnowProf_24hr.v, it, u) == 1 && (imin == (nsh_real - 1) / nsh_real * 60));
 
    ev_tot = 0; qe_tot = 0; runoff_tot = 0; surf_chang_tot = 0; chSnow_tot = 0;
    if (COMMIT) {
@@ -241,18 +250,21 @@ SU_DEVNI void SnowCalc(SuDiag &dg, const SuewsClassParams &P, const SuewsCellPar
    const double WaterHoldCapFrac =
       (sd_ >= 200) ? P.CRWmin : P.CRWmin + (P.CRWmax - P.CRWmin) * (200 - sd_) / 200;
 
-   if (sf_ < 1)
-      cal_evap(P.EvapMethod, st_, P.WetThresh[is], capStore_is, vpd_hPa, avdens, avcp, qn_e,
-               s_hPa, psyc_hPa, ResistSurf, RA, rb, tlv, ev, qe);
+   if (sf_ < 1) evap_surface<true>(et, st_, P.WetThresh[is], capStore_is, ev, qe);   // cal_evap with the trip's shared terms
 
    if (sf_ > 0) {   // Evap_SUEWS_Snow snow.f95:1154-1207
-      double T = Temp_C;
+      if (!ice.have) {
+         double T = Temp_C;
+         double esIce = sat_vap_pressIce(dg, T, Press_hPa, 1);
+         double EaIce = avRh / 100 * esIce;
+         double vdrcIce = (esIce - EaIce) * avdens * avcp;
+         ice.vdrc_RA = su_div0(vdrcIce, RAsnow);   // zero numerators are the rule here (su_div0)
+         ice.tlv_sub = lvS_J_kg / (double)P.tstep;
+         ice.have = true;
+      }
       double sae_snow = sIce_hPa * (h.Qm_rain[is] - h.Qm_melt[is]);
-      double esIce = sat_vap_pressIce(dg, T, Press_hPa, 1);
-      double EaIce = avRh / 100 * esIce;
-      double vdrcIce = (esIce - EaIce) * avdens * avcp;
-      tlv_sub = lvS_J_kg / (double)P.tstep;
-      double e_snow = sae_snow + su_div0(vdrcIce, RAsnow);   // zero numerators are the rule here (su_div0)
+      tlv_sub = ice.tlv_sub;
+      double e_snow = sae_snow + ice.vdrc_RA;
       double qe_snow = su_div0(e_snow, sIce_hPa + psyc_hPa);
       ev_snow = su_div0(qe_snow, tlv_sub);
    }

@@ -231,6 +231,8 @@ SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, int snowUse, cons
    double qe_per_tstep = 0, ev = 0, qe_surf = 0;
    SuEvapTrip et;
    evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
+   SuSnowIce ice;
+   ice.have = false; ice.vdrc_RA = 0; ice.tlv_sub = 0;
    SuQEIn win;   // SnowCalc reads the entry values of its surface from the work arrays it commits to
    win.state_id = W.state_id; win.soilstore_id = W.soilstore_id; win.SnowPack = W.SnowPack; win.SnowFrac = W.SnowFrac;
    win.SnowWater = W.SnowWater; win.SnowDens = W.SnowDens;
@@ -245,7 +247,7 @@ SU_UNROLL1
             SnowCalc<true>(dg, P, C, is, R.imin, R.it, R.dow, nsh_r, A.lvS_J_kg, A.avdens, avRh, R.Press_hPa, Temp_C, RAsnow,
                            Lm.psyc_hPa, A.avcp, Lm.sIce_hpa, PervFraction, VegFraction, A.VPd_hpa, qn_e, Lm.s_hPa, H.ResistSurf,
                            RA, rb, tlv, R.Precip, H.drain, S.state_id.v, Hs, Tsurf_ind, S.StoreDrainPrm.v, cap, H.AddWater,
-                           H.AddWaterRunoff, win, W.SurplusEvap, W, chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot);
+                           H.AddWaterRunoff, win, W.SurplusEvap, et, ice, W, chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot);
             T.ev_per_tstep = T.ev_per_tstep + ev_tot;
             qe_per_tstep = qe_per_tstep + qe_tot;
             T.runoff_per_tstep = T.runoff_per_tstep + runoff_tot;
@@ -310,6 +312,8 @@ SU_DEV double cal_QE_light_snow(SuDiag &dg, const SuewsClassParams &P, const Sue
    for (int is = 0; is < NSURF; is++) SurplusEvap[is] = 0;
    SuEvapTrip et;
    evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
+   SuSnowIce ice;
+   ice.have = false; ice.vdrc_RA = 0; ice.tlv_sub = 0;
    SuQEIn in;   // entry values of a trip: the *_prev state as Snow_cal_MeltHeat left it
    in.state_id = S.state_id.v; in.soilstore_id = S.soilstore_id.v; in.SnowPack = SnowPack_m; in.SnowFrac = SnowFrac_q;
    in.SnowWater = S.SnowWater.v; in.SnowDens = SnowDens_m;
@@ -322,7 +326,7 @@ SU_UNROLL1
             SnowCalc<false>(dg, P, C, is, R.imin, R.it, R.dow, nsh_r, A.lvS_J_kg, A.avdens, avRh, R.Press_hPa, Temp_C, RAsnow,
                             Lm.psyc_hPa, A.avcp, Lm.sIce_hpa, PervFraction, VegFraction, A.VPd_hpa, qn_e, Lm.s_hPa, H.ResistSurf,
                             RA, rb, tlv, R.Precip, H.drain, S.state_id.v, Hs, Tsurf_ind, S.StoreDrainPrm.v, cap, H.AddWater,
-                            H.AddWaterRunoff, in, SurplusEvap, Wdummy, chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot);
+                            H.AddWaterRunoff, in, SurplusEvap, et, ice, Wdummy, chSnow_tot, ev_tot, qe_tot, runoff_tot, surf_chang_tot);
             qe_per_tstep = qe_per_tstep + qe_tot;
          }
       } else {
