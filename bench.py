@@ -380,11 +380,28 @@ def main():
     fp64_peak = None
     if _lib.lib().suews_b200_fp64_peak(local_rank, C.byref(tf)) == 0:
         fp64_peak = tf.value
+    # executed FP64 flops (DFMA = 2) from the ncu captures, averaged over four points of the year (tools/run_captures.sh)
     fp64 = {"peak_tflops_measured_dfma": fp64_peak, "flops_per_cell_step_executed": prof.get("fp64_flops_per_cell_step"),
             "source": prof.get("source")}
     if fp64_peak and prof.get("fp64_flops_per_cell_step"):
         fp64["achieved_tflops"] = prof["fp64_flops_per_cell_step"] * ncell * 288 / launch_s / 1e12
         fp64["frac"] = fp64["achieved_tflops"] / fp64_peak
+    # the bound that matters: ALGORITHMIC flops of the hoisted minimal algorithm, counted by the oracle's op
+    # counter with the published libm weights (tools/oracle_opcount.py -> profiles/oracle_opcount_<scheme>.json), x the
+    # measured rate, against the DFMA peak measured on this device
+    roofline_fp64 = None
+    try:
+        oc = json.load(open(os.path.join(ROOT, "profiles", "oracle_opcount_%s.json" % a.scheme)))
+        falg = float(oc["hoisted"]["weighted_flops_per_cell_step"])
+        ach = falg * value / float(world) / 1e12
+        roofline_fp64 = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": (ach / fp64_peak) if fp64_peak else None, "flops_per_cell_step_algorithmic": falg,
+                         "flops_per_cell_step_as_written": float(oc["literal"]["weighted_flops_per_cell_step"]),
+                         "peak_source": "DFMA throughput measured on this device (suews_b200_fp64_peak)",
+                         "source": "oracle op counter, hoisted minimal algorithm, days-of-year %s (profiles/oracle_opcount_%s.json); "
+                                   "weights add/mul/div/sqrt 1, exp 20, log 25, pow 60, sin/cos 30, atan 35" % (oc["days_of_year"], a.scheme)}
+    except Exception:
+        pass
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -402,9 +419,11 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": (prof["dram_bytes_per_cell_step"] * ncell * 288.0 if "dram_bytes_per_cell_step" in prof else None), "peak_source": peak_src,
-                     "note": "kernel is FP64-pipe / latency bound, not HBM bound (SURVEY 8d); see fp64"},
+                     "note": "kernel is FP64-pipe / latency bound, not HBM bound (SURVEY 8d); see roofline_fp64"},
         "fp64": fp64,
     }
+    if roofline_fp64:
+        line["roofline_fp64"] = roofline_fp64
     if all_stages:
         line["all_stages"] = all_stages
     if schemes:

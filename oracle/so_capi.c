@@ -8,6 +8,10 @@
 #include <string.h>
 #include <strings.h>
 
+#ifdef __cplusplus   /* (the counting build compiles these sources as C++, so_count.h) */
+extern "C" {
+#endif
+
 typedef struct {
    const char *name;
    int is_int;
@@ -213,3 +217,30 @@ int so_run_cells(int ncell, const SoParams *params, SoState *states, const doubl
 
 size_t so_sizeof_params(void) { return sizeof(SoParams); }
 size_t so_sizeof_state(void) { return sizeof(SoState); }
+
+#ifdef SO_OPCOUNT
+/* ---- op counter of the counting build (so_count.h, `make count`) ---- */
+int so_opcount_on = 0, so_opcount_hoisted = 1;
+unsigned long long so_opcount_main[16], so_opcount_diag[16];
+unsigned long long *so_opcount_cur = so_opcount_main;
+/* mode: 0 = every operation the restated reference algorithm executes, 1 = the hoisted minimal algorithm */
+void so_opcount_start(int hoisted)
+{
+   int k;
+   for (k = 0; k < 16; k++) { so_opcount_main[k] = 0; so_opcount_diag[k] = 0; }
+   so_opcount_cur = so_opcount_main;
+   so_opcount_hoisted = hoisted;
+   so_opcount_on = 1;
+}
+/* out32: 16 counts of the flux/state path, then 16 of the diagnostics (RSL profile, SOLWEIG) */
+void so_opcount_stop(unsigned long long *out32)
+{
+   int k;
+   so_opcount_on = 0;
+   for (k = 0; k < 16; k++) { out32[k] = so_opcount_main[k]; out32[16 + k] = so_opcount_diag[k]; }
+}
+#endif
+
+#ifdef __cplusplus
+}
+#endif

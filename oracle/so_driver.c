@@ -449,6 +449,10 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
    Ts_iter = Temp_C;
    i_iter = 1;
    while ((!flag_converge) && i_iter < 100) {
+      /* SO_CNT_*: op-counter regions of the counting build (oracle/so_count.h; no-ops in the normal build).  In "hoisted"
+       * mode the stages whose inputs do not change from trip to trip are counted on the first trip only: that is the
+       * minimal algorithm SURVEY 8(d) defines the algorithmic flops on; the arithmetic itself is untouched. */
+      SO_CNT_ONCE_BEGIN(i_iter > 1);
       so_cal_dectime(f->id, f->it, f->imin, f->isec, &dectime);
       so_cal_tstep(p->tstep, &nsh, &nsh_real, &tstep_real);
       cal_surf(p->sfr, &VegFraction, &ImpervFraction, &PervFraction, &NonWaterFraction);
@@ -472,11 +476,13 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
                         pv.soilstore_id, nx.HDD_id, &nx.Tmin_id, &nx.Tmax_id, &nx.lenDay_id, &nx.albDecTr_id,
                         &nx.albEveTr_id, &nx.albGrass_id, &nx.porosity_id, &nx.DecidCap_id, nx.StoreDrainPrm,
                         nx.LAI_id, nx.GDD_id, nx.SDD_id, &deltaLAI, nx.WUDay_id);
+      SO_CNT_END;
 
       so_cal_AtmMoist(cx, &Temp_C, f->Press_hPa, f->avRh, dectime, &lv_J_kg, &lvS_J_kg, &es_hPa, &Ea_hPa, &VPd_hpa,
                       &VPD_Pa, &dq, &dens_dry, &avcp, &avdens);
       fl.Temp_C = Temp_C;
 
+      SO_CNT_ONCE_BEGIN(i_iter > 1);
       so_update_SoilMoist(NonWaterFraction, p->SoilStoreCap, p->sfr, pv.soilstore_id, &SoilMoistCap, &SoilState, &vsmd,
                           &smd);
 
@@ -487,7 +493,11 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
 
       cal_AnthropogenicEmission(cx, p, dayofWeek_id, DLS, nx.HDD_id, f->imin, f->it, f->qf_obs, Temp_C, &qf, &QF_SAHP,
                                 &Fc_anthro, &Fc_build, &Fc_metab, &Fc_point, &Fc_traff);
+      SO_CNT_END;
 
+      /* radiation, storage heat and melt heat repeat per trip only when the surface temperature feeds back into NARP
+       * (NetRadiationMethod 11-13) or ESTM advances its element temperatures (StorageHeatMethod 4/14) */
+      SO_CNT_ONCE_BEGIN(i_iter > 1 && !((p->NetRadiationMethod >= 10 && p->NetRadiationMethod < 100) || p->StorageHeatMethod == 4 || p->StorageHeatMethod == 14));
       cal_Qn(cx, p, &fl, pv.SnowPack, dectime, ZENITH_deg, Ts_iter, Temp_C, Ea_hPa, pv.SnowAlb, pv.SnowFrac,
              pv.IceFrac, pv.alb, nx.albDecTr_id, nx.albEveTr_id, nx.albGrass_id, nx.alb, &ldown, &fcld, &qn1,
              &qn1_snowfree, &qn1_S, &kclear, &kup, &lup, &tsurf, qn1_ind_snow, kup_ind_snow, Tsurf_ind_snow, tsurf_ind,
@@ -505,6 +515,7 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
                            &nx.SnowfallCum, &mwh, &Qm, &QmFreez, &QmRain, &veg_fr, snowCalcSwitch, Qm_melt,
                            Qm_freezState, Qm_rain, FreezMelt, FreezState, FreezStateVol, rainOnSnow, snowDepth, mw_ind,
                            out->Snow);
+      SO_CNT_END;
 
       if (i_iter == 1) {
          so_LUMPS_cal_QHQE(cx, p->veg_type, p->snowUse, qn1, qf, qs, Qm, Temp_C, veg_fr, avcp, f->Press_hPa, lv_J_kg,
@@ -516,9 +527,11 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
          QH_Init = qh;
       }
 
+      SO_CNT_ONCE_BEGIN(i_iter > 1);
       cal_Water(cx, p, NonWaterFraction, addPipes, addImpervious, addVeg, addWaterBody, pv.state_id, pv.soilstore_id,
                 nx.StoreDrainPrm, nsh_real, &drain_per_tstep, drain, frac_water2runoff, &AdditionalWater, &runoffPipes,
                 &runoff_per_interval, AddWater, state_id_updated, soilstore_updated);
+      SO_CNT_END;
 
       cal_Resistance(cx, p, &fl, avdens, avcp, QH_Init, ZZD, z0m, zdm, Temp_C, VegFraction, dq, vsmd, nx.LAI_id,
                      nx.SnowFrac, &UStar, &TStar, &L_mod, &zL, &gsc, &ResistSurf, &RA, &RAsnow, &rb);
@@ -535,12 +548,15 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
 
       cal_QH(qn1, qf, QmRain, qe, qs, QmFreez, Qm, avdens, avcp, tsurf, Temp_C, RA, &qh, &qh_residual, &qh_resist);
 
+      /* (every trip restarts from the *_prev state: only the last trip's soil-water exchange survives) */
+      SO_CNT_ONCE_BEGIN(i_iter > 1);
       so_cal_HorizontalSoilWater(p->sfr, p->SoilStoreCap, p->SoilDepth, p->SatHydraulicConduct, p->SurfaceArea,
                                  NonWaterFraction, tstep_real, nx.soilstore_id, runoffSoil, &runoffSoil_per_tstep);
 
       so_cal_SoilState(cx, p->SMDMethod, f->xsmd, NonWaterFraction, SoilMoistCap, p->SoilStoreCap,
                        surf_chang_per_tstep, nx.soilstore_id, soilstore_updated, p->sfr, &smd, smd_nsurf,
                        &tot_chang_per_tstep, &SoilState);
+      SO_CNT_END;
 
       TSfc_C = so_cal_tsfc(qh, avdens, avcp, RA, Temp_C);
 
@@ -555,8 +571,11 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
    }
    cx->n_iter_last = i_iter - 1;
 
+   /* diagnostics no flux sum and no state depends on (T2, q2, U10, RH2 and the SOLWEIG point values): counted apart */
+   SO_CNT_DIAG_BEGIN();
    so_RSLProfile(cx, zH, z0m, zdm, L_mod, p->sfr, FAI, p->StabilityMethod, avcp, lv_J_kg, avdens, f->avU1, Temp_C,
                  f->avRh, f->Press_hPa, p->Z, qh, qe, &t2_C, &q2_gkg, &U10_ms, &RH2, out->RSL);
+   SO_CNT_DIAG_END();
 
    /* BiogenCO2 still sees the un-committed SnowFrac argument (driver.f95:957) */
    cal_BiogenCO2(cx, p, &fl, dectime, Fc_anthro, gfunc, nx.LAI_id, st->SnowFrac, t2_C, Temp_C, vsmd, &Fc, &Fc_biogen,
@@ -575,8 +594,10 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
    st->alb1_hidden = alb1;
    /* SOLWEIG point diagnostics (driver.f95:997-1002): the state has been committed, so alb is alb_next */
    if (p->sfr[BLDG] > 0) {
-      so_SOLWEIG_cal_main(f->id, f->it, dectime, 0.8, FAI, f->avkdn, ldown, Temp_C, f->avRh, f->Press_hPa, TSfc_C, p->lat,
+SO_CNT_DIAG_BEGIN();
+            so_SOLWEIG_cal_main(f->id, f->it, dectime, 0.8, FAI, f->avkdn, ldown, Temp_C, f->avRh, f->Press_hPa, TSfc_C, p->lat,
                           ZENITH_deg, azimuth, 1.0, st->alb[0], st->alb[1], p->emis[0], p->emis[1], p->bldgH, out->SOLWEIG);
+      SO_CNT_DIAG_END();
    } else {
       for (i = 0; i < NCOL_SOLWEIG; i++) out->SOLWEIG[i] = NAN_;
    }

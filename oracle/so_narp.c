@@ -362,6 +362,9 @@ void so_NARP_cal_SunPosition(double year, double idectime, double UTC, double lo
    double num, den, argument, eq_par, u, x, y, ra_par, corr_elev, refr, app_elev;
    int month, day, hour, min, seas, dayofyear, year_int;
 
+   /* steps 1-10 (narp.f95:460-548) depend on the time and the time zone only: the minimal algorithm forms them once per
+    * timestep for all the cells of a time zone, so the hoisted count leaves them out of the per-cell figure */
+   SO_CNT_ONCE_BEGIN(1);
    so_dectime_to_timevec(idectime, &hour, &min, &sec);
    dayofyear = (int)floor(idectime);
    year_int = (int)year;
@@ -401,6 +404,7 @@ void so_NARP_cal_SunPosition(double year, double idectime, double UTC, double lo
               (cos(sg_lat * pi / F(180.0)) * sin(corr_obl * pi / 180) * sin(app_sun_lon * pi / F(180.0)));
    sun_dec = asin(argument) * F(180.0) / pi;
 
+   SO_CNT_END;
    /* observer_local_hour_calculation narp.f95:1086-1100 */
    obs_hour = app_stime + locationlongitude - sun_ra;
    obs_hour = set_to_range(obs_hour);

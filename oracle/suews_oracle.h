@@ -28,6 +28,24 @@ extern "C" {
 
 #define F(c) ((double)(c##f)) /* REAL(4) literal widened to REAL(8) */
 
+/* Op counter ("the oracle carries an op counter").  `make count` builds libsuews_oracle_count.so from these
+ * same sources as C++ with `double` replaced by a counting type (so_count.h): every FP64 add / multiply / divide / sqrt
+ * and every libm call the restated algorithm executes is counted, none of the arithmetic changes.  The regions below
+ * only steer where the counts go; in the normal C build they are empty. */
+#ifdef SO_OPCOUNT
+extern int so_opcount_on, so_opcount_hoisted;
+extern unsigned long long *so_opcount_cur, so_opcount_main[16], so_opcount_diag[16];
+#define SO_CNT_ONCE_BEGIN(cond) { int oc_save_ = so_opcount_on; if (so_opcount_hoisted && (cond)) so_opcount_on = 0
+#define SO_CNT_END so_opcount_on = oc_save_; }
+#define SO_CNT_DIAG_BEGIN() (so_opcount_cur = so_opcount_diag)
+#define SO_CNT_DIAG_END() (so_opcount_cur = so_opcount_main)
+#else
+#define SO_CNT_ONCE_BEGIN(cond) {
+#define SO_CNT_END }
+#define SO_CNT_DIAG_BEGIN() ((void)0)
+#define SO_CNT_DIAG_END() ((void)0)
+#endif
+
 enum { NSURF = 7, NVEG = 3 };
 /* 0-based surface indices (suews_ctrl_const.f95:188-199 are 1-based) */
 enum { PAV = 0, BLDG = 1, CONIF = 2, DECID = 3, GRASS = 4, BSOIL = 5, WATER = 6 };

@@ -189,3 +189,35 @@ def test_rsl_humidity_diagnostics_are_nan_exactly_where_the_reference_divides_ze
     assert not np.isnan(out[:, 78]).any() and not np.isnan(out[:, 80]).any()   # T2, U10 stay finite
     other = [c for c in range(82) if c not in (79, 81)]
     assert not np.isnan(out[:, other]).any()
+
+
+def test_op_counter_build_computes_the_same_numbers():
+    """oracle/libsuews_oracle_count.so (`make count`: the same sources as C++ with a counting `double`) must be
+    the same arithmetic: identical output blocks, non-zero counts, and the hoisted count below the as-written one."""
+    import ctypes as C
+    import os
+    import subprocess
+    d = fx.state_init(2005)
+    met = fx.forcing(2005)[:48]
+    plain = ol.Cell(d).run(met, want=("SUEWS", "RSL"))
+    subprocess.check_call(["make", "-C", ol.ORACLE_DIR, "-s", "count"])
+    keep = (ol.LIB_PATH, ol._lib)
+    try:
+        ol.LIB_PATH = os.path.join(ol.ORACLE_DIR, "libsuews_oracle_count.so")
+        ol._lib = None
+        L = ol.lib()
+        L.so_opcount_start.argtypes = [C.c_int]
+        L.so_opcount_stop.argtypes = [C.POINTER(C.c_ulonglong)]
+        counts = {}
+        for mode in (1, 0):
+            buf = (C.c_ulonglong * 32)()
+            L.so_opcount_start(mode)
+            got = ol.Cell(d).run(met, want=("SUEWS", "RSL"))
+            L.so_opcount_stop(buf)
+            counts[mode] = np.array(list(buf), dtype=float)
+            for k in plain:
+                assert np.array_equal(plain[k], got[k], equal_nan=True), k
+        assert counts[1][:4].sum() > 0 and counts[0][:4].sum() > counts[1][:4].sum()      # add/mul/div/sqrt of the flux path
+        assert np.array_equal(counts[0][16:], counts[1][16:])                             # diagnostics are counted alike
+    finally:
+        ol.LIB_PATH, ol._lib = keep

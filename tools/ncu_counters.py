@@ -57,6 +57,9 @@ res = {
 }
 for k, v in res.items():
     print(k, "=", v)
+if "--json" in sys.argv:   # one capture's counters to a file of its own (tools/run_captures.sh keeps these, not the reports)
+    with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+        json.dump(res, f, indent=1)
 if "--write" in sys.argv:
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     with open(os.path.join(root, "profiles", "kernel_counters.json"), "w") as f:
