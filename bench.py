@@ -180,6 +180,12 @@ def main():
     ap.add_argument("--scheme-steps", type=int, default=4,
                     help="timed days (spread over the year) of each extra scheme set in the `schemes` object; 0 = skip it")
     ap.add_argument("--schemes", default="baserun,snow,estm,netrad13", help="scheme sets of the `schemes` object (configs[3])")
+    ap.add_argument("--total-cells", type=int, default=0,
+                    help="strong scaling (BASELINE configs[4]): this many cells in total, split in contiguous blocks over the GPUs; "
+                         "use with --consecutive-days 0 --steps 30 for the 16.8 M cells x 30 days case")
+    ap.add_argument("--single-process", type=int, default=0,
+                    help="drive this many GPUs from ONE process through the library's multi-device handle (suews_b200_multi_*) "
+                         "instead of one process per GPU; the end-to-end region then includes the final gather to the first device")
     ap.add_argument("--sums", default="parity7", choices=["parity7", "all82", "hourly"],
                     help="on-device output reduction: P0 = running sums of the 7 parity fluxes (SURVEY 8d), of all 82 columns, "
                          "or P1 = the hourly-aggregated 87-column SUEWS block of every cell (SUEWS_Output_Agg in the kernel)")
@@ -188,14 +194,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    ngpu = a.single_process if a.single_process > 0 else world     # GPUs the job runs on
+    if a.total_cells > 0:       # strong scaling: contiguous blocks of the global cell index
+        per = a.total_cells // ngpu
+        a.cells_per_gpu = per + (1 if rank < a.total_cells % ngpu else 0)
+        cell0_rank = rank * per + min(rank, a.total_cells % ngpu)
+    else:
+        cell0_rank = rank * a.cells_per_gpu
     if a.consecutive_days >= 0:
         days_warm = [(a.consecutive_days + i) % 366 for i in range(W)]
         days_timed = [(a.consecutive_days + W + i) % 366 for i in range(K)]
     else:
         days_warm, days_timed = year_days(K, W)
-    workload = ("synthetic %d cells/GPU x 1 year (2004) of 5-min forcing sampled as %d one-day launches of 288 steps (days-of-year %s; "
+    workload = ("synthetic %s x 1 year (2004) of 5-min forcing sampled as %d one-day launches of 288 steps (days-of-year %s; "
                 "warm-up days %s), %s scheme set (%s), shared forcing + per-cell dT/dRH") % (
-        a.cells_per_gpu, K, ",".join(str(d + 1) for d in days_timed), ",".join(str(d + 1) for d in days_warm), a.scheme,
+        ("%d cells in total over %d GPUs" % (a.total_cells, ngpu)) if a.total_cells > 0 else ("%d cells/GPU" % a.cells_per_gpu),
+        K, ",".join(str(d + 1) for d in days_timed), ",".join(str(d + 1) for d in days_warm), a.scheme,
         "see suews_b200/synth.py SCHEMES")
 
     if a.impl == "reference":
@@ -243,9 +257,14 @@ def main():
     workload = workload.replace("see suews_b200/synth.py SCHEMES", "snowUse %d, NetRadiationMethod %d, StorageHeatMethod %d, StabilityMethod %d, EmissionsMethod %d" % (
         sch["snowuse"], sch["netradiationmethod"], sch["storageheatmethod"], sch["stabilitymethod"], sch["emissionsmethod"]))
     ncell = a.cells_per_gpu
-    b = SuewsBatch(ncell, 1, device=local_rank)
+    if a.single_process > 0:     # one process, several GPUs: the library's own partition + final gather
+        from suews_b200 import SuewsMultiBatch
+        ncell = a.total_cells if a.total_cells > 0 else a.cells_per_gpu * ngpu
+        b = SuewsMultiBatch(ncell, 1, devices=list(range(ngpu)))
+    else:
+        b = SuewsBatch(ncell, 1, device=local_rank)
     ts5 = synth.estm_ts_forcing(met) if use_estm else None   # synthetic Ts forcing = air temperature
-    synth.build_batch(b, base, cell0=rank * ncell, scheme=a.scheme, ts_row0=ts5[0] if use_estm else None)
+    synth.build_batch(b, base, cell0=cell0_rank, scheme=a.scheme, ts_row0=ts5[0] if use_estm else None)
     b.upload()
 
     def barrier():
@@ -281,7 +300,8 @@ def main():
         t = torch.tensor([dev_s, wall], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, wall = float(t[0]), float(t[1])
-    total_cs = float(world) * ncell * 288 * K
+    cells_job = float(a.total_cells) if a.total_cells > 0 else (float(ncell) if a.single_process > 0 else float(world) * ncell)
+    total_cs = cells_job * 288 * K
     value = total_cs / dev_s
 
     _f0, _w0, iters_after = b.diag()
@@ -304,7 +324,7 @@ def main():
             t = torch.tensor([fo_s], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             fo_s = float(t[0])
-        all_stages = {"value": float(world) * ncell * 288 * len(sub) / fo_s, "unit": UNIT,
+        all_stages = {"value": cells_job * 288 * len(sub) / fo_s, "unit": UNIT,
                       "note": "SUEWS_OUT_ALL_STAGES: every stage of SUEWS_cal_Main, including the RSL diagnostics T2/q2/U10/RH2 that the seven "
                               "flux sums of policy P0 cannot observe; identical sums and state; days-of-year %s re-run from the advanced "
                               "state; NOT the headline value" % ",".join(str(d + 1) for d in sub)}
@@ -334,7 +354,7 @@ def main():
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
-    e2e_val = float(world) * ncell * 288 * Ke / e2e_s
+    e2e_val = cells_job * 288 * Ke / e2e_s
     checksum = float(np.sum(res[:, 0]))
     nonfinite_cells = int((~np.isfinite(res).all(axis=1)).sum())
     fatal, warn, iters = b.diag()
@@ -342,7 +362,7 @@ def main():
 
     # ---------------- BASELINE configs[3]: the other scheme sets on the same cells, days spread over the year (N = 1 only)
     schemes = None
-    if world == 1 and a.scheme_steps > 0 and a.sums == "parity7":
+    if ngpu == 1 and a.scheme_steps > 0 and a.sums == "parity7":
         schemes = {}
         _w, sdays = year_days(a.scheme_steps, 0)
         sdays = [min(365, d + 9) for d in sdays]   # (days 10, 101, 192, 284 for 4 steps: mid-winter to autumn)
@@ -365,9 +385,10 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     # algorithmic bytes per launch: state read+write, cell params read, sums read+write, per cell; forcing shared
-    bytes_per_launch = ncell * 8.0 * (2 * N_STATE + N_CELL + 2 * n_sum) + 288 * 160.0
+    ncell_gpu = ncell // ngpu if a.single_process > 0 else ncell      # cells of one device = of one kernel launch
+    bytes_per_launch = ncell_gpu * 8.0 * (2 * N_STATE + N_CELL + 2 * n_sum) + 288 * 160.0
     if a.sums == "hourly":   # P1: no sums in/out; 24 aggregated rows x 87 columns written per cell
-        bytes_per_launch = ncell * 8.0 * (2 * N_STATE + N_CELL + 24 * 87) + 288 * 160.0
+        bytes_per_launch = ncell_gpu * 8.0 * (2 * N_STATE + N_CELL + 24 * 87) + 288 * 160.0
     launch_s = dev_s / K
     ach_gbs = bytes_per_launch / launch_s / 1e9
     prof = {}
@@ -384,7 +405,7 @@ def main():
     fp64 = {"peak_tflops_measured_dfma": fp64_peak, "flops_per_cell_step_executed": prof.get("fp64_flops_per_cell_step"),
             "source": prof.get("source")}
     if fp64_peak and prof.get("fp64_flops_per_cell_step"):
-        fp64["achieved_tflops"] = prof["fp64_flops_per_cell_step"] * ncell * 288 / launch_s / 1e12
+        fp64["achieved_tflops"] = prof["fp64_flops_per_cell_step"] * ncell_gpu * 288 / launch_s / 1e12
         fp64["frac"] = fp64["achieved_tflops"] / fp64_peak
     # the bound that matters: ALGORITHMIC flops of the hoisted minimal algorithm, counted by the oracle's op
     # counter with the published libm weights (tools/oracle_opcount.py -> profiles/oracle_opcount_<scheme>.json), x the
@@ -393,7 +414,7 @@ def main():
     try:
         oc = json.load(open(os.path.join(ROOT, "profiles", "oracle_opcount_%s.json" % a.scheme)))
         falg = float(oc["hoisted"]["weighted_flops_per_cell_step"])
-        ach = falg * value / float(world) / 1e12
+        ach = falg * value / float(ngpu) / 1e12
         roofline_fp64 = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": (ach / fp64_peak) if fp64_peak else None, "flops_per_cell_step_algorithmic": falg,
                          "flops_per_cell_step_as_written": float(oc["literal"]["weighted_flops_per_cell_step"]),
@@ -404,21 +425,23 @@ def main():
         pass
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "strong" if a.total_cells > 0 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "cells_per_gpu": ncell, "timesteps_per_step": 288, "output_policy": {
+        "config": {"workload": workload, "cells_per_gpu": ncell_gpu, "timesteps_per_step": 288,
+                   "processes": ("one process drives %d GPUs through suews_b200_multi_* (final gather to the first device inside e2e)" % ngpu)
+                   if a.single_process > 0 else "one process per GPU", "output_policy": {
                        "parity7": "P0: per-cell running sums of the 7 parity fluxes QN,QF,QS,QH,QE,RO,SWE",
                        "all82": "P0+: per-cell running sums of all 82 SUEWS columns",
                        "hourly": "P1: hourly-aggregated 87-column SUEWS block of every cell, aggregated in the kernel"}[a.sums],
-                   "l2": "inputs (state+params %.0f MB/GPU) larger than L2" % (ncell * 8.0 * (N_STATE + N_CELL + N_SUM) / 1e6),
+                   "l2": "inputs (state+params %.0f MB/GPU) larger than L2" % (ncell_gpu * 8.0 * (N_STATE + N_CELL + N_SUM) / 1e6),
                    "tsurf_iterations_per_step": trips_per_step, "wall_s_timed": wall,
                    "checksum_QN": checksum, "fatal_cells": int((fatal != 0).sum()), "nonfinite_sum_cells": nonfinite_cells},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 288 * 160, "d2h_bytes_per_step": ncell * len(cols) * 8},
-        "gpu_launches": K,
+        "gpu_launches": K * (ngpu if a.single_process > 0 else 1),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": (prof["dram_bytes_per_cell_step"] * ncell * 288.0 if "dram_bytes_per_cell_step" in prof else None), "peak_source": peak_src,
+                     "traffic": (prof["dram_bytes_per_cell_step"] * ncell_gpu * 288.0 if "dram_bytes_per_cell_step" in prof else None), "peak_source": peak_src,
                      "note": "kernel is FP64-pipe / latency bound, not HBM bound (SURVEY 8d); see roofline_fp64"},
         "fp64": fp64,
     }
@@ -428,7 +451,7 @@ def main():
         line["all_stages"] = all_stages
     if schemes:
         line["schemes"] = schemes
-    if world == 1 and not a.no_cpu_baseline:
+    if ngpu == 1 and not a.no_cpu_baseline:
         r, cores, cells, slowest, _ = cpu_arm(a.cpu_budget, a.scheme, days=days_timed)
         line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d cells x 288 steps (one day each, cycling through the bench's days of the year) of the same synthetic cells, one process per core (%.1f s)" % (cells, slowest)}

@@ -84,6 +84,10 @@ int suews_b200_get_clock(suews_b200_handle h, int *dt_since_start, int *tstep_pr
 
 /* Push parameters + state to HBM (SoA).  Call after the setters, before advancing. */
 int suews_b200_upload(suews_b200_handle h);
+/* Sort the thread slots again on the CURRENT state (snow activity, canopy height) -- divergence control for long runs:
+ * cells of a snow-on class that carry a snow pack are grouped apart from the bare ones.  State, running
+ * sums, diagnostics, clock and the staged forcing are kept; costs one device -> host -> device round trip of the state. */
+int suews_b200_resort(suews_b200_handle h);
 
 /* Forcing shared by all cells: MetForcingBlock [nsteps x 24], column-major, columns as in
  * driver.f95:3177-3201 (pressure already in hPa).  Copies host -> device and builds the per-step

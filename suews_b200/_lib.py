@@ -43,6 +43,7 @@ def lib():
         L.suews_b200_set_clock.argtypes = [H, C.c_int, C.c_int]
         L.suews_b200_get_clock.argtypes = [H, ip, ip]
         L.suews_b200_upload.argtypes = [H]
+        L.suews_b200_resort.argtypes = [H]
         L.suews_b200_set_forcing.argtypes = [H, dp, C.c_int]
         L.suews_b200_set_estm_forcing.argtypes = [H, dp, C.c_int]
         L.suews_b200_set_forcing_orig.argtypes = [H, dp] + [C.c_int] * 6

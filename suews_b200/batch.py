@@ -128,6 +128,10 @@ class SuewsBatch:
     def upload(self):
         check(self.L.suews_b200_upload(self.h))
 
+    def resort(self):
+        """sort the thread slots again on the current state (snow activity, canopy height); the run carries on"""
+        check(self.L.suews_b200_resort(self.h))
+
     def set_forcing(self, met):
         """met: [nsteps, 24] MetForcingBlock (driver.f95:3177-3201), pressure in hPa."""
         m = np.asfortranarray(np.asarray(met, dtype=np.float64))

@@ -622,6 +622,18 @@ int suews_b200_restart(suews_b200_handle h)
    h->uploaded = false;
    return SUEWS_OK;
 }
+// Re-sort the thread slots on the current state (the dynamic keys of upload(): snow activity, canopy height through the
+// deciduous porosity).  The device state comes back to the host mirror, the slots are sorted again and everything is
+// uploaded in the new order; running sums, diagnostics, the clock and the staged forcing carry on.  Worth calling every few
+// weeks of simulated time in snow-on runs (melt and first snow change which cells are active).
+int suews_b200_resort(suews_b200_handle h)
+{
+   if (!h || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "resort: nothing uploaded");
+   h->dev_dirty = true;   // the device holds the current copy (also right after an upload: harmless round trip)
+   int rc = pull_live(h);
+   if (rc != SUEWS_OK) return rc;
+   return suews_b200_upload(h);
+}
 // tstep_prev of SUEWS_cal_Main: rolls = 1 (default) lets the library's own clock set it to tstep after the first step of
 // a run; rolls = 0 keeps the value of set_clock for every step, as SUEWS_cal_multitsteps does with its INTENT(IN) argument
 int suews_b200_set_tstep_prev_rolls(suews_b200_handle h, int rolls)
@@ -696,7 +708,7 @@ int suews_b200_upload(suews_b200_handle h)
    }
    {
       const FieldDesc *fs = find_field("sfr"), *fb = find_field("bldgH"), *fe = find_field("EveTreeH"),
-                      *fd = find_field("DecTreeH"), *fp = find_field("porosity_id");
+                      *fd = find_field("DecTreeH"), *fp = find_field("porosity_id"), *fsp = find_field("SnowPack");
       const size_t sd = (size_t)h->stride;
       std::vector<double> key((size_t)h->ncell);
       for (int c = 0; c < h->ncell; c++) {
@@ -705,7 +717,17 @@ int suews_b200_upload(suews_b200_handle h)
          double zh = (a != 0) ? (h->cellp[fb->off * sd + c] * s1 + h->cellp[fe->off * sd + c] * s2 +
                                  h->cellp[fd->off * sd + c] * (1 - h->state[fp->off * sd + c]) * s3) / a : 0.0;
          const int k = h->cls_of_cell[(size_t)c];
-         key[(size_t)c] = ((double)bucket_of_class[(size_t)k] * 1e6 + (double)k) * 1e6 + zh;
+         // snow activity (SUM(SnowPack) > 0): in a snow-on class the cells that carry a pack run the snow branch
+         // of SUEWS_cal_QE and the melt-heat routine's inner arms, the bare ones do not; it moves with the seasons, so it
+         // is a sort key of the current state -- suews_b200_resort() re-applies it between launches
+         double active = 0;
+         if (h->classes[(size_t)k].snowUse == 1) {
+            double sp = 0;
+            for (int is = 0; is < SUEWS_NSURF; is++) sp += h->state[(fsp->off + is) * sd + c];
+            active = (sp > 0) ? 1.0 : 0.0;
+         }
+         // canopy heights are below 1e3 m: the activity flag sits above them, below the class number
+         key[(size_t)c] = (((double)bucket_of_class[(size_t)k] * 1e6 + (double)k) * 2 + active) * 1e4 + std::min(zh, 9999.0);
          order[(size_t)c] = c;
       }
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[(size_t)x] < key[(size_t)y]; });

@@ -79,19 +79,35 @@ class _SuewsDriver:
             raise SuewsError(rc, msg)
         return tuple(results)
 
-    def suews_cal_multitsteps(self, **kw):
+    def _positional(self, which, args, kw, optional=()):
+        """f2py call convention: positional arguments are the Fortran dummy arguments in declaration order without the
+        INTENT(OUT) ones (driver.f95:45-91 / :2814-2860); arguments f2py makes optional move behind them."""
+        if not args:
+            return kw
+        names = [nm.lower() for nm, _i, intent, _n, _r in arg_table(which) if intent != 2 and nm.lower() not in optional]
+        names += list(optional)
+        if len(args) > len(names):
+            raise TypeError("takes at most %d positional arguments (%d given)" % (len(names), len(args)))
+        out = dict(kw)
+        for nm, v in zip(names, args):
+            if nm in {k.lower() for k in kw}:
+                raise TypeError("got multiple values for argument '%s'" % nm)
+            out[nm] = v
+        return out
+
+    def suews_cal_multitsteps(self, *args, **kw):
         """SUEWS_cal_multitsteps (driver.f95:2814): returns (dataoutblocksuews, dataoutblocksnow, dataoutblockestm,
         dataoutblockrsl, dataoutblocksol, dailystateblock)."""
-        low = {k.lower(): v for k, v in kw.items()}
+        low = {k.lower(): v for k, v in self._positional(1, args, kw, optional=("len_sim",)).items()}
         met = np.asfortranarray(np.asarray(low["metforcingblock"], dtype=np.float64))
         low["metforcingblock"] = met
         low.setdefault("len_sim", met.shape[0])   # f2py makes len_sim optional (= shape(metforcingblock, 0))
         return self._call("suews_cal_multitsteps_c", 1, low, len_sim=int(low["len_sim"]))
 
-    def suews_cal_main(self, **kw):
+    def suews_cal_main(self, *args, **kw):
         """SUEWS_cal_Main (driver.f95:45): returns (datetimeline, dataoutlinesuews, dataoutlinesnow, dataoutlineestm,
-        dataoutlinersl, dataoutlinesolweig, dailystateline)."""
-        return self._call("suews_cal_main_c", 0, kw)
+        dataoutlinersl, dataoutlinesolweig, dailystateline).  Positional (f2py order) or keyword arguments."""
+        return self._call("suews_cal_main_c", 0, self._positional(0, args, kw))
 
     def output_size(self):
         """output_size (driver.f95:2802): SIZE(varListAll) = 500."""
@@ -178,3 +194,43 @@ class _SuewsDriver:
 
 
 suews_driver = _SuewsDriver()
+
+
+class _FortranModule:
+    """Stands where f2py puts a Fortran MODULE of the reference (supy_driver/__init__.py:13-27 re-exports twelve of them
+    beside suews_driver).  supy itself calls only suews_driver; the stage routines of these modules run inside the kernel
+    and have no host entry point of their own -- asking for one says so instead of silently computing on the CPU."""
+
+    def __init__(self, name, source, routines=None):
+        self.__name__ = name
+        self._source = source
+        self._routines = dict(routines or {})
+
+    def __getattr__(self, item):
+        r = self.__dict__.get("_routines", {})
+        if item.lower() in r:
+            return r[item.lower()]
+        raise NotImplementedError(
+            "%s.%s: the routines of %s run inside the CUDA timestep kernel (libsuews_b200.so); only suews_driver's entry "
+            "points are callable from the host%s" % (self.__name__, item, self._source,
+                                                     (" and %s" % ", ".join(sorted(r))) if r else ""))
+
+    def __dir__(self):
+        return sorted(self._routines)
+
+
+# NARP_cal_SunPosition (narp.f95:460) is the one stage routine with its own C entry point
+narp_module = _FortranModule("narp_module", "suews_phys_narp.f95",
+                             {"narp_cal_sunposition": suews_driver.suews_cal_sunposition})
+atmmoiststab_module = _FortranModule("atmmoiststab_module", "suews_phys_atmmoiststab.f95")
+resist_module = _FortranModule("resist_module", "suews_phys_resist.f95")
+evap_module = _FortranModule("evap_module", "suews_phys_evap.f95")
+snow_module = _FortranModule("snow_module", "suews_phys_snow.f95")
+dailystate_module = _FortranModule("dailystate_module", "suews_phys_dailystate.f95")
+lumps_module = _FortranModule("lumps_module", "suews_phys_lumps.f95")
+anemsn_module = _FortranModule("anemsn_module", "suews_phys_anemsn.f95")
+rsl_module = _FortranModule("rsl_module", "suews_phys_rslprof.f95")
+co2_module = _FortranModule("co2_module", "suews_phys_biogenco2.f95")
+waterdist_module = _FortranModule("waterdist_module", "suews_phys_waterdist.f95")
+meteo = _FortranModule("meteo", "suews_util_meteo.f95")
+__version__ = "2020b8+b200"

@@ -930,3 +930,41 @@ def test_ten_thousand_perturbed_cells_match_per_cell_oracle(scheme):
     print("   cells beyond 1e-9: %d of %d (worst %.2e)" % (flipped, n, per_cell.max()))
     assert per_cell.max() <= TOL_SUM
     assert flipped <= n // 1000
+
+
+@pytest.mark.gpu
+def test_resort_between_launches_changes_nothing():
+    """suews_b200_resort: the thread slots are sorted again on the current state (snow activity, canopy height) in the
+    middle of a run; sums, state, diagnostics and the clock must be those of the uninterrupted run, bit for bit."""
+    from suews_b200 import OUT_SUM7, SuewsBatch, synth
+    base = fx.state_init(2004)             # winter start: snow on the ground, melting unevenly over the perturbed cells
+    met = fx.forcing(2004)[:3 * 288]
+    n = 3000
+    runs = []
+    for resort in (False, True):
+        b = SuewsBatch(n, 1)
+        synth.build_batch(b, base, scheme="baserun")
+        # half of the cells start bare: the snow-activity key has something to separate
+        b.upload()
+        bare = np.arange(n) % 2 == 1
+        for nm in ("SnowPack", "SnowFrac", "SnowWater"):
+            v = np.tile(np.asarray(base[nm.lower()], dtype=float), (n, 1))
+            v[bare] = 0.0
+            b.set_state(nm, v)
+        b.upload()
+        b.set_forcing(met)
+        b.advance(0, 288, OUT_SUM7)
+        if resort:
+            b.resort()
+        b.advance(288, 288, OUT_SUM7)
+        if resort:
+            b.resort()
+        b.advance(576, 288, OUT_SUM7)
+        runs.append((b.sums_cols(list(PARITY_COLS.values())), {nm: b.get_state(nm) for nm in ("SnowPack", "state_id", "soilstore_id", "HDD_id", "SnowDens")},
+                     b.diag(), b.get_clock()))
+        b.close()
+    assert np.array_equal(runs[0][0], runs[1][0])
+    for nm in runs[0][1]:
+        assert np.array_equal(runs[0][1][nm], runs[1][1][nm]), nm
+    assert np.array_equal(runs[0][2][0], runs[1][2][0]) and np.array_equal(runs[0][2][2], runs[1][2][2])
+    assert runs[0][3] == runs[1][3]

@@ -179,3 +179,51 @@ def test_cal_multitsteps_with_estm():
     np.testing.assert_allclose(sd.estm_data_get("Twall", 5), cell.get_state("Twall"), rtol=1e-11)
     np.testing.assert_allclose(sd.estm_data_get("Tievolve", 1), cell.get_state("Tievolve"), rtol=1e-11)
     sd.reset_hidden_state()
+
+
+def test_positional_call_in_f2py_order_equals_keyword_call():
+    """f2py lets the reference's suews_cal_multitsteps be called positionally, the Fortran dummies in declaration order
+    without the INTENT(OUT) ones and the optional len_sim behind them (driver.f95:2814-2860); supy_driver here too."""
+    from suews_b200.supy_driver import arg_table, suews_driver as sd
+    d = fx.state_init(2005)
+    met = np.asfortranarray(fx.forcing(2005)[:24])
+    outs = []
+    for positional in (False, True):
+        sd.reset_hidden_state()
+        kw = _kwargs(d, 1)
+        kw["metforcingblock"] = met
+        if positional:
+            names = [nm.lower() for nm, _i, intent, _n, _r in arg_table(1) if intent != 2 and nm.lower() != "len_sim"]
+            args = []
+            for nm in names:
+                if nm not in kw:
+                    break               # trailing assumed-shape arguments the path never reads
+                args.append(kw.pop(nm))
+            outs.append(sd.suews_cal_multitsteps(*args, **kw))
+        else:
+            outs.append(sd.suews_cal_multitsteps(**kw))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_dropin_package_serves_the_reference_import():
+    """`import supy_driver as sd; sd.suews_driver.output_name_n(3)` -- the reference's own package test
+    (supy-driver/supy_driver/test/test-supy_driver.py:12) -- against the drop-in package."""
+    import importlib
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(fx.GOLDEN), "..", "suews_b200", "dropin")
+    sys.path.insert(0, os.path.abspath(here))
+    try:
+        sd = importlib.import_module("supy_driver")
+        s = sd.suews_driver.output_name_n(3)[0]
+        assert isinstance(s, bytes) and len(s) == 15
+        assert sd.__version__.startswith("2020b")
+        for nm in ("narp_module", "atmmoiststab_module", "resist_module", "evap_module", "snow_module", "dailystate_module",
+                   "lumps_module", "anemsn_module", "rsl_module", "co2_module", "waterdist_module", "meteo"):
+            assert hasattr(sd, nm)
+        az, zen = sd.narp_module.narp_cal_sunposition(2005.0, 1.5, 2.0, 57.77, 11.87, 10.0)
+        assert 0 <= az <= 360 and 0 <= zen <= 180
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("supy_driver", None)

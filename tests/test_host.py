@@ -250,3 +250,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_dropin_supy_driver_package_exports_the_reference_names():
+    """suews_b200/dropin/supy_driver re-exports what supy-driver/supy_driver/__init__.py:13-27 exports (no compute here)"""
+    import importlib
+    here = os.path.join(ROOT, "suews_b200", "dropin")
+    sys.path.insert(0, here)
+    try:
+        sd = importlib.import_module("supy_driver")
+        names = ["suews_driver", "narp_module", "atmmoiststab_module", "resist_module", "evap_module", "snow_module",
+                 "dailystate_module", "lumps_module", "anemsn_module", "rsl_module", "co2_module", "waterdist_module", "meteo"]
+        for nm in names:
+            assert hasattr(sd, nm), nm
+        assert sd.__version__.startswith("2020b")
+        for f in ("suews_cal_main", "suews_cal_multitsteps", "output_name_n", "output_size", "suews_cal_sunposition", "set_nan",
+                  "square", "square_real", "cal_tair_av", "cal_tsfc"):
+            assert callable(getattr(sd.suews_driver, f)), f
+        with pytest.raises(NotImplementedError):
+            sd.meteo.sat_vap_press_x
+        # positional arguments map onto the reference's declaration order without the INTENT(OUT) ones
+        from suews_b200.supy_driver import arg_table
+        kw = sd.suews_driver._positional(1, (1, 2, 3), {})
+        first3 = [nm.lower() for nm, _i, intent, _n, _r in arg_table(1) if intent != 2][:3]
+        assert list(kw) == first3
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("supy_driver", None)
