@@ -331,6 +331,7 @@ def main():
 
     # ---------------- end-to-end through the host API (host buffers in, host results out)
     e2e_t0 = None
+    gather_ms = []
     cols = PARITY_COLS
     Ke = a.e2e_steps if a.e2e_steps > 0 else K
     e2e_days = days_warm + [days_timed[i % max(K, 1)] for i in range(Ke)]   # the same days again, forcing from the host
@@ -346,7 +347,11 @@ def main():
         if a.sums == "hourly":                  # device -> host: the last hour's QN..QE maps of all cells
             res = np.stack([b.agg_column(23, 5 + c) for c in cols], axis=1)
         else:
-            res = b.sums_cols(cols)             # device -> host (pinned staging), waits for the kernel
+            if a.single_process > 0:            # the final gather: device -> first device (peer copies) -> host
+                res, gms = b.gather_sums(cols)
+                gather_ms.append(gms)
+            else:
+                res = b.sums_cols(cols)         # device -> host (pinned staging), waits for the kernel
     barrier()
     e2e_s = time.perf_counter() - e2e_t0
     if dist is not None:
@@ -447,6 +452,8 @@ def main():
     }
     if roofline_fp64:
         line["roofline_fp64"] = roofline_fp64
+    if gather_ms:
+        line["e2e"]["final_gather_ms_per_step"] = float(np.mean(gather_ms[W:])) if len(gather_ms) > W else float(np.mean(gather_ms))
     if all_stages:
         line["all_stages"] = all_stages
     if schemes:

@@ -215,6 +215,128 @@ MODULE suews_b200
          REAL(C_DOUBLE), INTENT(OUT) :: block(*)
       END FUNCTION
 
+      ! sort the thread slots again on the current state (snow activity, canopy height); the run carries on
+      INTEGER(C_INT) FUNCTION suews_b200_resort(h) BIND(C, name='suews_b200_resort')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: h
+      END FUNCTION
+
+      ! ---- several GPUs of one box behind one handle: contiguous blocks of grids, one per device, one host thread.
+      !    ierr = suews_b200_multi_create(NumberOfGrids, 1_C_INT, ndev, devices, m)          ! devices(ndev) = 0, 1, ...
+      !    ierr = suews_b200_multi_set_cell_param(m, 'sfr'//C_NULL_CHAR, sfr_all, 7_C_INT)   ! arrays of the WHOLE run
+      !    ierr = suews_b200_multi_upload(m); ierr = suews_b200_multi_set_forcing(m, met, irMax)
+      !    ierr = suews_b200_multi_advance(m, 0_C_INT, irMax, SUEWS_OUT_SUM7); ierr = suews_b200_multi_sync(m)
+      !    ierr = suews_b200_multi_gather_sums(m, cols, 7_C_INT, sums, ms)                   ! sums(7, NumberOfGrids)
+      INTEGER(C_INT) FUNCTION suews_b200_multi_create(ncell, nclass, ndev, devices, m) BIND(C, name='suews_b200_multi_create')
+         IMPORT :: C_INT, C_PTR
+         INTEGER(C_INT), VALUE :: ncell, nclass, ndev
+         INTEGER(C_INT), INTENT(IN) :: devices(*)
+         TYPE(C_PTR), INTENT(OUT) :: m
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_destroy(m) BIND(C, name='suews_b200_multi_destroy')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_ndev(m, ndev) BIND(C, name='suews_b200_multi_ndev')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+         INTEGER(C_INT), INTENT(OUT) :: ndev
+      END FUNCTION
+
+      ! block d (0-based) of the partition: its single-device handle, first grid (0-based) and grid count
+      INTEGER(C_INT) FUNCTION suews_b200_multi_part(m, d, h, cell0, ncell) BIND(C, name='suews_b200_multi_part')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+         INTEGER(C_INT), VALUE :: d
+         TYPE(C_PTR), INTENT(OUT) :: h
+         INTEGER(C_INT), INTENT(OUT) :: cell0, ncell
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_class_param(m, cls, name, vals, n) BIND(C, name='suews_b200_multi_set_class_param')
+         IMPORT :: C_INT, C_PTR, C_CHAR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         INTEGER(C_INT), VALUE :: cls, n
+         CHARACTER(KIND=C_CHAR), INTENT(IN) :: name(*)
+         REAL(C_DOUBLE), INTENT(IN) :: vals(*)
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_cell_param(m, name, vals, n) BIND(C, name='suews_b200_multi_set_cell_param')
+         IMPORT :: C_INT, C_PTR, C_CHAR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         CHARACTER(KIND=C_CHAR), INTENT(IN) :: name(*)
+         REAL(C_DOUBLE), INTENT(IN) :: vals(*)
+         INTEGER(C_INT), VALUE :: n
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_cell_class(m, class_of_cell) BIND(C, name='suews_b200_multi_set_cell_class')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+         INTEGER(C_INT), INTENT(IN) :: class_of_cell(*)
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_state(m, name, vals, n) BIND(C, name='suews_b200_multi_set_state')
+         IMPORT :: C_INT, C_PTR, C_CHAR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         CHARACTER(KIND=C_CHAR), INTENT(IN) :: name(*)
+         REAL(C_DOUBLE), INTENT(IN) :: vals(*)
+         INTEGER(C_INT), VALUE :: n
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_get_state(m, name, vals, n) BIND(C, name='suews_b200_multi_get_state')
+         IMPORT :: C_INT, C_PTR, C_CHAR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         CHARACTER(KIND=C_CHAR), INTENT(IN) :: name(*)
+         REAL(C_DOUBLE), INTENT(OUT) :: vals(*)
+         INTEGER(C_INT), VALUE :: n
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_clock(m, dt_since_start, tstep_prev) BIND(C, name='suews_b200_multi_set_clock')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+         INTEGER(C_INT), VALUE :: dt_since_start, tstep_prev
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_upload(m) BIND(C, name='suews_b200_multi_upload')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_forcing(m, met, nsteps) BIND(C, name='suews_b200_multi_set_forcing')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_DOUBLE), INTENT(IN) :: met(*)
+         INTEGER(C_INT), VALUE :: nsteps
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_advance(m, step0, nsteps, out_flags) BIND(C, name='suews_b200_multi_advance')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+         INTEGER(C_INT), VALUE :: step0, nsteps, out_flags
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_sync(m) BIND(C, name='suews_b200_multi_sync')
+         IMPORT :: C_INT, C_PTR
+         TYPE(C_PTR), VALUE :: m
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_last_advance_ms(m, ms) BIND(C, name='suews_b200_multi_last_advance_ms')
+         IMPORT :: C_INT, C_PTR, C_FLOAT
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_FLOAT), INTENT(OUT) :: ms
+      END FUNCTION
+
+      ! the final gather: out(ncols, ncell) -- the selected columns of every grid's running sums
+      INTEGER(C_INT) FUNCTION suews_b200_multi_gather_sums(m, cols, ncols, out, gather_ms) BIND(C, name='suews_b200_multi_gather_sums')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE, C_FLOAT
+         TYPE(C_PTR), VALUE :: m
+         INTEGER(C_INT), INTENT(IN) :: cols(*)
+         INTEGER(C_INT), VALUE :: ncols
+         REAL(C_DOUBLE), INTENT(OUT) :: out(*)
+         REAL(C_FLOAT), INTENT(OUT) :: gather_ms
+      END FUNCTION
+
       ! MODULE ESTM_data for the reference-shaped calls (INTEGRATION.md, "Semantics worth knowing")
       INTEGER(C_INT) FUNCTION suews_estm_data_set(name, vals, n) BIND(C, name='suews_estm_data_set')
          IMPORT :: C_INT, C_CHAR, C_DOUBLE
