@@ -100,7 +100,9 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps);
  * DisaggregateDateTime, Disagg_Lin with DisaggMethod 1/2/3, DisaggP_amongN with RainDisaggMethod 100) to the model
  * timestep of the uploaded classes, whole-file semantics (first and last half period repeated).  The block then holds
  * nrows * resolution_in_s / tstep rows, bit-identical to the reference's in-memory MetForcingData;
- * suews_b200_get_forcing_block reads it back ([nsteps x 24], column-major). */
+ * suews_b200_get_forcing_block reads it back ([nsteps x 24], column-major).  This is RunControl's KdownZen = 0; KdownZen = 1
+ * (K-down zeroed below each grid's own horizon and rescaled per day, :1568-1600) turns the shared series into one series
+ * per grid and is not built -- there is no switch for it, so it cannot be selected by accident. */
 int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int nrows, int resolution_in_s, int disagg_method,
                                 int rain_disagg_method, int raw_units, int smd_method);
 int suews_b200_get_forcing_block(suews_b200_handle h, double *met_fast, int nsteps);

@@ -140,10 +140,12 @@ class SuewsBatch:
         self.nsteps = m.shape[0]
 
     def set_forcing_orig(self, met_orig, resolution_in=3600, disagg_method=1, rain_disagg_method=100, raw_units=False,
-                         smd_method=0):
+                         smd_method=0, kdown_zen=0):
         """Forcing at file resolution, disaggregated to the model timestep on the device (DisaggregateMet,
         suews_ctrl_input.f95:1380-1640).  met_orig: [nrows, 24]; raw_units: the file's own units (pressure in kPa),
         i.e. a block that has not been through forcing.read_met.  Returns the number of model timesteps."""
+        if int(kdown_zen) != 0:   # per-grid forcing (sun below each grid's own horizon): not built, never silently ignored
+            raise NotImplementedError("KdownZen = 1 (suews_ctrl_input.f95:1568-1600) is not built: the device disaggregation implements KdownZen = 0")
         m = np.asfortranarray(np.asarray(met_orig, dtype=np.float64))
         assert m.shape[1] == 24
         check(self.L.suews_b200_set_forcing_orig(self.h, m.ctypes.data_as(dp), m.shape[0], int(resolution_in), int(disagg_method),

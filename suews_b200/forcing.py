@@ -154,8 +154,16 @@ def disaggregate_estm(ts_orig, tstep=300, resolution_in=3600, disagg_method=1):
 
 
 def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, rain_disagg_method=100,
-                     first_block=True, last_block=True, prev_row=None, next_row=None):
-    """Disaggregate an original-resolution met block (already passed through ``read_met``)."""
+                     first_block=True, last_block=True, prev_row=None, next_row=None, kdown_zen=0):
+    """Disaggregate an original-resolution met block (already passed through ``read_met``).
+
+    kdown_zen: RunControl's KdownZen.  1 = zero the disaggregated K-down while the sun is below the cell's horizon and
+    rescale each day to the original daily sum (suews_ctrl_input.f95:1568-1600): that makes the forcing a per-grid series
+    (it depends on each grid's latitude / longitude), which the shared-forcing layout of this library does not hold --
+    not built; asking for it raises instead of returning the KdownZen = 0 series."""
+    if int(kdown_zen) != 0:
+        raise NotImplementedError("KdownZen = 1 (zenith re-weighting of K-down, suews_ctrl_input.f95:1568-1600) is not built: "
+                                  "the disaggregation implements KdownZen = 0")
     met_orig = np.asarray(met_orig, dtype=np.float64)
     nper = resolution_in // tstep
     n = met_orig.shape[0]

@@ -277,3 +277,13 @@ def test_dropin_supy_driver_package_exports_the_reference_names():
     finally:
         sys.path.pop(0)
         sys.modules.pop("supy_driver", None)
+
+
+def test_kdown_zen_is_refused_not_ignored():
+    """KdownZen = 1 (suews_ctrl_input.f95:1568-1600) is not built: asking for it raises instead of silently returning the
+    KdownZen = 0 forcing"""
+    from suews_b200.forcing import disaggregate_met
+    met = np.zeros((24, 24))
+    met[:, 0] = 2004; met[:, 1] = 1; met[:, 2] = np.arange(24)
+    with pytest.raises(NotImplementedError):
+        disaggregate_met(met, kdown_zen=1)
