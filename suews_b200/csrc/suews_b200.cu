@@ -342,6 +342,8 @@ struct suews_b200_handle_s {
    cudaStream_t stream = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    int first_fatal_code = 0, first_fatal_cell = -1;
+   double *d_pack = nullptr;   // compact cell-ordered block of selected sums columns (get_sums_cols)
+   size_t pack_cap = 0;
    void *pinned = nullptr;   // pinned host staging (forcing records in, selected sums out)
    size_t pinned_bytes = 0;
    void *pinned_in = nullptr;
@@ -487,7 +489,7 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
    for (int i = 0; i < 6; i++) cudaFree(h->d_blk[i]);
-   cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg); cudaFree(h->d_agg_daily);
+   cudaFree(h->d_pack); cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg); cudaFree(h->d_agg_daily);
 }
 
 int suews_b200_destroy(suews_b200_handle h)
@@ -1215,28 +1217,47 @@ int suews_b200_get_sums(suews_b200_handle h, double *sums)
    return SUEWS_OK;
 }
 
-// Selected columns of the running sums, [ncell][ncols] cell-major, through a pinned staging buffer.
+// Selected columns of the running sums, [ncell][ncols] cell-major.  The slot -> cell permutation is done on the device
+// (suews_pack_sums_kernel: contiguous reads, scattered writes into a compact cell-ordered block), one copy brings the block
+// to pinned host memory, and the host only transposes [ncols][ncell] -> [ncell][ncols] with sequential reads -- the
+// per-cell gather through slot_of_cell on the host was a third of the end-to-end overhead of a bench step.
 int suews_b200_get_sums_cols(suews_b200_handle h, const int *cols, int ncols, double *out)
 {
-   if (!h || !h->uploaded || !cols || !out || ncols <= 0) return set_err(SUEWS_E_BAD_ARG, "get_sums_cols: bad arguments");
+   if (!h || !h->uploaded || !cols || !out || ncols <= 0 || ncols > 16) return set_err(SUEWS_E_BAD_ARG, "get_sums_cols: 1..16 columns");
    CUDA_OK(cudaSetDevice(h->device));
-   size_t need = sizeof(double) * (size_t)ncols * (size_t)h->stride;
+   SuPackCols pc;
+   pc.ncols = ncols;
+   for (int k = 0; k < ncols; k++) {
+      if (cols[k] < 0 || cols[k] >= SUEWS_NCOL_SUEWS) return set_err(SUEWS_E_BAD_ARG, "get_sums_cols: column %d", cols[k]);
+      pc.col[k] = cols[k];
+   }
+   const size_t n = (size_t)h->ncell, total = (size_t)ncols * n;
+   const size_t need = sizeof(double) * total;
    if (h->pinned_bytes < need) {
       if (h->pinned) cudaFreeHost(h->pinned);
       h->pinned = nullptr;
+      h->pinned_bytes = 0;
       CUDA_OK(cudaHostAlloc(&h->pinned, need, cudaHostAllocDefault));
       h->pinned_bytes = need;
    }
-   double *pin = (double *)h->pinned;
-   for (int k = 0; k < ncols; k++) {
-      if (cols[k] < 0 || cols[k] >= SUEWS_NCOL_SUEWS) return set_err(SUEWS_E_BAD_ARG, "get_sums_cols: column %d", cols[k]);
-      CUDA_OK(cudaMemcpyAsync(pin + (size_t)k * h->stride, h->d_sums + (size_t)cols[k] * h->stride,
-                              sizeof(double) * (size_t)h->ncell, cudaMemcpyDeviceToHost, h->stream));
+   if (h->pack_cap < total) {
+      if (h->d_pack) cudaFree(h->d_pack);
+      h->d_pack = nullptr;
+      h->pack_cap = 0;
+      CUDA_OK(cudaMalloc((void **)&h->d_pack, need));
+      h->pack_cap = total;
    }
+   suews_pack_sums_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_sums, h->d_order, h->stride, (int)n, pc, h->d_pack);
+   CUDA_OK(cudaGetLastError());
+   double *pin = (double *)h->pinned;
+   CUDA_OK(cudaMemcpyAsync(pin, h->d_pack, need, cudaMemcpyDeviceToHost, h->stream));
    CUDA_OK(cudaStreamSynchronize(h->stream));
-   for (int c = 0; c < h->ncell; c++) {
-      const size_t sl = (size_t)h->slot_of_cell[(size_t)c];
-      for (int k = 0; k < ncols; k++) out[(size_t)c * ncols + k] = pin[(size_t)k * h->stride + sl];
+   for (size_t c0 = 0; c0 < n; c0 += 4096) {   // blocked transpose: every source column is read sequentially
+      const size_t c1 = std::min(n, c0 + 4096);
+      for (int k = 0; k < ncols; k++) {
+         const double *src = pin + (size_t)k * n;
+         for (size_t c = c0; c < c1; c++) out[c * (size_t)ncols + k] = src[c];
+      }
    }
    return SUEWS_OK;
 }
