@@ -244,6 +244,9 @@ void so_cal_Stab(SoCtx *cx, int StabilityMethod, double zzd, double z0m, double 
       *L_MOD = ((*UStar) * (*UStar)) / (G_T_K * (*TStar));
       i = i + 1;
    }
+#ifdef SO_OPCOUNT   /* statistics of the counting build: calls, iterations, calls that ran to the cap of 330 */
+   if (so_opcount_on) { so_opcount_cur[12] += 1; so_opcount_cur[13] += (unsigned long long)(i - 1); so_opcount_cur[14] += (i >= 330); }
+#endif
    *zL = FMIN(F(5.), FMAX(F(-5.), *zL));
    *L_MOD = zzd / *zL;
    if (fabs(*L_MOD) > F(3e4)) *L_MOD = *L_MOD / fabs(*L_MOD) * F(3e4);

@@ -71,6 +71,8 @@ def main():
             "diagnostics_ops_per_cell_step": dict(zip(NAMES, [float(x) for x in diag_c])),
             "diagnostics_weighted_flops_per_cell_step": float(np.dot(diag_c, WEIGHT)),
         }
+        res[label]["cal_Stab"] = {"calls_per_cell_step": float(tot[12] / steps), "iterations_per_call": float(tot[13] / max(tot[12], 1)),
+                                  "share_of_calls_at_the_330_iteration_cap": float(tot[14] / max(tot[12], 1))}
         print("%-8s flux/state path: %8.0f weighted flops per cell-step (%s)" % (
             label, res[label]["weighted_flops_per_cell_step"], ", ".join("%s %.0f" % (n, v) for n, v in zip(NAMES, main_c))))
         print("%-8s diagnostics    : %8.0f weighted flops per cell-step (%s)" % (
