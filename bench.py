@@ -120,6 +120,7 @@ def cpu_arm(budget_s, scheme, cores=None, days=(0,)):
     import multiprocessing as mp
     import oracle_lib as ol
     ol.build()
+    ol.lib()   # mapped in this process too (the forked workers inherit it): the oracle is what this arm runs, visibly
     cores = cores or os.cpu_count() or 1
     with mp.get_context("fork").Pool(cores) as pool:
         t0 = time.perf_counter()

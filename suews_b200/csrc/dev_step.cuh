@@ -84,6 +84,7 @@ static __device__ unsigned long long su_phase_clk[16];
 #define SU_CLK_PARAM , long long &clk_, bool clkb_
 #define SU_CLK_PASS , clk_, true
 #define SU_CLK_PASS_NOBAR , clk_, false
+#define SU_CLK_PASS_INNER , clk_, clkb_
 #else
 #define SU_CLK_DECL
 #define SU_CLK(i)
@@ -92,6 +93,7 @@ static __device__ unsigned long long su_phase_clk[16];
 #define SU_CLK_PARAM
 #define SU_CLK_PASS
 #define SU_CLK_PASS_NOBAR
+#define SU_CLK_PASS_INNER
 #endif
 
 // Optional per-step output lines (reference layouts).  NULL = not wanted.
@@ -139,20 +141,14 @@ SU_DEV void stage_pre_atm(SuDiag &dg, const SuewsClassParams &P, const SuewsCell
                   R.Precip, R.LAI_obs, S.state_id.v, S.soilstore_id.v, D);
 }
 
-// Tsurf-independent stages that follow cal_AtmMoist (driver.f95:727-755, :827-834 and SurfaceResistance of :838)
-SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, int snowUse, const SuewsCellParams &C, const SuewsStepRec &R,
-                           const SuewsCellState &S, const SuAtm &A, int DLS, int nsh, double nsh_real, double Temp_C,
-                           double NonWaterFraction, const double *SnowFrac_res, SuHoist &H, const SuDaily &D SU_CLK_PARAM)
+// The water stages of the hoisted block -- irrigation (SUEWS_cal_WaterUse), drainage and its redistribution
+// (SUEWS_cal_Water) -- read the *_prev state only and feed the state update alone (plus output columns).  With snow off
+// nothing inside the surface-temperature loop reads them, so the step runs them right before the update (phase F1):
+// their 28 per-surface values are then produced and consumed inside one phase instead of sitting in the frame across
+// the whole loop.  (With snow on, a trip's evaporation surplus reads the drainage: they stay ahead of the loop.)
+SU_DEV void stage_water_a(const SuewsClassParams &P, const SuewsCellParams &C, const SuewsStepRec &R, int nsh, double nsh_real,
+                          int DLS, SuHoist &H, const SuDaily &D)
 {
-   const double *sfr = C.sfr.v;
-   double SoilState;
-   // (SU_SKIP: timing-only switches that drop one stage each -- the results are then wrong by construction; they price a
-   // stage with its memory traffic included, tools/variants.sh)
-#if !(SU_SKIP & 1)
-   update_SoilMoist(NonWaterFraction, P.SoilStoreCap.v, sfr, S.soilstore_id.v, H.SoilMoistCap, SoilState, H.vsmd, H.smd0);
-#else
-   H.SoilMoistCap = 100; SoilState = 50; H.vsmd = 10; H.smd0 = 50;
-#endif
 #if !(SU_SKIP & 2)
    cal_WaterUse(P, C, nsh_real, R.wu_m3, R.dow, D.HDD_id, D.WUDay_id, nsh, R.it, R.imin, DLS, H.wu_nsurf, H.wu_int,
                 H.wu_ext);
@@ -160,13 +156,11 @@ SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, int snowUse, c
    for (int is = 0; is < NSURF; is++) H.wu_nsurf[is] = 0;
    H.wu_int = 0; H.wu_ext = 0;
 #endif
-#if !(SU_SKIP & 4)
-   cal_AnthropogenicEmission(dg, P, C, R.dow, DLS, D.HDD_id, R.it, R.imin, R.qf_obs, Temp_C, H.an);
-#else
-   H.an.qf = 20; H.an.Fc_anthro = 0; H.an.Fc_metab = 0; H.an.Fc_traff = 0; H.an.Fc_build = 0; H.an.Fc_point = 0;
-#endif
-   H.SnowAlb_q = update_snow_albedo(P.tstep, S.SnowPack.v, S.SnowAlb, Temp_C, P.tau_a, P.tau_f, P.SnowAlbMax, P.SnowAlbMin);
-   SU_CLKB(11);
+}
+SU_DEV void stage_water_b(SuDiag &dg, const SuewsClassParams &P, int snowUse, const SuewsCellParams &C, const SuewsCellState &S,
+                          double nsh_real, double NonWaterFraction, SuHoist &H, const SuDaily &D SU_CLK_PARAM)
+{
+   const double *sfr = C.sfr.v;
    // SUEWS_cal_Water driver.f95:1614-1694 (StoreDrainPrm_next differs from _prev in (6,Decid) only)
    if (NonWaterFraction != 0 && !(SU_SKIP & 8)) {
       double s = 0;
@@ -189,6 +183,31 @@ SU_UNROLL1
 #else
    for (int is = 0; is < NSURF; is++) { H.AddWater[is] = 0; H.AddWaterRunoff[is] = 0.5; }
 #endif
+}
+
+// Tsurf-independent stages that follow cal_AtmMoist (driver.f95:727-755, :827-834 and SurfaceResistance of :838)
+SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, int snowUse, const SuewsCellParams &C, const SuewsStepRec &R,
+                           const SuewsCellState &S, const SuAtm &A, int DLS, int nsh, double nsh_real, double Temp_C,
+                           double NonWaterFraction, const double *SnowFrac_res, SuHoist &H, const SuDaily &D, bool water_late SU_CLK_PARAM)
+{
+   const double *sfr = C.sfr.v;
+   double SoilState;
+   // (SU_SKIP: timing-only switches that drop one stage each -- the results are then wrong by construction; they price a
+   // stage with its memory traffic included, tools/variants.sh)
+#if !(SU_SKIP & 1)
+   update_SoilMoist(NonWaterFraction, P.SoilStoreCap.v, sfr, S.soilstore_id.v, H.SoilMoistCap, SoilState, H.vsmd, H.smd0);
+#else
+   H.SoilMoistCap = 100; SoilState = 50; H.vsmd = 10; H.smd0 = 50;
+#endif
+   if (!water_late) stage_water_a(P, C, R, nsh, nsh_real, DLS, H, D);
+#if !(SU_SKIP & 4)
+   cal_AnthropogenicEmission(dg, P, C, R.dow, DLS, D.HDD_id, R.it, R.imin, R.qf_obs, Temp_C, H.an);
+#else
+   H.an.qf = 20; H.an.Fc_anthro = 0; H.an.Fc_metab = 0; H.an.Fc_traff = 0; H.an.Fc_build = 0; H.an.Fc_point = 0;
+#endif
+   H.SnowAlb_q = update_snow_albedo(P.tstep, S.SnowPack.v, S.SnowAlb, Temp_C, P.tau_a, P.tau_f, P.SnowAlbMax, P.SnowAlbMin);
+   SU_CLKB(11);
+   if (!water_late) stage_water_b(dg, P, snowUse, C, S, nsh_real, NonWaterFraction, H, D SU_CLK_PASS_INNER);
    SU_CLKB(13);
 #if !(SU_SKIP & 32)
    SurfaceResistance(dg, P, sfr, SnowFrac_res, R.avkdn, Temp_C, A.dq, R.xsmd, H.vsmd, D.LAI_id, H.gfunc, H.gsc, H.ResistSurf);
@@ -423,6 +442,11 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    const bool use_estm = (ESTMK != 0) && (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14);
    const bool want_snow_line = (L.snow98 != nullptr);
    const bool snow_arrays = (snowUse == 1) || want_snow_line;
+#ifdef SU_WATER_EARLY
+   const bool water_late = false;
+#else
+   const bool water_late = (SNOWK == 0);   // compile-time: the snow-off instances (see stage_water_a)
+#endif
    double lv_at_melt = 0;
 
    SU_CLK_DECL;
@@ -460,7 +484,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       lv_memo[sw_in] = A.lv_J_kg;
       lv_exit[sw_in] = lv_sw;
       SU_CLKB(10);
-      stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D SU_CLK_PASS);
+      stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D, water_late SU_CLK_PASS);
       qf = H.an.qf;
    }
 
@@ -481,7 +505,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
             if (i_iter == 2 && temp_will_rewrite) {   // trips >= 2 run the early stages with the rewritten Temp_C
                D = D_prev;
                stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
-               stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D SU_CLK_PASS_NOBAR);
+               stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D, water_late SU_CLK_PASS_NOBAR);
                qf = H.an.qf;
                rad_done = false;
             }
@@ -628,6 +652,10 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    SU_CLK(4);
    // ================= phase F1: state update of the last trip + soil water =================
    if (live && dg.fatal == 0) {
+      if (water_late) {
+         stage_water_a(P, C, R, nsh, nsh_real, DLS, H, D);
+         stage_water_b(dg, P, snowUse, C, S, nsh_real, NonWaterFraction, H, D SU_CLK_PASS_NOBAR);
+      }
       if (!qe_full_done) {
          const double qn_e = qn1_snowfree + qf - qs;
          cal_QE_full(dg, P, snowUse, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow, rb,

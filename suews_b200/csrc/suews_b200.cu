@@ -1602,6 +1602,11 @@ int suews_b200_multi_gather_sums(suews_b200_multi m, const int *cols, int ncols,
       if (cols[k] < 0 || cols[k] >= SUEWS_NCOL_SUEWS) return set_err(SUEWS_E_BAD_ARG, "multi_gather_sums: column %d", cols[k]);
       pc.col[k] = cols[k];
    }
+   // the gather is timed on its own: wait for the launches that are still running first
+   for (int d = 0; d < m->ndev; d++) {
+      CUDA_OK(cudaSetDevice(m->part[(size_t)d]->device));
+      CUDA_OK(cudaStreamSynchronize(m->part[(size_t)d]->stream));
+   }
    const auto t0 = std::chrono::steady_clock::now();
    suews_b200_handle h0 = m->part[0];
    const size_t total = (size_t)ncols * (size_t)m->ncell;
@@ -1645,10 +1650,13 @@ int suews_b200_multi_gather_sums(suews_b200_multi m, const int *cols, int ncols,
    CUDA_OK(cudaSetDevice(h0->device));
    CUDA_OK(cudaMemcpyAsync(m->pinned, m->d_gather, sizeof(double) * total, cudaMemcpyDeviceToHost, h0->stream));
    CUDA_OK(cudaStreamSynchronize(h0->stream));
-   // [ncols][ncell] -> [ncell][ncols], the layout of suews_b200_get_sums_cols
-   for (int k = 0; k < ncols; k++) {
-      const double *src = m->pinned + (size_t)k * m->ncell;
-      for (size_t c = 0; c < (size_t)m->ncell; c++) out[c * (size_t)ncols + k] = src[c];
+   // [ncols][ncell] -> [ncell][ncols], the layout of suews_b200_get_sums_cols (blocked: sequential reads, cache-sized writes)
+   for (size_t c0 = 0; c0 < (size_t)m->ncell; c0 += 4096) {
+      const size_t c1 = std::min((size_t)m->ncell, c0 + 4096);
+      for (int k = 0; k < ncols; k++) {
+         const double *src = m->pinned + (size_t)k * m->ncell;
+         for (size_t c = c0; c < c1; c++) out[c * (size_t)ncols + k] = src[c];
+      }
    }
    if (gather_ms) *gather_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
    return SUEWS_OK;
