@@ -1087,6 +1087,7 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
       if (const char *e = getenv("SUEWS_B200_GEOMETRY")) small = (strcmp(e, "small") == 0) ? true : ((strcmp(e, "large") == 0) ? false : small);
       cudaError_t (*launch)(int, cudaStream_t, const SuRunArgs &) = nullptr;
       if (kind == SU_K_FULL) launch = small ? SU_LAUNCHER_NAME(0, m1, m1, 256) : SU_LAUNCHER_NAME(0, m1, m1, 1024);
+      else if (kind == SU_K_P0 && !small && estm && !snow1 && !snow_rt) launch = SU_LAUNCHER_NAME(2, 0, m1, 1024);
       else if (small || estm || snow_rt) launch = small ? SU_LAUNCHER_NAME(1, m1, m1, 256) : SU_LAUNCHER_NAME(1, m1, m1, 1024);
       else if (kind == SU_K_ACC) launch = snow1 ? SU_LAUNCHER_NAME(1, m1, m1, 1024) : SU_LAUNCHER_NAME(1, 0, 0, 1024);
       else launch = snow1 ? SU_LAUNCHER_NAME(2, 1, 0, 1024) : SU_LAUNCHER_NAME(2, 0, 0, 1024);

@@ -146,6 +146,7 @@ SU_DECL_LAUNCHER(1, m1, m1, 256);
 SU_DECL_LAUNCHER(1, 0, 0, 1024);
 SU_DECL_LAUNCHER(2, 0, 0, 1024);
 SU_DECL_LAUNCHER(2, 1, 0, 1024);
+SU_DECL_LAUNCHER(2, 0, m1, 1024);   // policy P0, snow off, ESTM (StorageHeatMethod 4/14) per class at run time
 
 #ifdef SU_CONST_CLASS   // tuning build: the (single) class record in the constant bank instead of behind a pointer
 static __constant__ SuewsClassParams su_c_class;

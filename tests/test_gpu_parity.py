@@ -968,3 +968,38 @@ def test_resort_between_launches_changes_nothing():
         assert np.array_equal(runs[0][1][nm], runs[1][1][nm]), nm
     assert np.array_equal(runs[0][2][0], runs[1][2][0]) and np.array_equal(runs[0][2][2], runs[1][2][2])
     assert runs[0][3] == runs[1][3]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["default", "snow", "estm", "netrad13"])
+def test_specialised_p0_instances_equal_the_generic_kernel(scheme):
+    """Batches large enough for the 1024-thread geometry run policy P0 through the kernel instance compiled for their
+    bucket (snow off / snow on / ESTM per class; suews_kernel.cuh): sums, state and ESTM element temperatures must be
+    bit-identical to the accumulating kernel that runs every stage (SUEWS_OUT_ALL_STAGES, the generic instance)."""
+    from suews_b200 import OUT_ALL_STAGES, OUT_SUM7, SuewsBatch, synth
+    from suews_b200.batch import all_fields
+    base = fx.state_init(2004 if scheme == "snow" else 2005)
+    met = fx.forcing(2004 if scheme == "snow" else 2005)[:288]
+    n = 60000                                    # above the small-geometry threshold (1.5 x 256 cells per SM)
+    use_estm = scheme == "estm"
+    ts5 = synth.estm_ts_forcing(met) if use_estm else None
+    res = []
+    for flags in (OUT_SUM7 | OUT_ALL_STAGES, OUT_SUM7):
+        b = SuewsBatch(n, 1)
+        synth.build_batch(b, base, cell0=0, scheme=scheme, ts_row0=ts5[0] if use_estm else None)
+        b.upload()
+        b.set_forcing(met)
+        if use_estm:
+            b.set_estm_forcing(ts5)
+        b.advance(0, 144, flags)
+        b.advance(144, 144, flags)
+        st = {nm: b.get_state(nm).copy() for nm, kind, _n in all_fields()
+              if (kind == 3 and nm != "rsl_cache") or (kind == 4 and use_estm)}
+        fatal, _w, iters = b.diag()
+        res.append((b.sums_cols(list(PARITY_COLS.values())), st, fatal.copy(), iters.copy()))
+        b.close()
+    assert not res[0][2].any() and not res[1][2].any()
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][3], res[1][3])
+    for nm in res[0][1]:
+        assert np.array_equal(res[0][1][nm], res[1][1][nm], equal_nan=True), nm
