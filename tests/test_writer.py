@@ -120,3 +120,31 @@ def test_real_fields_follow_fw_d_editing_on_random_values():
         f146 = ln[start:start + 14]
         want = "%14.6f" % v
         assert f146 == (want if len(want) == 14 else "*" * 14), (v, f146, want)
+
+
+def test_initial_state_folds_the_users_namelist_like_the_reference():
+    """checkpoint.initial_state: InitialState + SUEWS_Translate(ir = 0) (suews_ctrl_init.f95:1443-1999,
+    suews_ctrl_translate.f95:886-990).  Pin: the reference's own golden run starts the year 2004 from
+    Input/InitialConditionstest_2004.nml (LeavesOutInitially = 0, snow given) and dumps the arguments of its first
+    SUEWS_cal_Main call (test1_2004_state_init.txt): the fold must land on those values exactly."""
+    import fixtures as fx
+    from suews_b200 import checkpoint
+    d = fx.state_init(2004)
+    nml = checkpoint.read(os.path.join(fx.GOLDEN, "ref_InitialConditions_2004_input.nml"))
+    st = checkpoint.initial_state(nml, d, water_depth=20000.0)     # WaterDepth of the test site's SUEWS_Water.txt
+    checked = 0
+    for nm, vals in st.items():
+        ref = np.atleast_1d(np.asarray(d[nm.lower()], dtype=float)).ravel()
+        assert np.array_equal(np.asarray(vals, dtype=float), ref), (nm, vals, ref)
+        checked += 1
+    assert checked >= 28
+    # the shortcuts and the reference's complaints
+    summer = checkpoint.initial_state(dict(nml, LeavesOutInitially=1), d, water_depth=1.0)
+    assert summer["LAI_id"] == [float(x) for x in d["laimax"]] and summer["SDD_id"] == [0.0] * 3
+    assert summer["GDD_id"][0] == float(np.dot(d["gddfull"], d["sfr"][2:5]) / np.sum(d["sfr"][2:5]))
+    nosnow = checkpoint.initial_state(dict(nml, SnowInitially=0), d, water_depth=1.0)
+    assert nosnow["SnowPack"] == [0.0] * 7 and nosnow["SnowAlb"] == [0.0]
+    with pytest.raises(ValueError):
+        checkpoint.initial_state({k: v for k, v in nml.items() if k != "SoilstoreGrassState"}, d, water_depth=1.0)
+    with pytest.raises(ValueError):
+        checkpoint.initial_state(dict(nml, LeavesOutInitially=-999), d, water_depth=1.0)

@@ -15,7 +15,8 @@ and committed.  Nothing here is reference *code*: only its test data.
   estm_ts_2005_60min.txt, ref_estm_ts_2005_5min.txt
                                 ESTM surface-temperature forcing: the hourly input and the 5-min series the reference wrote
                                 from it (DisaggregateESTM with KeepTstepFilesIn = 1, f9.4; Release/InputTables/2020a/)
-  ref_InitialConditions_2005.nml, ref_InitialConditions_2005_EndofRun.nml
+  ref_InitialConditions_2004_input.nml (the user-written file the golden run starts from), ref_InitialConditions_2005.nml,
+  ref_InitialConditions_2005_EndofRun.nml
                                 the state the reference wrote at the end of its 2004 leg (105 408 steps) and of its 2005
                                 leg (1 440 steps): NextInitial, suews_ctrl_init.f95:2022-2149, list-directed, 17
                                 significant digits -- i.e. the exact doubles (Test/BaseRun/2020b/Input/)
@@ -73,6 +74,7 @@ def main():
         ("2020b/Output/test1_2004_SOLWEIG_60.txt", "ref_2004_SOLWEIG_60.txt"),
         ("../../Release/InputTables/2020a/test1_2005_ESTM_Ts_data_60.txt", "estm_ts_2005_60min.txt"),
         ("../../Release/InputTables/2020a/test1_2005_ESTM_Ts_data_5.txt", "ref_estm_ts_2005_5min.txt"),
+        ("2020b/Input/InitialConditionstest_2004.nml", "ref_InitialConditions_2004_input.nml"),
         ("2020b/Input/InitialConditionstest1_2005.nml", "ref_InitialConditions_2005.nml"),
         ("2020b/Input/InitialConditionstest1_2005_EndofRun.nml", "ref_InitialConditions_2005_EndofRun.nml"),
     ]
