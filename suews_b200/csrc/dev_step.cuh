@@ -303,9 +303,10 @@ SU_DEV double cal_QE_light(const SuewsClassParams &P, const SuewsCellParams &C, 
    double qe = 0, ev = 0, qe_surf = 0;
    SuEvapTrip et;
    evap_trip_init(et, P.EvapMethod, A.VPd_hpa, A.avdens, A.avcp, qn_e, Lm.s_hPa, Lm.psyc_hPa, H.ResistSurf, RA, rb, tlv);
+   const bool need_cap = (P.EvapMethod == 1);   // the store capacity only enters the Rutter form (evap.f95:108-117)
 SU_UNROLL1
    for (int is = 0; is < NSURF; is++) {
-      const double cap = (is == DECID) ? D.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is);
+      const double cap = !need_cap ? 0.0 : ((is == DECID) ? D.DecidStoreCap : SU_SDP(S.StoreDrainPrm.v, 5, is));
       evap_surface<false>(et, S.state_id[is], P.WetThresh[is], cap, ev, qe_surf);
       qe = qe + qe_surf * C.sfr[is];
    }
@@ -418,7 +419,6 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    int lv_sw = (int)S.lv_switch;
    double qn1_av_next = S.qn1_av, dqndt_next = S.dqndt, qn1_s_av_next = S.qn1_s_av, dqnsdt_next = S.dqnsdt;
    double SnowfallCum_next = S.SnowfallCum, SnowAlb_next = S.SnowAlb;
-   double alb_next[NSURF];
    SuHoist H;
    SuDaily D_prev;   // only filled when Temp_C is about to be rewritten (rare)
    SuAtm A;
@@ -521,16 +521,18 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          const bool redo_rad = !(rad_invariant && rad_done);
          if (redo_rad) {
             // ---------------- SUEWS_cal_Qn driver.f95:1288-1455
-            for (int is = 0; is < NSURF; is++) { alb_next[is] = S.alb[is]; SnowFrac_q[is] = S.SnowFrac[is]; }
+            // alb_next = alb_prev with the three vegetation albedos of the day (driver.f95:1409-1413): the same values on
+            // every trip and nothing reads alb_prev afterwards, so the state array is updated in place
+            for (int is = 0; is < NSURF; is++) SnowFrac_q[is] = S.SnowFrac[is];
             if (nrm_use > 0) {
                if (snowUse == 0)
                   for (int is = 0; is < NSURF; is++) SnowFrac_q[is] = 0;
                Rd.ldown = (ldown_option == 1) ? R.ldown_obs : -9.0;
                if (ldown_option == 2) Rd.fcld = R.fcld_obs;
-               alb_next[DECID] = D.albDecTr_id;
-               alb_next[CONIF] = D.albEveTr_id;
-               alb_next[GRASS] = D.albGrass_id;
-               NARP(sfr, SnowFrac_q, alb_next, P.emis.v, S.IceFrac.v, P.NARP_EMIS_SNOW, zenith_deg, Ts_iter, avkdn, Temp_C,
+               S.alb[DECID] = D.albDecTr_id;
+               S.alb[CONIF] = D.albEveTr_id;
+               S.alb[GRASS] = D.albGrass_id;
+               NARP(sfr, SnowFrac_q, S.alb.v, P.emis.v, S.IceFrac.v, P.NARP_EMIS_SNOW, zenith_deg, Ts_iter, avkdn, Temp_C,
                     avRh, A.Ea_hPa, R.qn1_obs, H.SnowAlb_q, AlbedoChoice, ldown_option, nrm_use, Rd);
                qn1 = Rd.qn1; qn1_snowfree = Rd.qn1_snowfree; qn1_S = Rd.qn1_S;
             } else {
@@ -713,11 +715,11 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       if (snow_arrays) {
          S.IceFrac[is] = W.iceFrac[is]; S.SnowWater[is] = W.SnowWater[is]; S.SnowDens[is] = W.SnowDens[is];
          S.SnowFrac[is] = W.SnowFrac[is]; S.SnowPack[is] = W.SnowPack[is];
-      } else {
+      } else if (SNOWK != 0) {
          S.SnowFrac[is] = 0;   // snowUse = 0: ice fraction, snow water, density and pack are carried unchanged
-      }
+      }                        // (SNOWK == 0: nothing reads SnowFrac during a snow-off launch; the kernel zeroes it once at the end)
       S.soilstore_id[is] = W.soilstore_id[is];
-      S.state_id[is] = W.state_id[is]; S.alb[is] = alb_next[is];
+      S.state_id[is] = W.state_id[is];
    }
    // Daily state: D already holds this step's values (stage_pre_atm); on the last step of the day the one element of
    // StoreDrainPrm that evolves follows (dailystate.f95:671)

@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    }
 
    if (active) {
+      if (SNOWK == 0 && dg.fatal == 0 && a.nsteps > 0)   // SnowFrac_next of a snow-off step (dev_step.cuh, phase F3), once per launch
+         for (int is = 0; is < NSURF; is++) S.SnowFrac[is] = 0;
       for (int i = 0; i < 12; i++) S.HDD_id[i] = D.HDD_id[i];
       for (int i = 0; i < 3; i++) { S.GDD_id[i] = D.GDD_id[i]; S.SDD_id[i] = D.SDD_id[i]; S.LAI_id[i] = D.LAI_id[i]; }
       for (int i = 0; i < 9; i++) S.WUDay_id[i] = D.WUDay_id[i];
