@@ -366,6 +366,8 @@ SU_UNROLL1
    return qe_per_tstep;
 }
 
+SU_COLD void su_copy_daily(SuDaily &dst, const SuDaily &src) { dst = src; }
+
 // Site constants of a launch (pure functions of the cell parameters, formed once by the kernel prologue)
 struct SuSite {
    SuSpaSite spa;    // observer terms of the solar position
@@ -468,7 +470,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          SnowFrac_res[is] = (snowUse == 1) ? ((nrm_use > 0) ? S.SnowFrac[is] : R.snowFrac_obs) : 0.0;
       // the reference runs the stages ahead of cal_AtmMoist again on trips >= 2 when sat_vap_press_x rewrites Temp_C
       // (|Temp_C| < 0.001, see phase L1): only then is a copy of the daily state kept to restart from
-      if (temp_will_rewrite) D_prev = D;
+      if (temp_will_rewrite) su_copy_daily(D_prev, D);   // (out of line: a rare path whose 45 loads and stores must not be scheduled ahead of the test)
 #if !(SU_SKIP & 512)
       stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
 #else
@@ -503,7 +505,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       if (run) {
          if (i_iter > 1) {
             if (i_iter == 2 && temp_will_rewrite) {   // trips >= 2 run the early stages with the rewritten Temp_C
-               D = D_prev;
+               su_copy_daily(D, D_prev);
                stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
                stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D, water_late SU_CLK_PASS_NOBAR);
                qf = H.an.qf;

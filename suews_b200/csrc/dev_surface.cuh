@@ -413,14 +413,22 @@ SU_DEV void ReDistributeWater(int snowUse, const double *WaterDist, const double
    AddWaterRunoff[WATER] = 0;
    // same accumulation order as the reference's ii/jj loops; a surface that does not drain adds an exact zero
    // and is skipped, and the running sum of a receiving surface stays in a register
+   // Drain[jj] * sfr[jj], the leading product of every term of column jj, once per column (in registers: the loop over jj
+   // below is unrolled) instead of once per (ii, jj) pair from the frame
+   double ds[NSURF - 1];
+#pragma unroll
+   for (int jj = 0; jj < NSURF - 1; jj++) ds[jj] = Drain[jj] * sfr[jj];
    for (int ii = 0; ii < NSURF; ii++) {
       if (sfr[ii] != 0 && snowUse == 0) {
          double a = 0;
+         const double sfr_ii = sfr[ii];
+#pragma unroll
          for (int jj = 0; jj < NSURF - 1; jj++) {
             // (most of the 7 x 6 WaterDist matrix is zero -- a surface hands its drainage to one or two others -- and a
-            // zero fraction adds +0 to a sum of non-negative terms: the division is only made for the others)
+            // zero fraction adds +0 to a sum of non-negative terms: the division is only made for the others; a column that
+            // does not drain has ds = 0 (or -0 for a zero fraction, as Drain is never negative) and adds an exact zero too)
             const double wd = SU_WDIST(WaterDist, ii, jj);
-            if (Drain[jj] != 0 && wd != 0) a = a + (Drain[jj] * sfr[jj] / sfr[ii]) * wd;
+            if (ds[jj] != 0 && wd != 0) a = a + (ds[jj] / sfr_ii) * wd;
          }
          AddWater[ii] = a;
       } else {
