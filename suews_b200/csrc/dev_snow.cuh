@@ -180,7 +180,11 @@ SU_DEV double SnowDepletionCurve(int is, double swe, double sweD)
 
 // Working set shared by the 7 per-surface calls inside SUEWS_cal_QE (driver.f95:1973-2059)
 struct SuQEWork {
-   double state_id[NSURF], soilstore_id[NSURF], SnowPack[NSURF], SnowFrac[NSURF], SnowWater[NSURF], iceFrac[NSURF],
+   // The surface and soil stores are updated IN PLACE in the cell's state record: the committing evaluation runs once per
+   // step, after the surface-temperature loop, every surface reads its old value before it writes the new one, and the
+   // step's commit then has nothing to copy (the reference's *_next arrays, driver.f95:1973-2059)
+   double *state_id, *soilstore_id;
+   double SnowPack[NSURF], SnowFrac[NSURF], SnowWater[NSURF], iceFrac[NSURF],
       SnowDens[NSURF], SurplusEvap[NSURF], runoffSoil[NSURF], SnowDepth[NSURF];
    double SnowRemoval[2];
    SuFlood fl;

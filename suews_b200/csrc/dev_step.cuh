@@ -219,16 +219,16 @@ SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, int snowUse, c
 
 // SUEWS_cal_QE driver.f95:1744-2082: per-surface evaporation + surface/soil/snow state update.
 SU_DEV void cal_QE_full(SuDiag &dg, const SuewsClassParams &P, int snowUse, const SuewsCellParams &C, const SuewsStepRec &R,
-                        const SuewsCellState &S, const SuAtm &A, const SuLumps &Lm, const SuHoist &H, const SuSnowHeat &Hs,
+                        SuewsCellState &S, const SuAtm &A, const SuLumps &Lm, const SuHoist &H, const SuSnowHeat &Hs,
                         const double *Tsurf_ind, const double *SnowPack_m, const double *SnowFrac_q,
                         const double *SnowDens_m, double Temp_C, double avRh, double RA, double RAsnow, double rb,
                         double qn_e, double PervFraction, double VegFraction, double NonWaterFraction, bool snow_arrays,
                         SuQEWork &W, SuQETot &T, const SuDaily &D)
 {
    const double *sfr = C.sfr.v;
+   W.state_id = S.state_id.v;          // updated in place (SuQEWork)
+   W.soilstore_id = S.soilstore_id.v;
    for (int is = 0; is < NSURF; is++) {
-      W.state_id[is] = S.state_id[is];
-      W.soilstore_id[is] = S.soilstore_id[is];
       if (snow_arrays) {
          W.SnowPack[is] = SnowPack_m[is];
          W.SnowFrac[is] = SnowFrac_q[is];
@@ -278,14 +278,15 @@ SU_UNROLL1
             W.SnowPack[is] = 0;
          }
       } else {
-         evap_surface<true>(et, W.state_id[is], P.WetThresh[is], cap, ev, qe_surf);
-         double runoff_is, state_is = W.state_id[is];
-         cal_water_storage(dg, is, P, C, pin, H.wu_nsurf[is], H.drain[is], H.AddWater[is], nsh_r, S.state_id[is],
+         const double state_old = S.state_id[is];
+         evap_surface<true>(et, state_old, P.WetThresh[is], cap, ev, qe_surf);
+         double runoff_is, state_is = state_old;
+         cal_water_storage(dg, is, P, C, pin, H.wu_nsurf[is], H.drain[is], H.AddWater[is], nsh_r, state_old,
                            H.AddWaterRunoff[is], PervFraction, W.fl, ev, W.soilstore_id, W.SurplusEvap, runoff_is, state_is);
          W.state_id[is] = state_is;
          T.ev_per_tstep = T.ev_per_tstep + ev * sfr[is];
          qe_per_tstep = qe_per_tstep + qe_surf * sfr[is];
-         T.surf_chang_per_tstep = T.surf_chang_per_tstep + (state_is - S.state_id[is]) * sfr[is];
+         T.surf_chang_per_tstep = T.surf_chang_per_tstep + (state_is - state_old) * sfr[is];
          T.runoff_per_tstep = T.runoff_per_tstep + runoff_is * sfr[is];
          T.state_per_tstep = T.state_per_tstep + state_is * sfr[is];
          if (NonWaterFraction != 0 && is != WATER)
@@ -611,16 +612,9 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          if (snowUse == 1)
             for (int is = 0; is < NSURF; is++) snow_branch = snow_branch || (Hs.snowCalcSwitch[is] == 1);
          if (snow_branch) {
-#ifdef SU_SNOW_FULL_TRIPS   // (first release: the full state update on every trip that has a surface in the snow branch)
-            cal_QE_full(dg, P, snowUse, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow,
-                        rb, qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
-            qe = QT.qe;
-            qe_full_done = true;
-#else
             qe = cal_QE_light_snow(dg, P, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA,
                                    RAsnow, rb, qn_e, PervFraction, VegFraction, W, D);
             qe_full_done = false;
-#endif
          } else {
             qe = cal_QE_light(P, C, S, A, Lm, H, RA, rb, qn_e, D);
             qe_full_done = false;
@@ -660,21 +654,23 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
          stage_water_a(P, C, R, nsh, nsh_real, DLS, H, D);
          stage_water_b(dg, P, snowUse, C, S, nsh_real, NonWaterFraction, H, D SU_CLK_PASS_NOBAR);
       }
-      if (!qe_full_done) {
+      constexpr bool want_out = (K != 2);    // policy P0 forms no output line: SMD columns and TotCh are not needed
+      double soilstoreOld[NSURF];
+      if (want_out)
+         for (int is = 0; is < NSURF; is++) soilstoreOld[is] = S.soilstore_id[is];
+      {   // the state update of the step: once, with the converged trip's resistances (stores updated in place)
          const double qn_e = qn1_snowfree + qf - qs;
          cal_QE_full(dg, P, snowUse, C, R, S, A, Lm, H, Hs, Rd.Tsurf_ind, SnowPack_m, SnowFrac_q, SnowDens_m, Temp_C, avRh, RA, RAsnow, rb,
                      qn_e, PervFraction, VegFraction, NonWaterFraction, snow_arrays, W, QT, D);
       }
       SU_CLKB(15);
       qh_resist = (RA != 0) ? A.avdens * A.avcp * (Rd.tsurf - Temp_C) / RA : -999.0;
-      double soilstoreOld[NSURF];
-      for (int is = 0; is < NSURF; is++) soilstoreOld[is] = S.soilstore_id[is];
 #if !(SU_SKIP & 128)
       cal_HorizontalSoilWater(P, sfr, C.SurfaceArea, NonWaterFraction, tstep_real, W.soilstore_id, W.runoffSoil,
                               runoffSoil_per_tstep);
 #endif
-      cal_SoilState(dg, P.SMDMethod, R.xsmd, NonWaterFraction, H.SoilMoistCap, P.SoilStoreCap.v, QT.surf_chang_per_tstep,
-                    W.soilstore_id, soilstoreOld, sfr, smd, smd_nsurf, tot_chang_per_tstep);
+      cal_SoilState<want_out>(dg, P.SMDMethod, R.xsmd, NonWaterFraction, H.SoilMoistCap, P.SoilStoreCap.v, QT.surf_chang_per_tstep,
+                              W.soilstore_id, soilstoreOld, sfr, smd, smd_nsurf, tot_chang_per_tstep);
    }
    SU_SYNCN(4);
    SU_CLK(5);
@@ -720,8 +716,6 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       } else if (SNOWK != 0) {
          S.SnowFrac[is] = 0;   // snowUse = 0: ice fraction, snow water, density and pack are carried unchanged
       }                        // (SNOWK == 0: nothing reads SnowFrac during a snow-off launch; the kernel zeroes it once at the end)
-      S.soilstore_id[is] = W.soilstore_id[is];
-      S.state_id[is] = W.state_id[is];
    }
    // Daily state: D already holds this step's values (stage_pre_atm); on the last step of the day the one element of
    // StoreDrainPrm that evolves follows (dailystate.f95:671)

@@ -459,6 +459,8 @@ SU_DEV void update_SoilMoist(double NonWaterFraction, const double *SoilStoreCap
 }
 
 // waterdist.f95:553-619
+// (WANT_OUT = false: only the range check of the soil moisture state, for launches that form no output line)
+template <bool WANT_OUT>
 SU_DEV void cal_SoilState(SuDiag &dg, int SMDMethod, double xsmd, double NonWaterFraction, double SoilMoistCap,
                           const double *SoilStoreCap, double surf_chang_per_tstep, const double *soilstore_id,
                           const double *soilstoreOld, const double *sfr, double &smd, double *smd_nsurf,
@@ -471,6 +473,7 @@ SU_DEV void cal_SoilState(SuDiag &dg, int SMDMethod, double xsmd, double NonWate
          if (SoilState < 0 || SoilState > SoilMoistCap) su_fatal(dg, 62);
       }
    }
+   if (!WANT_OUT) return;
    smd = SoilMoistCap - SoilState;
    for (int is = 0; is < NSURF; is++) smd_nsurf[is] = SoilStoreCap[is] - soilstore_id[is];
    tot_chang_per_tstep = surf_chang_per_tstep;
