@@ -522,51 +522,61 @@ SU_BIG2 void cal_HorizontalSoilWater(const SuewsClassParams &P, const double *sf
    // pair is a pure function of its content, which a pair only changes when water actually flows (equal matric
    // potentials -- e.g. two saturated stores -- give dI = 0).  Each store's last evaluation is kept with the content it
    // was made for and reused while the content is bit-identical.
+   // The values of the outer store `is` live in registers for its whole row of pairs (it never comes back as a `jj`:
+   // jj > is), only the inner store's are read from and written to the arrays: half the array traffic of the pair loop.
    double vg_at[NSURF - 1], vg_mp[NSURF - 1], vg_km[NSURF - 1];
    for (int is = 0; is < NSURF - 1; is++) vg_at[is] = -1.0;   // soil stores are never negative
    for (int is = 0; is < NSURF - 1; is++) {
-      if (sfr[is] != 0 && P.SoilStoreCap[is] > 0) {
+      const double sfr_is = sfr[is], cap_is = P.SoilStoreCap[is];
+      if (sfr_is != 0 && cap_is > 0) {
+         double s_is = soilstore_id[is], at_is = vg_at[is], mp_is = vg_mp[is], km_is = vg_km[is], ro_is = runoffSoil[is];
+         const double rt_is = rt[is], depth_is = P.SoilDepth[is], ksat_is = P.SatHydraulicConduct[is];
          for (int jj = is + 1; jj < NSURF - 1; jj++) {
-            if (sfr[jj] != 0 && P.SoilStoreCap[jj] > 0) {
-               if (vg_at[is] != soilstore_id[is]) {
-                  vg_store(soilstore_id[is], P.SoilStoreCap[is], P.SoilDepth[is], P.SatHydraulicConduct[is], vg_mp[is], vg_km[is]);
-                  vg_at[is] = soilstore_id[is];
+            const double sfr_jj = sfr[jj], cap_jj = P.SoilStoreCap[jj];
+            if (sfr_jj != 0 && cap_jj > 0) {
+               double s_jj = soilstore_id[jj];
+               if (at_is != s_is) {
+                  vg_store(s_is, cap_is, depth_is, ksat_is, mp_is, km_is);
+                  at_is = s_is;
                }
-               if (vg_at[jj] != soilstore_id[jj]) {
-                  vg_store(soilstore_id[jj], P.SoilStoreCap[jj], P.SoilDepth[jj], P.SatHydraulicConduct[jj], vg_mp[jj], vg_km[jj]);
-                  vg_at[jj] = soilstore_id[jj];
+               if (vg_at[jj] != s_jj) {
+                  vg_store(s_jj, cap_jj, P.SoilDepth[jj], P.SatHydraulicConduct[jj], vg_mp[jj], vg_km[jj]);
+                  vg_at[jj] = s_jj;
                }
-               const double MatPot1 = vg_mp[is], Km1 = vg_km[is], MatPot2 = vg_mp[jj], Km2 = vg_km[jj];
+               const double MatPot1 = mp_is, Km1 = km_is, MatPot2 = vg_mp[jj], Km2 = vg_km[jj];
                // Equal matric potentials (two saturated stores, two dry ones): the gradient is an exact zero, dI = -0 and the
                // pair exchanges nothing -- both stores, already capped by the water balance or by an earlier pair, keep their
-               // bits (x + -0 = x, x - -0 = x); with neither above its capacity the tests below do not fire either.  Nothing to do for this pair.
-               if (MatPot1 == MatPot2 && !(soilstore_id[is] > P.SoilStoreCap[is]) && !(soilstore_id[jj] > P.SoilStoreCap[jj])) continue;
-               double Distance = (rt[is] + rt[jj]) / 2;
-               double KmWeight = (sfr[is] * Km1 + sfr[jj] * Km2) / (sfr[is] + sfr[jj]);
+               // bits (x + -0 = x, x - -0 = x); with neither above its capacity the tests below do not fire either.
+               if (MatPot1 == MatPot2 && !(s_is > cap_is) && !(s_jj > cap_jj)) continue;
+               double Distance = (rt_is + rt[jj]) / 2;
+               double KmWeight = (sfr_is * Km1 + sfr_jj * Km2) / (sfr_is + sfr_jj);
                double dI_dt = su_div0(-(KmWeight) * (-MatPot1 + MatPot2), Distance * 1000);
                double dI = dI_dt * tstep_real;
-               const double dI_jj = su_div0(dI * sfr[is], sfr[jj]);
-               if ((soilstore_id[jj] >= dI_jj) && ((soilstore_id[is] + dI) >= 0)) {
-                  soilstore_id[is] = soilstore_id[is] + dI;
-                  soilstore_id[jj] = soilstore_id[jj] - dI_jj;
-               } else if ((soilstore_id[is] + dI) < 0) {
-                  soilstore_id[jj] = soilstore_id[jj] + soilstore_id[is] * sfr[is] / sfr[jj];
-                  soilstore_id[is] = 0;
+               const double dI_jj = su_div0(dI * sfr_is, sfr_jj);
+               if ((s_jj >= dI_jj) && ((s_is + dI) >= 0)) {
+                  s_is = s_is + dI;
+                  s_jj = s_jj - dI_jj;
+               } else if ((s_is + dI) < 0) {
+                  s_jj = s_jj + s_is * sfr_is / sfr_jj;
+                  s_is = 0;
                } else {
-                  soilstore_id[is] = soilstore_id[is] + soilstore_id[jj] * sfr[jj] / sfr[is];
-                  soilstore_id[jj] = 0;
+                  s_is = s_is + s_jj * sfr_jj / sfr_is;
+                  s_jj = 0;
                }
-               if (soilstore_id[is] > P.SoilStoreCap[is]) {
-                  runoffSoil[is] = runoffSoil[is] + (soilstore_id[is] - P.SoilStoreCap[is]);
-                  soilstore_id[is] = P.SoilStoreCap[is];
+               if (s_is > cap_is) {
+                  ro_is = ro_is + (s_is - cap_is);
+                  s_is = cap_is;
                }
-               if (soilstore_id[jj] > P.SoilStoreCap[jj]) {
-                  runoffSoil[jj] = runoffSoil[jj] + (soilstore_id[jj] - P.SoilStoreCap[jj]);
-                  soilstore_id[jj] = P.SoilStoreCap[jj];
+               if (s_jj > cap_jj) {
+                  runoffSoil[jj] = runoffSoil[jj] + (s_jj - cap_jj);
+                  s_jj = cap_jj;
                }
+               soilstore_id[jj] = s_jj;
             }
          }
-         runoffSoil_per_tstep = runoffSoil_per_tstep + su_div0(runoffSoil[is] * sfr[is], NonWaterFraction);
+         soilstore_id[is] = s_is;
+         runoffSoil[is] = ro_is;
+         runoffSoil_per_tstep = runoffSoil_per_tstep + su_div0(ro_is * sfr_is, NonWaterFraction);
       }
    }
 }
