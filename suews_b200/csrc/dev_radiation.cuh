@@ -262,8 +262,9 @@ struct SuRad {
 SU_BIG3 void NARP(const double *sfr, const double *SnowFrac, const double *alb, const double *emis,
                    const double *IceFrac, double NARP_EMIS_SNOW, double ZENITH_deg, double tsurf_0, double kdown,
                    double Temp_C, double RH, double ea_hPa, double qn1_obs, double SnowAlb, int AlbedoChoice,
-                   int ldown_option, int nrm_use, SuRad &r)
-{
+                   int ldown_option, int nrm_use, bool store_ind, SuRad &r)
+{   // store_ind: keep the per-surface arrays (Tsurf_ind and the snow-part terms) -- read by the snow routines and the snow
+    // output line only, so snow-off launches without that line do not write them
    const double SIGMA_SB = F(5.67E-8);
    const double acos0 = (double)1.57079637f;   // ACOS(0.0) in REAL(4)
    const double tsurf_0_K = tsurf_0 + F(273.16);
@@ -320,9 +321,11 @@ SU_BIG3 void NARP(const double *sfr, const double *SnowFrac, const double *alb, 
          QSTAR_SNOW = kdown - KUP_SNOW + LDOWN - LUP_SNOW;
          TSURF_SNOW = TSURF_SNOW - F(273.16);
       }
-      r.qn1_ind_snow[is] = QSTAR_SNOW;
-      r.kup_ind_snow[is] = KUP_SNOW;
-      r.Tsurf_ind_snow[is] = TSURF_SNOW;
+      if (store_ind) {
+         r.qn1_ind_snow[is] = QSTAR_SNOW;
+         r.kup_ind_snow[is] = KUP_SNOW;
+         r.Tsurf_ind_snow[is] = TSURF_SNOW;
+      }
 
       if (SF_all != 0) qsf = qsf + QSTAR * sfr[is] * (1 - SnowFrac[is]) / SF_all;
       else qsf = qsf + QSTAR * sfr[is] * (1 - SnowFrac[is]);
@@ -337,7 +340,7 @@ SU_BIG3 void NARP(const double *sfr, const double *SnowFrac, const double *alb, 
       kup_cum = kup_cum + (kup_is * sfr[is]);
       lup_cum = lup_cum + (lup_is * sfr[is]);
       tsurf_cum = tsurf_cum + (tsurf_is * sfr[is]);
-      r.Tsurf_ind[is] = tsurf_is;
+      if (store_ind) r.Tsurf_ind[is] = tsurf_is;
    }
    r.qn1_snowfree = qsf;
    r.qn1_S = qs;

@@ -526,17 +526,19 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
             // ---------------- SUEWS_cal_Qn driver.f95:1288-1455
             // alb_next = alb_prev with the three vegetation albedos of the day (driver.f95:1409-1413): the same values on
             // every trip and nothing reads alb_prev afterwards, so the state array is updated in place
-            for (int is = 0; is < NSURF; is++) SnowFrac_q[is] = S.SnowFrac[is];
+            if (nrm_use > 0 && snowUse == 0) {
+               for (int is = 0; is < NSURF; is++) SnowFrac_q[is] = 0;
+            } else {
+               for (int is = 0; is < NSURF; is++) SnowFrac_q[is] = S.SnowFrac[is];
+            }
             if (nrm_use > 0) {
-               if (snowUse == 0)
-                  for (int is = 0; is < NSURF; is++) SnowFrac_q[is] = 0;
                Rd.ldown = (ldown_option == 1) ? R.ldown_obs : -9.0;
                if (ldown_option == 2) Rd.fcld = R.fcld_obs;
                S.alb[DECID] = D.albDecTr_id;
                S.alb[CONIF] = D.albEveTr_id;
                S.alb[GRASS] = D.albGrass_id;
                NARP(sfr, SnowFrac_q, S.alb.v, P.emis.v, S.IceFrac.v, P.NARP_EMIS_SNOW, zenith_deg, Ts_iter, avkdn, Temp_C,
-                    avRh, A.Ea_hPa, R.qn1_obs, H.SnowAlb_q, AlbedoChoice, ldown_option, nrm_use, Rd);
+                    avRh, A.Ea_hPa, R.qn1_obs, H.SnowAlb_q, AlbedoChoice, ldown_option, nrm_use, snow_arrays, Rd);
                qn1 = Rd.qn1; qn1_snowfree = Rd.qn1_snowfree; qn1_S = Rd.qn1_S;
             } else {
                for (int is = 0; is < NSURF; is++) { SnowFrac_q[is] = R.snowFrac_obs; Rd.Tsurf_ind[is] = -999; }
@@ -549,7 +551,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
             if (P.StorageHeatMethod == 0) {
                qs = R.qs_obs;
             } else if (P.StorageHeatMethod == 1) {
-               OHM(dg, P, sfr, qn1_use, S.qn1_av, S.dqndt, qn1_av_next, dqndt_next, qn1_S, S.qn1_s_av, S.dqnsdt, qn1_s_av_next,
+               OHM(dg, P, snowUse, sfr, qn1_use, S.qn1_av, S.dqndt, qn1_av_next, dqndt_next, qn1_S, S.qn1_s_av, S.dqnsdt, qn1_s_av_next,
                    dqnsdt_next, dt_since_start, D.HDD_id[9], S.soilstore_id.v, S.state_id.v, SnowFrac_q, a1, a2, a3, qs,
                    deltaQi);
             } else if (!use_estm) {

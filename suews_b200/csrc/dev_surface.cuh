@@ -18,14 +18,13 @@ SU_INL void OHM_dqndt_cal_X(int dt, int dt_since_start, double qn1_av_prev, doub
 }
 
 // ohm.f95:12-199 with OHM_coef_cal :202-268 and OHM_QS_cal :347-356
-SU_DEV void OHM(SuDiag &dg, const SuewsClassParams &P, const double *sfr, double qn1, double qn1_av_prev,
+SU_DEV void OHM(SuDiag &dg, const SuewsClassParams &P, int SnowUse, const double *sfr, double qn1, double qn1_av_prev,
                 double dqndt_prev, double &qn1_av_next, double &dqndt_next, double qn1_S, double qn1_s_av_prev,
                 double dqnsdt_prev, double &qn1_s_av_next, double &dqnsdt_next, int dt_since_start, double Tair_mav_5d,
                 const double *soilstore_id, const double *state_id, const double *SnowFrac, double &a1, double &a2,
                 double &a3, double &qs, double *deltaQi)
 {
-   a1 = 0; a2 = 0; a3 = 0;
-   const int SnowUse = P.snowUse;
+   a1 = 0; a2 = 0; a3 = 0;   // (SnowUse: the caller's value -- a compile-time constant in the specialised kernel instances)
    for (int is = 0; is < NSURF; is++) {
       double surfrac = sfr[is];
       int ii = (Tair_mav_5d >= P.OHM_threshSW[is]) ? 0 : 2;
