@@ -429,6 +429,7 @@ SU_DEV double AerodynamicResistance(SuDiag &dg, double ZZD, double z0m, double l
 }
 
 // resist.f95:108-368 (gsModel 1/3 = Jarvi 2011, 2/4 = Ward 2016)
+// (SnowFrac == NULL: no snow anywhere -- the snow-off instances do not build an array of zeros for it)
 SU_DEV void SurfaceResistance(SuDiag &dg, const SuewsClassParams &P, const double *sfr, const double *SnowFrac,
                               double avkdn, double Temp_C, double dq, double xsmd, double vsmd,
                               const double *LAI_id, double &gfunc, double &gsc, double &ResistSurf)
@@ -450,11 +451,12 @@ SU_DEV void SurfaceResistance(SuDiag &dg, const SuewsClassParams &P, const doubl
          gdq = G3 + (1 - G3) * pow(G4, dq);
       }
       double TC = (TH - G5) / (G5 - TL);
-      double TC2 = (G5 - TL) * pow(TH - G5, TC);
+      double TC2 = (G5 - TL) * P.gs_pow_TH_G5;   // pow(TH - G5, TC): a class constant, formed at upload
       if (Temp_C <= TL) {
          gtemp = (TL + F(0.1) - TL) * pow(TH - (TL + F(0.1)), TC) / TC2;
-         double mn = SnowFrac[0];
-         for (int i = 1; i < 6; i++) mn = SU_MIN(mn, SnowFrac[i]);
+         double mn = SnowFrac ? SnowFrac[0] : 0.0;
+         if (SnowFrac)
+            for (int i = 1; i < 6; i++) mn = SU_MIN(mn, SnowFrac[i]);
          if (mn != 1) su_warn(dg, 29);
       } else if (Temp_C >= TH) {
          gtemp = ((TH - F(0.1)) - TL) * pow(TH - (TH - F(0.1)), TC) / TC2;
@@ -475,7 +477,7 @@ SU_DEV void SurfaceResistance(SuDiag &dg, const SuewsClassParams &P, const doubl
       }
       double gl = 0;
       for (int iv = 0; iv < 3; iv++)
-         gl = gl + (sfr[iv + 2] * (1 - SnowFrac[iv + 2])) * LAI_id[iv] / P.LAIMax[iv] * P.MaxConductance[iv];
+         gl = gl + (sfr[iv + 2] * (1 - (SnowFrac ? SnowFrac[iv + 2] : 0.0))) * LAI_id[iv] / P.LAIMax[iv] * P.MaxConductance[iv];
       if (avkdn <= 0) gsc = F(0.1);
       else gsc = (G1 * gq * gdq * gtemp * gs * gl);
       if (gsc <= 0) {

@@ -210,7 +210,7 @@ SU_DEV void stage_post_atm(SuDiag &dg, const SuewsClassParams &P, int snowUse, c
    if (!water_late) stage_water_b(dg, P, snowUse, C, S, nsh_real, NonWaterFraction, H, D SU_CLK_PASS_INNER);
    SU_CLKB(13);
 #if !(SU_SKIP & 32)
-   SurfaceResistance(dg, P, sfr, SnowFrac_res, R.avkdn, Temp_C, A.dq, R.xsmd, H.vsmd, D.LAI_id, H.gfunc, H.gsc, H.ResistSurf);
+   SurfaceResistance(dg, P, sfr, SnowFrac_res, R.avkdn, Temp_C, A.dq, R.xsmd, H.vsmd, D.LAI_id, H.gfunc, H.gsc, H.ResistSurf);   // (SnowFrac_res: NULL in the snow-off instances)
 #else
    H.gfunc = 1; H.gsc = 0.01; H.ResistSurf = 100;
 #endif
@@ -468,7 +468,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       rad_invariant = (nrm_use < 10);
       // snow fraction seen by SurfaceResistance = SnowFrac_next after Snow_cal_MeltHeat (driver.f95:848)
       for (int is = 0; is < NSURF; is++)
-         SnowFrac_res[is] = (snowUse == 1) ? ((nrm_use > 0) ? S.SnowFrac[is] : R.snowFrac_obs) : 0.0;
+         if (SNOWK != 0) SnowFrac_res[is] = (snowUse == 1) ? ((nrm_use > 0) ? S.SnowFrac[is] : R.snowFrac_obs) : 0.0;
       // the reference runs the stages ahead of cal_AtmMoist again on trips >= 2 when sat_vap_press_x rewrites Temp_C
       // (|Temp_C| < 0.001, see phase L1): only then is a copy of the daily state kept to restart from
       if (temp_will_rewrite) su_copy_daily(D_prev, D);   // (out of line: a rare path whose 45 loads and stores must not be scheduled ahead of the test)
@@ -487,7 +487,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
       lv_memo[sw_in] = A.lv_J_kg;
       lv_exit[sw_in] = lv_sw;
       SU_CLKB(10);
-      stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D, water_late SU_CLK_PASS);
+      stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, (SNOWK == 0) ? nullptr : SnowFrac_res, H, D, water_late SU_CLK_PASS);
       qf = H.an.qf;
    }
 
@@ -508,7 +508,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
             if (i_iter == 2 && temp_will_rewrite) {   // trips >= 2 run the early stages with the rewritten Temp_C
                su_copy_daily(D, D_prev);
                stage_pre_atm(dg, P, C, R, S, dt_since_start, tstep_prev, nsh_real, Temp_C, H, D);
-               stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, SnowFrac_res, H, D, water_late SU_CLK_PASS_NOBAR);
+               stage_post_atm(dg, P, snowUse, C, R, S, A, DLS, nsh, nsh_real, Temp_C, NonWaterFraction, (SNOWK == 0) ? nullptr : SnowFrac_res, H, D, water_late SU_CLK_PASS_NOBAR);
                qf = H.an.qf;
                rad_done = false;
             }

@@ -10,6 +10,7 @@
 //   sums      double[82][stride]                  per-cell running sums of the SUEWS output line
 // One thread owns one cell and advances it through all requested timesteps of a launch.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -675,6 +676,11 @@ int suews_b200_upload(suews_b200_handle h)
             for (int i = 0; i < 24; i++) s += prof[k][24 * u + i];
             P.prof_sum[k][u] = s;
          }
+      {   // the same REAL(8) expression the reference evaluates on every call, with the host libm
+         const double TH = P.TH, G5 = P.G5, TL = P.TL;
+         const double TC = (TH - G5) / (G5 - TL);
+         P.gs_pow_TH_G5 = pow(TH - G5, TC);
+      }
       if (P.tstep != h->tstep || P.tstep <= 0)
          return set_err(SUEWS_E_BAD_ARG, "upload: all classes must share one positive tstep (got %d and %d)", h->tstep, (int)P.tstep);
    }

@@ -141,6 +141,7 @@ struct SuewsClassParams {
    SUEWS_CLASS_DBL_FIELDS(SUEWS_DECL_DBL)
    // derived at upload (bit-identical to what the reference recomputes every call):
    double prof_sum[6][2];   // sequential SUM of AH, HumAct, Pop, Traff, WUProfA, WUProfM (weekday, weekend)
+   double gs_pow_TH_G5;     // (TH - G5)**TC, TC = (TH - G5)/(G5 - TL): the class constant inside SurfaceResistance's TC2 (resist.f95:269-270)
 };
 
 // device-side records of one cell: the COLD fields by value (the first SUEWS_N_*_COLD doubles of the struct, in list
