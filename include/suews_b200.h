@@ -123,6 +123,16 @@ int suews_b200_set_estm_forcing(suews_b200_handle h, const double *ts5, int nste
 int suews_b200_set_estm_forcing_orig(suews_b200_handle h, const double *ts_orig, int nrows, int resolution_in_s, int disagg_method);
 int suews_b200_get_estm_forcing_block(suews_b200_handle h, double *ts_fast, int nsteps);
 
+/* AnOHM (StorageHeatMethod 3; suews_phys_anohm.f95, called at suews_ctrl_driver.f95:1586).  Parameters: the class fields
+ * cpAnOHM, kkAnOHM, chAnOHM (7 each) next to alb / emis.  Its memory -- the SAVE'd locals of AnOHM and AnOHM_coef
+ * (:79, :215-216) -- is per-cell state of kind SUEWS_KIND_ESTM_STATE: anohm_id_save, anohm_coef_id_save,
+ * anohm_coef_grid_save, anohm_coeff_grid_day (7 x 3, initially -999).  MetForcingData_grid, the grid's whole forcing block
+ * from which the once-a-day fit takes the day's on-the-hour rows (suews_ctrl_translate.f95:1216), is the forcing block
+ * staged by set_forcing / set_forcing_orig (at most 24 on-the-hour rows per day of year, i.e. up to one year per block);
+ * set_anohm_forcing supplies a different one ([nrows x 24] column-major) until the next set_forcing.  Every cell behaves
+ * as a single-grid run of the reference. */
+int suews_b200_set_anohm_forcing(suews_b200_handle h, const double *met, int nrows);
+
 /* Advance all cells over forcing rows [step0, step0 + nsteps).  One kernel launch.  Asynchronous
  * with respect to the host; suews_b200_sync waits and returns the first fatal cell error (0 if none). */
 int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags);
@@ -200,6 +210,13 @@ void suews_refapi_reset_hidden(void);
  * listed at suews_b200_set_estm_forcing); state variables are updated by every SUEWS_cal_Main / _multitsteps call
  * with StorageHeatMethod 4/14 and can be read back.  Ts5mindata_ir is the argument of those calls. */
 int suews_estm_data_set(const char *name, const double *vals, int n);
+/* MetForcingData_grid for the reference-shaped calls with StorageHeatMethod 3 (AnOHM): the argument is assumed-shape in
+ * the reference (driver.f95:277) and cannot travel through a pointer table, so the host hands the grid's forcing block
+ * over here ([nrows x 24] column-major, copied; NULL forgets it).  Without it suews_cal_multitsteps_c uses its own
+ * MetForcingBlock (the reference passes an uninitialised 10 x 10 placeholder there, driver.f95:3163) and suews_cal_main_c
+ * returns 1003.  AnOHM's SAVE'd locals are process-wide, like the reference's (readable through suews_estm_data_get
+ * under the names anohm_id_save, anohm_coef_id_save, anohm_coef_grid_save, anohm_coeff_grid_day). */
+int suews_anohm_set_met_grid(const double *met, int nrows);
 int suews_estm_data_get(const char *name, double *vals, int n);
 
 int suews_cal_sunposition_c(double year, double idectime, double UTC, double locationlatitude,

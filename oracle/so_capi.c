@@ -70,6 +70,10 @@ static const SoField STATE_FIELDS[] = {
    SDE(Tair2), SDE(Tievolve), SDE(lup_ground), SDE(lup_wall), SDE(lup_roof), SDE(T0_ibld), SDE(T0_ground), SDE(T0_wall),
    SDE(T0_roof), SDE(TN_wall), SDE(TN_roof), SDE(Tground), SDE(Twall), SDE(Troof), SDE(Tibld), SDE(Tw_4), SDE(HVAC),
    SDE(Tair2Set), SDE(NewtonConverged),
+   /* AnOHM's SAVE'd locals (suews_phys_anohm.f95:79, :215-216) */
+   {"anohm_id_save", 0, offsetof(SoState, anohm.id_save), 1}, {"anohm_coef_id_save", 0, offsetof(SoState, anohm.coef_id_save), 1},
+   {"anohm_coef_grid_save", 0, offsetof(SoState, anohm.coef_grid_save), 1},
+   {"anohm_coeff_grid_day", 0, offsetof(SoState, anohm.coeff_grid_day), 21},
 };
 #undef SD
 #undef SI
@@ -116,7 +120,14 @@ static int get_field(const void *base, const SoField *fd, double *vals, int n)
 #define NSF ((int)(sizeof(STATE_FIELDS) / sizeof(STATE_FIELDS[0])))
 
 SoParams *so_params_new(void) { return (SoParams *)calloc(1, sizeof(SoParams)); }
-SoState *so_state_new(void) { return (SoState *)calloc(1, sizeof(SoState)); }
+SoState *so_state_new(void)
+{
+   SoState *s = (SoState *)calloc(1, sizeof(SoState));
+   int k;
+   if (s)
+      for (k = 0; k < 21; k++) s->anohm.coeff_grid_day[k] = -999.;   /* coeff_grid_day(7,3) = -999. (anohm.f95:216) */
+   return s;
+}
 void so_free(void *p) { free(p); }
 void so_state_copy(SoState *dst, const SoState *src) { *dst = *src; }
 
@@ -176,6 +187,27 @@ int so_run(const SoParams *p, SoState *st, const double *met, int len_sim, doubl
  * Troof Troad Twall Twall_n Twall_e Twall_s Twall_w), or NULL.  The pointer is borrowed. */
 void so_set_ts5_block(const double *ts5) { so_ts5_block = ts5; }
 
+/* MetForcingData_grid for AnOHM: [nrows x 24] column-major, or NULL (then so_run uses its own block).  Borrowed. */
+void so_set_met_grid(const double *met, int nrows) { so_met_grid = met; so_met_grid_nrows = met ? nrows : 0; }
+
+/* The day's AnOHM coefficients of the seven surfaces as a fresh process would form them on its first call of day `id`
+ * (tests of the device-side fit): coeff21 = coeff_grid_day(7,3) column-major. */
+void so_anohm_coefs(const double *met, int nrows, int id, int EmissionsMethod, double qf, const double *moist,
+                    const double *alb, const double *emis, const double *cp, const double *kk, const double *ch,
+                    double *coeff21)
+{
+   SoCtx cx;
+   SoAnohmState an;
+   double sfr[NSURF] = {0, 0, 0, 0, 0, 0, 0}, dq[NSURF], qa, dqn, a1, a2, a3, qs;
+   int k;
+   so_ctx_init(&cx);
+   an.id_save = 0; an.coef_id_save = 0; an.coef_grid_save = 0;
+   for (k = 0; k < 21; k++) an.coeff_grid_day[k] = -999.;
+   so_AnOHM(&cx, &an, 300, 0, 0.0, 0.0, 0.0, qf, met, nrows, moist, alb, emis, cp, kk, ch, sfr, EmissionsMethod, id, 1,
+            &qa, &dqn, &a1, &a2, &a3, &qs, dq);
+   for (k = 0; k < 21; k++) coeff21[k] = an.coeff_grid_day[k];
+}
+
 /* First-call initialisation of the ESTM element temperatures (ESTM_translate, ESTMStart == 1) */
 void so_estm_start(const SoParams *p, SoState *st, const double *ts_row1_13)
 {
@@ -195,6 +227,7 @@ int so_run_cells(int ncell, const SoParams *params, SoState *states, const doubl
       SoOutLines out;
       const double *m = met + (size_t)c * (size_t)met_stride;
       so_ctx_init(&cx);
+      so_met_grid = m; so_met_grid_nrows = len_sim;
       if (sum_suews)
          for (k = 0; k < NCOL_SUEWS; k++) sum_suews[(size_t)c * NCOL_SUEWS + k] = 0;
       for (ir = 0; ir < len_sim; ir++) {
@@ -212,6 +245,7 @@ int so_run_cells(int ncell, const SoParams *params, SoState *states, const doubl
          if (cx.fatal_code) { rc = cx.fatal_code; break; }
       }
    }
+   so_met_grid = 0; so_met_grid_nrows = 0;
    return rc;
 }
 

@@ -139,6 +139,7 @@ static void cal_Qn(SoCtx *cx, const SoParams *p, const SoForcing *f, const doubl
 
 /* driver.f95:1457-1612 */
 static void cal_Qs(SoCtx *cx, const SoParams *p, const SoForcing *f, int dt_since_start, SoEstmState *estm,
+                   SoAnohmState *anohm, const double alb_next[NSURF], const double *StoreDrainPrm_next,
                    double zenith_deg, double ldown, double Tair_av,
                    const double soilstore_id[NSURF], const double state_id[NSURF], const double SnowFrac[NSURF],
                    const double HDD_id[12], double qf, double qn1, double qn1_av_prev, double dqndt_prev,
@@ -166,7 +167,17 @@ static void cal_Qs(SoCtx *cx, const SoParams *p, const SoForcing *f, int dt_sinc
              p->OHM_threshWD, soilstore_id, p->SoilStoreCap, state_id, p->snowUse, SnowFrac, p->DiagQS, a1, a2, a3, qs,
              deltaQi);
    } else if (p->StorageHeatMethod == 3) {
-      so_error_hint(cx, 1003, "oracle: StorageHeatMethod=3 (AnOHM) not restated", -999, -999, 3);
+      /* driver.f95:1577-1594; MetForcingData_grid is the host's whole forcing block of the grid */
+      double moist_surf[NSURF];
+      int is;
+      for (is = 0; is < NSURF; is++) moist_surf[is] = state_id[is] / SDP(StoreDrainPrm_next, 5, is);
+      if (!so_met_grid) {
+         so_error_hint(cx, 1006, "oracle: StorageHeatMethod=3 (AnOHM) needs MetForcingData_grid", -999, -999, 3);
+      } else {
+         so_AnOHM(cx, anohm, p->tstep, dt_since_start, qn1_use, qn1_av_prev, dqndt_prev, qf, so_met_grid,
+                  so_met_grid_nrows, moist_surf, alb_next, p->emis, p->cpAnOHM, p->kkAnOHM, p->chAnOHM, p->sfr,
+                  p->EmissionsMethod, f->id, p->Gridiv, qn1_av_next, dqndt_next, a1, a2, a3, qs, deltaQi);
+      }
    } else if (p->StorageHeatMethod == 4 || p->StorageHeatMethod == 14) {
       so_ESTM(cx, p, estm, p->tstep, f->avkdn, f->avU1, f->Temp_C, zenith_deg, f->avRh, f->Press_hPa, ldown, p->bldgH,
               f->Ts5mindata_ir, Tair_av, dataOutLineESTM, qs);
@@ -503,7 +514,7 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
              &qn1_snowfree, &qn1_S, &kclear, &kup, &lup, &tsurf, qn1_ind_snow, kup_ind_snow, Tsurf_ind_snow, tsurf_ind,
              &alb1, nx.SnowFrac, &nx.SnowAlb);
 
-      cal_Qs(cx, p, &fl, st->dt_since_start, &st->estm, ZENITH_deg, ldown, nx.Tair_av, pv.soilstore_id, pv.state_id, nx.SnowFrac, nx.HDD_id, qf, qn1, pv.qn1_av,
+      cal_Qs(cx, p, &fl, st->dt_since_start, &st->estm, &st->anohm, nx.alb, nx.StoreDrainPrm, ZENITH_deg, ldown, nx.Tair_av, pv.soilstore_id, pv.state_id, nx.SnowFrac, nx.HDD_id, qf, qn1, pv.qn1_av,
              pv.dqndt, pv.qn1_s_av, pv.dqnsdt, qn1_S, out->ESTM, &qs, &nx.qn1_av, &nx.dqndt, &nx.qn1_s_av, &nx.dqnsdt,
              deltaQi, &a1, &a2, &a3);
 
@@ -585,6 +596,7 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
    {
       int dt = st->dt_since_start, tp = st->tstep_prev, s1 = st->lv_switch1, s2 = st->lv_switch2;
       nx.estm = st->estm;   /* MODULE ESTM_data variables: advanced in place by every trip */
+      nx.anohm = st->anohm; /* AnOHM's SAVE'd locals likewise */
       *st = nx;
       st->dt_since_start = dt;
       st->tstep_prev = tp;
@@ -674,7 +686,9 @@ void so_cal_multitsteps(SoCtx *cx, const SoParams *p, SoState *st, const double 
    int ir, c;
 #define MET(col) met[(size_t)ir + (size_t)len_sim * (col)]
 #define PUT(blk, col, v) (blk)[(size_t)ir + (size_t)len_sim * (col)] = (v)
+   const int own_grid = (so_met_grid == 0);
    (void)NCOLS_BLK;
+   if (own_grid) { so_met_grid = met; so_met_grid_nrows = len_sim; }
    for (ir = 0; ir < len_sim; ir++) {
       f.iy = (int)MET(0);
       f.id = (int)MET(1);
@@ -728,6 +742,7 @@ void so_cal_multitsteps(SoCtx *cx, const SoParams *p, SoState *st, const double 
       }
       if (cx->fatal_code) break;
    }
+   if (own_grid) { so_met_grid = 0; so_met_grid_nrows = 0; }
 #undef MET
 #undef PUT
 }

@@ -33,7 +33,7 @@ static void OHM_coef_cal(const double sfr[NSURF], double Tair_mav_5d, const doub
 }
 
 /* ohm.f95:271-305 */
-static void OHM_dqndt_cal_X(int dt, int dt_since_start, double qn1_av_prev, double qn1, double dqndt_prev,
+void so_OHM_dqndt_cal_X(int dt, int dt_since_start, double qn1_av_prev, double qn1, double dqndt_prev,
                             double *qn1_av_next, double *dqndt_next)
 {
    const double dt0_thresh = 3600, window_hr = 2;
@@ -47,7 +47,7 @@ static void OHM_dqndt_cal_X(int dt, int dt_since_start, double qn1_av_prev, doub
 }
 
 /* ohm.f95:347-356 */
-static void OHM_QS_cal(double qn1, double dqndt, double a1, double a2, double a3, double *qs)
+void so_OHM_QS_cal(double qn1, double dqndt, double a1, double a2, double a3, double *qs)
 {
    *qs = qn1 * a1 + dqndt * a2 + a3;
 }
@@ -68,16 +68,16 @@ void so_OHM(SoCtx *cx, double qn1, double qn1_av_prev, double dqndt_prev, double
                 SnowFrac, a1, a2, a3);
    *qs = -999;
    if (qn1 > -999) {
-      OHM_dqndt_cal_X(tstep, dt_since_start, qn1_av_prev, qn1, dqndt_prev, qn1_av_next, dqndt_next);
-      OHM_QS_cal(qn1, *dqndt_next, *a1, *a2, *a3, qs);
+      so_OHM_dqndt_cal_X(tstep, dt_since_start, qn1_av_prev, qn1, dqndt_prev, qn1_av_next, dqndt_next);
+      so_OHM_QS_cal(qn1, *dqndt_next, *a1, *a2, *a3, qs);
    } else {
       so_error_hint(cx, 21, "In SUEWS_OHM.f95: bad value for qn1 found during qs calculation.", qn1, -55.55, -55);
    }
    if (SnowUse == 1) {
       for (is = 0; is < NSURF; is++) deltaQi[is] = -999;
       if (qn1_S > -999) {
-         OHM_dqndt_cal_X(tstep, dt_since_start, qn1_s_av_prev, qn1_S, dqnsdt_prev, qn1_s_av_next, dqnsdt_next);
-         OHM_QS_cal(qn1_S, *dqnsdt_next, OHMCOEF(OHM_coef, NSURF, 2, 0), OHMCOEF(OHM_coef, NSURF, 2, 1),
+         so_OHM_dqndt_cal_X(tstep, dt_since_start, qn1_s_av_prev, qn1_S, dqnsdt_prev, qn1_s_av_next, dqnsdt_next);
+         so_OHM_QS_cal(qn1_S, *dqnsdt_next, OHMCOEF(OHM_coef, NSURF, 2, 0), OHMCOEF(OHM_coef, NSURF, 2, 1),
                     OHMCOEF(OHM_coef, NSURF, 2, 2), &deltaQi0);
          for (is = 0; is < NSURF; is++) deltaQi[is] = deltaQi0;
       } else {

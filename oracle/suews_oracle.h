@@ -85,6 +85,16 @@ typedef struct {
    double NewtonConverged;     /* LOGICAL :: converged = .FALSE., SAVE (estm.f95:222): once true, true for ever */
 } SoEstmState;
 
+/* AnOHM (StorageHeatMethod 3) keeps its memory in SAVE'd locals: AnOHM's id_save (suews_phys_anohm.f95:79, the last
+ * day whose forcing had enough daylight rows) and AnOHM_coef's id_save / grid_save / coeff_grid_day(7,3) (:215-216,
+ * the day's coefficients, formed on the first call of a day and reloaded afterwards).  gfortran gives uninitialised
+ * SAVE integers static storage, i.e. 0; coeff_grid_day is initialised to -999. */
+typedef struct {
+   double id_save;                        /* AnOHM */
+   double coef_id_save, coef_grid_save;   /* AnOHM_coef */
+   double coeff_grid_day[21];             /* (7,3) column-major: [is + 7*k] */
+} SoAnohmState;
+
 /* Static per-cell configuration: the INTENT(IN) arguments of SUEWS_cal_Main
  * that do not change from step to step (suews_ctrl_driver.f95:97-285).
  * Arrays keep Fortran column-major storage; see the index macros below. */
@@ -161,6 +171,7 @@ typedef struct {
     * stack slot keeps the previous call's value otherwise (golden snow file: 0 on step 1, 0.18 after) */
    double alb1_hidden;
    SoEstmState estm;
+   SoAnohmState anohm;
 } SoState;
 
 typedef struct {
@@ -262,6 +273,38 @@ void so_OHM(SoCtx *cx, double qn1, double qn1_av_prev, double dqndt_prev, double
             const double soilstore_id[NSURF], const double SoilStoreCap[NSURF], const double state_id[NSURF],
             int SnowUse, const double SnowFrac[NSURF], int DiagQS, double *a1, double *a2, double *a3, double *qs,
             double deltaQi[NSURF]);
+
+void so_OHM_dqndt_cal_X(int dt, int dt_since_start, double qn1_av_prev, double qn1, double dqndt_prev,
+                        double *qn1_av_next, double *dqndt_next);
+void so_OHM_QS_cal(double qn1, double dqndt, double a1, double a2, double a3, double *qs);
+
+/* ---- suews_util_minpack.f95 (the two drivers AnOHM calls) ---- */
+enum { SO_MP_MAXN = 4, SO_MP_MAXM = 96 };
+typedef void (*so_lm_fcn)(int m, int n, const double *x, double *fvec, void *ctx);
+typedef void (*so_hy_fcn)(int n, const double *x, double *fvec, void *ctx);
+int so_lmdif1(so_lm_fcn fcn, void *ctx, int m, int n, double *x, double *fvec, double tol);
+int so_hybrd1(so_hy_fcn fcn, void *ctx, int n, double *x, double *fvec, double tol);
+
+/* ---- suews_phys_anohm.f95 ---- */
+/* MetForcingData_grid of the cell being stepped: [nrows x 24] column-major (the host's whole forcing block,
+ * suews_ctrl_translate.f95:1216), or NULL.  so_cal_multitsteps / so_run_cells point it at their own block unless the
+ * caller set one. */
+extern const double *so_met_grid;
+extern int so_met_grid_nrows;
+void so_AnOHM_coef_land_cal(double ASd, double mSd, double ATa, double mTa, double tau, double mWS, double mWF,
+                            double mAH, double xalb, double xemis, double xcp, double xk, double xch, double xBo,
+                            double *xa1, double *xa2, double *xa3, double *ATs, double *mTs, double *gamma);
+void so_AnOHM_coef_water_cal(double ASd, double mSd, double ATa, double mTa, double tau, double mWS, double mWF,
+                             double mAH, double xalb, double xemis, double xcp, double xk, double xch, double xBo,
+                             double xeta, double xmu, double *xa1, double *xa2, double *xa3, double *ATs, double *mTs,
+                             double *gamma);
+void so_AnOHM_ShapeFit(int m, const double *tHr, const double *obs, double *amp, double *mean, double *tpeak);
+void so_AnOHM(SoCtx *cx, SoAnohmState *an, int tstep, int dt_since_start, double qn1, double qn1_av_prev,
+              double dqndt_prev, double qf, const double *MetForcingData_grid, int nrows,
+              const double moist_surf[NSURF], const double alb[NSURF], const double emis[NSURF],
+              const double cpAnOHM[NSURF], const double kkAnOHM[NSURF], const double chAnOHM[NSURF],
+              const double sfr[NSURF], int EmissionsMethod, int id, int Gridiv, double *qn1_av_next,
+              double *dqndt_next, double *a1, double *a2, double *a3, double *qs, double deltaQi[NSURF]);
 
 /* ---- suews_phys_lumps.f95 ---- */
 void so_LUMPS_cal_QHQE(SoCtx *cx, int veg_type, int snowUse, double qn1, double qf, double qs, double Qm,

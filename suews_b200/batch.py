@@ -171,6 +171,13 @@ class SuewsBatch:
         assert t.shape == (self.nsteps, 13)
         check(self.L.suews_b200_set_estm_forcing(self.h, t.ctypes.data_as(dp), t.shape[0]))
 
+    def set_anohm_forcing(self, met):
+        """AnOHM's MetForcingData_grid ([nrows, 24], the MetForcingBlock columns) when it is not the staged forcing block
+        itself (suews_ctrl_translate.f95:1216); holds until the next set_forcing."""
+        m = np.asfortranarray(np.asarray(met, dtype=np.float64))
+        assert m.ndim == 2 and m.shape[1] == 24
+        check(self.L.suews_b200_set_anohm_forcing(self.h, m.ctypes.data_as(dp), m.shape[0]))
+
     def set_estm_forcing_orig(self, ts_orig, resolution_in=3600, disagg_method=1):
         """ESTM surface temperatures at file resolution [nrows, 13], disaggregated on the device (DisaggregateESTM,
         suews_ctrl_input.f95:1650-1849).  Returns the [nsteps, 13] block the device built."""

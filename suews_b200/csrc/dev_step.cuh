@@ -28,6 +28,7 @@
 #include "dev_rsl.cuh"
 #include "dev_solweig.cuh"
 #include "dev_estm.cuh"
+#include "dev_anohm.cuh"
 
 #ifndef SU_SKIP
 #define SU_SKIP 0
@@ -390,7 +391,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
                           const SuewsStepRec &R, const SuewsEphem &E, int dt_since_start, int tstep_prev,
                           SuewsCellState &S, SuDaily &D, double *acc82_in, double *acc7, const SuLines &L_in, SuewsEstmState *ES = nullptr,
                           const double *ts9 = nullptr, unsigned long long last_lo = 0, unsigned long long last_hi = 0,
-                          bool flux_only = false)
+                          bool flux_only = false, const SuAnohmIn *AN = nullptr)
 {
    // what the variant rules out is ruled out for the compiler as well: no accumulator of the 82-column line and no
    // output line under policy P0, no per-step lines (bar the DailyState row of P1) when only accumulating
@@ -554,8 +555,13 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
                OHM(dg, P, snowUse, sfr, qn1_use, S.qn1_av, S.dqndt, qn1_av_next, dqndt_next, qn1_S, S.qn1_s_av, S.dqnsdt, qn1_s_av_next,
                    dqnsdt_next, dt_since_start, D.HDD_id[9], S.soilstore_id.v, S.state_id.v, SnowFrac_q, a1, a2, a3, qs,
                    deltaQi);
+            } else if (ESTMK != 0 && P.StorageHeatMethod == 3) {
+               // AnOHM (driver.f95:1577-1594); alb is alb_next, the stores are the step's entry values
+               if (ES && AN) AnOHM(dg, P, C, *ES, *AN, R.id, sfr, S.state_id.v, S.StoreDrainPrm.v, D.DecidStoreCap, S.alb.v, qn1_use, qf,
+                                   S.qn1_av, S.dqndt, dt_since_start, qn1_av_next, dqndt_next, a1, a2, a3, qs, deltaQi);
+               else su_fatal(dg, 1003);   // no forcing block with on-the-hour rows behind this call
             } else if (!use_estm) {
-               su_fatal(dg, 1003);   // AnOHM needs module state outside the cal_Main argument list
+               su_fatal(dg, 1003);
             }
          }
          if (use_estm) {

@@ -282,7 +282,7 @@ static const char *fatal_text(int code)
    case 75: return "RunControl.nml: BaseTMethod / TrafficUnits not usable";
    case 1001: return "NetRadiationMethod: Value not usable";
    case 1005: return "StorageHeatMethod 4/14 (ESTM) needs the ESTM state and a surface-temperature forcing block (suews_b200_set_estm_forcing)";
-   case 1003: return "StorageHeatMethod 3 (AnOHM) is not part of this library";
+   case 1003: return "StorageHeatMethod 3 (AnOHM) needs the forcing block's on-the-hour rows (batched API: set the forcing after the classes; the reference-shaped single-step calls do not carry MetForcingData_grid)";
    case 1004: return "EmissionsMethod outside 0-6 / 11-46";
    default: return "Fatal error in SUEWS!";
    }
@@ -297,6 +297,9 @@ struct suews_b200_handle_s {
    std::vector<double> ts5;            // ESTM surface-temperature forcing [nsteps][SUEWS_N_TS5]
    std::vector<double> ts5_block;      // ... as disaggregated on the device, [nsteps x 13] column-major
    double *d_estm = nullptr, *d_ts5 = nullptr;
+   // AnOHM (StorageHeatMethod 3): the on-the-hour rows of the staged forcing block grouped by day of year (dev_anohm.cuh)
+   SuewsHourRec *d_an_hours = nullptr;
+   int *d_an_day = nullptr;   // [3][367]: first row, row count, rows with Sd > 0 of each day of year
    double *d_met_orig = nullptr, *d_met_fast = nullptr;   // forcing at file resolution / disaggregated on the device
    double *d_agg = nullptr;                               // aggregated SUEWS block [rows][87][stride] (thread-slot order)
    double *d_agg_daily = nullptr;                         // DailyState rows of the same launch [rows][50][stride]
@@ -381,6 +384,14 @@ static void to_cell_order(const double *slot_major, double *cell_major, const st
    }
 }
 
+// The storage-scheme record of a fresh batch: zeros, AnOHM's coeff_grid_day = -999. (suews_phys_anohm.f95:216)
+static void init_storage_record(std::vector<double> &v, size_t stride)
+{
+   v.assign((size_t)SUEWS_N_ESTM_DBL * stride, 0.0);
+   const size_t o = offsetof(SuewsEstmState, anohm_coeff_grid_day) / sizeof(double);
+   std::fill(v.begin() + (std::ptrdiff_t)(o * stride), v.begin() + (std::ptrdiff_t)((o + 21) * stride), -999.0);
+}
+
 // A setter called after an advance must not roll the run back: the host mirror of the state (and of the ESTM
 // state) is refreshed from the device first, and the running sums and per-cell diagnostics are kept for the
 // re-upload that follows (they restart from zero only on the first upload or through suews_b200_reset_sums).
@@ -438,6 +449,9 @@ int suews_last_error(int *code, char *buf, int len)
    return tl_err_code;
 }
 
+// (for the other translation units of the library)
+extern "C" int suews_set_last_error(int code, const char *msg) { return set_err(code, "%s", msg); }
+
 int suews_b200_device_count(void)
 {
    int n = 0;
@@ -490,7 +504,7 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
    for (int i = 0; i < 6; i++) cudaFree(h->d_blk[i]);
-   cudaFree(h->d_pack); cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg); cudaFree(h->d_agg_daily);
+   cudaFree(h->d_an_hours); cudaFree(h->d_an_day); cudaFree(h->d_pack); cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg); cudaFree(h->d_agg_daily);
 }
 
 int suews_b200_destroy(suews_b200_handle h)
@@ -572,7 +586,7 @@ int suews_b200_set_state(suews_b200_handle h, const char *name, const double *va
    { int rc_ = pull_live(h); if (rc_) return rc_; }
    h->uploaded = false;
    if (f->kind == 4) {
-      if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
+      if (h->estm.empty()) init_storage_record(h->estm, (size_t)h->stride);
       return set_soa(h->estm, h->stride, h->ncell, f, vals);
    }
    return set_soa(h->state, h->stride, h->ncell, f, vals);
@@ -585,7 +599,7 @@ int suews_b200_get_state(suews_b200_handle h, const char *name, double *vals, in
    if (!f || (f->kind != 3 && f->kind != 4)) return set_err(SUEWS_E_BAD_NAME, "get_state: '%s' is not a state field", name);
    if (n != f->n) return set_err(SUEWS_E_BAD_SIZE, "get_state: '%s' has %d values per cell, got %d", name, f->n, n);
    if (f->kind == 4) {
-      if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
+      if (h->estm.empty()) init_storage_record(h->estm, (size_t)h->stride);
       if (h->uploaded && h->d_estm) {
          CUDA_OK(cudaSetDevice(h->device));
          CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -708,7 +722,7 @@ int suews_b200_upload(suews_b200_handle h)
       const SuewsClassParams &P = h->classes[(size_t)k];
       const int nrm = P.NetRadiationMethod;
       int b = 0;
-      if (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14) b |= 4;
+      if (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14 || P.StorageHeatMethod == 3) b |= 4;   // schemes with a storage record
       if (P.snowUse == 1) b |= 2;
       else if (P.snowUse != 0) b |= 8;
       if (nrm >= 10 && nrm < 100) b |= 1;   // RadMethod: nrm_use >= 10 iterates on the surface temperature (narp.f95:337)
@@ -775,9 +789,9 @@ int suews_b200_upload(suews_b200_handle h)
    CUDA_OK(cudaMemcpy(h->d_tzlist, h->tz_list.data(), sizeof(double) * h->tz_list.size(), cudaMemcpyHostToDevice));
    {   // ESTM state travels only when some class runs ESTM
       bool any_estm = false;
-      for (const auto &P : h->classes) any_estm = any_estm || P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14;
+      for (const auto &P : h->classes) any_estm = any_estm || P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14 || P.StorageHeatMethod == 3;
       if (any_estm) {
-         if (h->estm.empty()) h->estm.assign((size_t)SUEWS_N_ESTM_DBL * h->stride, 0.0);
+         if (h->estm.empty()) init_storage_record(h->estm, (size_t)h->stride);
          CUDA_OK(dev_alloc(&h->d_estm, (size_t)SUEWS_N_ESTM_DBL * st));
          to_slot_order(h->estm.data(), h->xfer.data(), order, SUEWS_N_ESTM_DBL, st);
          CUDA_OK(cudaMemcpy(h->d_estm, h->xfer.data(), sizeof(double) * h->estm.size(), cudaMemcpyHostToDevice));
@@ -819,6 +833,56 @@ int suews_b200_upload(suews_b200_handle h)
    return SUEWS_OK;
 }
 
+// AnOHM reads MetForcingData_grid, the host's whole forcing block of the grid (suews_ctrl_translate.f95:1216): its rows
+// with imin == 0 of the day being fitted (AnOHM_FcLoad, suews_phys_anohm.f95:717-805).  Here: the staged block's
+// on-the-hour rows grouped by day of year, block order kept inside a day, so that a cell reads its day's rows directly.
+// Built only when a class runs StorageHeatMethod 3.  recs == nullptr: the step records are on the device only.
+static int build_anohm_hours(suews_b200_handle h, const SuewsStepRec *recs, size_t n)
+{
+   bool any = false;
+   for (const auto &P : h->classes) any = any || P.StorageHeatMethod == 3;
+   if (!any) {
+      if (h->d_an_hours) { cudaFree(h->d_an_hours); h->d_an_hours = nullptr; }
+      if (h->d_an_day) { cudaFree(h->d_an_day); h->d_an_day = nullptr; }
+      return SUEWS_OK;
+   }
+   std::vector<SuewsStepRec> back;
+   if (!recs) {
+      back.resize(n);
+      CUDA_OK(cudaMemcpy(back.data(), h->d_steps, sizeof(SuewsStepRec) * n, cudaMemcpyDeviceToHost));
+      recs = back.data();
+   }
+   std::vector<int> day(3 * 367, 0);
+   int *first = day.data(), *count = first + 367, *nsun = count + 367;
+   size_t nh = 0;
+   for (size_t i = 0; i < n; i++)
+      if (recs[i].imin == 0 && recs[i].id >= 1 && recs[i].id <= 366) {
+         count[recs[i].id]++;
+         if (recs[i].avkdn > 0) nsun[recs[i].id]++;
+         nh++;
+      }
+   for (int d = 1; d <= 366; d++) {
+      first[d] = first[d - 1] + count[d - 1];
+      if (count[d] > AN_MAXM)
+         return set_err(SUEWS_E_NOT_IMPL, "AnOHM: the forcing block holds %d on-the-hour rows of day of year %d (at most %d: stage one year at a time)", count[d], d, AN_MAXM);
+   }
+   std::vector<SuewsHourRec> hours(nh ? nh : 1);
+   std::vector<int> fill(367, 0);
+   for (size_t i = 0; i < n; i++)
+      if (recs[i].imin == 0 && recs[i].id >= 1 && recs[i].id <= 366) {
+         const SuewsStepRec &r = recs[i];
+         SuewsHourRec &q = hours[(size_t)(first[r.id] + fill[r.id]++)];
+         q.id = (double)r.id; q.tHr = (double)r.it; q.Sd = r.avkdn; q.Ta = r.Temp_C; q.RH = r.avRh; q.pres = r.Press_hPa;
+         q.WS = r.avU1; q.qf_obs = r.qf_obs;
+      }
+   if (h->d_an_hours) { cudaFree(h->d_an_hours); h->d_an_hours = nullptr; }
+   CUDA_OK(cudaMalloc((void **)&h->d_an_hours, sizeof(SuewsHourRec) * hours.size()));
+   CUDA_OK(cudaMemcpy(h->d_an_hours, hours.data(), sizeof(SuewsHourRec) * hours.size(), cudaMemcpyHostToDevice));
+   if (!h->d_an_day) CUDA_OK(cudaMalloc((void **)&h->d_an_day, sizeof(int) * day.size()));
+   CUDA_OK(cudaMemcpy(h->d_an_day, day.data(), sizeof(int) * day.size(), cudaMemcpyHostToDevice));
+   return SUEWS_OK;
+}
+
 int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
 {
    if (!h || !met || nsteps <= 0) return set_err(SUEWS_E_BAD_ARG, "set_forcing: bad arguments");
@@ -850,7 +914,20 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps)
    h->nsteps = nsteps;
    h->ts5_nsteps = 0;   // a surface-temperature block belongs to one forcing block
    if (h->d_met_fast) { cudaFree(h->d_met_fast); h->d_met_fast = nullptr; }
-   return SUEWS_OK;
+   return build_anohm_hours(h, recs, n);
+}
+
+// AnOHM's MetForcingData_grid given explicitly ([nrows x 24] column-major, the MetForcingBlock column layout) instead of
+// the staged forcing block: for hosts that stage the forcing in pieces (the reference-shaped single-step call) while the
+// reference's AnOHM sees the grid's whole block (suews_ctrl_translate.f95:1216).  Call it after set_forcing; the next
+// set_forcing goes back to its own block.
+int suews_b200_set_anohm_forcing(suews_b200_handle h, const double *met, int nrows)
+{
+   if (!h || !met || nrows <= 0 || !h->uploaded) return set_err(SUEWS_E_BAD_ARG, "set_anohm_forcing: bad arguments (upload and set the forcing first)");
+   CUDA_OK(cudaSetDevice(h->device));
+   std::vector<SuewsStepRec> recs((size_t)nrows);
+   for (int i = 0; i < nrows; i++) pack_step(recs[(size_t)i], met, (size_t)nrows, (size_t)i);
+   return build_anohm_hours(h, recs.data(), (size_t)nrows);
 }
 
 // Forcing at its original resolution: disaggregated to the model timestep on the device.
@@ -904,7 +981,7 @@ int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int
    CUDA_OK(cudaStreamSynchronize(h->stream));
    h->nsteps = (int)nfast;
    h->ts5_nsteps = 0;
-   return SUEWS_OK;
+   return build_anohm_hours(h, nullptr, nfast);
 }
 
 // The disaggregated MetForcingBlock [nsteps x 24], column-major, as the device holds it
@@ -1063,6 +1140,8 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.blkSUEWS = h->d_blk[0]; a.blkSnow = h->d_blk[1]; a.blkRSL = h->d_blk[2]; a.blkDaily = h->d_blk[3]; a.blkSOL = h->d_blk[4];
    a.blkESTM = h->d_estm ? h->d_blk[5] : nullptr;
    a.estm = h->d_estm;
+   a.an_hours = h->d_an_hours;
+   a.an_day = h->d_an_day;
    a.ts5 = (h->d_estm && h->ts5_nsteps == h->nsteps) ? h->d_ts5 + (size_t)step0 * SUEWS_N_TS5 : nullptr;
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
    a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;

@@ -83,10 +83,15 @@
 // ---- ESTM state: what MODULE ESTM_data carries from call to call (the *_grids copies, estm.f95:1587-1603, and
 // the SAVE'd HVAC, Tair2Set and NewtonPolynomial's `converged`).  A separate SoA [field][cell], resident only when
 // a class runs StorageHeatMethod 4/14.  Tw_4 is (layer, wall) column-major with leading dimension 5.
+// The same record carries what AnOHM (StorageHeatMethod 3) keeps in SAVE'd locals (suews_phys_anohm.f95:79, :215-216): the last
+// day of year with enough daylight rows, the day and grid of the cached coefficients, and coeff_grid_day(7,3) (initially
+// -999) -- the record is "the storage-heat scheme's memory outside the SUEWS_cal_Main argument list" and is resident when
+// a class runs StorageHeatMethod 3, 4 or 14.
 #define SUEWS_ESTM_STATE_FIELDS(X) \
    X(Tair2, 1) X(Tievolve, 1) X(lup_ground, 1) X(lup_wall, 1) X(lup_roof, 1) X(T0_ibld, 1) X(T0_ground, 1) \
    X(T0_wall, 1) X(T0_roof, 1) X(TN_wall, 1) X(TN_roof, 1) X(Tground, 5) X(Twall, 5) X(Troof, 5) X(Tibld, 5) \
-   X(Tw_4, 20) X(HVAC, 1) X(Tair2Set, 1) X(NewtonConverged, 1)
+   X(Tw_4, 20) X(HVAC, 1) X(Tair2Set, 1) X(NewtonConverged, 1) \
+   X(anohm_id_save, 1) X(anohm_coef_id_save, 1) X(anohm_coef_grid_save, 1) X(anohm_coeff_grid_day, 21)
 
 #define SUEWS_COUNT_X(name, n) +(n)
 enum {

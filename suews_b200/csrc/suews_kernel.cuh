@@ -60,6 +60,10 @@ struct SuRunArgs {
    // surface-temperature forcing [nsteps][SUEWS_N_TS5], offset to step0; NULL when no class runs ESTM
    double *estm;
    const double *ts5;
+   // AnOHM (StorageHeatMethod 3): the forcing block's on-the-hour rows grouped by day of year and their index [3][367]
+   // (dev_anohm.cuh); its per-cell memory is part of the `estm` record.  NULL when no class runs AnOHM
+   const SuewsHourRec *an_hours;
+   const int *an_day;
    // output policy P1 (SUEWS_OUT_AGG): the SUEWS block aggregated over every agg_nlines steps as SUEWS_Output_Agg
    // does (suews_ctrl_output.f95:912-957), [row][87][stride] indexed by thread slot so that a warp writes 256 B lines
    double *agg;
@@ -194,6 +198,8 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    int cls = 0, tz = 0;
    SuewsEstmState ES;
    const bool estm_on = (ESTMK != 0) && a.estm;
+   SuAnohmIn an_in;
+   an_in.hours = a.an_hours; an_in.day_first = a.an_day; an_in.day_count = a.an_day + 367; an_in.day_nsun = a.an_day + 734;
    if (active && estm_on) {
       double *ep = reinterpret_cast<double *>(&ES);
 #pragma unroll 1
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
                                             (K != SU_K_P0 && (a.agg || (a.sums && !a.sum7))) ? acc : nullptr,
                                             ((K == SU_K_P0 || !a.agg) && a.sums && a.sum7) ? acc7 : nullptr, L,
                                             estm_on ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
-                                            a.flux_only != 0);
+                                            a.flux_only != 0, (estm_on && a.an_hours) ? &an_in : nullptr);
          if (K != SU_K_P0) {
             if (day_end) {
                if (live && dg.fatal == 0 && n_day_rows < a.agg_daily_rows) {

@@ -24,6 +24,8 @@
 #include <strings.h>
 #include <vector>
 
+extern "C" int suews_set_last_error(int code, const char *msg);   // suews_b200.cu
+
 namespace {
 
 enum { SU_ARG_INT = 0, SU_ARG_DBL = 1 };
@@ -78,6 +80,9 @@ struct {
 // lower-cased variable name.  Parameters are set by the host (suews_estm_data_set) where the reference runs
 // ESTM_initials / SUEWS_Translate; the element temperatures come back here after every call.
 std::map<std::string, std::vector<double>> g_estm;
+// MetForcingData_grid for AnOHM (suews_anohm_set_met_grid): [g_an_rows x 24] column-major, empty = none
+std::vector<double> g_an_met;
+int g_an_rows = 0;
 std::string lower(const char *s)
 {
    std::string r(s ? s : "");
@@ -93,6 +98,17 @@ int ensure_handle()
       suews_b200_set_tstep_prev_rolls(g_h, 0);   // tstep_prev is INTENT(IN): the same value for every step of a call
    }
    return suews_b200_restart(g_h);   // every call passes all of its arguments: nothing of the previous call is kept
+}
+
+// AnOHM's SAVE'd locals (suews_phys_anohm.f95:79, :215-216) are process-wide in the reference: they ride in the same
+// name-keyed store as MODULE ESTM_data, created on the first call that selects StorageHeatMethod 3
+void anohm_saves()
+{
+   if (g_estm.count("anohm_id_save")) return;
+   g_estm["anohm_id_save"] = {0.0};
+   g_estm["anohm_coef_id_save"] = {0.0};
+   g_estm["anohm_coef_grid_save"] = {0.0};
+   g_estm["anohm_coeff_grid_day"] = std::vector<double>(21, -999.0);
 }
 
 // Push every argument that is a library field (parameters and evolving state) into the batch.
@@ -177,6 +193,7 @@ int run_rows(const double *met, int len_sim, int dt_since_start, int tstep_prev,
    int rc = suews_b200_set_clock(g_h, dt_since_start, tstep_prev);
    if (!rc) rc = suews_b200_upload(g_h);
    if (!rc) rc = suews_b200_set_forcing(g_h, met, len_sim);
+   if (!rc && g_an_rows > 0) rc = suews_b200_set_anohm_forcing(g_h, g_an_met.data(), g_an_rows);
    if (!rc && ts5_ir) {   // Ts5mindata_ir is one row, used for every step of the block (driver.f95:3044, :3475)
       std::vector<double> ts((size_t)len_sim * 13);
       for (int c = 0; c < 13; c++)
@@ -256,6 +273,9 @@ int suews_cal_multitsteps_c(void *const *args, int nargs)
    const int i_shm = find_arg(kMultiArgs, kNMulti, "StorageHeatMethod"), i_ts5 = find_arg(kMultiArgs, kNMulti, "Ts5mindata_ir");
    const int shm = (i_shm >= 0 && args[i_shm]) ? *(const int *)args[i_shm] : 0;
    const double *ts5 = ((shm == 4 || shm == 14) && i_ts5 >= 0) ? (const double *)args[i_ts5] : nullptr;
+   if (shm == 3) anohm_saves();
+   rc = shm == 3 ? push_fields(kMultiArgs, kNMulti, args) : 0;
+   if (rc) return rc;
    const int run_rc = run_rows(met, *len_sim, *(const int *)args[i_dt], *(const int *)args[i_tp], blk, ts5, shm == 4);
    if (run_rc >= SUEWS_E_NO_DEVICE) return run_rc;
    rc = pull_state(kMultiArgs, kNMulti, args);
@@ -293,6 +313,13 @@ int suews_cal_main_c(void *const *args, int nargs)
    const int i_shm = find_arg(kMainArgs, kNMain, "StorageHeatMethod"), i_ts5 = find_arg(kMainArgs, kNMain, "Ts5mindata_ir");
    const int shm = (i_shm >= 0 && args[i_shm]) ? *(const int *)args[i_shm] : 0;
    const double *ts5 = ((shm == 4 || shm == 14) && i_ts5 >= 0) ? (const double *)args[i_ts5] : nullptr;
+   if (shm == 3) {
+      if (g_an_rows <= 0)
+         return suews_set_last_error(1003, "StorageHeatMethod 3 (AnOHM): hand MetForcingData_grid over with suews_anohm_set_met_grid before suews_cal_main");
+      anohm_saves();
+      rc = push_fields(kMainArgs, kNMain, args);
+      if (rc) return rc;
+   }
    const int run_rc = run_rows(met, 1, *(const int *)args[i_dt], *(const int *)args[i_tp], blk, ts5, shm == 4 || shm == 14);
    if (run_rc >= SUEWS_E_NO_DEVICE) return run_rc;
    rc = pull_state(kMainArgs, kNMain, args);
@@ -512,6 +539,19 @@ int suews_estm_data_set(const char *name, const double *vals, int n)
    g_estm[lower(name)].assign(vals, vals + n);
    return SUEWS_OK;
 }
+int suews_anohm_set_met_grid(const double *met, int nrows)
+{
+   std::lock_guard<std::mutex> lk(g_mu);
+   if (!met || nrows <= 0) {
+      g_an_met.clear();
+      g_an_rows = 0;
+      return SUEWS_OK;
+   }
+   g_an_met.assign(met, met + (size_t)nrows * 24);
+   g_an_rows = nrows;
+   return SUEWS_OK;
+}
+
 int suews_estm_data_get(const char *name, double *vals, int n)
 {
    std::lock_guard<std::mutex> lk(g_mu);

@@ -183,6 +183,19 @@ class _SuewsDriver:
             if rc != 0:
                 raise SuewsError(rc, "estm_data_set: '%s' (%d values) is not an ESTM_data variable of that size" % (name, a.size))
 
+    def anohm_set_met_grid(self, met=None):
+        """MetForcingData_grid for calls with StorageHeatMethod 3 (AnOHM): the grid's forcing block [nrows, 24], which the
+        reference passes as an assumed-shape argument (suews_ctrl_driver.f95:277); None forgets it."""
+        L = lib()
+        L.suews_anohm_set_met_grid.argtypes = [C.POINTER(C.c_double), C.c_int]
+        if met is None:
+            L.suews_anohm_set_met_grid(None, 0)
+            return
+        m = np.asfortranarray(np.asarray(met, dtype=np.float64))
+        if m.ndim != 2 or m.shape[1] != 24:
+            raise ValueError("MetForcingData_grid is [nrows, 24]")
+        L.suews_anohm_set_met_grid(m.ctypes.data_as(C.POINTER(C.c_double)), m.shape[0])
+
     def estm_data_get(self, name, n=1):
         L = lib()
         L.suews_estm_data_get.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int]

@@ -15,11 +15,15 @@ SCHEMES = {
                  roughlenheatmethod=2, roughlenmommethod=2, smdmethod=0, waterusemethod=0),
 }
 # the scheme sweep of BASELINE.json configs[3] / SURVEY 8d(iv): one switch changed against the default set
-for _name, _over in (("estm", dict(storageheatmethod=4)), ("stab2", dict(stabilitymethod=2)), ("stab4", dict(stabilitymethod=4)),
+for _name, _over in (("estm", dict(storageheatmethod=4)), ("anohm", dict(storageheatmethod=3)), ("stab2", dict(stabilitymethod=2)), ("stab4", dict(stabilitymethod=4)),
                      ("netrad13", dict(netradiationmethod=13)), ("netrad300", dict(netradiationmethod=300))):
     SCHEMES[_name] = dict(SCHEMES["default"], **_over)
 
 C2K = float(np.float32(273.15))
+
+# AnOHM columns (AnOHM_Cp, AnOHM_Kk, AnOHM_Ch) of Test/BaseRun/2020b/Input/SUEWS_NonVeg.txt (codes 551, 552, 553),
+# SUEWS_Veg.txt and SUEWS_Water.txt; the 2020b argument dump carries zeros because AnOHM is off in that run
+ANOHM_EXAMPLE = dict(cpanohm=[2e6, 2e6, 1e6, 1e6, 1e6, 2e6, 4.1e6], kkanohm=[1.2] * 7, chanohm=[4.0] * 7)
 
 
 def estm_example(surface_area, **over):
@@ -99,6 +103,8 @@ def base_with_scheme(base, scheme="default"):
     d = {k.lower(): v for k, v in base.items()}
     for k, v in SCHEMES[scheme].items():
         d[k] = [v]
+    if SCHEMES[scheme]["storageheatmethod"] == 3:
+        d.update({k: list(v) for k, v in ANOHM_EXAMPLE.items()})
     if SCHEMES[scheme]["snowuse"] == 0:
         # a snow-free start: the BaseRun dump starts with snow on the ground
         for k in ("snowpack", "snowfrac", "snowwater"):

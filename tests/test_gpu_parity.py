@@ -1003,3 +1003,124 @@ def test_specialised_p0_instances_equal_the_generic_kernel(scheme):
     assert np.array_equal(res[0][3], res[1][3])
     for nm in res[0][1]:
         assert np.array_equal(res[0][1][nm], res[1][1][nm], equal_nan=True), nm
+
+
+# ---- AnOHM (StorageHeatMethod 3): the once-a-day fit runs inside the kernel; its memory is per-cell state
+ANOHM_VARIANTS = [{}, {"snowuse": 0, "netradiationmethod": 3, "emissionsmethod": 2},
+                  {"snowuse": 0, "netradiationmethod": 3, "emissionsmethod": 0, "ohmincqf": 1}]
+
+
+def _anohm_case(over):
+    from suews_b200 import synth
+    d = fx.state_init(2005)
+    d.update({k: list(v) for k, v in synth.ANOHM_EXAMPLE.items()})
+    d["storageheatmethod"] = [3]
+    for k, v in over.items():
+        d[k] = [v]
+    if d["snowuse"][0] == 0:
+        for k in ("snowpack", "snowfrac", "snowwater"):
+            d[k] = [0.0] * 7
+    return d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("over", ANOHM_VARIANTS, ids=lambda o: "-".join("%s%s" % kv for kv in o.items()) or "baserun")
+def test_anohm_two_days_match_oracle(over):
+    """Full output of 2 days + 20 steps (three fits: the first step, and the first step of each new day), the DailyState
+    row's a1/a2/a3 and AnOHM's memory, against the oracle whose MetForcingData_grid is the same block."""
+    from suews_b200 import OUT_FULL, SuewsBatch
+    d = _anohm_case(over)
+    n = 288 * 2 + 20
+    met = fx.forcing(2005)[:n]
+    cell = ol.Cell(d)
+    ref = cell.run(met, want=("SUEWS", "DailyState"))
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, n, OUT_FULL)
+    out = b.block("SUEWS", 0, n)
+    assert np.array_equal(out[:, :5], ref["SUEWS"][:, :5])
+    e = rel_err(out[:, 5:], ref["SUEWS"][:, 5:], "SUEWS")
+    print("AnOHM %s: worst rel err %.3e" % (over, float(e.max())))
+    assert float(e.max()) <= TOL_DAY1, (float(e.max()), np.unravel_index(e.argmax(), e.shape))
+    od, rd = b.block("DailyState", 0, n), ref["DailyState"]
+    assert np.array_equal(od == -999.0, rd == -999.0)
+    np.testing.assert_allclose(od[:, -3:], rd[:, -3:], rtol=1e-10, atol=0)
+    for name in ("anohm_id_save", "anohm_coef_id_save", "anohm_coef_grid_save"):
+        assert np.array_equal(b.get_state(name)[0], cell.get_state(name)), name
+    np.testing.assert_allclose(b.get_state("anohm_coeff_grid_day")[0], cell.get_state("anohm_coeff_grid_day"), rtol=1e-10, atol=0)
+    for name in ("qn1_av", "dqndt", "state_id", "soilstore_id"):
+        np.testing.assert_allclose(b.get_state(name)[0], cell.get_state(name), rtol=1e-10, atol=1e-13, err_msg=name)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_anohm_many_cells_policy_p0_and_launch_boundaries():
+    """Perturbed cells (fractions, location, morphology, forcing offsets) under policy P0, advanced in three launches that
+    cut a day in two (the fit's memory must carry over), each against its own oracle run; the forcing block is staged
+    once, so every launch sees the same MetForcingData_grid."""
+    from suews_b200 import OUT_SUM7, SuewsBatch, synth
+    base = fx.state_init(2005)
+    n = 288 * 2
+    met = fx.forcing(2005)[:n]
+    nc = 40
+    b = SuewsBatch(nc, 1)
+    _missing, site = synth.build_batch(b, base, cell0=500, scheme="anohm")
+    b.upload()
+    b.set_forcing(met)
+    for s0, s1 in ((0, 100), (100, 400), (400, n)):
+        b.advance(s0, s1 - s0, OUT_SUM7)
+    sums = b.sums()
+    fatal, _warn, _it = b.diag()
+    assert (fatal == 0).all()
+    d0 = synth.base_with_scheme(base, "anohm")
+    worst = 0.0
+    for c in range(0, nc, 4):
+        dd = dict(d0)
+        for k in ("sfr", "lat", "lng", "bldgH", "EveTreeH", "DecTreeH", "Z"):
+            dd[k.lower()] = np.atleast_1d(site[k][c])
+        m = met.copy()
+        m[:, 11] += site["dTemp_C"][c]
+        m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + site["dRH"][c]))
+        cell = ol.Cell(dd)
+        ref = cell.run(m, want=("SUEWS",))["SUEWS"][:, 5:].sum(axis=0)
+        for nm, col in PARITY_COLS.items():
+            err = abs(sums[c, col] - ref[col]) / max(abs(ref[col]), 1e-30)
+            worst = max(worst, err)
+            assert err <= TOL_SUM, (c, nm, sums[c, col], ref[col])
+        np.testing.assert_allclose(b.get_state("anohm_coeff_grid_day")[c], cell.get_state("anohm_coeff_grid_day"), rtol=1e-9, atol=0)
+    print("AnOHM cells: worst flux-sum rel err %.3e" % worst)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_anohm_explicit_met_grid_and_too_many_rows():
+    """set_anohm_forcing: a forcing staged in pieces with the whole block handed over as MetForcingData_grid gives the
+    whole-block run; a block with more than 24 on-the-hour rows of one day of year (two years) is refused."""
+    from suews_b200 import OUT_FULL, SuewsBatch, SuewsError
+    d = _anohm_case(ANOHM_VARIANTS[1])
+    n = 288 + 50
+    met = fx.forcing(2005)[:n]
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(met)
+    b.advance(0, n, OUT_FULL)
+    whole = b.block("SUEWS", 0, n).copy()
+    b.close()
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    parts = []
+    for s0 in range(0, n, 97):
+        s1 = min(n, s0 + 97)
+        b.set_forcing(met[s0:s1])
+        b.set_anohm_forcing(met)
+        b.advance(0, s1 - s0, OUT_FULL)
+        parts.append(b.block("SUEWS", 0, s1 - s0).copy())
+    assert np.array_equal(np.vstack(parts), whole)
+    two_years = np.vstack([met[:288], met[:288]])
+    with pytest.raises(SuewsError):
+        b.set_forcing(two_years)
+    b.close()

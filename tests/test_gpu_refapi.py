@@ -227,3 +227,58 @@ def test_dropin_package_serves_the_reference_import():
     finally:
         sys.path.pop(0)
         sys.modules.pop("supy_driver", None)
+
+
+def _anohm_dump():
+    from suews_b200 import synth
+    d = fx.state_init(2005)
+    d.update({k: list(v) for k, v in synth.ANOHM_EXAMPLE.items()})
+    d["storageheatmethod"] = [3]
+    return d
+
+
+def test_anohm_through_the_reference_shaped_calls():
+    """StorageHeatMethod 3 through suews_cal_multitsteps (MetForcingData_grid = its own MetForcingBlock; a chunked second
+    call continues with the process-wide SAVE'd coefficients) and step by step through suews_cal_main with the grid's
+    block handed over by anohm_set_met_grid; without it the single-step call refuses (1003)."""
+    from suews_b200 import SuewsError
+    from suews_b200.supy_driver import suews_driver as sd
+    sd.reset_hidden_state()
+    sd.anohm_set_met_grid(None)
+    d = _anohm_dump()
+    n = 288 + 30
+    met = fx.forcing(2005)[:n]
+    cell = ol.Cell(d)
+    ref = cell.run(met, want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
+    kw = _kwargs(d, 1)
+    outs = sd.suews_cal_multitsteps(metforcingblock=met, len_sim=n, **kw)
+    _check_blocks(outs, ref, n)
+    assert np.allclose(sd.estm_data_get("anohm_coeff_grid_day", 21), cell.get_state("anohm_coeff_grid_day"), rtol=1e-10, atol=0)
+    assert sd.estm_data_get("anohm_coef_id_save", 1)[0] == cell.get_state("anohm_coef_id_save")[0]
+
+    # single steps: the first 20 steps of the same run, the whole block as MetForcingData_grid
+    sd.reset_hidden_state()
+    kw = _kwargs(d, 0)
+    cols = {"iy": 0, "id": 1, "it": 2, "imin": 3, "qn1_obs": 4, "qs_obs": 7, "qf_obs": 8, "avu1": 9, "avrh": 10, "temp_c": 11,
+            "press_hpa": 12, "precip": 13, "avkdn": 14, "snowfrac_obs": 15, "ldown_obs": 16, "fcld_obs": 17, "wu_m3": 18,
+            "xsmd": 19, "lai_obs": 20}
+    tstep = int(kw["tstep"][0])
+
+    def step(i):
+        for k, c in cols.items():
+            kw[k] = np.array([met[i, c]], dtype=kw[k].dtype)
+        kw["isec"] = np.array([0], dtype=np.int32)
+        return sd.suews_cal_main(**kw)
+    with pytest.raises(SuewsError) as e:
+        step(0)
+    assert e.value.code == 1003
+    sd.anohm_set_met_grid(met)
+    kw = _kwargs(d, 0)
+    for i in range(20):
+        line = step(i)
+        r = ref["SUEWS"][i:i + 1, 5:]
+        err = rel_err(line[1][None, :], r, "SUEWS")
+        assert err.max() <= TOL_DAY1, (i, float(err.max()))
+        kw["dt_since_start"] = kw["dt_since_start"] + tstep
+    sd.anohm_set_met_grid(None)
+    sd.reset_hidden_state()
