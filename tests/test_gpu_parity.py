@@ -497,16 +497,18 @@ def test_sun_position_entry_point():
 def test_fatal_error_is_reported_not_aborted():
     """RunControl errors surface as SuewsError (the reference STOPs, supy_driver raises RuntimeError)"""
     from suews_b200 import OUT_SUM82, SuewsBatch, SuewsError
-    d = fx.state_init(2005)
-    d["storageheatmethod"] = [3]
-    b = SuewsBatch(1, 1)
-    b.load_reference_args(d)
-    b.upload()
-    b.set_forcing(fx.forcing(2005)[:12])
-    with pytest.raises(SuewsError) as ei:
-        b.advance(0, 12, OUT_SUM82)
-    assert ei.value.code == 1003
-    b.close()
+    for key, val, code in (("storageheatmethod", 2, 1003),      # no such storage-heat scheme
+                           ("netradiationmethod", 7, 1001)):    # RadMethod's bare STOP (narp.f95:95-99)
+        d = fx.state_init(2005)
+        d[key] = [val]
+        b = SuewsBatch(1, 1)
+        b.load_reference_args(d)
+        b.upload()
+        b.set_forcing(fx.forcing(2005)[:12])
+        with pytest.raises(SuewsError) as ei:
+            b.advance(0, 12, OUT_SUM82)
+        assert ei.value.code == code
+        b.close()
 
 
 # ---- ESTM (StorageHeatMethod 4/14): parity unpinned -- no ESTM output of the reference exists; CUDA == oracle

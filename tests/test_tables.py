@@ -1,0 +1,89 @@
+"""The table join (suews_b200/tables.py: InitializeSurfaceCharacteristics + SUEWS_Translate) against the reference's own
+argument dumps of the same run: Test/BaseRun/2020b's input tables -> every table-derived argument of
+test1_{2004,2005}_state_init.txt, exactly."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fixtures as fx  # noqa: E402
+
+from suews_b200 import tables  # noqa: E402
+
+RUN = os.path.join(fx.GOLDEN, "baserun_2020b")
+
+# arguments of the dump that do not come from the tables: clock, forcing row, evolving state (InitialState / the previous
+# year's end), and the arguments the 2020b dump predates
+NOT_TABLE = {"iy", "id", "it", "imin", "isec", "dt_since_start", "tstep_prev", "avkdn", "avrh", "avu1", "fcld_obs", "lai_obs",
+             "ldown_obs", "precip", "press_hpa", "qf_obs", "qh_obs", "qn1_obs", "qs_obs", "snowfrac_obs", "temp_c", "wu_m3", "xsmd",
+             "qn1_av", "dqndt", "qn1_s_av", "dqnsdt", "snowfallcum", "snowalb", "icefrac", "snowwater", "snowdens", "snowfrac",
+             "snowpack", "soilstore_id", "state_id", "gdd_id", "sdd_id", "lai_id", "tmin_id", "tmax_id", "lenday_id",
+             "decidcap_id", "albdectr_id", "albevetr_id", "albgrass_id", "porosity_id", "hdd_id", "wuday_id", "tair_av"}
+
+
+@pytest.mark.parametrize("year", [2004, 2005])
+def test_table_join_lands_on_the_reference_argument_dump(year):
+    rc = tables.read_runcontrol(os.path.join(RUN, "RunControl.nml"))
+    tabs = tables.load_tables(os.path.join(RUN, "Input"))
+    a = tables.site_arguments(tabs, rc, grid=1, year=year)
+    aux = a.pop("_aux")
+    dump = fx.state_init(year)
+    dump = {k: v for k, v in dump.items() if k not in fx.DUMP_DEFAULTS}
+    checked = 0
+    for k, want in dump.items():
+        if k in NOT_TABLE:
+            continue
+        assert k in a, "argument %s of the dump is not produced by the join" % k
+        got = np.asarray(a[k], dtype=np.float64)
+        want = np.asarray(want, dtype=np.float64)
+        assert got.shape == want.shape, (k, got.shape, want.shape)
+        if k == "alb":              # the vegetation albedos of the first step come from the daily state (translate.f95:1147)
+            got, want = got[[0, 1, 5, 6]], want[[0, 1, 5, 6]]
+        if k == "storedrainprm":    # StoreDrainPrm(6, DecTr) is the deciduous capacity of the day
+            keep = np.ones(42, bool)
+            keep[5 + 6 * 3] = False
+            got, want = got[keep], want[keep]
+        assert np.array_equal(got, want), (k, got, want)
+        checked += 1
+    assert checked >= 140, checked
+    # the join produces nothing the argument list does not have (bar the arguments the 2020b dump predates)
+    extra = set(a) - set(dump) - set(fx.DUMP_DEFAULTS) - {"irrfracpaved", "irrfracbldgs", "irrfracbsoil", "irrfracwater", "h_maintain",
+                                                          "basetmethod"}
+    assert not extra, extra
+    assert aux["waterdepth"] > 0 and aux["grid"] == 1 and aux["year"] == year
+
+
+def test_run_arguments_reproduce_the_first_step_of_2004():
+    """run directory -> (table join + InitialState) -> the complete first-step argument set of the reference's 2004 leg."""
+    a, aux, rc = tables.run_arguments(RUN, grid=1, year=2004,
+                                      initial_conditions=os.path.join(RUN, "Input", "InitialConditionstest_2004.nml"))
+    dump = fx.state_init(2004)
+    skip = {"iy", "id", "it", "imin", "isec", "avkdn", "avrh", "avu1", "fcld_obs", "lai_obs", "ldown_obs", "precip", "press_hpa",
+            "qf_obs", "qh_obs", "qn1_obs", "qs_obs", "snowfrac_obs", "temp_c", "wu_m3", "xsmd"}
+    n = 0
+    for k, want in dump.items():
+        if k in skip or k in fx.DUMP_DEFAULTS:
+            continue
+        assert k in a, k
+        assert np.array_equal(np.asarray(a[k], dtype=np.float64), np.asarray(want, dtype=np.float64)), (k, a[k], want)
+        n += 1
+    assert n >= 180, n
+    assert rc["tstep"] == 300
+
+
+def test_header_and_code_errors_are_the_references():
+    tabs = tables.load_tables(os.path.join(RUN, "Input"))
+    rc = tables.read_runcontrol(os.path.join(RUN, "RunControl.nml"))
+    with pytest.raises(tables.TableError):
+        tables.site_arguments(tabs, rc, grid=1, year=1999)               # no such SiteSelect row
+    bad = tables.Table(os.path.join(RUN, "Input", "SUEWS_Soil.txt"), tables.HEADERS["SUEWS_Soil.txt"])
+    bad.rows = bad.rows[:0]
+    broken = dict(tabs, Soil=bad)
+    with pytest.raises(tables.TableError) as e:
+        tables.site_arguments(broken, rc, grid=1, year=2005)             # a code that matches no row: ErrorHint 57
+    assert "57" in str(e.value)
+    with pytest.raises(tables.TableError) as e:
+        tables.Table(os.path.join(RUN, "Input", "SUEWS_Soil.txt"), tables.HEADERS["SUEWS_Conductance.txt"])   # ErrorHint 56
+    assert "56" in str(e.value)

@@ -20,6 +20,9 @@ and committed.  Nothing here is reference *code*: only its test data.
                                 the state the reference wrote at the end of its 2004 leg (105 408 steps) and of its 2005
                                 leg (1 440 steps): NextInitial, suews_ctrl_init.f95:2022-2149, list-directed, 17
                                 significant digits -- i.e. the exact doubles (Test/BaseRun/2020b/Input/)
+  baserun_2020b/RunControl.nml, baserun_2020b/Input/SUEWS_*.txt, ESTMinput.nml, InitialConditionstest_2004.nml
+                                the run directory of the same golden run: the code-keyed input tables the state_init
+                                dumps were translated from
 """
 import json, os, re, shutil
 
@@ -81,6 +84,15 @@ def main():
     for src, dst in cp:
         shutil.copyfile(f"{REF}/{src}", os.path.join(OUT, dst))
         os.chmod(os.path.join(OUT, dst), 0o644)
+    # the input tables and RunControl.nml of the same run: what suews_b200/tables.py joins (tests/test_tables.py)
+    run = os.path.join(OUT, "baserun_2020b")
+    os.makedirs(os.path.join(run, "Input"), exist_ok=True)
+    shutil.copyfile(f"{REF}/2020b/RunControl.nml", os.path.join(run, "RunControl.nml"))
+    for fn in sorted(os.listdir(f"{REF}/2020b/Input")):
+        if fn.startswith("SUEWS_") and fn.endswith(".txt") or fn in ("ESTMinput.nml", "InitialConditionstest_2004.nml"):
+            shutil.copyfile(f"{REF}/2020b/Input/{fn}", os.path.join(run, "Input", fn))
+            os.chmod(os.path.join(run, "Input", fn), 0o644)
+    os.chmod(os.path.join(run, "RunControl.nml"), 0o644)
     print("golden files in", OUT)
 
 

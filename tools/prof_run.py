@@ -18,9 +18,12 @@ scheme = sys.argv[3] if len(sys.argv) > 3 else "default"
 row0 = int(sys.argv[4]) if len(sys.argv) > 4 else 120   # start at 10:00 so day-time physics is in the sample
 base, met = bench.load_inputs(max(2, (row0 + 3 * nsteps + 287) // 288))
 b = SuewsBatch(ncell, 1)
-synth.build_batch(b, base, scheme=scheme)
+ts5 = synth.estm_ts_forcing(met[: row0 + 3 * nsteps]) if synth.SCHEMES[scheme]["storageheatmethod"] in (4, 14) else None
+synth.build_batch(b, base, scheme=scheme, ts_row0=None if ts5 is None else ts5[0])
 b.upload()
 b.set_forcing(met[: row0 + 3 * nsteps])
+if ts5 is not None:
+    b.set_estm_forcing(ts5)
 if row0 > 0:
     b.advance(0, row0, OUT)
 import ctypes as C
