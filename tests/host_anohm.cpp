@@ -2,6 +2,30 @@
 // compiles, with the device qualifiers defined away, so tests/test_anohm_oracle.py can compare it with the oracle without
 // a GPU.  Test infrastructure; built by the test into a temporary directory.
 #define SU_ANOHM_HOST 1
+#ifdef SU_ANOHM_ULP
+// -DSU_ANOHM_ULP: every sin / cos / atan / exp result moved by one ulp, up or down, for a pseudo-random two thirds of the
+// arguments -- what another libm may return.  The test measures how far the fitted coefficients move (the tolerance of the
+// GPU parity tests for this scheme rests on that number).
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+static inline double ulp_shift(double r, double x)
+{
+   uint64_t b;
+   memcpy(&b, &x, 8);
+   b ^= b >> 29; b *= 0x9E3779B97F4A7C15ull; b ^= b >> 32;
+   const int k = (int)(b % 3);
+   return k == 0 ? r : nextafter(r, k == 1 ? INFINITY : -INFINITY);
+}
+static inline double p_sin(double x) { return ulp_shift(sin(x), x); }
+static inline double p_cos(double x) { return ulp_shift(cos(x), x); }
+static inline double p_atan(double x) { return ulp_shift(atan(x), x); }
+static inline double p_exp(double x) { return ulp_shift(exp(x), x); }
+#define sin p_sin
+#define cos p_cos
+#define atan p_atan
+#define exp p_exp
+#endif
 #include "../suews_b200/csrc/dev_anohm.cuh"
 #include <vector>
 

@@ -230,10 +230,10 @@ def test_bowen_ratio_is_the_closed_form_its_residual_reduces_to():
     assert np.all(np.isfinite(out))
 
 
-def _host_lib(tmp_path_factory):
+def _host_lib(tmp_path_factory, *defs):
     src = os.path.join(ol.ROOT, "tests", "host_anohm.cpp")
     out = str(tmp_path_factory.mktemp("host_anohm") / "host_anohm.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src])
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", *defs, "-o", out, src])
     return C.CDLL(out)
 
 
@@ -268,3 +268,30 @@ def test_device_code_on_the_host_equals_the_oracle_bit_for_bit(host_lib, dT, dRH
         host_lib.an_host_day_coefs(P(hrs), hrs.shape[0], day, dT, dRH, em, qf, P(moist), P(ALB), P(EMIS), P(CP), P(KK), P(CH), P(b))
         assert np.all(np.isfinite(a)), day
         assert np.array_equal(a, b), (day, a, b)
+
+
+def test_the_fit_amplifies_last_ulp_differences_of_libm(host_lib, tmp_path_factory):
+    """Why the GPU parity tests of this scheme cannot hold 1e-10: the sinusoid fit stops at a relative tolerance of 1e-5
+    (anohm.f95:972) with a forward-difference Jacobian of step 1.5e-8 |x| (fdjac2), so a last-ulp difference in sin / cos /
+    exp -- CUDA's libm against glibc's, or one glibc against another under the reference itself -- moves the iterates by
+    ~1e-8 and can move the stopping point.  Measured here with the same source and libm results shifted by one ulp:
+    the day's coefficients move by ~1e-7 (median) and up to a few 1e-4 on single days.  The GPU tests therefore bound this
+    scheme's outputs at 1e-5 per step and say so; the algorithm itself is pinned by the bit-for-bit test above."""
+    ulp = _host_lib(tmp_path_factory, "-DSU_ANOHM_ULP")
+    for lib in (host_lib, ulp):
+        lib.an_host_day_coefs.argtypes = [dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double] + [dp] * 7
+    met = fx.forcing(2004)
+    hrs = np.ascontiguousarray(met[met[:, 3] == 0][:, [1, 2, 14, 11, 10, 12, 9, 8]])
+    rng = np.random.default_rng(0)
+    moved = []
+    for day in range(1, 367, 3):
+        moist = rng.uniform(0.05, 1.2, 7)
+        qf = rng.uniform(5, 60)
+        a, b = np.zeros(21), np.zeros(21)
+        for lib, o in ((host_lib, a), (ulp, b)):
+            lib.an_host_day_coefs(P(hrs), hrs.shape[0], day, 0.0, 0.0, 2, qf, P(moist), P(ALB), P(EMIS), P(CP), P(KK), P(CH), P(o))
+        moved.append(float(np.max(np.abs(a - b) / np.maximum(np.abs(a), 1e-3))))
+    moved = np.array(moved)
+    print("AnOHM coefficients under one-ulp libm shifts: median %.1e, 90%% %.1e, max %.1e" % (np.median(moved), np.percentile(moved, 90), moved.max()))
+    assert np.median(moved) > 1e-10          # far above the 1e-10 of the other schemes: the fit is the amplifier
+    assert moved.max() < 1e-2                # ... and still a small change of the coefficients

