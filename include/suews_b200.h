@@ -133,6 +133,15 @@ int suews_b200_get_estm_forcing_block(suews_b200_handle h, double *ts_fast, int 
  * as a single-grid run of the reference. */
 int suews_b200_set_anohm_forcing(suews_b200_handle h, const double *met, int nrows);
 
+/* BLUEWS, the convective boundary-layer slab model (suews_phys_bluews.f95; the reference's grid loop runs it after every
+ * SUEWS_cal_Main, suews_ctrl_calculations.f95:194-218).  Class fields: CBLuse (RunControl.nml) and CBLInput.nml's
+ * EntrainmentType, QH_choice (1 SUEWS, 2 LUMPS), isubs, CO2_included, InitialData_use (2), sondeflag (0), wsb.  The slab's
+ * variables are per-cell state of kind SUEWS_KIND_ESTM_STATE (cbl_blh_m, cbl_tm_K, cbl_qm_kgkg, cbl_tp_K, cbl_qp_kgkg, cbl_cm,
+ * cbl_gamt_Km, cbl_gamq_kgkgm).  ini is IniCBLdata, the rows of CBL_initial_data.txt ([nline x 8] row-major: DOY zi0 gamt
+ * gamq theta+ q+ theta q), shared by the batch.  Output: the "BL" group of get_block ([nsteps x 22]: the five date columns,
+ * z theta q theta+ q+ Temp_C rh QH_use QE_use Press_hPa avu1 UStar avdens lv_J_kg avcp gamt gamq), policy SUEWS_OUT_FULL. */
+int suews_b200_set_cbl_initial(suews_b200_handle h, const double *ini, int nline);
+
 /* Advance all cells over forcing rows [step0, step0 + nsteps).  One kernel launch.  Asynchronous
  * with respect to the host; suews_b200_sync waits and returns the first fatal cell error (0 if none). */
 int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags);

@@ -54,6 +54,11 @@ static const SoField PARAM_FIELDS[] = {
    PDE(ivf_fi), PDE(zibld), PDE(kibld), PDE(ribld), PDE(zwall), PDE(kwall), PDE(rwall), PDE(zroof), PDE(kroof),
    PDE(rroof), PDE(zground), PDE(kground), PDE(rground), PDE(nroom), PDE(alb_ibld), PDE(em_ibld), PDE(CH_iroof),
    PDE(CH_iwall), PDE(CH_ibld), PDE(AreaWall), PDE(Tfloor),
+   /* CBLInput.nml (suews_phys_bluews.f95:300-357) and RunControl's CBLuse */
+   {"CBLuse", 1, offsetof(SoParams, cbl.CBLuse), 1}, {"EntrainmentType", 1, offsetof(SoParams, cbl.EntrainmentType), 1},
+   {"QH_choice", 1, offsetof(SoParams, cbl.QH_choice), 1}, {"isubs", 1, offsetof(SoParams, cbl.isubs), 1},
+   {"CO2_included", 1, offsetof(SoParams, cbl.CO2_included), 1}, {"InitialData_use", 1, offsetof(SoParams, cbl.InitialData_use), 1},
+   {"sondeflag", 1, offsetof(SoParams, cbl.sondeflag), 1}, {"wsb", 0, offsetof(SoParams, cbl.wsb), 1},
 };
 #undef PD
 #undef PI
@@ -74,6 +79,11 @@ static const SoField STATE_FIELDS[] = {
    {"anohm_id_save", 0, offsetof(SoState, anohm.id_save), 1}, {"anohm_coef_id_save", 0, offsetof(SoState, anohm.coef_id_save), 1},
    {"anohm_coef_grid_save", 0, offsetof(SoState, anohm.coef_grid_save), 1},
    {"anohm_coeff_grid_day", 0, offsetof(SoState, anohm.coeff_grid_day), 21},
+   /* MODULE cbl_MODULE between calls (suews_phys_bluews.f95:24-47) */
+   {"cbl_blh_m", 0, offsetof(SoState, cbl.blh_m), 1}, {"cbl_tm_K", 0, offsetof(SoState, cbl.tm_K), 1},
+   {"cbl_qm_kgkg", 0, offsetof(SoState, cbl.qm_kgkg), 1}, {"cbl_tp_K", 0, offsetof(SoState, cbl.tp_K), 1},
+   {"cbl_qp_kgkg", 0, offsetof(SoState, cbl.qp_kgkg), 1}, {"cbl_cm", 0, offsetof(SoState, cbl.cm), 1},
+   {"cbl_gamt_Km", 0, offsetof(SoState, cbl.gamt_Km), 1}, {"cbl_gamq_kgkgm", 0, offsetof(SoState, cbl.gamq_kgkgm), 1},
 };
 #undef SD
 #undef SI
@@ -186,6 +196,10 @@ int so_run(const SoParams *p, SoState *st, const double *met, int len_sim, doubl
 /* ESTM forcing block for the next so_run / so_run_cells: [len_sim x 13] column-major (iy id it imin Tiair Tsurf
  * Troof Troad Twall Twall_n Twall_e Twall_s Twall_w), or NULL.  The pointer is borrowed. */
 void so_set_ts5_block(const double *ts5) { so_ts5_block = ts5; }
+
+/* BLUEWS: the initial-data table (IniCBLdata, [nline x 8] row-major; borrowed) and an output block for so_run */
+void so_set_cbl_initial(const double *ini, int nline) { so_cbl_ini = ini; so_cbl_ini_nline = ini ? nline : 0; }
+void so_set_bl_block(double *blk) { so_blk_BL = blk; }
 
 /* MetForcingData_grid for AnOHM: [nrows x 24] column-major, or NULL (then so_run uses its own block).  Borrowed. */
 void so_set_met_grid(const double *met, int nrows) { so_met_grid = met; so_met_grid_nrows = met ? nrows : 0; }

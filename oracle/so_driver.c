@@ -581,6 +581,7 @@ void so_cal_main(SoCtx *cx, const SoParams *p, const SoForcing *f, SoState *st, 
       i_iter = i_iter + 1;
    }
    cx->n_iter_last = i_iter - 1;
+   cx->last_avcp = avcp; cx->last_avdens = avdens; cx->last_lv_J_kg = lv_J_kg;   /* MODULE moist after the call */
 
    /* diagnostics no flux sum and no state depends on (T2, q2, U10, RH2 and the SOLWEIG point values): counted apart */
    SO_CNT_DIAG_BEGIN();
@@ -714,6 +715,17 @@ void so_cal_multitsteps(SoCtx *cx, const SoParams *p, SoState *st, const double 
 
       so_cal_main(cx, p, &f, st, &out);
       st->dt_since_start = st->dt_since_start + p->tstep;
+
+      /* BLUEWS after the step (suews_ctrl_calculations.f95:194-218): QH / QE of SUEWS (columns 9, 10) or of LUMPS (11, 12),
+       * UStar = column 55 */
+      if (p->cbl.CBLuse >= 1 && !cx->fatal_code) {
+         double line[22], qh_use = out.SUEWS[8], qe_use = out.SUEWS[9];
+         if (p->cbl.QH_choice == 2) { qh_use = out.SUEWS[10]; qe_use = out.SUEWS[11]; }
+         so_CBL(cx, &p->cbl, &st->cbl, &f, out.datetimeLine[4], p->tstep, qh_use, qe_use, out.SUEWS[54], cx->last_avdens,
+                cx->last_lv_J_kg, cx->last_avcp, line);
+         if (so_blk_BL)
+            for (c = 0; c < 22; c++) so_blk_BL[(size_t)ir + (size_t)len_sim * c] = line[c];
+      }
 
       if (blkDaily) {
          for (c = 0; c < 5; c++) PUT(blkDaily, c, out.datetimeLine[c]);

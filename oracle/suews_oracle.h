@@ -95,6 +95,15 @@ typedef struct {
    double coeff_grid_day[21];             /* (7,3) column-major: [is + 7*k] */
 } SoAnohmState;
 
+/* BLUEWS (suews_phys_bluews.f95): CBLInput.nml, and the slab's variables in MODULE cbl_MODULE between calls */
+typedef struct {
+   int CBLuse, EntrainmentType, QH_choice, isubs, CO2_included, InitialData_use, sondeflag;
+   double wsb;
+} SoCblParams;
+typedef struct {
+   double blh_m, tm_K, qm_kgkg, tp_K, qp_kgkg, cm, gamt_Km, gamq_kgkgm;
+} SoCblState;
+
 /* Static per-cell configuration: the INTENT(IN) arguments of SUEWS_cal_Main
  * that do not change from step to step (suews_ctrl_driver.f95:97-285).
  * Arrays keep Fortran column-major storage; see the index macros below. */
@@ -133,6 +142,7 @@ typedef struct {
    double AHProf_24hr[48], HumActivity_24hr[48], PopProf_24hr[48], TraffProf_24hr[48];
    double WUProfA_24hr[48], WUProfM_24hr[48];
    SoEstmParams estm;
+   SoCblParams cbl;
 } SoParams;
 
 #define PROF24(p, hr, col) ((p)[(hr) + 24 * (col)])       /* col 0 = weekday, 1 = weekend */
@@ -172,6 +182,7 @@ typedef struct {
    double alb1_hidden;
    SoEstmState estm;
    SoAnohmState anohm;
+   SoCblState cbl;
 } SoState;
 
 typedef struct {
@@ -194,6 +205,9 @@ typedef struct {
    /* hidden Lat_vap SAVE state lives in SoState; a pointer to the active one */
    int *lv_switch1, *lv_switch2;
    int n_iter_last; /* diagnostics: Tsurf iterations used by the last step */
+   /* what the last SUEWS_cal_Main left in MODULE moist (driver.f95: use moist, only: avcp, avdens, lv_J_kg) and its
+    * friction velocity: the inputs of BLUEWS (suews_ctrl_calculations.f95:194-218) */
+   double last_avcp, last_avdens, last_lv_J_kg;
 } SoCtx;
 
 void so_ctx_init(SoCtx *cx);
@@ -305,6 +319,13 @@ void so_AnOHM(SoCtx *cx, SoAnohmState *an, int tstep, int dt_since_start, double
               const double cpAnOHM[NSURF], const double kkAnOHM[NSURF], const double chAnOHM[NSURF],
               const double sfr[NSURF], int EmissionsMethod, int id, int Gridiv, double *qn1_av_next,
               double *dqndt_next, double *a1, double *a2, double *a3, double *qs, double deltaQi[NSURF]);
+
+/* ---- suews_phys_bluews.f95 ---- */
+extern const double *so_cbl_ini;   /* IniCBLdata [nline x 8] row-major, or NULL */
+extern int so_cbl_ini_nline;
+extern double *so_blk_BL;          /* optional [len_sim x 22] column-major block filled by so_cal_multitsteps */
+void so_CBL(SoCtx *cx, const SoCblParams *p, SoCblState *s, const SoForcing *f, double dectime, int tstep, double qh_use,
+            double qe_use, double UStar, double avdens, double lv_J_kg, double avcp, double line22[22]);
 
 /* ---- suews_phys_lumps.f95 ---- */
 void so_LUMPS_cal_QHQE(SoCtx *cx, int veg_type, int snowUse, double qn1, double qf, double qs, double Qm,

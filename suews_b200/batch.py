@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, dp, ip
 
-NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50, "SOLWEIG": 31, "ESTM": 32}
+NCOL = {"SUEWS": 87, "snow": 103, "RSL": 138, "DailyState": 50, "SOLWEIG": 31, "ESTM": 32, "BL": 22}
 OUT_SUM82 = 1
 OUT_FULL = 2
 OUT_SUM7 = 4   # only the seven parity fluxes (output policy P0)
@@ -170,6 +170,13 @@ class SuewsBatch:
         t = np.asfortranarray(np.asarray(ts5, dtype=np.float64))
         assert t.shape == (self.nsteps, 13)
         check(self.L.suews_b200_set_estm_forcing(self.h, t.ctypes.data_as(dp), t.shape[0]))
+
+    def set_cbl_initial(self, ini):
+        """BLUEWS: the rows of CBL_initial_data.txt, [nline, 8] (DOY zi0 gamt gamq theta+ q+ theta q), shared by the batch
+        (IniCBLdata, suews_phys_bluews.f95:319-341)."""
+        t = np.ascontiguousarray(np.asarray(ini, dtype=np.float64))
+        assert t.ndim == 2 and t.shape[1] == 8
+        check(self.L.suews_b200_set_cbl_initial(self.h, t.ctypes.data_as(dp), t.shape[0]))
 
     def set_anohm_forcing(self, met):
         """AnOHM's MetForcingData_grid ([nrows, 24], the MetForcingBlock columns) when it is not the staged forcing block
@@ -401,5 +408,7 @@ def estm_names():
                   "AreaWall"}
         names |= {"ivf_" + a + b for a in "iwrf" for b in "iwrf"}
         names |= {p + e for p in "zkr" for e in ("ibld", "wall", "roof", "ground")}
+        # CBLInput.nml / RunControl's CBLuse (BLUEWS runs beside SUEWS_cal_Main, not inside its argument list)
+        names |= {"CBLuse", "EntrainmentType", "QH_choice", "isubs", "CO2_included", "InitialData_use", "sondeflag", "wsb"}
         _ESTM_NAMES = names
     return _ESTM_NAMES

@@ -57,6 +57,9 @@ struct SuewsHourRec {
 struct SuAnohmIn {
    const SuewsHourRec *hours;
    const int *day_first, *day_count, *day_nsun;   // [367], index = day of year (0 unused)
+   // (the record also carries BLUEWS's shared table: IniCBLdata [cbl_nline][8] row-major, dev_bluews.cuh)
+   const double *cbl_ini;
+   int cbl_nline;
 };
 
 struct AnDay {

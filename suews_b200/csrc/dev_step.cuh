@@ -29,6 +29,7 @@
 #include "dev_solweig.cuh"
 #include "dev_estm.cuh"
 #include "dev_anohm.cuh"
+#include "dev_bluews.cuh"
 
 #ifndef SU_SKIP
 #define SU_SKIP 0
@@ -99,7 +100,7 @@ static __device__ unsigned long long su_phase_clk[16];
 
 // Optional per-step output lines (reference layouts).  NULL = not wanted.
 struct SuLines {
-   double *datetime5, *suews82, *snow98, *rsl133, *daily45, *sol26, *estm27;
+   double *datetime5, *suews82, *snow98, *rsl133, *daily45, *sol26, *estm27, *bl17;
 };
 
 // Tsurf-independent quantities of a step
@@ -397,7 +398,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    // output line under policy P0, no per-step lines (bar the DailyState row of P1) when only accumulating
    double *const acc82 = (K == 2) ? nullptr : acc82_in;
    SuLines L = L_in;
-   if (K != 0) { L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.sol26 = nullptr; L.estm27 = nullptr; }
+   if (K != 0) { L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.sol26 = nullptr; L.estm27 = nullptr; L.bl17 = nullptr; }
    if (K == 2) L.daily45 = nullptr;
    const double *sfr = C.sfr.v;
    const int sm = P.StabilityMethod;
@@ -557,7 +558,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
                    deltaQi);
             } else if (ESTMK != 0 && P.StorageHeatMethod == 3) {
                // AnOHM (driver.f95:1577-1594); alb is alb_next, the stores are the step's entry values
-               if (ES && AN) AnOHM(dg, P, C, *ES, *AN, R.id, sfr, S.state_id.v, S.StoreDrainPrm.v, D.DecidStoreCap, S.alb.v, qn1_use, qf,
+               if (ES && AN && AN->hours) AnOHM(dg, P, C, *ES, *AN, R.id, sfr, S.state_id.v, S.StoreDrainPrm.v, D.DecidStoreCap, S.alb.v, qn1_use, qf,
                                    S.qn1_av, S.dqndt, dt_since_start, qn1_av_next, dqndt_next, a1, a2, a3, qs, deltaQi);
                else su_fatal(dg, 1003);   // no forcing block with on-the-hour rows behind this call
             } else if (!use_estm) {
@@ -731,6 +732,13 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    if ((R.it * 3600 + R.imin * 60 + P.tstep) >= 86400) SU_SDP(S.StoreDrainPrm.v, 5, DECID) = D.DecidStoreCap;
    S.lv_switch = (double)lv_sw;
    S.alb1_hidden = Rd.alb1;
+   // BLUEWS (suews_ctrl_calculations.f95:194-218): after the step, from its QH / QE (SUEWS's or LUMPS's), UStar and the
+   // moist-air values of the last trip
+   if (ESTMK != 0 && P.CBLuse >= 1) {
+      if (ES && AN) BLUEWS(dg, P, *ES, AN->cbl_ini, AN->cbl_nline, R, (P.QH_choice == 2) ? Lm.QH_LUMPS : qh, (P.QH_choice == 2) ? Lm.QE_LUMPS : qe,
+                           UStar, A.avdens, A.lv_J_kg, A.avcp, L.bl17);
+      else su_fatal(dg, 1007);
+   }
 
    // output policy P0: running sums of the seven parity fluxes only -- QN, QF, QS, QH, QE, RO, SWE,
    // the same values the 82-column line carries in columns 6-10, 17 and 72

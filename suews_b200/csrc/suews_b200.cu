@@ -281,6 +281,7 @@ static const char *fatal_text(int code)
    case 73: return "RunControl.nml:EmissionsMethod unusable";
    case 75: return "RunControl.nml: BaseTMethod / TrafficUnits not usable";
    case 1001: return "NetRadiationMethod: Value not usable";
+   case 1007: return "BLUEWS (CBLuse >= 1) needs the initial-data table (suews_b200_set_cbl_initial) with a row for the day, InitialData_use = 2 and sondeflag = 0";
    case 1005: return "StorageHeatMethod 4/14 (ESTM) needs the ESTM state and a surface-temperature forcing block (suews_b200_set_estm_forcing)";
    case 1003: return "StorageHeatMethod: 0, 1, 3, 4 and 14 are available; AnOHM (3) needs the forcing block's on-the-hour rows (batched API: classes first, then the forcing; reference-shaped single steps: suews_anohm_set_met_grid)";
    case 1004: return "EmissionsMethod outside 0-6 / 11-46";
@@ -340,9 +341,11 @@ struct suews_b200_handle_s {
    long long *d_iters = nullptr;
    SuewsStepRec *d_steps = nullptr;
    SuewsEphem *d_ephem = nullptr;
-   double *d_blk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SUEWS, snow, RSL, DailyState, SOLWEIG, ESTM
+   double *d_blk[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SUEWS, snow, RSL, DailyState, SOLWEIG, ESTM, BL
+   double *d_cbl_ini = nullptr;   // BLUEWS: IniCBLdata [cbl_nline][8] row-major
+   int cbl_nline = 0;
    int blk_nsteps = 0;
-   size_t blk_cap[6] = {0, 0, 0, 0, 0, 0};
+   size_t blk_cap[7] = {0, 0, 0, 0, 0, 0, 0};
    cudaStream_t stream = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    int first_fatal_code = 0, first_fatal_cell = -1;
@@ -503,7 +506,8 @@ static void free_dev(suews_b200_handle h)
    cudaFree(h->d_classes); cudaFree(h->d_cls); cudaFree(h->d_tz); cudaFree(h->d_fatal); cudaFree(h->d_cellp);
    cudaFree(h->d_state); cudaFree(h->d_sums); cudaFree(h->d_tzlist); cudaFree(h->d_warn); cudaFree(h->d_iters);
    cudaFree(h->d_steps); cudaFree(h->d_ephem); cudaFree(h->d_order);
-   for (int i = 0; i < 6; i++) cudaFree(h->d_blk[i]);
+   for (int i = 0; i < 7; i++) cudaFree(h->d_blk[i]);
+   cudaFree(h->d_cbl_ini);
    cudaFree(h->d_an_hours); cudaFree(h->d_an_day); cudaFree(h->d_pack); cudaFree(h->d_estm); cudaFree(h->d_ts5); cudaFree(h->d_met_orig); cudaFree(h->d_met_fast); cudaFree(h->d_agg); cudaFree(h->d_agg_daily);
 }
 
@@ -722,7 +726,7 @@ int suews_b200_upload(suews_b200_handle h)
       const SuewsClassParams &P = h->classes[(size_t)k];
       const int nrm = P.NetRadiationMethod;
       int b = 0;
-      if (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14 || P.StorageHeatMethod == 3) b |= 4;   // schemes with a storage record
+      if (P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14 || P.StorageHeatMethod == 3 || P.CBLuse >= 1) b |= 4;   // schemes with a record of their own
       if (P.snowUse == 1) b |= 2;
       else if (P.snowUse != 0) b |= 8;
       if (nrm >= 10 && nrm < 100) b |= 1;   // RadMethod: nrm_use >= 10 iterates on the surface temperature (narp.f95:337)
@@ -789,7 +793,7 @@ int suews_b200_upload(suews_b200_handle h)
    CUDA_OK(cudaMemcpy(h->d_tzlist, h->tz_list.data(), sizeof(double) * h->tz_list.size(), cudaMemcpyHostToDevice));
    {   // ESTM state travels only when some class runs ESTM
       bool any_estm = false;
-      for (const auto &P : h->classes) any_estm = any_estm || P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14 || P.StorageHeatMethod == 3;
+      for (const auto &P : h->classes) any_estm = any_estm || P.StorageHeatMethod == 4 || P.StorageHeatMethod == 14 || P.StorageHeatMethod == 3 || P.CBLuse >= 1;
       if (any_estm) {
          if (h->estm.empty()) init_storage_record(h->estm, (size_t)h->stride);
          CUDA_OK(dev_alloc(&h->d_estm, (size_t)SUEWS_N_ESTM_DBL * st));
@@ -928,6 +932,19 @@ int suews_b200_set_anohm_forcing(suews_b200_handle h, const double *met, int nro
    std::vector<SuewsStepRec> recs((size_t)nrows);
    for (int i = 0; i < nrows; i++) pack_step(recs[(size_t)i], met, (size_t)nrows, (size_t)i);
    return build_anohm_hours(h, recs.data(), (size_t)nrows);
+}
+
+// BLUEWS: IniCBLdata (CBL_ReadInputData, suews_phys_bluews.f95:319-341), [nline x 8] row-major: day of year, zi0, gamt [K m-1],
+// gamq [g kg-1 m-1], theta+ [K], q+ [g kg-1], theta [K], q [g kg-1]; shared by all cells of the batch.
+int suews_b200_set_cbl_initial(suews_b200_handle h, const double *ini, int nline)
+{
+   if (!h || !ini || nline <= 0) return set_err(SUEWS_E_BAD_ARG, "set_cbl_initial: bad arguments");
+   CUDA_OK(cudaSetDevice(h->device));
+   if (h->d_cbl_ini) { cudaFree(h->d_cbl_ini); h->d_cbl_ini = nullptr; }
+   CUDA_OK(cudaMalloc((void **)&h->d_cbl_ini, sizeof(double) * 8 * (size_t)nline));
+   CUDA_OK(cudaMemcpy(h->d_cbl_ini, ini, sizeof(double) * 8 * (size_t)nline, cudaMemcpyHostToDevice));
+   h->cbl_nline = nline;
+   return SUEWS_OK;
 }
 
 // Forcing at its original resolution: disaggregated to the model timestep on the device.
@@ -1069,10 +1086,13 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    CUDA_OK(cudaSetDevice(h->device));
    const bool full = (out_flags & SUEWS_OUT_FULL) != 0;
    if (full) {
-      const int ncol[6] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5,
-                           SUEWS_NCOL_ESTM + 5};
-      for (int i = 0; i < 6; i++) {
+      const int ncol[7] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5,
+                           SUEWS_NCOL_ESTM + 5, SUEWS_NCOL_BL + 5};
+      bool any_cbl = false;
+      for (const auto &P : h->classes) any_cbl = any_cbl || P.CBLuse >= 1;
+      for (int i = 0; i < 7; i++) {
          if (i == 5 && !h->d_estm) continue;   // the ESTM block exists only when ESTM runs
+         if (i == 6 && !any_cbl) continue;     // ... and the BL block only with BLUEWS
          size_t cnt = (size_t)h->ncell * (size_t)nsteps * (size_t)ncol[i];
          if (h->blk_cap[i] < cnt) {
             CUDA_OK(dev_alloc(&h->d_blk[i], cnt));
@@ -1142,6 +1162,9 @@ int suews_b200_advance(suews_b200_handle h, int step0, int nsteps, int out_flags
    a.estm = h->d_estm;
    a.an_hours = h->d_an_hours;
    a.an_day = h->d_an_day;
+   a.cbl_ini = h->d_cbl_ini;
+   a.cbl_nline = h->cbl_nline;
+   a.blkBL = (full && h->d_estm) ? h->d_blk[6] : nullptr;
    a.ts5 = (h->d_estm && h->ts5_nsteps == h->nsteps) ? h->d_ts5 + (size_t)step0 * SUEWS_N_TS5 : nullptr;
    a.ncell = h->ncell; a.stride = h->stride; a.nsteps = nsteps;
    a.dt_since_start = h->dt_since_start; a.tstep_prev = h->tstep_prev; a.tstep = h->tstep;
@@ -1399,11 +1422,11 @@ int suews_b200_reset_sums(suews_b200_handle h)
 int suews_b200_get_block(suews_b200_handle h, const char *group, int cell, double *block, int nsteps, int ncol)
 {
    if (!h || !group || !block) return set_err(SUEWS_E_BAD_ARG, "null argument");
-   const char *names[6] = {"SUEWS", "snow", "RSL", "DailyState", "SOLWEIG", "ESTM"};
-   const int ncols[6] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5,
-                         SUEWS_NCOL_ESTM + 5};
+   const char *names[7] = {"SUEWS", "snow", "RSL", "DailyState", "SOLWEIG", "ESTM", "BL"};
+   const int ncols[7] = {SUEWS_NCOL_SUEWS + 5, SUEWS_NCOL_SNOW + 5, SUEWS_NCOL_RSL + 5, SUEWS_NCOL_DAILY + 5, SUEWS_NCOL_SOLWEIG + 5,
+                         SUEWS_NCOL_ESTM + 5, SUEWS_NCOL_BL + 5};
    int g = -1;
-   for (int i = 0; i < 6; i++)
+   for (int i = 0; i < 7; i++)
       if (strcasecmp(group, names[i]) == 0) g = i;
    if (g < 0) return set_err(SUEWS_E_BAD_NAME, "get_block: unknown group '%s'", group);
    if (!h->d_blk[g] || nsteps != h->blk_nsteps || ncol != ncols[g] || cell < 0 || cell >= h->ncell)

@@ -24,7 +24,9 @@
    X(RoughLenMomMethod, 1) X(SMDMethod, 1) X(snowUse, 1) X(StabilityMethod, 1) X(StorageHeatMethod, 1) \
    X(tstep, 1) X(veg_type, 1) X(WaterUseMethod, 1) X(LAIType, 3) \
    /* MODULE ESTM_data (suews_phys_estm.f95:1-176): ESTMinput.nml switches and layer counts */ \
-   X(evolveTibld, 1) X(TsurfChoice, 1) X(ibldCHmod, 1) X(Nibld, 1) X(Nwall, 1) X(Nroof, 1) X(Nground, 1)
+   X(evolveTibld, 1) X(TsurfChoice, 1) X(ibldCHmod, 1) X(Nibld, 1) X(Nwall, 1) X(Nroof, 1) X(Nground, 1) \
+   /* BLUEWS (suews_phys_bluews.f95): RunControl's CBLuse and CBLInput.nml */ \
+   X(CBLuse, 1) X(EntrainmentType, 1) X(QH_choice, 1) X(isubs, 1) X(CO2_included, 1) X(InitialData_use, 1) X(sondeflag, 1)
 
 // ---- class-level doubles
 #define SUEWS_CLASS_DBL_FIELDS(X) \
@@ -51,7 +53,8 @@
    X(ivf_if, 1) X(ivf_ww, 1) X(ivf_wr, 1) X(ivf_wi, 1) X(ivf_wf, 1) X(ivf_rw, 1) X(ivf_ri, 1) X(ivf_rf, 1) \
    X(ivf_fw, 1) X(ivf_fr, 1) X(ivf_fi, 1) X(zibld, 5) X(kibld, 5) X(ribld, 5) X(zwall, 5) X(kwall, 5) X(rwall, 5) \
    X(zroof, 5) X(kroof, 5) X(rroof, 5) X(zground, 5) X(kground, 5) X(rground, 5) X(nroom, 1) X(alb_ibld, 1) \
-   X(em_ibld, 1) X(CH_iroof, 1) X(CH_iwall, 1) X(CH_ibld, 1) X(Tfloor, 1)
+   X(em_ibld, 1) X(CH_iroof, 1) X(CH_iwall, 1) X(CH_ibld, 1) X(Tfloor, 1) \
+   X(wsb, 1) /* BLUEWS: subsidence velocity (CBLInput.nml) */
 
 // ---- per-cell doubles (the SUEWS_SiteSelect.txt site columns)
 // HOT fields are the small per-surface arrays every stage of a step indexes with a run-time surface number: on the device
@@ -91,7 +94,9 @@
    X(Tair2, 1) X(Tievolve, 1) X(lup_ground, 1) X(lup_wall, 1) X(lup_roof, 1) X(T0_ibld, 1) X(T0_ground, 1) \
    X(T0_wall, 1) X(T0_roof, 1) X(TN_wall, 1) X(TN_roof, 1) X(Tground, 5) X(Twall, 5) X(Troof, 5) X(Tibld, 5) \
    X(Tw_4, 20) X(HVAC, 1) X(Tair2Set, 1) X(NewtonConverged, 1) \
-   X(anohm_id_save, 1) X(anohm_coef_id_save, 1) X(anohm_coef_grid_save, 1) X(anohm_coeff_grid_day, 21)
+   X(anohm_id_save, 1) X(anohm_coef_id_save, 1) X(anohm_coef_grid_save, 1) X(anohm_coeff_grid_day, 21) \
+   /* BLUEWS: MODULE cbl_MODULE between calls (suews_phys_bluews.f95:24-47) */ \
+   X(cbl_blh_m, 1) X(cbl_tm_K, 1) X(cbl_qm_kgkg, 1) X(cbl_tp_K, 1) X(cbl_qp_kgkg, 1) X(cbl_cm, 1) X(cbl_gamt_Km, 1) X(cbl_gamq_kgkgm, 1)
 
 #define SUEWS_COUNT_X(name, n) +(n)
 enum {
@@ -110,7 +115,7 @@ enum {
 // Output widths without the 5 datetime columns (suews_ctrl_const.f95:49-55)
 enum {
    SUEWS_NCOL_SUEWS = 82, SUEWS_NCOL_SNOW = 98, SUEWS_NCOL_ESTM = 27, SUEWS_NCOL_RSL = 133,
-   SUEWS_NCOL_SOLWEIG = 26, SUEWS_NCOL_DAILY = 45, SUEWS_NCOL_MET = 24
+   SUEWS_NCOL_SOLWEIG = 26, SUEWS_NCOL_DAILY = 45, SUEWS_NCOL_MET = 24, SUEWS_NCOL_BL = 17
 };
 
 // ---- structs generated from the lists

@@ -64,6 +64,11 @@ struct SuRunArgs {
    // (dev_anohm.cuh); its per-cell memory is part of the `estm` record.  NULL when no class runs AnOHM
    const SuewsHourRec *an_hours;
    const int *an_day;
+   // BLUEWS (CBLuse >= 1): IniCBLdata [cbl_nline][8] shared by the batch; its slab variables are part of the `estm` record
+   // and its output line goes to blkBL (policy P2), [nsteps x 22] per cell
+   const double *cbl_ini;
+   int cbl_nline;
+   double *blkBL;
    // output policy P1 (SUEWS_OUT_AGG): the SUEWS block aggregated over every agg_nlines steps as SUEWS_Output_Agg
    // does (suews_ctrl_output.f95:912-957), [row][87][stride] indexed by thread slot so that a warp writes 256 B lines
    double *agg;
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    const bool estm_on = (ESTMK != 0) && a.estm;
    SuAnohmIn an_in;
    an_in.hours = a.an_hours; an_in.day_first = a.an_day; an_in.day_count = a.an_day + 367; an_in.day_nsun = a.an_day + 734;
+   an_in.cbl_ini = a.cbl_ini; an_in.cbl_nline = a.cbl_nline;
    if (active && estm_on) {
       double *ep = reinterpret_cast<double *>(&ES);
 #pragma unroll 1
@@ -273,10 +279,11 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
          const bool live = active && dg.fatal == 0;
          SuLines L;
          L.datetime5 = nullptr; L.suews82 = nullptr; L.snow98 = nullptr; L.rsl133 = nullptr; L.daily45 = nullptr; L.sol26 = nullptr;
-         L.estm27 = nullptr;
+         L.estm27 = nullptr; L.bl17 = nullptr;
          double l_dt[FULL ? 5 : 1], l_su[FULL ? SUEWS_NCOL_SUEWS : 1], l_sn[FULL ? SUEWS_NCOL_SNOW : 1], l_rs[FULL ? SUEWS_NCOL_RSL : 1],
             l_da[(K != SU_K_P0) ? SUEWS_NCOL_DAILY : 1], l_so[FULL ? SUEWS_NCOL_SOLWEIG : 1];
-         double l_es[FULL ? SUEWS_NCOL_ESTM : 1];
+         double l_es[FULL ? SUEWS_NCOL_ESTM : 1], l_bl[(FULL && ESTMK != 0) ? SUEWS_NCOL_BL : 1];
+         if (FULL && ESTMK != 0 && a.blkBL) L.bl17 = l_bl;
          if (FULL) { L.datetime5 = l_dt; L.suews82 = l_su; L.snow98 = l_sn; L.rsl133 = l_rs; L.daily45 = l_da; L.sol26 = l_so; L.estm27 = l_es; }
          // policy P1 also keeps the DailyState line, which only exists on the last step of a day (dailystate.f95:1094)
          const bool day_end = (K != SU_K_P0) && a.agg_daily &&
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
                                             (K != SU_K_P0 && (a.agg || (a.sums && !a.sum7))) ? acc : nullptr,
                                             ((K == SU_K_P0 || !a.agg) && a.sums && a.sum7) ? acc7 : nullptr, L,
                                             estm_on ? &ES : nullptr, a.ts5 ? a.ts5 + (size_t)gs * SUEWS_N_TS5 : nullptr, last_lo, last_hi,
-                                            a.flux_only != 0, (estm_on && a.an_hours) ? &an_in : nullptr);
+                                            a.flux_only != 0, estm_on ? &an_in : nullptr);
          if (K != SU_K_P0) {
             if (day_end) {
                if (live && dg.fatal == 0 && n_day_rows < a.agg_daily_rows) {
@@ -335,6 +342,11 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
                b = a.blkESTM + (size_t)cell * n * (SUEWS_NCOL_ESTM + 5);
                for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
                for (int c = 0; c < SUEWS_NCOL_ESTM; c++) b[gs + n * (5 + c)] = (fabs(l_es[c]) > 30000) ? -999.0 : l_es[c];
+            }
+            if (ESTMK != 0 && P.CBLuse >= 1 && a.blkBL) {   // dataOutBL (bluews.f95:130-133, :253-258)
+               b = a.blkBL + (size_t)cell * n * (SUEWS_NCOL_BL + 5);
+               for (int c = 0; c < 5; c++) b[gs + n * c] = l_dt[c];
+               for (int c = 0; c < SUEWS_NCOL_BL; c++) b[gs + n * (5 + c)] = l_bl[c];
             }
             if (P.snowUse == 1) {   // SUEWS_update_output, driver.f95:2499-2501 (with set_nan :2737)
                b = a.blkSnow + (size_t)cell * n * (SUEWS_NCOL_SNOW + 5);

@@ -335,6 +335,24 @@ def site_arguments(tables, runcontrol, grid, year):
     return a
 
 
+def read_cbl(input_dir):
+    """BLUEWS inputs of a run directory (CBL_ReadInputData, suews_phys_bluews.f95:300-357): the switches of CBLInput.nml as
+    class fields, and IniCBLdata -- the rows of its InitialDataFileName up to a -9 line, [nline, 8]."""
+    nml = read_runcontrol(os.path.join(input_dir, "CBLInput.nml"))
+    params = {k: [nml[k]] for k in ("entrainmenttype", "qh_choice", "isubs", "co2_included", "initialdata_use", "sondeflag", "wsb")
+              if k in nml}
+    ini = None
+    if int(nml.get("initialdata_use", 0)) in (1, 2):
+        rows = []
+        for ln in open(os.path.join(input_dir, nml["initialdatafilename"])).read().splitlines()[1:]:
+            tok = ln.split()
+            if not tok or float(tok[0]) == -9:
+                break
+            rows.append([float(t) for t in tok[:8]])
+        ini = np.array(rows, dtype=np.float64)
+    return params, ini
+
+
 def run_arguments(run_dir, grid, year, initial_conditions=None):
     """Everything SuewsBatch.load_reference_args needs for one grid of a reference run directory: the table join above plus
     the first step's state from an InitialConditions namelist (checkpoint.initial_state; default

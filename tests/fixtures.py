@@ -63,3 +63,11 @@ def text_tolerance(group, ncol):
 
 # ESTM example parameter set / synthetic surface-temperature forcing: shared with the bench's scheme sweep
 from suews_b200.synth import C2K, estm_example, estm_ts_forcing  # noqa: E402,F401
+
+
+def cbl_inputs():
+    """BLUEWS inputs of the golden run (CBLInput.nml + CBLinputfiles/CBL_initial_data.txt): class fields and IniCBLdata"""
+    from suews_b200 import tables
+    params, ini = tables.read_cbl(os.path.join(GOLDEN, "baserun_2020b", "Input"))
+    params["cbluse"] = [1]
+    return params, ini

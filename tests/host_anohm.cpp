@@ -48,6 +48,6 @@ extern "C" void an_host_day_coefs(const double *hours8, int nrows, int xid, doub
          }
       }
    }
-   SuAnohmIn in = {hours.data(), first.data(), count.data(), nsun.data()};
+   SuAnohmIn in = {hours.data(), first.data(), count.data(), nsun.data(), nullptr, 0};
    an_day_coefs(in, xid, dTemp_C, dRH, EmissionsMethod, qf, moist, alb, emis, cp, kk, ch, coeff21);
 }

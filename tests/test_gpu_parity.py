@@ -1132,3 +1132,94 @@ def test_anohm_explicit_met_grid_and_too_many_rows():
     with pytest.raises(SuewsError):
         b.set_forcing(two_years)
     b.close()
+
+
+# ---- BLUEWS (suews_phys_bluews.f95): the boundary-layer slab model as the last stage of the step
+@pytest.mark.gpu
+def test_bluews_matches_oracle_and_the_reference_bl_file():
+    """The BL output block of the 2005 golden run (1440 steps, nights and days) against the oracle's line step by step, its
+    hourly means against the reference's test1_2005_BL_60.txt to the printed digit, and the slab variables at the end."""
+    import ctypes as C
+    from suews_b200 import OUT_FULL, SuewsBatch
+    params, ini = fx.cbl_inputs()
+    d = fx.state_init(2005)
+    d.update(params)
+    met = fx.forcing(2005)
+    n = met.shape[0]
+    dp = C.POINTER(C.c_double)
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    L.so_set_bl_block.argtypes = [dp]
+    ini = np.ascontiguousarray(ini)
+    bl = np.full((n, 22), -999.0, order="F")
+    L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+    L.so_set_bl_block(bl.ctypes.data_as(dp))
+    cell = ol.Cell(d)
+    try:
+        ref = cell.run(met, want=("SUEWS",))
+    finally:
+        L.so_set_bl_block(None)
+        L.so_set_cbl_initial(None, 0)
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_cbl_initial(ini)
+    b.set_forcing(met)
+    b.advance(0, n, OUT_FULL)
+    out = b.block("BL", 0, n)
+    assert np.array_equal(out[:, :5], bl[:, :5])
+    scale = np.maximum(np.abs(bl[:, 5:]), np.abs(bl[:, 5:]).max(axis=0) * 1e-3)
+    e = np.abs(out[:, 5:] - bl[:, 5:]) / scale
+    assert float(e.max()) <= TOL_DAY1, (float(e.max()), np.unravel_index(e.argmax(), e.shape))
+    su = b.block("SUEWS", 0, n)                                  # the surface scheme is untouched by it
+    assert float(rel_err(su[:, 5:], ref["SUEWS"][:, 5:], "SUEWS").max()) <= TOL_DAY1
+    _hdr, gold = fx.load_ref_table("ref_2005_BL_60.txt")
+    agg = out[:gold.shape[0] * 12, 5:].reshape(gold.shape[0], 12, 17).mean(axis=1)
+    assert np.all(np.abs(agg - gold[:, 5:]) <= fx.text_tolerance("BL", 17))
+    for name in ("cbl_blh_m", "cbl_tm_K", "cbl_qm_kgkg", "cbl_tp_K", "cbl_qp_kgkg", "cbl_gamt_Km", "cbl_gamq_kgkgm"):
+        np.testing.assert_allclose(b.get_state(name)[0], cell.get_state(name), rtol=1e-10, atol=0, err_msg=name)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_bluews_entrainment_schemes_and_policy_p0():
+    """EntrainmentType 1-4, subsidence on, QH_choice 2 (LUMPS fluxes): slab state after a day under policy P0 (no output
+    line) equals the oracle's; without the initial-data table the run stops with 1007."""
+    import ctypes as C
+    from suews_b200 import OUT_SUM7, SuewsBatch, SuewsError
+    params, ini = fx.cbl_inputs()
+    ini = np.ascontiguousarray(ini)
+    met = fx.forcing(2004)[288 * 150:288 * 151 + 100]         # a summer day: the slab grows
+    dp = C.POINTER(C.c_double)
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    for et, isubs, qhc in ((1, 0, 1), (2, 0, 1), (3, 1, 1), (4, 1, 2)):
+        d = fx.state_init(2004)
+        d.update(params)
+        d.update(entrainmenttype=[et], isubs=[isubs], qh_choice=[qhc], snowuse=[0], netradiationmethod=[3])
+        for k in ("snowpack", "snowfrac", "snowwater"):
+            d[k] = [0.0] * 7
+        L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+        cell = ol.Cell(d)
+        try:
+            cell.run(met, want=("SUEWS",))
+        finally:
+            L.so_set_cbl_initial(None, 0)
+        b = SuewsBatch(1, 1)
+        b.load_reference_args(d)
+        b.upload()
+        b.set_cbl_initial(ini)
+        b.set_forcing(met)
+        b.advance(0, met.shape[0], OUT_SUM7)
+        for name in ("cbl_blh_m", "cbl_tm_K", "cbl_qm_kgkg", "cbl_tp_K", "cbl_qp_kgkg"):
+            np.testing.assert_allclose(b.get_state(name)[0], cell.get_state(name), rtol=1e-9, atol=0, err_msg="%s et=%d" % (name, et))
+        assert b.get_state("cbl_blh_m")[0, 0] > 250.0
+        b.close()
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_forcing(met[:10])
+    with pytest.raises(SuewsError) as e:
+        b.advance(0, 10, OUT_SUM7)
+    assert e.value.code == 1007
+    b.close()

@@ -221,3 +221,36 @@ def test_op_counter_build_computes_the_same_numbers():
         assert np.array_equal(counts[0][16:], counts[1][16:])                             # diagnostics are counted alike
     finally:
         ol.LIB_PATH, ol._lib = keep
+
+
+@pytest.mark.parametrize("year", [2005, 2004])
+def test_bluews_reproduces_the_reference_bl_files(year):
+    """BLUEWS (suews_phys_bluews.f95) run after every step from the oracle's QH / QE / UStar and moist-air values: the hourly
+    means of its line are the reference's test1_<year>_BL_60.txt to the printed digit -- 120 h of 2005 and all 8784 h of
+    2004 (nocturnal resets from CBL_initial_data.txt, daytime Runge-Kutta growth with EntrainmentType 4)."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    L.so_set_bl_block.argtypes = [dp]
+    params, ini = fx.cbl_inputs()
+    ini = np.ascontiguousarray(ini)
+    d = fx.state_init(year)
+    d.update(params)
+    met = fx.forcing(year)
+    bl = np.full((met.shape[0], 22), -999.0, order="F")
+    L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+    L.so_set_bl_block(bl.ctypes.data_as(dp))
+    try:
+        ol.Cell(d).run(met, want=("SUEWS",))
+    finally:
+        L.so_set_bl_block(None)
+        L.so_set_cbl_initial(None, 0)
+    _hdr, ref = fx.load_ref_table("ref_%d_BL_60.txt" % year)
+    nh = ref.shape[0]
+    assert nh == (120 if year == 2005 else 8784)
+    assert np.array_equal(bl[11:nh * 12:12, :4], ref[:, :4])            # the hour's last step carries its date columns
+    agg = bl[:nh * 12, 5:].reshape(nh, 12, 17).mean(axis=1)
+    tol = fx.text_tolerance("BL", 17)
+    assert np.all(np.abs(agg - ref[:, 5:]) <= tol), np.abs(agg - ref[:, 5:]).max(axis=0)
+    assert agg[:, 0].max() > 1000 and agg[:, 0].min() == 200.0            # the slab really grows by day and resets at night

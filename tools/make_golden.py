@@ -10,7 +10,7 @@ and committed.  Nothing here is reference *code*: only its test data.
   forcing_2005_5min.txt         Test/BaseRun/2019a/Input/test_2005_data_5.txt (1440 rows)
   forcing_2005_60min.txt        Test/BaseRun/2020b/Input/test_2005_data_60.txt (119 rows)
   forcing_2004_60min.txt        Test/BaseRun/2020b/Input/test_2004_data_60.txt.long (8784 rows)
-  ref_2005_{SUEWS,snow,RSL,SOLWEIG}_60.txt, ref_2005_DailyState.txt, ref_2004_DailyState.txt, ref_2004_SOLWEIG_60.txt
+  ref_2005_{SUEWS,snow,RSL,SOLWEIG,BL}_60.txt, ref_2005_DailyState.txt, ref_2004_DailyState.txt, ref_2004_{SOLWEIG,BL}_60.txt
                                 the reference's golden outputs (hourly, 4-6 decimals)
   estm_ts_2005_60min.txt, ref_estm_ts_2005_5min.txt
                                 ESTM surface-temperature forcing: the hourly input and the 5-min series the reference wrote
@@ -75,6 +75,8 @@ def main():
         ("2020b/Output/test1_2004_DailyState.txt", "ref_2004_DailyState.txt"),
         ("2020b/Output/test1_2005_SOLWEIG_60.txt", "ref_2005_SOLWEIG_60.txt"),
         ("2020b/Output/test1_2004_SOLWEIG_60.txt", "ref_2004_SOLWEIG_60.txt"),
+        ("2020b/Output/test1_2005_BL_60.txt", "ref_2005_BL_60.txt"),
+        ("2020b/Output/test1_2004_BL_60.txt", "ref_2004_BL_60.txt"),
         ("../../Release/InputTables/2020a/test1_2005_ESTM_Ts_data_60.txt", "estm_ts_2005_60min.txt"),
         ("../../Release/InputTables/2020a/test1_2005_ESTM_Ts_data_5.txt", "ref_estm_ts_2005_5min.txt"),
         ("2020b/Input/InitialConditionstest_2004.nml", "ref_InitialConditions_2004_input.nml"),
@@ -89,10 +91,13 @@ def main():
     os.makedirs(os.path.join(run, "Input"), exist_ok=True)
     shutil.copyfile(f"{REF}/2020b/RunControl.nml", os.path.join(run, "RunControl.nml"))
     for fn in sorted(os.listdir(f"{REF}/2020b/Input")):
-        if fn.startswith("SUEWS_") and fn.endswith(".txt") or fn in ("ESTMinput.nml", "InitialConditionstest_2004.nml"):
+        if fn.startswith("SUEWS_") and fn.endswith(".txt") or fn in ("ESTMinput.nml", "InitialConditionstest_2004.nml", "CBLInput.nml"):
             shutil.copyfile(f"{REF}/2020b/Input/{fn}", os.path.join(run, "Input", fn))
             os.chmod(os.path.join(run, "Input", fn), 0o644)
     os.chmod(os.path.join(run, "RunControl.nml"), 0o644)
+    os.makedirs(os.path.join(run, "Input", "CBLinputfiles"), exist_ok=True)   # BLUEWS: the slab's initial values per day of year
+    shutil.copyfile(f"{REF}/2020b/Input/CBLinputfiles/CBL_initial_data.txt", os.path.join(run, "Input", "CBLinputfiles", "CBL_initial_data.txt"))
+    os.chmod(os.path.join(run, "Input", "CBLinputfiles", "CBL_initial_data.txt"), 0o644)
     print("golden files in", OUT)
 
 
