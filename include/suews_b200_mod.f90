@@ -146,6 +146,22 @@ MODULE suews_b200
          INTEGER(C_INT), VALUE :: nsteps
       END FUNCTION
 
+      ! met(nrows, 24): MetForcingData(:, :, igrid), AnOHM's MetForcingData_grid when it is not the staged block (StorageHeatMethod 3)
+      INTEGER(C_INT) FUNCTION suews_b200_set_anohm_forcing(h, met, nrows) BIND(C, name='suews_b200_set_anohm_forcing')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: h
+         REAL(C_DOUBLE), INTENT(IN) :: met(*)
+         INTEGER(C_INT), VALUE :: nrows
+      END FUNCTION
+
+      ! ini(8, nline): TRANSPOSE(IniCBLdata) -- the rows of CBL_initial_data.txt, one row per column here (BLUEWS, CBLuse >= 1)
+      INTEGER(C_INT) FUNCTION suews_b200_set_cbl_initial(h, ini, nline) BIND(C, name='suews_b200_set_cbl_initial')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: h
+         REAL(C_DOUBLE), INTENT(IN) :: ini(*)
+         INTEGER(C_INT), VALUE :: nline
+      END FUNCTION
+
       INTEGER(C_INT) FUNCTION suews_b200_set_estm_forcing_orig(h, ts_orig, nrows, resolution_in_s, disagg_method) &
          BIND(C, name='suews_b200_set_estm_forcing_orig')
          IMPORT :: C_INT, C_PTR, C_DOUBLE
@@ -338,6 +354,13 @@ MODULE suews_b200
       END FUNCTION
 
       ! MODULE ESTM_data for the reference-shaped calls (INTEGRATION.md, "Semantics worth knowing")
+      ! MetForcingData_grid for the reference-shaped calls with StorageHeatMethod 3: met(nrows, 24)
+      INTEGER(C_INT) FUNCTION suews_anohm_set_met_grid(met, nrows) BIND(C, name='suews_anohm_set_met_grid')
+         IMPORT :: C_INT, C_DOUBLE
+         REAL(C_DOUBLE), INTENT(IN) :: met(*)
+         INTEGER(C_INT), VALUE :: nrows
+      END FUNCTION
+
       INTEGER(C_INT) FUNCTION suews_estm_data_set(name, vals, n) BIND(C, name='suews_estm_data_set')
          IMPORT :: C_INT, C_CHAR, C_DOUBLE
          CHARACTER(KIND=C_CHAR), INTENT(IN) :: name(*)
