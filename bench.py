@@ -180,7 +180,7 @@ def main():
                     help="time K consecutive days starting at this day of 2004 instead of K days spread over the year")
     ap.add_argument("--scheme-steps", type=int, default=4,
                     help="timed days (spread over the year) of each extra scheme set in the `schemes` object; 0 = skip it")
-    ap.add_argument("--schemes", default="baserun,snow,estm,netrad13", help="scheme sets of the `schemes` object (configs[3])")
+    ap.add_argument("--schemes", default="baserun,snow,estm,netrad13,anohm", help="scheme sets of the `schemes` object (configs[3])")
     ap.add_argument("--total-cells", type=int, default=0,
                     help="strong scaling (BASELINE configs[4]): this many cells in total, split in contiguous blocks over the GPUs; "
                          "use with --consecutive-days 0 --steps 30 for the 16.8 M cells x 30 days case")

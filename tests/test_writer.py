@@ -148,3 +148,30 @@ def test_initial_state_folds_the_users_namelist_like_the_reference():
         checkpoint.initial_state({k: v for k, v in nml.items() if k != "SoilstoreGrassState"}, d, water_depth=1.0)
     with pytest.raises(ValueError):
         checkpoint.initial_state(dict(nml, LeavesOutInitially=-999), d, water_depth=1.0)
+
+
+def test_bl_file_is_byte_identical():
+    """BLUEWS's output file: the oracle's BL line of the 2005 leg, aggregated and formatted by the library's writer, against
+    the reference's test1_2005_BL_60.txt."""
+    dp = C.POINTER(C.c_double)
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    L.so_set_bl_block.argtypes = [dp]
+    params, ini = fx.cbl_inputs()
+    ini = np.ascontiguousarray(ini)
+    d = fx.state_init(2005)
+    d.update(params)
+    met = fx.forcing(2005)
+    bl = np.full((met.shape[0], 22), -999.0, order="F")
+    L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+    L.so_set_bl_block(bl.ctypes.data_as(dp))
+    try:
+        ol.Cell(d).run(met, want=("SUEWS",))
+    finally:
+        L.so_set_bl_block(None)
+        L.so_set_cbl_initial(None, 0)
+    gold = open(os.path.join(fx.GOLDEN, "ref_2005_BL_60.txt")).read().splitlines()
+    ours = _write_txt(_agg(bl, "BL"), "BL", outlevel=2).splitlines()
+    assert len(ours) == len(gold) and ours[0] == gold[0]
+    nbad = sum(x != y for a, b in zip(ours[1:], gold[1:]) for x, y in zip(a.split(), b.split()))
+    assert nbad == 0 and "\n".join(ours) == "\n".join(gold)
