@@ -106,6 +106,11 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps);
 int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int nrows, int resolution_in_s, int disagg_method,
                                 int rain_disagg_method, int raw_units, int smd_method);
 int suews_b200_get_forcing_block(suews_b200_handle h, double *met_fast, int nsteps);
+/* KdownZen = 1 (RunControl.nml; DisaggregateMet, suews_ctrl_input.f95:1568-1600) on the block set_forcing_orig has just
+ * built: K-down is zeroed wherever the sun is below the horizon of the given site at the middle of the step before, and
+ * every day's worth of rows is rescaled to keep its sum.  The reference does it per grid; a batch shares one forcing
+ * block, so the site is the forcing's own. */
+int suews_b200_apply_kdown_zen(suews_b200_handle h, double lat, double lng, double timezone, double alt);
 
 /* ESTM (StorageHeatMethod 4/14) only.  The reference keeps ESTM's parameters and element temperatures in MODULE
  * ESTM_data (suews_phys_estm.f95:1-176), outside the SUEWS_cal_Main argument list.  Here the parameters are class

@@ -146,6 +146,13 @@ MODULE suews_b200
          INTEGER(C_INT), VALUE :: nsteps
       END FUNCTION
 
+      ! KdownZen = 1 on the block set_forcing_orig disaggregated (suews_ctrl_input.f95:1568-1600)
+      INTEGER(C_INT) FUNCTION suews_b200_apply_kdown_zen(h, lat, lng, timezone, alt) BIND(C, name='suews_b200_apply_kdown_zen')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: h
+         REAL(C_DOUBLE), VALUE :: lat, lng, timezone, alt
+      END FUNCTION
+
       ! met(nrows, 24): MetForcingData(:, :, igrid), AnOHM's MetForcingData_grid when it is not the staged block (StorageHeatMethod 3)
       INTEGER(C_INT) FUNCTION suews_b200_set_anohm_forcing(h, met, nrows) BIND(C, name='suews_b200_set_anohm_forcing')
          IMPORT :: C_INT, C_PTR, C_DOUBLE

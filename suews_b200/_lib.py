@@ -49,6 +49,7 @@ def lib():
         L.suews_b200_set_anohm_forcing.argtypes = [H, dp, C.c_int]
         L.suews_b200_set_cbl_initial.argtypes = [H, dp, C.c_int]
         L.suews_b200_set_forcing_orig.argtypes = [H, dp] + [C.c_int] * 6
+        L.suews_b200_apply_kdown_zen.argtypes = [H] + [C.c_double] * 4
         L.suews_b200_set_estm_forcing_orig.argtypes = [H, dp, C.c_int, C.c_int, C.c_int]
         L.suews_b200_get_estm_forcing_block.argtypes = [H, dp, C.c_int]
         L.suews_b200_get_forcing_block.argtypes = [H, dp, C.c_int]

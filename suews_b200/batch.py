@@ -140,17 +140,23 @@ class SuewsBatch:
         self.nsteps = m.shape[0]
 
     def set_forcing_orig(self, met_orig, resolution_in=3600, disagg_method=1, rain_disagg_method=100, raw_units=False,
-                         smd_method=0, kdown_zen=0):
+                         smd_method=0, kdown_zen=0, site=None):
         """Forcing at file resolution, disaggregated to the model timestep on the device (DisaggregateMet,
         suews_ctrl_input.f95:1380-1640).  met_orig: [nrows, 24]; raw_units: the file's own units (pressure in kPa),
-        i.e. a block that has not been through forcing.read_met.  Returns the number of model timesteps."""
-        if int(kdown_zen) != 0:   # per-grid forcing (sun below each grid's own horizon): not built, never silently ignored
-            raise NotImplementedError("KdownZen = 1 (suews_ctrl_input.f95:1568-1600) is not built: the device disaggregation implements KdownZen = 0")
+        i.e. a block that has not been through forcing.read_met.  kdown_zen = 1 (RunControl's KdownZen, :1568-1600) needs
+        site = (lat, lng, timezone, alt): the reference re-weights K-down per grid with the grid's own sun, a batch
+        shares one forcing block, so the site is the forcing's.  Returns the number of model timesteps."""
+        if int(kdown_zen) not in (0, 1):
+            raise ValueError("KdownZen is 0 or 1")
+        if int(kdown_zen) == 1 and site is None:
+            raise ValueError("KdownZen = 1 needs site=(lat, lng, timezone, alt)")
         m = np.asfortranarray(np.asarray(met_orig, dtype=np.float64))
         assert m.shape[1] == 24
         check(self.L.suews_b200_set_forcing_orig(self.h, m.ctypes.data_as(dp), m.shape[0], int(resolution_in), int(disagg_method),
                                                  int(rain_disagg_method), int(bool(raw_units)), int(smd_method)))
         self.nsteps = m.shape[0] * (int(resolution_in) // self.tstep())
+        if int(kdown_zen) == 1:
+            check(self.L.suews_b200_apply_kdown_zen(self.h, *[float(v) for v in site]))
         return self.nsteps
 
     def tstep(self):

@@ -101,6 +101,39 @@ __global__ void suews_pack_sums_kernel(const double *sums, const int *cell_of_sl
    for (int k = 0; k < pc.ncols; k++) out[(size_t)k * n + c] = sums[(size_t)pc.col[k] * stride + sl];
 }
 
+// KdownZen = 1 (DisaggregateMet, suews_ctrl_input.f95:1568-1600): the disaggregated K-down is set to zero wherever the sun is
+// below the horizon at the middle of the step before (zenith > 90 deg at dectime - halftimestep) ...
+__global__ void suews_kdownzen_mask_kernel(const double *fast, long long nfast, int tstep, double lat, double lng, double tz,
+                                           double alt, double *adj)
+{
+   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+   if (i >= nfast) return;
+   const double id = fast[(size_t)i + (size_t)nfast], it = fast[(size_t)i + 2 * (size_t)nfast], im = fast[(size_t)i + 3 * (size_t)nfast];
+   const double dectimeFast = id + it / 24.0 + im / (double)(60.0f * 24.0f);
+   const double halftimestep = (double)(((float)tstep * 1.0f) / 2 / (24 * 3600));   // REAL(tstep_real)/2/(24*3600), ctrl_init.f95:328
+   SuewsEphem e;
+   spa_time_part(id, dectimeFast - halftimestep, tz, e);   // the reference passes the day of year where the year belongs (:1581)
+   double az, zen;
+   spa_location_part(e, lat, lng, alt, az, zen);
+   const double k = fast[(size_t)i + 14 * (size_t)nfast];
+   adj[i] = (zen > 90) ? 0.0 : k;
+}
+// ... and each block of nsd rows (a day's worth, counted from the first row) is rescaled to keep its sum; rows after the last
+// whole block keep the masked values.  One thread per block: the sums are the reference's sequential SUMs.
+__global__ void suews_kdownzen_renorm_kernel(double *kdown, const double *adj, long long nfast, int nsd)
+{
+   const long long d = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+   const long long ndays = nfast / nsd;
+   if (d > ndays) return;
+   if (d == ndays) {
+      for (long long j = ndays * nsd; j < nfast; j++) kdown[j] = adj[j];
+      return;
+   }
+   double s1 = 0, s2 = 0;
+   for (int j = 0; j < nsd; j++) { s1 = s1 + kdown[d * nsd + j]; s2 = s2 + adj[d * nsd + j]; }
+   for (int j = 0; j < nsd; j++) kdown[d * nsd + j] = adj[d * nsd + j] * s1 / s2;
+}
+
 __global__ void suews_fill_kernel(double *p, size_t n, double v)
 {
    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -999,6 +1032,28 @@ int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int
    h->nsteps = (int)nfast;
    h->ts5_nsteps = 0;
    return build_anohm_hours(h, nullptr, nfast);
+}
+
+// KdownZen = 1 on the block set_forcing_orig has just disaggregated: K-down zero below the horizon of (lat, lng, alt) in
+// time zone tz and rescaled day by day (suews_ctrl_input.f95:1568-1600).  The reference does this per grid, with each grid's
+// own coordinates; a batch shares one forcing block, so the site given here is the forcing's.
+int suews_b200_apply_kdown_zen(suews_b200_handle h, double lat, double lng, double timezone, double alt)
+{
+   if (!h || !h->d_met_fast || h->nsteps <= 0) return set_err(SUEWS_E_BAD_ARG, "apply_kdown_zen: no device-disaggregated block (call set_forcing_orig first)");
+   CUDA_OK(cudaSetDevice(h->device));
+   const long long nfast = h->nsteps;
+   const int tstep = h->tstep, nsd = 24 * (3600 / tstep);
+   double *d_adj = nullptr;
+   CUDA_OK(cudaMalloc((void **)&d_adj, sizeof(double) * (size_t)nfast));
+   suews_kdownzen_mask_kernel<<<(unsigned)((nfast + 127) / 128), 128, 0, h->stream>>>(h->d_met_fast, nfast, tstep, lat, lng, timezone, alt, d_adj);
+   const long long ndays = nfast / nsd;
+   suews_kdownzen_renorm_kernel<<<(unsigned)((ndays + 1 + 63) / 64), 64, 0, h->stream>>>(h->d_met_fast + 14 * (size_t)nfast, d_adj, nfast, nsd);
+   suews_pack_steps_kernel<<<(unsigned)((nfast + 255) / 256), 256, 0, h->stream>>>(h->d_met_fast, (int)nfast, h->d_steps);
+   cudaError_t e = cudaGetLastError();
+   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+   cudaFree(d_adj);
+   CUDA_OK(e);
+   return build_anohm_hours(h, nullptr, (size_t)nfast);
 }
 
 // The disaggregated MetForcingBlock [nsteps x 24], column-major, as the device holds it

@@ -154,16 +154,17 @@ def disaggregate_estm(ts_orig, tstep=300, resolution_in=3600, disagg_method=1):
 
 
 def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, rain_disagg_method=100,
-                     first_block=True, last_block=True, prev_row=None, next_row=None, kdown_zen=0):
+                     first_block=True, last_block=True, prev_row=None, next_row=None, kdown_zen=0, zenith_fn=None):
     """Disaggregate an original-resolution met block (already passed through ``read_met``).
 
-    kdown_zen: RunControl's KdownZen.  1 = zero the disaggregated K-down while the sun is below the cell's horizon and
-    rescale each day to the original daily sum (suews_ctrl_input.f95:1568-1600): that makes the forcing a per-grid series
-    (it depends on each grid's latitude / longitude), which the shared-forcing layout of this library does not hold --
-    not built; asking for it raises instead of returning the KdownZen = 0 series."""
-    if int(kdown_zen) != 0:
-        raise NotImplementedError("KdownZen = 1 (zenith re-weighting of K-down, suews_ctrl_input.f95:1568-1600) is not built: "
-                                  "the disaggregation implements KdownZen = 0")
+    kdown_zen: RunControl's KdownZen.  1 = zero the disaggregated K-down while the sun is below the site's horizon and
+    rescale each day to the original daily sum (suews_ctrl_input.f95:1568-1600).  That needs the sun position, which this
+    package only has on the device (SuewsBatch.set_forcing_orig(kdown_zen=1, site=...) does the whole thing there); here the
+    caller supplies zenith_fn(year, dectime) -> zenith [deg] for the forcing's site, e.g. a binding of
+    suews_cal_sunposition_c.  Asking for KdownZen = 1 without it raises instead of returning the KdownZen = 0 series."""
+    if int(kdown_zen) != 0 and zenith_fn is None:
+        raise NotImplementedError("KdownZen = 1 (zenith re-weighting of K-down, suews_ctrl_input.f95:1568-1600) needs the sun position: "
+                                  "pass zenith_fn, or let the device do it (SuewsBatch.set_forcing_orig(kdown_zen=1, site=...))")
     met_orig = np.asarray(met_orig, dtype=np.float64)
     nper = resolution_in // tstep
     n = met_orig.shape[0]
@@ -193,6 +194,31 @@ def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, r
             sp = prev_row[c] if prev_row is not None else -999.0
             sn = next_row[c] if next_row is not None else -999.0
             out[:, c] = _disagg_lin(met_orig[:, c], sp, sn, method[c], nper, first_block, last_block)
+    if int(kdown_zen) == 1:
+        out[:, 14] = apply_kdown_zen(out, zenith_fn, tstep)
     if np.all(out[:, 15] == -999):
         out[:, 15] = 0.0
     return out
+
+
+def apply_kdown_zen(met_fast, zenith_fn, tstep=300):
+    """KdownZen = 1 (suews_ctrl_input.f95:1568-1600) on a disaggregated block: K-down (column 15) zero wherever
+    zenith_fn(year, dectime) > 90 at dectime - halftimestep -- with the day of year where the year belongs, as the
+    reference calls NARP_cal_SunPosition(Met_tt(i, 2), ...) -- then every block of nsd = 24 * nsh rows rescaled to its
+    original sum (sequential sums, rows after the last whole block left masked).  Returns the new column."""
+    k = np.array(met_fast[:, 14], dtype=np.float64)
+    adj = k.copy()
+    half = float(np.float32(np.float32(tstep) * np.float32(1.0)) / np.float32(2) / np.float32(24 * 3600))
+    dectime = met_fast[:, 1] + met_fast[:, 2] / 24.0 + met_fast[:, 3] / float(np.float32(60.0) * np.float32(24.0))
+    for i in range(k.size):
+        if zenith_fn(float(met_fast[i, 1]), float(dectime[i] - half)) > 90:
+            adj[i] = 0.0
+    nsd = 24 * (3600 // tstep)
+    for d in range(k.size // nsd):
+        s1 = s2 = 0.0
+        for j in range(d * nsd, (d + 1) * nsd):
+            s1 = s1 + k[j]
+            s2 = s2 + adj[j]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            adj[d * nsd:(d + 1) * nsd] = adj[d * nsd:(d + 1) * nsd] * s1 / s2
+    return adj

@@ -1223,3 +1223,29 @@ def test_bluews_entrainment_schemes_and_policy_p0():
         b.advance(0, 10, OUT_SUM7)
     assert e.value.code == 1007
     b.close()
+
+
+@pytest.mark.gpu
+def test_kdown_zen_on_the_device_equals_the_numpy_restatement():
+    """KdownZen = 1 (suews_ctrl_input.f95:1568-1600) applied by the device to the block it disaggregated, against the numpy
+    restatement fed with the oracle's sun position: same mask, same day sums, same bits."""
+    import os
+    from suews_b200 import SuewsBatch
+    from suews_b200.forcing import disaggregate_met, read_met
+    met = read_met(os.path.join(fx.GOLDEN, "forcing_2005_60min.txt"))
+    lat, lng, tz, alt = 51.5, -0.1, 0.0, 20.0
+    host = disaggregate_met(met, kdown_zen=1, zenith_fn=lambda y, t: ol.sun_position(y, t, tz, lat, lng, alt)[1])
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(fx.state_init(2005))
+    b.upload()
+    n = b.set_forcing_orig(met, resolution_in=3600, disagg_method=1, kdown_zen=1, site=(lat, lng, tz, alt))
+    assert n == host.shape[0]
+    dev = b.forcing_block()
+    cols = [c for c in range(24) if c != 23]
+    # the zenith at the horizon crossing can differ in its last bits between CUDA's and glibc's trigonometry: a step whose
+    # zenith sits within 1e-9 deg of 90 may be masked on one side only -- none in this file
+    assert np.array_equal(dev[:, cols], host[:, cols])
+    assert (dev[:, 14] == 0).sum() > (disaggregate_met(met)[:, 14] == 0).sum()
+    with pytest.raises(ValueError):
+        b.set_forcing_orig(met, kdown_zen=1)
+    b.close()

@@ -279,11 +279,24 @@ def test_dropin_supy_driver_package_exports_the_reference_names():
         sys.modules.pop("supy_driver", None)
 
 
-def test_kdown_zen_is_refused_not_ignored():
-    """KdownZen = 1 (suews_ctrl_input.f95:1568-1600) is not built: asking for it raises instead of silently returning the
-    KdownZen = 0 forcing"""
-    from suews_b200.forcing import disaggregate_met
-    met = np.zeros((24, 24))
-    met[:, 0] = 2004; met[:, 1] = 1; met[:, 2] = np.arange(24)
+def test_kdown_zen_needs_a_sun_and_keeps_the_daily_sums():
+    """KdownZen = 1 (suews_ctrl_input.f95:1568-1600): without a sun-position function the numpy path raises instead of
+    silently returning the KdownZen = 0 forcing; with one (the oracle's here) K-down is zero below the horizon and every
+    day keeps its sum."""
+    import fixtures as fx
+    import oracle_lib as ol
+    from suews_b200.forcing import disaggregate_met, read_met
+    met = read_met(os.path.join(fx.GOLDEN, "forcing_2005_60min.txt"))
     with pytest.raises(NotImplementedError):
         disaggregate_met(met, kdown_zen=1)
+    lat, lng, tz, alt = 51.5, -0.1, 0.0, 20.0
+    zen = lambda year, dectime: ol.sun_position(year, dectime, tz, lat, lng, alt)[1]   # noqa: E731
+    plain = disaggregate_met(met)
+    adj = disaggregate_met(met, kdown_zen=1, zenith_fn=zen)
+    cols = [c for c in range(24) if c != 14]
+    assert np.array_equal(plain[:, cols], adj[:, cols])
+    night = np.array([zen(float(r[1]), float(r[1] + r[2] / 24.0 + r[3] / 1440.0 - 150.0 / 86400.0)) > 90 for r in plain[:576]])
+    assert night.any() and np.all(adj[:576, 14][night] == 0.0)
+    for d in range(plain.shape[0] // 288):
+        a, b = plain[d * 288:(d + 1) * 288, 14].sum(), adj[d * 288:(d + 1) * 288, 14].sum()
+        assert abs(a - b) <= 1e-9 * max(a, 1.0)
