@@ -335,6 +335,100 @@ def site_arguments(tables, runcontrol, grid, year):
     return a
 
 
+def estm_arguments(tables, args, aux, estm_nml):
+    """ESTM's parameters as SUEWS_Translate (suews_ctrl_translate.f95:393-668) and ESTM_initials (suews_phys_estm.f95:589-634)
+    leave them in MODULE ESTM_data, by the library's field names: layer thickness / conductivity / heat capacity of the roof,
+    the wall, the internal elements and the ground facet (area-weighted over the non-building surfaces), layer counts, the
+    indoor properties, AreaWall, the heating thresholds in K and the constants ESTM_translate hard-codes (:673-692).
+    tables needs 'ESTMCoefficients' (load_tables(..., estm=True)); args / aux are site_arguments' results; estm_nml is
+    ESTMinput.nml as read_runcontrol returns it.  An ESTMCode of 0 for the paved / building surface means the three / five
+    ESTM classes of the SiteSelect row, weighted by their fractions."""
+    E = tables["ESTMCoefficients"]
+    sfr = np.asarray(args["sfr"], dtype=np.float64)
+
+    def trio(row, stem):
+        return (np.array([E.get(row, "%s_thick%d" % (stem, k)) for k in range(1, 6)]),
+                np.array([E.get(row, "%s_k%d" % (stem, k)) for k in range(1, 6)]),
+                np.array([E.get(row, "%s_rhoCp%d" % (stem, k)) for k in range(1, 6)]))
+
+    def classes(codes, fracs, what):
+        fr = np.asarray(fracs, dtype=np.float64)
+        if not 0.999 <= fr.sum() <= 1.001:
+            if (sfr[0] if what == "Paved" else sfr[1]) > 0:
+                raise TableError("ErrorHint 10: surface fractions (Fr_ESTMClass_%s) should sum to 1 (%g)" % (what, fr.sum()))
+            fr = np.array([1.0] + [0.0] * (len(fr) - 1))      # no such surface: the first class stands in (ErrorHint 67)
+        return [E.lookup(c, "ESTM class (%s)" % what) for c in codes], fr
+
+    def weighted(rows, fr, getter):
+        acc = getter(rows[0]) * fr[0]
+        for r, f in zip(rows[1:], fr[1:]):
+            acc = acc + getter(r) * f
+        return acc
+
+    z = np.zeros((5, 8)); k = np.zeros((5, 8)); r = np.zeros((5, 8))
+    codes = aux["estmcode"]
+    out = {}
+    # paved
+    if codes[0] == 0:
+        rows, fr = classes(aux["code_estmclass_paved"], aux["fr_estmclass_paved"], "Paved")
+        for j, arr in enumerate((z, k, r)):
+            arr[:, 0] = weighted(rows, fr, lambda row, j=j: trio(row, "Surf")[j])
+    else:
+        z[:, 0], k[:, 0], r[:, 0] = trio(E.lookup(codes[0], "ESTM (Paved)"), "Surf")
+    # buildings: roof = the surface columns, plus wall and internal elements and the indoor scalars
+    scal = (("nroom", "nroom"), ("alb_ibld", "Internal_albedo"), ("em_ibld", "Internal_emissivity"), ("CH_iwall", "Internal_CHwall"),
+            ("CH_iroof", "Internal_CHroof"), ("CH_ibld", "Internal_CHbld"))
+    if codes[1] == 0:
+        rows, fr = classes(aux["code_estmclass_bldgs"], aux["fr_estmclass_bldgs"], "Bldgs")
+        for j, arr in enumerate((z, k, r)):
+            arr[:, 1] = weighted(rows, fr, lambda row, j=j: trio(row, "Surf")[j])
+        wall = [weighted(rows, fr, lambda row, j=j: trio(row, "Wall")[j]) for j in range(3)]
+        ibld = [weighted(rows, fr, lambda row, j=j: trio(row, "Internal")[j]) for j in range(3)]
+        for nm, col in scal:
+            out[nm] = [float(weighted(rows, fr, lambda row, col=col: np.float64(E.get(row, col))))]
+    else:
+        row = E.lookup(codes[1], "ESTM (Bldgs)")
+        z[:, 1], k[:, 1], r[:, 1] = trio(row, "Surf")
+        wall, ibld = trio(row, "Wall"), trio(row, "Internal")
+        for nm, col in scal:
+            out[nm] = [E.get(row, col)]
+    for iv in range(2, 8):                                  # EveTr .. Water, snow
+        z[:, iv], k[:, iv], r[:, iv] = trio(E.lookup(codes[iv], "ESTM (%s)" % (SURF[iv] if iv < 7 else "snow")), "Surf")
+    fground = sfr[0] + sfr[2] + sfr[3] + sfr[4] + sfr[5] + sfr[6]
+    zg = np.zeros(5); kg = np.zeros(5); rg = np.zeros(5)
+    for iv in range(7):
+        if iv != 1 and fground != 0:
+            zg = zg + z[:, iv] * sfr[iv] / fground
+            kg = kg + k[:, iv] * sfr[iv] / fground
+            rg = rg + r[:, iv] * sfr[iv] / fground
+        elif fground == 0:
+            zg, kg, rg = zg + F32(0.01), kg + F32(0.01), rg + F32(0.01)
+
+    def count(zz):
+        for i in range(5):
+            if zz[i] <= 0:
+                return i
+        return 5
+    out.update(zground=list(zg), kground=list(kg), rground=list(rg), zroof=list(z[:, 1]), kroof=list(k[:, 1]), rroof=list(r[:, 1]),
+               zwall=list(wall[0]), kwall=list(wall[1]), rwall=list(wall[2]), zibld=list(ibld[0]), kibld=list(ibld[1]), ribld=list(ibld[2]),
+               Nground=[count(zg)], Nroof=[count(z[:, 1])], Nwall=[count(wall[0])], Nibld=[count(ibld[0])],
+               AreaWall=[aux["areawall"]])
+    c2k = F32(273.15)
+    nml = {kk.lower(): v for kk, v in estm_nml.items()}
+    out.update(TsurfChoice=[int(nml["tsurfchoice"])], evolveTibld=[int(nml["evolvetibld"])], ibldCHmod=[int(nml["ibldchmod"])],
+               LBC_soil=[float(nml["lbc_soil"])], THEAT_ON=[float(nml["theat_on"]) + c2k], THEAT_OFF=[float(nml["theat_off"]) + c2k],
+               THEAT_fix=[float(nml["theat_fix"]) + c2k])
+    # internal view factors and the floor temperature of ESTM_translate (suews_phys_estm.f95:673-692)
+    out.update(ivf_iw=[F32(0.1)], ivf_ir=[0.0], ivf_ii=[F32(0.9)], ivf_if=[0.0], ivf_ww=[F32(0.05)], ivf_wr=[0.0], ivf_wi=[F32(0.95)],
+               ivf_wf=[0.0], ivf_rw=[F32(0.05)], ivf_ri=[F32(0.95)], ivf_rf=[0.0], ivf_fw=[F32(0.05)], ivf_fr=[0.0], ivf_fi=[F32(0.95)],
+               Tfloor=[F32(20.0) + c2k])
+    return out
+
+
+def F32(x):
+    return float(np.float32(x))
+
+
 def read_cbl(input_dir):
     """BLUEWS inputs of a run directory (CBL_ReadInputData, suews_phys_bluews.f95:300-357): the switches of CBLInput.nml as
     class fields, and IniCBLdata -- the rows of its InitialDataFileName up to a -9 line, [nline, 8]."""

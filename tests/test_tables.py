@@ -87,3 +87,31 @@ def test_header_and_code_errors_are_the_references():
     with pytest.raises(tables.TableError) as e:
         tables.Table(os.path.join(RUN, "Input", "SUEWS_Soil.txt"), tables.HEADERS["SUEWS_Conductance.txt"])   # ErrorHint 56
     assert "56" in str(e.value)
+
+
+def test_estm_translation_of_the_baserun_tables():
+    """ESTM facet parameters from SUEWS_ESTMCoefficients.txt + the SiteSelect row (SUEWS_Translate :393-668): roof, wall and
+    internal elements are building class 801 (what suews_b200.synth.estm_example was written out from by hand), the ground
+    facet is the area-weighted mean over the non-building surfaces, the layer counts stop at the first non-positive
+    thickness.  (No reference output pins this: the BaseRun has ESTM off, so its dump does not carry these variables.)"""
+    from suews_b200 import synth
+    rc = tables.read_runcontrol(os.path.join(RUN, "RunControl.nml"))
+    tabs = tables.load_tables(os.path.join(RUN, "Input"), estm=True)
+    a = tables.site_arguments(tabs, rc, grid=1, year=2005)
+    aux = a.pop("_aux")
+    e = tables.estm_arguments(tabs, a, aux, tables.read_runcontrol(os.path.join(RUN, "Input", "ESTMinput.nml")))
+    ex = synth.estm_example(a["surfacearea"][0])
+    for k, want in ex.items():
+        if k in ("AreaWall", "zground", "kground", "rground", "Nground"):
+            continue
+        got = np.asarray(e[k], dtype=np.float64)
+        want = np.asarray(want, dtype=np.float64)
+        n = int(e["N" + k[1:]][0]) if k[0] in "zkr" and k[1:] in ("ibld", "wall", "roof") else want.size
+        assert np.allclose(got[:n], want[:n], rtol=1e-12, atol=0), (k, got, want)
+    E = tabs["ESTMCoefficients"]
+    sfr = np.array(a["sfr"])
+    fg = sfr.sum() - sfr[1]
+    codes = [807.0, None, 810.0, 811.0, 812.0, 809.0, 813.0]      # paved: class 807 with fraction 1; the others by ESTMCode
+    z1 = sum(E.get(E.lookup(c, "t"), "Surf_thick1") * sfr[i] / fg for i, c in enumerate(codes) if c is not None)
+    assert abs(e["zground"][0] - z1) < 1e-15 and e["Nground"] == [4] and e["Nroof"] == [3]
+    assert e["AreaWall"] == [-999.0]        # not given in this SiteSelect row: ESTM is off in the BaseRun
