@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) suews_run_kernel(SuRunArgs a
    SuewsEstmState ES;
    const bool estm_on = (ESTMK != 0) && a.estm;
    SuAnohmIn an_in;
-   an_in.hours = a.an_hours; an_in.day_first = a.an_day; an_in.day_count = a.an_day + 367; an_in.day_nsun = a.an_day + 734;
+   an_in.hours = a.an_day ? a.an_hours : nullptr; an_in.day_first = a.an_day;
+   an_in.day_count = a.an_day ? a.an_day + 367 : nullptr; an_in.day_nsun = a.an_day ? a.an_day + 734 : nullptr;
    an_in.cbl_ini = a.cbl_ini; an_in.cbl_nline = a.cbl_nline;
    if (active && estm_on) {
       double *ep = reinterpret_cast<double *>(&ES);

@@ -1249,3 +1249,23 @@ def test_kdown_zen_on_the_device_equals_the_numpy_restatement():
     with pytest.raises(ValueError):
         b.set_forcing_orig(met, kdown_zen=1)
     b.close()
+
+
+@pytest.mark.gpu
+def test_reference_run_directory_to_reference_output_files(tmp_path):
+    """examples/run_directory.py: the 2004 leg of the reference's golden run from its own input directory (table join,
+    InitialState, CBLInput, hourly forcing disaggregated on the device), 105 408 steps on the GPU, written in the
+    reference's file formats -- against the files the reference wrote: the boundary-layer file (8784 h x 17 columns), the
+    DailyState file (366 days x 45) and the checkpoint the 2005 leg starts from."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("run_directory", os.path.join(ol.ROOT, "examples", "run_directory.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rep = mod.golden_2004(str(tmp_path))
+    bad, nf, _same = rep["test1_2004_BL_60.txt"]
+    assert nf == 8784 * 22 and bad <= 1e-4 * nf, (bad, nf)         # last-decimal roundings of values on a rounding boundary only
+    bad, nf, _same = rep["test1_2004_DailyState.txt"]
+    assert nf == 366 * 50 and bad <= 1e-3 * nf, (bad, nf)
+    nbit, worst = rep["checkpoint"]
+    assert nbit >= 50 and worst <= 1e-10, (nbit, worst)
