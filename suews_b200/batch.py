@@ -140,7 +140,7 @@ class SuewsBatch:
         self.nsteps = m.shape[0]
 
     def set_forcing_orig(self, met_orig, resolution_in=3600, disagg_method=1, rain_disagg_method=100, raw_units=False,
-                         smd_method=0, kdown_zen=0, site=None):
+                         smd_method=0, kdown_zen=0, site=None, **random_rain):
         """Forcing at file resolution, disaggregated to the model timestep on the device (DisaggregateMet,
         suews_ctrl_input.f95:1380-1640).  met_orig: [nrows, 24]; raw_units: the file's own units (pressure in kPa),
         i.e. a block that has not been through forcing.read_met.  kdown_zen = 1 (RunControl's KdownZen, :1568-1600) needs
@@ -148,6 +148,18 @@ class SuewsBatch:
         shares one forcing block, so the site is the forcing's.  Returns the number of model timesteps."""
         if int(kdown_zen) not in (0, 1):
             raise ValueError("KdownZen is 0 or 1")
+        if int(rain_disagg_method) in (101, 102):
+            # random sub-intervals (RandomSamples, suews_ctrl_input.f95:2147): drawn on the host -- rng=, rain_among_n= or
+            # mult_rain_among_n= / mult_rain_among_n_upper_i= as forcing.disaggregate_met takes them -- and the block staged whole
+            from . import forcing
+            if raw_units:
+                raise ValueError("RainDisaggMethod 101/102: pass the block through forcing.read_met first")
+            if int(kdown_zen) == 1:
+                raise NotImplementedError("RainDisaggMethod 101/102 together with KdownZen = 1: disaggregate with forcing.disaggregate_met and set_forcing")
+            block = forcing.disaggregate_met(np.asarray(met_orig, dtype=np.float64), tstep=self.tstep(), resolution_in=int(resolution_in),
+                                             disagg_method=int(disagg_method), rain_disagg_method=int(rain_disagg_method), **random_rain)
+            self.set_forcing(block)
+            return self.nsteps
         if int(kdown_zen) == 1 and site is None:
             raise ValueError("KdownZen = 1 needs site=(lat, lng, timezone, alt)")
         m = np.asfortranarray(np.asarray(met_orig, dtype=np.float64))

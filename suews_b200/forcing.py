@@ -116,13 +116,49 @@ def _disagg_lin(slow, slow_prev, slow_next, dtype, nper, first_block=True, last_
     return fast
 
 
-def _disagg_p_among_n(slow, among_n, nper):
-    if among_n != nper:
-        raise NotImplementedError("RainDisaggMethod 101/102 draw unseeded random sub-intervals in the reference")
+def _random_samples(n, out_of, rng):
+    """RandomSamples (suews_ctrl_input.f95:2147-2177): n distinct sub-intervals of 1..out_of by rejection, X = INT(r*OutOf) + 1
+    with r uniform on [0, 1).  The reference draws r from an unseeded RANDOM_NUMBER, so its own runs do not repeat; here
+    the caller's generator decides."""
+    samples = []
+    while len(samples) < n:
+        x = int(rng.random() * out_of) + 1
+        if x not in samples:
+            samples.append(x)
+    return samples
+
+
+def _disagg_p_among_n(slow, among_n, nper, rng=None):
+    """DisaggP_amongN (:2016-2068): each interval's amount in among_n of its nper sub-intervals, equal shares -- all of
+    them for among_n = nper (RainDisaggMethod 100), a random draw otherwise (101)."""
+    if among_n > nper:
+        raise ValueError("ErrorHint 2: no. of rainy periods cannot exceed number of subintervals")
+    if among_n != nper and rng is None:
+        raise NotImplementedError("RainDisaggMethod 101/102 draw random sub-intervals: pass rng")
     fast = np.zeros(slow.shape[0] * nper)
     for i in range(slow.shape[0]):
         if slow[i] > 0:
-            fast[nper * i:nper * (i + 1)] = slow[i] / among_n
+            if among_n == nper:
+                fast[nper * i:nper * (i + 1)] = slow[i] / among_n
+            else:
+                for x in _random_samples(among_n, nper, rng):
+                    fast[nper * i + x - 1] = slow[i] / among_n
+    return fast
+
+
+def _disagg_p_among_n_mult(slow, upper_i, among_n5, nper, rng):
+    """DisaggP_amongNMult (:2070-2145, RainDisaggMethod 102): the number of wet sub-intervals depends on the interval's
+    amount through five intensity bins (MultRainAmongNUpperI / MultRainAmongN of RunControl.nml)."""
+    fast = np.zeros(slow.shape[0] * nper)
+    for i in range(slow.shape[0]):
+        if slow[i] > 0:
+            k = next((j for j in range(5) if slow[i] <= upper_i[j]), 4)     # above the last bound: the last bin (ErrorHint 4, a warning)
+            n = int(among_n5[k])
+            if n > nper:
+                raise ValueError("ErrorHint 2: no. of rainy periods cannot exceed number of subintervals")
+            xs = range(1, nper + 1) if n == nper else _random_samples(n, nper, rng)
+            for x in xs:
+                fast[nper * i + x - 1] = slow[i] / n
     return fast
 
 
@@ -154,7 +190,8 @@ def disaggregate_estm(ts_orig, tstep=300, resolution_in=3600, disagg_method=1):
 
 
 def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, rain_disagg_method=100,
-                     first_block=True, last_block=True, prev_row=None, next_row=None, kdown_zen=0, zenith_fn=None):
+                     first_block=True, last_block=True, prev_row=None, next_row=None, kdown_zen=0, zenith_fn=None,
+                     rain_among_n=None, mult_rain_among_n=None, mult_rain_among_n_upper_i=None, rng=None):
     """Disaggregate an original-resolution met block (already passed through ``read_met``).
 
     kdown_zen: RunControl's KdownZen.  1 = zero the disaggregated K-down while the sun is below the site's horizon and
@@ -162,6 +199,17 @@ def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, r
     package only has on the device (SuewsBatch.set_forcing_orig(kdown_zen=1, site=...) does the whole thing there); here the
     caller supplies zenith_fn(year, dectime) -> zenith [deg] for the forcing's site, e.g. a binding of
     suews_cal_sunposition_c.  Asking for KdownZen = 1 without it raises instead of returning the KdownZen = 0 series."""
+    # RainDisaggMethod 101 (rain_among_n = RainAmongN) / 102 (the five bins MultRainAmongN, MultRainAmongNUpperI) put each
+    # interval's rain into randomly chosen sub-intervals: rng is a numpy Generator or a seed.  The reference's generator is
+    # unseeded, so there is no reference sequence to reproduce -- only the distribution (amounts, number of wet sub-steps).
+    if rain_disagg_method in (101, 102):
+        if rng is None:
+            raise ValueError("RainDisaggMethod %d is random: pass rng (a numpy Generator or a seed)" % rain_disagg_method)
+        rng = rng if hasattr(rng, "random") else np.random.default_rng(rng)
+        if rain_disagg_method == 101 and rain_among_n in (None, -999):
+            raise ValueError("ErrorHint 2: RainDisaggMethod 101 requires RainAmongN")
+        if rain_disagg_method == 102 and (mult_rain_among_n is None or mult_rain_among_n_upper_i is None):
+            raise ValueError("ErrorHint 2: RainDisaggMethod 102 requires MultRainAmongN and MultRainAmongNUpperI")
     if int(kdown_zen) != 0 and zenith_fn is None:
         raise NotImplementedError("KdownZen = 1 (zenith re-weighting of K-down, suews_ctrl_input.f95:1568-1600) needs the sun position: "
                                   "pass zenith_fn, or let the device do it (SuewsBatch.set_forcing_orig(kdown_zen=1, site=...))")
@@ -175,17 +223,24 @@ def disaggregate_met(met_orig, tstep=300, resolution_in=3600, disagg_method=1, r
         method[9:13] = 20
     elif disagg_method != 1:
         raise ValueError("DisaggMethod value should be 1, 2, or 3")  # ErrorHint 2
-    if rain_disagg_method != 100:
-        raise NotImplementedError("only RainDisaggMethod=100 is deterministic in the reference")
+    if rain_disagg_method not in (100, 101, 102):
+        raise ValueError("Disaggregation code for rain not recognised")
+
+    def rain(col):
+        if rain_disagg_method == 100:
+            return _disagg_p_among_n(col, nper, nper)
+        if rain_disagg_method == 101:
+            return _disagg_p_among_n(col, int(rain_among_n), nper, rng)
+        return _disagg_p_among_n_mult(col, list(mult_rain_among_n_upper_i), list(mult_rain_among_n), nper, rng)
     out = np.full((n * nper, NCOL_MET), -999.0)
     out[:, 0:4] = _disagg_datetime(met_orig[:, 0:4], tstep, nper)
     for c in range(4, NCOL_MET):
         if c == 13:
-            out[:, 13] = _disagg_p_among_n(met_orig[:, 13], nper, nper)
+            out[:, 13] = rain(met_orig[:, 13])
             if np.all(met_orig[:, 15] == -999):
                 out[:, 15] = -999.0
             else:
-                out[:, 15] = _disagg_p_among_n(met_orig[:, 15], nper, nper)
+                out[:, 15] = rain(met_orig[:, 15])
         elif c == 23:
             continue  # wind direction: not disaggregated by the reference
         elif np.all(met_orig[:, c] == -999):

@@ -300,3 +300,36 @@ def test_kdown_zen_needs_a_sun_and_keeps_the_daily_sums():
     for d in range(plain.shape[0] // 288):
         a, b = plain[d * 288:(d + 1) * 288, 14].sum(), adj[d * 288:(d + 1) * 288, 14].sum()
         assert abs(a - b) <= 1e-9 * max(a, 1.0)
+
+
+def test_random_rain_disaggregation_keeps_amounts_and_counts():
+    """RainDisaggMethod 101 / 102 (DisaggP_amongN with RainAmongN, DisaggP_amongNMult; RandomSamples,
+    suews_ctrl_input.f95:2016-2177): every wet hour's rain lands in exactly amongN distinct sub-intervals in equal shares
+    (the bin's amongN for method 102), dry hours stay dry, everything else is the deterministic disaggregation.  The
+    reference's generator is unseeded, so there is no sequence to compare with; the same seed repeats here."""
+    import fixtures as fx
+    from suews_b200.forcing import disaggregate_met, read_met
+    met = read_met(os.path.join(fx.GOLDEN, "forcing_2004_60min.txt"))[:2000]
+    plain = disaggregate_met(met)
+    with pytest.raises(ValueError):
+        disaggregate_met(met, rain_disagg_method=101, rain_among_n=4)            # no generator given
+    a = disaggregate_met(met, rain_disagg_method=101, rain_among_n=4, rng=7)
+    b = disaggregate_met(met, rain_disagg_method=101, rain_among_n=4, rng=7)
+    c = disaggregate_met(met, rain_disagg_method=101, rain_among_n=4, rng=8)
+    assert np.array_equal(a, b) and not np.array_equal(a[:, 13], c[:, 13])
+    cols = [k for k in range(24) if k not in (13, 15)]
+    assert np.array_equal(a[:, cols], plain[:, cols])
+    wet = met[:, 13] > 0
+    assert wet.sum() > 50
+    fast = a[:, 13].reshape(-1, 12)
+    assert np.all(fast[~wet] == 0)
+    assert np.all((fast[wet] > 0).sum(axis=1) == 4)
+    assert np.allclose(fast[wet].sum(axis=1), met[wet, 13], rtol=1e-15)
+    assert np.all(np.abs(fast[wet].max(axis=1) - met[wet, 13] / 4) == 0)
+    upper, among = [0.2, 0.5, 1.0, 2.0, 5.0], [2, 3, 6, 12, 12]
+    m = disaggregate_met(met, rain_disagg_method=102, mult_rain_among_n=among, mult_rain_among_n_upper_i=upper, rng=3).reshape(-1, 12, 24)[:, :, 13]
+    for i in np.nonzero(wet)[0]:
+        k = next((j for j in range(5) if met[i, 13] <= upper[j]), 4)
+        assert (m[i] > 0).sum() == among[k] and abs(m[i].sum() - met[i, 13]) <= 1e-15 * met[i, 13]
+    with pytest.raises(ValueError):
+        disaggregate_met(met, rain_disagg_method=101, rain_among_n=13, rng=1)    # RainAmongN > Nper: ErrorHint 2
