@@ -137,7 +137,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 //         SU_K_ACC the 82-column line accumulated (running sums P0+, or the in-kernel aggregation P1; also P0 for the
 //         buckets without a specialised instance), SU_K_P0 the seven parity sums only (policy P0: no output line is formed)
 //   SNOW  1 / 0: every / no class of the bucket has snowUse = 1; -1: decided per class at run time
-//   ESTM  0: no class of the bucket runs StorageHeatMethod 4/14; -1: decided per class at run time
+//   ESTM  0: no class of the bucket keeps a record of its own (StorageHeatMethod 3 AnOHM, 4/14 ESTM, BLUEWS); -1: the record is
+//         resident and the scheme is decided per class at run time
 enum { SU_K_FULL = 0, SU_K_ACC = 1, SU_K_P0 = 2 };
 #ifdef SU_PHASE_CLOCKS
 typedef cudaError_t (*su_clk_reader_t)(unsigned long long *out16, int reset);
