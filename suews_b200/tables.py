@@ -447,16 +447,25 @@ def read_cbl(input_dir):
     return params, ini
 
 
-def run_arguments(run_dir, grid, year, initial_conditions=None):
+def run_arguments(run_dir, grid, year, initial_conditions=None, estm_ts_row0=None):
     """Everything SuewsBatch.load_reference_args needs for one grid of a reference run directory: the table join above plus
     the first step's state from an InitialConditions namelist (checkpoint.initial_state; default
-    Input/InitialConditions<FileCode>_<year>.nml)."""
+    Input/InitialConditions<FileCode>_<year>.nml).  With StorageHeatMethod 4 / 14 in RunControl.nml the ESTM parameters
+    (estm_arguments, ESTMinput.nml) are included, and -- given the first row [13] of the surface-temperature forcing -- the
+    element temperatures ESTM_translate starts from (estm.initial_state)."""
     from . import checkpoint
     rc = read_runcontrol(os.path.join(run_dir, "RunControl.nml"))
     input_dir = os.path.join(run_dir, rc.get("fileinputpath", "./Input/"))
-    tabs = load_tables(input_dir)
+    with_estm = int(rc.get("storageheatmethod", 1)) in (4, 14)
+    tabs = load_tables(input_dir, estm=with_estm)
     a = site_arguments(tabs, rc, grid, year)
     aux = a.pop("_aux")
+    if with_estm:
+        e = estm_arguments(tabs, a, aux, read_runcontrol(os.path.join(input_dir, "ESTMinput.nml")))
+        a.update({k.lower(): v for k, v in e.items()})
+        if estm_ts_row0 is not None:
+            from . import estm
+            a.update({k.lower(): list(np.atleast_1d(v)) for k, v in estm.initial_state(e, a["sfr"], a["emis"], estm_ts_row0).items()})
     if initial_conditions is None:
         initial_conditions = os.path.join(input_dir, "InitialConditions%s_%d.nml" % (rc.get("filecode", ""), year))
     st = checkpoint.initial_state(checkpoint.read(initial_conditions), a, water_depth=aux["waterdepth"])

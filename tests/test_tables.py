@@ -115,3 +115,24 @@ def test_estm_translation_of_the_baserun_tables():
     z1 = sum(E.get(E.lookup(c, "t"), "Surf_thick1") * sfr[i] / fg for i, c in enumerate(codes) if c is not None)
     assert abs(e["zground"][0] - z1) < 1e-15 and e["Nground"] == [4] and e["Nroof"] == [3]
     assert e["AreaWall"] == [-999.0]        # not given in this SiteSelect row: ESTM is off in the BaseRun
+
+
+def test_run_arguments_with_estm_switched_on(tmp_path):
+    """The same run directory with StorageHeatMethod = 4 in RunControl.nml: run_arguments adds MODULE ESTM_data's parameters
+    and, given the first surface-temperature row, the start temperatures -- every ESTM field of the library is covered."""
+    import shutil
+    from suews_b200 import batch
+    run = tmp_path / "run"
+    shutil.copytree(RUN, run)
+    rcp = run / "RunControl.nml"
+    rcp.write_text(rcp.read_text().replace("StorageHeatMethod=1", "StorageHeatMethod=4"))
+    ts_row0 = [2005, 1, 0, 5, 20.0, 1.0, 2.0, 1.5, 0.5, 0.3, 0.8, 0.1, 0.2]
+    a, aux, rc = tables.run_arguments(str(run), grid=1, year=2004, estm_ts_row0=ts_row0,
+                                      initial_conditions=os.path.join(RUN, "Input", "InitialConditionstest_2004.nml"))
+    assert a["storageheatmethod"] == [4] and a["nroof"] == [3] and a["nground"] == [4]
+    names = {nm.lower() for nm in batch.estm_names()} - {"cbluse", "entrainmenttype", "qh_choice", "isubs", "co2_included",
+                                                          "initialdata_use", "sondeflag", "wsb"}
+    names = {n for n in names if not n.startswith(("anohm_", "cbl_"))} & {nm.lower() for nm, _k, _n in batch.all_fields()}
+    missing = sorted(n for n in names if n not in a)
+    assert not missing, missing
+    assert len(a["tw_4"]) == 20 and a["tievolve"][0] == 20.0 + float(np.float32(273.15))
