@@ -14,34 +14,7 @@ SU_DEV double sat_vap_press(double TK, double P)
    return e * f;
 }
 
-// suews_util_meteo.f95:148-192.  The reference rewrites its argument T to 0.001 when |T| < 0.001 (a side
-// effect the callers see); by-reference scalars of out-of-line device functions live in local memory, so the
-// rewrite is a separate inline step (su_fix_T) and the evaluation takes T by value.  Warnings 28/29 are
-// raised by the callers through sat_vap_press_warn.
-SU_INL double su_fix_T(double T) { return (fabs(T) < F(0.001000)) ? (double)F(0.001000) : T; }
-SU_HOT double sat_vap_press_v(double T, double Press_hPa)   // T already through su_fix_T
-{
-   // water (T >= 0.001) and ice (T <= -0.001) branches of meteo.f95:171-186 differ only in seven constants;
-   // selecting the constants keeps a warp whose cells straddle 0 degC on one instruction stream
-   const bool w = (T >= F(0.001000));
-   const double c0 = w ? F(6.1121) : F(6.1115), c1 = w ? F(18.678) : F(23.036), c2 = w ? F(234.5) : F(333.7),
-                c3 = w ? F(257.14) : F(279.82), f0 = w ? F(1.00072) : F(1.00022), f1 = w ? F(3.2E-6) : F(3.83E-6),
-                f2 = w ? F(5.9E-10) : F(6.4E-10);
-   const double Press_kPa = Press_hPa / 10;
-   const double e_mb = c0 * exp(((c1 - T / c2) * T) / (T + c3));
-   const double f = f0 + Press_kPa * (f1 + f2 * (T * T));
-   const bool in_range = (T < 50 && T > -40) && (w || T <= -F(0.001000));
-   return in_range ? e_mb * f : 1000.0;
-}
-SU_INL double sat_vap_press_x(SuDiag &dg, double &T, double Press_hPa, int from)
-{
-   if (fabs(T) < F(0.001000)) {
-      if (from == 1) su_warn(dg, 29);
-      T = F(0.001000);
-   }
-   if (!(T < 50 && T > -40)) su_warn(dg, 28);
-   return sat_vap_press_v(T, Press_hPa);
-}
+#include "dev_latvap.cuh"   // sat_vap_press_x, psyc_const and Lat_vap (suews_util_meteo.f95:148-192, :277-346, :409-427)
 
 // suews_util_meteo.f95:195-228
 SU_COLD double sat_vap_pressIce(SuDiag &dg, double &T, double Press_hPa, int from)
@@ -60,14 +33,6 @@ SU_COLD double sat_vap_pressIce(SuDiag &dg, double &T, double Press_hPa, int fro
       su_warn(dg, 28);
    }
    return es_hPa;
-}
-
-// suews_util_meteo.f95:409-427
-SU_INL double psyc_const(SuDiag &dg, double cp, double Press_hPa, double lv_J_kg)
-{
-   const double epsil = F(0.62197);
-   if (cp * Press_hPa < 900 || lv_J_kg < 10000) su_warn(dg, 19);
-   return (cp * Press_hPa) / (epsil * lv_J_kg);
 }
 
 // suews_util_meteo.f95:444-492 (genuine double-precision literals)
@@ -97,92 +62,6 @@ SU_DEV double qa2RH(double qa_gkg, double pres_hPa, double Ta_degC)
    double es = sat_vap_press(Ta_degC + F(273.15), pres_hPa);
    double ea = 500 * pres_hPa * qa_kgkg / (311 + 189 * qa_kgkg);
    return ea / es;
-}
-
-// suews_util_meteo.f95:277-346.  The reference keeps switch1/switch2 in implicit-SAVE locals, so
-// their exit values seed the next call; here they are per-cell state (sw = switch1 | switch2 << 1).
-//
-// The wet-bulb search takes ~21 trips on the bench forcing, each with a full sat_vap_press (EXP) and a division, and
-// all it keeps of them is a three-way decision: |ea_est - ea_fix| < 0.001, ea_est above, ea_est below.  The result
-// (tw, hence lv, and the two switches) depends on those decisions only.  So each trip first forms ea_est in single
-// precision (fast intrinsics; relative error <= ~1.5e-6 of the terms' magnitudes) and takes the decision from it when it clears the 0.001
-// threshold by a margin several times that error; only the last one to three trips, where the estimate is within a few
-// thousandths of a hPa of the target, evaluate the reference expression in double.  Same decisions, same tw sequence
-// (the additions tw +- incr are the reference's), same bits (checked against the plain loop on random arguments by
-// suews_b200_selftest_latvap).  SU_LATVAP_PLAIN builds the plain loop.
-SU_INL float su_es_single(float T, float Press_kPa)
-{
-   const bool w = (T >= 0.001f);
-   const float c0 = w ? 6.1121f : 6.1115f, c1 = w ? 18.678f : 23.036f, c2 = w ? 234.5f : 333.7f, c3 = w ? 257.14f : 279.82f,
-               f0 = w ? 1.00072f : 1.00022f, f1 = w ? 3.2E-6f : 3.83E-6f, f2 = w ? 5.9E-10f : 6.4E-10f;
-   // fast intrinsics (MUFU): __expf <= 6 ulp for arguments below 4, __fdividef <= 2 ulp
-   return (c0 * __expf(__fdividef((c1 - __fdividef(T, c2)) * T, T + c3))) * (f0 + Press_kPa * (f1 + f2 * (T * T)));
-}
-template <bool PLAIN>
-SU_INL double Lat_vap_t(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
-{
-   bool switch1 = (sw & 1) != 0, switch2 = (sw & 2) != 0;
-   const double ea_fix = Ea_hPa;
-   double lv_J_kg = (F(2500.25) - F(2.365) * Temp_C) * 1000;
-   double tw = Temp_C / F(2.);
-   double incr = F(3.);
-   if (Press_hPa < 900) su_warn(dg, 45);
-   const float Tf = (float)Temp_C, eaf = (float)Ea_hPa, pkf = (float)(Press_hPa / 10), cpPf = (float)(cp * Press_hPa);
-   for (int ii = 1; ii <= 100; ii++) {
-      int dec = 2;   // 0: within 0.001, 1: ea_est above, -1: below, 2: not decided yet
-      if (!PLAIN && tw < 49 && tw > -39 && !(fabs(tw) < F(0.001000))) {
-         const float twf = (float)tw;
-         const float es_a = su_es_single(twf, pkf);
-         const float pt_a = __fdividef(cpPf, 0.62197f * (float)lv_J_kg) * (Tf - twf);
-         const float d = (es_a - pt_a) - eaf;
-         const float margin = 0.002f + 8e-6f * (fabsf(es_a) + fabsf(pt_a) + fabsf(eaf));
-         if (d > margin) dec = 1;
-         else if (d < -margin) dec = -1;
-         if (dec != 2) {   // the side effects of the calls not made: warnings 28 (never: tw is in range here) and 19
-            if (cp * Press_hPa < 900 || lv_J_kg < 10000) su_warn(dg, 19);
-         }
-      }
-      if (dec == 2) {
-         double es_tw = sat_vap_press_x(dg, tw, Press_hPa, 2);
-         double psyc = psyc_const(dg, cp, Press_hPa, lv_J_kg);
-         double ea_est = es_tw - psyc * (Temp_C - tw);
-         dec = (fabs(ea_est - ea_fix) < F(0.001000)) ? 0 : ((ea_est > ea_fix) ? 1 : ((ea_est < ea_fix) ? -1 : 3));
-      }
-      lv_J_kg = (F(2500.25) - F(2.365) * tw) * F(1e3);
-      if (switch1 && switch2) {
-         incr = incr / F(10.);
-         switch1 = false;
-         switch2 = false;
-      }
-      if (dec == 0) {
-         break;
-      } else if (dec == 1) {
-         tw = tw - incr;
-         switch1 = true;
-      } else if (dec == -1) {
-         tw = tw + incr;
-         switch2 = true;
-      }
-   }
-   sw = (switch1 ? 1 : 0) | (switch2 ? 2 : 0);
-   return lv_J_kg;
-}
-// The search is a real function: its ~21-trip loop then has the register file to itself instead of spilling inside the
-// loop next to the caller's live values (+1.3 %; SU_LATVAP_INLINE restores the inlined form).
-#ifndef SU_LATVAP_INLINE
-SU_DEVNI double Lat_vap(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
-#else
-SU_INL double Lat_vap(SuDiag &dg, double Temp_C, double Ea_hPa, double Press_hPa, double cp, int &sw)
-#endif
-{
-#if defined(SU_SKIP) && (SU_SKIP & 256)   // timing-only switch (dev_step.cuh)
-   return (F(2500.25) - F(2.365) * Temp_C) * 1000;
-#endif
-#ifdef SU_LATVAP_PLAIN
-   return Lat_vap_t<true>(dg, Temp_C, Ea_hPa, Press_hPa, cp, sw);
-#else
-   return Lat_vap_t<false>(dg, Temp_C, Ea_hPa, Press_hPa, cp, sw);
-#endif
 }
 
 struct SuAtm {

@@ -485,6 +485,20 @@ def test_library_exp_log_equal_cuda_libm_bit_for_bit():
     assert (be.value, bl.value) == (0, 0)
 
 
+def test_wet_bulb_search_levels_equal_the_plain_loop():
+    """dev_latvap.cuh: the screened wet-bulb search of the build (single-precision screen, then double; with
+    -DSU_LATVAP_MODE=2 also the root bound) against the plain loop of the reference on 2x10^8 random arguments -- whole temperature range, around 0 degC, low pressure, near saturation, every
+    entry state of the SAVE'd switches: same Lv, same exit switches, same warnings, bit for bit."""
+    import ctypes as C
+    from suews_b200._lib import lib
+    L = lib()
+    L.suews_b200_selftest_latvap.argtypes = [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
+    for seed in (20261020, 7):
+        bad = C.c_longlong(-1)
+        assert L.suews_b200_selftest_latvap(100_000_000, seed, C.byref(bad)) == 0
+        assert bad.value == 0, bad.value
+
+
 def test_sun_position_entry_point():
     import ctypes as C
     from suews_b200 import _lib
