@@ -473,3 +473,92 @@ def run_arguments(run_dir, grid, year, initial_conditions=None, estm_ts_row0=Non
     # (alb keeps the AlbMax defaults of SUEWS_Translate on the first step: SUEWS_cal_Qn puts the day's vegetation albedos
     # into alb_next during the step, driver.f95:1409-1413)
     return a, aux, rc
+
+
+def grid_arguments(run_dir, year, grids=None, initial_conditions=None):
+    """The grid loop of the reference's main program (suews_program.f95: one SUEWS_Translate + SUEWS_cal_Main per SiteSelect
+    row of the year) as the batch layout: every grid of `year` in SiteSelect -> one cell; grids whose class-kind values (the
+    scheme switches and the code-keyed tables they share) are equal -> one class.
+
+    Returns {"grids": [ids], "class_of_grid": int32[ngrid], "classes": [{name: values}], "cells": {name: [ngrid, n]},
+             "state": {name: [ngrid, n]}, "clock": (dt_since_start, tstep_prev), "runcontrol": rc, "aux": [aux per grid],
+             "cbl_initial": the rows of the CBL initial-data file (CBLuse >= 1; for set_cbl_initial after upload) or None}
+    with names as suews_fields.h spells them.  `initial_conditions`: a path used for every grid, a function grid -> path, or
+    None for the reference's own rule (MultipleInitFiles = 1: InitialConditions<FileCode><grid>_<year>.nml, else the shared
+    InitialConditions<FileCode>_<year>.nml)."""
+    from .batch import KIND_CELL, KIND_CLASS_DBL, KIND_CLASS_INT, all_fields
+    rc = read_runcontrol(os.path.join(run_dir, "RunControl.nml"))
+    input_dir = os.path.join(run_dir, rc.get("fileinputpath", "./Input/"))
+    if grids is None:
+        ss = Table(os.path.join(input_dir, "SUEWS_SiteSelect.txt"))
+        grids = [int(r[0]) for r in ss.rows if int(r[1]) == int(year)]   # (columns Grid, Year)
+        if not grids:
+            raise TableError("SUEWS_SiteSelect.txt has no row for year %d" % year)
+    if len(set(grids)) != len(grids):
+        raise TableError("SUEWS_SiteSelect.txt lists a grid twice for year %d" % year)
+
+    def ic_path(g):
+        if callable(initial_conditions):
+            return initial_conditions(g)
+        if initial_conditions is not None:
+            return initial_conditions
+        code = rc.get("filecode", "")
+        return os.path.join(input_dir, "InitialConditions%s%s_%d.nml" % (code, g if int(rc.get("multipleinitfiles", 0)) == 1 else "", year))
+
+    fields = all_fields()
+    cbl_on = int(rc.get("cbluse", 0)) >= 1
+    cbl_params, cbl_ini = read_cbl(input_dir) if cbl_on else ({}, None)
+    keys, classes, class_of_grid, auxs = {}, [], [], []
+    cells = {nm: [] for nm, kind, _n in fields if kind == KIND_CELL}
+    state = {nm: [] for nm, kind, _n in fields if kind not in (KIND_CLASS_INT, KIND_CLASS_DBL, KIND_CELL)}
+    clock = None
+    for g in grids:
+        a, aux, _rc = run_arguments(run_dir, g, year, initial_conditions=ic_path(g))
+        if cbl_on:
+            a.update({k.lower(): v for k, v in cbl_params.items()})
+            a["cbluse"] = [int(rc["cbluse"])]
+        auxs.append(aux)
+        cls = {}
+        for nm, kind, n in fields:
+            if nm.lower() not in a:
+                continue
+            v = np.atleast_1d(np.asarray(a[nm.lower()], dtype=np.float64)).ravel()
+            if v.size != n:
+                raise TableError("%s: %d values from the tables, the library holds %d" % (nm, v.size, n))
+            if kind in (KIND_CLASS_INT, KIND_CLASS_DBL):
+                cls[nm] = v
+            elif kind == KIND_CELL:
+                cells[nm].append(v)
+            else:
+                state[nm].append(v)
+        key = tuple((nm, v.tobytes()) for nm, v in sorted(cls.items()))
+        if key not in keys:
+            keys[key] = len(classes)
+            classes.append(cls)
+        class_of_grid.append(keys[key])
+        c = (int(a["dt_since_start"][0]), int(a.get("tstep_prev", a["tstep"])[0]))
+        if clock is not None and c != clock:
+            raise TableError("grids of one run start from different clocks")
+        clock = c
+    ng = len(grids)
+    for d in (cells, state):
+        for nm in [k for k, v in d.items() if len(v) not in (0, ng)]:
+            raise TableError("%s is set for some grids only" % nm)
+    return {"grids": list(grids), "class_of_grid": np.asarray(class_of_grid, dtype=np.int32), "classes": classes,
+            "cells": {k: np.vstack(v) for k, v in cells.items() if v}, "state": {k: np.vstack(v) for k, v in state.items() if v},
+            "clock": clock, "runcontrol": rc, "aux": auxs, "cbl_initial": cbl_ini}
+
+
+def load_batch(batch, ga):
+    """grid_arguments' result into a SuewsBatch / SuewsMultiBatch made for len(ga["grids"]) cells and len(ga["classes"])
+    classes (cell i = grid ga["grids"][i]); the caller uploads."""
+    for c, cls in enumerate(ga["classes"]):
+        for nm, v in cls.items():
+            batch.set_class_param(c, nm, v)
+    batch.set_cell_class(ga["class_of_grid"])
+    for nm, v in ga["cells"].items():
+        batch.set_cell_param(nm, v)
+    for nm, v in ga["state"].items():
+        batch.set_state(nm, v)
+    batch.set_clock(*ga["clock"])
+    return batch

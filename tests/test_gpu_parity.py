@@ -1266,6 +1266,48 @@ def test_kdown_zen_on_the_device_equals_the_numpy_restatement():
 
 
 @pytest.mark.gpu
+def test_grid_loop_of_a_run_directory_on_the_device(tmp_path):
+    """tables.grid_arguments + load_batch: a run directory with three grids (two classes) as one batch, BLUEWS on -- every
+    cell's first day equals the oracle started from that grid's own one-grid join."""
+    import ctypes as C
+    import os
+    from suews_b200 import OUT_FULL, SuewsBatch, tables
+    from test_tables import _three_grid_run
+    run = _three_grid_run(tmp_path)
+    ga = tables.grid_arguments(run, 2004)
+    met = fx.forcing(2004)[:288]
+    b = tables.load_batch(SuewsBatch(len(ga["grids"]), len(ga["classes"])), ga)
+    b.upload()
+    ini = np.ascontiguousarray(ga["cbl_initial"])
+    b.set_cbl_initial(ini)
+    b.set_forcing(met)
+    b.advance(0, met.shape[0], OUT_FULL)
+    dp = C.POINTER(C.c_double)
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    cbl_params, _ini = tables.read_cbl(os.path.join(run, "Input"))
+    blocks = []
+    for i, g in enumerate(ga["grids"]):
+        d, _aux, rc = tables.run_arguments(run, g, 2004)
+        d.update(cbl_params)
+        d["cbluse"] = [int(rc["cbluse"])]
+        L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+        cell = ol.Cell(d)
+        try:
+            ref = cell.run(met, want=("SUEWS",))
+        finally:
+            L.so_set_cbl_initial(None, 0)
+        out = b.block("SUEWS", i, met.shape[0])
+        blocks.append(out)
+        assert np.array_equal(out[:, :5], ref["SUEWS"][:, :5])
+        assert float(rel_err(out[:, 5:], ref["SUEWS"][:, 5:], "SUEWS").max()) <= TOL_DAY1, g
+        for name in ("cbl_blh_m", "cbl_tm_K", "cbl_qm_kgkg", "soilstore_id", "state_id"):
+            np.testing.assert_allclose(b.get_state(name)[i], cell.get_state(name), rtol=1e-10, atol=1e-300, err_msg="%s grid %d" % (name, g))
+    assert not np.array_equal(blocks[0][:, 5:], blocks[1][:, 5:])      # other fractions, other fluxes
+    b.close()
+
+
+@pytest.mark.gpu
 def test_reference_run_directory_to_reference_output_files(tmp_path):
     """examples/run_directory.py: the 2004 leg of the reference's golden run from its own input directory (table join,
     InitialState, CBLInput, hourly forcing disaggregated on the device), 105 408 steps on the GPU, written in the

@@ -136,3 +136,58 @@ def test_run_arguments_with_estm_switched_on(tmp_path):
     missing = sorted(n for n in names if n not in a)
     assert not missing, missing
     assert len(a["tw_4"]) == 20 and a["tievolve"][0] == 20.0 + float(np.float32(273.15))
+
+
+def _three_grid_run(tmp_path):
+    """the golden run directory with three grids in 2004: grid 2 differs in site values (fractions, building height),
+    grid 3 in a value the grids of a class share (the daylight-saving start day)"""
+    import shutil
+    run = tmp_path / "run3"
+    shutil.copytree(RUN, run)
+    p = run / "Input" / "SUEWS_SiteSelect.txt"
+    lines = p.read_text(encoding="latin-1").splitlines()
+    names = lines[1].split()
+    i04 = next(i for i, ln in enumerate(lines) if ln.split()[:2] == ["1", "2004"])
+
+    def variant(grid, **kw):
+        tok = lines[i04].split("!")[0].split()
+        tok[0] = str(grid)
+        for k, v in kw.items():
+            tok[names.index(k)] = str(v)
+        return "   ".join(tok)
+    lines[i04 + 1:i04 + 1] = [variant(2, Fr_Paved=0.1, Fr_Grass=0.2, H_Bldgs=22.0), variant(3, StartDLS=90)]
+    p.write_text("\n".join(lines) + "\n", encoding="latin-1")
+    return str(run)
+
+
+def test_grid_loop_of_a_run_directory_as_classes_and_cells(tmp_path):
+    """grid_arguments: every SiteSelect row of the year is a cell, rows with equal class-kind values share a class; each
+    grid's values are those of the one-grid join."""
+    run = _three_grid_run(tmp_path)
+    ga = tables.grid_arguments(run, 2004)
+    assert ga["grids"] == [1, 2, 3] and list(ga["class_of_grid"]) == [0, 0, 1] and len(ga["classes"]) == 2
+    assert ga["clock"] == (0, 300) and ga["cbl_initial"].shape[1] == 8 and ga["classes"][0]["CBLuse"][0] == 1
+    assert ga["classes"][0]["startDLS"][0] == 85 and ga["classes"][1]["startDLS"][0] == 90
+    differ = [k for k in ga["classes"][0] if not np.array_equal(ga["classes"][0][k], ga["classes"][1][k])]
+    assert differ == ["startDLS"]
+    assert list(ga["cells"]["sfr"][:, 0]) == [0.2, 0.1, 0.2] and list(ga["cells"]["bldgH"][:, 0]) == [15.0, 22.0, 15.0]
+    for i, g in enumerate(ga["grids"]):
+        a, _aux, _rc = tables.run_arguments(run, g, 2004)
+        for d in (ga["cells"], ga["state"]):
+            for nm, v in d.items():
+                assert np.array_equal(v[i], np.asarray(a[nm.lower()], dtype=np.float64).ravel()), (g, nm)
+    # (state that depends on the fractions follows its grid: a surface that is absent has no store)
+    assert ga["state"]["soilstore_id"].shape == (3, 7)
+    with pytest.raises(tables.TableError):
+        tables.grid_arguments(run, 1999)
+
+    class Recorder:          # load_batch's calls, without a device
+        def __init__(self):
+            self.calls = []
+
+        def __getattr__(self, name):
+            return lambda *a: self.calls.append((name, a))
+    r = tables.load_batch(Recorder(), ga)
+    kinds = [c[0] for c in r.calls]
+    assert kinds.count("set_class_param") == 2 * len(ga["classes"][0]) and kinds.count("set_cell_class") == 1
+    assert kinds.count("set_cell_param") == len(ga["cells"]) and kinds.count("set_state") == len(ga["state"]) and kinds[-1] == "set_clock"
