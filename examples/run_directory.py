@@ -10,6 +10,8 @@ the user's InitialConditions namelist (InitialState), CBLInput.nml + its initial
 With no arguments it runs the 2004 leg of the reference's own golden run (Test/BaseRun/2020b, kept under tests/golden/) and
 compares what it wrote with the files the reference wrote.  Needs a CUDA device.
 
+Every grid SUEWS_SiteSelect.txt lists for the year runs in the same batch (tables.grid_arguments), one set of files per grid.
+
     python examples/run_directory.py [run_dir year forcing_file [outdir]]
 """
 import os
@@ -41,41 +43,47 @@ def hourly(block, group, nper=12):
     return out
 
 
-def run(run_dir, year, forcing_file, outdir, grid=1, days_per_launch=61):
+def run(run_dir, year, forcing_file, outdir, grids=None, days_per_launch=61):
+    """Every grid SUEWS_SiteSelect.txt lists for `year` (or `grids`) as one batch -- the grid loop of the reference's main
+    program -- under the one forcing file (MultipleMetFiles = 0); one set of output files per grid."""
     os.makedirs(outdir, exist_ok=True)
-    args, aux, rc = tables.run_arguments(run_dir, grid, year)
-    input_dir = os.path.join(run_dir, rc.get("fileinputpath", "./Input/"))
-    cbl_on = int(rc.get("cbluse", 0)) >= 1
-    if cbl_on:
-        cbl_params, cbl_ini = tables.read_cbl(input_dir)
-        args.update(cbl_params)
-        args["cbluse"] = [int(rc["cbluse"])]
-    b = SuewsBatch(1, 1)
-    b.load_reference_args(args)
+    ga = tables.grid_arguments(run_dir, year, grids)
+    rc, ng = ga["runcontrol"], len(ga["grids"])
+    if int(rc.get("multiplemetfiles", 0)) == 1 and ng > 1:
+        raise NotImplementedError("MultipleMetFiles = 1: run the grids one by one, each with its own forcing file")
+    cbl_on = ga["cbl_initial"] is not None
+    b = tables.load_batch(SuewsBatch(ng, len(ga["classes"])), ga)
     b.upload()
     if cbl_on:
-        b.set_cbl_initial(cbl_ini)
+        b.set_cbl_initial(ga["cbl_initial"])
     tstep, res_in = int(rc.get("tstep", 300)), int(rc.get("resolutionfilesin", 3600))
+    site = tuple(float(ga["cells"][k][0, 0]) for k in ("lat", "lng", "timezone", "alt"))
+    if int(rc.get("kdownzen", 0)) == 1 and any(np.ptp(ga["cells"][k][:, 0]) != 0 for k in ("lat", "lng", "timezone", "alt")):
+        raise NotImplementedError("KdownZen = 1 with grids at different sites: one batch per site")
     nsteps = b.set_forcing_orig(read_met(forcing_file), resolution_in=res_in, disagg_method=int(rc.get("disaggmethod", 1)),
                                 rain_disagg_method=int(rc.get("raindisaggmethod", 100)), kdown_zen=int(rc.get("kdownzen", 0)),
-                                site=(args["lat"][0], args["lng"][0], args["timezone"][0], args["alt"][0]))
+                                site=site)
     per_day = 86400 // tstep
-    blocks = {g: [] for g in ("SUEWS", "DailyState") + (("BL",) if cbl_on else ())}
+    groups = ("SUEWS", "DailyState") + (("BL",) if cbl_on else ())
+    blocks = [{g: [] for g in groups} for _ in range(ng)]
     for s0 in range(0, nsteps, days_per_launch * per_day):
         n = min(days_per_launch * per_day, nsteps - s0)
         b.advance(s0, n, OUT_FULL)
-        for g in blocks:
-            blocks[g].append(b.block(g, 0, n))
-    blocks = {g: np.vstack(v) for g, v in blocks.items()}
-    code = "%s%d_%d" % (rc.get("filecode", "run"), grid, year)
+        for i in range(ng):
+            for g in groups:
+                blocks[i][g].append(b.block(g, i, n))
     nper = int(rc.get("resolutionfilesout", 3600)) // tstep
-    files = {code + "_SUEWS_60.txt": write_txt(hourly(blocks["SUEWS"], "SUEWS", nper), "SUEWS", int(rc.get("writeoutoption", 0)))}
-    if cbl_on:
-        files[code + "_BL_60.txt"] = write_txt(hourly(blocks["BL"], "BL", nper), "BL", 2)
-    ds = blocks["DailyState"]
-    files[code + "_DailyState.txt"] = write_txt(ds[ds[:, 5] != -999.0], "DailyState", 2)
-    files["InitialConditions%s%d_%d.nml" % (rc.get("filecode", "run"), grid, year + 1)] = checkpoint.write_text(
-        checkpoint.state_vector(lambda n: b.get_state(n)[0]), snow_use=int(rc.get("snowuse", 0)))
+    files = {}
+    for i, grid in enumerate(ga["grids"]):
+        blk = {g: np.vstack(v) for g, v in blocks[i].items()}
+        code = "%s%d_%d" % (rc.get("filecode", "run"), grid, year)
+        files[code + "_SUEWS_60.txt"] = write_txt(hourly(blk["SUEWS"], "SUEWS", nper), "SUEWS", int(rc.get("writeoutoption", 0)))
+        if cbl_on:
+            files[code + "_BL_60.txt"] = write_txt(hourly(blk["BL"], "BL", nper), "BL", 2)
+        ds = blk["DailyState"]
+        files[code + "_DailyState.txt"] = write_txt(ds[ds[:, 5] != -999.0], "DailyState", 2)
+        files["InitialConditions%s%d_%d.nml" % (rc.get("filecode", "run"), grid, year + 1)] = checkpoint.write_text(
+            checkpoint.state_vector(lambda n, i=i: b.get_state(n)[i]), snow_use=int(rc.get("snowuse", 0)))
     b.close()
     for name, text in files.items():
         open(os.path.join(outdir, name), "w").write(text)
