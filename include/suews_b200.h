@@ -100,9 +100,8 @@ int suews_b200_set_forcing(suews_b200_handle h, const double *met, int nsteps);
  * DisaggregateDateTime, Disagg_Lin with DisaggMethod 1/2/3, DisaggP_amongN with RainDisaggMethod 100) to the model
  * timestep of the uploaded classes, whole-file semantics (first and last half period repeated).  The block then holds
  * nrows * resolution_in_s / tstep rows, bit-identical to the reference's in-memory MetForcingData;
- * suews_b200_get_forcing_block reads it back ([nsteps x 24], column-major).  This is RunControl's KdownZen = 0; KdownZen = 1
- * (K-down zeroed below each grid's own horizon and rescaled per day, :1568-1600) turns the shared series into one series
- * per grid and is not built -- there is no switch for it, so it cannot be selected by accident. */
+ * suews_b200_get_forcing_block reads it back ([nsteps x 24], column-major).  This is RunControl's KdownZen = 0; for
+ * KdownZen = 1 call suews_b200_apply_kdown_zen (below) on the block this call built. */
 int suews_b200_set_forcing_orig(suews_b200_handle h, const double *met_orig, int nrows, int resolution_in_s, int disagg_method,
                                 int rain_disagg_method, int raw_units, int smd_method);
 int suews_b200_get_forcing_block(suews_b200_handle h, double *met_fast, int nsteps);
@@ -289,6 +288,16 @@ int suews_b200_multi_get_state(suews_b200_multi m, const char *name, double *val
 int suews_b200_multi_set_clock(suews_b200_multi m, int dt_since_start, int tstep_prev);
 int suews_b200_multi_upload(suews_b200_multi m);
 int suews_b200_multi_set_forcing(suews_b200_multi m, const double *met, int nsteps);
+/* the other forcing / input blocks a batch shares (same arguments as the single-device calls): a copy per device */
+int suews_b200_multi_set_forcing_orig(suews_b200_multi m, const double *met_orig, int nrows, int resolution_in_s, int disagg_method,
+                                      int rain_disagg_method, int raw_units, int smd_method);
+int suews_b200_multi_apply_kdown_zen(suews_b200_multi m, double lat, double lng, double timezone, double alt);
+int suews_b200_multi_set_estm_forcing(suews_b200_multi m, const double *ts5, int nsteps);
+int suews_b200_multi_set_estm_forcing_orig(suews_b200_multi m, const double *ts_orig, int nrows, int resolution_in_s, int disagg_method);
+int suews_b200_multi_set_anohm_forcing(suews_b200_multi m, const double *met, int nrows);
+int suews_b200_multi_set_cbl_initial(suews_b200_multi m, const double *ini, int nline);
+/* suews_b200_get_block for cell `cell` of the whole run, from the device that holds it */
+int suews_b200_multi_get_block(suews_b200_multi m, const char *group, int cell, double *block, int nsteps, int ncol);
 int suews_b200_multi_advance(suews_b200_multi m, int step0, int nsteps, int out_flags);   /* every device, asynchronous */
 int suews_b200_multi_sync(suews_b200_multi m);
 /* device time of the last advance: the slowest device's (CUDA events on each device's launch stream) */

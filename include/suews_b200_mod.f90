@@ -333,6 +333,58 @@ MODULE suews_b200
          INTEGER(C_INT), VALUE :: nsteps
       END FUNCTION
 
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_forcing_orig(m, met_orig, nrows, resolution_in_s, disagg_method, &
+                                                                rain_disagg_method, raw_units, smd_method) &
+         BIND(C, name='suews_b200_multi_set_forcing_orig')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_DOUBLE), INTENT(IN) :: met_orig(*)
+         INTEGER(C_INT), VALUE :: nrows, resolution_in_s, disagg_method, rain_disagg_method, raw_units, smd_method
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_apply_kdown_zen(m, lat, lng, timezone, alt) BIND(C, name='suews_b200_multi_apply_kdown_zen')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_DOUBLE), VALUE :: lat, lng, timezone, alt
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_estm_forcing(m, ts5, nsteps) BIND(C, name='suews_b200_multi_set_estm_forcing')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_DOUBLE), INTENT(IN) :: ts5(*)
+         INTEGER(C_INT), VALUE :: nsteps
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_estm_forcing_orig(m, ts_orig, nrows, resolution_in_s, disagg_method) &
+         BIND(C, name='suews_b200_multi_set_estm_forcing_orig')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_DOUBLE), INTENT(IN) :: ts_orig(*)
+         INTEGER(C_INT), VALUE :: nrows, resolution_in_s, disagg_method
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_anohm_forcing(m, met, nrows) BIND(C, name='suews_b200_multi_set_anohm_forcing')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_DOUBLE), INTENT(IN) :: met(*)
+         INTEGER(C_INT), VALUE :: nrows
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_set_cbl_initial(m, ini, nline) BIND(C, name='suews_b200_multi_set_cbl_initial')
+         IMPORT :: C_INT, C_PTR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         REAL(C_DOUBLE), INTENT(IN) :: ini(*)
+         INTEGER(C_INT), VALUE :: nline
+      END FUNCTION
+
+      INTEGER(C_INT) FUNCTION suews_b200_multi_get_block(m, group, cell, block, nsteps, ncol) BIND(C, name='suews_b200_multi_get_block')
+         IMPORT :: C_INT, C_PTR, C_CHAR, C_DOUBLE
+         TYPE(C_PTR), VALUE :: m
+         CHARACTER(KIND=C_CHAR), INTENT(IN) :: group(*)
+         INTEGER(C_INT), VALUE :: cell, nsteps, ncol
+         REAL(C_DOUBLE), INTENT(OUT) :: block(*)
+      END FUNCTION
+
       INTEGER(C_INT) FUNCTION suews_b200_multi_advance(m, step0, nsteps, out_flags) BIND(C, name='suews_b200_multi_advance')
          IMPORT :: C_INT, C_PTR
          TYPE(C_PTR), VALUE :: m

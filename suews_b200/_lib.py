@@ -82,6 +82,13 @@ def lib():
         L.suews_b200_multi_set_clock.argtypes = [M, C.c_int, C.c_int]
         L.suews_b200_multi_upload.argtypes = [M]
         L.suews_b200_multi_set_forcing.argtypes = [M, dp, C.c_int]
+        L.suews_b200_multi_set_forcing_orig.argtypes = [M, dp] + [C.c_int] * 6
+        L.suews_b200_multi_apply_kdown_zen.argtypes = [M] + [C.c_double] * 4
+        L.suews_b200_multi_set_estm_forcing.argtypes = [M, dp, C.c_int]
+        L.suews_b200_multi_set_estm_forcing_orig.argtypes = [M, dp, C.c_int, C.c_int, C.c_int]
+        L.suews_b200_multi_set_anohm_forcing.argtypes = [M, dp, C.c_int]
+        L.suews_b200_multi_set_cbl_initial.argtypes = [M, dp, C.c_int]
+        L.suews_b200_multi_get_block.argtypes = [M, C.c_char_p, C.c_int, dp, C.c_int, C.c_int]
         L.suews_b200_multi_advance.argtypes = [M, C.c_int, C.c_int, C.c_int]
         L.suews_b200_multi_sync.argtypes = [M]
         L.suews_b200_multi_last_advance_ms.argtypes = [M, C.POINTER(C.c_float)]

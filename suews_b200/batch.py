@@ -58,6 +58,12 @@ class SuewsBatch:
     def _class_value(self, name):
         return self._class_cache[name.lower()]
 
+    _PREFIX = "suews_b200_"
+
+    def _fn(self, name):
+        # (the calls SuewsMultiBatch shares with this class resolve to its suews_b200_multi_* twins there)
+        return getattr(self.L, self._PREFIX + name)
+
     def set_class_param(self, cls, name, vals):
         a = _arr(np.atleast_1d(vals)).ravel()
         if int(cls) == 0 and a.size == 1:
@@ -164,11 +170,11 @@ class SuewsBatch:
             raise ValueError("KdownZen = 1 needs site=(lat, lng, timezone, alt)")
         m = np.asfortranarray(np.asarray(met_orig, dtype=np.float64))
         assert m.shape[1] == 24
-        check(self.L.suews_b200_set_forcing_orig(self.h, m.ctypes.data_as(dp), m.shape[0], int(resolution_in), int(disagg_method),
+        check(self._fn("set_forcing_orig")(self.h, m.ctypes.data_as(dp), m.shape[0], int(resolution_in), int(disagg_method),
                                                  int(rain_disagg_method), int(bool(raw_units)), int(smd_method)))
         self.nsteps = m.shape[0] * (int(resolution_in) // self.tstep())
         if int(kdown_zen) == 1:
-            check(self.L.suews_b200_apply_kdown_zen(self.h, *[float(v) for v in site]))
+            check(self._fn("apply_kdown_zen")(self.h, *[float(v) for v in site]))
         return self.nsteps
 
     def tstep(self):
@@ -187,28 +193,28 @@ class SuewsBatch:
         forcing block set just before.  Only read when StorageHeatMethod is 4/14."""
         t = np.asfortranarray(np.asarray(ts5, dtype=np.float64))
         assert t.shape == (self.nsteps, 13)
-        check(self.L.suews_b200_set_estm_forcing(self.h, t.ctypes.data_as(dp), t.shape[0]))
+        check(self._fn("set_estm_forcing")(self.h, t.ctypes.data_as(dp), t.shape[0]))
 
     def set_cbl_initial(self, ini):
         """BLUEWS: the rows of CBL_initial_data.txt, [nline, 8] (DOY zi0 gamt gamq theta+ q+ theta q), shared by the batch
         (IniCBLdata, suews_phys_bluews.f95:319-341)."""
         t = np.ascontiguousarray(np.asarray(ini, dtype=np.float64))
         assert t.ndim == 2 and t.shape[1] == 8
-        check(self.L.suews_b200_set_cbl_initial(self.h, t.ctypes.data_as(dp), t.shape[0]))
+        check(self._fn("set_cbl_initial")(self.h, t.ctypes.data_as(dp), t.shape[0]))
 
     def set_anohm_forcing(self, met):
         """AnOHM's MetForcingData_grid ([nrows, 24], the MetForcingBlock columns) when it is not the staged forcing block
         itself (suews_ctrl_translate.f95:1216); holds until the next set_forcing."""
         m = np.asfortranarray(np.asarray(met, dtype=np.float64))
         assert m.ndim == 2 and m.shape[1] == 24
-        check(self.L.suews_b200_set_anohm_forcing(self.h, m.ctypes.data_as(dp), m.shape[0]))
+        check(self._fn("set_anohm_forcing")(self.h, m.ctypes.data_as(dp), m.shape[0]))
 
     def set_estm_forcing_orig(self, ts_orig, resolution_in=3600, disagg_method=1):
         """ESTM surface temperatures at file resolution [nrows, 13], disaggregated on the device (DisaggregateESTM,
         suews_ctrl_input.f95:1650-1849).  Returns the [nsteps, 13] block the device built."""
         t = np.asfortranarray(np.asarray(ts_orig, dtype=np.float64))
         assert t.shape[1] == 13
-        check(self.L.suews_b200_set_estm_forcing_orig(self.h, t.ctypes.data_as(dp), t.shape[0], int(resolution_in), int(disagg_method)))
+        check(self._fn("set_estm_forcing_orig")(self.h, t.ctypes.data_as(dp), t.shape[0], int(resolution_in), int(disagg_method)))
         b = np.zeros((self.nsteps, 13), order="F")
         check(self.L.suews_b200_get_estm_forcing_block(self.h, b.ctypes.data_as(dp), self.nsteps))
         return b
@@ -267,7 +273,7 @@ class SuewsBatch:
 
     def block(self, group, cell, nsteps):
         b = np.zeros((nsteps, NCOL[group]), order="F")
-        check(self.L.suews_b200_get_block(self.h, group.encode(), int(cell), b.ctypes.data_as(dp), nsteps, NCOL[group]))
+        check(self._fn("get_block")(self.h, group.encode(), int(cell), b.ctypes.data_as(dp), nsteps, NCOL[group]))
         return b
 
     def diag(self):
@@ -354,6 +360,29 @@ class SuewsMultiBatch(SuewsBatch):
         assert m.shape[1] == 24
         check(self.L.suews_b200_multi_set_forcing(self.h, m.ctypes.data_as(dp), m.shape[0]))
         self.nsteps = m.shape[0]
+
+    # the blocks a batch shares (set_forcing_orig, set_estm_forcing, set_cbl_initial, set_anohm_forcing) and one cell's
+    # per-step output (block) are SuewsBatch's methods on the multi-device entry points
+    _PREFIX = "suews_b200_multi_"
+
+    def _part_handle(self, d=0):
+        h = C.c_void_p()
+        check(self.L.suews_b200_multi_part(self.h, int(d), C.byref(h), None, None))
+        return h
+
+    def forcing_block(self):
+        """The MetForcingBlock [nsteps, 24] the devices built in set_forcing_orig (every device holds the same rows)."""
+        b = np.zeros((self.nsteps, 24), order="F")
+        check(self.L.suews_b200_get_forcing_block(self._part_handle(0), b.ctypes.data_as(dp), self.nsteps))
+        return b
+
+    def set_estm_forcing_orig(self, ts_orig, resolution_in=3600, disagg_method=1):
+        t = np.asfortranarray(np.asarray(ts_orig, dtype=np.float64))
+        assert t.shape[1] == 13
+        check(self.L.suews_b200_multi_set_estm_forcing_orig(self.h, t.ctypes.data_as(dp), t.shape[0], int(resolution_in), int(disagg_method)))
+        b = np.zeros((self.nsteps, 13), order="F")
+        check(self.L.suews_b200_get_estm_forcing_block(self._part_handle(0), b.ctypes.data_as(dp), self.nsteps))
+        return b
 
     def advance(self, step0, nsteps, out_flags=OUT_SUM7, sync=True):
         check(self.L.suews_b200_multi_advance(self.h, int(step0), int(nsteps), int(out_flags)))

@@ -1723,6 +1723,32 @@ int suews_b200_multi_set_clock(suews_b200_multi m, int dt_since_start, int tstep
 }
 int suews_b200_multi_upload(suews_b200_multi m) { MULTI_EACH(suews_b200_upload(h)); }
 int suews_b200_multi_set_forcing(suews_b200_multi m, const double *met, int nsteps) { MULTI_EACH(suews_b200_set_forcing(h, met, nsteps)); }
+// the forcing blocks are shared by the batch: every device gets its own copy of the same rows
+int suews_b200_multi_set_forcing_orig(suews_b200_multi m, const double *met_orig, int nrows, int resolution_in_s, int disagg_method,
+                                      int rain_disagg_method, int raw_units, int smd_method)
+{
+   MULTI_EACH(suews_b200_set_forcing_orig(h, met_orig, nrows, resolution_in_s, disagg_method, rain_disagg_method, raw_units, smd_method));
+}
+int suews_b200_multi_apply_kdown_zen(suews_b200_multi m, double lat, double lng, double timezone, double alt)
+{
+   MULTI_EACH(suews_b200_apply_kdown_zen(h, lat, lng, timezone, alt));
+}
+int suews_b200_multi_set_estm_forcing(suews_b200_multi m, const double *ts5, int nsteps) { MULTI_EACH(suews_b200_set_estm_forcing(h, ts5, nsteps)); }
+int suews_b200_multi_set_estm_forcing_orig(suews_b200_multi m, const double *ts_orig, int nrows, int resolution_in_s, int disagg_method)
+{
+   MULTI_EACH(suews_b200_set_estm_forcing_orig(h, ts_orig, nrows, resolution_in_s, disagg_method));
+}
+int suews_b200_multi_set_anohm_forcing(suews_b200_multi m, const double *met, int nrows) { MULTI_EACH(suews_b200_set_anohm_forcing(h, met, nrows)); }
+int suews_b200_multi_set_cbl_initial(suews_b200_multi m, const double *ini, int nline) { MULTI_EACH(suews_b200_set_cbl_initial(h, ini, nline)); }
+// one cell's per-step block (policy FULL) from whichever device holds it; `cell` is the index of the whole run
+int suews_b200_multi_get_block(suews_b200_multi m, const char *group, int cell, double *block, int nsteps, int ncol)
+{
+   if (!m || cell < 0 || cell >= m->ncell) return set_err(SUEWS_E_BAD_ARG, "multi_get_block: cell %d of %d", cell, m ? m->ncell : 0);
+   for (int d = 0; d < m->ndev; d++)
+      if (cell >= m->cell0[(size_t)d] && cell < m->cell0[(size_t)d] + m->n[(size_t)d])
+         return suews_b200_get_block(m->part[(size_t)d], group, cell - m->cell0[(size_t)d], block, nsteps, ncol);
+   return set_err(SUEWS_E_BAD_ARG, "multi_get_block: cell %d is in no block", cell);
+}
 // every launch is asynchronous on its device's stream: one host thread keeps all devices busy
 int suews_b200_multi_advance(suews_b200_multi m, int step0, int nsteps, int out_flags) { MULTI_EACH(suews_b200_advance(h, step0, nsteps, out_flags)); }
 int suews_b200_multi_sync(suews_b200_multi m)

@@ -10,6 +10,8 @@ T profile, Tsnow); and rho*cp*273/RA ~ 1e4 W m-2 for QHresis = rho*cp*(Tsurf - T
 of two ~273 K numbers.  The only source of CUDA-vs-oracle differences is the last-ulp behaviour of
 exp/log/pow/sin/cos in the two math libraries (the arithmetic is contraction-free on both sides).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -875,6 +877,40 @@ def test_multi_device_handle_equals_one_batch():
     assert np.array_equal(f1, f2) and np.array_equal(it1, it2)
     one.close()
     multi.close()
+
+
+@pytest.mark.gpu
+def test_multi_device_handle_shares_the_forcing_and_cbl_blocks(tmp_path):
+    """The rest of the multi-device surface: a three-grid run directory (two classes, BLUEWS on) loaded into a
+    SuewsMultiBatch, forcing at file resolution disaggregated on every device with KdownZen = 1, the CBL initial data and an
+    explicit AnOHM forcing grid set through the multi handle -- per-step blocks of every cell, from whichever device holds
+    it, bit for bit those of one single-device batch."""
+    from suews_b200 import OUT_FULL, SuewsBatch, SuewsMultiBatch, tables, _lib
+    from suews_b200.forcing import read_met
+    from test_tables import _three_grid_run
+    ga = tables.grid_arguments(_three_grid_run(tmp_path), 2004)
+    hourly = read_met(os.path.join(fx.GOLDEN, "forcing_2004_60min.txt"))[:72]
+    site = tuple(float(ga["cells"][k][0, 0]) for k in ("lat", "lng", "timezone", "alt"))
+    ngpu = _lib.lib().suews_b200_device_count()
+    out = []
+    for make in (lambda: SuewsBatch(3, 2), lambda: SuewsMultiBatch(3, 2, devices=[0, 1 % ngpu])):
+        b = tables.load_batch(make(), ga)
+        b.upload()
+        b.set_cbl_initial(ga["cbl_initial"])
+        n = b.set_forcing_orig(hourly, resolution_in=3600, kdown_zen=1, site=site)
+        assert n == 72 * 12
+        b.set_anohm_forcing(b.forcing_block())        # (accepted; no AnOHM class in this run)
+        b.advance(0, n, OUT_FULL)
+        out.append(dict(met=b.forcing_block(), su=[b.block("SUEWS", i, n) for i in range(3)], bl=[b.block("BL", i, n) for i in range(3)],
+                        st={k: b.get_state(k) for k in ("cbl_blh_m", "cbl_tm_K", "soilstore_id", "state_id")}))
+        b.close()
+    one, multi = out
+    assert np.array_equal(one["met"], multi["met"])
+    for i in range(3):
+        assert np.array_equal(one["su"][i], multi["su"][i]) and np.array_equal(one["bl"][i], multi["bl"][i]), i
+    assert float(np.abs(one["bl"][0][:, 5]).max()) > 200.0            # the slab was running
+    for k, v in one["st"].items():
+        assert np.array_equal(v, multi["st"][k]), k
 
 
 def _oracle_cells_worker(args):
