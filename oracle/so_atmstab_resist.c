@@ -298,6 +298,7 @@ void so_AerodynamicResistance(SoCtx *cx, double ZZD, double z0m, double AVU1, do
       t = ZZD / L_mod;
       psim = so_stab_psi_mom(StabilityMethod, &t);
       psih = so_stab_psi_heat(StabilityMethod, ZZD / L_mod);
+      cx->last_psih = psih;   /* (a module variable in the reference: USE sues_data, ONLY: psih) */
       z0V = so_cal_z0V(RoughLenHeatMethod, z0m, VegFraction, UStar);
       if (ZZD / L_mod == 0 || UStar == 0) {
          *RA = (log(ZZD / z0m) * log(ZZD / z0V)) / (k2 * AVU1);

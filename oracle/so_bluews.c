@@ -12,8 +12,11 @@
  * Pinned: the hourly means of this line reproduce the reference's test1_2004_BL_60.txt (8784 h) and test1_2005_BL_60.txt
  * (120 h) to the printed digit (tests/test_oracle_golden.py).
  *
- * Restated: InitialData_use = 2 (the BaseRun's choice: every quantity from the file) with any EntrainmentType and isubs;
- * InitialData_use 0 / 1 (start values diagnosed from the forcing through psih) and sondeflag = 1 (sounding files) are not.
+ * Restated: InitialData_use = 2 (the BaseRun's choice: every quantity from the file) and 1 (height and gradients from the
+ * file on the days it lists, theta and q diagnosed from the night's line through psih) with any EntrainmentType and isubs.
+ * InitialData_use = 0 cannot run in the reference (NBL reads IniCBLdata, :523-536, which CBL_ReadInputData allocates for 1
+ * and 2 only, :325) and sondeflag = 1 (sounding files) is not restated: both stop with 1007.  Only InitialData_use = 2 is
+ * pinned (the BL golden files); 1 follows the source alone.
  * Kept as the reference has them: REAL(4) clock arithmetic (float(it) + float(imin)/60.), the REAL(4) exponents
  * 0.3333333333 and 0.6666666667, C2K = 273.16, cm = -999 integrated along when CO2 is off, gamq of the night line
  * being the previous call's value.
@@ -130,8 +133,8 @@ void so_CBL(SoCtx *cx, const SoCblParams *p, SoCblState *s, const SoForcing *f, 
    int k;
    line22[0] = f->iy; line22[1] = f->id; line22[2] = f->it; line22[3] = f->imin; line22[4] = dectime;
    for (k = 5; k < 22; k++) line22[k] = -999;
-   if (p->InitialData_use != 2 || p->sondeflag != 0 || !so_cbl_ini) {
-      so_error_hint(cx, 1007, "oracle: BLUEWS restated for InitialData_use = 2, sondeflag = 0 only", -999, -999, p->InitialData_use);
+   if ((p->InitialData_use != 2 && p->InitialData_use != 1) || p->sondeflag != 0 || !so_cbl_ini) {
+      so_error_hint(cx, 1007, "oracle: BLUEWS restated for InitialData_use = 1 / 2, sondeflag = 0 only", -999, -999, p->InitialData_use);
       return;
    }
    if (qh_use < -900 || qe_use < -900) so_error_hint(cx, 22, "Unrealistic qh or qe_value for CBL.", qh_use, qe_use, p->QH_choice);
@@ -157,14 +160,35 @@ void so_CBL(SoCtx *cx, const SoCblParams *p, SoCblState *s, const SoForcing *f, 
       line22[10] = Temp_C; line22[11] = avrh; line22[12] = qh_use; line22[13] = qe_use; line22[14] = f->Press_hPa;
       line22[15] = f->avU1; line22[16] = UStar; line22[17] = avdens; line22[18] = lv_J_kg; line22[19] = avcp;
       line22[20] = s->gamt_Km; line22[21] = s->gamq_kgkgm;   /* gamq: still the previous call's value */
-      /* InitialData_use == 2 */
-      s->blh_m = ini[1];
-      s->gamt_Km = ini[2];
-      s->tp_K = ini[4];
-      s->tm_K = ini[6];
-      s->gamq_kgkgm = ini[3] / F(1000.);
-      s->qp_kgkg = ini[5] / 1000;
-      s->qm_kgkg = ini[7] / 1000;
+      if (p->InitialData_use == 2) {
+         s->blh_m = ini[1];
+         s->gamt_Km = ini[2];
+         s->tp_K = ini[4];
+         s->tm_K = ini[6];
+         s->gamq_kgkgm = ini[3] / F(1000.);
+         s->qp_kgkg = ini[5] / 1000;
+         s->qm_kgkg = ini[7] / 1000;
+      } else {
+         /* InitialData_use == 1 (bluews.f95:570-581): only on a day the file lists; otherwise the night's 200 m values stay */
+         double gamq_gkgm = ini[3];
+         if (ini[0] == f->id) {
+            const double k = F(0.4);
+            double tm_K_zm, qm_gkg_zm, lv;
+            s->blh_m = ini[1];
+            s->gamt_Km = ini[2];
+            tm_K_zm = (Temp_C + CBL_C2K) * pow(1000 / f->Press_hPa, CBL_GAS_CT_DRY / avcp);
+            s->tm_K = tm_K_zm - cx->last_psih * qh_use / (k * UStar * avcp * avdens);
+            es_hPa = so_sat_vap_press_x(cx, &Temp_C, f->Press_hPa, 1, dectime);
+            qm_gkg_zm = 622 * avrh / (100 * f->Press_hPa / es_hPa - avrh);
+            lv = (F(2500.25) - F(2.365) * Temp_C) * 1000;
+            qm_gkg = qm_gkg_zm - cx->last_psih * qe_use / (k * UStar * avdens * lv);
+            s->tp_K = s->tm_K;
+            qp_gkg = qm_gkg;
+         }
+         s->gamq_kgkgm = gamq_gkgm / F(1000.);
+         s->qp_kgkg = qp_gkg / 1000;
+         s->qm_kgkg = qm_gkg / 1000;
+      }
       {
          double tp_C = s->tp_K - CBL_C2K, tm_C = s->tm_K - CBL_C2K, qs;
          qs = so_qsatf(cx, tp_C, f->Press_hPa);

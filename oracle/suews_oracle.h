@@ -208,6 +208,7 @@ typedef struct {
    /* what the last SUEWS_cal_Main left in MODULE moist (driver.f95: use moist, only: avcp, avdens, lv_J_kg) and its
     * friction velocity: the inputs of BLUEWS (suews_ctrl_calculations.f95:194-218) */
    double last_avcp, last_avdens, last_lv_J_kg;
+   double last_psih;   /* MODULE sues_data's psih: AerodynamicResistance leaves it there (resist.f95:40,78), BLUEWS reads it */
 } SoCtx;
 
 void so_ctx_init(SoCtx *cx);

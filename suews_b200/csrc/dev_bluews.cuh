@@ -9,8 +9,11 @@
 // timestep.  Nothing of it feeds back into the surface scheme (SUEWS_Translate re-reads the forcing every step).
 // Its variables (MODULE cbl_MODULE) are per-cell state in the storage record (cbl_* of SUEWS_ESTM_STATE_FIELDS), the
 // CBLInput.nml switches are class fields, IniCBLdata is a table shared by the batch (suews_b200_set_cbl_initial).
-// Built: InitialData_use = 2 (all start values from the table), any EntrainmentType, isubs; InitialData_use 0 / 1 and
-// sounding files (sondeflag = 1) return error 1007.  The reference's REAL(4) clock arithmetic and exponents are kept.
+// Built: InitialData_use = 2 (all start values from the table) and 1 (height and gradients from the table on the days it
+// lists, theta and q diagnosed from the night's line through psih -- the value AerodynamicResistance left in MODULE sues_data,
+// resist.f95:40,78, recomputed here from the step's last z/L), any EntrainmentType, isubs.  InitialData_use = 0 cannot run in
+// the reference (NBL reads IniCBLdata, :523-536, allocated for 1 and 2 only, :325) and sounding files (sondeflag = 1) are not
+// built: error 1007.  The reference's REAL(4) clock arithmetic and exponents are kept.
 #pragma once
 
 #define SU_CBL_C2K F(273.16)
@@ -68,9 +71,11 @@ SU_INL double cbl_qsatf(SuDiag &dg, double T, double PMB)
 // CBL / NBL for one cell-step.  bl17: z theta q theta+ q+ Temp_C rh QH_use QE_use Press_hPa avu1 UStar avdens lv_J_kg avcp gamt
 // gamq (the BL output line without its five date columns), or nullptr
 SU_COLD void BLUEWS(SuDiag &dg, const SuewsClassParams &P, SuewsEstmState &S, const double *ini, int nline, const SuewsStepRec &R,
-                    double qh_use, double qe_use, double UStar, double avdens, double lv_J_kg, double avcp, double *bl17)
+                    double qh_use, double qe_use, double UStar, double avdens, double lv_J_kg, double avcp, double zl_meas, double *bl17)
 {
-   if (P.InitialData_use != 2 || P.sondeflag != 0 || !ini || nline <= 0) {
+   const bool diagnosed = (P.InitialData_use == 1);
+   if ((P.InitialData_use != 2 && !diagnosed) || (diagnosed && P.AerodynamicResistanceMethod != 2) || P.sondeflag != 0 || !ini ||
+       nline <= 0) {
       su_fatal(dg, 1007);
       return;
    }
@@ -122,31 +127,52 @@ SU_COLD void BLUEWS(SuDiag &dg, const SuewsClassParams &P, SuewsEstmState &S, co
       qp_gkg_out = S.cbl_qp_kgkg * 1000;
       gamq_out = S.cbl_gamq_kgkgm;
    }
-   if (bl17) {
-      double Temp_C = S.cbl_tm_K / su_pow_general(1000 / Press_hPa, SU_CBL_GAS_CT_DRY / avcp) - SU_CBL_C2K;
+   double Temp_C = 0, avrh = 0;
+   if (bl17 || (diagnosed && R.avkdn < 5)) {
+      Temp_C = S.cbl_tm_K / su_pow_general(1000 / Press_hPa, SU_CBL_GAS_CT_DRY / avcp) - SU_CBL_C2K;
       const double es_hPa = sat_vap_press_x(dg, Temp_C, Press_hPa, 1);   // (rewrites Temp_C when |T| < 0.001, as in the reference)
-      double avrh = 100 * ((qm_gkg * Press_hPa / (622 + qm_gkg)) / es_hPa);
+      avrh = 100 * ((qm_gkg * Press_hPa / (622 + qm_gkg)) / es_hPa);
       if (avrh > 100) {
          su_warn(dg, 34);
          avrh = 100;
       }
+   }
+   if (bl17) {
       bl17[0] = S.cbl_blh_m; bl17[1] = S.cbl_tm_K; bl17[2] = qm_gkg; bl17[3] = S.cbl_tp_K; bl17[4] = qp_gkg_out;
       bl17[5] = Temp_C; bl17[6] = avrh; bl17[7] = qh_use; bl17[8] = qe_use; bl17[9] = Press_hPa; bl17[10] = R.avU1;
       bl17[11] = UStar; bl17[12] = avdens; bl17[13] = lv_J_kg; bl17[14] = avcp; bl17[15] = S.cbl_gamt_Km; bl17[16] = gamq_out;
    }
    if (R.avkdn < 5) {
-      // the slab's start values of the day, InitialData_use = 2 (bluews.f95:571-578, :609-621)
+      // the slab's start values of the day (bluews.f95:562-594, :596-621)
       int n = 0;
       for (int i = 0; i < nline; i++)
          if ((int)ini[(size_t)i * 8] <= R.id) n++;
       const double *row = ini + (size_t)(n - 1) * 8;
-      S.cbl_blh_m = row[1];
-      S.cbl_gamt_Km = row[2];
-      S.cbl_tp_K = row[4];
-      S.cbl_tm_K = row[6];
+      double qp_gkg = row[5];
+      qm_gkg = row[7];
+      if (!diagnosed) {
+         S.cbl_blh_m = row[1];
+         S.cbl_gamt_Km = row[2];
+         S.cbl_tp_K = row[4];
+         S.cbl_tm_K = row[6];
+      } else if (row[0] == (double)R.id) {
+         // InitialData_use = 1, on a day the table lists (otherwise the night's 200 m line stays)
+         const double k = F(0.4);
+         const double psih = stab_psi_heat(P.StabilityMethod, zl_meas);
+         S.cbl_blh_m = row[1];
+         S.cbl_gamt_Km = row[2];
+         const double tm_K_zm = (Temp_C + SU_CBL_C2K) * su_pow_general(1000 / Press_hPa, SU_CBL_GAS_CT_DRY / avcp);
+         S.cbl_tm_K = tm_K_zm - psih * qh_use / (k * UStar * avcp * avdens);
+         const double es_hPa = sat_vap_press_x(dg, Temp_C, Press_hPa, 1);
+         const double qm_gkg_zm = 622 * avrh / (100 * Press_hPa / es_hPa - avrh);
+         const double lv = (F(2500.25) - F(2.365) * Temp_C) * 1000;
+         qm_gkg = qm_gkg_zm - psih * qe_use / (k * UStar * avdens * lv);
+         S.cbl_tp_K = S.cbl_tm_K;
+         qp_gkg = qm_gkg;
+      }
       S.cbl_gamq_kgkgm = row[3] / F(1000.);
-      S.cbl_qp_kgkg = row[5] / 1000;
-      S.cbl_qm_kgkg = row[7] / 1000;
+      S.cbl_qp_kgkg = qp_gkg / 1000;
+      S.cbl_qm_kgkg = qm_gkg / 1000;
       double qs = cbl_qsatf(dg, S.cbl_tp_K - SU_CBL_C2K, Press_hPa);
       if (S.cbl_qp_kgkg > qs || S.cbl_qp_kgkg < 0) S.cbl_qp_kgkg = qs;
       qs = cbl_qsatf(dg, S.cbl_tm_K - SU_CBL_C2K, Press_hPa);

@@ -736,7 +736,7 @@ static __device__ int suews_step(bool live, SuDiag &dg, const SuewsClassParams &
    // moist-air values of the last trip
    if (ESTMK != 0 && P.CBLuse >= 1) {
       if (ES && AN) BLUEWS(dg, P, *ES, AN->cbl_ini, AN->cbl_nline, R, (P.QH_choice == 2) ? Lm.QH_LUMPS : qh, (P.QH_choice == 2) ? Lm.QE_LUMPS : qe,
-                           UStar, A.avdens, A.lv_J_kg, A.avcp, L.bl17);
+                           UStar, A.avdens, A.lv_J_kg, A.avcp, ZZD / L_mod, L.bl17);
       else su_fatal(dg, 1007);
    }
 

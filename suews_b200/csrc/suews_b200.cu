@@ -314,7 +314,7 @@ static const char *fatal_text(int code)
    case 73: return "RunControl.nml:EmissionsMethod unusable";
    case 75: return "RunControl.nml: BaseTMethod / TrafficUnits not usable";
    case 1001: return "NetRadiationMethod: Value not usable";
-   case 1007: return "BLUEWS (CBLuse >= 1) needs the initial-data table (suews_b200_set_cbl_initial) with a row for the day, InitialData_use = 2 and sondeflag = 0";
+   case 1007: return "BLUEWS (CBLuse >= 1) needs the initial-data table (suews_b200_set_cbl_initial) with a row for the day, InitialData_use = 1 or 2 and sondeflag = 0";
    case 1005: return "StorageHeatMethod 4/14 (ESTM) needs the ESTM state and a surface-temperature forcing block (suews_b200_set_estm_forcing)";
    case 1003: return "StorageHeatMethod: 0, 1, 3, 4 and 14 are available; AnOHM (3) needs the forcing block's on-the-hour rows (batched API: classes first, then the forcing; reference-shaped single steps: suews_anohm_set_met_grid)";
    case 1004: return "EmissionsMethod outside 0-6 / 11-46";

@@ -1276,6 +1276,64 @@ def test_bluews_entrainment_schemes_and_policy_p0():
 
 
 @pytest.mark.gpu
+def test_bluews_start_values_diagnosed_from_the_forcing():
+    """InitialData_use = 1: theta and q of the slab's start diagnosed from the night's line through psih (recomputed on the
+    device from the step's last z/L; the oracle keeps the value AerodynamicResistance left behind) on a day the file lists,
+    the night's 200 m values on a day it does not -- line by line and in the state, with the output line (policy FULL) and
+    without it (P0)."""
+    import ctypes as C
+    from suews_b200 import OUT_FULL, OUT_SUM7, SuewsBatch, SuewsError
+    dp = C.POINTER(C.c_double)
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    L.so_set_bl_block.argtypes = [dp]
+    params, ini = fx.cbl_inputs()
+    ini = np.ascontiguousarray(ini[:1])                       # day 1 only: day 2 finds no row of its own
+    d = fx.state_init(2005)
+    d.update(params)
+    d["initialdata_use"] = [1]
+    met = fx.forcing(2005)[:288 + 150]                        # day 1, and day 2 until after noon: the slab grows from the 200 m start
+    names = ("cbl_blh_m", "cbl_tm_K", "cbl_qm_kgkg", "cbl_tp_K", "cbl_qp_kgkg", "cbl_gamt_Km", "cbl_gamq_kgkgm")
+    for nsteps, policy in ((36, OUT_SUM7), (met.shape[0], OUT_FULL)):
+        bl = np.full((nsteps, 22), -999.0, order="F")
+        L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+        L.so_set_bl_block(bl.ctypes.data_as(dp))
+        cell = ol.Cell(d)
+        try:
+            cell.run(met[:nsteps], want=("SUEWS",))
+        finally:
+            L.so_set_bl_block(None)
+            L.so_set_cbl_initial(None, 0)
+        b = SuewsBatch(1, 1)
+        b.load_reference_args(d)
+        b.upload()
+        b.set_cbl_initial(ini)
+        b.set_forcing(met[:nsteps])
+        b.advance(0, nsteps, policy)
+        for name in names:
+            np.testing.assert_allclose(b.get_state(name)[0], cell.get_state(name), rtol=1e-9, atol=0, err_msg="%s after %d steps" % (name, nsteps))
+        if policy == OUT_FULL:
+            out = b.block("BL", 0, nsteps)
+            scale = np.maximum(np.abs(bl[:, 5:]), np.abs(bl[:, 5:]).max(axis=0) * 1e-3)
+            e = np.abs(out[:, 5:] - bl[:, 5:]) / scale
+            assert np.array_equal(out[:, :5], bl[:, :5]) and float(e.max()) <= 1e-9, float(e.max())
+            assert out[:, 5].max() > 250.0                                      # it grew
+        else:
+            assert b.get_state("cbl_tm_K")[0, 0] != ini[0, 6] and b.get_state("cbl_blh_m")[0, 0] == ini[0, 1]
+        b.close()
+    d["initialdata_use"] = [0]                                # no behaviour in the reference (a table it never allocated): refused
+    b = SuewsBatch(1, 1)
+    b.load_reference_args(d)
+    b.upload()
+    b.set_cbl_initial(ini)
+    b.set_forcing(met[:4])
+    with pytest.raises(SuewsError) as err:
+        b.advance(0, 4, OUT_SUM7)
+    assert err.value.code == 1007
+    b.close()
+
+
+@pytest.mark.gpu
 def test_kdown_zen_on_the_device_equals_the_numpy_restatement():
     """KdownZen = 1 (suews_ctrl_input.f95:1568-1600) applied by the device to the block it disaggregated, against the numpy
     restatement fed with the oracle's sun position: same mask, same day sums, same bits."""

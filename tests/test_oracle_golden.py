@@ -254,3 +254,67 @@ def test_bluews_reproduces_the_reference_bl_files(year):
     tol = fx.text_tolerance("BL", 17)
     assert np.all(np.abs(agg - ref[:, 5:]) <= tol), np.abs(agg - ref[:, 5:]).max(axis=0)
     assert agg[:, 0].max() > 1000 and agg[:, 0].min() == 200.0            # the slab really grows by day and resets at night
+
+
+def test_bluews_start_values_diagnosed_from_the_forcing():
+    """InitialData_use = 1 (suews_phys_bluews.f95:570-581): on a day the initial-data file lists, height and gradients come
+    from the file and theta, q from the night's line through psih (the value AerodynamicResistance left behind); on any
+    other day the night's 200 m values stay.  Checked against the formulas written out here from the oracle's own output
+    columns (UStar, Lob, zdm, QH, QE and the BL line)."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    L.so_set_bl_block.argtypes = [dp]
+    L.so_stab_psi_heat.restype = C.c_double
+    L.so_stab_psi_heat.argtypes = [C.c_int, C.c_double]
+    params, ini = fx.cbl_inputs()
+    ini = np.ascontiguousarray(ini[:1])                       # day 1 only: day 2 finds no row of its own
+    d = fx.state_init(2005)
+    d.update(params)
+    d["initialdata_use"] = [1]
+    met = fx.forcing(2005)[:288 + 36]
+    n = met.shape[0]
+
+    def run(nsteps):
+        bl = np.full((nsteps, 22), -999.0, order="F")
+        L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+        L.so_set_bl_block(bl.ctypes.data_as(dp))
+        cell = ol.Cell(d)
+        try:
+            out = cell.run(met[:nsteps], want=("SUEWS",))["SUEWS"]
+        finally:
+            L.so_set_bl_block(None)
+            L.so_set_cbl_initial(None, 0)
+        return cell, out, bl
+    for nsteps in (36, n):                                    # 03:00 of day 1 (a night step), 03:00 of day 2
+        cell, su, bl = run(nsteps)
+        assert met[nsteps - 1, 14] < 5                        # Kdown: night
+        get = lambda k: float(cell.get_state(k)[0])           # noqa: E731
+        row, line, s = ini[0], bl[-1], su[-1]
+        assert line[5] == 200.0 and line[6] == row[6] and line[7] == row[7]
+        assert get("cbl_gamq_kgkgm") == row[3] / float(np.float32(1000.0))
+        if nsteps == 36:
+            k, c2k = float(np.float32(0.4)), float(np.float32(273.16))
+            Temp_C, avrh, qh, qe, press, ustar, avdens, avcp = line[10], line[11], line[12], line[13], line[14], line[16], line[17], line[19]
+            assert qh == s[5 + 8] and qe == s[5 + 9] and ustar == s[5 + 54]
+            psih = L.so_stab_psi_heat(3, (d["z"][0] - s[5 + 53]) / s[5 + 55])
+            gas = float(np.float32(8.31451) / np.float32(0.028965))
+            tm_zm = (Temp_C + c2k) * (1000 / press) ** (gas / avcp)
+            tm = tm_zm - psih * qh / (k * ustar * avcp * avdens)
+            assert get("cbl_blh_m") == row[1] and get("cbl_gamt_Km") == row[2]
+            assert abs(get("cbl_tm_K") - tm) <= 1e-12 * tm and get("cbl_tp_K") == get("cbl_tm_K")
+            assert abs(tm - row[6]) < 5.0 and tm != row[6]     # a correction of the file's theta, not the file's theta
+            assert get("cbl_qp_kgkg") == get("cbl_qm_kgkg") and 0 < get("cbl_qm_kgkg") < 0.03
+        else:
+            assert get("cbl_blh_m") == 200.0 and get("cbl_tm_K") == row[6] and get("cbl_tp_K") == row[4]
+            assert get("cbl_qp_kgkg") <= row[5] / 1000 and get("cbl_qm_kgkg") <= row[7] / 1000
+    # InitialData_use = 0 has no behaviour in the reference (it reads a table it never allocated): refused
+    d["initialdata_use"] = [0]
+    cell = ol.Cell(d)
+    L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+    try:
+        with pytest.raises(Exception):
+            cell.run(met[:2], want=("SUEWS",))
+    finally:
+        L.so_set_cbl_initial(None, 0)
