@@ -139,7 +139,7 @@ int suews_b200_set_anohm_forcing(suews_b200_handle h, const double *met, int nro
 
 /* BLUEWS, the convective boundary-layer slab model (suews_phys_bluews.f95; the reference's grid loop runs it after every
  * SUEWS_cal_Main, suews_ctrl_calculations.f95:194-218).  Class fields: CBLuse (RunControl.nml) and CBLInput.nml's
- * EntrainmentType, QH_choice (1 SUEWS, 2 LUMPS), isubs, CO2_included, InitialData_use (2), sondeflag (0), wsb.  The slab's
+ * EntrainmentType, QH_choice (1 SUEWS, 2 LUMPS), isubs, CO2_included, InitialData_use (1 or 2), sondeflag (0), wsb.  The slab's
  * variables are per-cell state of kind SUEWS_KIND_ESTM_STATE (cbl_blh_m, cbl_tm_K, cbl_qm_kgkg, cbl_tp_K, cbl_qp_kgkg, cbl_cm,
  * cbl_gamt_Km, cbl_gamq_kgkgm).  ini is IniCBLdata, the rows of CBL_initial_data.txt ([nline x 8] row-major: DOY zi0 gamt
  * gamq theta+ q+ theta q), shared by the batch.  Output: the "BL" group of get_block ([nsteps x 22]: the five date columns,
