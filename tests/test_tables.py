@@ -191,3 +191,30 @@ def test_grid_loop_of_a_run_directory_as_classes_and_cells(tmp_path):
     kinds = [c[0] for c in r.calls]
     assert kinds.count("set_class_param") == 2 * len(ga["classes"][0]) and kinds.count("set_cell_class") == 1
     assert kinds.count("set_cell_param") == len(ga["cells"]) and kinds.count("set_state") == len(ga["state"]) and kinds[-1] == "set_clock"
+
+
+def test_grid_loop_picks_the_initial_conditions_file_as_the_reference_does(tmp_path):
+    """MultipleInitFiles = 1: InitialConditions<FileCode><grid>_<year>.nml per grid (suews_ctrl_init.f95, InitialState's file
+    name); 0: the shared InitialConditions<FileCode>_<year>.nml; a function grid -> path overrides both."""
+    import shutil
+    run = _three_grid_run(tmp_path)
+    inp = os.path.join(run, "Input")
+    shared = os.path.join(inp, "InitialConditionstest_2004.nml")
+    text = open(shared).read()
+    assert "SoilstorePavedState" in text
+    for g, v in ((1, 100.0), (2, 110.0), (3, 120.0)):
+        lines = [("SoilstorePavedState=%g" % v) if ln.strip().lower().startswith("soilstorepavedstate") else ln for ln in text.splitlines()]
+        open(os.path.join(inp, "InitialConditionstest%d_2004.nml" % g), "w").write("\n".join(lines) + "\n")
+    rcp = os.path.join(run, "RunControl.nml")
+    rc_text = open(rcp).read()
+    assert "MultipleInitFiles=0" in rc_text.replace(" ", "")
+    ga0 = tables.grid_arguments(run, 2004)
+    assert len(set(ga0["state"]["soilstore_id"][:, 0])) == 1
+    open(rcp, "w").write(rc_text.replace("MultipleInitFiles=0", "MultipleInitFiles=1").replace("MultipleInitFiles = 0", "MultipleInitFiles=1"))
+    ga1 = tables.grid_arguments(run, 2004)
+    assert list(ga1["state"]["soilstore_id"][:, 0]) == [100.0, 110.0, 120.0]
+    ga2 = tables.grid_arguments(run, 2004, initial_conditions=lambda g: os.path.join(inp, "InitialConditionstest%d_2004.nml" % (4 - g)))
+    assert list(ga2["state"]["soilstore_id"][:, 0]) == [120.0, 110.0, 100.0]
+    ga3 = tables.grid_arguments(run, 2004, grids=[3, 1])
+    assert ga3["grids"] == [3, 1] and list(ga3["class_of_grid"]) == [0, 1] and list(ga3["state"]["soilstore_id"][:, 0]) == [120.0, 100.0]
+    shutil.rmtree(run)
