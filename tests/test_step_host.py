@@ -1,0 +1,232 @@
+"""The device-side timestep compiled for the host, against the oracle BIT FOR BIT.
+
+tests/host_step.cpp includes suews_b200/csrc/dev_step.cuh -- the source of the CUDA kernel's cell-step with every stage header it
+pulls in -- defines the device qualifiers away, maps the CUDA math wrappers to libm (the functions the oracle calls) and drives
+one cell the way suews_run_kernel drives a thread under output policy FULL.  Hoisting out of the surface-temperature loop, the
+deferred state update, the wet-bulb memo and its float screen, cycle detection, the in-place stores, the per-instance
+specialisations: each of them claims to leave the reference's arithmetic untouched.  Here the claim is checked on the CPU,
+without tolerance: every output column of every step and the state at the end equal the oracle's to the last bit, for the
+BaseRun over a whole year, the scheme sweep of the GPU parity tests, ESTM, AnOHM and BLUEWS.  The single documented
+exception is the psi-hat integration of the roughness-sublayer diagnostics (dev_rsl.cuh adds the same terms in another order,
+<= n 2^-53 relative): T2, Q2, U10, RH2 and the RSL profile block are compared at 1e-12.
+What remains between this build and the GPU is the math library alone (and the fast paths of dev_common.cuh / dev_math.cuh,
+which the device selftests check): that is the 1e-10 of the GPU parity tests."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fixtures as fx  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+from suews_b200.batch import all_fields  # noqa: E402
+
+dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+NCOL = {"SUEWS": 82, "snow": 98, "RSL": 133, "DailyState": 45, "SOLWEIG": 26, "ESTM": 27, "BL": 17}
+GROUPS = ["SUEWS", "snow", "RSL", "DailyState", "SOLWEIG", "ESTM", "BL"]
+RSL_COLS = [5 + 78, 5 + 79, 5 + 80, 5 + 81]          # T2 Q2 U10 RH2 of the SUEWS line: formed from the RSL profiles
+INTERNAL = ("alb1_hidden", "lv_switch", "rsl_cache")  # the library's own memo fields: no counterpart in the oracle's state
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("host_step") / "host_step.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out,
+                           os.path.join(ol.ROOT, "tests", "host_step.cpp")])
+    H = C.CDLL(out)
+    H.host_step_run.argtypes = [ip, dp, dp, dp, dp, dp, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(dp),
+                                C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
+    return H
+
+
+def _flat(d, kinds):
+    low = {k.lower(): v for k, v in d.items()}
+    out = []
+    for nm, kind, n in all_fields():
+        if kind not in kinds:
+            continue
+        if nm.lower() in low:
+            v = np.atleast_1d(np.asarray(low[nm.lower()], dtype=np.float64)).ravel()
+            assert v.size == n, (nm, v.size, n)
+        else:
+            v = np.full(n, -999.0 if nm == "anohm_coeff_grid_day" else 0.0)   # as suews_b200_create leaves them
+        out.append(v)
+    return np.concatenate(out)
+
+
+def run_host(H, d, met, groups, instance=0, record=False, ts5=None, cbl_ini=None):
+    """-> (fatal code, {group: block [n, 5 + ncol]}, {state name: values}, warning masks)"""
+    ci = np.ascontiguousarray(_flat(d, (0,)).astype(np.int32))
+    cd, ce, st = (np.ascontiguousarray(_flat(d, (k,))) for k in (1, 2, 3))
+    es = np.ascontiguousarray(_flat(d, (4,))) if record else None
+    n = met.shape[0]
+    m = np.asfortranarray(met)
+    t = np.asfortranarray(ts5) if ts5 is not None else None
+    ini = np.ascontiguousarray(cbl_ini) if cbl_ini is not None else None
+    blks = {g: np.full((n, 5 + NCOL[g]), -999.0, order="F") for g in groups}
+    arr = (dp * 7)(*[blks[g].ctypes.data_as(dp) if g in blks else None for g in GROUPS])
+    warn = (C.c_ulonglong * 2)()
+    iters = C.c_longlong()
+    rc = H.host_step_run(ci.ctypes.data_as(ip), cd.ctypes.data_as(dp), ce.ctypes.data_as(dp), st.ctypes.data_as(dp),
+                         es.ctypes.data_as(dp) if record else None, m.ctypes.data_as(dp), n,
+                         t.ctypes.data_as(dp) if t is not None else None, ini.ctypes.data_as(dp) if ini is not None else None,
+                         ini.shape[0] if ini is not None else 0, int(d["dt_since_start"][0]),
+                         int(d.get("tstep_prev", d["tstep"])[0]), instance, arr, warn, C.byref(iters))
+    state, k3, k4 = {}, 0, 0
+    for nm, kind, cnt in all_fields():
+        if kind == 3:
+            state[nm] = st[k3:k3 + cnt]
+            k3 += cnt
+        elif kind == 4 and record:
+            state[nm] = es[k4:k4 + cnt]
+            k4 += cnt
+    return rc, blks, state, (warn[0], warn[1])
+
+
+def same_bits(a, b):
+    return (a == b) | (np.isnan(a) & np.isnan(b))
+
+
+FC_COLS = [5 + 58, 5 + 59, 5 + 60]                   # Fc FcPhoto FcRespi
+
+
+def check_blocks(blks, ref, where="", t2_feeds_co2=False):
+    """t2_feeds_co2: with gsModel 3 / 4 the biogenic CO2 fluxes are evaluated at the RSL's 2 m temperature (driver.f95:1224-1262),
+    so they inherit its last-ulp difference."""
+    for g, a in blks.items():
+        b = ref[g]
+        ok = same_bits(a, b)
+        loose = (RSL_COLS + (FC_COLS if t2_feeds_co2 else [])) if g == "SUEWS" else (list(range(5, a.shape[1])) if g == "RSL" else [])
+        strict = np.ones(a.shape[1], dtype=bool)
+        strict[loose] = False
+        bad = np.argwhere(~ok[:, strict])
+        assert bad.size == 0, (where, g, "first differing (row, strict column):", bad[:5].tolist())
+        if loose:
+            al, bl = a[:, loose], b[:, loose]
+            assert np.array_equal(np.isnan(al), np.isnan(bl)), (where, g, "NaN pattern")
+            fin = ~np.isnan(bl)
+            if fin.any():
+                e = np.abs(al[fin] - bl[fin]) / np.maximum(np.abs(bl[fin]), 1e-3)
+                assert float(e.max()) <= 1e-12, (where, g, float(e.max()))
+
+
+def check_state(state, cell, names=None, where=""):
+    n = 0
+    for nm, v in state.items():
+        if nm in INTERNAL or (names is not None and nm not in names):
+            continue
+        try:
+            r = cell.get_state(nm)
+        except KeyError:
+            continue
+        assert np.all(same_bits(v, r)), (where, nm, v, r)
+        n += 1
+    return n
+
+
+def test_baserun_year_2004_is_bit_identical(host):
+    """All 105 408 steps of 2004 (snow on the ground in January, melt, summer, rain, every daily update) from the
+    reference's dump: the 82-column line, the snow line and the DailyState line of every step, and the state at the end."""
+    d = fx.state_init(2004)
+    met = fx.forcing(2004)
+    groups = ("SUEWS", "snow", "DailyState")
+    rc, blks, state, _w = run_host(host, d, met, groups)
+    assert rc == 0
+    cell = ol.Cell(d)
+    ref = cell.run(met, want=groups)
+    check_blocks(blks, ref, "2004")
+    assert check_state(state, cell, where="end of 2004") >= 25
+    differ = int((~same_bits(blks["SUEWS"][:, RSL_COLS], ref["SUEWS"][:, RSL_COLS])).sum())
+    assert differ < 0.5 * 4 * met.shape[0]          # even the re-ordered psi-hat sums mostly land on the same double
+
+
+@pytest.mark.parametrize("instance", [0, 2], ids=["generic", "snow-on-OHM"])
+def test_baserun_2005_every_output_group(host, instance):
+    """The five golden days of 2005, all five output groups (SOLWEIG and the RSL profiles included), through the generic
+    instance and through the snow-on specialisation the BaseRun's bucket launches."""
+    d = fx.state_init(2005)
+    met = fx.forcing(2005)[:1440]
+    groups = ("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG")
+    rc, blks, state, _w = run_host(host, d, met, groups, instance=instance)
+    assert rc == 0
+    cell = ol.Cell(d)
+    check_blocks(blks, cell.run(met, want=groups), "2005")
+    check_state(state, cell, where="2005 day 5")
+
+
+BIOCO2 = dict(theta_bioco2=[0.96] * 3, alpha_enh_bioco2=[0.016] * 3, beta_enh_bioco2=[33.454] * 3)
+SWEEP = [
+    dict(snowuse=0, netradiationmethod=3, emissionsmethod=2),
+    dict(netradiationmethod=1), dict(netradiationmethod=2), dict(netradiationmethod=3), dict(netradiationmethod=11),
+    dict(netradiationmethod=100), dict(netradiationmethod=300), dict(netradiationmethod=0),
+    dict(netradiationmethod=0, snowuse=0), dict(netradiationmethod=12), dict(netradiationmethod=200),
+    dict(stabilitymethod=2), dict(stabilitymethod=4), dict(stabilitymethod=1), dict(stabilitymethod=5), dict(stabilitymethod=6),
+    dict(stabilitymethod=7),
+    dict(roughlenheatmethod=1), dict(roughlenheatmethod=3), dict(roughlenheatmethod=4), dict(roughlenheatmethod=5),
+    dict(roughlenmommethod=1), dict(roughlenmommethod=3),
+    dict(emissionsmethod=0), dict(emissionsmethod=2), dict(emissionsmethod=3), dict(emissionsmethod=4),
+    dict(emissionsmethod=5), dict(emissionsmethod=6),
+    dict(storageheatmethod=0), dict(ohmincqf=1), dict(evapmethod=1), dict(aerodynamicresistancemethod=1),
+    dict(aerodynamicresistancemethod=3), dict(gsmodel=1), dict(smdmethod=1), dict(waterusemethod=1),
+    dict(basetmethod=2), dict(laicalcyes=0),
+    dict(emissionsmethod=11), dict(emissionsmethod=14), dict(emissionsmethod=22, **BIOCO2), dict(emissionsmethod=33, **BIOCO2),
+    dict(emissionsmethod=36, theta_bioco2=[0.9, 0.96, 0.8], alpha_enh_bioco2=[0.016] * 3, beta_enh_bioco2=[33.454] * 3),
+    dict(emissionsmethod=41), dict(emissionsmethod=45, gsmodel=4), dict(emissionsmethod=12, gsmodel=3),
+]
+
+
+def _with(d, over):
+    for k, v in over.items():
+        d[k] = list(v) if isinstance(v, (list, tuple)) else [v]
+    if over.get("snowuse", 1) == 0:
+        for k in ("snowpack", "snowfrac", "snowwater"):
+            d[k] = [0.0] * 7
+    return d
+
+
+@pytest.mark.parametrize("year,days", [(2005, 2), (2004, 3)], ids=["mild-start", "winter-start"])
+def test_scheme_sweep_is_bit_identical(host, year, days):
+    """Every scheme option of the GPU parity sweep (the reference's BTS_config.nml physics sweep and the stability /
+    emission / radiation methods it leaves out), from the mild 2005 start and from the 2004 start with snow on the ground."""
+    met0 = fx.forcing(year)[:288 * days]
+    for over in SWEEP:
+        d = _with(fx.state_init(year), over)
+        met = met0.copy()
+        if over.get("smdmethod", 0) > 0:
+            met[:, 19] = 30.0
+        groups = ("SUEWS", "snow") if d["snowuse"][0] == 1 else ("SUEWS",)
+        inst = [0] + ([1 if d["snowuse"][0] == 0 else 2] if d["storageheatmethod"][0] in (0, 1) else [])
+        cell = ol.Cell(d)
+        ref = cell.run(met, want=groups)
+        for instance in inst:
+            rc, blks, state, _w = run_host(host, d, met, groups, instance=instance)
+            assert rc == 0, over
+            check_blocks(blks, ref, (year, over, instance), t2_feeds_co2=over.get("gsmodel", 2) in (3, 4))
+            check_state(state, cell, where=(year, over, instance))
+
+
+def test_perturbed_cells_are_bit_identical(host):
+    """The synthetic cells of the bench (perturbed fractions, site, morphology, forcing offsets) for the default and the
+    snow scheme sets: one day each against a per-cell oracle run."""
+    from suews_b200 import synth
+    met = fx.forcing(2005)[:288]
+    for scheme in ("default", "snow"):
+        base = synth.base_with_scheme(fx.state_init(2005), scheme)
+        arrs = synth.cell_site_arrays(0, 24, base, offsets=True)
+        for c in range(24):
+            d = dict(base)
+            for k, v in arrs.items():
+                d[k.lower()] = list(np.atleast_1d(v[c]))
+            m = met.copy()
+            m[:, 11] += d.get("dtemp_c", [0.0])[0]
+            m[:, 10] = np.clip(m[:, 10] + d.get("drh", [0.0])[0], 5.0, 100.0)
+            dd = {k: v for k, v in d.items() if k not in ("dtemp_c", "drh")}
+            cell = ol.Cell(dd)
+            ref = cell.run(m, want=("SUEWS",))
+            rc, blks, state, _w = run_host(host, dd, m, ("SUEWS",))
+            assert rc == 0
+            check_blocks(blks, ref, (scheme, c))
+            check_state(state, cell, where=(scheme, c))
