@@ -220,13 +220,97 @@ def test_perturbed_cells_are_bit_identical(host):
             d = dict(base)
             for k, v in arrs.items():
                 d[k.lower()] = list(np.atleast_1d(v[c]))
+            # the cell's forcing offsets are applied by the step itself; the oracle gets the shifted series
             m = met.copy()
-            m[:, 11] += d.get("dtemp_c", [0.0])[0]
-            m[:, 10] = np.clip(m[:, 10] + d.get("drh", [0.0])[0], 5.0, 100.0)
-            dd = {k: v for k, v in d.items() if k not in ("dtemp_c", "drh")}
-            cell = ol.Cell(dd)
+            m[:, 11] += d["dtemp_c"][0]
+            m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + d["drh"][0]))
+            cell = ol.Cell({k: v for k, v in d.items() if k not in ("dtemp_c", "drh")})
             ref = cell.run(m, want=("SUEWS",))
-            rc, blks, state, _w = run_host(host, dd, m, ("SUEWS",))
+            rc, blks, state, _w = run_host(host, d, met, ("SUEWS",))
             assert rc == 0
             check_blocks(blks, ref, (scheme, c))
             check_state(state, cell, where=(scheme, c))
+
+
+ESTM_VARIANTS = [dict(), dict(evolveTibld=1, ibldCHmod=1), dict(evolveTibld=2, ibldCHmod=2), dict(TsurfChoice=1),
+                 dict(TsurfChoice=2, evolveTibld=1), dict(storageheatmethod=14)]
+
+
+@pytest.mark.parametrize("over", ESTM_VARIANTS, ids=lambda o: "-".join("%s%s" % kv for kv in o.items()) or "baserun")
+def test_estm_is_bit_identical(host, over):
+    """StorageHeatMethod 4 / 14 over two days: the 82-column line, the ESTM line and the element temperatures ESTM carries."""
+    from suews_b200 import estm
+    d = dict(fx.state_init(2005))
+    over = dict(over)
+    d["storageheatmethod"] = [over.pop("storageheatmethod", 4)]
+    ep = fx.estm_example(d["surfacearea"][0], **over)
+    d.update({k.lower(): v for k, v in ep.items()})
+    met = fx.forcing(2005)[:576]
+    ts = fx.estm_ts_forcing(met)
+    cell = ol.Cell(d)
+    cell.estm_start(ts[0])
+    ref = cell.run(met, want=("SUEWS", "ESTM"), ts5=ts)
+    dh = dict(d)
+    dh.update({k.lower(): list(np.atleast_1d(v)) for k, v in estm.initial_state(ep, d["sfr"], d["emis"], ts[0]).items()})
+    groups = ("SUEWS", "ESTM") if d["storageheatmethod"][0] == 4 else ("SUEWS",)
+    rc, blks, state, _w = run_host(host, dh, met, groups, record=True, ts5=ts)
+    assert rc == 0
+    check_blocks(blks, ref, over)
+    names = ("Tievolve", "Tground", "Twall", "Troof", "Tibld", "Tw_4", "T0_ibld", "TN_wall", "TN_roof", "lup_ground", "lup_wall",
+             "lup_roof", "Tair2", "HVAC", "Tair2Set", "NewtonConverged", "state_id", "soilstore_id", "qn1_av", "dqndt")
+    assert check_state(state, cell, names=names, where=over) == len(names)
+
+
+@pytest.mark.parametrize("over", [{}, {"snowuse": 0, "netradiationmethod": 3, "emissionsmethod": 2},
+                                  {"snowuse": 0, "netradiationmethod": 3, "emissionsmethod": 0, "ohmincqf": 1}],
+                         ids=["baserun", "default-set", "incqf"])
+def test_anohm_is_bit_identical(host, over):
+    """StorageHeatMethod 3 over 2 days + 20 steps (three Levenberg-Marquardt / hybrid fits per surface): with the same libm
+    on both sides even the fitted coefficients agree to the last bit -- the 1e-5 of the GPU tests is the math library's."""
+    from suews_b200 import synth
+    d = fx.state_init(2005)
+    d.update({k: list(v) for k, v in synth.ANOHM_EXAMPLE.items()})
+    d["storageheatmethod"] = [3]
+    _with(d, over)
+    met = fx.forcing(2005)[:288 * 2 + 20]
+    cell = ol.Cell(d)
+    ref = cell.run(met, want=("SUEWS", "DailyState"))
+    rc, blks, state, _w = run_host(host, d, met, ("SUEWS", "DailyState"), record=True)
+    assert rc == 0
+    check_blocks(blks, ref, over)
+    names = ("anohm_id_save", "anohm_coef_id_save", "anohm_coef_grid_save", "anohm_coeff_grid_day", "qn1_av", "dqndt", "state_id",
+             "soilstore_id")
+    assert check_state(state, cell, names=names, where=over) == len(names)
+    assert (state["anohm_coeff_grid_day"] != -999.0).all()
+
+
+@pytest.mark.parametrize("mode,et,isubs", [(2, 4, 0), (1, 1, 1), (2, 3, 0)])
+def test_bluews_in_the_step_is_bit_identical(host, mode, et, isubs):
+    """BLUEWS as the step's last stage (psih recomputed from the step's own z/L for InitialData_use 1): the BL line of three
+    summer days and the slab variables."""
+    L = ol.lib()
+    L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+    L.so_set_bl_block.argtypes = [dp]
+    params, ini = fx.cbl_inputs()
+    ini = np.ascontiguousarray(ini)
+    d = fx.state_init(2004)
+    d.update(params)
+    d.update(initialdata_use=[mode], entrainmenttype=[et], isubs=[isubs])
+    met = fx.forcing(2004)[288 * 150:288 * 153]
+    n = met.shape[0]
+    bl = np.full((n, 22), -999.0, order="F")
+    L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+    L.so_set_bl_block(bl.ctypes.data_as(dp))
+    cell = ol.Cell(d)
+    try:
+        ref = cell.run(met, want=("SUEWS",))
+    finally:
+        L.so_set_bl_block(None)
+        L.so_set_cbl_initial(None, 0)
+    ref["BL"] = bl
+    rc, blks, state, _w = run_host(host, d, met, ("SUEWS", "BL"), record=True, cbl_ini=ini)
+    assert rc == 0
+    check_blocks(blks, ref, (mode, et, isubs))
+    names = ("cbl_blh_m", "cbl_tm_K", "cbl_qm_kgkg", "cbl_tp_K", "cbl_qp_kgkg", "cbl_gamt_Km", "cbl_gamq_kgkgm")
+    assert check_state(state, cell, names=names) == len(names)
+    assert bl[:, 5].max() > 400.0
