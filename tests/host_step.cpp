@@ -64,10 +64,12 @@ static void host_pack_step(SuewsStepRec &r, const double *met, size_t n, size_t 
    r.pad0_ = 0; r.pad1_ = 0;
 }
 
-template <int SNOWK, int ESTMK>
+// K: 0 every output line of every step (policy FULL), 1 the 82-column line accumulated into acc[82], 2 the seven parity sums
+// into acc[7] (policy P0; flux_only: the diagnostics no flux sum depends on are skipped, as the bench's launches do)
+template <int K, int SNOWK, int ESTMK>
 static int run_cell(SuewsClassParams &P, SuewsCellParams &C, SuewsCellState &S, SuewsEstmState *ES, const SuAnohmIn *AN,
                     const double *met, int nsteps, const double *ts5, int dt_since_start, int tstep_prev, double **blk,
-                    SuDiag &dg, long long *iters_out)
+                    SuDiag &dg, long long *iters_out, double *acc = nullptr, bool flux_only = false)
 {
    SuDaily D;
    for (int i = 0; i < 12; i++) D.HDD_id[i] = S.HDD_id[i];
@@ -95,9 +97,9 @@ static int run_cell(SuewsClassParams &P, SuewsCellParams &C, SuewsCellState &S, 
       double ts9[SUEWS_N_TS5];
       if (ts5)
          for (int c = 0; c < SUEWS_N_TS5; c++) ts9[c] = ts5[(size_t)gs + n * (size_t)(4 + c)];
-      iters += suews_step<0, SNOWK, ESTMK>(true, dg, P, C, site, R, E, dt_since_start, (gs == 0) ? tstep_prev : (int)P.tstep, S, D,
-                                                         nullptr, nullptr, L, ES, ts5 ? ts9 : nullptr, 0, 0, false, AN);
-      if (!dg.fatal) {
+      iters += suews_step<K, SNOWK, ESTMK>(true, dg, P, C, site, R, E, dt_since_start, (gs == 0) ? tstep_prev : (int)P.tstep, S, D,
+                                           (K == 1) ? acc : nullptr, (K == 2) ? acc : nullptr, L, ES, ts5 ? ts9 : nullptr, 0, 0, flux_only, AN);
+      if (K == 0 && !dg.fatal) {
          double *lines[7] = {l_su, l_sn, l_rs, l_da, l_so, l_es, l_bl};
          for (int g = 0; g < 7; g++) {
             if (!blk[g]) continue;
@@ -126,11 +128,14 @@ static int run_cell(SuewsClassParams &P, SuewsCellParams &C, SuewsCellState &S, 
 // suews_fields.h (cell and state: COLD fields, then HOT fields).  state and estm are updated in place.  blk[7]: SUEWS snow
 // RSL DailyState SOLWEIG ESTM BL, each [nsteps x (5 + ncol)] column-major, or NULL.  instance: 0 generic (switches read
 // from the class record, <-1,-1>), 1 the snow-off OHM instance <0,0>, 2 the snow-on OHM instance <1,0>.
+// kind: 0 output blocks, 1 the 82-column line summed into acc[82], 2 the seven parity sums (QN QF QS QH QE RO SWE) into acc[7];
+// acc enters holding the sums so far (zero them before the first call).
 // ts5: the ESTM surface-temperature forcing [nsteps x 13] column-major or NULL; cbl_ini: IniCBLdata [cbl_nline x 8] row-major or NULL.
 #include <vector>
 extern "C" int host_step_run(const int *class_int, const double *class_dbl, const double *cell, double *state, double *estm,
                              const double *met, int nsteps, const double *ts5, const double *cbl_ini, int cbl_nline,
-                             int dt_since_start, int tstep_prev, int instance, double **blk, unsigned long long *warn2, long long *iters)
+                             int dt_since_start, int tstep_prev, int instance, double **blk, unsigned long long *warn2, long long *iters,
+                             int kind, int flux_only, double *acc)
 {
    static SuewsClassParams P;
    SuewsCellParams C;
@@ -202,9 +207,13 @@ extern "C" int host_step_run(const int *class_int, const double *class_dbl, cons
    SuDiag dg = {0, {0, 0}};
    long long it = 0;
    int rc;
-   if (instance == 1) rc = run_cell<0, 0>(P, C, S, nullptr, nullptr, met, nsteps, ts5, dt_since_start, tstep_prev, blk, dg, &it);
-   else if (instance == 2) rc = run_cell<1, 0>(P, C, S, nullptr, nullptr, met, nsteps, ts5, dt_since_start, tstep_prev, blk, dg, &it);
-   else rc = run_cell<-1, -1>(P, C, S, estm ? &ES : nullptr, estm ? &an : nullptr, met, nsteps, ts5, dt_since_start, tstep_prev, blk, dg, &it);
+   SuewsEstmState *es = estm ? &ES : nullptr;
+   const SuAnohmIn *anp = estm ? &an : nullptr;
+#define RUN(K_, SN_, ES_, es_, an_) run_cell<K_, SN_, ES_>(P, C, S, es_, an_, met, nsteps, ts5, dt_since_start, tstep_prev, blk, dg, &it, acc, flux_only != 0)
+   if (kind == 0) rc = (instance == 1) ? RUN(0, 0, 0, nullptr, nullptr) : ((instance == 2) ? RUN(0, 1, 0, nullptr, nullptr) : RUN(0, -1, -1, es, anp));
+   else if (kind == 1) rc = (instance == 1) ? RUN(1, 0, 0, nullptr, nullptr) : ((instance == 2) ? RUN(1, 1, 0, nullptr, nullptr) : RUN(1, -1, -1, es, anp));
+   else rc = (instance == 1) ? RUN(2, 0, 0, nullptr, nullptr) : ((instance == 2) ? RUN(2, 1, 0, nullptr, nullptr) : RUN(2, -1, -1, es, anp));
+#undef RUN
    k = 0;
 #define X(name, n) for (int i = 0; i < n; i++) state[k++] = S.name.v[i];
    SUEWS_STATE_COLD_FIELDS(X)

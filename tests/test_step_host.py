@@ -38,7 +38,7 @@ def host(tmp_path_factory):
                            os.path.join(ol.ROOT, "tests", "host_step.cpp")])
     H = C.CDLL(out)
     H.host_step_run.argtypes = [ip, dp, dp, dp, dp, dp, C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(dp),
-                                C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)]
+                                C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong), C.c_int, C.c_int, dp]
     return H
 
 
@@ -57,8 +57,9 @@ def _flat(d, kinds):
     return np.concatenate(out)
 
 
-def run_host(H, d, met, groups, instance=0, record=False, ts5=None, cbl_ini=None):
-    """-> (fatal code, {group: block [n, 5 + ncol]}, {state name: values}, warning masks)"""
+def run_host(H, d, met, groups, instance=0, record=False, ts5=None, cbl_ini=None, kind=0, flux_only=False, acc=None):
+    """-> (fatal code, {group: block [n, 5 + ncol]}, {state name: values}, warning masks)
+    kind 1 / 2: no blocks; the 82 / 7 running sums are added to `acc` (output policies P0+ / P0 of the library)"""
     ci = np.ascontiguousarray(_flat(d, (0,)).astype(np.int32))
     cd, ce, st = (np.ascontiguousarray(_flat(d, (k,))) for k in (1, 2, 3))
     es = np.ascontiguousarray(_flat(d, (4,))) if record else None
@@ -74,7 +75,8 @@ def run_host(H, d, met, groups, instance=0, record=False, ts5=None, cbl_ini=None
                          es.ctypes.data_as(dp) if record else None, m.ctypes.data_as(dp), n,
                          t.ctypes.data_as(dp) if t is not None else None, ini.ctypes.data_as(dp) if ini is not None else None,
                          ini.shape[0] if ini is not None else 0, int(d["dt_since_start"][0]),
-                         int(d.get("tstep_prev", d["tstep"])[0]), instance, arr, warn, C.byref(iters))
+                         int(d.get("tstep_prev", d["tstep"])[0]), instance, arr, warn, C.byref(iters), int(kind), int(bool(flux_only)),
+                         acc.ctypes.data_as(dp) if acc is not None else None)
     state, k3, k4 = {}, 0, 0
     for nm, kind, cnt in all_fields():
         if kind == 3:
@@ -314,3 +316,51 @@ def test_bluews_in_the_step_is_bit_identical(host, mode, et, isubs):
     names = ("cbl_blh_m", "cbl_tm_K", "cbl_qm_kgkg", "cbl_tp_K", "cbl_qp_kgkg", "cbl_gamt_Km", "cbl_gamq_kgkgm")
     assert check_state(state, cell, names=names) == len(names)
     assert bl[:, 5].max() > 400.0
+
+
+PARITY_COLS = [5, 6, 7, 8, 9, 16, 71]                # QN QF QS QH QE RO SWE in the 82-column line
+
+
+@pytest.mark.parametrize("instance", [0, 2], ids=["generic", "snow-on-OHM"])
+def test_accumulating_policies_over_the_year(host, instance):
+    """What the bench launches: output policy P0 (seven flux sums per cell, no output line formed, the diagnostics no flux
+    depends on skipped) and the 82-column running sums, over all of 2004.  The sums equal the oracle's lines added up in step
+    order, bit for bit, and the state at the end is the state of the run that wrote every line."""
+    d = fx.state_init(2004)
+    met = fx.forcing(2004)
+    cell = ol.Cell(d)
+    ref = cell.run(met, want=("SUEWS",))["SUEWS"][:, 5:]
+    seq = np.cumsum(ref, axis=0)[-1]                  # (cumsum adds strictly in order, as the accumulators do)
+    acc7 = np.zeros(7)
+    rc, _b, state, _w = run_host(host, d, met, (), instance=instance, kind=2, flux_only=True, acc=acc7)
+    assert rc == 0
+    assert np.array_equal(acc7, seq[PARITY_COLS]), (acc7, seq[PARITY_COLS])
+    check_state(state, cell, where="P0, flux only")
+    acc82 = np.zeros(82)
+    rc, _b, state, _w = run_host(host, d, met, (), instance=instance, kind=1, acc=acc82)
+    assert rc == 0
+    strict = [c for c in range(82) if c + 5 not in RSL_COLS]
+    assert np.all(same_bits(acc82[strict], seq[strict])), np.argwhere(~same_bits(acc82[strict], seq[strict])).ravel()
+    loose = [c - 5 for c in RSL_COLS]
+    assert np.allclose(acc82[loose], seq[loose], rtol=1e-12, atol=0, equal_nan=True)
+    check_state(state, cell, where="P0+")
+
+
+def test_policy_p0_in_two_launches_equals_one(host):
+    """A run cut in two launches (state, clock and sums handed over as the library does between advance calls) is the run."""
+    d = fx.state_init(2005)
+    met = fx.forcing(2005)[:1440]
+    one = np.zeros(7)
+    rc, _b, st1, _w = run_host(host, d, met, (), kind=2, flux_only=True, acc=one)
+    assert rc == 0
+    two = np.zeros(7)
+    rc, _b, mid, _w = run_host(host, d, met[:500], (), kind=2, flux_only=True, acc=two)
+    assert rc == 0
+    d2 = dict(d)
+    d2.update({k.lower(): list(v) for k, v in mid.items()})
+    d2["dt_since_start"] = [d["dt_since_start"][0] + 500 * d["tstep"][0]]
+    rc, _b, st2, _w = run_host(host, d2, met[500:], (), kind=2, flux_only=True, acc=two)
+    assert rc == 0
+    assert np.array_equal(one, two)
+    for k in st1:
+        assert np.all(same_bits(st1[k], st2[k])), k
