@@ -211,11 +211,12 @@ def test_scheme_sweep_is_bit_identical(host, year, days):
 
 
 def test_perturbed_cells_are_bit_identical(host):
-    """The synthetic cells of the bench (perturbed fractions, site, morphology, forcing offsets) for the default and the
-    snow scheme sets: one day each against a per-cell oracle run."""
+    """The synthetic cells of the bench (perturbed fractions, site, morphology, forcing offsets) for the bench's scheme sets
+    that need no extra input (default, snow, BaseRun, NetRadiationMethod 13, stability 2 / 4, AnOHM): one day each against a
+    per-cell oracle run."""
     from suews_b200 import synth
     met = fx.forcing(2005)[:288]
-    for scheme in ("default", "snow"):
+    for scheme in ("default", "snow", "baserun", "netrad13", "netrad300", "stab2", "stab4", "anohm"):
         base = synth.base_with_scheme(fx.state_init(2005), scheme)
         arrs = synth.cell_site_arrays(0, 24, base, offsets=True)
         for c in range(24):
@@ -228,7 +229,7 @@ def test_perturbed_cells_are_bit_identical(host):
             m[:, 10] = np.minimum(100.0, np.maximum(np.float64(np.float32(0.01)), m[:, 10] + d["drh"][0]))
             cell = ol.Cell({k: v for k, v in d.items() if k not in ("dtemp_c", "drh")})
             ref = cell.run(m, want=("SUEWS",))
-            rc, blks, state, _w = run_host(host, d, met, ("SUEWS",))
+            rc, blks, state, _w = run_host(host, d, met, ("SUEWS",), record=(scheme == "anohm"))
             assert rc == 0
             check_blocks(blks, ref, (scheme, c))
             check_state(state, cell, where=(scheme, c))
