@@ -115,6 +115,13 @@ def check_blocks(blks, ref, where="", t2_feeds_co2=False):
                 assert float(e.max()) <= 1e-12, (where, g, float(e.max()))
 
 
+def check_warnings(masks, ref, where=""):
+    """the warnings raised on the way (ErrorHint codes that let the run continue) are the same set"""
+    raised = {c for c in range(128) if ref["_warn"][c] > 0}
+    mask = {c for c in range(128) if (masks[c >> 6] >> (c & 63)) & 1}
+    assert mask == raised, (where, sorted(mask), sorted(raised))
+
+
 def check_state(state, cell, names=None, where=""):
     n = 0
     for nm, v in state.items():
@@ -141,6 +148,7 @@ def test_baserun_year_2004_is_bit_identical(host):
     ref = cell.run(met, want=groups)
     check_blocks(blks, ref, "2004")
     assert check_state(state, cell, where="end of 2004") >= 25
+    check_warnings(_w, ref, "2004")
     differ = int((~same_bits(blks["SUEWS"][:, RSL_COLS], ref["SUEWS"][:, RSL_COLS])).sum())
     assert differ < 0.5 * 4 * met.shape[0]          # even the re-ordered psi-hat sums mostly land on the same double
 
@@ -207,6 +215,7 @@ def test_scheme_sweep_is_bit_identical(host, year, days):
             rc, blks, state, _w = run_host(host, d, met, groups, instance=instance)
             assert rc == 0, over
             check_blocks(blks, ref, (year, over, instance), t2_feeds_co2=over.get("gsmodel", 2) in (3, 4))
+            check_warnings(_w, ref, (year, over, instance))
             check_state(state, cell, where=(year, over, instance))
 
 
