@@ -374,3 +374,28 @@ def test_policy_p0_in_two_launches_equals_one(host):
     assert np.array_equal(one, two)
     for k in st1:
         assert np.all(same_bits(st1[k], st2[k])), k
+
+
+@pytest.mark.parametrize("over,met_edit,own", [
+    # no such storage-heat scheme: the reference runs on with an unset QS; the library refuses (1003) instead of inventing one
+    (dict(storageheatmethod=2), None, 1003),
+    (dict(netradiationmethod=7), None, None),                 # RadMethod's bare STOP (narp.f95:95-99)
+    (dict(storageheatmethod=4), None, 1005),                  # ESTM without its surface-temperature forcing: the library's own check
+    (dict(), ("Press_hPa", 12, 8000.0), None),                # forcing out of the accepted range
+    (dict(), ("avU1", 9, -1.0), None),
+    (dict(smdmethod=1), ("xsmd", 19, -999.0), None),          # observed soil moisture asked for, none given
+], ids=["storage2", "netrad7", "estm-no-forcing", "pressure", "wind", "xsmd"])
+def test_fatal_errors_are_the_oracles(host, over, met_edit, own):
+    """Where the reference STOPs (ErrorHint's fatal codes and the driver's own checks) the step stops the cell with the code
+    the oracle reports -- or, if the reference carries on, so do both."""
+    d = _with(fx.state_init(2005), over)
+    met = fx.forcing(2005)[:24].copy()
+    if met_edit:
+        met[6:, met_edit[1]] = met_edit[2]
+    try:
+        ol.Cell(d).run(met, want=("SUEWS",))
+        code = 0
+    except RuntimeError as e:
+        code = int(str(e).split("error")[1].split(":")[0])
+    rc, _b, _s, _w = run_host(host, d, met, ("SUEWS",), record=(over.get("storageheatmethod") == 4))
+    assert rc == (own if own is not None else code), (rc, code)
