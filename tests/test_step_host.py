@@ -399,3 +399,47 @@ def test_fatal_errors_are_the_oracles(host, over, met_edit, own):
         code = int(str(e).split("error")[1].split(":")[0])
     rc, _b, _s, _w = run_host(host, d, met, ("SUEWS",), record=(over.get("storageheatmethod") == 4))
     assert rc == (own if own is not None else code), (rc, code)
+
+
+def test_kernel_source_writes_the_reference_files(host):
+    """No oracle in between: the host build of the kernel's step, the hourly aggregation and the library's text writer
+    against the files the reference wrote -- the SUEWS and snow files of 2005 byte for byte, every printed field of the RSL
+    and SOLWEIG files (bar SOLWEIG's unassigned night-time I0), the DailyState files of 2005 and of all 366 days of 2004."""
+    from test_writer import _agg, _write_txt
+    d = fx.state_init(2005)
+    groups = ("SUEWS", "snow", "RSL", "DailyState", "SOLWEIG")
+    rc, blks, _s, _w = run_host(host, d, fx.forcing(2005), groups)
+    assert rc == 0
+    gold = lambda f: open(os.path.join(fx.GOLDEN, f)).read()      # noqa: E731
+    for g in ("SUEWS", "snow"):
+        assert _write_txt(_agg(blks[g], g), g, outlevel=2) == gold("ref_2005_%s_60.txt" % g), g
+    assert _write_txt(_agg(blks["RSL"], "RSL"), "RSL", outlevel=2).splitlines()[1:] == gold("ref_2005_RSL_60.txt").splitlines()[1:]
+    ours, ref = _write_txt(_agg(blks["SOLWEIG"], "SOLWEIG"), "SOLWEIG", outlevel=2).splitlines(), gold("ref_2005_SOLWEIG_60.txt").splitlines()
+    i0 = ref[0].split().index("I0")
+    assert ours[0] == ref[0] and len(ours) == len(ref)
+    assert all(x == y for a, b in zip(ours[1:], ref[1:]) for c, (x, y) in enumerate(zip(a.split(), b.split())) if c != i0)
+    rows = blks["DailyState"]
+    assert _write_txt(rows[rows[:, 5] != -999], "DailyState", outlevel=2) == gold("ref_2005_DailyState.txt")
+    rc, blks, _s, _w = run_host(host, fx.state_init(2004), fx.forcing(2004), ("DailyState",))
+    assert rc == 0
+    rows = blks["DailyState"]
+    assert _write_txt(rows[rows[:, 5] != -999], "DailyState", outlevel=2) == gold("ref_2004_DailyState.txt")
+
+
+@pytest.mark.parametrize("year,fname", [(2005, "ref_InitialConditions_2005_EndofRun.nml"), (2004, "ref_InitialConditions_2005.nml")])
+def test_kernel_source_ends_on_the_reference_checkpoint(host, year, fname):
+    """The InitialConditions namelist the reference wrote at the end of each leg of its golden run holds the exact doubles of
+    54 state variables (17 significant digits): the host build of the kernel's step, run under the bench's policy P0, ends
+    on every one of them bit for bit, and the library's writer turns that state into the reference's file byte for byte."""
+    from suews_b200 import checkpoint
+    acc = np.zeros(7)
+    rc, _b, state, _w = run_host(host, fx.state_init(year), fx.forcing(year), (), kind=2, flux_only=True, acc=acc,
+                                 instance=2)
+    assert rc == 0
+    ref = checkpoint.read(os.path.join(fx.GOLDEN, fname))
+    text = checkpoint.write_text(checkpoint.state_vector(lambda n: state[next(k for k in state if k.lower() == n.lower())]), snow_use=1)
+    ours = checkpoint.read_text(text)
+    assert ours.keys() == ref.keys() and len(ref) == 54
+    bad = [(k, ours[k], r) for k, r in ref.items() if ours[k] != r]
+    assert not bad, bad
+    assert text == open(os.path.join(fx.GOLDEN, fname)).read()
