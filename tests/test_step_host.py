@@ -472,7 +472,9 @@ def fuzz_trial(host, rng, snaps, met_all):
         d["sfr"] = list(sfr / sfr.sum())
     if rng.random() < 0.5:
         d["bldgh"], d["evetreeh"], d["dectreeh"] = [float(rng.uniform(3, 40))], [float(rng.uniform(2, 25))], [float(rng.uniform(2, 25))]
-        d["z"] = [float(max(d["bldgh"][0], d["evetreeh"][0], d["dectreeh"][0]) * rng.uniform(1.5, 4))]
+        # (above 10 m: with no profile level over 10 m the reference's interp_z indexes element 0 of a 1-based array,
+        # rslprof.f95:331-342 -- U10 is then whatever lies in front of the array; the library keeps the index in range)
+        d["z"] = [float(max(12.0, max(d["bldgh"][0], d["evetreeh"][0], d["dectreeh"][0]) * rng.uniform(1.5, 4)))]
     if rng.random() < 0.5:
         d["lat"], d["lng"] = [float(rng.uniform(-60, 70))], [float(rng.uniform(-170, 170))]
     off = int(rng.integers(0, 288)) if rng.random() < 0.3 else 0
