@@ -28,6 +28,7 @@ dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
 NCOL = {"SUEWS": 82, "snow": 98, "RSL": 133, "DailyState": 45, "SOLWEIG": 26, "ESTM": 27, "BL": 17}
 GROUPS = ["SUEWS", "snow", "RSL", "DailyState", "SOLWEIG", "ESTM", "BL"]
 RSL_COLS = [5 + 78, 5 + 79, 5 + 80, 5 + 81]          # T2 Q2 U10 RH2 of the SUEWS line: formed from the RSL profiles
+PARITY_COLS = [5, 6, 7, 8, 9, 16, 71]                # QN QF QS QH QE RO SWE in the 82-column line
 INTERNAL = ("alb1_hidden", "lv_switch", "rsl_cache")  # the library's own memo fields: no counterpart in the oracle's state
 
 
@@ -331,9 +332,6 @@ def test_bluews_in_the_step_is_bit_identical(host, mode, et, isubs):
     assert bl[:, 5].max() > 400.0
 
 
-PARITY_COLS = [5, 6, 7, 8, 9, 16, 71]                # QN QF QS QH QE RO SWE in the 82-column line
-
-
 @pytest.mark.parametrize("instance", [0, 2], ids=["generic", "snow-on-OHM"])
 def test_accumulating_policies_over_the_year(host, instance):
     """What the bench launches: output policy P0 (seven flux sums per cell, no output line formed, the diagnostics no flux
@@ -495,7 +493,10 @@ def fuzz_trial(host, rng, snaps, met_all):
         code = 0
     except RuntimeError as e:
         code = int(str(e).split("error")[1].split(":")[0])
-    rc, blks, state, warn = run_host(host, d, met, groups)
+    # the generic instance or the specialisation this class would be launched with
+    special = (1 if d["snowuse"][0] == 0 else 2) if d["storageheatmethod"][0] in (0, 1) else 0
+    instance = special if rng.random() < 0.5 else 0
+    rc, blks, state, warn = run_host(host, d, met, groups, instance=instance)
     if rc != code:
         return None if (rc == 1003 and code == 0) else ("fatal code", over, rc, code)
     if code:
@@ -504,6 +505,12 @@ def fuzz_trial(host, rng, snaps, met_all):
         check_blocks(blks, ref, over)
         check_state(state, cell, where=over)
         check_warnings(warn, ref, over)
+        if rng.random() < 0.3:                                   # the same case under policy P0, flux only
+            acc = np.zeros(7)
+            rc, _b, state0, _w = run_host(host, d, met, (), instance=instance, kind=2, flux_only=True, acc=acc)
+            seq = np.cumsum(ref["SUEWS"][:, 5:], axis=0)[-1][PARITY_COLS]
+            assert rc == 0 and np.all(same_bits(acc, seq)), ("P0 sums", over, acc, seq)
+            check_state(state0, cell, where=("P0", over))
     except AssertionError as e:
         return str(e)[:600]
     return None
