@@ -488,18 +488,62 @@ def fuzz_trial(host, rng, snaps, met_all):
     if rng.random() < 0.3:
         met[:, 9] = np.maximum(0.05, met[:, 9] * float(rng.uniform(0.1, 3)))
     groups = ("SUEWS", "snow") if d["snowuse"][0] == 1 else ("SUEWS",)
+    # one case in three keeps a storage record: AnOHM, ESTM (random variant) or BLUEWS on top of the storage scheme drawn
+    record, ts, ini, dh = False, None, None, d
+    kind = rng.random()
+    if kind < 0.1:
+        from suews_b200 import synth
+        d.update({k: list(v) for k, v in synth.ANOHM_EXAMPLE.items()})
+        d["storageheatmethod"], record = [3], True
+    elif kind < 0.2:
+        from suews_b200 import estm
+        d["storageheatmethod"] = [int(rng.choice([4, 14]))]
+        ep = fx.estm_example(d["surfacearea"][0], **ESTM_VARIANTS[rng.integers(5)])
+        d.update({k.lower(): v for k, v in ep.items()})
+        ts, record = fx.estm_ts_forcing(met), True
+        dh = dict(d)
+        dh.update({k.lower(): list(np.atleast_1d(v)) for k, v in estm.initial_state(ep, d["sfr"], d["emis"], ts[0]).items()})
+        if d["storageheatmethod"][0] == 4:
+            groups = groups + ("ESTM",)
+    elif kind < 0.33:
+        params, ini = fx.cbl_inputs()
+        d.update(params)
+        d.update(initialdata_use=[int(rng.choice([1, 2]))], entrainmenttype=[int(rng.integers(1, 5))], isubs=[int(rng.integers(0, 2))],
+                 qh_choice=[int(rng.integers(1, 3))])
+        ini, record = np.ascontiguousarray(ini), True
+    L = ol.lib()
+    bl = np.full((met.shape[0], 22), -999.0, order="F")
     try:
+        if ini is not None:
+            L.so_set_cbl_initial.argtypes = [dp, C.c_int]
+            L.so_set_bl_block.argtypes = [dp]
+            L.so_set_cbl_initial(ini.ctypes.data_as(dp), ini.shape[0])
+            L.so_set_bl_block(bl.ctypes.data_as(dp))
         cell = ol.Cell(d)
-        ref = cell.run(met, want=groups)
+        if ts is not None:
+            cell.estm_start(ts[0])
+        ref = cell.run(met, want=groups, ts5=ts)
         code = 0
     except RuntimeError as e:
         code = int(str(e).split("error")[1].split(":")[0])
+    finally:
+        if ini is not None:
+            L.so_set_bl_block(None)
+            L.so_set_cbl_initial(None, 0)
+    if ini is not None and code == 0:
+        ref["BL"] = bl
+        groups = groups + ("BL",)
     # the generic instance or the specialisation this class would be launched with
-    special = (1 if d["snowuse"][0] == 0 else 2) if d["storageheatmethod"][0] in (0, 1) else 0
+    special = (1 if d["snowuse"][0] == 0 else 2) if (d["storageheatmethod"][0] in (0, 1) and not record) else 0
     instance = special if rng.random() < 0.5 else 0
-    rc, blks, state, warn = run_host(host, d, met, groups, instance=instance)
+    rc, blks, state, warn = run_host(host, dh, met, groups, instance=instance, record=record, ts5=ts, cbl_ini=ini)
+    d = dh
     if rc != code:
-        return None if (rc == 1003 and code == 0) else ("fatal code", over, rc, code)
+        # the library's own refusals where the reference runs on with an unset value: an unknown storage scheme (QS unset),
+        # BLUEWS' diagnosed start without the psih AerodynamicResistanceMethod 2 leaves behind
+        own = (rc == 1003 and code == 0) or (rc == 1007 and code == 0 and ini is not None and d["initialdata_use"][0] == 1
+                                             and d["aerodynamicresistancemethod"][0] != 2)
+        return None if own else ("fatal code", over, rc, code)
     if code:
         return None
     try:
@@ -508,7 +552,8 @@ def fuzz_trial(host, rng, snaps, met_all):
         check_warnings(warn, ref, over)
         if rng.random() < 0.3:                                   # the same case under policy P0, flux only
             acc = np.zeros(7)
-            rc, _b, state0, _w = run_host(host, d, met, (), instance=instance, kind=2, flux_only=True, acc=acc)
+            rc, _b, state0, _w = run_host(host, d, met, (), instance=instance, kind=2, flux_only=True, acc=acc, record=record,
+                                          ts5=ts, cbl_ini=ini)
             seq = np.cumsum(ref["SUEWS"][:, 5:], axis=0)[-1][PARITY_COLS]
             assert rc == 0 and np.all(same_bits(acc, seq)), ("P0 sums", over, acc, seq)
             check_state(state0, cell, where=("P0", over))
@@ -534,10 +579,11 @@ def year_snapshots(host):
 
 
 def test_random_scheme_cell_and_weather_combinations(host):
-    """150 random cases (tools/fuzz_step_host.py runs the same generator for as long as one likes: 4 000 cases without a
+    """150 random cases (tools/fuzz_step_host.py runs the same generator for as long as one likes: 10 000 cases without a
     difference when this was written): states from every month of 2004, scheme switches combined at random -- 10 radiation,
     7 stability, 10 emission methods, snow on / off, ... --, cells with absent surfaces, other heights and sites, warmer /
-    colder / wetter / windier forcing.  Every output value, the end state, the warnings and the fatal codes are the oracle's."""
+    colder / wetter / windier forcing, one in three with AnOHM, ESTM or BLUEWS, the generic or the specialised instance, some again
+    under policy P0.  Every output value, the end state, the warnings and the fatal codes are the oracle's."""
     snaps, met_all = year_snapshots(host)
     rng = np.random.default_rng(20261020)
     bad = [r for r in (fuzz_trial(host, rng, snaps, met_all) for _ in range(150)) if r]
