@@ -588,3 +588,33 @@ def test_random_scheme_cell_and_weather_combinations(host):
     rng = np.random.default_rng(20261020)
     bad = [r for r in (fuzz_trial(host, rng, snaps, met_all) for _ in range(150)) if r]
     assert not bad, bad[:3]
+
+
+def test_estm_from_the_run_directory_with_the_reference_s_own_forcing(host, tmp_path):
+    """StorageHeatMethod 4 end to end on the host: the golden run directory with ESTM switched on (table join, ESTM class
+    weighting, ESTMinput.nml), the reference's own surface-temperature file of 2005 (its 5-min disaggregation as the reference
+    wrote it), the 2005 checkpoint as InitialConditions -- five days through the host build of the step against the oracle."""
+    import shutil
+    from suews_b200 import tables
+    src = os.path.join(fx.GOLDEN, "baserun_2020b")
+    run = tmp_path / "run"
+    shutil.copytree(src, run)
+    rcp = run / "RunControl.nml"
+    rcp.write_text(rcp.read_text().replace("StorageHeatMethod=1", "StorageHeatMethod=4"))
+    ts5 = np.loadtxt(os.path.join(fx.GOLDEN, "ref_estm_ts_2005_5min.txt"), skiprows=1)[:1440]
+    met = fx.forcing(2005)
+    assert ts5.shape == (1440, 13) and np.array_equal(ts5[:, :4], met[:, :4])
+    ic = os.path.join(fx.GOLDEN, "ref_InitialConditions_2005.nml")
+    a0, _aux, _rc = tables.run_arguments(str(run), 1, 2005, initial_conditions=ic)
+    a1, _aux, _rc = tables.run_arguments(str(run), 1, 2005, initial_conditions=ic, estm_ts_row0=ts5[0])
+    assert a0["storageheatmethod"] == [4] and "tw_4" in a1 and "tw_4" not in a0
+    cell = ol.Cell(a0)
+    cell.estm_start(ts5[0])
+    ref = cell.run(met, want=("SUEWS", "ESTM"), ts5=ts5)
+    rc, blks, state, _w = run_host(host, a1, met, ("SUEWS", "ESTM"), record=True, ts5=ts5)
+    assert rc == 0
+    check_blocks(blks, ref, "ESTM from the run directory")
+    names = ("Tievolve", "Tground", "Twall", "Troof", "Tibld", "Tw_4", "T0_ibld", "TN_wall", "TN_roof", "Tair2", "state_id", "soilstore_id")
+    assert check_state(state, cell, names=names) == len(names)
+    qs = blks["SUEWS"][:, 5 + 7]
+    assert np.isfinite(qs).all() and qs.max() - qs.min() > 10.0          # a storage heat flux with a diurnal course
