@@ -618,3 +618,24 @@ def test_estm_from_the_run_directory_with_the_reference_s_own_forcing(host, tmp_
     assert check_state(state, cell, names=names) == len(names)
     qs = blks["SUEWS"][:, 5 + 7]
     assert np.isfinite(qs).all() and qs.max() - qs.min() > 10.0          # a storage heat flux with a diurnal course
+
+
+def test_anohm_from_the_run_directory(host, tmp_path):
+    """StorageHeatMethod 3 with the AnOHM columns of the run directory's own surface tables (SUEWS_NonVeg / Veg / Water)."""
+    import shutil
+    from suews_b200 import tables
+    run = tmp_path / "run"
+    shutil.copytree(os.path.join(fx.GOLDEN, "baserun_2020b"), run)
+    rcp = run / "RunControl.nml"
+    rcp.write_text(rcp.read_text().replace("StorageHeatMethod=1", "StorageHeatMethod=3"))
+    a, _aux, _rc = tables.run_arguments(str(run), 1, 2004)
+    assert a["storageheatmethod"] == [3] and min(a["cpanohm"]) > 0 and min(a["kkanohm"]) > 0 and min(a["chanohm"]) > 0
+    met = fx.forcing(2004)[288 * 170:288 * 172 + 30]                # midsummer: long days, a fit on every surface
+    a["dt_since_start"] = [288 * 170 * 300]
+    cell = ol.Cell(a)
+    ref = cell.run(met, want=("SUEWS", "DailyState"))
+    rc, blks, state, _w = run_host(host, a, met, ("SUEWS", "DailyState"), record=True)
+    assert rc == 0
+    check_blocks(blks, ref, "AnOHM from the run directory")
+    assert check_state(state, cell, names=("anohm_coeff_grid_day", "anohm_id_save", "qn1_av", "dqndt")) == 4
+    assert (state["anohm_coeff_grid_day"] != -999.0).all()
