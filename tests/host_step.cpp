@@ -17,7 +17,14 @@
 #define __noinline__
 #define __constant__
 #define SU_INLINE_ALL 1   // no out-of-line math wrappers: exp / log / pow / sin ... are libm's
+#ifdef SO_OPCOUNT
+// -include oracle/so_count.h (tools/host_step_opcount.py): `double` is the oracle's counting class here, so the build counts the
+// FP64 operations the kernel's algorithm performs -- same weights, same reader as the oracle's own count
+extern "C" { unsigned long long so_opcount_buf[32]; unsigned long long *so_opcount_cur = so_opcount_buf; int so_opcount_on = 0; }
+static inline double __fma_rn(double a, double b, double c) { return a * b + c; }
+#else
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+#endif
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
@@ -35,6 +42,17 @@ static inline double su_root4_cr(double x) { return pow(x, 0.25); }
 static inline double su_exp_fast(double x) { return exp(x); }
 static inline double su_rcp_fast(double d) { return 1.0 / d; }
 static inline double su_pow_general(double x, double y) { return pow(x, y); }
+#ifdef SO_OPCOUNT
+// (int)field on a one-value field of the counting class would need two user conversions: give that one case its own
+// specialisation (same layout, same operators, plus the integer conversion)
+template <typename T, int N> struct SuewsFld;
+template <> struct SuewsFld<double, 1> {
+   double v[1];
+   operator double() const { return v[0]; }
+   explicit operator int() const { return (int)v[0]; }
+   SuewsFld &operator=(double x) { v[0] = x; return *this; }
+};
+#endif
 #include "../suews_b200/csrc/dev_step.cuh"
 
 // clock decode of one forcing row: the same statements as decode_clock / pack_step of suews_b200.cu (SUEWS_cal_dectime
@@ -90,7 +108,14 @@ static int run_cell(SuewsClassParams &P, SuewsCellParams &C, SuewsCellState &S, 
       SuewsStepRec R;
       host_pack_step(R, met, n, (size_t)gs);
       SuewsEphem E;
+#ifdef SO_OPCOUNT
+      const int counting = so_opcount_on;   // the time-only half of the sun position is the per-time-zone pre-pass, not the cell's work
+      so_opcount_on = 0;
+#endif
       spa_time_part((double)R.iy, R.dectime - (double)((int)P.tstep / 2), C.timezone, E);
+#ifdef SO_OPCOUNT
+      so_opcount_on = counting;
+#endif
       double l_dt[5], l_su[SUEWS_NCOL_SUEWS], l_sn[SUEWS_NCOL_SNOW], l_rs[SUEWS_NCOL_RSL], l_da[SUEWS_NCOL_DAILY], l_so[SUEWS_NCOL_SOLWEIG],
          l_es[SUEWS_NCOL_ESTM], l_bl[SUEWS_NCOL_BL];
       SuLines L = {l_dt, l_su, l_sn, l_rs, l_da, l_so, l_es, (ES && blk[6]) ? l_bl : nullptr};
