@@ -454,15 +454,25 @@ FUZZ_CHOICES = dict(netradiationmethod=[0, 1, 2, 3, 11, 12, 13, 100, 200, 300], 
                     aerodynamicresistancemethod=[1, 2, 2, 3])
 
 
+# class parameters the generator leaves alone: the timestep and the tables whose rows must keep their sums
+FUZZ_FIXED = {"tstep", "ohm_coef", "waterdist", "ahprof_24hr", "humactivity_24hr", "popprof_24hr", "traffprof_24hr", "wuprofa_24hr",
+              "wuprofm_24hr", "snowprof_24hr"}
+
+
 def fuzz_trial(host, rng, snaps, met_all):
-    """One random case: a state of the year, a random combination of scheme switches, a random cell (fractions with absent
-    surfaces, heights, site) and shifted forcing; -> None, or a description of what differs from the oracle."""
+    """One random case: a state of the year, a random combination of scheme switches, scaled class parameters, a random cell
+    (fractions with absent surfaces, heights, site) and shifted forcing; -> None, or a description of what differs from the oracle."""
     step, d0 = snaps[rng.integers(len(snaps))]
     d = dict(d0)
     for k in INTERNAL:
         d.pop(k, None)                                         # the library's memos restart, like the oracle's SAVE'd ones
     over = {k: int(rng.choice(v)) for k, v in FUZZ_CHOICES.items() if rng.random() < 0.5}
     _with(d, over)
+    if rng.random() < 0.5:                                     # six class parameters (albedos, capacities, conductances, ...) scaled
+        names = [nm.lower() for nm, kind, _n in all_fields() if kind == 1 and nm.lower() in d and nm.lower() not in FUZZ_FIXED]
+        for nm in rng.choice(names, size=6, replace=False):
+            v = np.asarray(d[nm], dtype=np.float64)
+            d[nm] = list(v * rng.uniform(0.6, 1.4, size=v.shape))
     if rng.random() < 0.8:
         u = rng.random(7) * (rng.random(7) < 0.8)
         u[1] = max(u[1], 0.02)
