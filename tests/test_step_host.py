@@ -459,6 +459,9 @@ FUZZ_FIXED = {"tstep", "ohm_coef", "waterdist", "ahprof_24hr", "humactivity_24hr
               "wuprofm_24hr", "snowprof_24hr"}
 
 
+EXTRA_GROUPS = ("RSL", "DailyState", "SOLWEIG")
+
+
 def fuzz_trial(host, rng, snaps, met_all):
     """One random case: a state of the year, a random combination of scheme switches, scaled class parameters, a random cell
     (fractions with absent surfaces, heights, site) and shifted forcing; -> None, or a description of what differs from the oracle."""
@@ -497,7 +500,7 @@ def fuzz_trial(host, rng, snaps, met_all):
         met[:, 13] *= float(rng.uniform(0, 5))
     if rng.random() < 0.3:
         met[:, 9] = np.maximum(0.05, met[:, 9] * float(rng.uniform(0.1, 3)))
-    groups = ("SUEWS", "snow") if d["snowuse"][0] == 1 else ("SUEWS",)
+    groups = (("SUEWS", "snow") if d["snowuse"][0] == 1 else ("SUEWS",)) + EXTRA_GROUPS
     # one case in three keeps a storage record: AnOHM, ESTM (random variant) or BLUEWS on top of the storage scheme drawn
     record, ts, ini, dh = False, None, None, d
     kind = rng.random()
