@@ -351,3 +351,42 @@ def test_wet_bulb_search_root_bound_on_the_host(tmp_path):
     assert L.latvap_host_selftest(3_000_000, 2026, trips) == 0
     root, screen, exact = trips[0], trips[1], trips[2]
     assert root > 3 * (screen + exact), (root, screen, exact)
+
+
+def test_device_disaggregation_source_on_the_host(tmp_path):
+    """suews_b200/csrc/forcing_kernels.cuh compiled for the host (tests/host_forcing.cpp): the kernel's rows are bit for bit
+    those of forcing.py -- whose output reproduces the reference's own disaggregated files -- for the met forcing of 2004 and
+    2005 with DisaggMethod 1 / 2 / 3, raw file units, and the ESTM surface temperatures (methods 1 / 2) against the 5-min file
+    the reference wrote."""
+    import ctypes as C
+    from suews_b200 import forcing
+    so = str(tmp_path / "host_forcing.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so,
+                           os.path.join(ROOT, "tests", "host_forcing.cpp")])
+    H = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    H.host_disagg.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+
+    def dev(slow, method, raw=0, smd=0, res=3600, tstep=300):
+        s = np.asfortranarray(slow, dtype=np.float64)
+        out = np.zeros((s.shape[0] * (res // tstep), s.shape[1]), order="F")
+        H.host_disagg(s.ctypes.data_as(dp), s.shape[0], s.shape[1], res, tstep, method, raw, smd, out.ctypes.data_as(dp))
+        return out
+    G = os.path.join(ROOT, "tests", "golden")
+    for year in (2004, 2005):
+        hourly = forcing.read_met(os.path.join(G, "forcing_%d_60min.txt" % year))
+        for method in (1, 2, 3):
+            ref = forcing.disaggregate_met(hourly, tstep=300, resolution_in=3600, disagg_method=method)
+            assert np.array_equal(dev(hourly, method), ref), (year, method)
+        for tstep in (600, 1800):
+            assert np.array_equal(dev(hourly, 1, tstep=tstep), forcing.disaggregate_met(hourly, tstep=tstep, resolution_in=3600))
+    raw = np.loadtxt(os.path.join(G, "forcing_2005_60min.txt"), skiprows=1)[:, :24]
+    assert np.array_equal(dev(raw, 1, raw=1), forcing.disaggregate_met(forcing.read_met(os.path.join(G, "forcing_2005_60min.txt")), disagg_method=1))
+    ts = np.loadtxt(os.path.join(G, "estm_ts_2005_60min.txt"), skiprows=1)
+    gold = np.loadtxt(os.path.join(G, "ref_estm_ts_2005_5min.txt"), skiprows=1)
+    for method in (1, 2):
+        out = dev(ts, method)
+        assert np.array_equal(out, forcing.disaggregate_estm(ts, disagg_method=method)), method
+    out = dev(ts, 1)
+    n = min(out.shape[0], gold.shape[0])
+    assert np.array_equal(out[:n, :4], gold[:n, :4]) and np.all(np.abs(out[:n, 4:] - gold[:n, 4:]) <= 5.1e-5)
